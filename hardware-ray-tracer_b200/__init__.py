@@ -1,0 +1,34 @@
+"""B200-native hot path of the Bloon RT Engine: Python view of the C ABI (include/brt.h).
+
+The product is lib/libbrt.so (hand-written sm_100a CUDA behind a C ABI). This package only loads
+it with ctypes; there is no CPU fallback — `load()` raises when the library is missing and
+`brt_create` fails when no CUDA device is usable.
+"""
+import ctypes
+import os
+
+from . import _binding as binding
+from ._binding import *  # noqa: F401,F403
+from . import scenes  # noqa: F401
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libbrt.so")
+LIB_COUNTERS_PATH = LIB_PATH  # counters are a runtime flag (BRT_CFG_COUNTERS), same library
+
+_lib = None
+
+
+def load():
+    """dlopen lib/libbrt.so (built by __graft_entry__.build() / csrc/Makefile). Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    return _lib
+
+
+def Context(device=0, tile_rank=0, tile_world=1, flags=0):
+    """A `brt_context` on CUDA device `device`."""
+    return binding.SceneApi(load(), "brt_", device, tile_rank, tile_world, flags)

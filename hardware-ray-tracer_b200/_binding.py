@@ -1,0 +1,288 @@
+"""ctypes view of include/brt.h.
+
+The same signatures are exported by libbrt.so (prefix ``brt_``, the CUDA product) and — for the
+parity tests only — by oracle/liboracle.so (prefix ``orc_``); `SceneApi` is parameterised by the
+prefix so one piece of test code drives both. Nothing in this module touches oracle/.
+"""
+import ctypes as C
+
+import numpy as np
+
+u32, i32, u64, f32 = C.c_uint32, C.c_int32, C.c_uint64, C.c_float
+
+
+class Vertex(C.Structure):  # RT/Scene.h:28-31
+    _fields_ = [("pos", f32 * 3), ("normal", f32 * 3), ("uv", f32 * 2)]
+
+
+class Material(C.Structure):  # RT/Scene.h:50-62
+    _fields_ = [("color", f32 * 3)] + [(n, f32) for n in (
+        "subsurface", "metallic", "roughness", "specular", "specularTint", "anisotropic", "sheen",
+        "sheenTint", "clearCoat", "clearCoatGloss")]
+
+
+class Light(C.Structure):  # RT/Scene.h:70-75
+    _fields_ = [("pos", f32 * 3), ("color", f32 * 3), ("intensity", f32), ("type", C.c_uint8), ("pad_", C.c_uint8 * 3)]
+
+
+class Uniform(C.Structure):  # RT/RTPipeline.h:24-30
+    _fields_ = [("viewInverse", f32 * 16), ("projInverse", f32 * 16), ("frame", u32), ("depthMax", u32), ("lightThreshold", f32)]
+
+
+class Sky(C.Structure):  # RT/Scene.h:90-104
+    _fields_ = [(n, f32 * 3) for n in ("skyColor", "horizonColor", "groundColor", "sunDirection", "upDirection")] + [
+        (n, f32) for n in ("brightness", "horizonSize", "angularSize", "glowIntensity", "glowSharpness", "glowSize", "lightRadiance")]
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", u32), ("device", i32), ("tile_rank", u32), ("tile_world", u32), ("flags", u32)]
+
+
+class RenderOpts(C.Structure):
+    _fields_ = [(n, u32) for n in ("width", "height", "spp", "flags", "crop_x0", "crop_y0", "crop_w", "crop_h")]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, u64) for n in (
+        "rays_closest", "rays_occlusion", "nodes_visited_closest", "prims_tested_closest", "spheres_tested_closest",
+        "nodes_visited_occlusion", "prims_tested_occlusion", "spheres_tested_occlusion")] + [
+        (n, f32) for n in ("ms_raygen", "ms_trace_closest", "ms_shade", "ms_trace_occlusion", "ms_accumulate", "ms_resolve", "ms_total")] + [
+        (n, u32) for n in ("launches_trace_closest", "launches_trace_occlusion", "launches_total")] + [
+        (n, f32) for n in ("ms_blas_build", "ms_tlas_build", "ms_cull")] + [("blas_built", u32)] + [
+        (n, u64) for n in ("total_triangles", "bvh_nodes", "bvh_bytes")] + [
+        ("sah_cost", f32), ("sah_cost_lbvh", f32), ("instances_visible", u32), ("instances_total", u32)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+assert C.sizeof(Vertex) == 32 and C.sizeof(Material) == 52 and C.sizeof(Light) == 32
+assert C.sizeof(Uniform) == 140 and C.sizeof(Sky) == 88
+
+CFG_COUNTERS = 1
+CFG_NO_TREELET = 2
+BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY = 1, 2, 4, 8, 16
+AOV_PRIM_ID, AOV_INST_ID, AOV_HIT_T = 0, 1, 2
+AOV_MISS = 0xFFFFFFFF
+
+# every symbol include/brt.h declares (tests/test_abi.py checks the .so exports each of them)
+BRT_SYMBOLS = [
+    "brt_create", "brt_destroy", "brt_last_error", "brt_set_stream", "brt_mesh_create", "brt_mesh_update_vertices",
+    "brt_sphere_create", "brt_material_create", "brt_material_set_transmission", "brt_light_create", "brt_sky_set",
+    "brt_instance_create", "brt_instance_set_transform", "brt_instance_set_material", "brt_instance_destroy",
+    "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
+    "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
+    "brt_camera_uniform",
+]
+
+
+class BrtError(RuntimeError):
+    """Non-zero status from the C ABI (the reference throws std::runtime_error, Graphics/Definitions.h:5)."""
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+class SceneApi:
+    """One context of libbrt.so (prefix ``brt_``) or of the oracle (prefix ``orc_``)."""
+
+    def __init__(self, lib, prefix, device=0, tile_rank=0, tile_world=1, flags=0):
+        self.lib, self.prefix = lib, prefix
+        self._declare()
+        cfg = Config(C.sizeof(Config), device, tile_rank, tile_world, flags)
+        self.ctx = C.c_void_p()
+        rc = self._f("create")(C.byref(cfg), C.byref(self.ctx))
+        if rc != 0:
+            msg = self._f("last_error")(None)
+            raise BrtError(f"{prefix}create failed (status {rc}): {msg.decode() if msg else ''}")
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _declare(self):
+        vp, P = C.c_void_p, C.POINTER
+        sig = {
+            "create": (C.c_int, [P(Config), P(vp)]),
+            "destroy": (None, [vp]),
+            "last_error": (C.c_char_p, [vp]),
+            "mesh_create": (C.c_int, [vp, P(Vertex), u32, P(u32), u32, P(u32)]),
+            "mesh_update_vertices": (C.c_int, [vp, u32, P(Vertex), u32]),
+            "sphere_create": (C.c_int, [vp, P(f32), f32, P(u32)]),
+            "material_create": (C.c_int, [vp, P(Material), P(u32)]),
+            "material_set_transmission": (C.c_int, [vp, u32, f32, f32]),
+            "light_create": (C.c_int, [vp, P(Light), P(u32)]),
+            "sky_set": (C.c_int, [vp, P(Sky)]),
+            "instance_create": (C.c_int, [vp, u32, u32, P(f32), P(u32)]),
+            "instance_set_transform": (C.c_int, [vp, u32, P(f32)]),
+            "instance_set_material": (C.c_int, [vp, u32, u32]),
+            "instance_destroy": (C.c_int, [vp, u32]),
+            "scene_build": (C.c_int, [vp]),
+            "smart_cull": (C.c_int, [vp, P(Uniform), u32, u32, f32, f32, P(u32)]),
+            "get_visibility": (C.c_int, [vp, P(C.c_uint8), u32]),
+            "render_frame": (C.c_int, [vp, P(Uniform), P(RenderOpts), vp]),
+            "get_aov": (C.c_int, [vp, C.c_int, vp]),
+            "get_stats": (C.c_int, [vp, P(Stats)]),
+            "trace_rays": (C.c_int, [vp, P(f32), u32, C.c_int, P(u32)]),
+            "camera_uniform": (None, [P(f32), P(f32), f32, f32, f32, f32, u32, u32, P(Uniform)]),
+        }
+        if self.prefix == "brt_":
+            sig.update({
+                "set_stream": (C.c_int, [vp, vp]),
+                "render_frame_tiles": (C.c_int, [vp, P(Uniform), P(RenderOpts), vp]),
+                "tile_buffer_bytes": (C.c_size_t, [u32, u32, u32]),
+                "untile": (C.c_int, [vp, vp, u32, u32, u32, vp]),
+                "device_image": (vp, [vp]),
+            })
+        else:
+            sig.update({"set_threads": (C.c_int, [vp, u32]), "get_threads": (u32, [vp])})
+        for name, (res, args) in sig.items():
+            fn = self._f(name)
+            fn.restype, fn.argtypes = res, args
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._f("last_error")(self.ctx)
+            raise BrtError(f"status {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.ctx:
+            self._f("destroy")(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene -----------------------------------------------------------------------------
+    def mesh_create(self, vertices, indices):
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 8)
+        i = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        out = u32()
+        self._ck(self._f("mesh_create")(self.ctx, _ptr(v, Vertex), v.shape[0], _ptr(i, u32), i.shape[0], C.byref(out)))
+        return out.value
+
+    def mesh_update_vertices(self, mesh_id, vertices):
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 8)
+        self._ck(self._f("mesh_update_vertices")(self.ctx, mesh_id, _ptr(v, Vertex), v.shape[0]))
+
+    def sphere_create(self, center, radius):
+        c = (f32 * 3)(*center)
+        out = u32()
+        self._ck(self._f("sphere_create")(self.ctx, c, radius, C.byref(out)))
+        return out.value
+
+    def material_create(self, color, metallic=0.0, roughness=1.0, specular=0.5, **kw):
+        """Scene::createMaterial defaults (RT/Scene.cpp:80-86, RT/Scene.h:55): specular 0.5, rest 0."""
+        m = Material()
+        m.color[:] = color
+        m.metallic, m.roughness, m.specular = metallic, roughness, specular
+        for k, val in kw.items():
+            setattr(m, k, val)
+        out = u32()
+        self._ck(self._f("material_create")(self.ctx, C.byref(m), C.byref(out)))
+        return out.value
+
+    def material_set_transmission(self, mat_id, transmission, ior):
+        self._ck(self._f("material_set_transmission")(self.ctx, mat_id, transmission, ior))
+
+    def light_create(self, pos, color, intensity, type=0):
+        l = Light()
+        l.pos[:] = pos
+        l.color[:] = color
+        l.intensity, l.type = intensity, type
+        out = u32()
+        self._ck(self._f("light_create")(self.ctx, C.byref(l), C.byref(out)))
+        return out.value
+
+    def sky_set(self, sky):
+        self._ck(self._f("sky_set")(self.ctx, C.byref(sky)))
+
+    def instance_create(self, mesh_id, material_id, xform3x4):
+        x = np.ascontiguousarray(xform3x4, dtype=np.float32).reshape(12)
+        out = u32()
+        self._ck(self._f("instance_create")(self.ctx, mesh_id, material_id, _ptr(x, f32), C.byref(out)))
+        return out.value
+
+    def instance_set_transform(self, inst_id, xform3x4):
+        x = np.ascontiguousarray(xform3x4, dtype=np.float32).reshape(12)
+        self._ck(self._f("instance_set_transform")(self.ctx, inst_id, _ptr(x, f32)))
+
+    def instance_set_material(self, inst_id, mat_id):
+        self._ck(self._f("instance_set_material")(self.ctx, inst_id, mat_id))
+
+    def instance_destroy(self, inst_id):
+        self._ck(self._f("instance_destroy")(self.ctx, inst_id))
+
+    def scene_build(self):
+        self._ck(self._f("scene_build")(self.ctx))
+
+    def smart_cull(self, uniform, width, height, threshold_px2, hysteresis):
+        out = u32()
+        self._ck(self._f("smart_cull")(self.ctx, C.byref(uniform), width, height, threshold_px2, hysteresis, C.byref(out)))
+        return out.value
+
+    def get_visibility(self, n):
+        out = np.zeros(n, dtype=np.uint8)
+        self._ck(self._f("get_visibility")(self.ctx, _ptr(out, C.c_uint8), n))
+        return out
+
+    # ---- render ----------------------------------------------------------------------------
+    def camera_uniform(self, pos, rot, fovy, aspect, znear=0.001, zfar=100000.0, frame=0, depth_max=2):
+        u = Uniform()
+        self._f("camera_uniform")((f32 * 3)(*pos), (f32 * 3)(*rot), fovy, aspect, znear, zfar, frame, depth_max, C.byref(u))
+        return u
+
+    @staticmethod
+    def opts(width, height, spp=1, flags=0, crop=None):
+        o = RenderOpts(width, height, spp, flags, 0, 0, 0, 0)
+        if crop:
+            o.crop_x0, o.crop_y0, o.crop_w, o.crop_h = crop
+        return o
+
+    def render_frame(self, uniform, opts, out=None, want_image=True):
+        """Returns the RGBA32F image as an (h, w, 4) array (or None with want_image=False)."""
+        ptr = None
+        if want_image:
+            if out is None:
+                out = np.zeros((opts.height, opts.width, 4), dtype=np.float32)
+            ptr = out.ctypes.data_as(C.c_void_p)
+        self._ck(self._f("render_frame")(self.ctx, C.byref(uniform), C.byref(opts), ptr))
+        return out
+
+    def render_frame_ptr(self, uniform, opts, host_ptr):
+        self._ck(self._f("render_frame")(self.ctx, C.byref(uniform), C.byref(opts), C.c_void_p(host_ptr)))
+
+    def get_aov(self, kind, width, height):
+        out = np.zeros((height, width), dtype=np.float32 if kind == AOV_HIT_T else np.uint32)
+        self._ck(self._f("get_aov")(self.ctx, kind, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_stats(self):
+        s = Stats()
+        self._ck(self._f("get_stats")(self.ctx, C.byref(s)))
+        return s
+
+    def trace_rays(self, rays, closest=True):
+        r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        out = np.zeros((r.shape[0], 4), dtype=np.uint32)
+        self._ck(self._f("trace_rays")(self.ctx, _ptr(r, f32), r.shape[0], 1 if closest else 0, _ptr(out, u32)))
+        return out
+
+    # ---- brt_ only ---------------------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        self._ck(self._f("set_stream")(self.ctx, C.c_void_p(stream_ptr)))
+
+    def render_frame_tiles(self, uniform, opts, d_tiles_ptr):
+        self._ck(self._f("render_frame_tiles")(self.ctx, C.byref(uniform), C.byref(opts), C.c_void_p(d_tiles_ptr)))
+
+    def tile_buffer_bytes(self, width, height, world):
+        return self._f("tile_buffer_bytes")(width, height, world)
+
+    def untile(self, d_all_ptr, width, height, world, d_rgba_ptr):
+        self._ck(self._f("untile")(self.ctx, C.c_void_p(d_all_ptr), width, height, world, C.c_void_p(d_rgba_ptr)))
+
+    def device_image(self):
+        return self._f("device_image")(self.ctx)

@@ -1,0 +1,232 @@
+/*
+ * brt.h — C ABI of the B200-native Bloon RT hot path (libbrt.so).
+ *
+ * This is the drop-in boundary for the reference's ray-gen / closest-hit / miss shader pipeline:
+ * everything the reference does through `RayTracing::Scene`, `RayTracing::Pipeline` and the four
+ * descriptor bindings (TLAS, outImage, Uniform, SceneBufferInfo) is reachable through the plain-C
+ * entry points below. Citations use the shorthand
+ *   RT/ = /root/reference/Hardware Ray Tracer/Graphics/RayTracing/
+ *   SH/ = /root/reference/Hardware Ray Tracer/shaders/
+ *
+ * Conventions
+ *   - every function returns an int status (BRT_OK == 0); brt_last_error(ctx) gives the message.
+ *     The reference throws std::runtime_error (Graphics/Definitions.h:5); the C++ facade in
+ *     include/bloon/ re-raises a non-zero status as std::runtime_error.
+ *   - handles are opaque; input arrays are copied during the call; one context is not thread-safe.
+ *   - the library has NO CPU path: brt_create fails when no CUDA device is usable.
+ *   - POD layouts are byte-identical to the reference's host structs / shader structs.
+ */
+#ifndef BRT_H_
+#define BRT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRT_OK 0
+#define BRT_ERR_INVALID 1  /* bad argument / bad id */
+#define BRT_ERR_CUDA 2     /* CUDA runtime error (message in brt_last_error) */
+#define BRT_ERR_STATE 3    /* call order violated (e.g. render before build) */
+#define BRT_ERR_LIMIT 4    /* internal capacity exceeded (e.g. BVH deeper than the traversal stack) */
+
+/* ---- POD layouts shared with the reference ------------------------------------------------- */
+
+/* RT/Scene.h:28-31, read by SH/objects.slang:49-51 at offsets 0/12/24, stride 32 */
+typedef struct brt_vertex {
+  float pos[3];
+  float normal[3];
+  float uv[2];
+} brt_vertex;
+
+/* RT/Scene.h:50-62 == SH/material.slang:3-15, 13 floats, stride 52 */
+typedef struct brt_material {
+  float color[3];
+  float subsurface;
+  float metallic;
+  float roughness;
+  float specular;
+  float specularTint;
+  float anisotropic;
+  float sheen;
+  float sheenTint;
+  float clearCoat;
+  float clearCoatGloss;
+} brt_material;
+
+/* RT/Scene.h:64-75, read by SH/light.slang:25-28 at offsets 0/12/24/28, stride 32 */
+enum { BRT_LIGHT_POINT = 0, BRT_LIGHT_SPOT = 1, BRT_LIGHT_DIRECTIONAL = 2 };
+typedef struct brt_light {
+  float pos[3];
+  float color[3];
+  float intensity;
+  uint8_t type;
+  uint8_t pad_[3];
+} brt_light;
+
+/* RT/RTPipeline.h:24-30 == SH/raytracing.slang:9-15 (std140 offsets 0/64/128/132/136), 140 bytes.
+ * viewInverse / projInverse hold glm::inverse(glm::transpose(M)) in glm column-major memory
+ * (RT/RTApp.cpp:44-49); the kernels read them exactly the way the shader's mul(rowVec, M) does. */
+typedef struct brt_uniform {
+  float viewInverse[16];
+  float projInverse[16];
+  uint32_t frame;
+  uint32_t depthMax;
+  float lightThreshold; /* uploaded but never read by the shader (SH/raytracing.slang:79 uses the macro) */
+} brt_uniform;
+
+/* RT/Scene.h:90-104, 88 bytes. The reference uploads it (RT/Scene.cpp:333-355) and never reads it;
+ * here it feeds the optional BRT_RENDER_SKY miss colour (extension). */
+typedef struct brt_sky {
+  float skyColor[3];
+  float horizonColor[3];
+  float groundColor[3];
+  float sunDirection[3];
+  float upDirection[3];
+  float brightness;
+  float horizonSize;
+  float angularSize;
+  float glowIntensity;
+  float glowSharpness;
+  float glowSize;
+  float lightRadiance;
+} brt_sky;
+
+/* ---- library-specific PODs ------------------------------------------------------------------ */
+
+typedef struct brt_config {
+  uint32_t struct_size; /* sizeof(brt_config) */
+  int32_t device;       /* CUDA device ordinal */
+  uint32_t tile_rank;   /* this context renders image tiles with tile_id % tile_world == tile_rank */
+  uint32_t tile_world;  /* 1 = whole image */
+  uint32_t flags;       /* BRT_CFG_* */
+} brt_config;
+
+#define BRT_CFG_COUNTERS 1u /* run the instrumented traversal kernels (node/primitive visit counters) */
+#define BRT_CFG_NO_TREELET 2u /* skip the SAH treelet refinement pass of the LBVH builder */
+
+/* render mode flags. With none of the BOUNCE flags set the behaviour is the reference's live path:
+ * direct light + hard shadows, weight = 0 after the first hit (SH/raytracing.slang:168). */
+#define BRT_RENDER_BOUNCE_REFLECT 1u /* the reference's dormant bounce, SH/raytracing.slang:166-167 */
+#define BRT_RENDER_BOUNCE_REFRACT 2u /* extension: dielectric transmission for materials with transmission > 0 */
+#define BRT_RENDER_BOUNCE_DIFFUSE 4u /* extension: cosine-hemisphere GI bounce (SH/sampler.slang:53-65 + toWorld) */
+#define BRT_RENDER_JITTER 8u         /* use the sub-pixel jitter the shader computes but drops (SH/raytracing.slang:96-98) */
+#define BRT_RENDER_SKY 16u           /* miss returns a sky gradient instead of black (SH/raytracing.slang:173-176) */
+
+typedef struct brt_render_opts {
+  uint32_t width, height;   /* vkCmdTraceRaysKHR(w, h, 1), RT/RTPipeline.cpp:41-43 */
+  uint32_t spp;             /* SAMPLES (SH/constants.slang:23-25); sample s uses frame + s as RNG frame */
+  uint32_t flags;           /* BRT_RENDER_* */
+  uint32_t crop_x0, crop_y0, crop_w, crop_h; /* crop_w == 0: whole image; else only this window is traced */
+} brt_render_opts;
+
+enum { BRT_AOV_PRIM_ID = 0, BRT_AOV_INST_ID = 1, BRT_AOV_HIT_T = 2 };
+#define BRT_AOV_MISS 0xffffffffu
+
+typedef struct brt_stats {
+  /* last frame */
+  uint64_t rays_closest;   /* closest-hit queries (primary + bounce) */
+  uint64_t rays_occlusion; /* occlusion queries (shadow rays) */
+  /* counters, only with BRT_CFG_COUNTERS */
+  uint64_t nodes_visited_closest, prims_tested_closest, spheres_tested_closest;
+  uint64_t nodes_visited_occlusion, prims_tested_occlusion, spheres_tested_occlusion;
+  /* device time of the last frame per kernel class, CUDA events on the library's stream (ms) */
+  float ms_raygen, ms_trace_closest, ms_shade, ms_trace_occlusion, ms_accumulate, ms_resolve, ms_total;
+  uint32_t launches_trace_closest, launches_trace_occlusion, launches_total;
+  /* last brt_scene_build / brt_smart_cull */
+  float ms_blas_build, ms_tlas_build, ms_cull;
+  uint32_t blas_built; /* number of BLAS rebuilt by the last brt_scene_build */
+  /* scene */
+  uint64_t total_triangles; /* sum over instances */
+  uint64_t bvh_nodes;       /* all BLAS + TLAS 8-wide nodes */
+  uint64_t bvh_bytes;       /* nodes + primitive records resident in HBM */
+  float sah_cost;           /* SAH cost of the largest BLAS (binary tree, after refinement) */
+  float sah_cost_lbvh;      /* same before refinement */
+  uint32_t instances_visible, instances_total;
+} brt_stats;
+
+/* ---- context ------------------------------------------------------------------------------- */
+typedef struct brt_context brt_context;
+
+/* Device::Device + Pipeline ctor (vulkan_core/Device.cpp:45-53, RT/RTPipeline.cpp:4-26): picks the
+ * CUDA device, creates the stream and the per-frame buffers. Fails (BRT_ERR_CUDA) without a GPU. */
+int brt_create(const brt_config* cfg, brt_context** out);
+void brt_destroy(brt_context* ctx);
+const char* brt_last_error(const brt_context* ctx);
+/* Launch all work of this context on an externally owned cudaStream_t (e.g. torch's current stream). */
+int brt_set_stream(brt_context* ctx, void* cuda_stream);
+
+/* ---- scene upload (RayTracing::Scene, RT/Scene.h:134-151) -------------------------------- */
+/* Mesh::Mesh (RT/Scene.cpp:419-458): vertices (stride 32) + uint32 indices, 3 per triangle. */
+int brt_mesh_create(brt_context* ctx, const brt_vertex* vertices, uint32_t n_vertices,
+                    const uint32_t* indices, uint32_t n_indices, uint32_t* mesh_id);
+/* Scene::prepareRendering placeholder (RT/Scene.cpp:135-138, "LBVH not implemented!"): replace the
+ * vertex array of a mesh; the next brt_scene_build rebuilds that BLAS with the GPU LBVH builder. */
+int brt_mesh_update_vertices(brt_context* ctx, uint32_t mesh_id, const brt_vertex* vertices, uint32_t n_vertices);
+/* extension (no reference counterpart): an analytic sphere usable as a mesh id in brt_instance_create */
+int brt_sphere_create(brt_context* ctx, const float center[3], float radius, uint32_t* mesh_id);
+/* Scene::createMaterial (RT/Scene.cpp:80-86) */
+int brt_material_create(brt_context* ctx, const brt_material* m, uint32_t* material_id);
+/* extension: dielectric parameters kept in a parallel array so the 52-byte material stays intact */
+int brt_material_set_transmission(brt_context* ctx, uint32_t material_id, float transmission, float ior);
+/* Scene::createLight (RT/Scene.cpp:88-97) */
+int brt_light_create(brt_context* ctx, const brt_light* l, uint32_t* light_id);
+/* Scene::createSky (RT/Scene.cpp:333-355) */
+int brt_sky_set(brt_context* ctx, const brt_sky* sky);
+/* Scene::createInstance (RT/Scene.cpp:76-78) + MeshInstance::calculateTransformation
+ * (RT/MeshInstance.h:82-85): xform is the row-major 3x4 object->world matrix of
+ * VkAccelerationStructureInstanceKHR (RT/Scene.cpp:183-190). */
+int brt_instance_create(brt_context* ctx, uint32_t mesh_id, uint32_t material_id, const float xform3x4[12], uint32_t* instance_id);
+int brt_instance_set_transform(brt_context* ctx, uint32_t instance_id, const float xform3x4[12]);
+int brt_instance_set_material(brt_context* ctx, uint32_t instance_id, uint32_t material_id);
+/* Scene::destroyInstance (RT/Scene.cpp:122-125): swap-remove, the last instance takes this id */
+int brt_instance_destroy(brt_context* ctx, uint32_t instance_id);
+/* Scene::build (RT/Scene.cpp:100-120): BLAS for new/dirty meshes (GPU LBVH + SAH treelets + BVH8),
+ * TLAS over the visible instances, material/light/instance tables. */
+int brt_scene_build(brt_context* ctx);
+/* README.md:15-18 "Smart Culling": screen-space footprint per instance, hysteresis, then TLAS rebuild
+ * over the survivors. threshold_px2 <= 0 makes every instance visible again. */
+int brt_smart_cull(brt_context* ctx, const brt_uniform* u, uint32_t width, uint32_t height,
+                   float threshold_px2, float hysteresis, uint32_t* visible_count);
+/* copy the per-instance visibility flags (1 byte each) of the last brt_smart_cull to the host */
+int brt_get_visibility(brt_context* ctx, uint8_t* out, uint32_t n);
+
+/* ---- render-frame entry (Pipeline::writeToUniformBuffer + traceRays, RT/RTPipeline.cpp:41-47) - */
+/* Traces the frame and, when rgba_host != NULL, copies the linear RGBA32F image (w*h*16 bytes, row
+ * major, alpha = 1) back to host memory — the reference's outImage (SH/raytracing.slang:132).
+ * With tile_world > 1 only the pixels of this rank's tiles are written, the rest stays 0. */
+int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, float* rgba_host);
+/* Same, but leaves the result on the device: d_tiles (device pointer, may be NULL) receives this
+ * rank's tiles packed tile-major (brt_tile_buffer_bytes bytes) for the NCCL gather. */
+int brt_render_frame_tiles(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, void* d_tiles);
+/* bytes of one rank's packed tile buffer (identical on every rank: the tile count is padded) */
+size_t brt_tile_buffer_bytes(uint32_t width, uint32_t height, uint32_t tile_world);
+/* after the gather: d_all = tile_world packed buffers back to back (device) -> row-major RGBA32F
+ * image at d_rgba (device). */
+int brt_untile(brt_context* ctx, const void* d_all, uint32_t width, uint32_t height, uint32_t tile_world, void* d_rgba);
+/* device pointer of the context's own full-frame RGBA32F image of the last frame */
+void* brt_device_image(brt_context* ctx);
+
+/* ---- test / measurement only ---------------------------------------------------------------- */
+/* primary-hit AOVs of sample 0 of the last frame: uint32 prim id, uint32 instance id
+ * (BRT_AOV_MISS on a miss), float hit distance; w*h elements each */
+int brt_get_aov(brt_context* ctx, int kind, void* out_host);
+int brt_get_stats(brt_context* ctx, brt_stats* out);
+/* Trace caller-supplied rays (8 floats each: origin xyz, tmin, direction xyz, tmax) against the
+ * built scene; closest != 0: out = 4 x uint32 per ray {float bits of t, prim, instance, hit?};
+ * closest == 0: out[4*i+3] = occluded ? 1 : 0. Used by the brute-force-vs-BVH equivalence tests. */
+int brt_trace_rays(brt_context* ctx, const float* rays_host, uint32_t n_rays, int closest, uint32_t* out_host);
+
+/* ---- host helper: Core::Camera + the uniform block of RTApp::run ---------------------------- */
+/* Camera::setView/updateView (Graphics/Camera.cpp:19-24,71-95), Camera::setPerspectiveProjection
+ * (Graphics/Camera.cpp:8-17) and Uniform{inverse(transpose(view)), inverse(transpose(proj)), frame,
+ * depthMax} (RT/RTApp.cpp:44-49). rot = (pitch x, yaw y, roll z), Tait-Bryan Y-X-Z. Pure host code. */
+void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar,
+                        uint32_t frame, uint32_t depth_max, brt_uniform* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRT_H_ */
