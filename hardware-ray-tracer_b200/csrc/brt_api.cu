@@ -1,0 +1,1098 @@
+// libbrt.so — the C ABI of include/brt.h over the hand-written sm_100a kernels.
+// Host side of the drop-in boundary: what the reference does in RayTracing::Scene (RT/Scene.cpp),
+// RayTracing::Pipeline (RT/RTPipeline.cpp) and the uniform block of RTApp::run (RT/RTApp.cpp:44-49).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/brt.h"
+#include "builder.h"
+#include "render_kernels.cuh"
+
+namespace brt {
+
+// ---- kernels ---------------------------------------------------------------------------------------
+BRT_KERNEL_1D(k_raygen, RaygenParams, raygen_body)
+BRT_KERNEL_1D(k_shade, ShadeParams, shade_body)
+BRT_KERNEL_1D(k_accumulate, AccumParams, accumulate_body)
+BRT_KERNEL_1D(k_resolve, ResolveParams, resolve_body)
+BRT_KERNEL_1D(k_untile, UntileParams, untile_body)
+BRT_KERNEL_1D(k_cull, CullParams, cull_body)
+
+#ifdef BRT_EMU
+template <bool ANY, bool COUNT>
+static void k_trace(const TraceParams p) {
+  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
+  TraceCounters c{0, 0, 0};
+  unsigned long long rays = 0;
+  for (uint32_t i = 0; i < n; ++i) rays += (ANY ? trace_occlusion_body<COUNT>(p, i, c) : trace_closest_body<COUNT>(p, i, c)) ? 1 : 0;
+  if (ANY) { p.stats->rays_occlusion += rays; p.stats->nodes_o += c.nodes; p.stats->prims_o += c.prims; p.stats->spheres_o += c.spheres; }
+  else { p.stats->rays_closest += rays; p.stats->nodes_c += c.nodes; p.stats->prims_c += c.prims; p.stats->spheres_c += c.spheres; }
+}
+#define BRT_LAUNCH_TRACE(ANY, COUNT, params, grid, stream) k_trace<ANY, COUNT>(params)
+#else
+// Persistent warps: each warp claims 32 consecutive rays at a time from a global cursor, so the SMs
+// stay busy until the queue is empty no matter how uneven the per-ray cost is.
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(const TraceParams p) {
+  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
+  const int lane = threadIdx.x & 31;
+  TraceCounters c{0, 0, 0};
+  uint32_t rays = 0;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(p.work, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    if (i < n) rays += (ANY ? trace_occlusion_body<COUNT>(p, i, c) : trace_closest_body<COUNT>(p, i, c)) ? 1u : 0u;
+  }
+  rays = __reduce_add_sync(0xffffffffu, rays);
+  if (COUNT) {
+    c.nodes = __reduce_add_sync(0xffffffffu, c.nodes);
+    c.prims = __reduce_add_sync(0xffffffffu, c.prims);
+    c.spheres = __reduce_add_sync(0xffffffffu, c.spheres);
+  }
+  if (lane == 0) {
+    if (rays) atomicAdd(ANY ? &p.stats->rays_occlusion : &p.stats->rays_closest, (unsigned long long)rays);
+    if (COUNT) {
+      atomicAdd(ANY ? &p.stats->nodes_o : &p.stats->nodes_c, (unsigned long long)c.nodes);
+      atomicAdd(ANY ? &p.stats->prims_o : &p.stats->prims_c, (unsigned long long)c.prims);
+      atomicAdd(ANY ? &p.stats->spheres_o : &p.stats->spheres_c, (unsigned long long)c.spheres);
+    }
+  }
+}
+#define BRT_LAUNCH_TRACE(ANY, COUNT, params, grid, stream) k_trace<ANY, COUNT><<<(grid), 128, 0, (stream)>>>(params)
+#endif
+
+// ---- host-side scene ---------------------------------------------------------------------------------
+struct MeshData {
+  bool sphere = false;
+  float center[3] = {0, 0, 0};
+  float radius = 0.0f;
+  uint32_t n_vertices = 0, n_indices = 0;
+  DevBuf vertices, indices, nodes, tris;
+  bool dirty = true;
+  BuildResult blas;
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+};
+struct InstanceData {
+  uint32_t mesh, material;
+  float o2w[12], w2o[12];
+};
+
+// row-major 3x4 affine inverse, computed in double and rounded once (the reference gets W2O from the driver)
+static void invert3x4(const float m[12], float out[12]) {
+  const double a = m[0], b = m[1], c = m[2], tx = m[3];
+  const double d = m[4], e = m[5], f = m[6], ty = m[7];
+  const double g = m[8], h = m[9], i = m[10], tz = m[11];
+  const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + b * B + c * C;
+  const double id = 1.0 / det;
+  const double r00 = A * id, r01 = -(b * i - c * h) * id, r02 = (b * f - c * e) * id;
+  const double r10 = B * id, r11 = (a * i - c * g) * id, r12 = -(a * f - c * d) * id;
+  const double r20 = C * id, r21 = -(a * h - b * g) * id, r22 = (a * e - b * d) * id;
+  out[0] = (float)r00; out[1] = (float)r01; out[2] = (float)r02; out[3] = (float)(-(r00 * tx + r01 * ty + r02 * tz));
+  out[4] = (float)r10; out[5] = (float)r11; out[6] = (float)r12; out[7] = (float)(-(r10 * tx + r11 * ty + r12 * tz));
+  out[8] = (float)r20; out[9] = (float)r21; out[10] = (float)r22; out[11] = (float)(-(r20 * tx + r21 * ty + r22 * tz));
+}
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cls = 0;
+};
+
+enum { CLS_RAYGEN = 0, CLS_CLOSEST, CLS_SHADE, CLS_OCCL, CLS_ACCUM, CLS_RESOLVE, CLS_COUNT };
+
+}  // namespace brt
+
+using namespace brt;
+
+struct brt_context {
+  int device = 0;
+  int sm_count = 148;
+  uint32_t tile_rank = 0, tile_world = 1, flags = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  std::unique_ptr<Builder> builder;
+
+  // scene (host mirrors)
+  std::vector<std::unique_ptr<MeshData>> meshes;
+  std::vector<InstanceData> instances;
+  std::vector<uint8_t> visible;  // per instance, Smart Culling state
+  std::vector<brt_material> materials;
+  std::vector<float> mat_ext;    // transmission, ior per material
+  std::vector<brt_light> lights;
+  brt_sky sky{};
+  bool built = false;
+  bool tables_dirty = true, tlas_dirty = true;
+
+  // scene (device)
+  DevBuf d_materials, d_mat_ext, d_lights, d_inst_shade, d_inst_src, d_inst_ids, d_mesh_bounds, d_visible;
+  DevBuf d_tlas_nodes, d_tlas_inst;
+  uint32_t tlas_count = 0;  // visible, non-empty instances in the TLAS
+  BuildResult tlas{};
+
+  // frame
+  uint32_t cap = 0;  // path slots
+  uint32_t frame_w = 0, frame_h = 0;
+  DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib, s_o, s_d, s_target;
+  DevBuf d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
+  DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
+  std::vector<EventPair> events;
+  size_t events_used = 0;
+  brt_stats stats{};
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class F>
+int guarded(brt_context* ctx, F&& f) {
+  try {
+    f();
+    return BRT_OK;
+  } catch (const CudaError& e) {
+    if (ctx) ctx->err = e.what();
+    return BRT_ERR_CUDA;
+  } catch (const LimitError& e) {
+    if (ctx) ctx->err = e.what();
+    return BRT_ERR_LIMIT;
+  } catch (const std::invalid_argument& e) {
+    if (ctx) ctx->err = e.what();
+    return BRT_ERR_INVALID;
+  } catch (const std::logic_error& e) {
+    if (ctx) ctx->err = e.what();
+    return BRT_ERR_STATE;
+  } catch (const std::exception& e) {
+    if (ctx) ctx->err = e.what();
+    return BRT_ERR_CUDA;
+  }
+}
+[[noreturn]] void invalid(const char* m) { throw std::invalid_argument(m); }
+[[noreturn]] void bad_state(const char* m) { throw std::logic_error(m); }
+
+void upload(cudaStream_t s, DevBuf& buf, const void* src, size_t bytes) {
+  buf.ensure(std::max<size_t>(bytes, 16));
+  if (bytes) BRT_CUDA(cudaMemcpyAsync(buf.ptr(), src, bytes, cudaMemcpyHostToDevice, s));
+}
+
+uint32_t grid_for(const brt_context* c, uint32_t n, uint32_t block, uint32_t blocks_per_sm) {
+  return std::max(1u, std::min(div_up(n, block), (uint32_t)c->sm_count * blocks_per_sm));
+}
+
+// ---- timing ----------------------------------------------------------------------------------------
+EventPair& next_events(brt_context* c, int cls) {
+  if (c->events_used == c->events.size()) {
+    EventPair e;
+    BRT_CUDA(cudaEventCreate(&e.a));
+    BRT_CUDA(cudaEventCreate(&e.b));
+    c->events.push_back(e);
+  }
+  EventPair& e = c->events[c->events_used++];
+  e.cls = cls;
+  return e;
+}
+struct Timed {  // brackets one launch with events of class `cls`
+  brt_context* c;
+  EventPair* e;
+  Timed(brt_context* ctx, int cls) : c(ctx), e(&next_events(ctx, cls)) { BRT_CUDA(cudaEventRecord(e->a, c->stream)); }
+  ~Timed() { cudaEventRecord(e->b, c->stream); }
+};
+
+// ---- scene tables ------------------------------------------------------------------------------------
+void build_tables(brt_context* c) {
+  cudaStream_t s = c->stream;
+  upload(s, c->d_materials, c->materials.data(), c->materials.size() * sizeof(brt_material));
+  upload(s, c->d_mat_ext, c->mat_ext.data(), c->mat_ext.size() * 4);
+  upload(s, c->d_lights, c->lights.data(), c->lights.size() * sizeof(brt_light));
+  // exact object-space box of every mesh (read by the TLAS builder and Smart Culling)
+  std::vector<float> mb(std::max<size_t>(c->meshes.size(), 1) * 8, 0.0f);
+  for (size_t mi = 0; mi < c->meshes.size(); ++mi)
+    for (int k = 0; k < 3; ++k) {
+      mb[8 * mi + k] = c->meshes[mi]->lo[k];
+      mb[8 * mi + 4 + k] = c->meshes[mi]->hi[k];
+    }
+  upload(s, c->d_mesh_bounds, mb.data(), mb.size() * 4);
+  std::vector<InstShade> shade(c->instances.size());
+  for (size_t i = 0; i < c->instances.size(); ++i) {
+    const InstanceData& in = c->instances[i];
+    const MeshData& m = *c->meshes[in.mesh];
+    InstShade& r = shade[i];
+    std::memset(&r, 0, sizeof(r));
+    std::memcpy(r.o2w, in.o2w, 48);
+    std::memcpy(r.w2o, in.w2o, 48);
+    r.vertices = m.vertices.as<float>();
+    r.indices = m.indices.as<uint32_t>();
+    r.sphere = make_float4(m.center[0], m.center[1], m.center[2], m.radius);
+    r.kind = m.sphere ? 1u : 0u;
+    r.material = in.material;
+    r.mesh = in.mesh;
+  }
+  upload(s, c->d_inst_shade, shade.data(), shade.size() * sizeof(InstShade));
+  c->tables_dirty = false;
+}
+
+void build_tlas(brt_context* c) {
+  cudaStream_t s = c->stream;
+  std::vector<InstRec> src;
+  std::vector<uint32_t> ids;
+  for (size_t i = 0; i < c->instances.size(); ++i) {
+    const InstanceData& in = c->instances[i];
+    const MeshData& m = *c->meshes[in.mesh];
+    if (!c->visible[i]) continue;
+    if (!m.sphere && m.n_indices == 0) continue;
+    InstRec r;
+    std::memset(&r, 0, sizeof(r));
+    std::memcpy(r.w2o, in.w2o, 48);
+    r.nodes = m.nodes.as<Node8>();
+    r.tris = m.tris.as<TriRec>();
+    r.sphere = make_float4(m.center[0], m.center[1], m.center[2], m.radius);
+    r.kind = m.sphere ? 1u : 0u;
+    r.inst_id = (uint32_t)i;
+    src.push_back(r);
+    ids.push_back((uint32_t)i);
+  }
+  c->tlas_count = (uint32_t)src.size();
+  c->tlas = BuildResult{};
+  if (c->tlas_count) {
+    upload(s, c->d_inst_src, src.data(), src.size() * sizeof(InstRec));
+    upload(s, c->d_inst_ids, ids.data(), ids.size() * 4);
+    c->d_tlas_nodes.ensure((size_t)Builder::node_capacity(c->tlas_count) * sizeof(Node8));
+    c->d_tlas_inst.ensure((size_t)c->tlas_count * sizeof(InstRec));
+    c->builder->build_instances(s, c->d_inst_shade.as<InstShade>(), c->d_inst_ids.as<uint32_t>(), c->d_inst_src.as<InstRec>(), c->tlas_count,
+                                c->d_mesh_bounds.as<float4>(), c->d_tlas_nodes.as<Node8>(), c->d_tlas_inst.as<InstRec>(), &c->tlas);
+  }
+  c->tlas_dirty = false;
+}
+
+uint32_t max_blas_levels(const brt_context* c) {
+  uint32_t l = 0;
+  for (const auto& m : c->meshes)
+    if (!m->sphere) l = std::max(l, m->blas.levels);
+  return l;
+}
+
+void refresh_scene_stats(brt_context* c) {
+  uint64_t tris = 0, nodes = c->tlas.n_nodes, bytes = (uint64_t)c->tlas.n_nodes * 80 + (uint64_t)c->tlas_count * sizeof(InstRec);
+  for (const InstanceData& in : c->instances) tris += c->meshes[in.mesh]->n_indices / 3;
+  float sah = 0.0f, sah0 = 0.0f;
+  uint32_t biggest = 0;
+  for (const auto& m : c->meshes) {
+    if (m->sphere || m->n_indices == 0) continue;
+    nodes += m->blas.n_nodes;
+    bytes += (uint64_t)m->blas.n_nodes * 80 + (uint64_t)(m->n_indices / 3) * 48;
+    if (m->n_indices / 3 >= biggest) { biggest = m->n_indices / 3; sah = m->blas.sah_final; sah0 = m->blas.sah_lbvh; }
+  }
+  c->stats.total_triangles = tris;
+  c->stats.bvh_nodes = nodes;
+  c->stats.bvh_bytes = bytes;
+  c->stats.sah_cost = sah;
+  c->stats.sah_cost_lbvh = sah0;
+  c->stats.instances_total = (uint32_t)c->instances.size();
+  c->stats.instances_visible = c->tlas_count;
+}
+
+void scene_build(brt_context* c) {
+  cudaStream_t s = c->stream;
+  cudaEvent_t e0, e1, e2;
+  BRT_CUDA(cudaEventCreate(&e0));
+  BRT_CUDA(cudaEventCreate(&e1));
+  BRT_CUDA(cudaEventCreate(&e2));
+  BRT_CUDA(cudaEventRecord(e0, s));
+  uint32_t rebuilt = 0;
+  for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
+    MeshData& m = *c->meshes[mi];
+    if (!m.dirty) continue;
+    if (m.sphere) {
+      for (int k = 0; k < 3; ++k) { m.lo[k] = m.center[k] - m.radius; m.hi[k] = m.center[k] + m.radius; }
+    } else if (m.n_indices == 0) {
+      for (int k = 0; k < 3; ++k) m.lo[k] = m.hi[k] = 0.0f;
+    } else {
+      const uint32_t nt = m.n_indices / 3;
+      m.nodes.ensure((size_t)Builder::node_capacity(nt) * sizeof(Node8));
+      m.tris.ensure((size_t)nt * sizeof(TriRec));
+      c->builder->build_triangles(s, m.vertices.as<float>(), m.indices.as<uint32_t>(), nt, m.nodes.as<Node8>(), m.tris.as<TriRec>(), nullptr,
+                                  !(c->flags & BRT_CFG_NO_TREELET), &m.blas);
+      for (int k = 0; k < 3; ++k) { m.lo[k] = m.blas.lo[k]; m.hi[k] = m.blas.hi[k]; }
+    }
+    m.dirty = false;
+    rebuilt++;
+  }
+  BRT_CUDA(cudaEventRecord(e1, s));
+  build_tables(c);
+  build_tlas(c);
+  BRT_CUDA(cudaEventRecord(e2, s));
+  BRT_CUDA(cudaStreamSynchronize(s));
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  c->stats.ms_blas_build = ms;
+  cudaEventElapsedTime(&ms, e1, e2);
+  c->stats.ms_tlas_build = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  c->stats.blas_built = rebuilt;
+  if (c->tlas.levels + max_blas_levels(c) + 4 > BRT_STACK_SIZE) throw LimitError("scene_build: BVH deeper than the traversal stack");
+  c->built = true;
+  refresh_scene_stats(c);
+}
+
+// ---- frame ---------------------------------------------------------------------------------------------
+TileMap make_tile_map(const brt_context* c, const brt_render_opts& o) {
+  TileMap m;
+  m.width = o.width;
+  m.height = o.height;
+  m.tiles_x = div_up(o.width, BRT_TILE);
+  m.n_tiles = m.tiles_x * div_up(o.height, BRT_TILE);
+  m.tile_rank = c->tile_rank;
+  m.tile_world = c->tile_world;
+  m.crop_x0 = 0; m.crop_y0 = 0; m.crop_x1 = o.width; m.crop_y1 = o.height;
+  if (o.crop_w) {
+    m.crop_x0 = o.crop_x0;
+    m.crop_y0 = o.crop_y0;
+    m.crop_x1 = std::min<uint64_t>(o.width, (uint64_t)o.crop_x0 + o.crop_w);
+    m.crop_y1 = std::min<uint64_t>(o.height, (uint64_t)o.crop_y0 + o.crop_h);
+  }
+  return m;
+}
+uint32_t tiles_per_rank(uint32_t width, uint32_t height, uint32_t world) {
+  const uint32_t n = div_up(width, BRT_TILE) * div_up(height, BRT_TILE);
+  return div_up(n, world ? world : 1);
+}
+
+void ensure_frame_buffers(brt_context* c, const brt_render_opts& o) {
+  const uint32_t cap = tiles_per_rank(o.width, o.height, c->tile_world) * 1024u;
+  const size_t npx = (size_t)o.width * o.height;
+  const uint32_t L = std::max<uint32_t>(1, (uint32_t)c->lights.size());
+  for (int k = 0; k < 2; ++k) {
+    c->q_o[k].ensure((size_t)cap * 16);
+    c->q_d[k].ensure((size_t)cap * 16);
+    c->q_w[k].ensure((size_t)cap * 16);
+    c->q_px[k].ensure((size_t)cap * 4);
+    c->q_seed[k].ensure((size_t)cap * 4);
+  }
+  c->d_hit.ensure((size_t)cap * 16);
+  c->d_hit_inst.ensure((size_t)cap * 4);
+  c->d_contrib.ensure((size_t)cap * 16 * L);
+  c->s_o.ensure((size_t)cap * 16 * L);
+  c->s_d.ensure((size_t)cap * 16 * L);
+  c->s_target.ensure((size_t)cap * 4 * L);
+  c->d_accum.ensure(npx * 16);
+  c->d_image.ensure(npx * 16);
+  c->d_tiles.ensure((size_t)cap * 16);
+  c->d_aov_prim.ensure(npx * 4);
+  c->d_aov_inst.ensure(npx * 4);
+  c->d_aov_t.ensure(npx * 4);
+  c->d_counters.ensure(sizeof(FrameCounters));
+  c->d_fstats.ensure(sizeof(FrameStats));
+  c->cap = cap;
+  c->frame_w = o.width;
+  c->frame_h = o.height;
+}
+
+PathQueue queue_of(brt_context* c, int k) {
+  return PathQueue{c->q_o[k].as<float4>(), c->q_d[k].as<float4>(), c->q_w[k].as<float4>(), c->q_px[k].as<uint32_t>(), c->q_seed[k].as<uint32_t>()};
+}
+
+template <bool ANY>
+void launch_trace(brt_context* c, const TraceParams& p) {
+  const uint32_t grid = (uint32_t)c->sm_count * 8u;
+  if (c->flags & BRT_CFG_COUNTERS) BRT_LAUNCH_TRACE(ANY, true, p, grid, c->stream);
+  else BRT_LAUNCH_TRACE(ANY, false, p, grid, c->stream);
+  BRT_CHECK_LAUNCH();
+}
+
+// renders into d_image (and d_tiles); no host synchronisation except the final stats read-back
+void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_opts& o, void* d_tiles_out) {
+  if (!c->built) bad_state("render_frame: scene not built (call brt_scene_build)");
+  if (!o.width || !o.height || !o.spp) invalid("render_frame: width, height and spp must be non-zero");
+  if (c->lights.size() > BRT_MAX_LIGHTS) throw LimitError("render_frame: more than BRT_MAX_LIGHTS lights");
+  if (c->tables_dirty) build_tables(c);
+  if (c->tlas_dirty) build_tlas(c);
+  ensure_frame_buffers(c, o);
+  cudaStream_t s = c->stream;
+  const TileMap map = make_tile_map(c, o);
+  const uint32_t cap = c->cap;
+  const size_t npx = (size_t)o.width * o.height;
+  const uint32_t n_lights = (uint32_t)c->lights.size();
+  const uint32_t n_slots = std::max(1u, n_lights);
+  c->events_used = 0;
+  FrameCounters* ctr = c->d_counters.as<FrameCounters>();
+  FrameStats* fst = c->d_fstats.as<FrameStats>();
+  EventPair& whole = next_events(c, CLS_COUNT);
+  BRT_CUDA(cudaEventRecord(whole.a, s));
+  BRT_CUDA(cudaMemsetAsync(c->d_accum.ptr(), 0, npx * 16, s));
+  BRT_CUDA(cudaMemsetAsync(fst, 0, sizeof(FrameStats), s));
+  BRT_CUDA(cudaMemsetAsync(c->d_aov_prim.ptr(), 0xff, npx * 4, s));
+  BRT_CUDA(cudaMemsetAsync(c->d_aov_inst.ptr(), 0xff, npx * 4, s));
+  BRT_CUDA(cudaMemsetAsync(c->d_aov_t.ptr(), 0, npx * 4, s));
+  if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(c->d_image.ptr(), 0, npx * 16, s));
+  const bool any_bounce = (o.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0;
+  const uint32_t rounds = any_bounce ? u.depthMax : std::min(u.depthMax, 1u);
+  uint32_t launches = 0, l_closest = 0, l_occl = 0;
+  const Node8* tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
+  const InstRec* insts = c->d_tlas_inst.as<InstRec>();
+
+  for (uint32_t sample = 0; sample < o.spp; ++sample) {
+    {
+      RaygenParams rp;
+      rp.count = cap;
+      rp.count_ptr = nullptr;
+      rp.map = map;
+      std::memcpy(rp.Vi, u.viewInverse, 64);
+      std::memcpy(rp.Pi, u.projInverse, 64);
+      rp.frame = u.frame + sample;
+      rp.flags = o.flags;
+      rp.q = queue_of(c, 0);
+      Timed t(c, CLS_RAYGEN);
+      BRT_LAUNCH_1D(k_raygen, rp, grid_for(c, cap, 256, 8), 256, s);
+      BRT_CHECK_LAUNCH();
+      launches++;
+    }
+    int cur = 0;
+    for (uint32_t round = 0; round < rounds; ++round) {
+      // counters of this round: n_paths[cur] is live (or == cap in round 0), everything else restarts
+      if (round == 0) {
+        BRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
+        // round 0 walks all `cap` slots (padding slots carry px == BRT_MISS)
+      } else {
+        // keep n_paths[cur]; zero n_paths[next], n_shadow and the work cursors
+        BRT_CUDA(cudaMemsetAsync(&ctr->n_paths[cur ^ 1], 0, 4, s));
+        BRT_CUDA(cudaMemsetAsync(&ctr->n_shadow, 0, sizeof(FrameCounters) - offsetof(FrameCounters, n_shadow), s));
+      }
+      const uint32_t* count_ptr = round == 0 ? nullptr : &ctr->n_paths[cur];
+      const PathQueue qc = queue_of(c, cur), qn = queue_of(c, cur ^ 1);
+      {
+        TraceParams tp{};
+        tp.count = cap;
+        tp.count_ptr = count_ptr;
+        tp.tlas = tlas;
+        tp.insts = insts;
+        tp.o = qc.o;
+        tp.d = qc.d;
+        tp.px = qc.px;
+        tp.hit = c->d_hit.as<float4>();
+        tp.hit_inst = c->d_hit_inst.as<uint32_t>();
+        tp.work = &ctr->work_closest;
+        tp.stats = fst;
+        Timed t(c, CLS_CLOSEST);
+        launch_trace<false>(c, tp);
+        launches++;
+        l_closest++;
+      }
+      {
+        ShadeParams sp{};
+        sp.count = cap;
+        sp.count_ptr = count_ptr;
+        sp.cur = qc;
+        sp.next = qn;
+        sp.hit = c->d_hit.as<float4>();
+        sp.hit_inst = c->d_hit_inst.as<uint32_t>();
+        sp.ctr = ctr;
+        sp.next_slot = (uint32_t)(cur ^ 1);
+        sp.cap = cap;
+        sp.inst = c->d_inst_shade.as<InstShade>();
+        sp.materials = c->d_materials.as<float>();
+        sp.mat_ext = c->d_mat_ext.as<float2>();
+        sp.lights = c->d_lights.as<LightRec>();
+        sp.n_lights = n_lights;
+        sp.contrib = c->d_contrib.as<float4>();
+        sp.s_o = c->s_o.as<float4>();
+        sp.s_d = c->s_d.as<float4>();
+        sp.s_target = c->s_target.as<uint32_t>();
+        sp.flags = o.flags;
+        sp.last_round = round + 1 == rounds ? 1u : 0u;
+        sp.write_aov = (sample == 0 && round == 0) ? 1u : 0u;
+        sp.aov_prim = c->d_aov_prim.as<uint32_t>();
+        sp.aov_inst = c->d_aov_inst.as<uint32_t>();
+        sp.aov_t = c->d_aov_t.as<float>();
+        sp.sky = c->sky;
+        Timed t(c, CLS_SHADE);
+        BRT_LAUNCH_1D(k_shade, sp, grid_for(c, cap, 128, 16), 128, s);
+        BRT_CHECK_LAUNCH();
+        launches++;
+      }
+      if (n_lights) {
+        TraceParams tp{};
+        tp.count = 0;
+        tp.count_ptr = &ctr->n_shadow;
+        tp.tlas = tlas;
+        tp.insts = insts;
+        tp.o = c->s_o.as<float4>();
+        tp.d = c->s_d.as<float4>();
+        tp.target = c->s_target.as<uint32_t>();
+        tp.contrib = c->d_contrib.as<float4>();
+        tp.work = &ctr->work_occl;
+        tp.stats = fst;
+        Timed t(c, CLS_OCCL);
+        launch_trace<true>(c, tp);
+        launches++;
+        l_occl++;
+      }
+      {
+        AccumParams ap{};
+        ap.count = cap;
+        ap.count_ptr = count_ptr;
+        ap.px = qc.px;
+        ap.w = qc.w;
+        ap.contrib = c->d_contrib.as<float4>();
+        ap.n_slots = n_slots;
+        ap.cap = cap;
+        ap.accum = c->d_accum.as<float4>();
+        Timed t(c, CLS_ACCUM);
+        BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, cap, 256, 8), 256, s);
+        BRT_CHECK_LAUNCH();
+        launches++;
+      }
+      cur ^= 1;
+    }
+  }
+  {
+    ResolveParams rp{};
+    rp.count = cap;
+    rp.count_ptr = nullptr;
+    rp.map = map;
+    rp.spp = (float)o.spp;
+    rp.accum = c->d_accum.as<float4>();
+    rp.image = c->d_image.as<float4>();
+    rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : c->d_tiles.as<float4>();
+    Timed t(c, CLS_RESOLVE);
+    BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
+    BRT_CHECK_LAUNCH();
+    launches++;
+  }
+  BRT_CUDA(cudaEventRecord(whole.b, s));
+  c->stats.launches_total = launches;
+  c->stats.launches_trace_closest = l_closest;
+  c->stats.launches_trace_occlusion = l_occl;
+}
+
+// waits for the frame and folds the device-side statistics / event timings into ctx->stats
+void finish_frame(brt_context* c) {
+  FrameStats fs;
+  BRT_CUDA(cudaMemcpyAsync(&fs, c->d_fstats.ptr(), sizeof(fs), cudaMemcpyDeviceToHost, c->stream));
+  BRT_CUDA(cudaStreamSynchronize(c->stream));
+  BRT_CUDA(cudaGetLastError());
+  float ms[CLS_COUNT + 1] = {0};
+  for (size_t i = 0; i < c->events_used; ++i) {
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, c->events[i].a, c->events[i].b);
+    ms[c->events[i].cls] += t;
+  }
+  brt_stats& st = c->stats;
+  st.rays_closest = fs.rays_closest;
+  st.rays_occlusion = fs.rays_occlusion;
+  st.nodes_visited_closest = fs.nodes_c;
+  st.prims_tested_closest = fs.prims_c;
+  st.spheres_tested_closest = fs.spheres_c;
+  st.nodes_visited_occlusion = fs.nodes_o;
+  st.prims_tested_occlusion = fs.prims_o;
+  st.spheres_tested_occlusion = fs.spheres_o;
+  st.ms_raygen = ms[CLS_RAYGEN];
+  st.ms_trace_closest = ms[CLS_CLOSEST];
+  st.ms_shade = ms[CLS_SHADE];
+  st.ms_trace_occlusion = ms[CLS_OCCL];
+  st.ms_accumulate = ms[CLS_ACCUM];
+  st.ms_resolve = ms[CLS_RESOLVE];
+  st.ms_total = ms[CLS_COUNT];
+}
+
+}  // namespace
+
+// ========================================================================================================
+extern "C" {
+
+int brt_create(const brt_config* cfg, brt_context** out) {
+  if (!out) return BRT_ERR_INVALID;
+  *out = nullptr;
+  brt_context* c = new brt_context();
+  int rc = guarded(c, [&] {
+    if (cfg) {
+      c->device = cfg->device;
+      c->tile_rank = cfg->tile_rank;
+      c->tile_world = cfg->tile_world ? cfg->tile_world : 1;
+      c->flags = cfg->flags;
+      if (c->tile_rank >= c->tile_world) invalid("brt_create: tile_rank >= tile_world");
+    }
+    int n = 0;
+    BRT_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0 || c->device < 0 || c->device >= n) throw CudaError("brt_create: no usable CUDA device (this library has no CPU path)");
+    BRT_CUDA(cudaSetDevice(c->device));
+    BRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    BRT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    c->builder.reset(new Builder(c->sm_count));
+  });
+  if (rc != BRT_OK) {
+    g_create_error = c->err;
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return BRT_OK;
+}
+
+void brt_destroy(brt_context* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (EventPair& e : c->events) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* brt_last_error(const brt_context* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int brt_set_stream(brt_context* c, void* stream) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    BRT_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->own_stream = false;
+    c->stream = static_cast<cudaStream_t>(stream);
+  });
+}
+
+int brt_mesh_create(brt_context* c, const brt_vertex* v, uint32_t nv, const uint32_t* idx, uint32_t ni, uint32_t* mesh_id) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if ((!v && nv) || (!idx && ni) || ni % 3) invalid("mesh_create: bad arguments");
+    for (uint32_t i = 0; i < ni; ++i)
+      if (idx[i] >= nv) invalid("mesh_create: index out of range");
+    BRT_CUDA(cudaSetDevice(c->device));
+    std::unique_ptr<MeshData> m(new MeshData());
+    m->n_vertices = nv;
+    m->n_indices = ni;
+    upload(c->stream, m->vertices, v, (size_t)nv * sizeof(brt_vertex));
+    upload(c->stream, m->indices, idx, (size_t)ni * 4);
+    BRT_CUDA(cudaStreamSynchronize(c->stream));  // "the library copies all input arrays during the call"
+    c->meshes.push_back(std::move(m));
+    if (mesh_id) *mesh_id = (uint32_t)c->meshes.size() - 1;
+    c->built = false;
+  });
+}
+
+int brt_mesh_update_vertices(brt_context* c, uint32_t mesh_id, const brt_vertex* v, uint32_t nv) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (mesh_id >= c->meshes.size() || c->meshes[mesh_id]->sphere || nv != c->meshes[mesh_id]->n_vertices || (!v && nv))
+      invalid("mesh_update_vertices: bad mesh id or vertex count");
+    BRT_CUDA(cudaSetDevice(c->device));
+    MeshData& m = *c->meshes[mesh_id];
+    BRT_CUDA(cudaMemcpyAsync(m.vertices.ptr(), v, (size_t)nv * sizeof(brt_vertex), cudaMemcpyHostToDevice, c->stream));
+    BRT_CUDA(cudaStreamSynchronize(c->stream));
+    m.dirty = true;
+    c->built = false;
+  });
+}
+
+int brt_sphere_create(brt_context* c, const float center[3], float radius, uint32_t* mesh_id) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!center || !(radius > 0.0f)) invalid("sphere_create: bad arguments");
+    std::unique_ptr<MeshData> m(new MeshData());
+    m->sphere = true;
+    std::memcpy(m->center, center, 12);
+    m->radius = radius;
+    c->meshes.push_back(std::move(m));
+    if (mesh_id) *mesh_id = (uint32_t)c->meshes.size() - 1;
+    c->built = false;
+  });
+}
+
+int brt_material_create(brt_context* c, const brt_material* m, uint32_t* id) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!m) invalid("material_create: null");
+    c->materials.push_back(*m);
+    c->mat_ext.push_back(0.0f);
+    c->mat_ext.push_back(1.5f);
+    if (id) *id = (uint32_t)c->materials.size() - 1;
+    c->tables_dirty = true;
+  });
+}
+
+int brt_material_set_transmission(brt_context* c, uint32_t id, float transmission, float ior) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (id >= c->materials.size()) invalid("material_set_transmission: bad id");
+    c->mat_ext[2 * id] = transmission;
+    c->mat_ext[2 * id + 1] = ior;
+    c->tables_dirty = true;
+  });
+}
+
+int brt_light_create(brt_context* c, const brt_light* l, uint32_t* id) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!l) invalid("light_create: null");
+    c->lights.push_back(*l);
+    if (id) *id = (uint32_t)c->lights.size() - 1;
+    c->tables_dirty = true;
+  });
+}
+
+int brt_sky_set(brt_context* c, const brt_sky* sky) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!sky) invalid("sky_set: null");
+    c->sky = *sky;
+  });
+}
+
+int brt_instance_create(brt_context* c, uint32_t mesh, uint32_t mat, const float x[12], uint32_t* id) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!x || mesh >= c->meshes.size() || mat >= c->materials.size()) invalid("instance_create: bad mesh/material id");
+    InstanceData in;
+    in.mesh = mesh;
+    in.material = mat;
+    std::memcpy(in.o2w, x, 48);
+    invert3x4(in.o2w, in.w2o);
+    c->instances.push_back(in);
+    c->visible.push_back(1);
+    if (id) *id = (uint32_t)c->instances.size() - 1;
+    c->built = false;
+    c->tables_dirty = c->tlas_dirty = true;
+  });
+}
+
+int brt_instance_set_transform(brt_context* c, uint32_t id, const float x[12]) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!x || id >= c->instances.size()) invalid("instance_set_transform: bad id");
+    std::memcpy(c->instances[id].o2w, x, 48);
+    invert3x4(c->instances[id].o2w, c->instances[id].w2o);
+    c->built = false;
+    c->tables_dirty = c->tlas_dirty = true;
+  });
+}
+
+int brt_instance_set_material(brt_context* c, uint32_t id, uint32_t mat) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (id >= c->instances.size() || mat >= c->materials.size()) invalid("instance_set_material: bad id");
+    c->instances[id].material = mat;
+    c->tables_dirty = true;
+  });
+}
+
+int brt_instance_destroy(brt_context* c, uint32_t id) {  // RT/Scene.cpp:122-125: swap-remove
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (id >= c->instances.size()) invalid("instance_destroy: bad id");
+    c->instances[id] = c->instances.back();
+    c->instances.pop_back();
+    c->visible[id] = c->visible.back();
+    c->visible.pop_back();
+    c->built = false;
+    c->tables_dirty = c->tlas_dirty = true;
+  });
+}
+
+int brt_scene_build(brt_context* c) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    BRT_CUDA(cudaSetDevice(c->device));
+    scene_build(c);
+  });
+}
+
+int brt_smart_cull(brt_context* c, const brt_uniform* u, uint32_t width, uint32_t height, float threshold_px2, float hysteresis,
+                   uint32_t* visible_count) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!u) invalid("smart_cull: null");
+    (void)width;
+    BRT_CUDA(cudaSetDevice(c->device));
+    bool dirty_mesh = false;
+    for (const auto& m : c->meshes) dirty_mesh |= m->dirty;
+    if (dirty_mesh || !c->built) scene_build(c);
+    if (c->tables_dirty) build_tables(c);
+    cudaStream_t s = c->stream;
+    const uint32_t n = (uint32_t)c->instances.size();
+    cudaEvent_t e0, e1, e2;
+    BRT_CUDA(cudaEventCreate(&e0));
+    BRT_CUDA(cudaEventCreate(&e1));
+    BRT_CUDA(cudaEventCreate(&e2));
+    BRT_CUDA(cudaEventRecord(e0, s));
+    if (n) {
+      upload(s, c->d_visible, c->visible.data(), n);
+      CullParams p{};
+      p.count = n;
+      p.count_ptr = nullptr;
+      p.inst = c->d_inst_shade.as<InstShade>();
+      p.mesh_bounds = c->d_mesh_bounds.as<float4>();
+      const float* Vi = u->viewInverse;
+      p.eye[0] = Vi[3]; p.eye[1] = Vi[7]; p.eye[2] = Vi[11];
+      p.fwd[0] = Vi[2]; p.fwd[1] = Vi[6]; p.fwd[2] = Vi[10];
+      const float p11 = 1.0f / u->projInverse[5];
+      p.k = p11 * ((float)height * 0.5f);
+      p.threshold = threshold_px2;
+      p.hysteresis = hysteresis;
+      p.visible = c->d_visible.as<uint8_t>();
+      BRT_LAUNCH_1D(k_cull, p, grid_for(c, n, 128, 8), 128, s);
+      BRT_CHECK_LAUNCH();
+      BRT_CUDA(cudaMemcpyAsync(c->visible.data(), c->d_visible.ptr(), n, cudaMemcpyDeviceToHost, s));
+    }
+    BRT_CUDA(cudaEventRecord(e1, s));
+    BRT_CUDA(cudaStreamSynchronize(s));
+    build_tlas(c);
+    BRT_CUDA(cudaEventRecord(e2, s));
+    BRT_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->stats.ms_cull = ms;
+    cudaEventElapsedTime(&ms, e1, e2);
+    c->stats.ms_tlas_build = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    if (c->tlas.levels + max_blas_levels(c) + 4 > BRT_STACK_SIZE) throw LimitError("smart_cull: BVH deeper than the traversal stack");
+    refresh_scene_stats(c);
+    if (visible_count) {
+      uint32_t k = 0;
+      for (uint8_t v : c->visible) k += v ? 1u : 0u;
+      *visible_count = k;
+    }
+  });
+}
+
+int brt_get_visibility(brt_context* c, uint8_t* out, uint32_t n) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!out || n != c->instances.size()) invalid("get_visibility: size mismatch");
+    std::memcpy(out, c->visible.data(), n);
+  });
+}
+
+int brt_render_frame(brt_context* c, const brt_uniform* u, const brt_render_opts* o, float* rgba_host) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!u || !o) invalid("render_frame: null");
+    BRT_CUDA(cudaSetDevice(c->device));
+    render_frame_device(c, *u, *o, nullptr);
+    if (rgba_host)
+      BRT_CUDA(cudaMemcpyAsync(rgba_host, c->d_image.ptr(), (size_t)o->width * o->height * 16, cudaMemcpyDeviceToHost, c->stream));
+    finish_frame(c);
+  });
+}
+
+int brt_render_frame_tiles(brt_context* c, const brt_uniform* u, const brt_render_opts* o, void* d_tiles) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!u || !o) invalid("render_frame_tiles: null");
+    BRT_CUDA(cudaSetDevice(c->device));
+    render_frame_device(c, *u, *o, d_tiles);
+    finish_frame(c);
+  });
+}
+
+size_t brt_tile_buffer_bytes(uint32_t width, uint32_t height, uint32_t tile_world) {
+  return (size_t)tiles_per_rank(width, height, tile_world) * 1024u * 16u;
+}
+
+int brt_untile(brt_context* c, const void* d_all, uint32_t width, uint32_t height, uint32_t tile_world, void* d_rgba) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!d_all || !d_rgba || !width || !height || !tile_world) invalid("untile: bad arguments");
+    BRT_CUDA(cudaSetDevice(c->device));
+    UntileParams p{};
+    p.count = width * height;
+    p.count_ptr = nullptr;
+    p.width = width;
+    p.height = height;
+    p.tiles_x = div_up(width, BRT_TILE);
+    p.tile_world = tile_world;
+    p.slots_per_rank = tiles_per_rank(width, height, tile_world) * 1024u;
+    p.all = static_cast<const float4*>(d_all);
+    p.image = static_cast<float4*>(d_rgba);
+    BRT_LAUNCH_1D(k_untile, p, grid_for(c, p.count, 256, 8), 256, c->stream);
+    BRT_CHECK_LAUNCH();
+  });
+}
+
+void* brt_device_image(brt_context* c) { return c ? c->d_image.ptr() : nullptr; }
+
+int brt_get_aov(brt_context* c, int kind, void* out) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!out) invalid("get_aov: null");
+    if (!c->frame_w) bad_state("get_aov: no frame rendered");
+    BRT_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->frame_w * c->frame_h;
+    const void* src = nullptr;
+    switch (kind) {
+      case BRT_AOV_PRIM_ID: src = c->d_aov_prim.ptr(); break;
+      case BRT_AOV_INST_ID: src = c->d_aov_inst.ptr(); break;
+      case BRT_AOV_HIT_T: src = c->d_aov_t.ptr(); break;
+      default: invalid("get_aov: bad kind");
+    }
+    BRT_CUDA(cudaMemcpyAsync(out, src, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    BRT_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int brt_get_stats(brt_context* c, brt_stats* out) {
+  if (!c || !out) return BRT_ERR_INVALID;
+  *out = c->stats;
+  return BRT_OK;
+}
+
+int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, uint32_t* out) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!rays || !out) invalid("trace_rays: null");
+    if (!c->built) bad_state("trace_rays: scene not built");
+    BRT_CUDA(cudaSetDevice(c->device));
+    if (c->tlas_dirty) build_tlas(c);
+    if (n == 0) return;
+    cudaStream_t s = c->stream;
+    // split the interleaved rays into the two float4 arrays the kernels read
+    std::vector<float> o4((size_t)n * 4), d4((size_t)n * 4);
+    for (uint32_t i = 0; i < n; ++i) {
+      std::memcpy(&o4[4 * (size_t)i], rays + 8 * (size_t)i, 16);
+      std::memcpy(&d4[4 * (size_t)i], rays + 8 * (size_t)i + 4, 16);
+    }
+    c->d_rays.ensure((size_t)n * 32);
+    c->d_ray_out.ensure((size_t)n * 16 + (size_t)n * 4 + (size_t)n * 4);
+    c->d_counters.ensure(sizeof(FrameCounters));
+    c->d_fstats.ensure(sizeof(FrameStats));
+    float4* d_o = c->d_rays.as<float4>();
+    float4* d_d = d_o + n;
+    float4* d_hit = c->d_ray_out.as<float4>();
+    uint32_t* d_inst = reinterpret_cast<uint32_t*>(d_hit + n);
+    uint32_t* d_target = d_inst + n;
+    BRT_CUDA(cudaMemcpyAsync(d_o, o4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s));
+    BRT_CUDA(cudaMemcpyAsync(d_d, d4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s));
+    BRT_CUDA(cudaMemsetAsync(c->d_counters.ptr(), 0, sizeof(FrameCounters), s));
+    BRT_CUDA(cudaMemsetAsync(c->d_fstats.ptr(), 0, sizeof(FrameStats), s));
+    FrameCounters* ctr = c->d_counters.as<FrameCounters>();
+    TraceParams tp{};
+    tp.count = n;
+    tp.tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
+    tp.insts = c->d_tlas_inst.as<InstRec>();
+    tp.o = d_o;
+    tp.d = d_d;
+    tp.stats = c->d_fstats.as<FrameStats>();
+    std::vector<float> hit((size_t)n * 4);
+    std::vector<uint32_t> inst(n);
+    if (closest) {
+      tp.hit = d_hit;
+      tp.hit_inst = d_inst;
+      tp.work = &ctr->work_closest;
+      launch_trace<false>(c, tp);
+      BRT_CUDA(cudaMemcpyAsync(hit.data(), d_hit, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+      BRT_CUDA(cudaMemcpyAsync(inst.data(), d_inst, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+      BRT_CUDA(cudaStreamSynchronize(s));
+      for (uint32_t i = 0; i < n; ++i) {
+        const bool h = inst[i] != BRT_MISS;
+        uint32_t tb, pb;
+        std::memcpy(&tb, &hit[4 * (size_t)i], 4);
+        std::memcpy(&pb, &hit[4 * (size_t)i + 3], 4);
+        out[4 * (size_t)i] = h ? tb : 0u;
+        out[4 * (size_t)i + 1] = h ? pb : BRT_MISS;
+        out[4 * (size_t)i + 2] = inst[i];
+        out[4 * (size_t)i + 3] = h ? 1u : 0u;
+      }
+    } else {
+      // occlusion: contrib[i] starts at 1 and is zeroed when ray i is blocked
+      std::vector<float> ones((size_t)n * 4, 1.0f);
+      std::vector<uint32_t> target(n);
+      for (uint32_t i = 0; i < n; ++i) target[i] = i;
+      BRT_CUDA(cudaMemcpyAsync(d_hit, ones.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s));
+      BRT_CUDA(cudaMemcpyAsync(d_target, target.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+      tp.target = d_target;
+      tp.contrib = d_hit;
+      tp.work = &ctr->work_occl;
+      launch_trace<true>(c, tp);
+      BRT_CUDA(cudaMemcpyAsync(hit.data(), d_hit, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+      BRT_CUDA(cudaStreamSynchronize(s));
+      for (uint32_t i = 0; i < n; ++i) {
+        out[4 * (size_t)i] = out[4 * (size_t)i + 1] = out[4 * (size_t)i + 2] = 0u;
+        out[4 * (size_t)i + 3] = hit[4 * (size_t)i] == 0.0f ? 1u : 0u;
+      }
+    }
+    FrameStats fs;
+    BRT_CUDA(cudaMemcpy(&fs, c->d_fstats.ptr(), sizeof(fs), cudaMemcpyDeviceToHost));
+    c->stats.rays_closest = fs.rays_closest;
+    c->stats.rays_occlusion = fs.rays_occlusion;
+    c->stats.nodes_visited_closest = fs.nodes_c;
+    c->stats.prims_tested_closest = fs.prims_c;
+    c->stats.spheres_tested_closest = fs.spheres_c;
+    c->stats.nodes_visited_occlusion = fs.nodes_o;
+    c->stats.prims_tested_occlusion = fs.prims_o;
+    c->stats.spheres_tested_occlusion = fs.spheres_o;
+  });
+}
+
+// 4x4 inverse in double (cofactor expansion along 2x2 minors), row-major in/out
+static void invert4x4(const double m[16], double inv[16]) {
+  const double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];
+  const double s3 = m[1] * m[6] - m[5] * m[2], s4 = m[1] * m[7] - m[5] * m[3], s5 = m[2] * m[7] - m[6] * m[3];
+  const double c5 = m[10] * m[15] - m[14] * m[11], c4 = m[9] * m[15] - m[13] * m[11], c3 = m[9] * m[14] - m[13] * m[10];
+  const double c2 = m[8] * m[15] - m[12] * m[11], c1 = m[8] * m[14] - m[12] * m[10], c0 = m[8] * m[13] - m[12] * m[9];
+  const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+  const double id = 1.0 / det;
+  inv[0] = (m[5] * c5 - m[6] * c4 + m[7] * c3) * id;
+  inv[1] = (-m[1] * c5 + m[2] * c4 - m[3] * c3) * id;
+  inv[2] = (m[13] * s5 - m[14] * s4 + m[15] * s3) * id;
+  inv[3] = (-m[9] * s5 + m[10] * s4 - m[11] * s3) * id;
+  inv[4] = (-m[4] * c5 + m[6] * c2 - m[7] * c1) * id;
+  inv[5] = (m[0] * c5 - m[2] * c2 + m[3] * c1) * id;
+  inv[6] = (-m[12] * s5 + m[14] * s2 - m[15] * s1) * id;
+  inv[7] = (m[8] * s5 - m[10] * s2 + m[11] * s1) * id;
+  inv[8] = (m[4] * c4 - m[5] * c2 + m[7] * c0) * id;
+  inv[9] = (-m[0] * c4 + m[1] * c2 - m[3] * c0) * id;
+  inv[10] = (m[12] * s4 - m[13] * s2 + m[15] * s0) * id;
+  inv[11] = (-m[8] * s4 + m[9] * s2 - m[11] * s0) * id;
+  inv[12] = (-m[4] * c3 + m[5] * c1 - m[6] * c0) * id;
+  inv[13] = (m[0] * c3 - m[1] * c1 + m[2] * c0) * id;
+  inv[14] = (-m[12] * s3 + m[13] * s1 - m[14] * s0) * id;
+  inv[15] = (m[8] * s3 - m[9] * s1 + m[10] * s0) * id;
+}
+
+void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar, uint32_t frame,
+                        uint32_t depth_max, brt_uniform* out) {
+  // Camera::updateView (Graphics/Camera.cpp:71-95): Tait-Bryan Y(yaw = rot.y) - X(rot.x) - Z(rot.z), rows u, v, w
+  const float c3 = std::cos(rot[2]), s3 = std::sin(rot[2]);
+  const float c2 = std::cos(rot[0]), s2 = std::sin(rot[0]);
+  const float c1 = std::cos(rot[1]), s1 = std::sin(rot[1]);
+  const float ux = c1 * c3 + s1 * s2 * s3, uy = c2 * s3, uz = c1 * s2 * s3 - c3 * s1;
+  const float vx = c3 * s1 * s2 - c1 * s3, vy = c2 * c3, vz = c1 * c3 * s2 + s1 * s3;
+  const float wx = c2 * s1, wy = -s2, wz = c1 * c2;
+  const float tu = -(ux * pos[0] + uy * pos[1] + uz * pos[2]);
+  const float tv = -(vx * pos[0] + vy * pos[1] + vz * pos[2]);
+  const float tw = -(wx * pos[0] + wy * pos[1] + wz * pos[2]);
+  const double view[16] = {ux, uy, uz, tu, vx, vy, vz, tv, wx, wy, wz, tw, 0, 0, 0, 1};
+  // Camera::setPerspectiveProjection (Graphics/Camera.cpp:8-17)
+  const float t = std::tan(fovy / 2.0f);
+  double proj[16] = {0};
+  proj[0] = 1.0f / (aspect * t);
+  proj[5] = 1.0f / t;
+  proj[10] = zfar / (zfar - znear);
+  proj[14] = 1.0f;
+  proj[11] = -(zfar * znear) / (zfar - znear);
+  // RTApp::run (RT/RTApp.cpp:44-49): glm::inverse(glm::transpose(M)) in column-major memory is M^-1 in row-major memory
+  double vi[16], pi[16];
+  invert4x4(view, vi);
+  invert4x4(proj, pi);
+  for (int i = 0; i < 16; ++i) {
+    out->viewInverse[i] = (float)(vi[i] + 0.0);  // + 0.0: no negative zeros
+    out->projInverse[i] = (float)(pi[i] + 0.0);
+  }
+  out->frame = frame;
+  out->depthMax = depth_max;
+  out->lightThreshold = 0.0001f;
+}
+
+}  // extern "C"

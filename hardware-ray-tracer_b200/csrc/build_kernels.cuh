@@ -1,0 +1,437 @@
+// GPU BVH builder, replacing vkCmdBuildAccelerationStructuresKHR (RT/Scene.cpp:163-174,176-255,
+// 256-311; the driver's builder has no source in the reference) and filling the LBVH placeholder
+// of Scene::prepareRendering (RT/Scene.cpp:135-138).
+//
+// Pipeline (one launch each, no host synchronisation in between):
+//   prim_bounds  : primitive AABBs (+ exact mesh bounds via warp-reduced atomics)
+//   morton       : 30-bit Morton code of the AABB centre inside the centroid... scene bounds
+//   radix sort   : (code, primitive) pairs                                  (radix_sort.cuh)
+//   hierarchy    : Karras 2012 — one thread per internal node, binary radix tree over the sorted codes
+//   refit        : bottom-up AABBs + subtree primitive counts, atomic arrival counters
+//   treelet      : SAH treelet restructuring (treelet.cuh, optional)
+//   collapse     : level-synchronous conversion into the compressed 8-wide layout of device_types.cuh
+#pragma once
+#include "device_types.cuh"
+#include "vecmath.cuh"
+
+namespace brt {
+
+// scratch words shared by the build kernels of one BVH
+struct BuildGlobals {
+  uint32_t bounds[6];        // ordered-uint min xyz / max xyz of the padded primitive boxes
+  uint32_t exact[6];         // ordered-uint min xyz / max xyz of the exact primitive boxes (mesh bounds)
+  uint32_t node_count;       // 8-wide nodes allocated so far
+  uint32_t prim_count;       // primitive records allocated so far
+  uint32_t levels;           // number of collapse levels that had work
+  uint32_t overflow;         // set when a capacity was exceeded
+  uint32_t level_count[64];  // work items per collapse level
+  float sah_binary;          // SAH cost of the binary tree (filled by sah_cost kernel)
+  uint32_t pad[3];
+};
+
+// ---- warp-aggregated float min/max into ordered uints -------------------------------------------------
+BRT_HD void reduce_bounds(uint32_t* dst, f3 lo, f3 hi) {
+  uint32_t l[3] = {float_to_ordered(lo.x), float_to_ordered(lo.y), float_to_ordered(lo.z)};
+  uint32_t h[3] = {float_to_ordered(hi.x), float_to_ordered(hi.y), float_to_ordered(hi.z)};
+#ifdef BRT_EMU
+  for (int k = 0; k < 3; ++k) {
+    atomic_min(dst + k, l[k]);
+    atomic_max(dst + 3 + k, h[k]);
+  }
+#else
+  const unsigned mask = __activemask();
+  const int leader = __ffs(mask) - 1;
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < 3; ++k) {
+    uint32_t a = __reduce_min_sync(mask, l[k]);
+    uint32_t b = __reduce_max_sync(mask, h[k]);
+    if (lane == leader) {
+      atomicMin(dst + k, a);
+      atomicMax(dst + 3 + k, b);
+    }
+  }
+#endif
+}
+
+// Every primitive box is padded by 2^-20 of its largest coordinate magnitude so that a primitive
+// test that accepts a ray passing a few ulps outside the exact geometry is never culled by a box.
+BRT_HD void pad_box(f3& lo, f3& hi) {
+  float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+  float e = fmaxf(m * 9.5367431640625e-07f, 1e-30f);
+  lo = F3(lo.x - e, lo.y - e, lo.z - e);
+  hi = F3(hi.x + e, hi.y + e, hi.z + e);
+}
+
+// ---- primitive bounds: triangles ---------------------------------------------------------------------
+struct TriBoundsParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const float* vertices;    // stride 8 floats (brt_vertex)
+  const uint32_t* indices;  // 3 per triangle
+  float4* prim_lo;          // xyz = padded min, w = unused
+  float4* prim_hi;
+  BuildGlobals* g;
+};
+BRT_HD void tri_bounds_body(const TriBoundsParams& p, uint32_t i) {
+  const uint32_t i0 = p.indices[3 * i], i1 = p.indices[3 * i + 1], i2 = p.indices[3 * i + 2];
+  const f3 a = F3(p.vertices[8 * (size_t)i0], p.vertices[8 * (size_t)i0 + 1], p.vertices[8 * (size_t)i0 + 2]);
+  const f3 b = F3(p.vertices[8 * (size_t)i1], p.vertices[8 * (size_t)i1 + 1], p.vertices[8 * (size_t)i1 + 2]);
+  const f3 c = F3(p.vertices[8 * (size_t)i2], p.vertices[8 * (size_t)i2 + 1], p.vertices[8 * (size_t)i2 + 2]);
+  f3 lo = fmin3(fmin3(a, b), c), hi = fmax3(fmax3(a, b), c);
+  reduce_bounds(p.g->exact, lo, hi);
+  pad_box(lo, hi);
+  reduce_bounds(p.g->bounds, lo, hi);
+  p.prim_lo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+  p.prim_hi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+}
+
+// ---- primitive bounds: instances (TLAS) ---------------------------------------------------------------
+// world box of an instance = |M| applied to the mesh box in centre/extent form
+struct InstBoundsParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const InstShade* shade;     // indexed by instance id
+  const uint32_t* inst_ids;   // TLAS primitive -> instance id
+  const float4* mesh_bounds;  // 2 per mesh: exact lo, hi
+  float4* prim_lo;
+  float4* prim_hi;
+  BuildGlobals* g;
+};
+BRT_HD void inst_bounds_body(const InstBoundsParams& p, uint32_t i) {
+  const InstShade& s = p.shade[p.inst_ids[i]];
+  f3 lo, hi;
+  instance_world_box(s.o2w, xyz(p.mesh_bounds[2 * s.mesh]), xyz(p.mesh_bounds[2 * s.mesh + 1]), lo, hi);
+  // the transform itself rounds: pad generously relative to the box magnitude
+  pad_box(lo, hi);
+  pad_box(lo, hi);
+  reduce_bounds(p.g->bounds, lo, hi);
+  p.prim_lo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+  p.prim_hi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+}
+
+// ---- Morton codes ------------------------------------------------------------------------------------
+BRT_HD uint32_t expand_bits10(uint32_t v) {  // 10 bits -> every third bit
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+struct MortonParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const float4* prim_lo;
+  const float4* prim_hi;
+  const BuildGlobals* g;
+  uint32_t* keys;
+  uint32_t* vals;
+};
+BRT_HD void morton_body(const MortonParams& p, uint32_t i) {
+  const f3 blo = F3(ordered_to_float(p.g->bounds[0]), ordered_to_float(p.g->bounds[1]), ordered_to_float(p.g->bounds[2]));
+  const f3 bhi = F3(ordered_to_float(p.g->bounds[3]), ordered_to_float(p.g->bounds[4]), ordered_to_float(p.g->bounds[5]));
+  const f3 c = (xyz(p.prim_lo[i]) + xyz(p.prim_hi[i])) * 0.5f;
+  const f3 ext = bhi - blo;
+  const float fx = ext.x > 0.0f ? (c.x - blo.x) / ext.x : 0.0f;
+  const float fy = ext.y > 0.0f ? (c.y - blo.y) / ext.y : 0.0f;
+  const float fz = ext.z > 0.0f ? (c.z - blo.z) / ext.z : 0.0f;
+  const uint32_t x = (uint32_t)fminf(fmaxf(fx * 1024.0f, 0.0f), 1023.0f);
+  const uint32_t y = (uint32_t)fminf(fmaxf(fy * 1024.0f, 0.0f), 1023.0f);
+  const uint32_t z = (uint32_t)fminf(fmaxf(fz * 1024.0f, 0.0f), 1023.0f);
+  p.keys[i] = (expand_bits10(x) << 2) | (expand_bits10(y) << 1) | expand_bits10(z);
+  p.vals[i] = i;
+}
+
+// ---- Karras hierarchy --------------------------------------------------------------------------------
+struct HierarchyParams {
+  uint32_t count;  // number of internal nodes = n - 1
+  const uint32_t* count_ptr;
+  uint32_t n;      // primitives
+  const uint32_t* keys;  // sorted
+  BNode* nodes;          // 2n-1
+  uint32_t* parent;      // 2n-1
+};
+BRT_HD int lcp(const uint32_t* keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint32_t a = keys[i], b = keys[j];
+  return a != b ? clz32(a ^ b) : 32 + clz32((uint32_t)i ^ (uint32_t)j);
+}
+BRT_HD void hierarchy_body(const HierarchyParams& p, uint32_t ui) {
+  const int n = (int)p.n, i = (int)ui;
+  const int d = (lcp(p.keys, n, i, i + 1) - lcp(p.keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = lcp(p.keys, n, i, i - d);
+  int lmax = 2;
+  while (lcp(p.keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (lcp(p.keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lcp(p.keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) / 2;
+    if (lcp(p.keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + (d < 0 ? -1 : 0);
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  const uint32_t n_int = p.n - 1;
+  const uint32_t left = lo == gamma ? n_int + (uint32_t)gamma : (uint32_t)gamma;
+  const uint32_t right = hi == gamma + 1 ? n_int + (uint32_t)(gamma + 1) : (uint32_t)(gamma + 1);
+  p.nodes[i].lo.w = u2f(left);
+  p.nodes[i].hi.w = u2f(right);
+  p.parent[left] = ui;
+  p.parent[right] = ui;
+  if (i == 0) p.parent[0] = BRT_MISS;
+}
+
+// ---- bottom-up refit ---------------------------------------------------------------------------------
+struct RefitParams {
+  uint32_t count;  // n leaves
+  const uint32_t* count_ptr;
+  const uint32_t* vals;  // sorted position -> primitive
+  const float4* prim_lo;
+  const float4* prim_hi;
+  BNode* nodes;
+  const uint32_t* parent;
+  uint32_t* arrive;     // n-1, zeroed
+  uint32_t* sub_count;  // 2n-1: primitives below each node
+};
+BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
+  const uint32_t n_int = p.count - 1;
+  const uint32_t prim = p.vals[i];
+  float4 lo = p.prim_lo[prim], hi = p.prim_hi[prim];
+  lo.w = u2f(prim);
+  hi.w = u2f(BRT_MISS);
+  p.nodes[n_int + i].lo = lo;
+  p.nodes[n_int + i].hi = hi;
+  p.sub_count[n_int + i] = 1;
+  uint32_t cur = n_int + i;
+  for (;;) {
+    const uint32_t par = p.parent[cur];
+    if (par == BRT_MISS) break;
+    fence();
+    if (atomic_add(&p.arrive[par], 1u) == 0u) break;  // the sibling subtree is not finished yet
+    fence();
+    volatile BNode* nd = p.nodes + par;
+    const uint32_t l = f2u(nd->lo.w), r = f2u(nd->hi.w);
+    volatile const BNode* a = p.nodes + l;
+    volatile const BNode* b = p.nodes + r;
+    nd->lo.x = fminf(a->lo.x, b->lo.x);
+    nd->lo.y = fminf(a->lo.y, b->lo.y);
+    nd->lo.z = fminf(a->lo.z, b->lo.z);
+    nd->hi.x = fmaxf(a->hi.x, b->hi.x);
+    nd->hi.y = fmaxf(a->hi.y, b->hi.y);
+    nd->hi.z = fmaxf(a->hi.z, b->hi.z);
+    volatile uint32_t* sc = p.sub_count;
+    sc[par] = sc[l] + sc[r];
+    cur = par;
+  }
+}
+
+// ---- SAH cost of the binary tree (statistics only) ----------------------------------------------------
+BRT_HD float box_area(f3 lo, f3 hi) {
+  const f3 e = hi - lo;
+  return 2.0f * ((e.x * e.y + e.y * e.z) + e.z * e.x);
+}
+
+// ---- collapse to the compressed 8-wide layout ----------------------------------------------------------
+struct CollapseParams {
+  uint32_t count;
+  const uint32_t* count_ptr;  // = &g->level_count[level]
+  uint32_t level;
+  uint32_t n;                 // primitives
+  uint32_t max_leaf;          // 3 for triangles, 1 for instances
+  const BNode* nodes;
+  const uint32_t* sub_count;
+  const uint2* queue_in;      // (binary node id, wide node index)
+  uint2* queue_out;
+  uint32_t queue_cap;
+  BuildGlobals* g;
+  Node8* out_nodes;
+  uint32_t node_cap;
+  // leaf payload: triangles
+  const float* vertices;
+  const uint32_t* indices;
+  TriRec* out_tris;
+  // leaf payload: instances
+  const InstRec* src_inst;  // indexed by TLAS primitive
+  InstRec* out_inst;
+};
+
+BRT_HD void emit_prim(const CollapseParams& p, uint32_t prim, uint32_t dst) {
+  if (p.out_tris) {
+    const uint32_t i0 = p.indices[3 * (size_t)prim], i1 = p.indices[3 * (size_t)prim + 1], i2 = p.indices[3 * (size_t)prim + 2];
+    TriRec r;
+    r.v0 = make_float4(p.vertices[8 * (size_t)i0], p.vertices[8 * (size_t)i0 + 1], p.vertices[8 * (size_t)i0 + 2], u2f(prim));
+    r.v1 = make_float4(p.vertices[8 * (size_t)i1], p.vertices[8 * (size_t)i1 + 1], p.vertices[8 * (size_t)i1 + 2], 0.0f);
+    r.v2 = make_float4(p.vertices[8 * (size_t)i2], p.vertices[8 * (size_t)i2 + 1], p.vertices[8 * (size_t)i2 + 2], 0.0f);
+    p.out_tris[dst] = r;
+  } else {
+    p.out_inst[dst] = p.src_inst[prim];
+  }
+}
+
+// smallest biased exponent e such that the 8-bit grid p + [0,255] * 2^(e-127) reaches `hi`
+BRT_HD uint32_t grid_exponent(float p, float hi) {
+  const float extent = hi - p;
+  uint32_t e = 1u;
+  if (extent > 0.0f) {
+    const float step = extent / 255.0f;
+    e = ((f2u(step) >> 23) & 0xffu) + 1u;  // floor(log2(step)) + 1
+    if (e < 1u) e = 1u;
+    if (e > 254u) e = 254u;
+    while (e < 254u && add_rd(p, 255.0f * u2f(e << 23)) < hi) e++;  // rounding of extent / step
+  }
+  return e;
+}
+// largest q in [0,255] with p + q*s <= v, evaluated with the same rounding the traversal may see
+BRT_HD uint32_t quant_lo(float p, float s, float v) {
+  float q = floorf((v - p) / s);
+  q = fminf(fmaxf(q, 0.0f), 255.0f);
+  while (q > 0.0f && add_ru(p, q * s) > v) q -= 1.0f;
+  return (uint32_t)q;
+}
+BRT_HD uint32_t quant_hi(float p, float s, float v) {
+  float q = ceilf((v - p) / s);
+  q = fminf(fmaxf(q, 0.0f), 255.0f);
+  while (q < 255.0f && add_rd(p, q * s) < v) q += 1.0f;
+  return (uint32_t)q;
+}
+
+BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
+  const uint2 work = p.queue_in[item];
+  const uint32_t n_int = p.n - 1;
+  uint32_t ch[8];
+  float area[8];  // < 0: not expandable (becomes a leaf slot)
+  int n = 1;
+  ch[0] = work.x;
+  {
+    const bool expandable = work.x < n_int && p.sub_count[work.x] > p.max_leaf;
+    area[0] = expandable ? 1.0f : -1.0f;
+  }
+  // greedy: always open the expandable child with the largest surface area
+  while (n < 8) {
+    int best = -1;
+    float ba = 0.0f;
+    for (int k = 0; k < n; ++k)
+      if (area[k] >= 0.0f && (best < 0 || area[k] > ba)) { best = k; ba = area[k]; }
+    if (best < 0) break;
+    const BNode nd = p.nodes[ch[best]];
+    const uint32_t c2[2] = {f2u(nd.lo.w), f2u(nd.hi.w)};
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t c = c2[s];
+      const int dst = s == 0 ? best : n;
+      ch[dst] = c;
+      if (c < n_int && p.sub_count[c] > p.max_leaf) {
+        const BNode cn = p.nodes[c];
+        area[dst] = box_area(xyz(cn.lo), xyz(cn.hi));
+      } else {
+        area[dst] = -1.0f;
+      }
+    }
+    n++;
+  }
+  // child boxes, node box
+  f3 clo[8], chi[8];
+  f3 nlo = F3(INFINITY), nhi = F3(-INFINITY);
+  for (int k = 0; k < n; ++k) {
+    const BNode cn = p.nodes[ch[k]];
+    clo[k] = xyz(cn.lo);
+    chi[k] = xyz(cn.hi);
+    nlo = fmin3(nlo, clo[k]);
+    nhi = fmax3(nhi, chi[k]);
+  }
+  // octant-ordered slot assignment: greedily give each (child, slot) pair with the highest
+  // projection of the child's offset onto the slot's diagonal
+  const f3 nc = (nlo + nhi) * 0.5f;
+  int slot_of[8];
+  int child_in[8];
+  for (int k = 0; k < 8; ++k) { slot_of[k] = -1; child_in[k] = -1; }
+  for (int round = 0; round < n; ++round) {
+    float bs = -INFINITY;
+    int bk = -1, bsl = -1;
+    for (int k = 0; k < n; ++k) {
+      if (slot_of[k] >= 0) continue;
+      const f3 off = (clo[k] + chi[k]) * 0.5f - nc;
+      for (int s = 0; s < 8; ++s) {
+        if (child_in[s] >= 0) continue;
+        const float sc = ((s & 1) ? off.x : -off.x) + ((s & 2) ? off.y : -off.y) + ((s & 4) ? off.z : -off.z);
+        if (sc > bs) { bs = sc; bk = k; bsl = s; }
+      }
+    }
+    if (bk < 0) {  // NaN boxes: fall back to first free
+      for (int k = 0; k < n && bk < 0; ++k) if (slot_of[k] < 0) bk = k;
+      for (int s = 0; s < 8 && bsl < 0; ++s) if (child_in[s] < 0) bsl = s;
+    }
+    slot_of[bk] = bsl;
+    child_in[bsl] = bk;
+  }
+  // allocation
+  uint32_t n_inner = 0, n_prims = 0;
+  for (int s = 0; s < 8; ++s) {
+    const int k = child_in[s];
+    if (k < 0) continue;
+    if (area[k] >= 0.0f) n_inner++;
+    else n_prims += p.sub_count[ch[k]];
+  }
+  uint32_t child_base = 0, prim_base = 0;
+  if (n_inner) child_base = atomic_add(&p.g->node_count, n_inner);
+  if (n_prims) prim_base = atomic_add(&p.g->prim_count, n_prims);
+  uint32_t queue_base = 0;
+  if (n_inner) {
+    queue_base = atomic_add(&p.g->level_count[p.level + 1], n_inner);
+    if (child_base + n_inner > p.node_cap || queue_base + n_inner > p.queue_cap) {
+      p.g->overflow = 1u;
+      n_inner = 0;  // drop the subtree rather than write out of bounds; the host reports the error
+    }
+  }
+  // grid
+  const uint32_t ex = grid_exponent(nlo.x, nhi.x), ey = grid_exponent(nlo.y, nhi.y), ez = grid_exponent(nlo.z, nhi.z);
+  const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+  uint32_t meta[8], qlx[8], qly[8], qlz[8], qhx[8], qhy[8], qhz[8];
+  uint32_t imask = 0, inner_i = 0, prim_off = 0;
+  for (int s = 0; s < 8; ++s) {
+    meta[s] = 0; qlx[s] = qly[s] = qlz[s] = 255u; qhx[s] = qhy[s] = qhz[s] = 0u;
+    const int k = child_in[s];
+    if (k < 0) continue;
+    if (area[k] >= 0.0f) {
+      if (n_inner == 0) continue;  // overflow: slot left empty
+      imask |= 1u << s;
+      meta[s] = (1u << 5) | (24u + (uint32_t)s);
+      p.queue_out[queue_base + inner_i] = make_uint2(ch[k], child_base + inner_i);
+      inner_i++;
+    } else {
+      // enumerate the (<= max_leaf) primitives of this small subtree
+      const uint32_t cnt = p.sub_count[ch[k]];
+      uint32_t st[4];
+      int sp = 0;
+      st[sp++] = ch[k];
+      uint32_t w = 0;
+      while (sp) {
+        const uint32_t id = st[--sp];
+        const BNode bn = p.nodes[id];
+        if (id >= n_int) {
+          emit_prim(p, f2u(bn.lo.w), prim_base + prim_off + w);
+          w++;
+        } else {
+          st[sp++] = f2u(bn.hi.w);
+          st[sp++] = f2u(bn.lo.w);
+        }
+      }
+      meta[s] = (((1u << cnt) - 1u) << 5) | prim_off;
+      prim_off += cnt;
+    }
+    qlx[s] = quant_lo(nlo.x, sx, clo[k].x); qly[s] = quant_lo(nlo.y, sy, clo[k].y); qlz[s] = quant_lo(nlo.z, sz, clo[k].z);
+    qhx[s] = quant_hi(nlo.x, sx, chi[k].x); qhy[s] = quant_hi(nlo.y, sy, chi[k].y); qhz[s] = quant_hi(nlo.z, sz, chi[k].z);
+  }
+  auto pack4 = [](const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+  Node8 out;
+  out.q[0] = make_uint4(f2u(nlo.x), f2u(nlo.y), f2u(nlo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
+  out.q[1] = make_uint4(child_base, prim_base, pack4(meta), pack4(meta + 4));
+  out.q[2] = make_uint4(pack4(qlx), pack4(qlx + 4), pack4(qly), pack4(qly + 4));
+  out.q[3] = make_uint4(pack4(qlz), pack4(qlz + 4), pack4(qhx), pack4(qhx + 4));
+  out.q[4] = make_uint4(pack4(qhy), pack4(qhy + 4), pack4(qhz), pack4(qhz + 4));
+  if (work.y < p.node_cap) p.out_nodes[work.y] = out;
+  if (item == 0) atomic_max(&p.g->levels, p.level + 1u);
+}
+
+}  // namespace brt

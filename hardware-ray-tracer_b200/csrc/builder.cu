@@ -1,0 +1,216 @@
+// Host orchestration of the GPU BVH builder (kernels in build_kernels.cuh, radix_sort.cuh, treelet.cuh).
+#include "builder.h"
+
+#include <algorithm>
+#include <vector>
+
+#include "build_kernels.cuh"
+#include "radix_sort.cuh"
+#include "treelet.cuh"
+
+namespace brt {
+
+BRT_KERNEL_1D(k_tri_bounds, TriBoundsParams, tri_bounds_body)
+BRT_KERNEL_1D(k_inst_bounds, InstBoundsParams, inst_bounds_body)
+BRT_KERNEL_1D(k_morton, MortonParams, morton_body)
+BRT_KERNEL_1D(k_hierarchy, HierarchyParams, hierarchy_body)
+BRT_KERNEL_1D(k_refit, RefitParams, refit_body)
+BRT_KERNEL_1D(k_collapse, CollapseParams, collapse_body)
+BRT_KERNEL_1D(k_sah_cost, SahParams, sah_cost_body)
+BRT_KERNEL_1D(k_treelet, TreeletParams, treelet_body)
+
+struct InitGlobalsParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  BuildGlobals* g;
+  uint32_t root;  // binary root id pushed as the first collapse work item
+  uint2* queue0;
+};
+BRT_HD void init_globals_body(const InitGlobalsParams& p, uint32_t) {
+  BuildGlobals& g = *p.g;
+  for (int k = 0; k < 3; ++k) {
+    g.bounds[k] = 0xffffffffu; g.bounds[3 + k] = 0u;
+    g.exact[k] = 0xffffffffu; g.exact[3 + k] = 0u;
+  }
+  g.node_count = 1u;  // the root
+  g.prim_count = 0u;
+  g.levels = 0u;
+  g.overflow = 0u;
+  for (int k = 0; k < 64; ++k) g.level_count[k] = 0u;
+  g.level_count[0] = 1u;
+  g.sah_binary = 0.0f;
+  p.queue0[0] = make_uint2(p.root, 0u);
+}
+BRT_KERNEL_1D(k_init_globals, InitGlobalsParams, init_globals_body)
+
+struct MeshBoundsParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const BuildGlobals* g;
+  float4* out;  // lo, hi
+};
+BRT_HD void mesh_bounds_body(const MeshBoundsParams& p, uint32_t) {
+  p.out[0] = make_float4(ordered_to_float(p.g->exact[0]), ordered_to_float(p.g->exact[1]), ordered_to_float(p.g->exact[2]), 0.0f);
+  p.out[1] = make_float4(ordered_to_float(p.g->exact[3]), ordered_to_float(p.g->exact[4]), ordered_to_float(p.g->exact[5]), 0.0f);
+}
+BRT_KERNEL_1D(k_mesh_bounds, MeshBoundsParams, mesh_bounds_body)
+
+void Builder::ensure_scratch(uint32_t n) {
+  const size_t N = n;
+  globals_.ensure(sizeof(BuildGlobals));
+  prim_lo_.ensure(N * 16);
+  prim_hi_.ensure(N * 16);
+  for (int k = 0; k < 2; ++k) {
+    keys_[k].ensure(N * 4);
+    vals_[k].ensure(N * 4);
+    queue_[k].ensure((N / 2 + 8) * 8);
+  }
+  sort_tmp_.ensure(radix_sort_temp_bytes(n));
+  nodes_.ensure((2 * N) * sizeof(BNode));
+  parent_.ensure(2 * N * 4);
+  arrive_.ensure(N * 4);
+  sub_count_.ensure(2 * N * 4);
+  treelet_.ensure(N * 4 + 16);
+}
+
+void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treelets, Node8* out_nodes, const float* d_vertices,
+                  const uint32_t* d_indices, TriRec* out_tris, const InstRec* d_src, InstRec* out_inst, float4* d_mesh_bounds,
+                  BuildResult* res) {
+  // prim_lo_/prim_hi_ and globals_->bounds have been filled by the caller
+  BuildGlobals* g = globals_.as<BuildGlobals>();
+  const uint32_t grid_n = std::max(1u, std::min(div_up(n, 256u), (uint32_t)sm_count_ * 8u));
+  {
+    MortonParams p{n, nullptr, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g, keys_[0].as<uint32_t>(), vals_[0].as<uint32_t>()};
+    BRT_LAUNCH_1D(k_morton, p, grid_n, 256, stream);
+    BRT_CHECK_LAUNCH();
+  }
+  uint32_t* keys = keys_[0].as<uint32_t>();
+  uint32_t* vals = vals_[0].as<uint32_t>();
+  if (n > 1) {
+    int out = radix_sort_pairs(stream, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(), vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), n,
+                               30, sort_tmp_.ptr(), sort_tmp_.capacity(), sm_count_);
+    keys = keys_[out].as<uint32_t>();
+    vals = vals_[out].as<uint32_t>();
+  }
+  BNode* nodes = nodes_.as<BNode>();
+  uint32_t* parent = parent_.as<uint32_t>();
+  uint32_t* sub_count = sub_count_.as<uint32_t>();
+  BRT_CUDA(cudaMemsetAsync(parent, 0xff, (size_t)(2 * n) * 4, stream));
+  if (n > 1) {
+    BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
+    HierarchyParams p{n - 1, nullptr, n, keys, nodes, parent};
+    BRT_LAUNCH_1D(k_hierarchy, p, grid_n, 256, stream);
+    BRT_CHECK_LAUNCH();
+  }
+  {
+    RefitParams p{n, nullptr, vals, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes, parent, arrive_.as<uint32_t>(), sub_count};
+    BRT_LAUNCH_1D(k_refit, p, grid_n, 256, stream);
+    BRT_CHECK_LAUNCH();
+  }
+  float* d_sah = &g->sah_binary;
+  float sah_before = 0.0f;
+  const bool want_sah = out_tris != nullptr && n > 1;
+  if (want_sah) {
+    SahParams p{n - 1, nullptr, n, nodes, sub_count, max_leaf, d_sah};
+    BRT_LAUNCH_1D(k_sah_cost, p, grid_n, 256, stream);
+    BRT_CHECK_LAUNCH();
+  }
+  if (treelets && n > 16 && out_tris != nullptr) {
+    if (want_sah) {
+      BRT_CUDA(cudaMemcpyAsync(&sah_before, d_sah, 4, cudaMemcpyDeviceToHost, stream));
+      BRT_CUDA(cudaMemsetAsync(d_sah, 0, 4, stream));
+    }
+    run_treelet_passes(stream, n, nodes, parent, sub_count, arrive_.as<uint32_t>(), treelet_.as<uint32_t>(), max_leaf, sm_count_);
+    if (want_sah) {
+      SahParams p{n - 1, nullptr, n, nodes, sub_count, max_leaf, d_sah};
+      BRT_LAUNCH_1D(k_sah_cost, p, grid_n, 256, stream);
+      BRT_CHECK_LAUNCH();
+    }
+  }
+  // collapse, level by level; the per-level work count lives on the device
+  const uint32_t node_cap = node_capacity(n);
+  const uint32_t queue_cap = n / 2 + 8;
+  CollapseParams cp{};
+  cp.n = n;
+  cp.max_leaf = max_leaf;
+  cp.nodes = nodes;
+  cp.sub_count = sub_count;
+  cp.queue_cap = queue_cap;
+  cp.g = g;
+  cp.out_nodes = out_nodes;
+  cp.node_cap = node_cap;
+  cp.vertices = d_vertices;
+  cp.indices = d_indices;
+  cp.out_tris = out_tris;
+  cp.src_inst = d_src;
+  cp.out_inst = out_inst;
+  BuildGlobals hg;
+  uint32_t level = 0;
+  for (;;) {
+    const uint32_t chunk_end = level + 8;
+    for (; level < chunk_end && level < 62; ++level) {
+      cp.level = level;
+      cp.count = 0;
+      cp.count_ptr = &g->level_count[level];
+      cp.queue_in = queue_[level & 1].as<uint2>();
+      cp.queue_out = queue_[(level + 1) & 1].as<uint2>();
+      // level L has at most min(8^L, queue_cap) items
+      uint64_t max_items = 1;
+      for (uint32_t k = 0; k < level && max_items < queue_cap; ++k) max_items *= 8;
+      max_items = std::min<uint64_t>(max_items, queue_cap);
+      const uint32_t grid = std::max(1u, std::min(div_up((uint32_t)max_items, 64u), (uint32_t)sm_count_ * 16u));
+      BRT_LAUNCH_1D(k_collapse, cp, grid, 64, stream);
+      BRT_CHECK_LAUNCH();
+    }
+    BRT_CUDA(cudaMemcpyAsync(&hg, g, sizeof(hg), cudaMemcpyDeviceToHost, stream));
+    BRT_CUDA(cudaStreamSynchronize(stream));
+    if (level >= 62 || hg.level_count[level] == 0) break;
+  }
+  if (d_mesh_bounds) {
+    MeshBoundsParams p{1, nullptr, g, d_mesh_bounds};
+    BRT_LAUNCH_1D(k_mesh_bounds, p, 1, 32, stream);
+    BRT_CHECK_LAUNCH();
+  }
+  if (hg.overflow) throw LimitError("BVH build: node or queue capacity exceeded");
+  if (hg.level_count[level] != 0) throw LimitError("BVH build: hierarchy deeper than 62 levels");
+  res->n_prims = n;
+  res->n_nodes = hg.node_count;
+  res->levels = hg.levels;
+  res->sah_final = hg.sah_binary;
+  res->sah_lbvh = (treelets && n > 16 && want_sah) ? sah_before : hg.sah_binary;
+  for (int k = 0; k < 3; ++k) {
+    res->lo[k] = ordered_to_float(hg.exact[k]);
+    res->hi[k] = ordered_to_float(hg.exact[3 + k]);
+  }
+}
+
+void Builder::build_triangles(cudaStream_t stream, const float* d_vertices, const uint32_t* d_indices, uint32_t n_tris, Node8* out_nodes,
+                              TriRec* out_tris, float4* d_mesh_bounds, bool treelets, BuildResult* res) {
+  ensure_scratch(n_tris);
+  BuildGlobals* g = globals_.as<BuildGlobals>();
+  const uint32_t root = n_tris > 1 ? 0u : 0u;  // internal node 0, or leaf id 0 when n == 1 (n_internal == 0)
+  InitGlobalsParams ip{1, nullptr, g, root, queue_[0].as<uint2>()};
+  BRT_LAUNCH_1D(k_init_globals, ip, 1, 32, stream);
+  BRT_CHECK_LAUNCH();
+  const uint32_t grid_n = std::max(1u, std::min(div_up(n_tris, 256u), (uint32_t)sm_count_ * 8u));
+  TriBoundsParams p{n_tris, nullptr, d_vertices, d_indices, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g};
+  BRT_LAUNCH_1D(k_tri_bounds, p, grid_n, 256, stream);
+  BRT_CHECK_LAUNCH();
+  run(stream, n_tris, 3, treelets, out_nodes, d_vertices, d_indices, out_tris, nullptr, nullptr, d_mesh_bounds, res);
+}
+
+void Builder::build_instances(cudaStream_t stream, const InstShade* d_shade, const uint32_t* d_inst_ids, const InstRec* d_src, uint32_t n,
+                              const float4* d_mesh_bounds, Node8* out_nodes, InstRec* out_inst, BuildResult* res) {
+  ensure_scratch(n);
+  BuildGlobals* g = globals_.as<BuildGlobals>();
+  InitGlobalsParams ip{1, nullptr, g, 0u, queue_[0].as<uint2>()};
+  BRT_LAUNCH_1D(k_init_globals, ip, 1, 32, stream);
+  BRT_CHECK_LAUNCH();
+  const uint32_t grid_n = std::max(1u, std::min(div_up(n, 256u), (uint32_t)sm_count_ * 8u));
+  InstBoundsParams p{n, nullptr, d_shade, d_inst_ids, d_mesh_bounds, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g};
+  BRT_LAUNCH_1D(k_inst_bounds, p, grid_n, 256, stream);
+  BRT_CHECK_LAUNCH();
+  run(stream, n, 1, false, out_nodes, nullptr, nullptr, nullptr, d_src, out_inst, nullptr, res);
+}
+
+}  // namespace brt

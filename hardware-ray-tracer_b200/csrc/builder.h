@@ -1,0 +1,39 @@
+// Host interface of the GPU BVH builder (builder.cu).
+#pragma once
+#include "device_types.cuh"
+#include "host_util.h"
+
+namespace brt {
+
+struct BuildResult {
+  uint32_t n_prims = 0;
+  uint32_t n_nodes = 0;    // 8-wide nodes written
+  uint32_t levels = 0;     // depth of the 8-wide tree
+  float sah_lbvh = 0.0f;   // SAH cost of the binary tree before / after treelet restructuring
+  float sah_final = 0.0f;
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // exact bounds of the primitives (triangle builds)
+};
+
+class Builder {
+ public:
+  explicit Builder(int sm_count) : sm_count_(sm_count) {}
+  // BLAS over an indexed triangle mesh (brt_vertex stride). out_nodes must hold node_capacity(n_tris)
+  // nodes, out_tris n_tris records. d_mesh_bounds (2 x float4, may be null) receives the exact mesh box.
+  // Synchronises `stream` once at the end to read the result back.
+  void build_triangles(cudaStream_t stream, const float* d_vertices, const uint32_t* d_indices, uint32_t n_tris, Node8* out_nodes,
+                       TriRec* out_tris, float4* d_mesh_bounds, bool treelets, BuildResult* res);
+  // TLAS over instances: primitive k is instance d_inst_ids[k], its traversal record is d_src[k].
+  void build_instances(cudaStream_t stream, const InstShade* d_shade, const uint32_t* d_inst_ids, const InstRec* d_src, uint32_t n,
+                       const float4* d_mesh_bounds, Node8* out_nodes, InstRec* out_inst, BuildResult* res);
+  static uint32_t node_capacity(uint32_t n_prims) { return n_prims < 8 ? 8 : n_prims; }
+
+ private:
+  void run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treelets, Node8* out_nodes, const float* d_vertices,
+           const uint32_t* d_indices, TriRec* out_tris, const InstRec* d_src, InstRec* out_inst, float4* d_mesh_bounds, BuildResult* res);
+  void ensure_scratch(uint32_t n);
+  int sm_count_;
+  DevBuf globals_, prim_lo_, prim_hi_, keys_[2], vals_[2], sort_tmp_, nodes_, parent_, arrive_, sub_count_, queue_[2], treelet_;
+  friend struct BuilderAccess;
+};
+
+}  // namespace brt

@@ -1,0 +1,419 @@
+// Wavefront restatement of the reference's shader pipeline (SH/ = reference shaders/):
+//   raygen      rgenMain prologue                      SH/raytracing.slang:92-112
+//   trace       TraceRay closest / occlusion           SH/raytracing.slang:121 / :67   (traverse.cuh)
+//   shade       rchitMain + calculateColor + rmissMain SH/raytracing.slang:135-176, :72-88, light.slang:23-39
+//   accumulate  `c += payload.color * weight`          SH/raytracing.slang:122
+//   resolve     `outImage = float4(c / SAMPLES, 1)`    SH/raytracing.slang:129-132
+// One path per pixel per sample; the per-pixel loop `while (depth < depthMax)` (:119-126) becomes one
+// trace/shade/occlude/accumulate round per depth over a compacted queue of live paths.
+#pragma once
+#include "../../include/brt.h"
+#include "device_types.cuh"
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace brt {
+
+struct PathQueue {  // structure of arrays, one slot per live path
+  float4* o;        // origin xyz, tmin
+  float4* d;        // direction xyz, tmax
+  float4* w;        // HitPayload.weight widened to RGB (the diffuse-bounce extension tints per channel)
+  uint32_t* px;     // pixel index y * width + x, BRT_MISS for padding slots
+  uint32_t* seed;   // PCG state (SH/random.slang)
+};
+
+struct FrameCounters {  // device-side, reset per round
+  uint32_t n_paths[2];  // live paths in queue 0 / 1
+  uint32_t n_shadow;
+  uint32_t work_closest, work_occl;  // dynamic-fetch cursors of the trace kernels
+  uint32_t pad[3];
+};
+struct FrameStats {  // device-side, reset per frame
+  unsigned long long rays_closest, rays_occlusion;
+  unsigned long long nodes_c, prims_c, spheres_c, nodes_o, prims_o, spheres_o;
+};
+
+struct TileMap {
+  uint32_t width, height;
+  uint32_t tiles_x, n_tiles;        // over the whole image
+  uint32_t tile_rank, tile_world;
+  uint32_t crop_x0, crop_y0, crop_x1, crop_y1;  // traced window [x0,x1) x [y0,y1)
+};
+BRT_HD uint32_t compact5(uint32_t v) {  // even bits of a 10-bit Morton code -> 5 bits
+  v &= 0x155u;
+  v = (v | (v >> 1)) & 0x133u;
+  v = (v | (v >> 2)) & 0x10fu;
+  v = (v | (v >> 4)) & 0x01fu;
+  return v;
+}
+// path slot -> pixel. Slots are laid out tile by tile (this rank's k-th tile = tile k*world + rank),
+// Morton order inside the 32x32 tile, so one warp covers an 8x4 pixel block.
+BRT_HD bool slot_to_pixel(const TileMap& m, uint32_t slot, uint32_t& x, uint32_t& y) {
+  const uint32_t tile = (slot >> 10) * m.tile_world + m.tile_rank;
+  if (tile >= m.n_tiles) return false;
+  const uint32_t j = slot & 1023u;
+  x = (tile % m.tiles_x) * BRT_TILE + compact5(j);
+  y = (tile / m.tiles_x) * BRT_TILE + compact5(j >> 1);
+  return x >= m.crop_x0 && x < m.crop_x1 && y >= m.crop_y0 && y < m.crop_y1;
+}
+
+// ---- raygen --------------------------------------------------------------------------------------
+struct RaygenParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  TileMap map;
+  float Vi[16], Pi[16];  // brt_uniform.viewInverse / projInverse, read as row-major M^-1 (RT/RTApp.cpp:44-49)
+  uint32_t frame;        // uniform.frame + sample index
+  uint32_t flags;
+  PathQueue q;
+};
+BRT_HD void raygen_body(const RaygenParams& p, uint32_t i) {
+  uint32_t px, py;
+  if (!slot_to_pixel(p.map, i, px, py)) {
+    p.q.px[i] = BRT_MISS;
+    return;
+  }
+  uint32_t seed = hash3(px, py, p.frame);  // :96
+  float jx = 0.0f, jy = 0.0f;
+  if (p.flags & BRT_RENDER_JITTER) {  // :97-98 (the shader computes it and then drops it at :100)
+    if (p.frame == 0u) { jx = 0.5f; jy = 0.5f; }
+    else { jx = rnd(seed); jy = rnd(seed); }
+  }
+  const float* Pi = p.Pi;
+  const float* Vi = p.Vi;
+  const float cx = ((float)px + jx) / (float)p.map.width * 2.0f - 1.0f;  // :100
+  const float cy = ((float)py + jy) / (float)p.map.height * 2.0f - 1.0f;
+  const f3 vc = F3(((Pi[0] * cx + Pi[1] * cy) + Pi[2] * 1.0f) + Pi[3] * 1.0f, ((Pi[4] * cx + Pi[5] * cy) + Pi[6] * 1.0f) + Pi[7] * 1.0f,
+                   ((Pi[8] * cx + Pi[9] * cy) + Pi[10] * 1.0f) + Pi[11] * 1.0f);  // :101
+  const f3 dn = normalize(vc);
+  const f3 dir = F3((Vi[0] * dn.x + Vi[1] * dn.y) + Vi[2] * dn.z, (Vi[4] * dn.x + Vi[5] * dn.y) + Vi[6] * dn.z,
+                    (Vi[8] * dn.x + Vi[9] * dn.y) + Vi[10] * dn.z);  // :104
+  p.q.o[i] = make_float4(Vi[3], Vi[7], Vi[11], 0.001f);               // :105-106
+  p.q.d[i] = make_float4(dir.x, dir.y, dir.z, BRT_INFINITE);           // :107
+  p.q.w[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);                      // :110
+  p.q.px[i] = py * p.map.width + px;
+  p.q.seed[i] = seed;
+}
+
+// ---- trace ---------------------------------------------------------------------------------------
+struct TraceParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const Node8* tlas;
+  const InstRec* insts;
+  const float4* o;
+  const float4* d;
+  const uint32_t* px;    // closest: padding slots are skipped; may be null
+  float4* hit;           // closest: t, u, v, bits(prim)
+  uint32_t* hit_inst;    // closest: instance or BRT_MISS
+  const uint32_t* target;  // occlusion: index into contrib
+  float4* contrib;         // occlusion: zeroed when the ray is blocked
+  uint32_t* work;          // dynamic-fetch cursor (device kernels)
+  FrameStats* stats;
+};
+template <bool COUNT>
+BRT_HD bool trace_closest_body(const TraceParams& p, uint32_t i, TraceCounters& ctr) {
+  if (p.px && p.px[i] == BRT_MISS) {
+    p.hit_inst[i] = BRT_MISS;
+    return false;
+  }
+  const float4 o = p.o[i], d = p.d[i];
+  Hit h;
+  trace_ray<false, COUNT>(p.tlas, p.insts, F3(o.x, o.y, o.z), F3(d.x, d.y, d.z), o.w, d.w, h, ctr);
+  p.hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+  p.hit_inst[i] = h.inst;
+  return true;
+}
+template <bool COUNT>
+BRT_HD bool trace_occlusion_body(const TraceParams& p, uint32_t i, TraceCounters& ctr) {
+  const float4 o = p.o[i], d = p.d[i];
+  Hit h;
+  if (trace_ray<true, COUNT>(p.tlas, p.insts, F3(o.x, o.y, o.z), F3(d.x, d.y, d.z), o.w, d.w, h, ctr))
+    p.contrib[p.target[i]] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // shadow factor 0 (SH/raytracing.slang:69)
+  return true;
+}
+
+// ---- shade ---------------------------------------------------------------------------------------
+struct ShadeParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  PathQueue cur, next;
+  const float4* hit;
+  const uint32_t* hit_inst;
+  FrameCounters* ctr;
+  uint32_t next_slot;      // which n_paths[] entry counts `next`
+  uint32_t cap;            // slots per queue == stride of contrib per light
+  const InstShade* inst;
+  const float* materials;  // 13 floats each (brt_material)
+  const float2* mat_ext;   // transmission, ior
+  const LightRec* lights;
+  uint32_t n_lights;
+  float4* contrib;         // [n_lights (>= 1)][cap]
+  float4* s_o;             // shadow queue
+  float4* s_d;
+  uint32_t* s_target;
+  uint32_t flags;
+  uint32_t last_round;     // no bounce is generated in the last round of the depth loop
+  uint32_t write_aov;
+  uint32_t* aov_prim;
+  uint32_t* aov_inst;
+  float* aov_t;
+  brt_sky sky;
+};
+
+BRT_HD uint32_t append_slot(uint32_t* counter) {
+#ifdef BRT_EMU
+  return atomic_add(counter, 1u);
+#else
+  const unsigned mask = __activemask();
+  const int leader = __ffs(mask) - 1;
+  const int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+#endif
+}
+
+// extension (BRT_RENDER_SKY): gradient from the SkyInfo the reference uploads but never reads (RT/Scene.cpp:333-355)
+BRT_HD f3 sky_color(const brt_sky& s, f3 dir) {
+  const f3 d = normalize(dir);
+  const float h = dot(d, F3(s.upDirection[0], s.upDirection[1], s.upDirection[2]));
+  const f3 hor = F3(s.horizonColor[0], s.horizonColor[1], s.horizonColor[2]);
+  f3 c;
+  if (h >= 0.0f)
+    c = lerp3(hor, F3(s.skyColor[0], s.skyColor[1], s.skyColor[2]), clampf(h / s.horizonSize, 0.0f, 1.0f));
+  else
+    c = lerp3(hor, F3(s.groundColor[0], s.groundColor[1], s.groundColor[2]), clampf(-h / s.horizonSize, 0.0f, 1.0f));
+  return c * s.brightness;
+}
+
+BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
+  const uint32_t px = p.cur.px[i];
+  if (px == BRT_MISS) return;
+  const uint32_t n_slots = p.n_lights ? p.n_lights : 1u;
+  const float4 ro = p.cur.o[i], rd = p.cur.d[i];
+  const f3 ray_o = F3(ro.x, ro.y, ro.z), ray_d = F3(rd.x, rd.y, rd.z);
+  const uint32_t inst_id = p.hit_inst[i];
+  const float4 hit = p.hit[i];
+  if (p.write_aov) {
+    p.aov_prim[px] = inst_id == BRT_MISS ? BRT_MISS : f2u(hit.w);
+    p.aov_inst[px] = inst_id;
+    p.aov_t[px] = inst_id == BRT_MISS ? 0.0f : hit.x;
+  }
+  if (inst_id == BRT_MISS) {  // rmissMain :172-176
+    f3 c = F3(0.0f);
+    if (p.flags & BRT_RENDER_SKY) c = sky_color(p.sky, ray_d);
+    p.contrib[i] = make_float4(c.x, c.y, c.z, 0.0f);
+    for (uint32_t l = 1; l < n_slots; ++l) p.contrib[(size_t)l * p.cap + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    return;
+  }
+  // rchitMain :136-169
+  const InstShade& in = p.inst[inst_id];
+  const float4 o2w[3] = {in.o2w[0], in.o2w[1], in.o2w[2]};
+  const float4 w2o[3] = {in.w2o[0], in.w2o[1], in.w2o[2]};
+  f3 pos, nrm;
+  if (in.kind == 1u) {
+    const f3 oo = xform_point(w2o, ray_o), od = xform_dir(w2o, ray_d);
+    pos = oo + od * hit.x;
+    nrm = (pos - xyz(in.sphere)) * (1.0f / in.sphere.w);
+  } else {
+    const uint32_t prim = f2u(hit.w);
+    const float b0 = 1.0f - hit.y - hit.z, b1 = hit.y, b2 = hit.z;  // :137
+    const uint32_t i0 = in.indices[3 * (size_t)prim], i1 = in.indices[3 * (size_t)prim + 1], i2 = in.indices[3 * (size_t)prim + 2];  // SH/objects.slang:30-33
+    const float4* v0 = reinterpret_cast<const float4*>(in.vertices + 8 * (size_t)i0);
+    const float4* v1 = reinterpret_cast<const float4*>(in.vertices + 8 * (size_t)i1);
+    const float4* v2 = reinterpret_cast<const float4*>(in.vertices + 8 * (size_t)i2);
+    const float4 a0 = ldg4(v0), a1 = ldg4(v0 + 1), b0_ = ldg4(v1), b1_ = ldg4(v1 + 1), c0 = ldg4(v2), c1 = ldg4(v2 + 1);
+    pos = (b0 * F3(a0.x, a0.y, a0.z) + b1 * F3(b0_.x, b0_.y, b0_.z)) + b2 * F3(c0.x, c0.y, c0.z);  // SH/objects.slang:35-41
+    nrm = (b0 * F3(a0.w, a1.x, a1.y) + b1 * F3(b0_.w, b1_.x, b1_.y)) + b2 * F3(c0.w, c1.x, c1.y);
+  }
+  const f3 worldPos = xform_point(o2w, pos);                       // :149
+  const f3 worldNormal = normalize(xform_normal(w2o, nrm));        // :150
+  Material mat;
+  {
+    const float* m = p.materials + 13 * (size_t)in.material;  // SH/objects.slang:56-59
+    mat.color = F3(m[0], m[1], m[2]);
+    mat.subsurface = m[3]; mat.metallic = m[4]; mat.roughness = m[5]; mat.specular = m[6]; mat.specularTint = m[7];
+    mat.anisotropic = m[8]; mat.sheen = m[9]; mat.sheenTint = m[10]; mat.clearCoat = m[11]; mat.clearCoatGloss = m[12];
+  }
+  f3 N = normalize(worldNormal);  // :154
+  const f3 V = ray_d;             // :155
+  bool flipped = false;
+  if (dot(N, -V) < 0.0f) { N = -N; flipped = true; }  // :157-158
+  const Frame fr = make_frame(N);
+  const BrdfSetup bs = brdf_setup(mat);
+  const f3 Vout = -V;
+  // calculateColor :72-88 — the unshadowed contribution of each light goes to contrib[l][slot]; lights
+  // whose contribution is not exactly zero get a shadow ray (a zero times the shadow factor is zero
+  // either way), which blanks the entry when it is blocked.
+  for (uint32_t l = 0; l < n_slots; ++l) {
+    f3 contrib = F3(0.0f);
+    if (l < p.n_lights) {
+      const LightRec lr = p.lights[l];
+      f3 ldir;
+      float intensity = lr.intensity;
+      if ((lr.type & 0xffu) == BRT_LIGHT_POINT) {  // SH/light.slang:23-39
+        ldir = F3(lr.pos_colr.x, lr.pos_colr.y, lr.pos_colr.z) - worldPos;
+        const float dist = length(ldir);
+        intensity /= (dist * dist);
+      } else {
+        ldir = F3(0.9f, -0.1f, 0.0f);
+      }
+      if (!(intensity < BRT_LIGHT_TRESHOLD)) {  // :79
+        const f3 L = normalize(ldir);
+        const f3 color = BRDF(mat, bs, fr, Vout, L);
+        contrib = color * F3(lr.pos_colr.w, lr.color_g, lr.color_b) * intensity;  // :83
+        if (!(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f)) {
+          const f3 so = worldPos + N * 0.0001f;  // testShadow :56-70
+          const uint32_t k = append_slot(&p.ctr->n_shadow);
+          p.s_o[k] = make_float4(so.x, so.y, so.z, 0.001f);
+          p.s_d[k] = make_float4(L.x, L.y, L.z, length(ldir));
+          p.s_target[k] = l * p.cap + i;
+        }
+      }
+    }
+    p.contrib[(size_t)l * p.cap + i] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+  }
+  // bounce (:161-168). With no BOUNCE flag this is the reference verbatim: weight = 0, the path ends.
+  const bool any_bounce = (p.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0u;
+  if (!any_bounce || p.last_round) return;
+  uint32_t seed = p.cur.seed[i];
+  const float r1 = rnd(seed), r2 = rnd(seed), r3 = rnd(seed);
+  const float4 w4 = p.cur.w[i];
+  f3 weight = F3(w4.x, w4.y, w4.z);
+  const float2 ext = p.mat_ext[in.material];  // transmission, ior
+  f3 ndir = F3(0.0f);
+  f3 norg = worldPos + N * 0.001f;  // :165
+  if ((p.flags & BRT_RENDER_BOUNCE_REFRACT) && ext.x > 0.0f) {
+    // extension: smooth dielectric, Schlick Fresnel, stochastic reflect / refract
+    const float eta = flipped ? ext.y : 1.0f / ext.y;
+    const float cosi = dot(N, -V);
+    const float k2 = 1.0f - eta * eta * (1.0f - cosi * cosi);
+    const float f0 = square((1.0f - ext.y) / (1.0f + ext.y));
+    const float Fr = k2 < 0.0f ? 1.0f : schlickFresnel(f0, cosi);
+    if (r3 < Fr) {
+      ndir = reflect(V, N);
+    } else {
+      ndir = V * eta + N * (eta * cosi - sqrtf(k2));
+      norg = worldPos - N * 0.001f;
+      weight = weight * (mat.color * ext.x);
+    }
+  } else {
+    const bool refl = (p.flags & BRT_RENDER_BOUNCE_REFLECT) != 0u, diff = (p.flags & BRT_RENDER_BOUNCE_DIFFUSE) != 0u;
+    const bool spec = (refl && diff) ? (r3 < mat.metallic) : refl;
+    if (spec) {
+      float pdf;
+      ndir = sampleGGXVNDFSphericalCap(mat, bs.ap, V, fr, r1, r2, pdf);  // :166
+      weight = weight * (diff ? pdf : mat.metallic * pdf);                // :167
+    } else if (diff) {
+      ndir = toWorld(sampleCosineWeightedHemisphere(r1, r2), fr);  // SH/sampler.slang:53-65 + toWorld
+      weight = weight * (refl ? mat.color : mat.color * (1.0f - mat.metallic));
+    } else {
+      weight = F3(0.0f);
+    }
+  }
+  if (!(weight.x > 0.0f || weight.y > 0.0f || weight.z > 0.0f)) return;  // no weight-0 rays
+  const uint32_t k = append_slot(&p.ctr->n_paths[p.next_slot]);
+  p.next.o[k] = make_float4(norg.x, norg.y, norg.z, 0.001f);
+  p.next.d[k] = make_float4(ndir.x, ndir.y, ndir.z, BRT_INFINITE);
+  p.next.w[k] = make_float4(weight.x, weight.y, weight.z, 0.0f);
+  p.next.px[k] = px;
+  p.next.seed[k] = seed;
+}
+
+// ---- accumulate ------------------------------------------------------------------------------------
+struct AccumParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const uint32_t* px;
+  const float4* w;
+  const float4* contrib;
+  uint32_t n_slots, cap;
+  float4* accum;  // per pixel running sum over samples and depths
+};
+BRT_HD void accumulate_body(const AccumParams& p, uint32_t i) {
+  const uint32_t px = p.px[i];
+  if (px == BRT_MISS) return;
+  const float4 c0 = p.contrib[i];
+  f3 c = F3(c0.x, c0.y, c0.z);
+  for (uint32_t l = 1; l < p.n_slots; ++l) {
+    const float4 cl = p.contrib[(size_t)l * p.cap + i];
+    c = c + F3(cl.x, cl.y, cl.z);  // :84, light order
+  }
+  const float4 w = p.w[i];
+  float4 a = p.accum[px];
+  a.x = a.x + c.x * w.x;  // :122
+  a.y = a.y + c.y * w.y;
+  a.z = a.z + c.z * w.z;
+  p.accum[px] = a;
+}
+
+// ---- resolve ---------------------------------------------------------------------------------------
+struct ResolveParams {
+  uint32_t count;  // slots (tiles owned * 1024)
+  const uint32_t* count_ptr;
+  TileMap map;
+  float spp;
+  const float4* accum;
+  float4* image;   // full frame, row major
+  float4* tiles;   // this rank's tiles packed tile-major, row-major inside a tile (may be null)
+};
+BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
+  // unlike the path slots this walks the tile row by row so that both stores coalesce
+  const uint32_t tile = (i >> 10) * p.map.tile_world + p.map.tile_rank;
+  if (tile >= p.map.n_tiles) return;
+  const uint32_t lx = i & 31u, ly = (i >> 5) & 31u;
+  const uint32_t x = (tile % p.map.tiles_x) * BRT_TILE + lx, y = (tile / p.map.tiles_x) * BRT_TILE + ly;
+  float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  const bool inside = x < p.map.width && y < p.map.height;
+  if (inside && x >= p.map.crop_x0 && x < p.map.crop_x1 && y >= p.map.crop_y0 && y < p.map.crop_y1) {
+    const float4 a = p.accum[(size_t)y * p.map.width + x];
+    out = make_float4(a.x / p.spp, a.y / p.spp, a.z / p.spp, 1.0f);  // :129-132
+  }
+  if (inside) p.image[(size_t)y * p.map.width + x] = out;
+  if (p.tiles) p.tiles[i] = out;
+}
+
+// ---- un-tile after the framebuffer gather (root rank) ----------------------------------------------------
+struct UntileParams {
+  uint32_t count;  // width * height
+  const uint32_t* count_ptr;
+  uint32_t width, height, tiles_x, tile_world, slots_per_rank;
+  const float4* all;  // tile_world packed buffers back to back
+  float4* image;
+};
+BRT_HD void untile_body(const UntileParams& p, uint32_t i) {
+  const uint32_t x = i % p.width, y = i / p.width;
+  const uint32_t tile = (y / BRT_TILE) * p.tiles_x + x / BRT_TILE;
+  const uint32_t rank = tile % p.tile_world, k = tile / p.tile_world;
+  p.image[i] = p.all[(size_t)rank * p.slots_per_rank + (size_t)k * 1024u + (y % BRT_TILE) * BRT_TILE + (x % BRT_TILE)];
+}
+
+// ---- Smart Culling (README.md:15-18; rule defined in DESIGN.md §6) ---------------------------------------
+struct CullParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const InstShade* inst;
+  const float4* mesh_bounds;
+  float eye[3], fwd[3];
+  float k;          // P[1][1] * height / 2
+  float threshold, hysteresis;
+  uint8_t* visible;  // in/out: previous state feeds the hysteresis
+};
+BRT_HD void cull_body(const CullParams& p, uint32_t i) {
+  if (!(p.threshold > 0.0f)) { p.visible[i] = 1; return; }
+  const InstShade& s = p.inst[i];
+  f3 lo, hi;
+  instance_world_box(s.o2w, xyz(p.mesh_bounds[2 * s.mesh]), xyz(p.mesh_bounds[2 * s.mesh + 1]), lo, hi);
+  const f3 ctr = (lo + hi) * 0.5f;
+  const float r = length((hi - lo) * 0.5f);
+  const float z = dot(ctr - F3(p.eye[0], p.eye[1], p.eye[2]), F3(p.fwd[0], p.fwd[1], p.fwd[2]));
+  if (z - r <= 0.0f) { p.visible[i] = 1; return; }  // touches the camera plane: keep
+  const float rp = (r * p.k) / z;
+  const float fp = BRT_PI * (rp * rp);  // footprint of the bounding sphere in px^2
+  const bool was = p.visible[i] != 0;
+  p.visible[i] = (was ? (fp >= p.threshold * (1.0f - p.hysteresis)) : (fp > p.threshold * (1.0f + p.hysteresis))) ? 1 : 0;
+}
+
+}  // namespace brt

@@ -1,0 +1,204 @@
+// Software replacement for TraceRay (SH/raytracing.slang:67,121; RT cores on the reference's
+// hardware): two-level traversal of compressed 8-wide BVHs, one ray per thread.
+//
+// Algorithm: stack of 8-byte "groups" after Ylitie, Karras & Laine (HPG 2017). A node group is
+// (child_base, hits<<24 | imask): the not-yet-visited inner children of one node, visited in
+// descending bit order, which the octant trick turns into front-to-back order. A leaf group is
+// (prim_base, 24-bit mask) of primitives whose slot box the ray hit. TLAS leaves are instances: the
+// ray is transformed to object space (t is preserved, the direction is not renormalised) and the
+// BLAS is traversed on the same stack; when the stack drops back to the entry level the world ray
+// is restored.
+//
+// Tie-break: the closest hit is the lexicographic minimum of (t, instance, primitive),
+// so the result does not depend on traversal order; boxes are culled with `entry <= best t` so that
+// equal-t candidates are still visited.
+#pragma once
+#include "device_types.cuh"
+#include "intersect.cuh"
+
+namespace brt {
+
+struct TraceCounters {
+  uint32_t nodes, prims, spheres;
+};
+
+struct RayBox {   // per-ray constants of the quantised slab test, valid for one coordinate space
+  f3 idir;        // 1/d with |d| clamped away from zero
+  uint32_t octinv;  // 7 - octant, octant bit k = (d_k < 0)
+};
+BRT_HD RayBox make_raybox(f3 d) {
+  RayBox rb;
+  const float tiny = 8.2718061e-25f;  // 2^-80
+  float dx = fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x);
+  float dy = fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y);
+  float dz = fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z);
+  rb.idir = F3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+  uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+  rb.octinv = 7u - oct;
+  return rb;
+}
+
+BRT_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
+
+// Tests the ray against the 8 quantised child boxes of one node.
+// out: G = (child_base, inner hits << 24 | imask), Gt = (prim_base, leaf hit bits)
+BRT_HD void intersect_node(const Node8* __restrict__ node, const RayBox& rb, f3 o, float tmin, float tmax, uint2& G, uint2& Gt) {
+  const uint4 n0 = ldg4(&node->q[0]);
+  const uint4 n1 = ldg4(&node->q[1]);
+  const uint4 n2 = ldg4(&node->q[2]);
+  const uint4 n3 = ldg4(&node->q[3]);
+  const uint4 n4 = ldg4(&node->q[4]);
+  const float px = u2f(n0.x) - o.x, py = u2f(n0.y) - o.y, pz = u2f(n0.z) - o.z;
+  const float sx = u2f((n0.w & 0xffu) << 23), sy = u2f(((n0.w >> 8) & 0xffu) << 23), sz = u2f(((n0.w >> 16) & 0xffu) << 23);
+  const float idx = sx * rb.idir.x, idy = sy * rb.idir.y, idz = sz * rb.idir.z;
+  // Rounding slack. The slab arithmetic below and the (differently rounded) primitive tests both
+  // carry errors of a few ulps of the largest coordinate difference involved; widening every slab
+  // by 2^-21 of that magnitude keeps the box test conservative with respect to the primitive tests.
+  const float mag = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz)) + 256.0f * fmaxf(fmaxf(sx, sy), sz);
+  const float slack = mag * 4.76837158e-07f;
+  const float ex = slack * fabsf(rb.idir.x), ey = slack * fabsf(rb.idir.y), ez = slack * fabsf(rb.idir.z);
+  const float ox = px * rb.idir.x, oy = py * rb.idir.y, oz = pz * rb.idir.z;
+  const float ox0 = ox - ex, ox1 = ox + ex, oy0 = oy - ey, oy1 = oy + ey, oz0 = oz - ez, oz1 = oz + ez;
+  const bool nx = rb.idir.x < 0.0f, ny = rb.idir.y < 0.0f, nz = rb.idir.z < 0.0f;
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t meta4 = h ? n1.w : n1.z;
+    const uint32_t lox4 = h ? n2.y : n2.x, loy4 = h ? n2.w : n2.z, loz4 = h ? n3.y : n3.x;
+    const uint32_t hix4 = h ? n3.w : n3.z, hiy4 = h ? n4.y : n4.x, hiz4 = h ? n4.w : n4.z;
+    const uint32_t nearx4 = nx ? hix4 : lox4, farx4 = nx ? lox4 : hix4;
+    const uint32_t neary4 = ny ? hiy4 : loy4, fary4 = ny ? loy4 : hiy4;
+    const uint32_t nearz4 = nz ? hiz4 : loz4, farz4 = nz ? loz4 : hiz4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t meta = byte_of(meta4, i);
+      const float t0x = fma_rn((float)byte_of(nearx4, i), idx, ox0), t1x = fma_rn((float)byte_of(farx4, i), idx, ox1);
+      const float t0y = fma_rn((float)byte_of(neary4, i), idy, oy0), t1y = fma_rn((float)byte_of(fary4, i), idy, oy1);
+      const float t0z = fma_rn((float)byte_of(nearz4, i), idz, oz0), t1z = fma_rn((float)byte_of(farz4, i), idz, oz1);
+      const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+      const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+      if (meta != 0u && tn <= tf) {
+        const uint32_t inner = (meta & 0x18u) == 0x18u ? rb.octinv : 0u;
+        hitmask |= (meta >> 5) << ((meta ^ inner) & 31u);
+      }
+    }
+  }
+  G = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+  Gt = make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
+
+// lexicographic (t, instance, primitive) order
+BRT_HD bool better_hit(float t, uint32_t inst, uint32_t prim, bool found, const Hit& best) {
+  if (!found || t < best.t) return true;
+  return t == best.t && (inst < best.inst || (inst == best.inst && prim < best.prim));
+}
+
+// ANY: occlusion query (RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | SKIP_CLOSEST_HIT_SHADER) — returns
+// at the first primitive with tmin < t < tmax. Otherwise: closest-hit query, `best` is filled.
+template <bool ANY, bool COUNT>
+BRT_HD bool trace_ray(const Node8* __restrict__ tlas, const InstRec* __restrict__ insts, f3 o, f3 d, float tmin, float tmax, Hit& best,
+                      TraceCounters& ctr) {
+  best.t = tmax;
+  best.u = 0.0f;
+  best.v = 0.0f;
+  best.inst = BRT_MISS;
+  best.prim = BRT_MISS;
+  bool found = false;
+  if (tlas == nullptr) return false;
+
+  uint2 stack[BRT_STACK_SIZE];
+  int sp = 0;
+  int blas_sp = -1;  // >= 0 while inside a BLAS: stack height at entry
+  const RayBox wrb = make_raybox(d);
+  RayBox rb = wrb;
+  f3 co = o, cd = d;
+  RayShear sh = make_shear(d);
+  const Node8* nodes = tlas;
+  const TriRec* tris = nullptr;
+  uint32_t cur_inst = 0;
+  uint2 G = make_uint2(0u, 0x80000000u);
+  uint2 Gt = make_uint2(0u, 0u);
+
+  for (;;) {
+    if (G.y & 0xff000000u) {
+      const int bit = 31 - clz32(G.y);
+      G.y &= ~(1u << bit);
+      if (G.y & 0xff000000u) stack[sp++] = G;
+      const uint32_t slot = (uint32_t)(bit - 24) ^ rb.octinv;
+      const uint32_t rel = popc(G.y & ~(0xffffffffu << slot));
+      if (COUNT) ctr.nodes++;
+      intersect_node(nodes + G.x + rel, rb, co, tmin, best.t, G, Gt);
+    } else {
+      Gt = G;
+      G = make_uint2(0u, 0u);
+    }
+
+    while (Gt.y) {
+      const int bit = ffs32(Gt.y) - 1;
+      Gt.y &= Gt.y - 1u;
+      if (blas_sp >= 0) {
+        const TriRec* tr = tris + Gt.x + bit;
+        const float4 a = ldg4(&tr->v0), b = ldg4(&tr->v1), c = ldg4(&tr->v2);
+        if (COUNT) ctr.prims++;
+        float t, u, v;
+        if (intersect_tri(co, sh, tmin, best.t, found, xyz(a), xyz(b), xyz(c), t, u, v)) {
+          if (ANY) return true;
+          const uint32_t prim = f2u(a.w);
+          if (better_hit(t, cur_inst, prim, found, best)) {
+            best.t = t; best.u = u; best.v = v; best.inst = cur_inst; best.prim = prim;
+            found = true;
+          }
+        }
+      } else {
+        const InstRec* ir = insts + Gt.x + bit;
+        const float4 m0 = ldg4(&ir->w2o[0]), m1 = ldg4(&ir->w2o[1]), m2 = ldg4(&ir->w2o[2]);
+        const uint4 tail = ldg4(reinterpret_cast<const uint4*>(&ir->kind));
+        const float4 m[3] = {m0, m1, m2};
+        const f3 oo = xform_point(m, o), od = xform_dir(m, d);
+        if (tail.x == 1u) {  // analytic sphere
+          const float4 s = ldg4(&ir->sphere);
+          if (COUNT) ctr.spheres++;
+          float t;
+          if (intersect_sphere(oo, od, tmin, best.t, found, xyz(s), s.w, t)) {
+            if (ANY) return true;
+            if (better_hit(t, tail.y, 0u, found, best)) {
+              best.t = t; best.u = 0.0f; best.v = 0.0f; best.inst = tail.y; best.prim = 0u;
+              found = true;
+            }
+          }
+        } else {
+          // enter the BLAS: keep the TLAS continuation on the stack
+          if (Gt.y) stack[sp++] = Gt;
+          if (G.y & 0xff000000u) stack[sp++] = G;
+          blas_sp = sp;
+          const uint4 ptrs = ldg4(reinterpret_cast<const uint4*>(&ir->nodes));
+          nodes = reinterpret_cast<const Node8*>(((uint64_t)ptrs.y << 32) | ptrs.x);
+          tris = reinterpret_cast<const TriRec*>(((uint64_t)ptrs.w << 32) | ptrs.z);
+          cur_inst = tail.y;
+          co = oo;
+          cd = od;
+          rb = make_raybox(od);
+          sh = make_shear(od);
+          G = make_uint2(0u, 0x80000000u);
+          Gt = make_uint2(0u, 0u);
+        }
+      }
+    }
+
+    if (!(G.y & 0xff000000u)) {
+      if (blas_sp >= 0 && sp == blas_sp) {  // BLAS exhausted: back to the world ray
+        blas_sp = -1;
+        nodes = tlas;
+        co = o;
+        cd = d;
+        rb = wrb;
+      }
+      if (sp == 0) break;
+      G = stack[--sp];
+    }
+  }
+  (void)cd;
+  return found;
+}
+
+}  // namespace brt

@@ -206,17 +206,23 @@ static inline void build_bvh(BVH& bvh, const std::vector<vec3>& plo, const std::
   }
 }
 
-// Conservative slab test: entry/exit are widened by 2^-20 relative so that rounding in the slab
-// arithmetic can never cull a box whose primitive the (differently rounded) primitive test accepts.
+// Conservative slab test. The primitive tests round differently from the slab arithmetic and accept
+// rays that pass a few ulps (of the coordinates involved) outside the exact geometry, so the box is
+// widened in SPACE by 2^-20 of the largest coordinate magnitude in play (a pad on t alone is not
+// enough for slabs the ray is nearly parallel to), and the interval by 2^-20 relative in t.
 static inline bool slab(const BNode& n, vec3 o, vec3 idir, float tmin, float tmax, float& entry) {
   const float pad = 9.5367431640625e-07f;
-  float x0 = (n.lo.x - o.x) * idir.x, x1 = (n.hi.x - o.x) * idir.x;
-  float y0 = (n.lo.y - o.y) * idir.y, y1 = (n.hi.y - o.y) * idir.y;
-  float z0 = (n.lo.z - o.z) * idir.z, z1 = (n.hi.z - o.z) * idir.z;
+  float mag = std::fmax(std::fmax(std::fabs(o.x), std::fabs(o.y)), std::fabs(o.z));
+  mag = std::fmax(mag, std::fmax(std::fmax(std::fabs(n.lo.x), std::fabs(n.lo.y)), std::fabs(n.lo.z)));
+  mag = std::fmax(mag, std::fmax(std::fmax(std::fabs(n.hi.x), std::fabs(n.hi.y)), std::fabs(n.hi.z)));
+  const float e = mag * pad;
+  float x0 = ((n.lo.x - e) - o.x) * idir.x, x1 = ((n.hi.x + e) - o.x) * idir.x;
+  float y0 = ((n.lo.y - e) - o.y) * idir.y, y1 = ((n.hi.y + e) - o.y) * idir.y;
+  float z0 = ((n.lo.z - e) - o.z) * idir.z, z1 = ((n.hi.z + e) - o.z) * idir.z;
   float tn = std::fmax(std::fmax(std::fmin(x0, x1), std::fmin(y0, y1)), std::fmin(z0, z1));
   float tf = std::fmin(std::fmin(std::fmax(x0, x1), std::fmax(y0, y1)), std::fmax(z0, z1));
-  float e0 = std::fmax(tn * (1.0f - pad), tmin);
-  float e1 = std::fmin(tf * (1.0f + pad), tmax);
+  float e0 = std::fmax(tn - std::fabs(tn) * pad, tmin);
+  float e1 = std::fmin(tf + std::fabs(tf) * pad, tmax);
   entry = e0;
   return e0 <= e1;
 }
