@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native Bloon RT hot path (BASELINE.json metric: Mrays/s).
+
+A *step* is one frame of the workload: every ray query (primary, bounce, shadow) of the frame traced and
+shaded by the CUDA path, the scene (BVH, tables) already resident in HBM. `value` = rays of all ranks per
+second of device time. `e2e` = the same through the reference-facing C-ABI call brt_render_frame with a
+HOST framebuffer (uniform from host memory in, RGBA32F image copied back to pinned host memory inside the
+timed region). N > 1 (torchrun, one process per GPU): the frame is split into 32x32 tiles round-robin over
+the ranks, scene replicated, one NCCL all-gather of the packed tile buffers per frame, un-tile on every rank.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3              # product arm (C2: 1M-tri scene, 1080p, 2 bounces)
+  python bench.py --impl reference --steps 2 --warmup 1       # CPU arm: the oracle (kind "port") on all host threads
+
+Only the cpu_baseline leg and --impl reference touch oracle/ (the checker); the product arm needs
+lib/libbrt.so and a CUDA device and fails loudly without them.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NODE_BYTES, TRI_BYTES, INST_BYTES, RAY_IO_BYTES = 80, 48, 96, 48  # algorithmic bytes per visit / per ray
+
+
+def load_pkg():
+    return importlib.import_module("hardware-ray-tracer_b200")
+
+
+def workload(pkg, name):
+    cfg = dict(pkg.scenes.CONFIGS[name])
+    scene = pkg.scenes.make_scene(cfg.pop("scene"))
+    return scene, cfg
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def traversal_bytes(st, which):
+    if which == "closest":
+        return (st.nodes_visited_closest * NODE_BYTES + st.prims_tested_closest * TRI_BYTES + st.spheres_tested_closest * INST_BYTES
+                + st.rays_closest * RAY_IO_BYTES)
+    return (st.nodes_visited_occlusion * NODE_BYTES + st.prims_tested_occlusion * TRI_BYTES + st.spheres_tested_occlusion * INST_BYTES
+            + st.rays_occlusion * RAY_IO_BYTES)
+
+
+def oracle_sample(pkg, scene, cfg, budget_s, threads=0):
+    """Times the CPU oracle on a centred crop of the workload sized for about `budget_s` seconds."""
+    from oracle import binding as ob
+    orc = ob.Oracle(pkg, threads=threads)
+    scene.upload(orc)
+    w, h = cfg["width"], cfg["height"]
+    u = scene.uniform(orc, w, h, 0, cfg["depth_max"])
+    cores = orc._f("get_threads")(orc.ctx)
+
+    def run(cw, ch):
+        crop = ((w - cw) // 2, (h - ch) // 2, cw, ch)
+        t0 = time.perf_counter()
+        orc.render_frame(u, orc.opts(w, h, cfg["spp"], cfg["flags"], crop))
+        dt = time.perf_counter() - t0
+        st = orc.get_stats()
+        return dt, st.rays_closest + st.rays_occlusion
+
+    dt, rays = run(max(32, w // 16), max(32, h // 16))  # calibration + warm-up
+    frac = min(1.0, (budget_s / max(dt, 1e-4)) / 256.0)
+    scale = max(1.0 / 16.0, frac ** 0.5)
+    cw, ch = max(32, int(w * scale)), max(32, int(h * scale))
+    dt, rays = run(cw, ch)
+    return {"mrays": rays / dt / 1e6, "cores": int(cores), "seconds": dt, "rays": int(rays),
+            "sample": f"centred {cw}x{ch} crop of the {w}x{h} frame, {cfg['spp']} spp, depthMax {cfg['depth_max']}, one pass"}, orc, u
+
+
+def run_reference(args):
+    """--impl reference: the reference cannot run here (Windows/Vulkan/RT cores, no CPU path), so this arm
+    times the oracle — the C++ restatement of its shaders — on all host threads, kind 'port'."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = load_pkg()
+    scene, cfg = workload(pkg, args.config)
+    total = args.steps + args.warmup
+    budget = min(20.0, 150.0 / max(total, 1))
+    base, orc, u = oracle_sample(pkg, scene, cfg, budget)
+    w, h = cfg["width"], cfg["height"]
+    cw, ch = [int(x) for x in base["sample"].split()[1].split("x")]
+    crop = ((w - cw) // 2, (h - ch) // 2, cw, ch)
+    times, rays = [], 0
+    for i in range(total):
+        t0 = time.perf_counter()
+        orc.render_frame(u, orc.opts(w, h, cfg["spp"], cfg["flags"], crop))
+        dt = time.perf_counter() - t0
+        st = orc.get_stats()
+        if i >= args.warmup:
+            times.append(dt)
+            rays = st.rays_closest + st.rays_occlusion
+    ms = 1e3 * float(np.mean(times))
+    v = rays / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(scene, cfg, args),
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": base["cores"], "kind": "port", "sample": base["sample"] + " per step"},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(scene, cfg, args):
+    return {"workload": f"{args.config}: {scene.name} {scene.triangles()} triangles, {cfg['width']}x{cfg['height']}, {cfg['spp']} spp, "
+                        f"depthMax {cfg['depth_max']} (primary + {cfg['depth_max'] - 1} bounces), shadow ray per light per hit",
+            "render_flags": cfg["flags"], "lights": len(scene.lights), "instances": len(scene.instances),
+            "l2": "flushed between steps (256 MiB write)", "parallelism": f"image tiles 32x32 round-robin over {args.gpus} GPU(s), scene replicated"}
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product arm has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = load_pkg()
+    scene, cfg = workload(pkg, args.config)
+    w, h, spp, flags = cfg["width"], cfg["height"], cfg["spp"], cfg["flags"]
+
+    ctx = pkg.Context(device=local, tile_rank=rank, tile_world=world)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    scene.upload(ctx)
+    build_s = time.perf_counter() - t0
+    build_stats = ctx.get_stats()
+    u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
+    opts = ctx.opts(w, h, spp, flags)
+
+    tile_bytes = ctx.tile_buffer_bytes(w, h, world)
+    tiles = torch.empty(tile_bytes // 4, dtype=torch.float32, device=dev)
+    gathered = torch.empty(world * tile_bytes // 4, dtype=torch.float32, device=dev) if world > 1 else tiles
+    image = torch.empty(h * w * 4, dtype=torch.float32, device=dev)
+    host_image = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        """one frame, result left in HBM (un-tiled full frame on every rank)"""
+        ctx.render_frame_tiles(u, opts, tiles.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, tiles)
+            ctx.untile(gathered.data_ptr(), w, h, world, image.data_ptr())
+
+    def step_e2e():
+        """the call a user makes: host uniform in, host framebuffer out"""
+        if world == 1:
+            ctx.render_frame_ptr(u, opts, host_image.data_ptr())
+        else:
+            ctx.render_frame_tiles(u, opts, tiles.data_ptr())
+            dist.all_gather_into_tensor(gathered, tiles)
+            ctx.untile(gathered.data_ptr(), w, h, world, image.data_ptr())
+            if rank == 0:
+                host_image.copy_(image, non_blocking=True)
+            stream.synchronize()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, collect=None):
+        for _ in range(warmup):
+            fn()
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)  # evict the BVH and the path queues from L2 (outside the timed region)
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            if collect is not None:
+                collect(ctx.get_stats())
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    kstats = {"closest": 0.0, "occl": 0.0, "shade": 0.0, "other": 0.0, "n": 0, "launches": 0, "rays": 0}
+
+    def collect(st):
+        kstats["closest"] += st.ms_trace_closest
+        kstats["occl"] += st.ms_trace_occlusion
+        kstats["shade"] += st.ms_shade
+        kstats["other"] += st.ms_raygen + st.ms_accumulate + st.ms_resolve
+        kstats["n"] += 1
+        kstats["launches"] += st.launches_total + (1 if world > 1 else 0)  # + un-tile
+        kstats["rays"] = st.rays_closest + st.rays_occlusion
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev = timed(step_device, args.steps, args.warmup, collect)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    rays_t = torch.tensor([kstats["rays"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+    rays = float(rays_t.item())
+    value = rays / (ms_dev * 1e-3) / 1e6
+    e2e_value = rays / (ms_e2e * 1e-3) / 1e6
+
+    line = None
+    if rank == 0:
+        # roofline of the dominant kernel: algorithmic bytes from an instrumented run of the same kernels on the
+        # same BVH (not the timed run), divided by that kernel's CUDA-event time inside the timed steps
+        cctx = pkg.Context(device=local, tile_rank=rank, tile_world=world, flags=pkg.CFG_COUNTERS)
+        scene.upload(cctx)
+        cctx.render_frame(u, opts, want_image=False)
+        cst = cctx.get_stats()
+        cctx.close()
+        n = max(kstats["n"], 1)
+        ms_c, ms_o = kstats["closest"] / n, kstats["occl"] / n
+        which = "closest" if ms_c >= ms_o else "occlusion"
+        kbytes = traversal_bytes(cst, which)
+        kms = ms_c if which == "closest" else ms_o
+        peak, peak_src = peaks()
+        achieved = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": f"k_trace<{'false' if which == 'closest' else 'true'}> ({which}-hit traversal)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": None, "algorithmic_bytes_per_step": int(kbytes), "kernel_ms_per_step": kms,
+                    "launches_per_step": int(cst.launches_trace_closest if which == "closest" else cst.launches_trace_occlusion),
+                    "nodes_per_ray": (cst.nodes_visited_closest / max(cst.rays_closest, 1)) if which == "closest"
+                    else (cst.nodes_visited_occlusion / max(cst.rays_occlusion, 1)),
+                    "prims_per_ray": (cst.prims_tested_closest / max(cst.rays_closest, 1)) if which == "closest"
+                    else (cst.prims_tested_occlusion / max(cst.rays_occlusion, 1)),
+                    "note": "the 1M-triangle BVH (nodes + triangle records) fits the 126 MB L2, so the fetches are served by L2 after "
+                            "first touch; the fraction is quoted against the HBM copy peak as the contract asks"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            b, _, _ = oracle_sample(pkg, scene, cfg, 12.0)
+            cpu = {"value": b["mrays"], "unit": "Mrays/s", "cores": b["cores"], "kind": "port", "sample": b["sample"],
+                   "seconds": b["seconds"]}
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": bench_config(scene, cfg, args),
+            "rays_per_step": int(rays),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 140 + 32,
+                    "d2h_bytes_per_step": w * h * 16},
+            "gpu_launches": int(kstats["launches"]),
+            "kernel_ms_per_step": {"trace_closest": ms_c, "trace_occlusion": ms_o, "shade": kstats["shade"] / n, "other": kstats["other"] / n},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "scene_build": {"seconds_incl_upload": build_s, "ms_blas": build_stats.ms_blas_build, "ms_tlas": build_stats.ms_tlas_build,
+                            "bvh_nodes": int(build_stats.bvh_nodes), "bvh_bytes": int(build_stats.bvh_bytes), "sah_cost": build_stats.sah_cost},
+        }
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

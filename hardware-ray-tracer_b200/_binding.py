@@ -1,8 +1,8 @@
-"""ctypes view of include/brt.h.
+"""ctypes view of include/brt.h (the C ABI of lib/libbrt.so, the CUDA product).
 
-The same signatures are exported by libbrt.so (prefix ``brt_``, the CUDA product) and — for the
-parity tests only — by oracle/liboracle.so (prefix ``orc_``); `SceneApi` is parameterised by the
-prefix so one piece of test code drives both. Nothing in this module touches oracle/.
+`SceneApi` takes the library handle and the symbol prefix as arguments, so test code can drive any
+library that exports the same ABI under another prefix through the same Python surface; this module
+itself only knows include/brt.h.
 """
 import ctypes as C
 
@@ -85,10 +85,11 @@ def _ptr(a, ty):
 
 
 class SceneApi:
-    """One context of libbrt.so (prefix ``brt_``) or of the oracle (prefix ``orc_``)."""
+    """One `brt_context` of a library exporting the include/brt.h ABI under `prefix`."""
 
-    def __init__(self, lib, prefix, device=0, tile_rank=0, tile_world=1, flags=0):
+    def __init__(self, lib, prefix="brt_", device=0, tile_rank=0, tile_world=1, flags=0, extra_signatures=None):
         self.lib, self.prefix = lib, prefix
+        self._extra = extra_signatures or {}
         self._declare()
         cfg = Config(C.sizeof(Config), device, tile_rank, tile_world, flags)
         self.ctx = C.c_void_p()
@@ -126,16 +127,15 @@ class SceneApi:
             "trace_rays": (C.c_int, [vp, P(f32), u32, C.c_int, P(u32)]),
             "camera_uniform": (None, [P(f32), P(f32), f32, f32, f32, f32, u32, u32, P(Uniform)]),
         }
-        if self.prefix == "brt_":
-            sig.update({
-                "set_stream": (C.c_int, [vp, vp]),
-                "render_frame_tiles": (C.c_int, [vp, P(Uniform), P(RenderOpts), vp]),
-                "tile_buffer_bytes": (C.c_size_t, [u32, u32, u32]),
-                "untile": (C.c_int, [vp, vp, u32, u32, u32, vp]),
-                "device_image": (vp, [vp]),
-            })
-        else:
-            sig.update({"set_threads": (C.c_int, [vp, u32]), "get_threads": (u32, [vp])})
+        device_side = {  # entry points that take device pointers / streams
+            "set_stream": (C.c_int, [vp, vp]),
+            "render_frame_tiles": (C.c_int, [vp, P(Uniform), P(RenderOpts), vp]),
+            "tile_buffer_bytes": (C.c_size_t, [u32, u32, u32]),
+            "untile": (C.c_int, [vp, vp, u32, u32, u32, vp]),
+            "device_image": (vp, [vp]),
+        }
+        sig.update({k: v for k, v in device_side.items() if hasattr(self.lib, self.prefix + k)})
+        sig.update(self._extra)
         for name, (res, args) in sig.items():
             fn = self._f(name)
             fn.restype, fn.argtypes = res, args
@@ -271,7 +271,7 @@ class SceneApi:
         self._ck(self._f("trace_rays")(self.ctx, _ptr(r, f32), r.shape[0], 1 if closest else 0, _ptr(out, u32)))
         return out
 
-    # ---- brt_ only ---------------------------------------------------------------------------
+    # ---- device-side entry points ------------------------------------------------------------
     def set_stream(self, stream_ptr):
         self._ck(self._f("set_stream")(self.ctx, C.c_void_p(stream_ptr)))
 

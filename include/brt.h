@@ -26,6 +26,13 @@
 extern "C" {
 #endif
 
+/* every entry point below is exported from libbrt.so; everything else in the library is hidden */
+#if defined(__GNUC__)
+#define BRT_API __attribute__((visibility("default")))
+#else
+#define BRT_API
+#endif
+
 #define BRT_OK 0
 #define BRT_ERR_INVALID 1  /* bad argument / bad id */
 #define BRT_ERR_CUDA 2     /* CUDA runtime error (message in brt_last_error) */
@@ -152,78 +159,78 @@ typedef struct brt_context brt_context;
 
 /* Device::Device + Pipeline ctor (vulkan_core/Device.cpp:45-53, RT/RTPipeline.cpp:4-26): picks the
  * CUDA device, creates the stream and the per-frame buffers. Fails (BRT_ERR_CUDA) without a GPU. */
-int brt_create(const brt_config* cfg, brt_context** out);
-void brt_destroy(brt_context* ctx);
-const char* brt_last_error(const brt_context* ctx);
+BRT_API int brt_create(const brt_config* cfg, brt_context** out);
+BRT_API void brt_destroy(brt_context* ctx);
+BRT_API const char* brt_last_error(const brt_context* ctx);
 /* Launch all work of this context on an externally owned cudaStream_t (e.g. torch's current stream). */
-int brt_set_stream(brt_context* ctx, void* cuda_stream);
+BRT_API int brt_set_stream(brt_context* ctx, void* cuda_stream);
 
 /* ---- scene upload (RayTracing::Scene, RT/Scene.h:134-151) -------------------------------- */
 /* Mesh::Mesh (RT/Scene.cpp:419-458): vertices (stride 32) + uint32 indices, 3 per triangle. */
-int brt_mesh_create(brt_context* ctx, const brt_vertex* vertices, uint32_t n_vertices,
+BRT_API int brt_mesh_create(brt_context* ctx, const brt_vertex* vertices, uint32_t n_vertices,
                     const uint32_t* indices, uint32_t n_indices, uint32_t* mesh_id);
 /* Scene::prepareRendering placeholder (RT/Scene.cpp:135-138, "LBVH not implemented!"): replace the
  * vertex array of a mesh; the next brt_scene_build rebuilds that BLAS with the GPU LBVH builder. */
-int brt_mesh_update_vertices(brt_context* ctx, uint32_t mesh_id, const brt_vertex* vertices, uint32_t n_vertices);
+BRT_API int brt_mesh_update_vertices(brt_context* ctx, uint32_t mesh_id, const brt_vertex* vertices, uint32_t n_vertices);
 /* extension (no reference counterpart): an analytic sphere usable as a mesh id in brt_instance_create */
-int brt_sphere_create(brt_context* ctx, const float center[3], float radius, uint32_t* mesh_id);
+BRT_API int brt_sphere_create(brt_context* ctx, const float center[3], float radius, uint32_t* mesh_id);
 /* Scene::createMaterial (RT/Scene.cpp:80-86) */
-int brt_material_create(brt_context* ctx, const brt_material* m, uint32_t* material_id);
+BRT_API int brt_material_create(brt_context* ctx, const brt_material* m, uint32_t* material_id);
 /* extension: dielectric parameters kept in a parallel array so the 52-byte material stays intact */
-int brt_material_set_transmission(brt_context* ctx, uint32_t material_id, float transmission, float ior);
+BRT_API int brt_material_set_transmission(brt_context* ctx, uint32_t material_id, float transmission, float ior);
 /* Scene::createLight (RT/Scene.cpp:88-97) */
-int brt_light_create(brt_context* ctx, const brt_light* l, uint32_t* light_id);
+BRT_API int brt_light_create(brt_context* ctx, const brt_light* l, uint32_t* light_id);
 /* Scene::createSky (RT/Scene.cpp:333-355) */
-int brt_sky_set(brt_context* ctx, const brt_sky* sky);
+BRT_API int brt_sky_set(brt_context* ctx, const brt_sky* sky);
 /* Scene::createInstance (RT/Scene.cpp:76-78) + MeshInstance::calculateTransformation
  * (RT/MeshInstance.h:82-85): xform is the row-major 3x4 object->world matrix of
  * VkAccelerationStructureInstanceKHR (RT/Scene.cpp:183-190). */
-int brt_instance_create(brt_context* ctx, uint32_t mesh_id, uint32_t material_id, const float xform3x4[12], uint32_t* instance_id);
-int brt_instance_set_transform(brt_context* ctx, uint32_t instance_id, const float xform3x4[12]);
-int brt_instance_set_material(brt_context* ctx, uint32_t instance_id, uint32_t material_id);
+BRT_API int brt_instance_create(brt_context* ctx, uint32_t mesh_id, uint32_t material_id, const float xform3x4[12], uint32_t* instance_id);
+BRT_API int brt_instance_set_transform(brt_context* ctx, uint32_t instance_id, const float xform3x4[12]);
+BRT_API int brt_instance_set_material(brt_context* ctx, uint32_t instance_id, uint32_t material_id);
 /* Scene::destroyInstance (RT/Scene.cpp:122-125): swap-remove, the last instance takes this id */
-int brt_instance_destroy(brt_context* ctx, uint32_t instance_id);
+BRT_API int brt_instance_destroy(brt_context* ctx, uint32_t instance_id);
 /* Scene::build (RT/Scene.cpp:100-120): BLAS for new/dirty meshes (GPU LBVH + SAH treelets + BVH8),
  * TLAS over the visible instances, material/light/instance tables. */
-int brt_scene_build(brt_context* ctx);
+BRT_API int brt_scene_build(brt_context* ctx);
 /* README.md:15-18 "Smart Culling": screen-space footprint per instance, hysteresis, then TLAS rebuild
  * over the survivors. threshold_px2 <= 0 makes every instance visible again. */
-int brt_smart_cull(brt_context* ctx, const brt_uniform* u, uint32_t width, uint32_t height,
+BRT_API int brt_smart_cull(brt_context* ctx, const brt_uniform* u, uint32_t width, uint32_t height,
                    float threshold_px2, float hysteresis, uint32_t* visible_count);
 /* copy the per-instance visibility flags (1 byte each) of the last brt_smart_cull to the host */
-int brt_get_visibility(brt_context* ctx, uint8_t* out, uint32_t n);
+BRT_API int brt_get_visibility(brt_context* ctx, uint8_t* out, uint32_t n);
 
 /* ---- render-frame entry (Pipeline::writeToUniformBuffer + traceRays, RT/RTPipeline.cpp:41-47) - */
 /* Traces the frame and, when rgba_host != NULL, copies the linear RGBA32F image (w*h*16 bytes, row
  * major, alpha = 1) back to host memory — the reference's outImage (SH/raytracing.slang:132).
  * With tile_world > 1 only the pixels of this rank's tiles are written, the rest stays 0. */
-int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, float* rgba_host);
+BRT_API int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, float* rgba_host);
 /* Same, but leaves the result on the device: d_tiles (device pointer, may be NULL) receives this
  * rank's tiles packed tile-major (brt_tile_buffer_bytes bytes) for the NCCL gather. */
-int brt_render_frame_tiles(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, void* d_tiles);
+BRT_API int brt_render_frame_tiles(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, void* d_tiles);
 /* bytes of one rank's packed tile buffer (identical on every rank: the tile count is padded) */
-size_t brt_tile_buffer_bytes(uint32_t width, uint32_t height, uint32_t tile_world);
+BRT_API size_t brt_tile_buffer_bytes(uint32_t width, uint32_t height, uint32_t tile_world);
 /* after the gather: d_all = tile_world packed buffers back to back (device) -> row-major RGBA32F
  * image at d_rgba (device). */
-int brt_untile(brt_context* ctx, const void* d_all, uint32_t width, uint32_t height, uint32_t tile_world, void* d_rgba);
+BRT_API int brt_untile(brt_context* ctx, const void* d_all, uint32_t width, uint32_t height, uint32_t tile_world, void* d_rgba);
 /* device pointer of the context's own full-frame RGBA32F image of the last frame */
-void* brt_device_image(brt_context* ctx);
+BRT_API void* brt_device_image(brt_context* ctx);
 
 /* ---- test / measurement only ---------------------------------------------------------------- */
 /* primary-hit AOVs of sample 0 of the last frame: uint32 prim id, uint32 instance id
  * (BRT_AOV_MISS on a miss), float hit distance; w*h elements each */
-int brt_get_aov(brt_context* ctx, int kind, void* out_host);
-int brt_get_stats(brt_context* ctx, brt_stats* out);
+BRT_API int brt_get_aov(brt_context* ctx, int kind, void* out_host);
+BRT_API int brt_get_stats(brt_context* ctx, brt_stats* out);
 /* Trace caller-supplied rays (8 floats each: origin xyz, tmin, direction xyz, tmax) against the
  * built scene; closest != 0: out = 4 x uint32 per ray {float bits of t, prim, instance, hit?};
  * closest == 0: out[4*i+3] = occluded ? 1 : 0. Used by the brute-force-vs-BVH equivalence tests. */
-int brt_trace_rays(brt_context* ctx, const float* rays_host, uint32_t n_rays, int closest, uint32_t* out_host);
+BRT_API int brt_trace_rays(brt_context* ctx, const float* rays_host, uint32_t n_rays, int closest, uint32_t* out_host);
 
 /* ---- host helper: Core::Camera + the uniform block of RTApp::run ---------------------------- */
 /* Camera::setView/updateView (Graphics/Camera.cpp:19-24,71-95), Camera::setPerspectiveProjection
  * (Graphics/Camera.cpp:8-17) and Uniform{inverse(transpose(view)), inverse(transpose(proj)), frame,
  * depthMax} (RT/RTApp.cpp:44-49). rot = (pitch x, yaw y, roll z), Tait-Bryan Y-X-Z. Pure host code. */
-void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar,
+BRT_API void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar,
                         uint32_t frame, uint32_t depth_max, brt_uniform* out);
 
 #ifdef __cplusplus

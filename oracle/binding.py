@@ -41,7 +41,9 @@ def load():
 def Oracle(pkg, brute_force=False, tile_rank=0, tile_world=1, threads=0):
     """An oracle context with the same Python surface as pkg.Context()."""
     flags = 0x80000000 if brute_force else 0
-    api = pkg.binding.SceneApi(load(), "orc_", 0, tile_rank, tile_world, flags)
+    C = ctypes
+    extra = {"set_threads": (C.c_int, [C.c_void_p, C.c_uint32]), "get_threads": (C.c_uint32, [C.c_void_p])}
+    api = pkg.binding.SceneApi(load(), "orc_", 0, tile_rank, tile_world, flags, extra_signatures=extra)
     if threads:
         api._f("set_threads")(api.ctx, threads)
     return api

@@ -221,8 +221,9 @@ static inline bool slab(const BNode& n, vec3 o, vec3 idir, float tmin, float tma
   float z0 = ((n.lo.z - e) - o.z) * idir.z, z1 = ((n.hi.z + e) - o.z) * idir.z;
   float tn = std::fmax(std::fmax(std::fmin(x0, x1), std::fmin(y0, y1)), std::fmin(z0, z1));
   float tf = std::fmin(std::fmin(std::fmax(x0, x1), std::fmax(y0, y1)), std::fmax(z0, z1));
-  float e0 = std::fmax(tn - std::fabs(tn) * pad, tmin);
-  float e1 = std::fmin(tf + std::fabs(tf) * pad, tmax);
+  // (multiplicative so that an infinite entry/exit stays infinite instead of turning into inf - inf = NaN)
+  float e0 = std::fmax(tn > 0.0f ? tn * (1.0f - pad) : tn * (1.0f + pad), tmin);
+  float e1 = std::fmin(tf > 0.0f ? tf * (1.0f + pad) : tf * (1.0f - pad), tmax);
   entry = e0;
   return e0 <= e1;
 }

@@ -1,0 +1,223 @@
+"""Parity cases shared by the CPU emulation tests (kernel logic, -m "not gpu") and the GPU tests proper
+(libbrt.so through the C ABI, -m gpu). `make` builds a context of the implementation under test,
+`orc_mod.Oracle(pkg)` the checker. Bars (BASELINE.json): primary-hit ids identical on >= 99.99 % of the
+pixels, linear radiance within 1e-3 relative RMSE; the arithmetic contract of DESIGN.md §3 in fact makes
+every case below bit-exact, which is asserted where noted."""
+import numpy as np
+import pytest
+
+from util import compare_frames, random_rays, render_pair
+
+R, T, D, J, SKY = 1, 2, 4, 8, 16  # BRT_RENDER_* flags
+
+FRAME_CASES = [  # name, scene, w, h, depth, flags, spp
+    ("c1_cornell_direct", "cornell", 128, 128, 1, 0, 1),
+    ("cornell_reflect_refract", "cornell", 96, 96, 3, R | T, 1),
+    ("cornell_gi_jitter_spp", "cornell", 64, 64, 5, R | T | D | J, 3),
+    ("cornell_diffuse_only", "cornell", 64, 64, 4, D, 2),
+    ("rtapp_demo_depth2", "rtapp", 160, 120, 2, 0, 1),
+    ("c2_terrain_bounces", "terrain", 160, 90, 3, R | T, 1),
+    ("c3_terrain_gi", "terrain", 96, 54, 5, R | T | D | J, 2),
+    ("c4_lattice_direct", "lattice", 160, 90, 1, 0, 1),
+    ("c5_terrain_diffuse8", "terrain_diffuse", 96, 54, 9, D, 1),
+]
+
+
+def frame_case(pkg, orc_mod, make, case):
+    name, kind, w, h, depth, flags, spp = case
+    scene = pkg.scenes.make_scene(kind, small=True)
+    r = render_pair(pkg, scene, make(), orc_mod.Oracle(pkg), w, h, depth, flags, spp)
+    assert r["id_agreement"] >= 0.9999, name
+    assert r["rmse"] <= 1e-3, name
+    assert r["stats"].rays_closest == r["ref_stats"].rays_closest, name
+    assert r["stats"].rays_occlusion == r["ref_stats"].rays_occlusion, name
+    assert r["t_agreement"] == 1.0 and r["bit_exact"], name  # stronger than the bar: identical bits
+    return r
+
+
+def sky_and_nonpoint_light(pkg, orc_mod, make):
+    """Sky miss colour (extension) and the constant-direction branch of processLight (SH/light.slang:33-36)."""
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    sky = pkg.Sky()
+    sky.skyColor[:] = (0.2, 0.4, 0.9)
+    sky.horizonColor[:] = (0.8, 0.8, 0.7)
+    sky.groundColor[:] = (0.2, 0.15, 0.1)
+    sky.upDirection[:] = (0.0, -1.0, 0.0)
+    sky.brightness, sky.horizonSize = 1.5, 0.4
+    for api in (a, b):
+        scene.upload(api, build=False)
+        api.sky_set(sky)
+        api.light_create((0, 0, 0), (1.0, 0.9, 0.8), 0.7, type=2)  # DIRECTIONAL
+        api.scene_build()
+    u = scene.uniform(a, 96, 96, 0, 3)
+    u.viewInverse[11] = -6.0  # step back so that some rays miss the box
+    r = compare_frames(pkg, a, b, u, 96, 96, R | T | SKY, 1)
+    assert r["id_agreement"] == 1.0 and r["bit_exact"]
+    assert (r["img"][..., :3].reshape(-1, 3)[a.get_aov(pkg.AOV_INST_ID, 96, 96).reshape(-1) == pkg.AOV_MISS] > 0).all()
+
+
+def random_rays_vs_brute_force(pkg, orc_mod, make, kind="terrain"):
+    """BVH8 traversal == brute force over all primitives (closest: same t bits, prim, instance; any-hit: same bool)."""
+    scene = pkg.scenes.make_scene(kind, small=True)
+    a, b = make(), orc_mod.Oracle(pkg, brute_force=True)
+    scene.upload(a)
+    scene.upload(b)
+    box = {"lattice": ((-5, -5, 9), (5, 5, 19)), "cornell": ((-1, -1, -1), (1, 1, 1))}.get(kind, ((-8, -4, -8), (8, 2, 8)))
+    rays = random_rays(20000, 11, *box)
+    # bounded segments too (shadow-ray style)
+    rays[::3, 7] = np.random.default_rng(5).random(len(rays[::3])).astype(np.float32) * 6.0
+    ha, hb = a.trace_rays(rays, True), b.trace_rays(rays, True)
+    assert np.array_equal(ha, hb)
+    assert hb[:, 3].sum() > 1000
+    oa, ob_ = a.trace_rays(rays, False), b.trace_rays(rays, False)
+    assert np.array_equal(oa[:, 3], ob_[:, 3])
+
+
+def grazing_and_axis_aligned_rays(pkg, orc_mod, make):
+    """Rays with zero direction components, rays inside box faces and along triangle edges of the Cornell box."""
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    a, b = make(), orc_mod.Oracle(pkg, brute_force=True)
+    scene.upload(a)
+    scene.upload(b)
+    rays = []
+    for ax in range(3):
+        for sgn in (1.0, -1.0):
+            for off in np.linspace(-1.0, 1.0, 41, dtype=np.float32):
+                for off2 in (-1.0, -0.5, 0.0, 0.25, 1.0):
+                    o = np.zeros(3, np.float32)
+                    o[ax] = -3.0 * sgn
+                    o[(ax + 1) % 3] = off
+                    o[(ax + 2) % 3] = off2
+                    d = np.zeros(3, np.float32)
+                    d[ax] = sgn
+                    rays.append(np.concatenate([o, [0.001], d, [1e32]]))
+    rays = np.array(rays, np.float32)
+    assert np.array_equal(a.trace_rays(rays, True), b.trace_rays(rays, True))
+    assert np.array_equal(a.trace_rays(rays, False)[:, 3], b.trace_rays(rays, False)[:, 3])
+
+
+def edge_cases(pkg, orc_mod, make):
+    """Empty scene, empty mesh, single triangle, duplicate triangles (tie-break), tiny and huge coordinates."""
+    S = pkg.scenes
+    # empty scene: every pixel misses, image is black with alpha 1
+    a, b = make(), orc_mod.Oracle(pkg)
+    for api in (a, b):
+        api.scene_build()
+    u = a.camera_uniform((0, 0, -2), (0, 0, 0), 1.0, 1.0, frame=0, depth_max=2)
+    r = compare_frames(pkg, a, b, u, 40, 24)
+    assert r["bit_exact"] and (a.get_aov(pkg.AOV_INST_ID, 40, 24) == pkg.AOV_MISS).all()
+    assert np.array_equal(r["img"][..., 3], np.ones((24, 40), np.float32))
+    # empty mesh + single triangle + two coincident triangles in different instances (lowest instance wins)
+    tri = np.zeros((3, 8), np.float32)
+    tri[:, 0:3] = [(-1, -1, 1), (1, -1, 1), (0, 1, 1)]
+    tri[:, 3:6] = (0, 0, -1)
+    a, b = make(), orc_mod.Oracle(pkg)
+    for api in (a, b):
+        e = api.mesh_create(np.zeros((0, 8), np.float32), np.zeros(0, np.uint32))
+        m = api.mesh_create(tri, [0, 1, 2])
+        dup = api.mesh_create(np.concatenate([tri, tri]), [0, 1, 2, 3, 4, 5])
+        mat = api.material_create((0.8, 0.8, 0.8))
+        api.light_create((0, 0, -1), (1, 1, 1), 3.0)
+        api.instance_create(e, mat, S.xform())
+        api.instance_create(m, mat, S.xform())
+        api.instance_create(m, mat, S.xform())                       # coincident with the previous one
+        api.instance_create(dup, mat, S.xform(translate=(3, 0, 0)))   # coincident primitives 0 and 1
+        api.instance_create(m, mat, S.xform(scale=(1e-3, 1e-3, 1e-3), translate=(-0.5, 0.9, -1.9)))
+        api.instance_create(m, mat, S.xform(scale=(3e3, 3e3, 3e3), translate=(0, 0, 5e3)))
+        api.scene_build()
+    u = a.camera_uniform((0.4, 0, -2), (0, 0.2, 0), 1.2, 1.5, frame=3, depth_max=2)
+    r = compare_frames(pkg, a, b, u, 96, 64, R | D, 2)
+    assert r["id_agreement"] == 1.0 and r["bit_exact"]
+    inst = a.get_aov(pkg.AOV_INST_ID, 96, 64)
+    prim = a.get_aov(pkg.AOV_PRIM_ID, 96, 64)
+    assert (inst == 1).any() and not (inst == 2).any()           # tie between instances 1 and 2 -> 1
+    assert ((inst == 3) & (prim == 0)).any() and not ((inst == 3) & (prim == 1)).any()
+
+
+def dynamic_rebuild_and_instances(pkg, orc_mod, make):
+    """Scene::prepareRendering placeholder (RT/Scene.cpp:135-138): vertex update + BLAS rebuild; instance
+    set_transform / set_material / destroy (swap-remove, RT/Scene.cpp:122-125)."""
+    scene = pkg.scenes.make_scene("lattice", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    base = scene.meshes[1][1]
+    w, h = 128, 72
+    for frame in range(3):
+        v = pkg.scenes.animate_icosphere(base, frame)
+        for api in (a, b):
+            api.mesh_update_vertices(1, v)
+            if frame == 1:
+                api.instance_set_transform(0, pkg.scenes.xform((1.5, 1.5, 1.5), (0.5, -0.5, 9.0)))
+                api.instance_set_material(2, 1)
+            if frame == 2:
+                api.instance_destroy(1)
+            api.scene_build()
+        assert a.get_stats().blas_built == 1
+        u = scene.uniform(a, w, h, frame, 1)
+        r = compare_frames(pkg, a, b, u, w, h)
+        assert r["id_agreement"] == 1.0 and r["bit_exact"], frame
+
+
+def smart_culling(pkg, orc_mod, make):
+    """README.md:15-18: per-instance screen footprint, hysteresis, TLAS over the survivors."""
+    scene = pkg.scenes.make_scene("lattice", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    n = len(scene.instances)
+    w, h = 128, 72
+    seen = set()
+    for step, (z, thr) in enumerate([(-12.0, 40.0), (-30.0, 40.0), (-26.0, 40.0), (-12.0, 40.0), (-12.0, 0.0)]):
+        u = a.camera_uniform((0.0, 0.0, z), (0, 0, 0), scene.fovy, w / h, frame=step, depth_max=1)
+        va, vb = a.smart_cull(u, w, h, thr, 0.25), b.smart_cull(u, w, h, thr, 0.25)
+        assert va == vb
+        assert np.array_equal(a.get_visibility(n), b.get_visibility(n))
+        seen.add(va)
+        r = compare_frames(pkg, a, b, u, w, h)
+        assert r["id_agreement"] == 1.0 and r["bit_exact"], step
+        assert a.get_stats().instances_visible == va
+    assert len(seen) > 1 and n in seen  # culling removed something, threshold 0 restored everything
+
+
+def tiles_and_crop(pkg, orc_mod, make_ranked):
+    """tile_rank / tile_world partition (32x32 tiles round-robin) and the crop window."""
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    w, h = 100, 70  # not a multiple of the tile size
+    full = orc_mod.Oracle(pkg)
+    scene.upload(full)
+    u = scene.uniform(full, w, h, 0, 2)
+    ref = full.render_frame(u, full.opts(w, h, 1, R | T))
+    world = 3
+    acc = np.zeros_like(ref)
+    for rank in range(world):
+        api = make_ranked(rank, world)
+        scene.upload(api)
+        part = api.render_frame(u, api.opts(w, h, 1, R | T))
+        ty, tx = np.meshgrid(np.arange(h) // 32, np.arange(w) // 32, indexing="ij")
+        own = (ty * ((w + 31) // 32) + tx) % world == rank
+        assert (part[~own] == 0).all()
+        assert np.array_equal(part[own].view(np.uint32), ref[own].view(np.uint32))
+        acc += part
+    assert np.array_equal(acc.view(np.uint32), ref.view(np.uint32))
+    api = make_ranked(0, 1)
+    scene.upload(api)
+    crop = (17, 9, 50, 40)
+    part = api.render_frame(u, api.opts(w, h, 1, R | T, crop))
+    mask = np.zeros((h, w), bool)
+    mask[9:49, 17:67] = True
+    assert (part[~mask] == 0).all() and np.array_equal(part[mask].view(np.uint32), ref[mask].view(np.uint32))
+
+
+def error_behaviour(pkg, make):
+    a = make()
+    with pytest.raises(pkg.BrtError):
+        a.mesh_create(np.zeros((3, 8), np.float32), [0, 1, 5])
+    with pytest.raises(pkg.BrtError):
+        a.instance_create(0, 0, np.eye(3, 4))
+    with pytest.raises(pkg.BrtError):
+        u = a.camera_uniform((0, 0, 0), (0, 0, 0), 1.0, 1.0)
+        a.render_frame(u, a.opts(4, 4))
+    with pytest.raises(pkg.BrtError):
+        a.sphere_create((0, 0, 0), -1.0)

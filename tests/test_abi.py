@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol include/brt.h declares; PODs have the reference's byte
+layouts; without a GPU the library fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_every_declared_symbol(pkg):
+    lib = pkg.load()
+    header = open(os.path.join(ROOT, "include", "brt.h")).read()
+    declared = sorted(set(re.findall(r"\b(brt_[a-z_0-9]+)\s*\(", header)))
+    assert declared == sorted(pkg.binding.BRT_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_pod_layouts(pkg):
+    B = pkg.binding
+    assert C.sizeof(B.Vertex) == 32 and B.Vertex.normal.offset == 12 and B.Vertex.uv.offset == 24
+    assert C.sizeof(B.Material) == 52 and B.Material.metallic.offset == 16 and B.Material.clearCoatGloss.offset == 48
+    assert C.sizeof(B.Light) == 32 and B.Light.color.offset == 12 and B.Light.intensity.offset == 24 and B.Light.type.offset == 28
+    assert C.sizeof(B.Uniform) == 140 and B.Uniform.projInverse.offset == 64 and B.Uniform.frame.offset == 128
+    assert B.Uniform.depthMax.offset == 132 and B.Uniform.lightThreshold.offset == 136
+    assert C.sizeof(B.Sky) == 88
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device brt_create must fail (BRT_ERR_CUDA); with one it must succeed."""
+    import torch
+    if torch.cuda.is_available():
+        ctx = pkg.Context(device=0)
+        ctx.close()
+    else:
+        with pytest.raises(pkg.BrtError, match="status 2"):
+            pkg.Context(device=0)
+
+
+def test_product_does_not_reference_oracle():
+    """Nothing under the package or include/ may import, link or name the oracle or the emulation shim."""
+    pkg_dir = os.path.join(ROOT, "hardware-ray-tracer_b200")
+    for base, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
+                text = open(os.path.join(base, f)).read()
+                assert "liboracle" not in text and not re.search(r"\borc_", text), os.path.join(base, f)
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), os.path.join(base, f)
+                assert "libbrt_emu" not in text, os.path.join(base, f)
+
+
+def test_tile_buffer_bytes(pkg):
+    lib = pkg.load()
+    lib.brt_tile_buffer_bytes.restype = C.c_size_t
+    lib.brt_tile_buffer_bytes.argtypes = [C.c_uint32] * 3
+    assert lib.brt_tile_buffer_bytes(1920, 1080, 1) == 60 * 34 * 1024 * 16
+    assert lib.brt_tile_buffer_bytes(1920, 1080, 8) == ((60 * 34 + 7) // 8) * 1024 * 16
+    assert lib.brt_tile_buffer_bytes(31, 1, 4) == 1024 * 16

@@ -1,0 +1,62 @@
+"""Kernel LOGIC of the CUDA path checked on the CPU: the product's kernel bodies (csrc/*.cuh) compiled by
+g++ as sequential loops (tests/emu, test infrastructure only) against the oracle. The GPU tests
+(test_gpu_parity.py, -m gpu) run the same cases through libbrt.so."""
+import pytest
+
+import parity_cases as pc
+
+
+@pytest.fixture()
+def make(pkg, emu_lib):
+    return lambda flags=0: pkg.binding.SceneApi(emu_lib, "brt_", 0, 0, 1, flags)
+
+
+@pytest.mark.parametrize("case", pc.FRAME_CASES, ids=[c[0] for c in pc.FRAME_CASES])
+def test_frames(pkg, orc_mod, make, case):
+    pc.frame_case(pkg, orc_mod, make, case)
+
+
+def test_sky_and_nonpoint_light(pkg, orc_mod, make):
+    pc.sky_and_nonpoint_light(pkg, orc_mod, make)
+
+
+@pytest.mark.parametrize("kind", ["terrain", "lattice", "cornell"])
+def test_random_rays_vs_brute_force(pkg, orc_mod, make, kind):
+    pc.random_rays_vs_brute_force(pkg, orc_mod, make, kind)
+
+
+def test_grazing_and_axis_aligned_rays(pkg, orc_mod, make):
+    pc.grazing_and_axis_aligned_rays(pkg, orc_mod, make)
+
+
+def test_edge_cases(pkg, orc_mod, make):
+    pc.edge_cases(pkg, orc_mod, make)
+
+
+def test_dynamic_rebuild_and_instances(pkg, orc_mod, make):
+    pc.dynamic_rebuild_and_instances(pkg, orc_mod, make)
+
+
+def test_smart_culling(pkg, orc_mod, make):
+    pc.smart_culling(pkg, orc_mod, make)
+
+
+def test_tiles_and_crop(pkg, orc_mod, emu_lib):
+    pc.tiles_and_crop(pkg, orc_mod, lambda rank, world: pkg.binding.SceneApi(emu_lib, "brt_", 0, rank, world, 0))
+
+
+def test_error_behaviour(pkg, make):
+    pc.error_behaviour(pkg, make)
+
+
+def test_counters_flag(pkg, orc_mod, make):
+    """BRT_CFG_COUNTERS fills the node / primitive visit counters that feed the roofline's algorithmic bytes."""
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a = make(pkg.CFG_COUNTERS)
+    scene.upload(a)
+    u = scene.uniform(a, 64, 36, 0, 2)
+    a.render_frame(u, a.opts(64, 36, 1, 1))
+    st = a.get_stats()
+    assert st.nodes_visited_closest > st.rays_closest > 0 and st.prims_tested_closest > 0
+    assert st.nodes_visited_occlusion > 0 and st.total_triangles == scene.triangles()
+    assert st.bvh_nodes > 0 and st.bvh_bytes > st.total_triangles
