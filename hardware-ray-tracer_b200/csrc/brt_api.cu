@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -143,7 +144,7 @@ struct brt_context {
   DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib, s_o, s_d, s_target;
   DevBuf d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
-  std::vector<EventPair> events;
+  std::deque<EventPair> events;  // deque: references stay valid while the pool grows
   size_t events_used = 0;
   brt_stats stats{};
 };

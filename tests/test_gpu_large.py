@@ -56,7 +56,7 @@ def test_c2_full_frame_properties(pkg, terrain, gpu_terrain):
     assert st.rays_occlusion <= 3 * st.rays_closest
     assert np.isfinite(full).all() and (full[..., :3] >= 0).all() and (full[..., 3] == 1).all()
     inst = gpu_terrain.get_aov(pkg.AOV_INST_ID, w, h)
-    assert (inst != pkg.AOV_MISS).mean() > 0.5
+    assert (inst != pkg.AOV_MISS).mean() > 0.3
     crop = (700, 400, 320, 200)
     part = gpu_terrain.render_frame(u, gpu_terrain.opts(w, h, 1, R | T, crop))
     assert np.array_equal(part[400:600, 700:1020].view(np.uint32), full[400:600, 700:1020].view(np.uint32))
