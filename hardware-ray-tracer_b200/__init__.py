@@ -22,10 +22,11 @@ def load():
     """dlopen lib/libbrt.so (built by __graft_entry__.build() / csrc/Makefile). Fails loudly."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+        path = os.environ.get("BRT_LIB", LIB_PATH)  # developer override: an alternative build of the same library
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
-        _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        _lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
     return _lib
 
 

@@ -26,30 +26,81 @@ BRT_KERNEL_1D(k_cull, CullParams, cull_body)
 #ifdef BRT_EMU
 template <bool ANY, bool COUNT>
 static void k_trace(const TraceParams p) {
-  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
+  const uint32_t n = trace_total(p);
   TraceCounters c{0, 0, 0};
   unsigned long long rays = 0;
-  for (uint32_t i = 0; i < n; ++i) rays += (ANY ? trace_occlusion_body<COUNT>(p, i, c) : trace_closest_body<COUNT>(p, i, c)) ? 1 : 0;
+  Traversal<ANY, COUNT> t;
+  uint2 stack[BRT_STACK_SIZE];
+  for (uint32_t w = 0; w < n; ++w) {
+    const uint32_t i = trace_slot(p, w);
+    if (!trace_load(p, i, t)) continue;
+    rays++;
+    while (!t.step(stack, c)) {}
+    trace_store(p, i, t);
+  }
   if (ANY) { p.stats->rays_occlusion += rays; p.stats->nodes_o += c.nodes; p.stats->prims_o += c.prims; p.stats->spheres_o += c.spheres; }
   else { p.stats->rays_closest += rays; p.stats->nodes_c += c.nodes; p.stats->prims_c += c.prims; p.stats->spheres_c += c.spheres; }
 }
 #define BRT_LAUNCH_TRACE(ANY, COUNT, params, grid, stream) k_trace<ANY, COUNT>(params)
 #else
-// Persistent warps: each warp claims 32 consecutive rays at a time from a global cursor, so the SMs
-// stay busy until the queue is empty no matter how uneven the per-ray cost is.
+#ifndef BRT_TRACE_MIN_BLOCKS
+#define BRT_TRACE_MIN_BLOCKS 6
+#endif
+#ifndef BRT_REFILL_LANES
+#define BRT_REFILL_LANES 0  // lanes of a warp that must still be traversing; below that the idle lanes fetch new rays
+#endif
+// Persistent warps with per-lane refill: every lane runs one ray's Traversal; when fewer than
+// BRT_REFILL_LANES lanes of the warp are still busy, the idle lanes claim the next rays of the queue from
+// a global cursor (one warp-aggregated atomic) so that the SIMD lanes stay occupied however uneven the
+// per-ray cost is. The first fetch of a warp is 32 consecutive rays = one 8x4 pixel block (coherent).
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(const TraceParams p) {
-  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const TraceParams p) {
+  const uint32_t n = trace_total(p);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
   TraceCounters c{0, 0, 0};
   uint32_t rays = 0;
+  Traversal<ANY, COUNT> t;
+  uint2 stack[BRT_STACK_SIZE];
+  bool active = false;
+  bool exhausted = false;  // warp-uniform
+  uint32_t ray = 0;
   for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(p.work, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    if (i < n) rays += (ANY ? trace_occlusion_body<COUNT>(p, i, c) : trace_closest_body<COUNT>(p, i, c)) ? 1u : 0u;
+    if (!exhausted) {
+      const unsigned idle = __ballot_sync(0xffffffffu, !active);
+      const int n_idle = __popc(idle);
+      const int leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(p.work, (uint32_t)n_idle);
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (!active) {
+        const uint32_t w = base + (uint32_t)__popc(idle & lt);
+        if (w < n) {
+          const uint32_t i = trace_slot(p, w);
+          if (trace_load(p, i, t)) {
+            active = true;
+            ray = i;
+            rays++;
+          }
+        }
+      }
+      exhausted = base + (uint32_t)n_idle >= n;
+    }
+    if (!__any_sync(0xffffffffu, active)) {
+      if (exhausted) break;
+      continue;  // only padding slots were fetched: fetch again
+    }
+    if (active) {
+      for (;;) {
+        if (t.step(stack, c)) {
+          trace_store(p, ray, t);
+          active = false;
+          break;
+        }
+        if (!exhausted && __popc(__activemask()) < BRT_REFILL_LANES) break;
+      }
+    }
+    __syncwarp();
   }
   rays = __reduce_add_sync(0xffffffffu, rays);
   if (COUNT) {
@@ -339,7 +390,7 @@ void scene_build(brt_context* c) {
   cudaEventDestroy(e1);
   cudaEventDestroy(e2);
   c->stats.blas_built = rebuilt;
-  if (c->tlas.levels + max_blas_levels(c) + 4 > BRT_STACK_SIZE) throw LimitError("scene_build: BVH deeper than the traversal stack");
+  if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) throw LimitError("scene_build: BVH deeper than the traversal stack allows");
   c->built = true;
   refresh_scene_stats(c);
 }
@@ -463,9 +514,9 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         BRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
         // round 0 walks all `cap` slots (padding slots carry px == BRT_MISS)
       } else {
-        // keep n_paths[cur]; zero n_paths[next], n_shadow and the work cursors
+        // keep n_paths[cur]; zero n_paths[next], the work cursors and the shadow counters
         BRT_CUDA(cudaMemsetAsync(&ctr->n_paths[cur ^ 1], 0, 4, s));
-        BRT_CUDA(cudaMemsetAsync(&ctr->n_shadow, 0, sizeof(FrameCounters) - offsetof(FrameCounters, n_shadow), s));
+        BRT_CUDA(cudaMemsetAsync(&ctr->work_closest, 0, sizeof(FrameCounters) - offsetof(FrameCounters, work_closest), s));
       }
       const uint32_t* count_ptr = round == 0 ? nullptr : &ctr->n_paths[cur];
       const PathQueue qc = queue_of(c, cur), qn = queue_of(c, cur ^ 1);
@@ -522,7 +573,9 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       if (n_lights) {
         TraceParams tp{};
         tp.count = 0;
-        tp.count_ptr = &ctr->n_shadow;
+        tp.seg_counts = ctr->n_shadow;
+        tp.n_segs = n_lights;
+        tp.seg_stride = cap;
         tp.tlas = tlas;
         tp.insts = insts;
         tp.o = c->s_o.as<float4>();
@@ -858,7 +911,7 @@ int brt_smart_cull(brt_context* c, const brt_uniform* u, uint32_t width, uint32_
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaEventDestroy(e2);
-    if (c->tlas.levels + max_blas_levels(c) + 4 > BRT_STACK_SIZE) throw LimitError("smart_cull: BVH deeper than the traversal stack");
+    if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) throw LimitError("smart_cull: BVH deeper than the traversal stack allows");
     refresh_scene_stats(c);
     if (visible_count) {
       uint32_t k = 0;

@@ -14,11 +14,13 @@
 // ---- host emulation: plain C++ ------------------------------------------------------------------
 #include "cuda_emu.h"  // tests/emu/: vector types + a stand-in for the few runtime calls used
 #define BRT_HD static inline
+#define BRT_HDM inline  /* member functions */
 #define BRT_HDH static inline
 #define BRT_DEVICE_ONLY 0
 #else
 #include <cuda_runtime.h>
 #define BRT_HD __device__ __forceinline__
+#define BRT_HDM __device__ __forceinline__
 #define BRT_HDH __host__ __device__ __forceinline__
 #define BRT_DEVICE_ONLY 1
 #endif

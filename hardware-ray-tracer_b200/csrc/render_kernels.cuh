@@ -24,9 +24,8 @@ struct PathQueue {  // structure of arrays, one slot per live path
 
 struct FrameCounters {  // device-side, reset per round
   uint32_t n_paths[2];  // live paths in queue 0 / 1
-  uint32_t n_shadow;
   uint32_t work_closest, work_occl;  // dynamic-fetch cursors of the trace kernels
-  uint32_t pad[3];
+  uint32_t n_shadow[BRT_MAX_LIGHTS];  // shadow rays queued per light (segment l of the shadow queue)
 };
 struct FrameStats {  // device-side, reset per frame
   unsigned long long rays_closest, rays_occlusion;
@@ -110,27 +109,49 @@ struct TraceParams {
   float4* contrib;         // occlusion: zeroed when the ray is blocked
   uint32_t* work;          // dynamic-fetch cursor (device kernels)
   FrameStats* stats;
+  // optional segmented queue: n_segs segments of `seg_stride` slots, segment k holds seg_counts[k] rays.
+  // (The shadow queue has one segment per light so that neighbouring lanes trace towards the same light.)
+  const uint32_t* seg_counts;
+  uint32_t n_segs, seg_stride;
 };
-template <bool COUNT>
-BRT_HD bool trace_closest_body(const TraceParams& p, uint32_t i, TraceCounters& ctr) {
-  if (p.px && p.px[i] == BRT_MISS) {
+BRT_HD uint32_t trace_total(const TraceParams& p) {
+  if (p.seg_counts) {
+    uint32_t n = 0;
+    for (uint32_t k = 0; k < p.n_segs; ++k) n += p.seg_counts[k];
+    return n;
+  }
+  return p.count_ptr ? *p.count_ptr : p.count;
+}
+// work item (0 .. trace_total) -> queue slot
+BRT_HD uint32_t trace_slot(const TraceParams& p, uint32_t w) {
+  if (!p.seg_counts) return w;
+  uint32_t k = 0;
+  for (; k + 1 < p.n_segs; ++k) {
+    const uint32_t c = p.seg_counts[k];
+    if (w < c) break;
+    w -= c;
+  }
+  return k * p.seg_stride + w;
+}
+// load ray i into a traversal; false for a padding slot (its miss is written right away)
+template <bool ANY, bool COUNT>
+BRT_HD bool trace_load(const TraceParams& p, uint32_t i, Traversal<ANY, COUNT>& t) {
+  if (!ANY && p.px && p.px[i] == BRT_MISS) {
     p.hit_inst[i] = BRT_MISS;
     return false;
   }
   const float4 o = p.o[i], d = p.d[i];
-  Hit h;
-  trace_ray<false, COUNT>(p.tlas, p.insts, F3(o.x, o.y, o.z), F3(d.x, d.y, d.z), o.w, d.w, h, ctr);
-  p.hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
-  p.hit_inst[i] = h.inst;
+  t.init(p.tlas, p.insts, F3(o.x, o.y, o.z), F3(d.x, d.y, d.z), o.w, d.w);
   return true;
 }
-template <bool COUNT>
-BRT_HD bool trace_occlusion_body(const TraceParams& p, uint32_t i, TraceCounters& ctr) {
-  const float4 o = p.o[i], d = p.d[i];
-  Hit h;
-  if (trace_ray<true, COUNT>(p.tlas, p.insts, F3(o.x, o.y, o.z), F3(d.x, d.y, d.z), o.w, d.w, h, ctr))
-    p.contrib[p.target[i]] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // shadow factor 0 (SH/raytracing.slang:69)
-  return true;
+template <bool ANY, bool COUNT>
+BRT_HD void trace_store(const TraceParams& p, uint32_t i, const Traversal<ANY, COUNT>& t) {
+  if (ANY) {
+    if (t.found) p.contrib[p.target[i]] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // shadow factor 0 (SH/raytracing.slang:69)
+  } else {
+    p.hit[i] = make_float4(t.best.t, t.best.u, t.best.v, u2f(t.best.prim));
+    p.hit_inst[i] = t.best.inst;
+  }
 }
 
 // ---- shade ---------------------------------------------------------------------------------------
@@ -266,7 +287,7 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
         contrib = color * F3(lr.pos_colr.w, lr.color_g, lr.color_b) * intensity;  // :83
         if (!(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f)) {
           const f3 so = worldPos + N * 0.0001f;  // testShadow :56-70
-          const uint32_t k = append_slot(&p.ctr->n_shadow);
+          const uint32_t k = l * p.cap + append_slot(&p.ctr->n_shadow[l]);
           p.s_o[k] = make_float4(so.x, so.y, so.z, 0.001f);
           p.s_d[k] = make_float4(L.x, L.y, L.z, length(ldir));
           p.s_target[k] = l * p.cap + i;

@@ -40,6 +40,27 @@ BRT_HD RayBox make_raybox(f3 d) {
 
 BRT_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
+// byte i of w -> the float 32768 + byte, built with ONE byte permute: 0x47000000 is 2^15 and byte 1 of
+// a binary32 with that exponent has weight 1. (An I2F.U8 conversion would run on the quarter-rate XU
+// pipe; ncu showed it as the busiest pipe of the first version of this kernel.)
+template <int I>
+BRT_HD float magic_byte(uint32_t w, uint32_t magic /* 0x47000000, held in a register */) {
+#ifdef BRT_EMU
+  return u2f(magic | (((w >> (8 * I)) & 0xffu) << 8));
+#else
+  return __uint_as_float(__byte_perm(w, magic, 0x7604u | (I << 4)));
+#endif
+}
+BRT_HD uint32_t magic_register() {
+#ifdef BRT_EMU
+  return 0x47000000u;
+#else
+  uint32_t m;  // opaque to the compiler: otherwise it folds the constant into the PRMT and spends a MOV per
+  asm("mov.b32 %0, 0x47000000;" : "=r"(m));  // permute on materialising the selector instead
+  return m;
+#endif
+}
+
 // Tests the ray against the 8 quantised child boxes of one node.
 // out: G = (child_base, inner hits << 24 | imask), Gt = (prim_base, leaf hit bits)
 BRT_HD void intersect_node(const Node8* __restrict__ node, const RayBox& rb, f3 o, float tmin, float tmax, uint2& G, uint2& Gt) {
@@ -54,72 +75,100 @@ BRT_HD void intersect_node(const Node8* __restrict__ node, const RayBox& rb, f3 
   // Rounding slack. The slab arithmetic below and the (differently rounded) primitive tests both
   // carry errors of a few ulps of the largest coordinate difference involved; widening every slab
   // by 2^-21 of that magnitude keeps the box test conservative with respect to the primitive tests.
+  // The 2^-8 grid-step term covers the rounding of the (origin - 32768 * step) constants below.
   const float mag = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz)) + 256.0f * fmaxf(fmaxf(sx, sy), sz);
   const float slack = mag * 4.76837158e-07f;
-  const float ex = slack * fabsf(rb.idir.x), ey = slack * fabsf(rb.idir.y), ez = slack * fabsf(rb.idir.z);
+  const float ex = fma_rn(fabsf(idx), 0.00390625f, slack * fabsf(rb.idir.x));
+  const float ey = fma_rn(fabsf(idy), 0.00390625f, slack * fabsf(rb.idir.y));
+  const float ez = fma_rn(fabsf(idz), 0.00390625f, slack * fabsf(rb.idir.z));
   const float ox = px * rb.idir.x, oy = py * rb.idir.y, oz = pz * rb.idir.z;
-  const float ox0 = ox - ex, ox1 = ox + ex, oy0 = oy - ey, oy1 = oy + ey, oz0 = oz - ez, oz1 = oz + ez;
+  // t = (32768 + q) * step + (origin - 32768 * step)
+  const float ox0 = fma_rn(-32768.0f, idx, ox - ex), ox1 = fma_rn(-32768.0f, idx, ox + ex);
+  const float oy0 = fma_rn(-32768.0f, idy, oy - ey), oy1 = fma_rn(-32768.0f, idy, oy + ey);
+  const float oz0 = fma_rn(-32768.0f, idz, oz - ez), oz1 = fma_rn(-32768.0f, idz, oz + ez);
   const bool nx = rb.idir.x < 0.0f, ny = rb.idir.y < 0.0f, nz = rb.idir.z < 0.0f;
+  const uint32_t octinv4 = rb.octinv * 0x01010101u;
+  const uint32_t mg = magic_register();
   uint32_t hitmask = 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const uint32_t meta4 = h ? n1.w : n1.z;
+    // four slots at a time: inner slots (low 5 bits = 11sss) get their bit index XORed with octinv
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     const uint32_t lox4 = h ? n2.y : n2.x, loy4 = h ? n2.w : n2.z, loz4 = h ? n3.y : n3.x;
     const uint32_t hix4 = h ? n3.w : n3.z, hiy4 = h ? n4.y : n4.x, hiz4 = h ? n4.w : n4.z;
     const uint32_t nearx4 = nx ? hix4 : lox4, farx4 = nx ? lox4 : hix4;
     const uint32_t neary4 = ny ? hiy4 : loy4, fary4 = ny ? loy4 : hiy4;
     const uint32_t nearz4 = nz ? hiz4 : loz4, farz4 = nz ? loz4 : hiz4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t meta = byte_of(meta4, i);
-      const float t0x = fma_rn((float)byte_of(nearx4, i), idx, ox0), t1x = fma_rn((float)byte_of(farx4, i), idx, ox1);
-      const float t0y = fma_rn((float)byte_of(neary4, i), idy, oy0), t1y = fma_rn((float)byte_of(fary4, i), idy, oy1);
-      const float t0z = fma_rn((float)byte_of(nearz4, i), idz, oz0), t1z = fma_rn((float)byte_of(farz4, i), idz, oz1);
-      const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-      const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-      if (meta != 0u && tn <= tf) {
-        const uint32_t inner = (meta & 0x18u) == 0x18u ? rb.octinv : 0u;
-        hitmask |= (meta >> 5) << ((meta ^ inner) & 31u);
-      }
-    }
+#define BRT_SLOT(I)                                                                                                         \
+  {                                                                                                                         \
+    const float t0x = fma_rn(magic_byte<I>(nearx4, mg), idx, ox0), t1x = fma_rn(magic_byte<I>(farx4, mg), idx, ox1);               \
+    const float t0y = fma_rn(magic_byte<I>(neary4, mg), idy, oy0), t1y = fma_rn(magic_byte<I>(fary4, mg), idy, oy1);               \
+    const float t0z = fma_rn(magic_byte<I>(nearz4, mg), idz, oz0), t1z = fma_rn(magic_byte<I>(farz4, mg), idz, oz1);               \
+    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));                                                              \
+    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                                                              \
+    if (tn <= tf) hitmask |= byte_of(child_bits4, I) << byte_of(bit_index4, I); /* empty slot: child bits are 0 */          \
+  }
+    BRT_SLOT(0) BRT_SLOT(1) BRT_SLOT(2) BRT_SLOT(3)
+#undef BRT_SLOT
   }
   G = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
   Gt = make_uint2(n1.y, hitmask & 0x00ffffffu);
 }
 
-// lexicographic (t, instance, primitive) order
-BRT_HD bool better_hit(float t, uint32_t inst, uint32_t prim, bool found, const Hit& best) {
-  if (!found || t < best.t) return true;
-  return t == best.t && (inst < best.inst || (inst == best.inst && prim < best.prim));
-}
-
-// ANY: occlusion query (RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | SKIP_CLOSEST_HIT_SHADER) — returns
-// at the first primitive with tmin < t < tmax. Otherwise: closest-hit query, `best` is filled.
+// One ray's traversal as a resumable state machine: init(), then step() until it returns true.
+// The CUDA kernel (brt_api.cu) keeps one Traversal per lane and refills finished lanes with new rays;
+// the host emulation simply loops.
+// ANY: occlusion query (RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | SKIP_CLOSEST_HIT_SHADER) — ends at
+// the first primitive with tmin < t < tmax. Otherwise: closest-hit query, `best` is filled.
 template <bool ANY, bool COUNT>
-BRT_HD bool trace_ray(const Node8* __restrict__ tlas, const InstRec* __restrict__ insts, f3 o, f3 d, float tmin, float tmax, Hit& best,
-                      TraceCounters& ctr) {
-  best.t = tmax;
-  best.u = 0.0f;
-  best.v = 0.0f;
-  best.inst = BRT_MISS;
-  best.prim = BRT_MISS;
-  bool found = false;
-  if (tlas == nullptr) return false;
+struct Traversal {
+  const Node8* tlas;
+  const InstRec* insts;
+  f3 o, d;  // world ray
+  float tmin;
+  f3 co;    // origin in the current space (world, or the object space of cur_inst)
+  RayBox rb;
+  RayShear sh;
+  const Node8* nodes;
+  const TriRec* tris;
+  uint32_t cur_inst;
+  uint2 G, Gt;
+  int sp, blas_sp;  // blas_sp >= 0 while inside a BLAS: stack height at entry
+  bool found;
+  Hit best;
+  // the stack itself (uint2[BRT_STACK_SIZE]) is a separate local array owned by the caller: keeping the
+  // dynamically indexed array out of this struct lets the compiler hold every other member in registers
 
-  uint2 stack[BRT_STACK_SIZE];
-  int sp = 0;
-  int blas_sp = -1;  // >= 0 while inside a BLAS: stack height at entry
-  const RayBox wrb = make_raybox(d);
-  RayBox rb = wrb;
-  f3 co = o, cd = d;
-  RayShear sh = make_shear(d);
-  const Node8* nodes = tlas;
-  const TriRec* tris = nullptr;
-  uint32_t cur_inst = 0;
-  uint2 G = make_uint2(0u, 0x80000000u);
-  uint2 Gt = make_uint2(0u, 0u);
+  BRT_HDM void init(const Node8* tlas_, const InstRec* insts_, f3 o_, f3 d_, float tmin_, float tmax_) {
+    tlas = tlas_;
+    insts = insts_;
+    o = o_;
+    d = d_;
+    tmin = tmin_;
+    best.t = tmax_;
+    best.u = 0.0f;
+    best.v = 0.0f;
+    best.inst = BRT_MISS;
+    best.prim = BRT_MISS;
+    found = false;
+    sp = 0;
+    blas_sp = -1;
+    co = o_;
+    rb = make_raybox(d_);
+    sh = make_shear(d_);
+    nodes = tlas_;
+    tris = nullptr;
+    cur_inst = 0;
+    G = make_uint2(0u, tlas_ ? 0x80000000u : 0u);
+    Gt = make_uint2(0u, 0u);
+  }
 
-  for (;;) {
+  // One round: visit at most one node, then the pending leaf group. Returns true when the ray is done.
+  BRT_HDM bool step(uint2* __restrict__ stack, TraceCounters& ctr) {
     if (G.y & 0xff000000u) {
       const int bit = 31 - clz32(G.y);
       G.y &= ~(1u << bit);
@@ -134,22 +183,24 @@ BRT_HD bool trace_ray(const Node8* __restrict__ tlas, const InstRec* __restrict_
     }
 
     while (Gt.y) {
-      const int bit = ffs32(Gt.y) - 1;
-      Gt.y &= Gt.y - 1u;
       if (blas_sp >= 0) {
+        const int bit = ffs32(Gt.y) - 1;
+        Gt.y &= Gt.y - 1u;
         const TriRec* tr = tris + Gt.x + bit;
         const float4 a = ldg4(&tr->v0), b = ldg4(&tr->v1), c = ldg4(&tr->v2);
         if (COUNT) ctr.prims++;
         float t, u, v;
         if (intersect_tri(co, sh, tmin, best.t, found, xyz(a), xyz(b), xyz(c), t, u, v)) {
+          found = true;  // (for ANY this is the answer)
           if (ANY) return true;
           const uint32_t prim = f2u(a.w);
-          if (better_hit(t, cur_inst, prim, found, best)) {
+          if (best.inst == BRT_MISS || t < best.t || cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)) {
             best.t = t; best.u = u; best.v = v; best.inst = cur_inst; best.prim = prim;
-            found = true;
           }
         }
       } else {
+        const int bit = ffs32(Gt.y) - 1;
+        Gt.y &= Gt.y - 1u;
         const InstRec* ir = insts + Gt.x + bit;
         const float4 m0 = ldg4(&ir->w2o[0]), m1 = ldg4(&ir->w2o[1]), m2 = ldg4(&ir->w2o[2]);
         const uint4 tail = ldg4(reinterpret_cast<const uint4*>(&ir->kind));
@@ -160,10 +211,10 @@ BRT_HD bool trace_ray(const Node8* __restrict__ tlas, const InstRec* __restrict_
           if (COUNT) ctr.spheres++;
           float t;
           if (intersect_sphere(oo, od, tmin, best.t, found, xyz(s), s.w, t)) {
+            found = true;
             if (ANY) return true;
-            if (better_hit(t, tail.y, 0u, found, best)) {
+            if (best.inst == BRT_MISS || t < best.t || tail.y < best.inst) {
               best.t = t; best.u = 0.0f; best.v = 0.0f; best.inst = tail.y; best.prim = 0u;
-              found = true;
             }
           }
         } else {
@@ -176,7 +227,6 @@ BRT_HD bool trace_ray(const Node8* __restrict__ tlas, const InstRec* __restrict_
           tris = reinterpret_cast<const TriRec*>(((uint64_t)ptrs.w << 32) | ptrs.z);
           cur_inst = tail.y;
           co = oo;
-          cd = od;
           rb = make_raybox(od);
           sh = make_shear(od);
           G = make_uint2(0u, 0x80000000u);
@@ -190,15 +240,13 @@ BRT_HD bool trace_ray(const Node8* __restrict__ tlas, const InstRec* __restrict_
         blas_sp = -1;
         nodes = tlas;
         co = o;
-        cd = d;
-        rb = wrb;
+        rb = make_raybox(d);
       }
-      if (sp == 0) break;
+      if (sp == 0) return true;
       G = stack[--sp];
     }
+    return false;
   }
-  (void)cd;
-  return found;
-}
+};
 
 }  // namespace brt
