@@ -198,30 +198,25 @@ def run_product(args):
     u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
     opts = ctx.opts(w, h, spp, flags)
 
-    tile_bytes = ctx.tile_buffer_bytes(w, h, world)
-    tiles = torch.empty(tile_bytes // 4, dtype=torch.float32, device=dev)
-    gathered = torch.empty(world * tile_bytes // 4, dtype=torch.float32, device=dev) if world > 1 else tiles
-    image = torch.empty(h * w * 4, dtype=torch.float32, device=dev)
+    frame = pkg.TiledFrame(ctx, w, h, rank, world, dev)  # per-rank tile buffer, gather buffer, full frame
     host_image = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step_device():
         """one frame, result left in HBM (un-tiled full frame on every rank)"""
-        ctx.render_frame_tiles(u, opts, tiles.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, tiles)
-            ctx.untile(gathered.data_ptr(), w, h, world, image.data_ptr())
+        if world == 1:
+            ctx.render_frame_tiles(u, opts, frame.tiles.data_ptr())
+        else:
+            frame.render(u, opts)  # trace own tiles, NCCL all-gather, un-tile
 
     def step_e2e():
         """the call a user makes: host uniform in, host framebuffer out"""
         if world == 1:
             ctx.render_frame_ptr(u, opts, host_image.data_ptr())
         else:
-            ctx.render_frame_tiles(u, opts, tiles.data_ptr())
-            dist.all_gather_into_tensor(gathered, tiles)
-            ctx.untile(gathered.data_ptr(), w, h, world, image.data_ptr())
+            frame.render(u, opts)
             if rank == 0:
-                host_image.copy_(image, non_blocking=True)
+                host_image.copy_(frame.image, non_blocking=True)
             stream.synchronize()
 
     def sync_all():

@@ -11,6 +11,12 @@ from . import _binding as binding
 from ._binding import *  # noqa: F401,F403
 from . import scenes  # noqa: F401
 
+
+def TiledFrame(*args, **kwargs):
+    """Tile-parallel multi-GPU frame (multigpu.TiledFrame); torch is only imported when this is used."""
+    import importlib
+    return importlib.import_module(__name__ + ".multigpu").TiledFrame(*args, **kwargs)
+
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libbrt.so")
 LIB_COUNTERS_PATH = LIB_PATH  # counters are a runtime flag (BRT_CFG_COUNTERS), same library
