@@ -311,6 +311,28 @@ def run_product(args):
             "scene_build": {"seconds_incl_upload": build_s, "ms_blas": build_stats.ms_blas_build, "ms_tlas": build_stats.ms_tlas_build,
                             "bvh_nodes": int(build_stats.bvh_nodes), "bvh_bytes": int(build_stats.bvh_bytes), "sah_cost": build_stats.sah_cost},
         }
+    if world > 1:
+        # the same workload on ONE GPU (rank 0 renders the whole frame alone), so that the line carries its own
+        # strong-scaling reference: the N=1 default run uses another workload (c2)
+        dist.barrier()
+        if rank == 0:
+            solo = pkg.Context(device=local)
+            solo.set_stream(stream.cuda_stream)
+            scene.upload(solo)
+            solo.render_frame(u, opts, want_image=False)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(2):
+                solo.render_frame(u, opts, want_image=False)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            st1 = solo.get_stats()
+            ms1 = e0.elapsed_time(e1) / 2
+            v1 = (st1.rays_closest + st1.rays_occlusion) / (ms1 * 1e-3) / 1e6
+            line["same_workload_1gpu"] = {"value": v1, "unit": "Mrays/s", "ms_per_step": ms1, "speedup": value / v1,
+                                          "efficiency": value / v1 / world}
+            solo.close()
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -325,10 +347,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--config", default=None, choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE config; default: c2 (1080p, the single-GPU headline) at N=1, c3 (4K, 16 spp, 4-bounce GI: the "
+                         "configuration BASELINE.json quotes for 1/2/4/8 GPUs) at N>1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.config is None:
+        args.config = "c2" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c3"
     if args.impl == "reference":
         run_reference(args)
     else:

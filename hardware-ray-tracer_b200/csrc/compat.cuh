@@ -75,6 +75,15 @@ BRT_HD int ffs32(uint32_t x) {  // 1-based index of the lowest set bit, 0 if non
   return __ffs((int)x);
 #endif
 }
+BRT_HD float fast_rcp(float x) {
+#ifdef BRT_EMU
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
 // directed roundings used by the builder's conservative quantisation
 BRT_HD float add_rd(float a, float b) {
 #ifdef BRT_EMU

@@ -32,7 +32,9 @@ BRT_HD RayBox make_raybox(f3 d) {
   float dx = fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x);
   float dy = fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y);
   float dz = fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z);
-  rb.idir = F3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+  // the slab test is conservative by construction (slack term), so the approximate reciprocal (1 ulp, one MUFU)
+  // is good enough here; the primitive tests keep IEEE division
+  rb.idir = F3(fast_rcp(dx), fast_rcp(dy), fast_rcp(dz));
   uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
   rb.octinv = 7u - oct;
   return rb;
