@@ -1,0 +1,297 @@
+// bloon.hpp — C++ host facade with the reference's class names over the C ABI of libbrt.so.
+//
+// A user of the reference's App/Graphics host API (RayTracing::Scene, RayTracing::Pipeline, Core::Camera,
+// RayTracing::MeshInstance, the Vertex / Material / Light / Uniform structs) finds the same names, argument
+// meaning and error behaviour (std::runtime_error, Graphics/Definitions.h:5) here; Vulkan-typed parameters
+// are replaced by neutral ones. Header-only; link with -lbrt. Citations: RT/ = reference
+// Graphics/RayTracing/, GFX/ = reference Graphics/.
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../brt.h"
+
+namespace bloon {
+struct vec3 {  // stands in for glm::vec3 in the signatures
+  float x = 0.0f, y = 0.0f, z = 0.0f;
+  vec3() = default;
+  vec3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
+};
+inline void check(int status, brt_context* ctx, const char* what) {
+  if (status != BRT_OK) throw std::runtime_error(std::string(what) + ": " + brt_last_error(ctx));
+}
+}  // namespace bloon
+
+namespace Core {
+
+// Core::Device (vulkan_core/Device.h): owns the connection to the GPU — here one brt_context.
+class Device {
+ public:
+  explicit Device(int cudaDevice = 0, uint32_t tileRank = 0, uint32_t tileWorld = 1, uint32_t flags = 0) {
+    brt_config cfg{};
+    cfg.struct_size = sizeof(cfg);
+    cfg.device = cudaDevice;
+    cfg.tile_rank = tileRank;
+    cfg.tile_world = tileWorld;
+    cfg.flags = flags;
+    int rc = brt_create(&cfg, &ctx_);
+    if (rc != BRT_OK) throw std::runtime_error(std::string("failed to create the ray tracing device: ") + brt_last_error(nullptr));
+  }
+  ~Device() { brt_destroy(ctx_); }
+  Device(const Device&) = delete;
+  Device& operator=(const Device&) = delete;
+  brt_context* getDevice() const { return ctx_; }
+
+ private:
+  brt_context* ctx_ = nullptr;
+};
+
+// Core::Camera (GFX/Camera.h:8-17): setView / setPerspectiveProjection keep the reference's conventions
+// (Y down, +Z forward, Tait-Bryan Y-X-Z, Vulkan 0..1 depth). handleInputs (GLFW) is out of scope.
+class Camera {
+ public:
+  void setPerspectiveProjection(float fovy, float aspectRatio, float near_, float far_) {
+    fovy_ = fovy; aspect_ = aspectRatio; near_z_ = near_; far_z_ = far_;
+  }
+  void setView(bloon::vec3 position, bloon::vec3 rotation) { position_ = position; rotation_ = rotation; }
+  bloon::vec3 getPosition() const { return position_; }
+  bloon::vec3 getRotation() const { return rotation_; }
+  // glm-style column-major matrices (GFX/Camera.cpp:8-17, 71-95)
+  std::array<float, 16> getProjection() const {
+    std::array<float, 16> m{};
+    const float t = std::tan(fovy_ / 2.0f);
+    m[0] = 1.0f / (aspect_ * t);
+    m[5] = 1.0f / t;
+    m[10] = far_z_ / (far_z_ - near_z_);
+    m[11] = 1.0f;
+    m[14] = -(far_z_ * near_z_) / (far_z_ - near_z_);
+    return m;
+  }
+  std::array<float, 16> getView() const {
+    const float c3 = std::cos(rotation_.z), s3 = std::sin(rotation_.z);
+    const float c2 = std::cos(rotation_.x), s2 = std::sin(rotation_.x);
+    const float c1 = std::cos(rotation_.y), s1 = std::sin(rotation_.y);
+    const float u[3] = {c1 * c3 + s1 * s2 * s3, c2 * s3, c1 * s2 * s3 - c3 * s1};
+    const float v[3] = {c3 * s1 * s2 - c1 * s3, c2 * c3, c1 * c3 * s2 + s1 * s3};
+    const float w[3] = {c2 * s1, -s2, c1 * c2};
+    const float p[3] = {position_.x, position_.y, position_.z};
+    std::array<float, 16> m{};
+    for (int k = 0; k < 3; ++k) { m[4 * k + 0] = u[k]; m[4 * k + 1] = v[k]; m[4 * k + 2] = w[k]; }
+    m[12] = -(u[0] * p[0] + u[1] * p[1] + u[2] * p[2]);
+    m[13] = -(v[0] * p[0] + v[1] * p[1] + v[2] * p[2]);
+    m[14] = -(w[0] * p[0] + w[1] * p[1] + w[2] * p[2]);
+    m[15] = 1.0f;
+    return m;
+  }
+  // Uniform{inverse(transpose(view)), inverse(transpose(proj)), frame, depthMax} of RTApp::run (RT/RTApp.cpp:44-49)
+  brt_uniform uniform(uint32_t frame, uint32_t depthMax) const {
+    brt_uniform u;
+    const float pos[3] = {position_.x, position_.y, position_.z}, rot[3] = {rotation_.x, rotation_.y, rotation_.z};
+    brt_camera_uniform(pos, rot, fovy_, aspect_, near_z_, far_z_, frame, depthMax, &u);
+    return u;
+  }
+
+ private:
+  bloon::vec3 position_, rotation_;
+  float fovy_ = 1.0471975512f, aspect_ = 1.0f, near_z_ = 0.001f, far_z_ = 100000.0f;
+};
+
+}  // namespace Core
+
+namespace RayTracing {
+
+using Vertex = brt_vertex;      // RT/Scene.h:28-38
+using Material = brt_material;  // RT/Scene.h:50-62
+using Light = brt_light;        // RT/Scene.h:70-75
+using Uniform = brt_uniform;    // RT/RTPipeline.h:24-30
+struct Extent2D { uint32_t width, height; };
+
+// RT/MeshInstance.h: mesh id, material id, position / rotation / scale -> 3x4 transform. As in the
+// reference only scale + translate is live (RT/MeshInstance.h:82-85; the rotation code is commented out).
+class MeshInstance {
+ public:
+  MeshInstance(uint32_t meshId, uint32_t materialId, bloon::vec3 position = {}, bloon::vec3 rotation = {}, bloon::vec3 scale = {1, 1, 1})
+      : meshId(meshId), materialId(materialId), position(position), rotation(rotation), scale(scale) { calculateTransformation(); }
+  void setPosition(bloon::vec3 p) { position = p; calculateTransformation(); }
+  void setRotation(bloon::vec3 r) { rotation = r; calculateTransformation(); }
+  void setScale(bloon::vec3 s) { scale = s; calculateTransformation(); }
+  void setMeshId(uint32_t id) { meshId = id; }
+  void setMaterialId(uint32_t id) { materialId = id; }
+  bloon::vec3 getPosition() const { return position; }
+  bloon::vec3 getRotation() const { return rotation; }
+  const float* getTransformation() const { return transform; }
+  uint32_t getMeshId() const { return meshId; }
+  uint32_t getMaterialId() const { return materialId; }
+
+ private:
+  void calculateTransformation() {
+    const float t[12] = {scale.x, 0.0f, 0.0f, position.x, 0.0f, scale.y, 0.0f, position.y, 0.0f, 0.0f, scale.z, position.z};
+    std::memcpy(transform, t, sizeof(t));
+  }
+  uint32_t meshId, materialId;
+  bloon::vec3 position, rotation, scale;
+  float transform[12];
+};
+
+// RT/Scene.h:132-192
+class Scene {
+ public:
+  explicit Scene(Core::Device& device) : device(device) {}
+  Scene(const Scene&) = delete;
+  Scene& operator=(const Scene&) = delete;
+
+  // RT/Scene.cpp:29-74: OBJ -> flip Y of positions and normals -> de-duplicate identical vertices -> indexed mesh.
+  // (The reference parses with tinyobjloader 1.0.6; this reads the v / vn / vt / f records that loader feeds it,
+  // fan-triangulating polygons.)
+  uint32_t loadModel(const std::string& path) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Cannot open file [" + path + "]");
+    std::vector<float> pos, nrm, tex;
+    std::vector<Vertex> vertices;
+    std::vector<uint32_t> indices;
+    std::unordered_map<std::string, uint32_t> unique;
+    std::string line;
+    auto resolve = [](int i, size_t n) { return i > 0 ? i - 1 : (i < 0 ? (int)n + i : -1); };
+    while (std::getline(in, line)) {
+      std::istringstream ss(line);
+      std::string tag;
+      ss >> tag;
+      if (tag == "v") { float a, b, c; ss >> a >> b >> c; pos.insert(pos.end(), {a, b, c}); }
+      else if (tag == "vn") { float a, b, c; ss >> a >> b >> c; nrm.insert(nrm.end(), {a, b, c}); }
+      else if (tag == "vt") { float a = 0, b = 0; ss >> a >> b; tex.insert(tex.end(), {a, b}); }
+      else if (tag == "f") {
+        std::vector<uint32_t> face;
+        std::string tok;
+        while (ss >> tok) {
+          int vi = 0, ti = 0, ni = 0;
+          if (std::sscanf(tok.c_str(), "%d/%d/%d", &vi, &ti, &ni) == 3) {}
+          else if (std::sscanf(tok.c_str(), "%d//%d", &vi, &ni) == 2) { ti = 0; }
+          else if (std::sscanf(tok.c_str(), "%d/%d", &vi, &ti) == 2) { ni = 0; }
+          else { std::sscanf(tok.c_str(), "%d", &vi); ti = ni = 0; }
+          Vertex v{};
+          const int pv = resolve(vi, pos.size() / 3), pt = resolve(ti, tex.size() / 2), pn = resolve(ni, nrm.size() / 3);
+          if (pv >= 0) { v.pos[0] = pos[3 * pv]; v.pos[1] = -pos[3 * pv + 1]; v.pos[2] = pos[3 * pv + 2]; }          // :47-51
+          if (pn >= 0) { v.normal[0] = nrm[3 * pn]; v.normal[1] = -nrm[3 * pn + 1]; v.normal[2] = nrm[3 * pn + 2]; }  // :53-57
+          if (pt >= 0) { v.uv[0] = tex[2 * pt]; v.uv[1] = tex[2 * pt + 1]; }                                           // :59-62
+          std::string key(reinterpret_cast<const char*>(&v), sizeof(v));  // equality on all 8 floats (RT/Scene.h:33-37)
+          auto it = unique.find(key);
+          if (it == unique.end()) { it = unique.emplace(key, (uint32_t)vertices.size()).first; vertices.push_back(v); }
+          face.push_back(it->second);
+        }
+        for (size_t k = 2; k < face.size(); ++k) { indices.push_back(face[0]); indices.push_back(face[k - 1]); indices.push_back(face[k]); }
+      }
+    }
+    return createMesh(vertices, indices);
+  }
+  // Mesh::Mesh (RT/Scene.cpp:419-458) for procedural geometry
+  uint32_t createMesh(const std::vector<Vertex>& vertices, const std::vector<uint32_t>& indices) {
+    uint32_t id = 0;
+    bloon::check(brt_mesh_create(ctx(), vertices.data(), (uint32_t)vertices.size(), indices.data(), (uint32_t)indices.size(), &id), ctx(), "createMesh");
+    return id;
+  }
+  void updateMeshVertices(uint32_t meshId, const std::vector<Vertex>& vertices) {
+    bloon::check(brt_mesh_update_vertices(ctx(), meshId, vertices.data(), (uint32_t)vertices.size()), ctx(), "updateMeshVertices");
+  }
+  uint32_t createSphere(bloon::vec3 center, float radius) {  // extension
+    const float c[3] = {center.x, center.y, center.z};
+    uint32_t id = 0;
+    bloon::check(brt_sphere_create(ctx(), c, radius, &id), ctx(), "createSphere");
+    return id;
+  }
+  void createInstance(uint32_t meshId, uint32_t materialId, bloon::vec3 position = {}, bloon::vec3 rotation = {}, bloon::vec3 scale = {1, 1, 1}) {
+    MeshInstance inst(meshId, materialId, position, rotation, scale);  // RT/Scene.cpp:76-78
+    uint32_t id = 0;
+    bloon::check(brt_instance_create(ctx(), meshId, materialId, inst.getTransformation(), &id), ctx(), "createInstance");
+    instances.push_back(inst);
+  }
+  // RT/Scene.cpp:80-86: emissive arguments are accepted and ignored, specular defaults to 0.5, the rest to 0
+  uint32_t createMaterial(bloon::vec3 color, float metallic = 0.f, float roughness = 1.f, bloon::vec3 /*emissiveColor*/ = {}, float /*emissionStrength*/ = 0.f) {
+    Material m{};
+    m.color[0] = color.x; m.color[1] = color.y; m.color[2] = color.z;
+    m.metallic = metallic;
+    m.roughness = roughness;
+    m.specular = 0.5f;
+    uint32_t id = 0;
+    bloon::check(brt_material_create(ctx(), &m, &id), ctx(), "createMaterial");
+    return id;
+  }
+  void createLight(bloon::vec3 position, bloon::vec3 color, float intensity) {  // RT/Scene.cpp:88-97: always POINT
+    Light l{};
+    l.pos[0] = position.x; l.pos[1] = position.y; l.pos[2] = position.z;
+    l.color[0] = color.x; l.color[1] = color.y; l.color[2] = color.z;
+    l.intensity = intensity;
+    l.type = BRT_LIGHT_POINT;
+    bloon::check(brt_light_create(ctx(), &l, nullptr), ctx(), "createLight");
+  }
+  void build() { bloon::check(brt_scene_build(ctx()), ctx(), "Scene::build"); }  // RT/Scene.cpp:100-120
+  void destroyInstance(uint32_t instanceID) {                                    // RT/Scene.cpp:122-125 (swap-remove)
+    bloon::check(brt_instance_destroy(ctx(), instanceID), ctx(), "destroyInstance");
+    instances[instanceID] = instances.back();
+    instances.pop_back();
+  }
+  void unloadModel(uint32_t) {}      // empty in the reference too (RT/Scene.cpp:126-133)
+  void destroyLight(uint32_t) {}
+  void destroyMaterial(uint32_t) {}
+  MeshInstance& getInstance(uint32_t id) { return instances.at(id); }
+  void commitInstance(uint32_t id) {  // push setPosition / setScale / setMaterialId changes of getInstance(id) to the GPU
+    bloon::check(brt_instance_set_transform(ctx(), id, instances.at(id).getTransformation()), ctx(), "commitInstance");
+    bloon::check(brt_instance_set_material(ctx(), id, instances.at(id).getMaterialId()), ctx(), "commitInstance");
+  }
+  // The reference's prepareRendering() prints "Not implemented!" and throws "LBVH not implemented!"
+  // (RT/Scene.cpp:135-138). Here it is the per-frame entry: rebuild the BLAS of updated meshes with the GPU LBVH
+  // builder, and — when a threshold is given — run Smart Culling (README.md:15-18) and rebuild the TLAS.
+  uint32_t prepareRendering(const Uniform* uniform = nullptr, Extent2D extent = {0, 0}, float thresholdPx2 = 0.0f, float hysteresis = 0.25f) {
+    build();
+    uint32_t visible = (uint32_t)instances.size();
+    if (uniform) bloon::check(brt_smart_cull(ctx(), uniform, extent.width, extent.height, thresholdPx2, hysteresis, &visible), ctx(), "prepareRendering");
+    return visible;
+  }
+  Core::Device& getDeviceRef() { return device; }
+
+ private:
+  brt_context* ctx() { return device.getDevice(); }
+  Core::Device& device;
+  std::vector<MeshInstance> instances;
+};
+
+// RT/RTPipeline.h:34-51 — the render-frame entry. bind / bindDescriptorSets have no CUDA analogue and are no-ops.
+class Pipeline {
+ public:
+  Pipeline(Core::Device& device, Extent2D extent, Scene& scene) : device(device), extent(extent), scene(scene) { rebuildRenderOutput(extent); }
+  static std::unique_ptr<Pipeline> createPipeline(Core::Device& device, Extent2D extent, Scene& scene) {
+    return std::unique_ptr<Pipeline>(new Pipeline(device, extent, scene));
+  }
+  void bind() {}
+  void bindDescriptorSets(uint32_t) {}
+  void writeToUniformBuffer(const void* data, uint32_t index) { std::memcpy(&uniforms[index % 2], data, sizeof(Uniform)); current = index % 2; }  // RT/RTPipeline.cpp:44-47
+  // vkCmdTraceRaysKHR(width, height, 1) (RT/RTPipeline.cpp:41-43) + the image read-back of copyImageToSwapchain
+  void traceRays(uint32_t width, uint32_t height, uint32_t /*depth*/ = 1, uint32_t spp = 1, uint32_t renderFlags = 0) {
+    if (width != extent.width || height != extent.height) rebuildRenderOutput({width, height});
+    brt_render_opts o{};
+    o.width = width; o.height = height; o.spp = spp; o.flags = renderFlags;
+    bloon::check(brt_render_frame(device.getDevice(), &uniforms[current], &o, storageImage.data()), device.getDevice(), "traceRays");
+  }
+  void rebuildRenderOutput(Extent2D e) { extent = e; storageImage.assign((size_t)e.width * e.height * 4, 0.0f); }  // RT/RTPipeline.cpp:49-55
+  void updateTopLevelAS() {}                                                                                       // empty in the reference (RT/RTPipeline.cpp:57-59)
+  std::vector<float>& getRenderOutput() { return storageImage; }  // linear RGBA32F, row-major (outImage, SH/raytracing.slang:132)
+  brt_stats getStats() { brt_stats s{}; brt_get_stats(device.getDevice(), &s); return s; }
+
+ private:
+  Core::Device& device;
+  Extent2D extent;
+  Scene& scene;
+  Uniform uniforms[2]{};  // MAX_FRAMES_IN_FLIGHT = 2 (vulkan_core/SwapChain.h:8)
+  uint32_t current = 0;
+  std::vector<float> storageImage;
+};
+
+}  // namespace RayTracing
