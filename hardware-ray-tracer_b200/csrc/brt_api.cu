@@ -128,6 +128,7 @@ struct MeshData {
   uint32_t n_vertices = 0, n_indices = 0;
   DevBuf vertices, indices, nodes, tris;
   bool dirty = true;
+  bool dynamic = false;  // vertices were replaced after the first build: rebuilds favour build speed
   BuildResult blas;
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 };
@@ -370,7 +371,7 @@ void scene_build(brt_context* c) {
       m.nodes.ensure((size_t)Builder::node_capacity(nt) * sizeof(Node8));
       m.tris.ensure((size_t)nt * sizeof(TriRec));
       c->builder->build_triangles(s, m.vertices.as<float>(), m.indices.as<uint32_t>(), nt, m.nodes.as<Node8>(), m.tris.as<TriRec>(), nullptr,
-                                  !(c->flags & BRT_CFG_NO_TREELET), &m.blas);
+                                  !(c->flags & BRT_CFG_NO_TREELET) && (!m.dynamic || (c->flags & BRT_CFG_TREELET_ON_REBUILD)), &m.blas);
       for (int k = 0; k < 3; ++k) { m.lo[k] = m.blas.lo[k]; m.hi[k] = m.blas.hi[k]; }
     }
     m.dirty = false;
@@ -745,6 +746,7 @@ int brt_mesh_update_vertices(brt_context* c, uint32_t mesh_id, const brt_vertex*
     BRT_CUDA(cudaMemcpyAsync(m.vertices.ptr(), v, (size_t)nv * sizeof(brt_vertex), cudaMemcpyHostToDevice, c->stream));
     BRT_CUDA(cudaStreamSynchronize(c->stream));
     m.dirty = true;
+    m.dynamic = true;
     c->built = false;
   });
 }

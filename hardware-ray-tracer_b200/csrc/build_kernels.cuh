@@ -25,8 +25,7 @@ struct BuildGlobals {
   uint32_t levels;           // number of collapse levels that had work
   uint32_t overflow;         // set when a capacity was exceeded
   uint32_t level_count[64];  // work items per collapse level
-  float sah_binary;          // SAH cost of the binary tree (filled by sah_cost kernel)
-  uint32_t pad[3];
+  uint32_t pad[4];
 };
 
 // ---- warp-aggregated float min/max into ordered uints -------------------------------------------------

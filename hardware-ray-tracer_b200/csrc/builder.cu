@@ -16,7 +16,6 @@ BRT_KERNEL_1D(k_morton, MortonParams, morton_body)
 BRT_KERNEL_1D(k_hierarchy, HierarchyParams, hierarchy_body)
 BRT_KERNEL_1D(k_refit, RefitParams, refit_body)
 BRT_KERNEL_1D(k_collapse, CollapseParams, collapse_body)
-BRT_KERNEL_1D(k_sah_cost, SahParams, sah_cost_body)
 BRT_KERNEL_1D(k_treelet, TreeletParams, treelet_body)
 
 struct InitGlobalsParams {
@@ -38,7 +37,6 @@ BRT_HD void init_globals_body(const InitGlobalsParams& p, uint32_t) {
   g.overflow = 0u;
   for (int k = 0; k < 64; ++k) g.level_count[k] = 0u;
   g.level_count[0] = 1u;
-  g.sah_binary = 0.0f;
   p.queue0[0] = make_uint2(p.root, 0u);
 }
 BRT_KERNEL_1D(k_init_globals, InitGlobalsParams, init_globals_body)
@@ -70,7 +68,7 @@ void Builder::ensure_scratch(uint32_t n) {
   parent_.ensure(2 * N * 4);
   arrive_.ensure(N * 4);
   sub_count_.ensure(2 * N * 4);
-  treelet_.ensure(N * 4 + 16);
+  treelet_.ensure(2 * N * 4 + 16);  // SAH cost per binary node
 }
 
 void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treelets, Node8* out_nodes, const float* d_vertices,
@@ -107,25 +105,32 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     BRT_LAUNCH_1D(k_refit, p, grid_n, 256, stream);
     BRT_CHECK_LAUNCH();
   }
-  float* d_sah = &g->sah_binary;
-  float sah_before = 0.0f;
+  // SAH cost of the LBVH, then SAH treelet restructuring (triangle BLAS only)
+  float cost_before = 0.0f, cost_after = 0.0f;
+  BNode root_before{}, root_after{};
   const bool want_sah = out_tris != nullptr && n > 1;
+  const bool do_treelets = treelets && want_sah && n >= 2 * BRT_TREELET_LEAVES;
   if (want_sah) {
-    SahParams p{n - 1, nullptr, n, nodes, sub_count, max_leaf, d_sah};
-    BRT_LAUNCH_1D(k_sah_cost, p, grid_n, 256, stream);
-    BRT_CHECK_LAUNCH();
-  }
-  if (treelets && n > 16 && out_tris != nullptr) {
-    if (want_sah) {
-      BRT_CUDA(cudaMemcpyAsync(&sah_before, d_sah, 4, cudaMemcpyDeviceToHost, stream));
-      BRT_CUDA(cudaMemsetAsync(d_sah, 0, 4, stream));
-    }
-    run_treelet_passes(stream, n, nodes, parent, sub_count, arrive_.as<uint32_t>(), treelet_.as<uint32_t>(), max_leaf, sm_count_);
-    if (want_sah) {
-      SahParams p{n - 1, nullptr, n, nodes, sub_count, max_leaf, d_sah};
-      BRT_LAUNCH_1D(k_sah_cost, p, grid_n, 256, stream);
+    float* cost = treelet_.as<float>();
+    const uint32_t grid_t = std::max(1u, std::min(div_up(n, 64u), (uint32_t)sm_count_ * 16u));
+    const int passes = do_treelets ? 3 : 0;
+    for (int pass = 0; pass <= passes; ++pass) {
+      BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
+      TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, pass == 0 ? 0u : 1u};
+#ifdef BRT_EMU
+      BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);
+#else
+      if (pass == 0) BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);  // cost only: one thread per leaf is enough
+      else k_treelet_warp<<<std::max(1u, std::min(div_up(n, 128u), (uint32_t)sm_count_ * 8u)), 128, 0, stream>>>(tp);
+#endif
       BRT_CHECK_LAUNCH();
+      if (pass == 0) {
+        BRT_CUDA(cudaMemcpyAsync(&cost_before, cost, 4, cudaMemcpyDeviceToHost, stream));
+        BRT_CUDA(cudaMemcpyAsync(&root_before, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
+      }
     }
+    BRT_CUDA(cudaMemcpyAsync(&cost_after, cost, 4, cudaMemcpyDeviceToHost, stream));
+    BRT_CUDA(cudaMemcpyAsync(&root_after, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
   }
   // collapse, level by level; the per-level work count lives on the device
   const uint32_t node_cap = node_capacity(n);
@@ -176,8 +181,12 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
   res->n_prims = n;
   res->n_nodes = hg.node_count;
   res->levels = hg.levels;
-  res->sah_final = hg.sah_binary;
-  res->sah_lbvh = (treelets && n > 16 && want_sah) ? sah_before : hg.sah_binary;
+  auto host_area = [](const BNode& b) {
+    const float ex = b.hi.x - b.lo.x, ey = b.hi.y - b.lo.y, ez = b.hi.z - b.lo.z;
+    return 2.0f * ((ex * ey + ey * ez) + ez * ex);
+  };
+  res->sah_lbvh = want_sah && host_area(root_before) > 0.0f ? cost_before / host_area(root_before) : 0.0f;
+  res->sah_final = want_sah && host_area(root_after) > 0.0f ? cost_after / host_area(root_after) : 0.0f;
   for (int k = 0; k < 3; ++k) {
     res->lo[k] = ordered_to_float(hg.exact[k]);
     res->hi[k] = ordered_to_float(hg.exact[3 + k]);

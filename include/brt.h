@@ -113,6 +113,10 @@ typedef struct brt_config {
 
 #define BRT_CFG_COUNTERS 1u /* run the instrumented traversal kernels (node/primitive visit counters) */
 #define BRT_CFG_NO_TREELET 2u /* skip the SAH treelet refinement pass of the LBVH builder */
+/* Build policy (the Vulkan build flags of RT/Scene.cpp:169 restated): the first build of a mesh is
+ * PREFER_FAST_TRACE (LBVH + SAH treelet restructuring); rebuilds after brt_mesh_update_vertices are
+ * PREFER_FAST_BUILD (plain LBVH, what the reference's prepareRendering placeholder names) unless this flag is set. */
+#define BRT_CFG_TREELET_ON_REBUILD 4u
 
 /* render mode flags. With none of the BOUNCE flags set the behaviour is the reference's live path:
  * direct light + hard shadows, weight = 0 after the first hit (SH/raytracing.slang:168). */
