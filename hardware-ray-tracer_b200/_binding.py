@@ -73,7 +73,7 @@ BRT_SYMBOLS = [
     "brt_instance_create", "brt_instance_set_transform", "brt_instance_set_material", "brt_instance_destroy",
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
-    "brt_camera_uniform",
+    "brt_camera_uniform", "brt_debug_sort_pairs",
 ]
 
 
@@ -126,6 +126,7 @@ class SceneApi:
             "get_aov": (C.c_int, [vp, C.c_int, vp]),
             "get_stats": (C.c_int, [vp, P(Stats)]),
             "trace_rays": (C.c_int, [vp, P(f32), u32, C.c_int, P(u32)]),
+            "debug_sort_pairs": (C.c_int, [vp, P(u32), P(u32), u32, C.c_int]),
             "camera_uniform": (None, [P(f32), P(f32), f32, f32, f32, f32, u32, u32, P(Uniform)]),
         }
         device_side = {  # entry points that take device pointers / streams
@@ -271,6 +272,12 @@ class SceneApi:
         out = np.zeros((r.shape[0], 4), dtype=np.uint32)
         self._ck(self._f("trace_rays")(self.ctx, _ptr(r, f32), r.shape[0], 1 if closest else 0, _ptr(out, u32)))
         return out
+
+    def debug_sort_pairs(self, keys, vals, bits=32):
+        k = np.ascontiguousarray(keys, dtype=np.uint32).copy()
+        v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._ck(self._f("debug_sort_pairs")(self.ctx, _ptr(k, u32), _ptr(v, u32), k.shape[0], bits))
+        return k, v
 
     # ---- device-side entry points ------------------------------------------------------------
     def set_stream(self, stream_ptr):

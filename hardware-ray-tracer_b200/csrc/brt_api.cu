@@ -1091,6 +1091,16 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
   });
 }
 
+int brt_debug_sort_pairs(brt_context* c, uint32_t* keys, uint32_t* vals, uint32_t n, int bits) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if ((!keys || !vals) && n) invalid("debug_sort_pairs: null");
+    if (bits < 1 || bits > 32) invalid("debug_sort_pairs: bits must be in 1..32");
+    BRT_CUDA(cudaSetDevice(c->device));
+    c->builder->debug_sort_pairs(c->stream, keys, vals, n, bits);
+  });
+}
+
 // 4x4 inverse in double (cofactor expansion along 2x2 minors), row-major in/out
 static void invert4x4(const double m[16], double inv[16]) {
   const double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];

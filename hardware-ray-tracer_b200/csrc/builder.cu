@@ -193,6 +193,18 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
   }
 }
 
+void Builder::debug_sort_pairs(cudaStream_t stream, uint32_t* keys_host, uint32_t* vals_host, uint32_t n, int bits) {
+  if (n == 0) return;
+  ensure_scratch(n);
+  BRT_CUDA(cudaMemcpyAsync(keys_[0].ptr(), keys_host, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+  BRT_CUDA(cudaMemcpyAsync(vals_[0].ptr(), vals_host, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+  const int out = radix_sort_pairs(stream, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(), vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), n, bits,
+                                   sort_tmp_.ptr(), sort_tmp_.capacity(), sm_count_);
+  BRT_CUDA(cudaMemcpyAsync(keys_host, keys_[out].ptr(), (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+  BRT_CUDA(cudaMemcpyAsync(vals_host, vals_[out].ptr(), (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+  BRT_CUDA(cudaStreamSynchronize(stream));
+}
+
 void Builder::build_triangles(cudaStream_t stream, const float* d_vertices, const uint32_t* d_indices, uint32_t n_tris, Node8* out_nodes,
                               TriRec* out_tris, float4* d_mesh_bounds, bool treelets, BuildResult* res) {
   ensure_scratch(n_tris);

@@ -25,6 +25,8 @@ class Builder {
   // TLAS over instances: primitive k is instance d_inst_ids[k], its traversal record is d_src[k].
   void build_instances(cudaStream_t stream, const InstShade* d_shade, const uint32_t* d_inst_ids, const InstRec* d_src, uint32_t n,
                        const float4* d_mesh_bounds, Node8* out_nodes, InstRec* out_inst, BuildResult* res);
+  // test hook: the builder's radix sort on host arrays
+  void debug_sort_pairs(cudaStream_t stream, uint32_t* keys_host, uint32_t* vals_host, uint32_t n, int bits);
   static uint32_t node_capacity(uint32_t n_prims) { return n_prims < 8 ? 8 : n_prims; }
 
  private:

@@ -230,6 +230,10 @@ BRT_API int brt_get_stats(brt_context* ctx, brt_stats* out);
  * closest == 0: out[4*i+3] = occluded ? 1 : 0. Used by the brute-force-vs-BVH equivalence tests. */
 BRT_API int brt_trace_rays(brt_context* ctx, const float* rays_host, uint32_t n_rays, int closest, uint32_t* out_host);
 
+/* Sorts n (key, value) pairs in place (host arrays) by the low `bits` bits of the key with the LBVH builder's own GPU
+ * radix sort; stable. Exposed so that the sort can be tested on its own. */
+BRT_API int brt_debug_sort_pairs(brt_context* ctx, uint32_t* keys_host, uint32_t* vals_host, uint32_t n, int bits);
+
 /* ---- host helper: Core::Camera + the uniform block of RTApp::run ---------------------------- */
 /* Camera::setView/updateView (Graphics/Camera.cpp:19-24,71-95), Camera::setPerspectiveProjection
  * (Graphics/Camera.cpp:8-17) and Uniform{inverse(transpose(view)), inverse(transpose(proj)), frame,

@@ -720,6 +720,18 @@ int orc_trace_rays(orc_context* c, const float* rays, uint32_t n, int closest, u
   return BRT_OK;
 }
 
+int orc_debug_sort_pairs(orc_context*, uint32_t* keys, uint32_t* vals, uint32_t n, int bits) {
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  const uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (keys[a] & mask) < (keys[b] & mask); });
+  std::vector<uint32_t> k(n), v(n);
+  for (uint32_t i = 0; i < n; ++i) { k[i] = keys[order[i]]; v[i] = vals[order[i]]; }
+  std::copy(k.begin(), k.end(), keys);
+  std::copy(v.begin(), v.end(), vals);
+  return BRT_OK;
+}
+
 uint32_t orc_kat_hash(uint32_t x, uint32_t y, uint32_t z) { return hash3(x, y, z); }
 uint32_t orc_kat_pcg(uint32_t* s) { return pcg(*s); }
 float orc_kat_rand(uint32_t* s) { return rnd(*s); }

@@ -42,6 +42,7 @@ int orc_get_visibility(orc_context* ctx, uint8_t* out, uint32_t n);
 int orc_render_frame(orc_context* ctx, const brt_uniform* u, const brt_render_opts* opts, float* rgba_host);
 int orc_get_aov(orc_context* ctx, int kind, void* out_host);
 int orc_get_stats(orc_context* ctx, brt_stats* out);
+int orc_debug_sort_pairs(orc_context* ctx, uint32_t* keys, uint32_t* vals, uint32_t n, int bits);
 int orc_trace_rays(orc_context* ctx, const float* rays, uint32_t n, int closest, uint32_t* out);
 
 /* known-answer / unit-test hooks into the transcribed shader functions */

@@ -89,3 +89,18 @@ def test_repeatable(pkg, make):
     i1 = a.render_frame(u, a.opts(192, 108, 2, 15)).copy()
     i2 = a.render_frame(u, a.opts(192, 108, 2, 15))
     assert np.array_equal(i1.view(np.uint32), i2.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,bits", [(1, 30), (2, 30), (31, 8), (4096, 30), (4097, 30), (100003, 30), (1 << 20, 32), (333333, 16)])
+def test_radix_sort_pairs(pkg, make, n, bits):
+    """The builder's own radix sort: sorted by the low `bits` bits, stable, a permutation of the input."""
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[: n // 3] = keys[0]  # long runs of equal keys exercise the stability
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = make().debug_sort_pairs(keys, vals, bits)
+    mask = np.uint32(0xFFFFFFFF if bits == 32 else (1 << bits) - 1)
+    order = np.argsort(keys & mask, kind="stable")
+    assert np.array_equal(v, order.astype(np.uint32))
+    assert np.array_equal(k, keys[order])

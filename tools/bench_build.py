@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("hardware-ray-tracer_b200")
 
 out = {}
-for name, flags in (("treelets", 0), ("lbvh_only", pkg.CFG_NO_TREELET)):
+for name, flags in (("treelets", pkg.CFG_TREELET_ON_REBUILD), ("lbvh_only", pkg.CFG_NO_TREELET)):
     scene = pkg.scenes.terrain_icospheres()
     ctx = pkg.Context(device=0, flags=flags)
     scene.upload(ctx)
