@@ -62,6 +62,7 @@ assert C.sizeof(Uniform) == 140 and C.sizeof(Sky) == 88
 CFG_COUNTERS = 1
 CFG_NO_TREELET = 2
 CFG_TREELET_ON_REBUILD = 4
+CFG_NO_OVERLAP = 8
 BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY = 1, 2, 4, 8, 16
 AOV_PRIM_ID, AOV_INST_ID, AOV_HIT_T = 0, 1, 2
 AOV_MISS = 0xFFFFFFFF

@@ -169,6 +169,8 @@ struct brt_context {
   int sm_count = 148;
   uint32_t tile_rank = 0, tile_world = 1, flags = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // shadow chain (occlusion + accumulate), overlapped with the next round's traversal
+  cudaEvent_t ev_shade = nullptr, ev_acc[2] = {nullptr, nullptr};
   bool own_stream = false;
   std::string err;
   std::unique_ptr<Builder> builder;
@@ -193,7 +195,7 @@ struct brt_context {
   // frame
   uint32_t cap = 0;  // path slots
   uint32_t frame_w = 0, frame_h = 0;
-  DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib, s_o, s_d, s_target;
+  DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
   DevBuf d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
   std::deque<EventPair> events;  // deque: references stay valid while the pool grows
@@ -251,11 +253,11 @@ EventPair& next_events(brt_context* c, int cls) {
   e.cls = cls;
   return e;
 }
-struct Timed {  // brackets one launch with events of class `cls`
-  brt_context* c;
+struct Timed {  // brackets one launch with events of class `cls` on the stream it is launched on
+  cudaStream_t s;
   EventPair* e;
-  Timed(brt_context* ctx, int cls) : c(ctx), e(&next_events(ctx, cls)) { BRT_CUDA(cudaEventRecord(e->a, c->stream)); }
-  ~Timed() { cudaEventRecord(e->b, c->stream); }
+  Timed(brt_context* ctx, int cls, cudaStream_t stream) : s(stream), e(&next_events(ctx, cls)) { BRT_CUDA(cudaEventRecord(e->a, s)); }
+  ~Timed() { cudaEventRecord(e->b, s); }
 };
 
 // ---- scene tables ------------------------------------------------------------------------------------
@@ -429,20 +431,22 @@ void ensure_frame_buffers(brt_context* c, const brt_render_opts& o) {
     c->q_w[k].ensure((size_t)cap * 16);
     c->q_px[k].ensure((size_t)cap * 4);
     c->q_seed[k].ensure((size_t)cap * 4);
+    // per round parity: what the occlusion / accumulate chain of a round owns
+    c->d_contrib[k].ensure((size_t)cap * 16 * L);
+    c->d_aux[k].ensure((size_t)cap * 16);
+    c->s_o[k].ensure((size_t)cap * 16 * L);
+    c->s_d[k].ensure((size_t)cap * 16 * L);
+    c->s_target[k].ensure((size_t)cap * 4 * L);
   }
   c->d_hit.ensure((size_t)cap * 16);
   c->d_hit_inst.ensure((size_t)cap * 4);
-  c->d_contrib.ensure((size_t)cap * 16 * L);
-  c->s_o.ensure((size_t)cap * 16 * L);
-  c->s_d.ensure((size_t)cap * 16 * L);
-  c->s_target.ensure((size_t)cap * 4 * L);
   c->d_accum.ensure(npx * 16);
   c->d_image.ensure(npx * 16);
   c->d_tiles.ensure((size_t)cap * 16);
   c->d_aov_prim.ensure(npx * 4);
   c->d_aov_inst.ensure(npx * 4);
   c->d_aov_t.ensure(npx * 4);
-  c->d_counters.ensure(sizeof(FrameCounters));
+  c->d_counters.ensure(sizeof(FrameCounters) + 2 * sizeof(ShadowCounters));
   c->d_fstats.ensure(sizeof(FrameStats));
   c->cap = cap;
   c->frame_w = o.width;
@@ -454,14 +458,21 @@ PathQueue queue_of(brt_context* c, int k) {
 }
 
 template <bool ANY>
-void launch_trace(brt_context* c, const TraceParams& p) {
+void launch_trace(brt_context* c, const TraceParams& p, cudaStream_t stream) {
   const uint32_t grid = (uint32_t)c->sm_count * 8u;
-  if (c->flags & BRT_CFG_COUNTERS) BRT_LAUNCH_TRACE(ANY, true, p, grid, c->stream);
-  else BRT_LAUNCH_TRACE(ANY, false, p, grid, c->stream);
+  if (c->flags & BRT_CFG_COUNTERS) BRT_LAUNCH_TRACE(ANY, true, p, grid, stream);
+  else BRT_LAUNCH_TRACE(ANY, false, p, grid, stream);
   BRT_CHECK_LAUNCH();
 }
 
-// renders into d_image (and d_tiles); no host synchronisation except the final stats read-back
+// Renders into d_image (and d_tiles); no host synchronisation except the final stats read-back.
+//
+// Two streams. The closest-hit chain  raygen -> { k_trace<closest> -> k_shade } per round  runs on the main stream; the
+// shadow chain of round k  { k_trace<occlusion> -> k_accumulate }  runs on the second stream and overlaps with round
+// k+1's closest-hit traversal (they are independent: shade(k) produced both the shadow rays of round k and the paths of
+// round k+1). The buffers the shadow chain owns (contributions, weights/pixels, shadow queue, counters) are
+// double-buffered by round parity; shade(k+2) waits for accumulate(k). Accumulation stays in round order on one stream,
+// so the result is bit-identical to the serial schedule (BRT_CFG_NO_OVERLAP, used for per-kernel timing).
 void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_opts& o, void* d_tiles_out) {
   if (!c->built) bad_state("render_frame: scene not built (call brt_scene_build)");
   if (!o.width || !o.height || !o.spp) invalid("render_frame: width, height and spp must be non-zero");
@@ -470,6 +481,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
   if (c->tlas_dirty) build_tlas(c);
   ensure_frame_buffers(c, o);
   cudaStream_t s = c->stream;
+  cudaStream_t s2 = (c->flags & BRT_CFG_NO_OVERLAP) ? c->stream : c->stream2;
   const TileMap map = make_tile_map(c, o);
   const uint32_t cap = c->cap;
   const size_t npx = (size_t)o.width * o.height;
@@ -477,6 +489,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
   const uint32_t n_slots = std::max(1u, n_lights);
   c->events_used = 0;
   FrameCounters* ctr = c->d_counters.as<FrameCounters>();
+  ShadowCounters* sctr = reinterpret_cast<ShadowCounters*>(ctr + 1);
   FrameStats* fst = c->d_fstats.as<FrameStats>();
   EventPair& whole = next_events(c, CLS_COUNT);
   BRT_CUDA(cudaEventRecord(whole.a, s));
@@ -491,6 +504,8 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
   uint32_t launches = 0, l_closest = 0, l_occl = 0;
   const Node8* tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
   const InstRec* insts = c->d_tlas_inst.as<InstRec>();
+  bool acc_pending[2] = {false, false};  // ev_acc[p] has been recorded and not yet waited for by the main stream
+  uint32_t global_round = 0;
 
   for (uint32_t sample = 0; sample < o.spp; ++sample) {
     {
@@ -503,21 +518,20 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       rp.frame = u.frame + sample;
       rp.flags = o.flags;
       rp.q = queue_of(c, 0);
-      Timed t(c, CLS_RAYGEN);
+      Timed t(c, CLS_RAYGEN, s);
       BRT_LAUNCH_1D(k_raygen, rp, grid_for(c, cap, 256, 8), 256, s);
       BRT_CHECK_LAUNCH();
       launches++;
     }
     int cur = 0;
-    for (uint32_t round = 0; round < rounds; ++round) {
-      // counters of this round: n_paths[cur] is live (or == cap in round 0), everything else restarts
+    for (uint32_t round = 0; round < rounds; ++round, ++global_round) {
+      const int par = (int)(global_round & 1u);
+      // main-chain counters: n_paths[cur] is live (round 0 walks all `cap` slots, padding slots carry px == BRT_MISS)
       if (round == 0) {
         BRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
-        // round 0 walks all `cap` slots (padding slots carry px == BRT_MISS)
       } else {
-        // keep n_paths[cur]; zero n_paths[next], the work cursors and the shadow counters
         BRT_CUDA(cudaMemsetAsync(&ctr->n_paths[cur ^ 1], 0, 4, s));
-        BRT_CUDA(cudaMemsetAsync(&ctr->work_closest, 0, sizeof(FrameCounters) - offsetof(FrameCounters, work_closest), s));
+        BRT_CUDA(cudaMemsetAsync(&ctr->work_closest, 0, 4, s));
       }
       const uint32_t* count_ptr = round == 0 ? nullptr : &ctr->n_paths[cur];
       const PathQueue qc = queue_of(c, cur), qn = queue_of(c, cur ^ 1);
@@ -534,11 +548,17 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         tp.hit_inst = c->d_hit_inst.as<uint32_t>();
         tp.work = &ctr->work_closest;
         tp.stats = fst;
-        Timed t(c, CLS_CLOSEST);
-        launch_trace<false>(c, tp);
+        Timed t(c, CLS_CLOSEST, s);
+        launch_trace<false>(c, tp, s);
         launches++;
         l_closest++;
       }
+      // the shadow-chain buffers of this parity were last used two rounds ago: wait for that accumulate
+      if (acc_pending[par]) {
+        if (s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, c->ev_acc[par], 0));
+        acc_pending[par] = false;
+      }
+      BRT_CUDA(cudaMemsetAsync(&sctr[par], 0, sizeof(ShadowCounters), s));
       {
         ShadeParams sp{};
         sp.count = cap;
@@ -548,6 +568,8 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         sp.hit = c->d_hit.as<float4>();
         sp.hit_inst = c->d_hit_inst.as<uint32_t>();
         sp.ctr = ctr;
+        sp.sctr = &sctr[par];
+        sp.aux = c->d_aux[par].as<float4>();
         sp.next_slot = (uint32_t)(cur ^ 1);
         sp.cap = cap;
         sp.inst = c->d_inst_shade.as<InstShade>();
@@ -555,10 +577,10 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         sp.mat_ext = c->d_mat_ext.as<float2>();
         sp.lights = c->d_lights.as<LightRec>();
         sp.n_lights = n_lights;
-        sp.contrib = c->d_contrib.as<float4>();
-        sp.s_o = c->s_o.as<float4>();
-        sp.s_d = c->s_d.as<float4>();
-        sp.s_target = c->s_target.as<uint32_t>();
+        sp.contrib = c->d_contrib[par].as<float4>();
+        sp.s_o = c->s_o[par].as<float4>();
+        sp.s_d = c->s_d[par].as<float4>();
+        sp.s_target = c->s_target[par].as<uint32_t>();
         sp.flags = o.flags;
         sp.last_round = round + 1 == rounds ? 1u : 0u;
         sp.write_aov = (sample == 0 && round == 0) ? 1u : 0u;
@@ -566,48 +588,56 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         sp.aov_inst = c->d_aov_inst.as<uint32_t>();
         sp.aov_t = c->d_aov_t.as<float>();
         sp.sky = c->sky;
-        Timed t(c, CLS_SHADE);
+        Timed t(c, CLS_SHADE, s);
         BRT_LAUNCH_1D(k_shade, sp, grid_for(c, cap, 128, 16), 128, s);
         BRT_CHECK_LAUNCH();
         launches++;
       }
+      if (s2 != s) {
+        BRT_CUDA(cudaEventRecord(c->ev_shade, s));
+        BRT_CUDA(cudaStreamWaitEvent(s2, c->ev_shade, 0));
+      }
       if (n_lights) {
         TraceParams tp{};
         tp.count = 0;
-        tp.seg_counts = ctr->n_shadow;
+        tp.seg_counts = sctr[par].n_shadow;
         tp.n_segs = n_lights;
         tp.seg_stride = cap;
         tp.tlas = tlas;
         tp.insts = insts;
-        tp.o = c->s_o.as<float4>();
-        tp.d = c->s_d.as<float4>();
-        tp.target = c->s_target.as<uint32_t>();
-        tp.contrib = c->d_contrib.as<float4>();
-        tp.work = &ctr->work_occl;
+        tp.o = c->s_o[par].as<float4>();
+        tp.d = c->s_d[par].as<float4>();
+        tp.target = c->s_target[par].as<uint32_t>();
+        tp.contrib = c->d_contrib[par].as<float4>();
+        tp.work = &sctr[par].work_occl;
         tp.stats = fst;
-        Timed t(c, CLS_OCCL);
-        launch_trace<true>(c, tp);
+        Timed t(c, CLS_OCCL, s2);
+        launch_trace<true>(c, tp, s2);
         launches++;
         l_occl++;
       }
       {
         AccumParams ap{};
-        ap.count = cap;
-        ap.count_ptr = count_ptr;
-        ap.px = qc.px;
-        ap.w = qc.w;
-        ap.contrib = c->d_contrib.as<float4>();
+        ap.count = 0;
+        ap.count_ptr = &sctr[par].n_items;
+        ap.aux = c->d_aux[par].as<float4>();
+        ap.contrib = c->d_contrib[par].as<float4>();
         ap.n_slots = n_slots;
         ap.cap = cap;
         ap.accum = c->d_accum.as<float4>();
-        Timed t(c, CLS_ACCUM);
-        BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, cap, 256, 8), 256, s);
+        Timed t(c, CLS_ACCUM, s2);
+        BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, cap, 256, 8), 256, s2);
         BRT_CHECK_LAUNCH();
         launches++;
       }
+      if (s2 != s) BRT_CUDA(cudaEventRecord(c->ev_acc[par], s2));
+      acc_pending[par] = true;
       cur ^= 1;
     }
   }
+  if (s2 != s)
+    for (int par = 0; par < 2; ++par)
+      if (acc_pending[par]) BRT_CUDA(cudaStreamWaitEvent(s, c->ev_acc[par], 0));
   {
     ResolveParams rp{};
     rp.count = cap;
@@ -617,7 +647,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
     rp.accum = c->d_accum.as<float4>();
     rp.image = c->d_image.as<float4>();
     rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : c->d_tiles.as<float4>();
-    Timed t(c, CLS_RESOLVE);
+    Timed t(c, CLS_RESOLVE, s);
     BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
     BRT_CHECK_LAUNCH();
     launches++;
@@ -681,6 +711,10 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     BRT_CUDA(cudaSetDevice(c->device));
     BRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     BRT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    BRT_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    BRT_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
+    BRT_CUDA(cudaEventCreateWithFlags(&c->ev_acc[0], cudaEventDisableTiming));
+    BRT_CUDA(cudaEventCreateWithFlags(&c->ev_acc[1], cudaEventDisableTiming));
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count));
   });
@@ -697,11 +731,16 @@ void brt_destroy(brt_context* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
   for (EventPair& e : c->events) {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_shade) cudaEventDestroy(c->ev_shade);
+  for (int k = 0; k < 2; ++k)
+    if (c->ev_acc[k]) cudaEventDestroy(c->ev_acc[k]);
   delete c;
 }
 
@@ -1021,7 +1060,7 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
     }
     c->d_rays.ensure((size_t)n * 32);
     c->d_ray_out.ensure((size_t)n * 16 + (size_t)n * 4 + (size_t)n * 4);
-    c->d_counters.ensure(sizeof(FrameCounters));
+    c->d_counters.ensure(sizeof(FrameCounters) + 2 * sizeof(ShadowCounters));
     c->d_fstats.ensure(sizeof(FrameStats));
     float4* d_o = c->d_rays.as<float4>();
     float4* d_d = d_o + n;
@@ -1030,7 +1069,7 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
     uint32_t* d_target = d_inst + n;
     BRT_CUDA(cudaMemcpyAsync(d_o, o4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s));
     BRT_CUDA(cudaMemcpyAsync(d_d, d4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s));
-    BRT_CUDA(cudaMemsetAsync(c->d_counters.ptr(), 0, sizeof(FrameCounters), s));
+    BRT_CUDA(cudaMemsetAsync(c->d_counters.ptr(), 0, sizeof(FrameCounters) + 2 * sizeof(ShadowCounters), s));
     BRT_CUDA(cudaMemsetAsync(c->d_fstats.ptr(), 0, sizeof(FrameStats), s));
     FrameCounters* ctr = c->d_counters.as<FrameCounters>();
     TraceParams tp{};
@@ -1046,7 +1085,7 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
       tp.hit = d_hit;
       tp.hit_inst = d_inst;
       tp.work = &ctr->work_closest;
-      launch_trace<false>(c, tp);
+      launch_trace<false>(c, tp, s);
       BRT_CUDA(cudaMemcpyAsync(hit.data(), d_hit, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
       BRT_CUDA(cudaMemcpyAsync(inst.data(), d_inst, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
       BRT_CUDA(cudaStreamSynchronize(s));
@@ -1069,8 +1108,8 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
       BRT_CUDA(cudaMemcpyAsync(d_target, target.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
       tp.target = d_target;
       tp.contrib = d_hit;
-      tp.work = &ctr->work_occl;
-      launch_trace<true>(c, tp);
+      tp.work = &reinterpret_cast<ShadowCounters*>(ctr + 1)->work_occl;
+      launch_trace<true>(c, tp, s);
       BRT_CUDA(cudaMemcpyAsync(hit.data(), d_hit, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
       BRT_CUDA(cudaStreamSynchronize(s));
       for (uint32_t i = 0; i < n; ++i) {

@@ -22,9 +22,15 @@ struct PathQueue {  // structure of arrays, one slot per live path
   uint32_t* seed;   // PCG state (SH/random.slang)
 };
 
-struct FrameCounters {  // device-side, reset per round
+struct FrameCounters {  // device-side, closest-hit / shade chain
   uint32_t n_paths[2];  // live paths in queue 0 / 1
-  uint32_t work_closest, work_occl;  // dynamic-fetch cursors of the trace kernels
+  uint32_t work_closest;  // dynamic-fetch cursor of the closest-hit kernel
+  uint32_t pad;
+};
+struct ShadowCounters {  // device-side, one per round parity: the occlusion / accumulate chain of a round runs on a second
+  uint32_t work_occl;    // stream, overlapped with the next round's closest-hit traversal
+  uint32_t n_items;      // path slots of the round (what k_accumulate walks)
+  uint32_t pad[2];
   uint32_t n_shadow[BRT_MAX_LIGHTS];  // shadow rays queued per light (segment l of the shadow queue)
 };
 struct FrameStats {  // device-side, reset per frame
@@ -162,6 +168,8 @@ struct ShadeParams {
   const float4* hit;
   const uint32_t* hit_inst;
   FrameCounters* ctr;
+  ShadowCounters* sctr;
+  float4* aux;             // per slot: path weight rgb + pixel (bits), read by k_accumulate
   uint32_t next_slot;      // which n_paths[] entry counts `next`
   uint32_t cap;            // slots per queue == stride of contrib per light
   const InstShade* inst;
@@ -211,6 +219,11 @@ BRT_HD f3 sky_color(const brt_sky& s, f3 dir) {
 
 BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   const uint32_t px = p.cur.px[i];
+  if (i == 0) p.sctr->n_items = p.count_ptr ? *p.count_ptr : p.count;
+  {
+    const float4 w = p.cur.w[i];
+    p.aux[i] = make_float4(w.x, w.y, w.z, u2f(px));
+  }
   if (px == BRT_MISS) return;
   const uint32_t n_slots = p.n_lights ? p.n_lights : 1u;
   const float4 ro = p.cur.o[i], rd = p.cur.d[i];
@@ -287,7 +300,7 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
         contrib = color * F3(lr.pos_colr.w, lr.color_g, lr.color_b) * intensity;  // :83
         if (!(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f)) {
           const f3 so = worldPos + N * 0.0001f;  // testShadow :56-70
-          const uint32_t k = l * p.cap + append_slot(&p.ctr->n_shadow[l]);
+          const uint32_t k = l * p.cap + append_slot(&p.sctr->n_shadow[l]);
           p.s_o[k] = make_float4(so.x, so.y, so.z, 0.001f);
           p.s_d[k] = make_float4(L.x, L.y, L.z, length(ldir));
           p.s_target[k] = l * p.cap + i;
@@ -347,14 +360,14 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
 struct AccumParams {
   uint32_t count;
   const uint32_t* count_ptr;
-  const uint32_t* px;
-  const float4* w;
+  const float4* aux;  // weight rgb, pixel
   const float4* contrib;
   uint32_t n_slots, cap;
   float4* accum;  // per pixel running sum over samples and depths
 };
 BRT_HD void accumulate_body(const AccumParams& p, uint32_t i) {
-  const uint32_t px = p.px[i];
+  const float4 w = p.aux[i];
+  const uint32_t px = f2u(w.w);
   if (px == BRT_MISS) return;
   const float4 c0 = p.contrib[i];
   f3 c = F3(c0.x, c0.y, c0.z);
@@ -362,7 +375,6 @@ BRT_HD void accumulate_body(const AccumParams& p, uint32_t i) {
     const float4 cl = p.contrib[(size_t)l * p.cap + i];
     c = c + F3(cl.x, cl.y, cl.z);  // :84, light order
   }
-  const float4 w = p.w[i];
   float4 a = p.accum[px];
   a.x = a.x + c.x * w.x;  // :122
   a.y = a.y + c.y * w.y;

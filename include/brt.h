@@ -117,6 +117,9 @@ typedef struct brt_config {
  * PREFER_FAST_TRACE (LBVH + SAH treelet restructuring); rebuilds after brt_mesh_update_vertices are
  * PREFER_FAST_BUILD (plain LBVH, what the reference's prepareRendering placeholder names) unless this flag is set. */
 #define BRT_CFG_TREELET_ON_REBUILD 4u
+/* run every kernel of a frame on one stream (default: the shadow chain of a round overlaps the next round's
+ * closest-hit traversal on a second stream). Same results; used when per-kernel event times must not overlap. */
+#define BRT_CFG_NO_OVERLAP 8u
 
 /* render mode flags. With none of the BOUNCE flags set the behaviour is the reference's live path:
  * direct light + hard shadows, weight = 0 after the first hit (SH/raytracing.slang:168). */

@@ -36,6 +36,9 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSucce
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event{0.0}; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emu_event{0.0}; return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : 2; }

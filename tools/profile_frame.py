@@ -20,11 +20,12 @@ def main():
     ap.add_argument("--counters", action="store_true")
     ap.add_argument("--no-treelet", action="store_true")
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
     pkg = importlib.import_module("hardware-ray-tracer_b200")
     cfg = dict(pkg.scenes.CONFIGS[args.config])
     scene = pkg.scenes.make_scene(cfg.pop("scene"), small=args.small)
-    flags = (pkg.CFG_COUNTERS if args.counters else 0) | (pkg.CFG_NO_TREELET if args.no_treelet else 0)
+    flags = (pkg.CFG_COUNTERS if args.counters else 0) | (pkg.CFG_NO_TREELET if args.no_treelet else 0) | (pkg.CFG_NO_OVERLAP if args.no_overlap else 0)
     ctx = pkg.Context(device=0, flags=flags)
     t0 = time.perf_counter()
     scene.upload(ctx)
