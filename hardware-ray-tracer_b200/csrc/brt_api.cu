@@ -44,13 +44,10 @@ static void k_trace(const TraceParams p) {
 #define BRT_LAUNCH_TRACE(ANY, COUNT, params, grid, stream) k_trace<ANY, COUNT>(params)
 #else
 #ifndef BRT_TRACE_MIN_BLOCKS
-#define BRT_TRACE_MIN_BLOCKS 6
-#endif
-#ifndef BRT_REFILL_LANES
-#define BRT_REFILL_LANES 0  // lanes of a warp that must still be traversing; below that the idle lanes fetch new rays
+#define BRT_TRACE_MIN_BLOCKS 7
 #endif
 // Persistent warps with per-lane refill: every lane runs one ray's Traversal; when fewer than
-// BRT_REFILL_LANES lanes of the warp are still busy, the idle lanes claim the next rays of the queue from
+// p.refill_lanes lanes of the warp are still busy (0 = only when all are done), the idle lanes claim the next rays of the queue from
 // a global cursor (one warp-aggregated atomic) so that the SIMD lanes stay occupied however uneven the
 // per-ray cost is. The first fetch of a warp is 32 consecutive rays = one 8x4 pixel block (coherent).
 template <bool ANY, bool COUNT>
@@ -97,7 +94,7 @@ __global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const Trace
           active = false;
           break;
         }
-        if (!exhausted && __popc(__activemask()) < BRT_REFILL_LANES) break;
+        if (!exhausted && __popc(__activemask()) < (int)p.refill_lanes) break;
       }
     }
     __syncwarp();
@@ -158,6 +155,7 @@ struct EventPair {
   int cls = 0;
 };
 
+#define BRT_REFILL_LANES_INCOHERENT 16u
 enum { CLS_RAYGEN = 0, CLS_CLOSEST, CLS_SHADE, CLS_OCCL, CLS_ACCUM, CLS_RESOLVE, CLS_COUNT };
 
 }  // namespace brt
@@ -548,6 +546,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         tp.hit_inst = c->d_hit_inst.as<uint32_t>();
         tp.work = &ctr->work_closest;
         tp.stats = fst;
+        tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;  // measured: refill pays for bounce rays only
         Timed t(c, CLS_CLOSEST, s);
         launch_trace<false>(c, tp, s);
         launches++;
@@ -611,6 +610,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         tp.contrib = c->d_contrib[par].as<float4>();
         tp.work = &sctr[par].work_occl;
         tp.stats = fst;
+        tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;
         Timed t(c, CLS_OCCL, s2);
         launch_trace<true>(c, tp, s2);
         launches++;

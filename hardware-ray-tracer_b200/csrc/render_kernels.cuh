@@ -119,6 +119,7 @@ struct TraceParams {
   // (The shadow queue has one segment per light so that neighbouring lanes trace towards the same light.)
   const uint32_t* seg_counts;
   uint32_t n_segs, seg_stride;
+  uint32_t refill_lanes;  // device kernel: idle lanes fetch new rays when fewer than this many lanes are still traversing
 };
 BRT_HD uint32_t trace_total(const TraceParams& p) {
   if (p.seg_counts) {
@@ -190,17 +191,21 @@ struct ShadeParams {
   brt_sky sky;
 };
 
+// Warp-aggregated append: the lanes that execute this together AND target the same counter share one atomic.
+// (Grouping by address matters: with independent thread scheduling, lanes that are in different iterations of
+// the per-light loop — different counters — can be converged at this instruction; a plain __activemask()
+// aggregate would then hand them slots of the wrong queue segment.)
 BRT_HD uint32_t append_slot(uint32_t* counter) {
 #ifdef BRT_EMU
   return atomic_add(counter, 1u);
 #else
-  const unsigned mask = __activemask();
-  const int leader = __ffs(mask) - 1;
+  const unsigned peers = __match_any_sync(__activemask(), (unsigned long long)counter);
+  const int leader = __ffs(peers) - 1;
   const int lane = threadIdx.x & 31;
   uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-  base = __shfl_sync(mask, base, leader);
-  return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 #endif
 }
 
