@@ -17,7 +17,10 @@ namespace brt {
 
 // ---- kernels ---------------------------------------------------------------------------------------
 BRT_KERNEL_1D(k_raygen, RaygenParams, raygen_body)
-BRT_KERNEL_1D(k_shade, ShadeParams, shade_body)
+#ifndef BRT_SHADE_MIN_BLOCKS
+#define BRT_SHADE_MIN_BLOCKS 4
+#endif
+BRT_KERNEL_1D_LB(k_shade, ShadeParams, shade_body, 128, BRT_SHADE_MIN_BLOCKS)
 BRT_KERNEL_1D(k_accumulate, AccumParams, accumulate_body)
 BRT_KERNEL_1D(k_resolve, ResolveParams, resolve_body)
 BRT_KERNEL_1D(k_untile, UntileParams, untile_body)

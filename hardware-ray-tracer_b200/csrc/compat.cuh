@@ -191,3 +191,14 @@ BRT_HD uint4 ldg4(const uint4* p) {
   }
 #define BRT_LAUNCH_1D(name, params, grid, block, stream) name<<<(grid), (block), 0, (stream)>>>(params)
 #endif
+// same, with an explicit (threads per block, resident blocks per SM) occupancy target for register-heavy kernels
+#ifdef BRT_EMU
+#define BRT_KERNEL_1D_LB(name, Params, body, threads, min_blocks) BRT_KERNEL_1D(name, Params, body)
+#else
+#define BRT_KERNEL_1D_LB(name, Params, body, threads, min_blocks)                                       \
+  __global__ void __launch_bounds__(threads, min_blocks) name(const Params p) {                         \
+    const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;                                            \
+    const uint32_t stride = gridDim.x * blockDim.x;                                                     \
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) body(p, i);            \
+  }
+#endif
