@@ -22,6 +22,7 @@ BRT_KERNEL_1D(k_raygen, RaygenParams, raygen_body)
 #endif
 BRT_KERNEL_1D_LB(k_shade, ShadeParams, shade_body, 128, BRT_SHADE_MIN_BLOCKS)
 BRT_KERNEL_1D(k_accumulate, AccumParams, accumulate_body)
+BRT_KERNEL_1D(k_sum_samples, SumSamplesParams, sum_samples_body)
 BRT_KERNEL_1D(k_resolve, ResolveParams, resolve_body)
 BRT_KERNEL_1D(k_untile, UntileParams, untile_body)
 BRT_KERNEL_1D(k_cull, CullParams, cull_body)
@@ -194,10 +195,12 @@ struct brt_context {
   BuildResult tlas{};
 
   // frame
-  uint32_t cap = 0;  // path slots
+  uint32_t cap = 0;    // path slots per sample (owned tiles * 1024)
+  uint32_t batch = 1;  // samples traced together in one wavefront
+  size_t frame_bytes = 0;
   uint32_t frame_w = 0, frame_h = 0;
   DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
-  DevBuf d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
+  DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
   std::deque<EventPair> events;  // deque: references stay valid while the pool grows
   size_t events_used = 0;
@@ -422,26 +425,40 @@ uint32_t tiles_per_rank(uint32_t width, uint32_t height, uint32_t world) {
   return div_up(n, world ? world : 1);
 }
 
-void ensure_frame_buffers(brt_context* c, const brt_render_opts& o) {
+// Sizes the per-frame buffers. A wavefront holds `batch` samples of every owned pixel at once (cap slots per sample): the
+// more samples share a launch, the less the latency-bound tail of every launch costs — this is what keeps the tile-parallel
+// multi-GPU frames efficient, where each rank only has 1/N of the pixels.
+void ensure_frame_buffers(brt_context* c, const brt_render_opts& o, uint32_t rounds) {
   const uint32_t cap = tiles_per_rank(o.width, o.height, c->tile_world) * 1024u;
   const size_t npx = (size_t)o.width * o.height;
   const uint32_t L = std::max<uint32_t>(1, (uint32_t)c->lights.size());
+  const uint32_t R = std::max(1u, rounds);
+  // bytes per sample of the batch: two path queues, hits, and per round parity: contributions, weights, shadow queue; + radiance terms
+  const size_t per_sample = (size_t)cap * (2 * 56 + 20 + 2 * (16 * L + 16 + 36 * L) + 16 * R);
+  size_t free_b = 0, total_b = 0;
+  BRT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + c->frame_bytes) * 2 / 5);
+  uint32_t batch = (uint32_t)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_sample, 1), BRT_MAX_SAMPLE_BATCH));
+  batch = std::min(batch, std::max(1u, o.spp));
+  if ((uint64_t)cap * batch > 0xfffffff0ull / L) batch = std::max<uint64_t>(1, 0xfffffff0ull / L / cap);  // 32-bit shadow-queue targets
+  const size_t capw = (size_t)cap * batch;
   for (int k = 0; k < 2; ++k) {
-    c->q_o[k].ensure((size_t)cap * 16);
-    c->q_d[k].ensure((size_t)cap * 16);
-    c->q_w[k].ensure((size_t)cap * 16);
-    c->q_px[k].ensure((size_t)cap * 4);
-    c->q_seed[k].ensure((size_t)cap * 4);
+    c->q_o[k].ensure(capw * 16);
+    c->q_d[k].ensure(capw * 16);
+    c->q_w[k].ensure(capw * 16);
+    c->q_px[k].ensure(capw * 4);
+    c->q_seed[k].ensure(capw * 4);
     // per round parity: what the occlusion / accumulate chain of a round owns
-    c->d_contrib[k].ensure((size_t)cap * 16 * L);
-    c->d_aux[k].ensure((size_t)cap * 16);
-    c->s_o[k].ensure((size_t)cap * 16 * L);
-    c->s_d[k].ensure((size_t)cap * 16 * L);
-    c->s_target[k].ensure((size_t)cap * 4 * L);
+    c->d_contrib[k].ensure(capw * 16 * L);
+    c->d_aux[k].ensure(capw * 16);
+    c->s_o[k].ensure(capw * 16 * L);
+    c->s_d[k].ensure(capw * 16 * L);
+    c->s_target[k].ensure(capw * 4 * L);
   }
-  c->d_hit.ensure((size_t)cap * 16);
-  c->d_hit_inst.ensure((size_t)cap * 4);
-  c->d_accum.ensure(npx * 16);
+  c->d_hit.ensure(capw * 16);
+  c->d_hit_inst.ensure(capw * 4);
+  c->d_rad.ensure(capw * 16 * R);
+  c->d_accum.ensure((size_t)cap * 16);
   c->d_image.ensure(npx * 16);
   c->d_tiles.ensure((size_t)cap * 16);
   c->d_aov_prim.ensure(npx * 4);
@@ -449,7 +466,9 @@ void ensure_frame_buffers(brt_context* c, const brt_render_opts& o) {
   c->d_aov_t.ensure(npx * 4);
   c->d_counters.ensure(sizeof(FrameCounters) + 2 * sizeof(ShadowCounters));
   c->d_fstats.ensure(sizeof(FrameStats));
+  c->frame_bytes = per_sample * batch;
   c->cap = cap;
+  c->batch = batch;
   c->frame_w = o.width;
   c->frame_h = o.height;
 }
@@ -480,7 +499,9 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
   if (c->lights.size() > BRT_MAX_LIGHTS) throw LimitError("render_frame: more than BRT_MAX_LIGHTS lights");
   if (c->tables_dirty) build_tables(c);
   if (c->tlas_dirty) build_tlas(c);
-  ensure_frame_buffers(c, o);
+  const bool any_bounce = (o.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0;
+  const uint32_t rounds = any_bounce ? u.depthMax : std::min(u.depthMax, 1u);
+  ensure_frame_buffers(c, o, rounds);
   cudaStream_t s = c->stream;
   cudaStream_t s2 = (c->flags & BRT_CFG_NO_OVERLAP) ? c->stream : c->stream2;
   const TileMap map = make_tile_map(c, o);
@@ -494,40 +515,42 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
   FrameStats* fst = c->d_fstats.as<FrameStats>();
   EventPair& whole = next_events(c, CLS_COUNT);
   BRT_CUDA(cudaEventRecord(whole.a, s));
-  BRT_CUDA(cudaMemsetAsync(c->d_accum.ptr(), 0, npx * 16, s));
+  BRT_CUDA(cudaMemsetAsync(c->d_accum.ptr(), 0, (size_t)cap * 16, s));
   BRT_CUDA(cudaMemsetAsync(fst, 0, sizeof(FrameStats), s));
   BRT_CUDA(cudaMemsetAsync(c->d_aov_prim.ptr(), 0xff, npx * 4, s));
   BRT_CUDA(cudaMemsetAsync(c->d_aov_inst.ptr(), 0xff, npx * 4, s));
   BRT_CUDA(cudaMemsetAsync(c->d_aov_t.ptr(), 0, npx * 4, s));
   if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(c->d_image.ptr(), 0, npx * 16, s));
-  const bool any_bounce = (o.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0;
-  const uint32_t rounds = any_bounce ? u.depthMax : std::min(u.depthMax, 1u);
   uint32_t launches = 0, l_closest = 0, l_occl = 0;
   const Node8* tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
   const InstRec* insts = c->d_tlas_inst.as<InstRec>();
   bool acc_pending[2] = {false, false};  // ev_acc[p] has been recorded and not yet waited for by the main stream
   uint32_t global_round = 0;
 
-  for (uint32_t sample = 0; sample < o.spp; ++sample) {
+  for (uint32_t sample = 0; sample < o.spp; sample += c->batch) {
+    const uint32_t nb = std::min(c->batch, o.spp - sample);  // samples in this wavefront
+    const uint32_t capw = cap * nb;                          // its path slots
+    if (rounds) BRT_CUDA(cudaMemsetAsync(c->d_rad.ptr(), 0, (size_t)capw * rounds * 16, s));
     {
       RaygenParams rp;
-      rp.count = cap;
+      rp.count = capw;
       rp.count_ptr = nullptr;
       rp.map = map;
       std::memcpy(rp.Vi, u.viewInverse, 64);
       std::memcpy(rp.Pi, u.projInverse, 64);
       rp.frame = u.frame + sample;
       rp.flags = o.flags;
+      rp.cap = cap;
       rp.q = queue_of(c, 0);
       Timed t(c, CLS_RAYGEN, s);
-      BRT_LAUNCH_1D(k_raygen, rp, grid_for(c, cap, 256, 8), 256, s);
+      BRT_LAUNCH_1D(k_raygen, rp, grid_for(c, capw, 256, 8), 256, s);
       BRT_CHECK_LAUNCH();
       launches++;
     }
     int cur = 0;
     for (uint32_t round = 0; round < rounds; ++round, ++global_round) {
       const int par = (int)(global_round & 1u);
-      // main-chain counters: n_paths[cur] is live (round 0 walks all `cap` slots, padding slots carry px == BRT_MISS)
+      // main-chain counters: n_paths[cur] is live (round 0 walks all `capw` slots, padding slots carry id == BRT_MISS)
       if (round == 0) {
         BRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
       } else {
@@ -538,7 +561,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       const PathQueue qc = queue_of(c, cur), qn = queue_of(c, cur ^ 1);
       {
         TraceParams tp{};
-        tp.count = cap;
+        tp.count = capw;
         tp.count_ptr = count_ptr;
         tp.tlas = tlas;
         tp.insts = insts;
@@ -563,7 +586,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       BRT_CUDA(cudaMemsetAsync(&sctr[par], 0, sizeof(ShadowCounters), s));
       {
         ShadeParams sp{};
-        sp.count = cap;
+        sp.count = capw;
         sp.count_ptr = count_ptr;
         sp.cur = qc;
         sp.next = qn;
@@ -573,7 +596,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         sp.sctr = &sctr[par];
         sp.aux = c->d_aux[par].as<float4>();
         sp.next_slot = (uint32_t)(cur ^ 1);
-        sp.cap = cap;
+        sp.cap = capw;
         sp.inst = c->d_inst_shade.as<InstShade>();
         sp.materials = c->d_materials.as<float>();
         sp.mat_ext = c->d_mat_ext.as<float2>();
@@ -586,12 +609,13 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         sp.flags = o.flags;
         sp.last_round = round + 1 == rounds ? 1u : 0u;
         sp.write_aov = (sample == 0 && round == 0) ? 1u : 0u;
+        sp.map = map;
         sp.aov_prim = c->d_aov_prim.as<uint32_t>();
         sp.aov_inst = c->d_aov_inst.as<uint32_t>();
         sp.aov_t = c->d_aov_t.as<float>();
         sp.sky = c->sky;
         Timed t(c, CLS_SHADE, s);
-        BRT_LAUNCH_1D(k_shade, sp, grid_for(c, cap, 128, 16), 128, s);
+        BRT_LAUNCH_1D(k_shade, sp, grid_for(c, capw, 128, 16), 128, s);
         BRT_CHECK_LAUNCH();
         launches++;
       }
@@ -604,7 +628,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         tp.count = 0;
         tp.seg_counts = sctr[par].n_shadow;
         tp.n_segs = n_lights;
-        tp.seg_stride = cap;
+        tp.seg_stride = capw;
         tp.tlas = tlas;
         tp.insts = insts;
         tp.o = c->s_o[par].as<float4>();
@@ -626,10 +650,13 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         ap.aux = c->d_aux[par].as<float4>();
         ap.contrib = c->d_contrib[par].as<float4>();
         ap.n_slots = n_slots;
-        ap.cap = cap;
-        ap.accum = c->d_accum.as<float4>();
+        ap.cap = capw;
+        ap.slots = cap;
+        ap.rounds = rounds;
+        ap.round = round;
+        ap.rad = c->d_rad.as<float4>();
         Timed t(c, CLS_ACCUM, s2);
-        BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, cap, 256, 8), 256, s2);
+        BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, capw, 256, 8), 256, s2);
         BRT_CHECK_LAUNCH();
         launches++;
       }
@@ -637,10 +664,25 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       acc_pending[par] = true;
       cur ^= 1;
     }
+    // join the shadow chain, then add this batch's radiance terms to the per-slot sums in the shader's order
+    for (int par = 0; par < 2; ++par) {
+      if (acc_pending[par] && s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, c->ev_acc[par], 0));
+      acc_pending[par] = false;
+    }
+    if (rounds) {
+      SumSamplesParams sp{};
+      sp.count = cap;
+      sp.count_ptr = nullptr;
+      sp.samples = nb;
+      sp.rounds = rounds;
+      sp.rad = c->d_rad.as<float4>();
+      sp.accum = c->d_accum.as<float4>();
+      Timed t(c, CLS_ACCUM, s);
+      BRT_LAUNCH_1D(k_sum_samples, sp, grid_for(c, cap, 256, 8), 256, s);
+      BRT_CHECK_LAUNCH();
+      launches++;
+    }
   }
-  if (s2 != s)
-    for (int par = 0; par < 2; ++par)
-      if (acc_pending[par]) BRT_CUDA(cudaStreamWaitEvent(s, c->ev_acc[par], 0));
   {
     ResolveParams rp{};
     rp.count = cap;

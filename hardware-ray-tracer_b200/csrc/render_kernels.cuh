@@ -18,7 +18,7 @@ struct PathQueue {  // structure of arrays, one slot per live path
   float4* o;        // origin xyz, tmin
   float4* d;        // direction xyz, tmax
   float4* w;        // HitPayload.weight widened to RGB (the diffuse-bounce extension tints per channel)
-  uint32_t* px;     // pixel index y * width + x, BRT_MISS for padding slots
+  uint32_t* px;     // path id: tile-order slot of the pixel (low 26 bits) | sample-in-batch (high 6 bits); BRT_MISS for padding
   uint32_t* seed;   // PCG state (SH/random.slang)
 };
 
@@ -44,6 +44,9 @@ struct TileMap {
   uint32_t tile_rank, tile_world;
   uint32_t crop_x0, crop_y0, crop_x1, crop_y1;  // traced window [x0,x1) x [y0,y1)
 };
+#define BRT_SLOT_BITS 26
+#define BRT_SLOT_MASK 0x03ffffffu
+#define BRT_MAX_SAMPLE_BATCH 63u  // sample-in-batch must stay below 63 so that an id never equals BRT_MISS
 BRT_HD uint32_t compact5(uint32_t v) {  // even bits of a 10-bit Morton code -> 5 bits
   v &= 0x155u;
   v = (v | (v >> 1)) & 0x133u;
@@ -62,26 +65,42 @@ BRT_HD bool slot_to_pixel(const TileMap& m, uint32_t slot, uint32_t& x, uint32_t
   return x >= m.crop_x0 && x < m.crop_x1 && y >= m.crop_y0 && y < m.crop_y1;
 }
 
+BRT_HD uint32_t spread5(uint32_t v) {  // 5 bits -> even bits of a 10-bit Morton code
+  v &= 0x1fu;
+  v = (v | (v << 4)) & 0x10fu;
+  v = (v | (v << 2)) & 0x133u;
+  v = (v | (v << 1)) & 0x155u;
+  return v;
+}
+// pixel -> path slot of the rank that owns its tile (inverse of slot_to_pixel)
+BRT_HD uint32_t pixel_to_slot(const TileMap& m, uint32_t x, uint32_t y) {
+  const uint32_t tile = (y / BRT_TILE) * m.tiles_x + x / BRT_TILE;
+  return (tile / m.tile_world) * 1024u + (spread5(x % BRT_TILE) | (spread5(y % BRT_TILE) << 1));
+}
+
 // ---- raygen --------------------------------------------------------------------------------------
 struct RaygenParams {
   uint32_t count;
   const uint32_t* count_ptr;
   TileMap map;
   float Vi[16], Pi[16];  // brt_uniform.viewInverse / projInverse, read as row-major M^-1 (RT/RTApp.cpp:44-49)
-  uint32_t frame;        // uniform.frame + sample index
+  uint32_t frame;        // uniform.frame + index of the first sample of this batch
   uint32_t flags;
+  uint32_t cap;          // path slots per sample; the batch traces count = cap * samples paths at once
   PathQueue q;
 };
 BRT_HD void raygen_body(const RaygenParams& p, uint32_t i) {
+  const uint32_t sib = i / p.cap, slot = i - sib * p.cap;  // sample in batch, tile-order slot
   uint32_t px, py;
-  if (!slot_to_pixel(p.map, i, px, py)) {
+  if (!slot_to_pixel(p.map, slot, px, py)) {
     p.q.px[i] = BRT_MISS;
     return;
   }
-  uint32_t seed = hash3(px, py, p.frame);  // :96
+  const uint32_t frame = p.frame + sib;
+  uint32_t seed = hash3(px, py, frame);  // :96
   float jx = 0.0f, jy = 0.0f;
   if (p.flags & BRT_RENDER_JITTER) {  // :97-98 (the shader computes it and then drops it at :100)
-    if (p.frame == 0u) { jx = 0.5f; jy = 0.5f; }
+    if (frame == 0u) { jx = 0.5f; jy = 0.5f; }
     else { jx = rnd(seed); jy = rnd(seed); }
   }
   const float* Pi = p.Pi;
@@ -96,7 +115,7 @@ BRT_HD void raygen_body(const RaygenParams& p, uint32_t i) {
   p.q.o[i] = make_float4(Vi[3], Vi[7], Vi[11], 0.001f);               // :105-106
   p.q.d[i] = make_float4(dir.x, dir.y, dir.z, BRT_INFINITE);           // :107
   p.q.w[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);                      // :110
-  p.q.px[i] = py * p.map.width + px;
+  p.q.px[i] = slot | (sib << BRT_SLOT_BITS);
   p.q.seed[i] = seed;
 }
 
@@ -184,7 +203,8 @@ struct ShadeParams {
   uint32_t* s_target;
   uint32_t flags;
   uint32_t last_round;     // no bounce is generated in the last round of the depth loop
-  uint32_t write_aov;
+  uint32_t write_aov;      // round 0 of the first batch: sample 0 writes the primary-hit AOVs
+  TileMap map;
   uint32_t* aov_prim;
   uint32_t* aov_inst;
   float* aov_t;
@@ -235,10 +255,13 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   const f3 ray_o = F3(ro.x, ro.y, ro.z), ray_d = F3(rd.x, rd.y, rd.z);
   const uint32_t inst_id = p.hit_inst[i];
   const float4 hit = p.hit[i];
-  if (p.write_aov) {
-    p.aov_prim[px] = inst_id == BRT_MISS ? BRT_MISS : f2u(hit.w);
-    p.aov_inst[px] = inst_id;
-    p.aov_t[px] = inst_id == BRT_MISS ? 0.0f : hit.x;
+  if (p.write_aov && (px >> BRT_SLOT_BITS) == 0u) {
+    uint32_t x, y;
+    slot_to_pixel(p.map, px & BRT_SLOT_MASK, x, y);
+    const size_t pix = (size_t)y * p.map.width + x;
+    p.aov_prim[pix] = inst_id == BRT_MISS ? BRT_MISS : f2u(hit.w);
+    p.aov_inst[pix] = inst_id;
+    p.aov_t[pix] = inst_id == BRT_MISS ? 0.0f : hit.x;
   }
   if (inst_id == BRT_MISS) {  // rmissMain :172-176
     f3 c = F3(0.0f);
@@ -362,29 +385,49 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
 }
 
 // ---- accumulate ------------------------------------------------------------------------------------
+// `c += payload.color * weight` (SH/raytracing.slang:122), deferred: round r of sample-in-batch s of a slot writes its
+// term into rad[s][r][slot]; k_sum_samples then adds the terms of a slot in the shader's order (samples in order, depths
+// in order). That keeps the sum bit-identical to the sequential loop while a whole batch of samples shares one wavefront.
 struct AccumParams {
   uint32_t count;
   const uint32_t* count_ptr;
-  const float4* aux;  // weight rgb, pixel
+  const float4* aux;  // weight rgb, path id
   const float4* contrib;
-  uint32_t n_slots, cap;
-  float4* accum;  // per pixel running sum over samples and depths
+  uint32_t n_slots, cap;   // light slots; stride of contrib per light (= slots of the whole batch)
+  uint32_t slots, rounds, round;  // path slots per sample, depth rounds per sample, this round
+  float4* rad;        // [sample in batch][round][slot]
 };
 BRT_HD void accumulate_body(const AccumParams& p, uint32_t i) {
   const float4 w = p.aux[i];
-  const uint32_t px = f2u(w.w);
-  if (px == BRT_MISS) return;
+  const uint32_t id = f2u(w.w);
+  if (id == BRT_MISS) return;
   const float4 c0 = p.contrib[i];
   f3 c = F3(c0.x, c0.y, c0.z);
   for (uint32_t l = 1; l < p.n_slots; ++l) {
     const float4 cl = p.contrib[(size_t)l * p.cap + i];
     c = c + F3(cl.x, cl.y, cl.z);  // :84, light order
   }
-  float4 a = p.accum[px];
-  a.x = a.x + c.x * w.x;  // :122
-  a.y = a.y + c.y * w.y;
-  a.z = a.z + c.z * w.z;
-  p.accum[px] = a;
+  const uint32_t sib = id >> BRT_SLOT_BITS, slot = id & BRT_SLOT_MASK;
+  p.rad[((size_t)sib * p.rounds + p.round) * p.slots + slot] = make_float4(c.x * w.x, c.y * w.y, c.z * w.z, 0.0f);
+}
+
+struct SumSamplesParams {
+  uint32_t count;  // slots
+  const uint32_t* count_ptr;
+  uint32_t samples, rounds;
+  const float4* rad;
+  float4* accum;   // per slot running sum over all samples so far
+};
+BRT_HD void sum_samples_body(const SumSamplesParams& p, uint32_t i) {
+  float4 a = p.accum[i];
+  for (uint32_t s = 0; s < p.samples; ++s)
+    for (uint32_t r = 0; r < p.rounds; ++r) {
+      const float4 t = p.rad[((size_t)s * p.rounds + r) * p.count + i];
+      a.x = a.x + t.x;  // :122
+      a.y = a.y + t.y;
+      a.z = a.z + t.z;
+    }
+  p.accum[i] = a;
 }
 
 // ---- resolve ---------------------------------------------------------------------------------------
@@ -393,7 +436,7 @@ struct ResolveParams {
   const uint32_t* count_ptr;
   TileMap map;
   float spp;
-  const float4* accum;
+  const float4* accum;  // per slot
   float4* image;   // full frame, row major
   float4* tiles;   // this rank's tiles packed tile-major, row-major inside a tile (may be null)
 };
@@ -406,7 +449,7 @@ BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
   float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   const bool inside = x < p.map.width && y < p.map.height;
   if (inside && x >= p.map.crop_x0 && x < p.map.crop_x1 && y >= p.map.crop_y0 && y < p.map.crop_y1) {
-    const float4 a = p.accum[(size_t)y * p.map.width + x];
+    const float4 a = p.accum[(i & ~1023u) | spread5(lx) | (spread5(ly) << 1)];
     out = make_float4(a.x / p.spp, a.y / p.spp, a.z / p.spp, 1.0f);  // :129-132
   }
   if (inside) p.image[(size_t)y * p.map.width + x] = out;
