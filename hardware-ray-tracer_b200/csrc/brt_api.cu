@@ -3,6 +3,7 @@
 // RayTracing::Pipeline (RT/RTPipeline.cpp) and the uniform block of RTApp::run (RT/RTApp.cpp:44-49).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -197,7 +198,9 @@ struct brt_context {
   // frame
   uint32_t cap = 0;    // path slots per sample (owned tiles * 1024)
   uint32_t batch = 1;  // samples traced together in one wavefront
+  uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
   size_t frame_bytes = 0;
+  uint64_t frame_key[4] = {0, 0, 0, 0};
   uint32_t frame_w = 0, frame_h = 0;
   DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
   DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
@@ -433,12 +436,18 @@ void ensure_frame_buffers(brt_context* c, const brt_render_opts& o, uint32_t rou
   const size_t npx = (size_t)o.width * o.height;
   const uint32_t L = std::max<uint32_t>(1, (uint32_t)c->lights.size());
   const uint32_t R = std::max(1u, rounds);
+  const uint64_t key[4] = {((uint64_t)o.width << 32) | o.height, ((uint64_t)o.spp << 32) | R, L, c->target_wavefront};
+  if (c->frame_bytes && std::memcmp(key, c->frame_key, sizeof(key)) == 0) return;  // same frame shape as last time
+  std::memcpy(c->frame_key, key, sizeof(key));
   // bytes per sample of the batch: two path queues, hits, and per round parity: contributions, weights, shadow queue; + radiance terms
   const size_t per_sample = (size_t)cap * (2 * 56 + 20 + 2 * (16 * L + 16 + 36 * L) + 16 * R);
   size_t free_b = 0, total_b = 0;
   BRT_CUDA(cudaMemGetInfo(&free_b, &total_b));
   size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + c->frame_bytes) * 2 / 5);
   uint32_t batch = (uint32_t)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_sample, 1), BRT_MAX_SAMPLE_BATCH));
+  // enough samples per wavefront to amortise the per-launch tails (about 16 M paths), no more: larger wavefronts only cost
+  // memory traffic
+  batch = std::min(batch, std::max(1u, div_up(c->target_wavefront, std::max(cap, 1u))));
   batch = std::min(batch, std::max(1u, o.spp));
   if ((uint64_t)cap * batch > 0xfffffff0ull / L) batch = std::max<uint64_t>(1, 0xfffffff0ull / L / cap);  // 32-bit shadow-queue targets
   const size_t capw = (size_t)cap * batch;
@@ -762,6 +771,7 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     BRT_CUDA(cudaEventCreateWithFlags(&c->ev_acc[1], cudaEventDisableTiming));
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count));
+    if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
   });
   if (rc != BRT_OK) {
     g_create_error = c->err;
