@@ -292,28 +292,28 @@ __device__ __forceinline__ void warp_optimize_treelet(const TreeletParams& p, ui
     }
     __syncwarp();
   }
-  // 5. subsets of 6 and 7 leaves: the 31 / 63 partitions of each subset are spread over the lanes
-  for (int size = 6; size <= 7; ++size) {
-    for (uint32_t s = 1; s < 128u; ++s) {
-      if (__popc(s) != size) continue;
-      const uint32_t low = s & (0u - s), rest = s ^ low;
-      const uint32_t n_part = (1u << (size - 1)) - 1u;
-      float best = INFINITY;
-      uint32_t bq = 0;
-      for (uint32_t k = lane + 1u; k <= n_part; k += 32u) {
-        const uint32_t q = deposit_bits(k, rest);
-        const float c = sh.copt[q] + sh.copt[s ^ q];
-        if (c < best) { best = c; bq = q; }
-      }
-      for (int off = 16; off > 0; off >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-        const uint32_t oq = __shfl_xor_sync(0xffffffffu, bq, off);
-        if (ob < best || (ob == best && oq < bq)) { best = ob; bq = oq; }
-      }
-      if (lane == 0) { sh.copt[s] = BRT_SAH_CI * sh.area[s] + best; sh.popt[s] = (uint8_t)bq; }
+  // 5. subsets of 6 and 7 leaves (127 without one leaf, then 127): the 31 / 63 partitions of each are spread over the lanes
+  for (int idx = 0; idx < 8; ++idx) {
+    const uint32_t s = idx < 7 ? (127u ^ (1u << idx)) : 127u;
+    const int size = idx < 7 ? 6 : 7;
+    const uint32_t low = s & (0u - s), rest = s ^ low;
+    const uint32_t n_part = (1u << (size - 1)) - 1u;
+    float best = INFINITY;
+    uint32_t bq = 0;
+    for (uint32_t k = lane + 1u; k <= n_part; k += 32u) {
+      const uint32_t q = deposit_bits(k, rest);
+      const float c = sh.copt[q] + sh.copt[s ^ q];
+      if (c < best) { best = c; bq = q; }
     }
-    __syncwarp();
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const uint32_t oq = __shfl_xor_sync(0xffffffffu, bq, off);
+      if (ob < best || (ob == best && oq < bq)) { best = ob; bq = oq; }
+    }
+    if (lane == 0) { sh.copt[s] = BRT_SAH_CI * sh.area[s] + best; sh.popt[s] = (uint8_t)bq; }
+    if (idx >= 6) __syncwarp();  // the full set reads all 6-subsets
   }
+  __syncwarp();
   // 6. rewrite (lane 0)
   if (lane == 0) {
     const float old_cost = cost[root];
