@@ -174,6 +174,7 @@ struct brt_context {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // shadow chain (occlusion + accumulate), overlapped with the next round's traversal
   cudaEvent_t ev_shade = nullptr, ev_acc[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};  // build / cull timing
   bool own_stream = false;
   std::string err;
   std::unique_ptr<Builder> builder;
@@ -362,10 +363,7 @@ void refresh_scene_stats(brt_context* c) {
 
 void scene_build(brt_context* c) {
   cudaStream_t s = c->stream;
-  cudaEvent_t e0, e1, e2;
-  BRT_CUDA(cudaEventCreate(&e0));
-  BRT_CUDA(cudaEventCreate(&e1));
-  BRT_CUDA(cudaEventCreate(&e2));
+  cudaEvent_t e0 = c->ev_t[0], e1 = c->ev_t[1], e2 = c->ev_t[2];
   BRT_CUDA(cudaEventRecord(e0, s));
   uint32_t rebuilt = 0;
   for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
@@ -396,9 +394,6 @@ void scene_build(brt_context* c) {
   c->stats.ms_blas_build = ms;
   cudaEventElapsedTime(&ms, e1, e2);
   c->stats.ms_tlas_build = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaEventDestroy(e2);
   c->stats.blas_built = rebuilt;
   if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) throw LimitError("scene_build: BVH deeper than the traversal stack allows");
   c->built = true;
@@ -769,6 +764,7 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     BRT_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
     BRT_CUDA(cudaEventCreateWithFlags(&c->ev_acc[0], cudaEventDisableTiming));
     BRT_CUDA(cudaEventCreateWithFlags(&c->ev_acc[1], cudaEventDisableTiming));
+    for (int k = 0; k < 3; ++k) BRT_CUDA(cudaEventCreate(&c->ev_t[k]));
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count));
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
@@ -796,6 +792,8 @@ void brt_destroy(brt_context* c) {
   if (c->ev_shade) cudaEventDestroy(c->ev_shade);
   for (int k = 0; k < 2; ++k)
     if (c->ev_acc[k]) cudaEventDestroy(c->ev_acc[k]);
+  for (int k = 0; k < 3; ++k)
+    if (c->ev_t[k]) cudaEventDestroy(c->ev_t[k]);
   delete c;
 }
 
@@ -970,10 +968,7 @@ int brt_smart_cull(brt_context* c, const brt_uniform* u, uint32_t width, uint32_
     if (c->tables_dirty) build_tables(c);
     cudaStream_t s = c->stream;
     const uint32_t n = (uint32_t)c->instances.size();
-    cudaEvent_t e0, e1, e2;
-    BRT_CUDA(cudaEventCreate(&e0));
-    BRT_CUDA(cudaEventCreate(&e1));
-    BRT_CUDA(cudaEventCreate(&e2));
+    cudaEvent_t e0 = c->ev_t[0], e1 = c->ev_t[1], e2 = c->ev_t[2];
     BRT_CUDA(cudaEventRecord(e0, s));
     if (n) {
       upload(s, c->d_visible, c->visible.data(), n);
@@ -1004,9 +999,6 @@ int brt_smart_cull(brt_context* c, const brt_uniform* u, uint32_t width, uint32_
     c->stats.ms_cull = ms;
     cudaEventElapsedTime(&ms, e1, e2);
     c->stats.ms_tlas_build = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
     if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) throw LimitError("smart_cull: BVH deeper than the traversal stack allows");
     refresh_scene_stats(c);
     if (visible_count) {

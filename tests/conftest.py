@@ -34,6 +34,8 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def pkg():
+    """The product package; lib/libbrt.so is (re)built by its Makefile when sources are newer (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "hardware-ray-tracer_b200", "csrc")])
     return importlib.import_module("hardware-ray-tracer_b200")
 
 

@@ -221,3 +221,49 @@ def error_behaviour(pkg, make):
         a.render_frame(u, a.opts(4, 4))
     with pytest.raises(pkg.BrtError):
         a.sphere_create((0, 0, 0), -1.0)
+
+
+def general_transforms_and_many_lights(pkg, orc_mod, make):
+    """Instances with rotation, non-uniform and mirrored (negative) scale — the C ABI takes any affine 3x4, beyond the
+    scale + translate of RT/MeshInstance.h:82-85 — plus BRT_MAX_LIGHTS lights, a degenerate (zero-area) triangle and clear-coat /
+    sheen / anisotropic / subsurface material fields."""
+    S = pkg.scenes
+    sv, si = S.icosphere(2)
+    quad_v, quad_i = S._quad((-4, 1, -4), (4, 1, -4), (4, 1, 4), (-4, 1, 4))
+    deg = np.zeros((3, 8), np.float32)
+    deg[:, 0:3] = [(0, 0, 0), (1, 0, 0), (2, 0, 0)]  # collinear
+    deg[:, 3:6] = (0, -1, 0)
+    a, b = make(), orc_mod.Oracle(pkg)
+    rng = np.random.default_rng(42)
+    for api in (a, b):
+        ms = api.mesh_create(sv, si)
+        mq = api.mesh_create(quad_v, quad_i)
+        md = api.mesh_create(deg, [0, 1, 2])
+        mats = [api.material_create((0.8, 0.7, 0.6), metallic=0.2, roughness=0.6, clearCoat=1.0, clearCoatGloss=0.7, sheenTint=0.5),
+                api.material_create((0.3, 0.6, 0.9), metallic=0.9, roughness=0.35, anisotropic=0.8, specularTint=0.6),
+                api.material_create((0.9, 0.9, 0.9), metallic=0.0, roughness=0.9, subsurface=0.7, sheen=1.0)]
+        for k in range(16):
+            ang = 2 * np.pi * k / 16
+            api.light_create((3 * np.cos(ang), -2.5, 3 * np.sin(ang)), (0.3 + 0.7 * (k % 3 == 0), 0.3 + 0.7 * (k % 3 == 1), 0.3 + 0.7 * (k % 3 == 2)), 1.5)
+        api.instance_create(mq, mats[2], S.xform())
+        api.instance_create(md, mats[0], S.xform(translate=(0, 0.5, 0)))
+    r2 = np.random.default_rng(7)
+    for k in range(12):
+        ax = r2.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        ang = r2.uniform(0, 2 * np.pi)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        Rm = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        sc = np.diag(r2.uniform(0.3, 0.9, size=3) * np.where(r2.random(3) < 0.25, -1.0, 1.0))
+        x = np.zeros((3, 4), np.float32)
+        x[:, :3] = (Rm @ sc).astype(np.float32)
+        x[:, 3] = (r2.uniform(-2.5, 2.5), r2.uniform(-0.8, 0.6), r2.uniform(-2.0, 2.5))
+        for api in (a, b):
+            api.instance_create(0, k % 3, x)
+    for api in (a, b):
+        api.scene_build()
+    u = a.camera_uniform((0.3, -1.2, -5.0), (-0.2, 0.05, 0.1), 1.0, 1.5, frame=2, depth_max=4)
+    r = compare_frames(pkg, a, b, u, 144, 96, R | D | J, 2)
+    assert r["id_agreement"] == 1.0 and r["bit_exact"] and r["t_agreement"] == 1.0
+    assert r["stats"].rays_occlusion > 16 * 1000
+    return r

@@ -52,6 +52,10 @@ def test_error_behaviour(pkg, make):
     pc.error_behaviour(pkg, make)
 
 
+def test_general_transforms_and_many_lights(pkg, orc_mod, make):
+    pc.general_transforms_and_many_lights(pkg, orc_mod, make)
+
+
 def test_counters_match_plain_run(pkg, make):
     """The instrumented kernels (BRT_CFG_COUNTERS) produce the same image as the plain ones."""
     scene = pkg.scenes.make_scene("terrain", small=True)
