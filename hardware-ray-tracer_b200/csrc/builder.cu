@@ -8,6 +8,11 @@
 #include "radix_sort.cuh"
 #include "treelet.cuh"
 
+#ifndef BRT_TRI_LEAF
+#define BRT_TRI_LEAF 1  // triangles per leaf slot (at most 3: the slot metadata stores the count in unary). Measured on B200:
+                        // 1 is 3-4 % faster than 3 (a primitive test runs with ~5 active lanes, a node test with ~27)
+#endif
+
 namespace brt {
 
 BRT_KERNEL_1D(k_tri_bounds, TriBoundsParams, tri_bounds_body)
@@ -217,7 +222,7 @@ void Builder::build_triangles(cudaStream_t stream, const float* d_vertices, cons
   TriBoundsParams p{n_tris, nullptr, d_vertices, d_indices, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g};
   BRT_LAUNCH_1D(k_tri_bounds, p, grid_n, 256, stream);
   BRT_CHECK_LAUNCH();
-  run(stream, n_tris, 3, treelets, out_nodes, d_vertices, d_indices, out_tris, nullptr, nullptr, d_mesh_bounds, res);
+  run(stream, n_tris, BRT_TRI_LEAF, treelets, out_nodes, d_vertices, d_indices, out_tris, nullptr, nullptr, d_mesh_bounds, res);
 }
 
 void Builder::build_instances(cudaStream_t stream, const InstShade* d_shade, const uint32_t* d_inst_ids, const InstRec* d_src, uint32_t n,
