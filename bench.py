@@ -198,7 +198,14 @@ def run_product(args):
     u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
     opts = ctx.opts(w, h, spp, flags)
 
-    frame = pkg.TiledFrame(ctx, w, h, rank, world, dev)  # per-rank tile buffer, gather buffer, full frame
+    exchange = args.exchange if world > 1 else "none"
+    try:
+        frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode=args.exchange)  # per-rank buffers + the exchange step
+    except Exception as e:  # peer memory not available on this box: NCCL all-gather + un-tile
+        if args.exchange != "p2p":
+            raise
+        exchange = f"nccl (p2p unavailable: {type(e).__name__})"
+        frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="nccl")
     host_image = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -207,7 +214,7 @@ def run_product(args):
         if world == 1:
             ctx.render_frame_tiles(u, opts, frame.tiles.data_ptr())
         else:
-            frame.render(u, opts)  # trace own tiles, NCCL all-gather, un-tile
+            frame.render(u, opts)  # trace own tiles + exchange (fused peer stores, or NCCL all-gather + un-tile)
 
     def step_e2e():
         """the call a user makes: host uniform in, host framebuffer out"""
@@ -216,7 +223,7 @@ def run_product(args):
         else:
             frame.render(u, opts)
             if rank == 0:
-                host_image.copy_(frame.image, non_blocking=True)
+                frame.to_host(host_image)
             stream.synchronize()
 
     def sync_all():
@@ -345,7 +352,7 @@ def run_product(args):
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(scene, cfg, args),
+            "config": dict(bench_config(scene, cfg, args), exchange=exchange),
             "rays_per_step": int(rays),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 140 + 32,
                     "d2h_bytes_per_step": w * h * 16},
@@ -396,6 +403,9 @@ def main():
                     help="BASELINE config; default: c2 (1080p, the single-GPU headline) at N=1, c3 (4K, 16 spp, 4-bounce GI: the "
                          "configuration BASELINE.json quotes for 1/2/4/8 GPUs) at N>1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: framebuffer exchange — p2p = resolve kernel stores into every rank's frame through NVLink peer memory "
+                         "(fused, default); nccl = all-gather of packed tiles + un-tile kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.config is None:

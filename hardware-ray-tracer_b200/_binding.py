@@ -74,7 +74,8 @@ BRT_SYMBOLS = [
     "brt_instance_create", "brt_instance_set_transform", "brt_instance_set_material", "brt_instance_destroy",
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
-    "brt_camera_uniform", "brt_debug_sort_pairs",
+    "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
+    "brt_render_frame_peers", "brt_gather_image",
 ]
 
 
@@ -136,6 +137,10 @@ class SceneApi:
             "tile_buffer_bytes": (C.c_size_t, [u32, u32, u32]),
             "untile": (C.c_int, [vp, vp, u32, u32, u32, vp]),
             "device_image": (vp, [vp]),
+            "gather_image_export": (C.c_int, [vp, u32, u32, vp]),
+            "gather_image_open": (C.c_int, [vp, vp, u32]),
+            "render_frame_peers": (C.c_int, [vp, P(Uniform), P(RenderOpts)]),
+            "gather_image": (vp, [vp]),
         }
         sig.update({k: v for k, v in device_side.items() if hasattr(self.lib, self.prefix + k)})
         sig.update(self._extra)
@@ -295,3 +300,19 @@ class SceneApi:
 
     def device_image(self):
         return self._f("device_image")(self.ctx)
+
+    # fused resolve + exchange over peer memory
+    def gather_image_export(self, width, height):
+        h = C.create_string_buffer(64)
+        self._ck(self._f("gather_image_export")(self.ctx, width, height, h))
+        return h.raw
+
+    def gather_image_open(self, handles):
+        blob = b"".join(handles)
+        self._ck(self._f("gather_image_open")(self.ctx, C.c_char_p(blob), len(handles)))
+
+    def render_frame_peers(self, uniform, opts):
+        self._ck(self._f("render_frame_peers")(self.ctx, C.byref(uniform), C.byref(opts)))
+
+    def gather_image(self):
+        return self._f("gather_image")(self.ctx)

@@ -206,6 +206,11 @@ struct brt_context {
   DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
   DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
+  // fused resolve + exchange: own gather image and the peers' (opened through cudaIpc)
+  DevBuf d_gather;
+  uint32_t gather_w = 0, gather_h = 0, n_peers = 0;
+  void* peer_images[BRT_MAX_PEERS] = {nullptr};
+  bool peer_opened[BRT_MAX_PEERS] = {false};
   std::deque<EventPair> events;  // deque: references stay valid while the pool grows
   size_t events_used = 0;
   brt_stats stats{};
@@ -497,7 +502,7 @@ void launch_trace(brt_context* c, const TraceParams& p, cudaStream_t stream) {
 // round k+1). The buffers the shadow chain owns (contributions, weights/pixels, shadow queue, counters) are
 // double-buffered by round parity; shade(k+2) waits for accumulate(k). Accumulation stays in round order on one stream,
 // so the result is bit-identical to the serial schedule (BRT_CFG_NO_OVERLAP, used for per-kernel timing).
-void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_opts& o, void* d_tiles_out) {
+void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_opts& o, void* d_tiles_out, bool to_peers = false) {
   if (!c->built) bad_state("render_frame: scene not built (call brt_scene_build)");
   if (!o.width || !o.height || !o.spp) invalid("render_frame: width, height and spp must be non-zero");
   if (c->lights.size() > BRT_MAX_LIGHTS) throw LimitError("render_frame: more than BRT_MAX_LIGHTS lights");
@@ -696,6 +701,13 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
     rp.accum = c->d_accum.as<float4>();
     rp.image = c->d_image.as<float4>();
     rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : c->d_tiles.as<float4>();
+    rp.n_peers = 0;
+    if (to_peers) {
+      if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
+      rp.tiles = nullptr;
+      rp.n_peers = c->n_peers;
+      for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]);
+    }
     Timed t(c, CLS_RESOLVE, s);
     BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
     BRT_CHECK_LAUNCH();
@@ -706,6 +718,17 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
   c->stats.launches_trace_closest = l_closest;
   c->stats.launches_trace_occlusion = l_occl;
 }
+
+#ifndef BRT_EMU
+void close_peers(brt_context* c) {
+  for (uint32_t k = 0; k < BRT_MAX_PEERS; ++k) {
+    if (c->peer_opened[k]) cudaIpcCloseMemHandle(c->peer_images[k]);
+    c->peer_opened[k] = false;
+    c->peer_images[k] = nullptr;
+  }
+  c->n_peers = 0;
+}
+#endif
 
 // waits for the frame and folds the device-side statistics / event timings into ctx->stats
 void finish_frame(brt_context* c) {
@@ -783,6 +806,9 @@ void brt_destroy(brt_context* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->stream2) cudaStreamSynchronize(c->stream2);
+#ifndef BRT_EMU
+  close_peers(c);
+#endif
   for (EventPair& e : c->events) {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
@@ -1064,6 +1090,65 @@ int brt_untile(brt_context* c, const void* d_all, uint32_t width, uint32_t heigh
 }
 
 void* brt_device_image(brt_context* c) { return c ? c->d_image.ptr() : nullptr; }
+
+int brt_gather_image_export(brt_context* c, uint32_t width, uint32_t height, void* handle_out) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!width || !height || !handle_out) invalid("gather_image_export: bad arguments");
+#ifdef BRT_EMU
+    bad_state("gather_image_export: peer memory needs CUDA devices");
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == BRT_IPC_HANDLE_BYTES, "ipc handle size");
+    BRT_CUDA(cudaSetDevice(c->device));
+    close_peers(c);
+    c->d_gather.release();  // a fresh allocation: an exported handle stays tied to its allocation
+    c->d_gather.ensure((size_t)width * height * 16);
+    BRT_CUDA(cudaMemset(c->d_gather.ptr(), 0, (size_t)width * height * 16));
+    cudaIpcMemHandle_t h;
+    BRT_CUDA(cudaIpcGetMemHandle(&h, c->d_gather.ptr()));
+    std::memcpy(handle_out, &h, sizeof(h));
+    c->gather_w = width;
+    c->gather_h = height;
+#endif
+  });
+}
+
+int brt_gather_image_open(brt_context* c, const void* handles, uint32_t world) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!handles || world != c->tile_world || world > BRT_MAX_PEERS) invalid("gather_image_open: world must equal tile_world (<= 16)");
+#ifdef BRT_EMU
+    bad_state("gather_image_open: peer memory needs CUDA devices");
+#else
+    if (!c->gather_w) bad_state("gather_image_open: call brt_gather_image_export first");
+    BRT_CUDA(cudaSetDevice(c->device));
+    close_peers(c);
+    for (uint32_t k = 0; k < world; ++k) {
+      if (k == c->tile_rank) {
+        c->peer_images[k] = c->d_gather.ptr();
+      } else {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + (size_t)k * BRT_IPC_HANDLE_BYTES, sizeof(h));
+        BRT_CUDA(cudaIpcOpenMemHandle(&c->peer_images[k], h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened[k] = true;
+      }
+    }
+    c->n_peers = world;
+#endif
+  });
+}
+
+int brt_render_frame_peers(brt_context* c, const brt_uniform* u, const brt_render_opts* o) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!u || !o) invalid("render_frame_peers: null");
+    BRT_CUDA(cudaSetDevice(c->device));
+    render_frame_device(c, *u, *o, nullptr, true);
+    finish_frame(c);
+  });
+}
+
+void* brt_gather_image(brt_context* c) { return c ? c->d_gather.ptr() : nullptr; }
 
 int brt_get_aov(brt_context* c, int kind, void* out) {
   if (!c) return BRT_ERR_INVALID;

@@ -44,6 +44,7 @@ struct TileMap {
   uint32_t tile_rank, tile_world;
   uint32_t crop_x0, crop_y0, crop_x1, crop_y1;  // traced window [x0,x1) x [y0,y1)
 };
+#define BRT_MAX_PEERS 16
 #define BRT_SLOT_BITS 26
 #define BRT_SLOT_MASK 0x03ffffffu
 #define BRT_MAX_SAMPLE_BATCH 63u  // sample-in-batch must stay below 63 so that an id never equals BRT_MISS
@@ -439,6 +440,8 @@ struct ResolveParams {
   const float4* accum;  // per slot
   float4* image;   // full frame, row major
   float4* tiles;   // this rank's tiles packed tile-major, row-major inside a tile (may be null)
+  float4* peers[BRT_MAX_PEERS];  // fused exchange: every rank's gather image (peer memory over NVLink), n_peers of them
+  uint32_t n_peers;
 };
 BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
   // unlike the path slots this walks the tile row by row so that both stores coalesce
@@ -454,6 +457,8 @@ BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
   }
   if (inside) p.image[(size_t)y * p.map.width + x] = out;
   if (p.tiles) p.tiles[i] = out;
+  if (inside)
+    for (uint32_t k = 0; k < p.n_peers; ++k) p.peers[k][(size_t)y * p.map.width + x] = out;  // st.global to mapped peer pointers
 }
 
 // ---- un-tile after the framebuffer gather (root rank) ----------------------------------------------------

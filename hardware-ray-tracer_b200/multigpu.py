@@ -6,7 +6,15 @@ tile_id % world == rank and packs them tile-major. One collective per frame — 
 equal-sized packed tile buffers (NCCL over NVLink on GPUs; gloo in the CPU tests) — then the un-tile
 kernel rebuilds the row-major RGBA32F frame on every rank. Smart-Culling results and the BVH are identical
 on every rank by construction (same inputs, deterministic builder), so nothing else is exchanged.
+
+Two exchange modes:
+  "nccl"  brt_render_frame_tiles -> all_gather_into_tensor (NCCL over NVLink; gloo in the CPU tests) -> brt_untile
+  "p2p"   brt_render_frame_peers: the resolve kernel itself stores every owned pixel into all ranks' gather images through
+          cudaIpc-mapped peer memory (NVLink stores inside the producing kernel), then one barrier. No collective moves
+          pixels, no un-tile pass.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -14,8 +22,16 @@ import torch.distributed as dist
 class TiledFrame:
     """Per-rank buffers + the gather / un-tile step for frames of one size."""
 
-    def __init__(self, ctx, width, height, rank, world, device, group=None):
+    def __init__(self, ctx, width, height, rank, world, device, group=None, mode="nccl"):
         self.ctx, self.width, self.height, self.rank, self.world, self.group = ctx, width, height, rank, world, group
+        self.mode = mode if world > 1 else "nccl"
+        if self.mode == "p2p":
+            mine = ctx.gather_image_export(width, height)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine, group=group)
+            ctx.gather_image_open(handles)
+            dist.barrier(group=group)
+            self._barrier_token = torch.zeros(1, dtype=torch.int32, device=device)
         n = ctx.tile_buffer_bytes(width, height, world) // 4
         self.tiles = torch.zeros(n, dtype=torch.float32, device=device)
         self.gathered = torch.zeros(n * world, dtype=torch.float32, device=device) if world > 1 else self.tiles
@@ -24,8 +40,29 @@ class TiledFrame:
     def render(self, uniform, opts):
         """Traces this rank's tiles, gathers everybody's, returns the full (H, W, 4) frame (a view of self.image)."""
         assert opts.width == self.width and opts.height == self.height
+        if self.mode == "p2p":
+            self.ctx.render_frame_peers(uniform, opts)               # returns when this rank's peer stores have landed
+            dist.all_reduce(self._barrier_token, group=self.group)  # barrier: everybody's have
+            torch.cuda.current_stream().synchronize()
+            return None  # the frame is brt_gather_image(ctx) (device memory owned by the library); see frame_ptr()
         self.ctx.render_frame_tiles(uniform, opts, self.tiles.data_ptr())
         if self.world > 1:
             dist.all_gather_into_tensor(self.gathered, self.tiles, group=self.group)
         self.ctx.untile(self.gathered.data_ptr(), self.width, self.height, self.world, self.image.data_ptr())
         return self.image.view(self.height, self.width, 4)
+
+    def frame_ptr(self):
+        """Device pointer of the complete row-major RGBA32F frame of the last render()."""
+        return self.ctx.gather_image() if self.mode == "p2p" else self.image.data_ptr()
+
+    def to_host(self, host):
+        """Copies the complete frame of the last render() into `host` (a pinned float32 tensor of h*w*4 elements)."""
+        if self.mode == "p2p":
+            rt = ctypes.CDLL("libcudart.so")
+            rc = rt.cudaMemcpy(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(self.ctx.gather_image()),
+                               ctypes.c_size_t(self.height * self.width * 16), 2)  # cudaMemcpyDeviceToHost
+            if rc != 0:
+                raise RuntimeError(f"cudaMemcpy failed: {rc}")
+        else:
+            host.copy_(self.image, non_blocking=True)
+            torch.cuda.current_stream().synchronize()

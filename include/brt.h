@@ -220,6 +220,19 @@ BRT_API size_t brt_tile_buffer_bytes(uint32_t width, uint32_t height, uint32_t t
 /* after the gather: d_all = tile_world packed buffers back to back (device) -> row-major RGBA32F
  * image at d_rgba (device). */
 BRT_API int brt_untile(brt_context* ctx, const void* d_all, uint32_t width, uint32_t height, uint32_t tile_world, void* d_rgba);
+/* ---- fused resolve + framebuffer exchange over NVLink peer memory -------------------------------------
+ * Alternative to brt_render_frame_tiles + NCCL all-gather + brt_untile for the ranks of one box: every rank exports its
+ * full-frame "gather image" (cudaIpc handle), opens everybody else's, and the resolve kernel of brt_render_frame_peers
+ * stores each pixel this rank owns straight into ALL ranks' gather images (row-major RGBA32F, the final layout) with
+ * peer stores — the exchange happens inside the producing kernel, no collective, no un-tile pass. After the call returns
+ * this rank's stores have landed; a barrier among the ranks (any kind) makes every gather image complete, and another one
+ * is needed before the next frame overwrites it. */
+#define BRT_IPC_HANDLE_BYTES 64
+BRT_API int brt_gather_image_export(brt_context* ctx, uint32_t width, uint32_t height, void* handle_out);
+/* handles: tile_world x BRT_IPC_HANDLE_BYTES, in rank order (this rank's own entry is ignored) */
+BRT_API int brt_gather_image_open(brt_context* ctx, const void* handles, uint32_t world);
+BRT_API int brt_render_frame_peers(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts);
+BRT_API void* brt_gather_image(brt_context* ctx);
 /* device pointer of the context's own full-frame RGBA32F image of the last frame */
 BRT_API void* brt_device_image(brt_context* ctx);
 
