@@ -238,7 +238,7 @@ struct CollapseParams {
   const uint32_t* count_ptr;  // = &g->level_count[level]
   uint32_t level;
   uint32_t n;                 // primitives
-  uint32_t max_leaf;          // 3 for triangles, 1 for instances
+  uint32_t max_leaf;          // primitives per leaf slot: 1 (the node format has one leaf bit per slot)
   const BNode* nodes;
   const uint32_t* sub_count;
   const uint2* queue_in;      // (binary node id, wide node index)
@@ -386,20 +386,20 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
   // grid
   const uint32_t ex = grid_exponent(nlo.x, nhi.x), ey = grid_exponent(nlo.y, nhi.y), ez = grid_exponent(nlo.z, nhi.z);
   const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
-  uint32_t meta[8], qlx[8], qly[8], qlz[8], qhx[8], qhy[8], qhz[8];
-  uint32_t imask = 0, inner_i = 0, prim_off = 0;
+  uint32_t qlx[8], qly[8], qlz[8], qhx[8], qhy[8], qhz[8];
+  uint32_t imask = 0, leafmask = 0, inner_i = 0, prim_off = 0;
   for (int s = 0; s < 8; ++s) {
-    meta[s] = 0; qlx[s] = qly[s] = qlz[s] = 255u; qhx[s] = qhy[s] = qhz[s] = 0u;
+    qlx[s] = qly[s] = qlz[s] = 255u; qhx[s] = qhy[s] = qhz[s] = 0u;
     const int k = child_in[s];
     if (k < 0) continue;
     if (area[k] >= 0.0f) {
       if (n_inner == 0) continue;  // overflow: slot left empty
       imask |= 1u << s;
-      meta[s] = (1u << 5) | (24u + (uint32_t)s);
       p.queue_out[queue_base + inner_i] = make_uint2(ch[k], child_base + inner_i);
       inner_i++;
     } else {
-      // enumerate the (<= max_leaf) primitives of this small subtree
+      // a leaf slot holds exactly one primitive (max_leaf == 1): its record index is prim_base + the rank of
+      // the slot among the node's leaf slots; the walk below tolerates a larger subtree only to stay in bounds
       const uint32_t cnt = p.sub_count[ch[k]];
       uint32_t st[4];
       int sp = 0;
@@ -416,7 +416,7 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
           st[sp++] = f2u(bn.lo.w);
         }
       }
-      meta[s] = (((1u << cnt) - 1u) << 5) | prim_off;
+      leafmask |= 1u << s;
       prim_off += cnt;
     }
     qlx[s] = quant_lo(nlo.x, sx, clo[k].x); qly[s] = quant_lo(nlo.y, sy, clo[k].y); qlz[s] = quant_lo(nlo.z, sz, clo[k].z);
@@ -425,7 +425,15 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
   auto pack4 = [](const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
   Node8 out;
   out.q[0] = make_uint4(f2u(nlo.x), f2u(nlo.y), f2u(nlo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
-  out.q[1] = make_uint4(child_base, prim_base, pack4(meta), pack4(meta + 4));
+  // byte x of q1.z / q1.w = inner / leaf mask with the two low bits of every slot index XORed with x: the traversal
+  // selects the byte for its ray octant instead of permuting bits (traverse.cuh)
+  uint32_t iperm = 0, lperm = 0;
+  for (uint32_t x = 0; x < 4; ++x)
+    for (uint32_t j = 0; j < 8; ++j) {
+      iperm |= ((imask >> (j ^ x)) & 1u) << (8 * x + j);
+      lperm |= ((leafmask >> (j ^ x)) & 1u) << (8 * x + j);
+    }
+  out.q[1] = make_uint4(child_base, prim_base, iperm, lperm);
   out.q[2] = make_uint4(pack4(qlx), pack4(qlx + 4), pack4(qly), pack4(qly + 4));
   out.q[3] = make_uint4(pack4(qlz), pack4(qlz + 4), pack4(qhx), pack4(qhx + 4));
   out.q[4] = make_uint4(pack4(qhy), pack4(qhy + 4), pack4(qhz), pack4(qhz + 4));

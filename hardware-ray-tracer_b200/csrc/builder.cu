@@ -8,10 +8,10 @@
 #include "radix_sort.cuh"
 #include "treelet.cuh"
 
-#ifndef BRT_TRI_LEAF
-#define BRT_TRI_LEAF 1  // triangles per leaf slot (at most 3: the slot metadata stores the count in unary). Measured on B200:
-                        // 1 is 3-4 % faster than 3 (a primitive test runs with ~5 active lanes, a node test with ~27)
-#endif
+// One primitive per leaf slot: a node addresses its primitives as prim_base + rank of the slot among its leaf slots.
+// (Leaves of up to 3 triangles were measured 3-4 % slower on B200: a primitive test runs with ~5 active lanes, a node
+// test with ~27, so trading node tests for primitive tests loses.)
+#define BRT_TRI_LEAF 1
 
 namespace brt {
 

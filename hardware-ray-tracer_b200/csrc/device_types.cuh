@@ -10,9 +10,10 @@ namespace brt {
 //  q0: p.x, p.y, p.z (float, origin of the local grid), [ex | ey<<8 | ez<<16 | imask<<24]
 //      e* = biased binary32 exponent of the per-axis grid step, imask = slots holding inner nodes
 //  q1: child_base (index of the first inner child, children are contiguous in slot order),
-//      prim_base  (index of the first primitive record of this node's leaf slots),
-//      meta[0..3], meta[4..7]  — per slot: 0 empty | 001 11sss inner (sss = slot)
-//                                           | ccc ooooo leaf (ccc = unary count 001/011/111, ooooo = first primitive offset < 24)
+//      prim_base  (index of the first primitive record; a leaf slot holds ONE primitive, record index =
+//                  prim_base + number of leaf slots below it),
+//      iperm, lperm — byte x (x = 0..3) = the inner / leaf slot mask with bit j taken from slot j ^ x, i.e. the
+//                  mask in the order a ray with (7 - octant) & 3 == x visits the slots of each half
 //  q2: qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7]
 //  q3: qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7]
 //  q4: qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7]

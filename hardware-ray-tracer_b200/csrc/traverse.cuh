@@ -4,7 +4,7 @@
 // Algorithm: stack of 8-byte "groups" after Ylitie, Karras & Laine (HPG 2017). A node group is
 // (child_base, hits<<24 | imask): the not-yet-visited inner children of one node, visited in
 // descending bit order, which the octant trick turns into front-to-back order. A leaf group is
-// (prim_base, 24-bit mask) of primitives whose slot box the ray hit. TLAS leaves are instances: the
+// (prim_base, hit bits | leaf slot mask << 8): the leaf slots (one primitive each) whose box the ray hit. TLAS leaves are instances: the
 // ray is transformed to object space (t is preserved, the direction is not renormalised) and the
 // BLAS is traversed on the same stack; when the stack drops back to the entry level the world ray
 // is restored.
@@ -40,31 +40,31 @@ BRT_HD RayBox make_raybox(f3 d) {
   return rb;
 }
 
-BRT_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
+// PRMT: result byte i = byte (nibble i of sel) of the 8-byte pool {a: 0..3, b: 4..7}
+BRT_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef BRT_EMU
+  const uint64_t pool = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+  return r;
+#else
+  return __byte_perm(a, b, sel);
+#endif
+}
 
-// byte i of w -> the float 32768 + byte, built with ONE byte permute: 0x47000000 is 2^15 and byte 1 of
-// a binary32 with that exponent has weight 1. (An I2F.U8 conversion would run on the quarter-rate XU
-// pipe; ncu showed it as the busiest pipe of the first version of this kernel.)
-template <int I>
-BRT_HD float magic_byte(uint32_t w, uint32_t magic /* 0x47000000, held in a register */) {
-#ifdef BRT_EMU
-  return u2f(magic | (((w >> (8 * I)) & 0xffu) << 8));
-#else
-  return __uint_as_float(__byte_perm(w, magic, 0x7604u | (I << 4)));
-#endif
-}
-BRT_HD uint32_t magic_register() {
-#ifdef BRT_EMU
-  return 0x47000000u;
-#else
-  uint32_t m;  // opaque to the compiler: otherwise it folds the constant into the PRMT and spends a MOV per
-  asm("mov.b32 %0, 0x47000000;" : "=r"(m));  // permute on materialising the selector instead
-  return m;
-#endif
-}
+// One byte of w -> the float 32768 + byte with ONE byte permute: 0x47000000 is 2^15 and byte 1 of a binary32 with that
+// exponent has weight 1. (An I2F.U8 conversion would run on the quarter-rate XU pipe; ncu showed it as the busiest
+// pipe of the first version of this kernel.) sel = 0x7604 | (byte index << 4); the byte index is per-ray data, see below.
+BRT_HD float magic_byte(uint32_t w, uint32_t sel) { return u2f(byte_perm(w, 0x47000000u, sel)); }
 
 // Tests the ray against the 8 quantised child boxes of one node.
-// out: G = (child_base, inner hits << 24 | imask), Gt = (prim_base, leaf hit bits)
+// out: G  = (child_base, inner hits << 24 | inner slot mask)        hits in visiting order: bit p <-> slot p ^ octinv
+//      Gt = (prim_base, leaf hits | leaf slot mask << 8)            (descending p = front to back)
+//
+// Front-to-back order is "descending slot ^ octinv". The XOR is applied to the DATA instead of to the result bits:
+// the two low bits of octinv pick which byte of each 4-slot word a PRMT converts (a per-ray selector, no extra
+// instruction), the node stores its slot masks pre-permuted for the four possible values (iperm / lperm), and bit 2
+// swaps the two 4-slot halves of the result. The eight comparisons then land on constant bit positions.
 BRT_HD void intersect_node(const Node8* __restrict__ node, const RayBox& rb, f3 o, float tmin, float tmax, uint2& G, uint2& Gt) {
   const uint4 n0 = ldg4(&node->q[0]);
   const uint4 n1 = ldg4(&node->q[1]);
@@ -89,36 +89,33 @@ BRT_HD void intersect_node(const Node8* __restrict__ node, const RayBox& rb, f3 
   const float oy0 = fma_rn(-32768.0f, idy, oy - ey), oy1 = fma_rn(-32768.0f, idy, oy + ey);
   const float oz0 = fma_rn(-32768.0f, idz, oz - ez), oz1 = fma_rn(-32768.0f, idz, oz + ez);
   const bool nx = rb.idir.x < 0.0f, ny = rb.idir.y < 0.0f, nz = rb.idir.z < 0.0f;
-  const uint32_t octinv4 = rb.octinv * 0x01010101u;
-  const uint32_t mg = magic_register();
-  uint32_t hitmask = 0;
+  const uint32_t x = rb.octinv & 3u;
+  const uint32_t sel0 = 0x7604u | (x << 4), sel1 = sel0 ^ 0x10u, sel2 = sel0 ^ 0x20u, sel3 = sel0 ^ 0x30u;
+  uint32_t hits = 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const uint32_t meta4 = h ? n1.w : n1.z;
-    // four slots at a time: inner slots (low 5 bits = 11sss) get their bit index XORed with octinv
-    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
-    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     const uint32_t lox4 = h ? n2.y : n2.x, loy4 = h ? n2.w : n2.z, loz4 = h ? n3.y : n3.x;
     const uint32_t hix4 = h ? n3.w : n3.z, hiy4 = h ? n4.y : n4.x, hiz4 = h ? n4.w : n4.z;
     const uint32_t nearx4 = nx ? hix4 : lox4, farx4 = nx ? lox4 : hix4;
     const uint32_t neary4 = ny ? hiy4 : loy4, fary4 = ny ? loy4 : hiy4;
     const uint32_t nearz4 = nz ? hiz4 : loz4, farz4 = nz ? loz4 : hiz4;
-#define BRT_SLOT(I)                                                                                                         \
-  {                                                                                                                         \
-    const float t0x = fma_rn(magic_byte<I>(nearx4, mg), idx, ox0), t1x = fma_rn(magic_byte<I>(farx4, mg), idx, ox1);               \
-    const float t0y = fma_rn(magic_byte<I>(neary4, mg), idy, oy0), t1y = fma_rn(magic_byte<I>(fary4, mg), idy, oy1);               \
-    const float t0z = fma_rn(magic_byte<I>(nearz4, mg), idz, oz0), t1z = fma_rn(magic_byte<I>(farz4, mg), idz, oz1);               \
-    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));                                                              \
-    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                                                              \
-    if (tn <= tf) hitmask |= byte_of(child_bits4, I) << byte_of(bit_index4, I); /* empty slot: child bits are 0 */          \
+#define BRT_SLOT(I, SEL)                                                                                              \
+  {                                                                                                                   \
+    const float t0x = fma_rn(magic_byte(nearx4, SEL), idx, ox0), t1x = fma_rn(magic_byte(farx4, SEL), idx, ox1);       \
+    const float t0y = fma_rn(magic_byte(neary4, SEL), idy, oy0), t1y = fma_rn(magic_byte(fary4, SEL), idy, oy1);       \
+    const float t0z = fma_rn(magic_byte(nearz4, SEL), idz, oz0), t1z = fma_rn(magic_byte(farz4, SEL), idz, oz1);       \
+    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));                                                        \
+    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                                                        \
+    if (tn <= tf) hits |= 1u << (4 * h + I);                                                                          \
   }
-    BRT_SLOT(0) BRT_SLOT(1) BRT_SLOT(2) BRT_SLOT(3)
+    BRT_SLOT(0, sel0) BRT_SLOT(1, sel1) BRT_SLOT(2, sel2) BRT_SLOT(3, sel3)
 #undef BRT_SLOT
   }
-  G = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-  Gt = make_uint2(n1.y, hitmask & 0x00ffffffu);
+  // byte 0: inner hits, byte 1: leaf hits (empty slots are in neither mask)
+  uint32_t v = (hits * 0x0101u) & byte_perm(n1.z, n1.w, 0x40u | (x * 0x11u));
+  if (rb.octinv & 4u) v = ((v & 0x0f0fu) << 4) | ((v >> 4) & 0x0f0fu);
+  G = make_uint2(n1.x, (v << 24) | (n0.w >> 24));
+  Gt = make_uint2(n1.y, (v >> 8) | ((n1.w & 0xffu) << 8));
 }
 
 // One ray's traversal as a resumable state machine: init(), then step() until it returns true.
@@ -184,11 +181,13 @@ struct Traversal {
       G = make_uint2(0u, 0u);
     }
 
-    while (Gt.y) {
+    while (Gt.y & 0xffu) {
+      // hit bit p <-> slot p ^ octinv; a leaf slot's record is prim_base + its rank among the node's leaf slots
+      const uint32_t slot = (uint32_t)(ffs32(Gt.y) - 1) ^ rb.octinv;
+      Gt.y &= Gt.y - 1u;
+      const uint32_t rank = (uint32_t)popc((Gt.y >> 8) & ~(0xffffffffu << slot));
       if (blas_sp >= 0) {
-        const int bit = ffs32(Gt.y) - 1;
-        Gt.y &= Gt.y - 1u;
-        const TriRec* tr = tris + Gt.x + bit;
+        const TriRec* tr = tris + Gt.x + rank;
         const float4 a = ldg4(&tr->v0), b = ldg4(&tr->v1), c = ldg4(&tr->v2);
         if (COUNT) ctr.prims++;
         float t, u, v;
@@ -201,9 +200,7 @@ struct Traversal {
           }
         }
       } else {
-        const int bit = ffs32(Gt.y) - 1;
-        Gt.y &= Gt.y - 1u;
-        const InstRec* ir = insts + Gt.x + bit;
+        const InstRec* ir = insts + Gt.x + rank;
         const float4 m0 = ldg4(&ir->w2o[0]), m1 = ldg4(&ir->w2o[1]), m2 = ldg4(&ir->w2o[2]);
         const uint4 tail = ldg4(reinterpret_cast<const uint4*>(&ir->kind));
         const float4 m[3] = {m0, m1, m2};
@@ -221,7 +218,7 @@ struct Traversal {
           }
         } else {
           // enter the BLAS: keep the TLAS continuation on the stack
-          if (Gt.y) stack[sp++] = Gt;
+          if (Gt.y & 0xffu) stack[sp++] = Gt;
           if (G.y & 0xff000000u) stack[sp++] = G;
           blas_sp = sp;
           const uint4 ptrs = ldg4(reinterpret_cast<const uint4*>(&ir->nodes));
