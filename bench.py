@@ -189,6 +189,7 @@ def run_product(args):
     w, h, spp, flags = cfg["width"], cfg["height"], cfg["spp"], cfg["flags"]
 
     ctx = pkg.Context(device=local, tile_rank=rank, tile_world=world)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # a real (non-default) stream for torch work and frame slot 0
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
@@ -208,6 +209,7 @@ def run_product(args):
         frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="nccl")
     host_image = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pipelined = world == 1 and args.frames_in_flight == 2
 
     def step_device():
         """one frame, result left in HBM (un-tiled full frame on every rank)"""
@@ -251,6 +253,47 @@ def run_product(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    def timed_pipelined(to_host, steps, warmup, collect=None):
+        """N = 1 product schedule: two frames in flight (brt_render_frame_async / brt_frame_wait — the reference's
+        MAX_FRAMES_IN_FLIGHT = 2, VK/SwapChain.h:8). K frames are enqueued alternately on the two frame slots; ONE timed
+        region brackets all K steps (synchronize on both sides, CUDA events on the slots' streams). The L2 flush (a write
+        larger than L2) of every step is enqueued on the frame's stream right before the frame, INSIDE the timed region."""
+        streams = [torch.cuda.ExternalStream(ctx.frame_stream(k), device=dev) for k in range(2)]
+        hosts = [host_image, host_image2]
+
+        def submit(i):
+            k = i % 2
+            ctx.frame_wait(k)  # the slot's fence: frame i-2 (and its copy to the host) is complete
+            with torch.cuda.stream(streams[k]):
+                flush_small.fill_(i & 0xff)
+            ctx.render_frame_async(u, opts, k, hosts[k].data_ptr() if to_host else None)
+
+        for i in range(warmup):
+            submit(i)
+        ctx.frame_wait(0)
+        ctx.frame_wait(1)
+        sync_all()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(streams[0])
+        for i in range(steps):
+            submit(i)
+        ends = []
+        for k in range(2):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(streams[k])
+            ends.append(e)
+        ctx.frame_wait(0)
+        ctx.frame_wait(1)
+        torch.cuda.synchronize()
+        if collect is not None:
+            for _ in range(steps):
+                collect(ctx.get_stats())  # every step renders the same frame: same launches, same rays
+        return max(e0.elapsed_time(e) for e in ends) / steps
+
+    if pipelined:
+        host_image2 = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
+        flush_small = torch.empty(160 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
     kstats = {"closest": 0.0, "occl": 0.0, "shade": 0.0, "other": 0.0, "n": 0, "launches": 0, "rays": 0}
 
     def collect(st):
@@ -269,9 +312,17 @@ def run_product(args):
         kstats["rays"] = st.rays_closest + st.rays_occlusion
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev = timed(step_device, args.steps, args.warmup, count_launches)
-    clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    frame_latency = None
+    if pipelined:
+        ms_dev = timed_pipelined(False, args.steps, args.warmup, count_launches)
+        clocks = sampler.stop() if sampler else None
+        ms_e2e = timed_pipelined(True, args.steps, max(2, args.warmup // 2))
+        # one frame alone, nothing else in flight: the latency a single brt_render_frame call sees
+        frame_latency = {"device_ms": timed(step_device, min(args.steps, 5), 1), "e2e_ms": timed(step_e2e, min(args.steps, 5), 1)}
+    else:
+        ms_dev = timed(step_device, args.steps, args.warmup, count_launches)
+        clocks = sampler.stop() if sampler else None
+        ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
     rays_t = torch.tensor([kstats["rays"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -352,8 +403,11 @@ def run_product(args):
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(bench_config(scene, cfg, args), exchange=exchange),
-            "rays_per_step": int(rays),
+            "config": dict(bench_config(scene, cfg, args), exchange=exchange, **(
+                {"frames_in_flight": 2, "l2": "flushed before every frame (160 MiB write enqueued on the frame's stream, inside the timed region)",
+                 "schedule": "K frames alternate over 2 frame slots (brt_render_frame_async / brt_frame_wait, as the reference's "
+                             "MAX_FRAMES_IN_FLIGHT = 2); one timed region around all K steps"} if pipelined else {"frames_in_flight": 1})),
+            "rays_per_step": int(rays), "single_frame_latency": frame_latency,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 140 + 32,
                     "d2h_bytes_per_step": w * h * 16},
             "gpu_launches": int(launches["n"]),
@@ -403,6 +457,9 @@ def main():
                     help="BASELINE config; default: c2 (1080p, the single-GPU headline) at N=1, c3 (4K, 16 spp, 4-bounce GI: the "
                          "configuration BASELINE.json quotes for 1/2/4/8 GPUs) at N>1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
+                    help="N = 1: 2 = frames alternate over two frame slots (default, the reference keeps 2 frames in flight); "
+                         "1 = every step is one synchronous brt_render_frame call")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: framebuffer exchange — p2p = resolve kernel stores into every rank's frame through NVLink peer memory "
                          "(fused, default); nccl = all-gather of packed tiles + un-tile kernel")

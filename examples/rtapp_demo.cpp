@@ -3,7 +3,7 @@
 // RTApp::run — minus window, swapchain and present (no display on a compute box): the frame is written to disk.
 //
 //   g++ -std=c++17 -O2 -Iinclude examples/rtapp_demo.cpp -Lhardware-ray-tracer_b200/lib -lbrt -Wl,-rpath,... -o rtapp_demo
-//   ./rtapp_demo out_prefix [frames]
+//   ./rtapp_demo out_prefix [frames] [async]      (async: two frames in flight, RTApp::beginFrame / endFrame)
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -23,6 +23,7 @@ static void writePlaneObj(const std::string& path) {  // stands in for the missi
 int main(int argc, char** argv) {
   const std::string prefix = argc > 1 ? argv[1] : "rtapp_demo";
   const int frames = argc > 2 ? std::atoi(argv[2]) : 1;
+  const bool async = argc > 3 && std::string(argv[3]) == "async";
   try {
     const uint32_t width = 800, height = 600;  // Window({800, 600, ...}), RT/RTApp.cpp:3
     Core::Device device(0);
@@ -45,9 +46,10 @@ int main(int argc, char** argv) {
       camera.setPerspectiveProjection(1.0471975512f /* glm::radians(60.f) */, (float)width / (float)height, 0.001f, 100000.f);  // :41
       RayTracing::Uniform uniform = camera.uniform(/*frame = imageIndex*/ (uint32_t)frame % 2, /*depthMax*/ 2);  // :44-49
       rtPipeline->writeToUniformBuffer(&uniform, (uint32_t)frame % 2);          // :51
-      rtPipeline->traceRays(width, height, 1);                                  // rayTraceScene -> traceRays, :159-160
+      if (async) rtPipeline->submitFrame((uint32_t)frame % 2, width, height);   // beginFrame (fence of the slot) ... endFrame (submit), :171-212
+      else rtPipeline->traceRays(width, height, 1);                             // rayTraceScene -> traceRays, :159-160
     }
-    const std::vector<float>& img = rtPipeline->getRenderOutput();
+    const std::vector<float>& img = async ? rtPipeline->waitFrame((uint32_t)(frames - 1) % 2) : rtPipeline->getRenderOutput();
     std::ofstream raw(prefix + ".rgba32f", std::ios::binary);
     raw.write(reinterpret_cast<const char*>(img.data()), (std::streamsize)(img.size() * sizeof(float)));
     std::ofstream ppm(prefix + ".ppm", std::ios::binary);

@@ -75,7 +75,7 @@ BRT_SYMBOLS = [
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
-    "brt_render_frame_peers", "brt_gather_image",
+    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream",
 ]
 
 
@@ -141,6 +141,9 @@ class SceneApi:
             "gather_image_open": (C.c_int, [vp, vp, u32]),
             "render_frame_peers": (C.c_int, [vp, P(Uniform), P(RenderOpts)]),
             "gather_image": (vp, [vp]),
+            "render_frame_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32, vp]),
+            "frame_wait": (C.c_int, [vp, u32]),
+            "frame_stream": (vp, [vp, u32]),
         }
         sig.update({k: v for k, v in device_side.items() if hasattr(self.lib, self.prefix + k)})
         sig.update(self._extra)
@@ -300,6 +303,18 @@ class SceneApi:
 
     def device_image(self):
         return self._f("device_image")(self.ctx)
+
+    # frames in flight (VK/SwapChain.h:8: MAX_FRAMES_IN_FLIGHT = 2)
+    def render_frame_async(self, uniform, opts, slot, host_ptr=None):
+        """Enqueues the frame on `slot` (after waiting for the slot's previous frame) and returns; host_ptr = address of a
+        (pinned) RGBA32F host buffer or None."""
+        self._ck(self._f("render_frame_async")(self.ctx, C.byref(uniform), C.byref(opts), slot, C.c_void_p(host_ptr) if host_ptr else None))
+
+    def frame_wait(self, slot):
+        self._ck(self._f("frame_wait")(self.ctx, slot))
+
+    def frame_stream(self, slot):
+        return self._f("frame_stream")(self.ctx, slot) or 0  # NULL = the legacy default stream
 
     # fused resolve + exchange over peer memory
     def gather_image_export(self, width, height):

@@ -167,13 +167,35 @@ enum { CLS_RAYGEN = 0, CLS_CLOSEST, CLS_SHADE, CLS_OCCL, CLS_ACCUM, CLS_RESOLVE,
 
 using namespace brt;
 
+// Everything one frame in flight owns: its streams, wavefront buffers, output images and timing events. The reference keeps
+// MAX_FRAMES_IN_FLIGHT = 2 frames in flight with a fence per frame (VK/SwapChain.h:8, VK/SwapChain.cpp:45-60,92-131) so that
+// the tail of one frame overlaps the head of the next; brt_render_frame_async / brt_frame_wait expose the same here.
+struct FrameSlot {
+  cudaStream_t stream = nullptr;   // closest-hit chain
+  cudaStream_t stream2 = nullptr;  // shadow chain (occlusion + accumulate), overlapped with the next round's traversal
+  bool own_stream = false;
+  cudaEvent_t ev_shade = nullptr, ev_acc[2] = {nullptr, nullptr};
+  cudaEvent_t ev_head = nullptr;  // recorded when the frame's last full-width wavefront (round 0 of the last batch) has been traced
+  uint32_t cap = 0;    // path slots per sample (owned tiles * 1024)
+  uint32_t batch = 1;  // samples traced together in one wavefront
+  size_t frame_bytes = 0;
+  uint64_t frame_key[4] = {0, 0, 0, 0};
+  uint32_t frame_w = 0, frame_h = 0;
+  DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
+  DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
+  std::deque<EventPair> events;  // deque: references stay valid while the pool grows
+  size_t events_used = 0;
+  uint32_t launches = 0, l_closest = 0, l_occl = 0;
+  FrameStats* fs_host = nullptr;  // pinned: device-side statistics of the frame, copied back on the frame's stream
+  bool in_flight = false;
+  bool ready = false;  // streams / events / pinned block created
+};
+
 struct brt_context {
   int device = 0;
   int sm_count = 148;
   uint32_t tile_rank = 0, tile_world = 1, flags = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // shadow chain (occlusion + accumulate), overlapped with the next round's traversal
-  cudaEvent_t ev_shade = nullptr, ev_acc[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;  // scene work (uploads, builds, culling) and frame slot 0
   cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};  // build / cull timing
   bool own_stream = false;
   std::string err;
@@ -196,23 +218,17 @@ struct brt_context {
   uint32_t tlas_count = 0;  // visible, non-empty instances in the TLAS
   BuildResult tlas{};
 
-  // frame
-  uint32_t cap = 0;    // path slots per sample (owned tiles * 1024)
-  uint32_t batch = 1;  // samples traced together in one wavefront
+  // frames
+  FrameSlot slots[BRT_FRAMES_IN_FLIGHT];
+  cudaEvent_t prev_head = nullptr;        // ev_head of the frame submitted last: the next frame starts behind it (staggered frames)
+  uint32_t last_slot = 0;                 // slot of the frame most recently waited for (brt_get_aov / brt_device_image read it)
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
-  size_t frame_bytes = 0;
-  uint64_t frame_key[4] = {0, 0, 0, 0};
-  uint32_t frame_w = 0, frame_h = 0;
-  DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
-  DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
   // fused resolve + exchange: own gather image and the peers' (opened through cudaIpc)
   DevBuf d_gather;
   uint32_t gather_w = 0, gather_h = 0, n_peers = 0;
   void* peer_images[BRT_MAX_PEERS] = {nullptr};
   bool peer_opened[BRT_MAX_PEERS] = {false};
-  std::deque<EventPair> events;  // deque: references stay valid while the pool grows
-  size_t events_used = 0;
   brt_stats stats{};
 };
 
@@ -255,7 +271,7 @@ uint32_t grid_for(const brt_context* c, uint32_t n, uint32_t block, uint32_t blo
 }
 
 // ---- timing ----------------------------------------------------------------------------------------
-EventPair& next_events(brt_context* c, int cls) {
+EventPair& next_events(FrameSlot* c, int cls) {
   if (c->events_used == c->events.size()) {
     EventPair e;
     BRT_CUDA(cudaEventCreate(&e.a));
@@ -269,7 +285,7 @@ EventPair& next_events(brt_context* c, int cls) {
 struct Timed {  // brackets one launch with events of class `cls` on the stream it is launched on
   cudaStream_t s;
   EventPair* e;
-  Timed(brt_context* ctx, int cls, cudaStream_t stream) : s(stream), e(&next_events(ctx, cls)) { BRT_CUDA(cudaEventRecord(e->a, s)); }
+  Timed(FrameSlot* ctx, int cls, cudaStream_t stream) : s(stream), e(&next_events(ctx, cls)) { BRT_CUDA(cudaEventRecord(e->a, s)); }
   ~Timed() { cudaEventRecord(e->b, s); }
 };
 
@@ -431,19 +447,19 @@ uint32_t tiles_per_rank(uint32_t width, uint32_t height, uint32_t world) {
 // Sizes the per-frame buffers. A wavefront holds `batch` samples of every owned pixel at once (cap slots per sample): the
 // more samples share a launch, the less the latency-bound tail of every launch costs — this is what keeps the tile-parallel
 // multi-GPU frames efficient, where each rank only has 1/N of the pixels.
-void ensure_frame_buffers(brt_context* c, const brt_render_opts& o, uint32_t rounds) {
+void ensure_frame_buffers(brt_context* c, FrameSlot* f, const brt_render_opts& o, uint32_t rounds) {
   const uint32_t cap = tiles_per_rank(o.width, o.height, c->tile_world) * 1024u;
   const size_t npx = (size_t)o.width * o.height;
   const uint32_t L = std::max<uint32_t>(1, (uint32_t)c->lights.size());
   const uint32_t R = std::max(1u, rounds);
   const uint64_t key[4] = {((uint64_t)o.width << 32) | o.height, ((uint64_t)o.spp << 32) | R, L, c->target_wavefront};
-  if (c->frame_bytes && std::memcmp(key, c->frame_key, sizeof(key)) == 0) return;  // same frame shape as last time
-  std::memcpy(c->frame_key, key, sizeof(key));
+  if (f->frame_bytes && std::memcmp(key, f->frame_key, sizeof(key)) == 0) return;  // same frame shape as last time
+  std::memcpy(f->frame_key, key, sizeof(key));
   // bytes per sample of the batch: two path queues, hits, and per round parity: contributions, weights, shadow queue; + radiance terms
   const size_t per_sample = (size_t)cap * (2 * 56 + 20 + 2 * (16 * L + 16 + 36 * L) + 16 * R);
   size_t free_b = 0, total_b = 0;
   BRT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + c->frame_bytes) * 2 / 5);
+  size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + f->frame_bytes) * 2 / 5);
   uint32_t batch = (uint32_t)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_sample, 1), BRT_MAX_SAMPLE_BATCH));
   // enough samples per wavefront to amortise the per-launch tails (about 16 M paths), no more: larger wavefronts only cost
   // memory traffic
@@ -452,38 +468,38 @@ void ensure_frame_buffers(brt_context* c, const brt_render_opts& o, uint32_t rou
   if ((uint64_t)cap * batch > 0xfffffff0ull / L) batch = std::max<uint64_t>(1, 0xfffffff0ull / L / cap);  // 32-bit shadow-queue targets
   const size_t capw = (size_t)cap * batch;
   for (int k = 0; k < 2; ++k) {
-    c->q_o[k].ensure(capw * 16);
-    c->q_d[k].ensure(capw * 16);
-    c->q_w[k].ensure(capw * 16);
-    c->q_px[k].ensure(capw * 4);
-    c->q_seed[k].ensure(capw * 4);
+    f->q_o[k].ensure(capw * 16);
+    f->q_d[k].ensure(capw * 16);
+    f->q_w[k].ensure(capw * 16);
+    f->q_px[k].ensure(capw * 4);
+    f->q_seed[k].ensure(capw * 4);
     // per round parity: what the occlusion / accumulate chain of a round owns
-    c->d_contrib[k].ensure(capw * 16 * L);
-    c->d_aux[k].ensure(capw * 16);
-    c->s_o[k].ensure(capw * 16 * L);
-    c->s_d[k].ensure(capw * 16 * L);
-    c->s_target[k].ensure(capw * 4 * L);
+    f->d_contrib[k].ensure(capw * 16 * L);
+    f->d_aux[k].ensure(capw * 16);
+    f->s_o[k].ensure(capw * 16 * L);
+    f->s_d[k].ensure(capw * 16 * L);
+    f->s_target[k].ensure(capw * 4 * L);
   }
-  c->d_hit.ensure(capw * 16);
-  c->d_hit_inst.ensure(capw * 4);
-  c->d_rad.ensure(capw * 16 * R);
-  c->d_accum.ensure((size_t)cap * 16);
-  c->d_image.ensure(npx * 16);
-  c->d_tiles.ensure((size_t)cap * 16);
-  c->d_aov_prim.ensure(npx * 4);
-  c->d_aov_inst.ensure(npx * 4);
-  c->d_aov_t.ensure(npx * 4);
-  c->d_counters.ensure(sizeof(FrameCounters) + 2 * sizeof(ShadowCounters));
-  c->d_fstats.ensure(sizeof(FrameStats));
-  c->frame_bytes = per_sample * batch;
-  c->cap = cap;
-  c->batch = batch;
-  c->frame_w = o.width;
-  c->frame_h = o.height;
+  f->d_hit.ensure(capw * 16);
+  f->d_hit_inst.ensure(capw * 4);
+  f->d_rad.ensure(capw * 16 * R);
+  f->d_accum.ensure((size_t)cap * 16);
+  f->d_image.ensure(npx * 16);
+  f->d_tiles.ensure((size_t)cap * 16);
+  f->d_aov_prim.ensure(npx * 4);
+  f->d_aov_inst.ensure(npx * 4);
+  f->d_aov_t.ensure(npx * 4);
+  f->d_counters.ensure(sizeof(FrameCounters) + 2 * sizeof(ShadowCounters));
+  f->d_fstats.ensure(sizeof(FrameStats));
+  f->frame_bytes = per_sample * batch;
+  f->cap = cap;
+  f->batch = batch;
+  f->frame_w = o.width;
+  f->frame_h = o.height;
 }
 
-PathQueue queue_of(brt_context* c, int k) {
-  return PathQueue{c->q_o[k].as<float4>(), c->q_d[k].as<float4>(), c->q_w[k].as<float4>(), c->q_px[k].as<uint32_t>(), c->q_seed[k].as<uint32_t>()};
+PathQueue queue_of(FrameSlot* f, int k) {
+  return PathQueue{f->q_o[k].as<float4>(), f->q_d[k].as<float4>(), f->q_w[k].as<float4>(), f->q_px[k].as<uint32_t>(), f->q_seed[k].as<uint32_t>()};
 }
 
 template <bool ANY>
@@ -502,7 +518,7 @@ void launch_trace(brt_context* c, const TraceParams& p, cudaStream_t stream) {
 // round k+1). The buffers the shadow chain owns (contributions, weights/pixels, shadow queue, counters) are
 // double-buffered by round parity; shade(k+2) waits for accumulate(k). Accumulation stays in round order on one stream,
 // so the result is bit-identical to the serial schedule (BRT_CFG_NO_OVERLAP, used for per-kernel timing).
-void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_opts& o, void* d_tiles_out, bool to_peers = false) {
+void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, const brt_render_opts& o, void* d_tiles_out, bool to_peers = false) {
   if (!c->built) bad_state("render_frame: scene not built (call brt_scene_build)");
   if (!o.width || !o.height || !o.spp) invalid("render_frame: width, height and spp must be non-zero");
   if (c->lights.size() > BRT_MAX_LIGHTS) throw LimitError("render_frame: more than BRT_MAX_LIGHTS lights");
@@ -510,36 +526,41 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
   if (c->tlas_dirty) build_tlas(c);
   const bool any_bounce = (o.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0;
   const uint32_t rounds = any_bounce ? u.depthMax : std::min(u.depthMax, 1u);
-  ensure_frame_buffers(c, o, rounds);
-  cudaStream_t s = c->stream;
-  cudaStream_t s2 = (c->flags & BRT_CFG_NO_OVERLAP) ? c->stream : c->stream2;
+  ensure_frame_buffers(c, f, o, rounds);
+  cudaStream_t s = f->stream;
+  cudaStream_t s2 = (c->flags & BRT_CFG_NO_OVERLAP) ? f->stream : f->stream2;
   const TileMap map = make_tile_map(c, o);
-  const uint32_t cap = c->cap;
+  const uint32_t cap = f->cap;
   const size_t npx = (size_t)o.width * o.height;
   const uint32_t n_lights = (uint32_t)c->lights.size();
   const uint32_t n_slots = std::max(1u, n_lights);
-  c->events_used = 0;
-  FrameCounters* ctr = c->d_counters.as<FrameCounters>();
+  f->events_used = 0;
+  FrameCounters* ctr = f->d_counters.as<FrameCounters>();
   ShadowCounters* sctr = reinterpret_cast<ShadowCounters*>(ctr + 1);
-  FrameStats* fst = c->d_fstats.as<FrameStats>();
-  EventPair& whole = next_events(c, CLS_COUNT);
+  FrameStats* fst = f->d_fstats.as<FrameStats>();
+  // Frames in flight are staggered: this frame starts when the previous one has traced its last full-width wavefront, so
+  // that its saturating head overlaps the latency-bound tail (bounce rounds, resolve, copy-out) of the previous frame
+  // instead of running in lockstep with it.
+  if (c->prev_head && c->prev_head != f->ev_head) BRT_CUDA(cudaStreamWaitEvent(s, c->prev_head, 0));
+  EventPair& whole = next_events(f, CLS_COUNT);
   BRT_CUDA(cudaEventRecord(whole.a, s));
-  BRT_CUDA(cudaMemsetAsync(c->d_accum.ptr(), 0, (size_t)cap * 16, s));
+  BRT_CUDA(cudaMemsetAsync(f->d_accum.ptr(), 0, (size_t)cap * 16, s));
   BRT_CUDA(cudaMemsetAsync(fst, 0, sizeof(FrameStats), s));
-  BRT_CUDA(cudaMemsetAsync(c->d_aov_prim.ptr(), 0xff, npx * 4, s));
-  BRT_CUDA(cudaMemsetAsync(c->d_aov_inst.ptr(), 0xff, npx * 4, s));
-  BRT_CUDA(cudaMemsetAsync(c->d_aov_t.ptr(), 0, npx * 4, s));
-  if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(c->d_image.ptr(), 0, npx * 16, s));
+  BRT_CUDA(cudaMemsetAsync(f->d_aov_prim.ptr(), 0xff, npx * 4, s));
+  BRT_CUDA(cudaMemsetAsync(f->d_aov_inst.ptr(), 0xff, npx * 4, s));
+  BRT_CUDA(cudaMemsetAsync(f->d_aov_t.ptr(), 0, npx * 4, s));
+  if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(f->d_image.ptr(), 0, npx * 16, s));
   uint32_t launches = 0, l_closest = 0, l_occl = 0;
   const Node8* tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
   const InstRec* insts = c->d_tlas_inst.as<InstRec>();
   bool acc_pending[2] = {false, false};  // ev_acc[p] has been recorded and not yet waited for by the main stream
   uint32_t global_round = 0;
 
-  for (uint32_t sample = 0; sample < o.spp; sample += c->batch) {
-    const uint32_t nb = std::min(c->batch, o.spp - sample);  // samples in this wavefront
+  const uint32_t c_batch = f->batch;
+  for (uint32_t sample = 0; sample < o.spp; sample += f->batch) {
+    const uint32_t nb = std::min(f->batch, o.spp - sample);  // samples in this wavefront
     const uint32_t capw = cap * nb;                          // its path slots
-    if (rounds) BRT_CUDA(cudaMemsetAsync(c->d_rad.ptr(), 0, (size_t)capw * rounds * 16, s));
+    if (rounds) BRT_CUDA(cudaMemsetAsync(f->d_rad.ptr(), 0, (size_t)capw * rounds * 16, s));
     {
       RaygenParams rp;
       rp.count = capw;
@@ -550,8 +571,8 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       rp.frame = u.frame + sample;
       rp.flags = o.flags;
       rp.cap = cap;
-      rp.q = queue_of(c, 0);
-      Timed t(c, CLS_RAYGEN, s);
+      rp.q = queue_of(f, 0);
+      Timed t(f, CLS_RAYGEN, s);
       BRT_LAUNCH_1D(k_raygen, rp, grid_for(c, capw, 256, 8), 256, s);
       BRT_CHECK_LAUNCH();
       launches++;
@@ -567,7 +588,7 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         BRT_CUDA(cudaMemsetAsync(&ctr->work_closest, 0, 4, s));
       }
       const uint32_t* count_ptr = round == 0 ? nullptr : &ctr->n_paths[cur];
-      const PathQueue qc = queue_of(c, cur), qn = queue_of(c, cur ^ 1);
+      const PathQueue qc = queue_of(f, cur), qn = queue_of(f, cur ^ 1);
       {
         TraceParams tp{};
         tp.count = capw;
@@ -577,19 +598,19 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         tp.o = qc.o;
         tp.d = qc.d;
         tp.px = qc.px;
-        tp.hit = c->d_hit.as<float4>();
-        tp.hit_inst = c->d_hit_inst.as<uint32_t>();
+        tp.hit = f->d_hit.as<float4>();
+        tp.hit_inst = f->d_hit_inst.as<uint32_t>();
         tp.work = &ctr->work_closest;
         tp.stats = fst;
         tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;  // measured: refill pays for bounce rays only
-        Timed t(c, CLS_CLOSEST, s);
+        Timed t(f, CLS_CLOSEST, s);
         launch_trace<false>(c, tp, s);
         launches++;
         l_closest++;
       }
       // the shadow-chain buffers of this parity were last used two rounds ago: wait for that accumulate
       if (acc_pending[par]) {
-        if (s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, c->ev_acc[par], 0));
+        if (s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, f->ev_acc[par], 0));
         acc_pending[par] = false;
       }
       BRT_CUDA(cudaMemsetAsync(&sctr[par], 0, sizeof(ShadowCounters), s));
@@ -599,11 +620,11 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         sp.count_ptr = count_ptr;
         sp.cur = qc;
         sp.next = qn;
-        sp.hit = c->d_hit.as<float4>();
-        sp.hit_inst = c->d_hit_inst.as<uint32_t>();
+        sp.hit = f->d_hit.as<float4>();
+        sp.hit_inst = f->d_hit_inst.as<uint32_t>();
         sp.ctr = ctr;
         sp.sctr = &sctr[par];
-        sp.aux = c->d_aux[par].as<float4>();
+        sp.aux = f->d_aux[par].as<float4>();
         sp.next_slot = (uint32_t)(cur ^ 1);
         sp.cap = capw;
         sp.inst = c->d_inst_shade.as<InstShade>();
@@ -611,26 +632,26 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         sp.mat_ext = c->d_mat_ext.as<float2>();
         sp.lights = c->d_lights.as<LightRec>();
         sp.n_lights = n_lights;
-        sp.contrib = c->d_contrib[par].as<float4>();
-        sp.s_o = c->s_o[par].as<float4>();
-        sp.s_d = c->s_d[par].as<float4>();
-        sp.s_target = c->s_target[par].as<uint32_t>();
+        sp.contrib = f->d_contrib[par].as<float4>();
+        sp.s_o = f->s_o[par].as<float4>();
+        sp.s_d = f->s_d[par].as<float4>();
+        sp.s_target = f->s_target[par].as<uint32_t>();
         sp.flags = o.flags;
         sp.last_round = round + 1 == rounds ? 1u : 0u;
         sp.write_aov = (sample == 0 && round == 0) ? 1u : 0u;
         sp.map = map;
-        sp.aov_prim = c->d_aov_prim.as<uint32_t>();
-        sp.aov_inst = c->d_aov_inst.as<uint32_t>();
-        sp.aov_t = c->d_aov_t.as<float>();
+        sp.aov_prim = f->d_aov_prim.as<uint32_t>();
+        sp.aov_inst = f->d_aov_inst.as<uint32_t>();
+        sp.aov_t = f->d_aov_t.as<float>();
         sp.sky = c->sky;
-        Timed t(c, CLS_SHADE, s);
+        Timed t(f, CLS_SHADE, s);
         BRT_LAUNCH_1D(k_shade, sp, grid_for(c, capw, 128, 16), 128, s);
         BRT_CHECK_LAUNCH();
         launches++;
       }
       if (s2 != s) {
-        BRT_CUDA(cudaEventRecord(c->ev_shade, s));
-        BRT_CUDA(cudaStreamWaitEvent(s2, c->ev_shade, 0));
+        BRT_CUDA(cudaEventRecord(f->ev_shade, s));
+        BRT_CUDA(cudaStreamWaitEvent(s2, f->ev_shade, 0));
       }
       if (n_lights) {
         TraceParams tp{};
@@ -640,42 +661,43 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
         tp.seg_stride = capw;
         tp.tlas = tlas;
         tp.insts = insts;
-        tp.o = c->s_o[par].as<float4>();
-        tp.d = c->s_d[par].as<float4>();
-        tp.target = c->s_target[par].as<uint32_t>();
-        tp.contrib = c->d_contrib[par].as<float4>();
+        tp.o = f->s_o[par].as<float4>();
+        tp.d = f->s_d[par].as<float4>();
+        tp.target = f->s_target[par].as<uint32_t>();
+        tp.contrib = f->d_contrib[par].as<float4>();
         tp.work = &sctr[par].work_occl;
         tp.stats = fst;
         tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;
-        Timed t(c, CLS_OCCL, s2);
+        Timed t(f, CLS_OCCL, s2);
         launch_trace<true>(c, tp, s2);
         launches++;
         l_occl++;
       }
+      if (round == 0 && sample + c_batch >= o.spp) BRT_CUDA(cudaEventRecord(f->ev_head, s2));
       {
         AccumParams ap{};
         ap.count = 0;
         ap.count_ptr = &sctr[par].n_items;
-        ap.aux = c->d_aux[par].as<float4>();
-        ap.contrib = c->d_contrib[par].as<float4>();
+        ap.aux = f->d_aux[par].as<float4>();
+        ap.contrib = f->d_contrib[par].as<float4>();
         ap.n_slots = n_slots;
         ap.cap = capw;
         ap.slots = cap;
         ap.rounds = rounds;
         ap.round = round;
-        ap.rad = c->d_rad.as<float4>();
-        Timed t(c, CLS_ACCUM, s2);
+        ap.rad = f->d_rad.as<float4>();
+        Timed t(f, CLS_ACCUM, s2);
         BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, capw, 256, 8), 256, s2);
         BRT_CHECK_LAUNCH();
         launches++;
       }
-      if (s2 != s) BRT_CUDA(cudaEventRecord(c->ev_acc[par], s2));
+      if (s2 != s) BRT_CUDA(cudaEventRecord(f->ev_acc[par], s2));
       acc_pending[par] = true;
       cur ^= 1;
     }
     // join the shadow chain, then add this batch's radiance terms to the per-slot sums in the shader's order
     for (int par = 0; par < 2; ++par) {
-      if (acc_pending[par] && s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, c->ev_acc[par], 0));
+      if (acc_pending[par] && s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, f->ev_acc[par], 0));
       acc_pending[par] = false;
     }
     if (rounds) {
@@ -684,9 +706,9 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       sp.count_ptr = nullptr;
       sp.samples = nb;
       sp.rounds = rounds;
-      sp.rad = c->d_rad.as<float4>();
-      sp.accum = c->d_accum.as<float4>();
-      Timed t(c, CLS_ACCUM, s);
+      sp.rad = f->d_rad.as<float4>();
+      sp.accum = f->d_accum.as<float4>();
+      Timed t(f, CLS_ACCUM, s);
       BRT_LAUNCH_1D(k_sum_samples, sp, grid_for(c, cap, 256, 8), 256, s);
       BRT_CHECK_LAUNCH();
       launches++;
@@ -698,9 +720,9 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
     rp.count_ptr = nullptr;
     rp.map = map;
     rp.spp = (float)o.spp;
-    rp.accum = c->d_accum.as<float4>();
-    rp.image = c->d_image.as<float4>();
-    rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : c->d_tiles.as<float4>();
+    rp.accum = f->d_accum.as<float4>();
+    rp.image = f->d_image.as<float4>();
+    rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : f->d_tiles.as<float4>();
     rp.n_peers = 0;
     if (to_peers) {
       if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
@@ -708,15 +730,20 @@ void render_frame_device(brt_context* c, const brt_uniform& u, const brt_render_
       rp.n_peers = c->n_peers;
       for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]);
     }
-    Timed t(c, CLS_RESOLVE, s);
+    Timed t(f, CLS_RESOLVE, s);
     BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
     BRT_CHECK_LAUNCH();
     launches++;
   }
   BRT_CUDA(cudaEventRecord(whole.b, s));
-  c->stats.launches_total = launches;
-  c->stats.launches_trace_closest = l_closest;
-  c->stats.launches_trace_occlusion = l_occl;
+  if (!rounds) BRT_CUDA(cudaEventRecord(f->ev_head, s));
+  c->prev_head = f->ev_head;
+  f->launches = launches;
+  f->l_closest = l_closest;
+  f->l_occl = l_occl;
+  // device-side statistics of this frame travel back on its stream (read by finish_frame)
+  BRT_CUDA(cudaMemcpyAsync(f->fs_host, f->d_fstats.ptr(), sizeof(FrameStats), cudaMemcpyDeviceToHost, s));
+  f->in_flight = true;
 }
 
 #ifndef BRT_EMU
@@ -730,19 +757,23 @@ void close_peers(brt_context* c) {
 }
 #endif
 
-// waits for the frame and folds the device-side statistics / event timings into ctx->stats
-void finish_frame(brt_context* c) {
-  FrameStats fs;
-  BRT_CUDA(cudaMemcpyAsync(&fs, c->d_fstats.ptr(), sizeof(fs), cudaMemcpyDeviceToHost, c->stream));
-  BRT_CUDA(cudaStreamSynchronize(c->stream));
+// waits for the slot's frame and folds the device-side statistics / event timings into ctx->stats
+void finish_frame(brt_context* c, FrameSlot* f) {
+  if (!f->in_flight) return;
+  BRT_CUDA(cudaStreamSynchronize(f->stream));
+  f->in_flight = false;
   BRT_CUDA(cudaGetLastError());
+  const FrameStats fs = *f->fs_host;
   float ms[CLS_COUNT + 1] = {0};
-  for (size_t i = 0; i < c->events_used; ++i) {
+  for (size_t i = 0; i < f->events_used; ++i) {
     float t = 0.0f;
-    cudaEventElapsedTime(&t, c->events[i].a, c->events[i].b);
-    ms[c->events[i].cls] += t;
+    cudaEventElapsedTime(&t, f->events[i].a, f->events[i].b);
+    ms[f->events[i].cls] += t;
   }
   brt_stats& st = c->stats;
+  st.launches_total = f->launches;
+  st.launches_trace_closest = f->l_closest;
+  st.launches_trace_occlusion = f->l_occl;
   st.rays_closest = fs.rays_closest;
   st.rays_occlusion = fs.rays_occlusion;
   st.nodes_visited_closest = fs.nodes_c;
@@ -758,6 +789,46 @@ void finish_frame(brt_context* c) {
   st.ms_accumulate = ms[CLS_ACCUM];
   st.ms_resolve = ms[CLS_RESOLVE];
   st.ms_total = ms[CLS_COUNT];
+  c->last_slot = (uint32_t)(f - c->slots);
+}
+
+// scene changes (builds, uploads, culling) and the synchronous entry points first drain every frame in flight
+void wait_all_frames(brt_context* c) {
+  for (FrameSlot& f : c->slots) finish_frame(c, &f);
+}
+
+// creates a slot's streams and events on first use (slot 0 shares the context's stream)
+void ensure_slot(brt_context* c, FrameSlot* f) {
+  if (f == &c->slots[0]) f->stream = c->stream;  // (brt_set_stream may have replaced it)
+  if (f->ready) return;
+  if (f != &c->slots[0]) {
+    BRT_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    f->own_stream = true;
+  }
+  BRT_CUDA(cudaStreamCreateWithFlags(&f->stream2, cudaStreamNonBlocking));
+  BRT_CUDA(cudaEventCreateWithFlags(&f->ev_shade, cudaEventDisableTiming));
+  BRT_CUDA(cudaEventCreateWithFlags(&f->ev_acc[0], cudaEventDisableTiming));
+  BRT_CUDA(cudaEventCreateWithFlags(&f->ev_acc[1], cudaEventDisableTiming));
+  BRT_CUDA(cudaEventCreateWithFlags(&f->ev_head, cudaEventDisableTiming));
+  BRT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&f->fs_host), sizeof(FrameStats)));
+  f->ready = true;
+}
+
+void destroy_slot(FrameSlot* f) {
+  if (!f->ready) return;
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  if (f->stream2) cudaStreamSynchronize(f->stream2);
+  for (EventPair& e : f->events) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
+  if (f->stream2) cudaStreamDestroy(f->stream2);
+  if (f->ev_shade) cudaEventDestroy(f->ev_shade);
+  if (f->ev_head) cudaEventDestroy(f->ev_head);
+  for (int k = 0; k < 2; ++k)
+    if (f->ev_acc[k]) cudaEventDestroy(f->ev_acc[k]);
+  if (f->fs_host) cudaFreeHost(f->fs_host);
 }
 
 }  // namespace
@@ -783,10 +854,6 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     BRT_CUDA(cudaSetDevice(c->device));
     BRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     BRT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    BRT_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    BRT_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
-    BRT_CUDA(cudaEventCreateWithFlags(&c->ev_acc[0], cudaEventDisableTiming));
-    BRT_CUDA(cudaEventCreateWithFlags(&c->ev_acc[1], cudaEventDisableTiming));
     for (int k = 0; k < 3; ++k) BRT_CUDA(cudaEventCreate(&c->ev_t[k]));
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count));
@@ -805,19 +872,11 @@ void brt_destroy(brt_context* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  for (FrameSlot& f : c->slots) destroy_slot(&f);
 #ifndef BRT_EMU
   close_peers(c);
 #endif
-  for (EventPair& e : c->events) {
-    cudaEventDestroy(e.a);
-    cudaEventDestroy(e.b);
-  }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-  if (c->stream2) cudaStreamDestroy(c->stream2);
-  if (c->ev_shade) cudaEventDestroy(c->ev_shade);
-  for (int k = 0; k < 2; ++k)
-    if (c->ev_acc[k]) cudaEventDestroy(c->ev_acc[k]);
   for (int k = 0; k < 3; ++k)
     if (c->ev_t[k]) cudaEventDestroy(c->ev_t[k]);
   delete c;
@@ -828,6 +887,7 @@ const char* brt_last_error(const brt_context* c) { return c ? c->err.c_str() : g
 int brt_set_stream(brt_context* c, void* stream) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
+    wait_all_frames(c);
     BRT_CUDA(cudaStreamSynchronize(c->stream));
     if (c->own_stream) cudaStreamDestroy(c->stream);
     c->own_stream = false;
@@ -838,6 +898,7 @@ int brt_set_stream(brt_context* c, void* stream) {
 int brt_mesh_create(brt_context* c, const brt_vertex* v, uint32_t nv, const uint32_t* idx, uint32_t ni, uint32_t* mesh_id) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
+    wait_all_frames(c);
     if ((!v && nv) || (!idx && ni) || ni % 3) invalid("mesh_create: bad arguments");
     for (uint32_t i = 0; i < ni; ++i)
       if (idx[i] >= nv) invalid("mesh_create: index out of range");
@@ -857,6 +918,7 @@ int brt_mesh_create(brt_context* c, const brt_vertex* v, uint32_t nv, const uint
 int brt_mesh_update_vertices(brt_context* c, uint32_t mesh_id, const brt_vertex* v, uint32_t nv) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
+    wait_all_frames(c);
     if (mesh_id >= c->meshes.size() || c->meshes[mesh_id]->sphere || nv != c->meshes[mesh_id]->n_vertices || (!v && nv))
       invalid("mesh_update_vertices: bad mesh id or vertex count");
     BRT_CUDA(cudaSetDevice(c->device));
@@ -872,6 +934,7 @@ int brt_mesh_update_vertices(brt_context* c, uint32_t mesh_id, const brt_vertex*
 int brt_sphere_create(brt_context* c, const float center[3], float radius, uint32_t* mesh_id) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
+    wait_all_frames(c);
     if (!center || !(radius > 0.0f)) invalid("sphere_create: bad arguments");
     std::unique_ptr<MeshData> m(new MeshData());
     m->sphere = true;
@@ -976,6 +1039,7 @@ int brt_instance_destroy(brt_context* c, uint32_t id) {  // RT/Scene.cpp:122-125
 int brt_scene_build(brt_context* c) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
+    wait_all_frames(c);
     BRT_CUDA(cudaSetDevice(c->device));
     scene_build(c);
   });
@@ -985,6 +1049,7 @@ int brt_smart_cull(brt_context* c, const brt_uniform* u, uint32_t width, uint32_
                    uint32_t* visible_count) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
+    wait_all_frames(c);
     if (!u) invalid("smart_cull: null");
     (void)width;
     BRT_CUDA(cudaSetDevice(c->device));
@@ -1048,11 +1113,46 @@ int brt_render_frame(brt_context* c, const brt_uniform* u, const brt_render_opts
   return guarded(c, [&] {
     if (!u || !o) invalid("render_frame: null");
     BRT_CUDA(cudaSetDevice(c->device));
-    render_frame_device(c, *u, *o, nullptr);
+    wait_all_frames(c);
+    FrameSlot* f = &c->slots[0];
+    ensure_slot(c, f);
+    render_frame_device(c, f, *u, *o, nullptr);
     if (rgba_host)
-      BRT_CUDA(cudaMemcpyAsync(rgba_host, c->d_image.ptr(), (size_t)o->width * o->height * 16, cudaMemcpyDeviceToHost, c->stream));
-    finish_frame(c);
+      BRT_CUDA(cudaMemcpyAsync(rgba_host, f->d_image.ptr(), (size_t)o->width * o->height * 16, cudaMemcpyDeviceToHost, f->stream));
+    finish_frame(c, f);
   });
+}
+
+int brt_render_frame_async(brt_context* c, const brt_uniform* u, const brt_render_opts* o, uint32_t slot, float* rgba_host) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!u || !o) invalid("render_frame_async: null");
+    if (slot >= BRT_FRAMES_IN_FLIGHT) invalid("render_frame_async: slot >= BRT_FRAMES_IN_FLIGHT");
+    if (c->tile_world > 1) bad_state("render_frame_async: single-GPU contexts only (tile_world == 1)");
+    BRT_CUDA(cudaSetDevice(c->device));
+    FrameSlot* f = &c->slots[slot];
+    finish_frame(c, f);  // the fence of this slot (VK/SwapChain.cpp:45-60): its previous frame must be complete
+    if (c->tables_dirty || c->tlas_dirty) wait_all_frames(c);  // the scene tables are about to be rewritten
+    ensure_slot(c, f);
+    render_frame_device(c, f, *u, *o, nullptr);
+    if (rgba_host)
+      BRT_CUDA(cudaMemcpyAsync(rgba_host, f->d_image.ptr(), (size_t)o->width * o->height * 16, cudaMemcpyDeviceToHost, f->stream));
+  });
+}
+
+int brt_frame_wait(brt_context* c, uint32_t slot) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (slot >= BRT_FRAMES_IN_FLIGHT) invalid("frame_wait: slot >= BRT_FRAMES_IN_FLIGHT");
+    BRT_CUDA(cudaSetDevice(c->device));
+    finish_frame(c, &c->slots[slot]);
+  });
+}
+
+void* brt_frame_stream(brt_context* c, uint32_t slot) {
+  if (!c || slot >= BRT_FRAMES_IN_FLIGHT) return nullptr;
+  if (guarded(c, [&] { BRT_CUDA(cudaSetDevice(c->device)); ensure_slot(c, &c->slots[slot]); }) != BRT_OK) return nullptr;
+  return c->slots[slot].stream;
 }
 
 int brt_render_frame_tiles(brt_context* c, const brt_uniform* u, const brt_render_opts* o, void* d_tiles) {
@@ -1060,8 +1160,11 @@ int brt_render_frame_tiles(brt_context* c, const brt_uniform* u, const brt_rende
   return guarded(c, [&] {
     if (!u || !o) invalid("render_frame_tiles: null");
     BRT_CUDA(cudaSetDevice(c->device));
-    render_frame_device(c, *u, *o, d_tiles);
-    finish_frame(c);
+    wait_all_frames(c);
+    FrameSlot* f = &c->slots[0];
+    ensure_slot(c, f);
+    render_frame_device(c, f, *u, *o, d_tiles);
+    finish_frame(c, f);
   });
 }
 
@@ -1089,7 +1192,7 @@ int brt_untile(brt_context* c, const void* d_all, uint32_t width, uint32_t heigh
   });
 }
 
-void* brt_device_image(brt_context* c) { return c ? c->d_image.ptr() : nullptr; }
+void* brt_device_image(brt_context* c) { return c ? c->slots[c->last_slot].d_image.ptr() : nullptr; }
 
 int brt_gather_image_export(brt_context* c, uint32_t width, uint32_t height, void* handle_out) {
   if (!c) return BRT_ERR_INVALID;
@@ -1143,8 +1246,11 @@ int brt_render_frame_peers(brt_context* c, const brt_uniform* u, const brt_rende
   return guarded(c, [&] {
     if (!u || !o) invalid("render_frame_peers: null");
     BRT_CUDA(cudaSetDevice(c->device));
-    render_frame_device(c, *u, *o, nullptr, true);
-    finish_frame(c);
+    wait_all_frames(c);
+    FrameSlot* f = &c->slots[0];
+    ensure_slot(c, f);
+    render_frame_device(c, f, *u, *o, nullptr, true);
+    finish_frame(c, f);
   });
 }
 
@@ -1154,14 +1260,16 @@ int brt_get_aov(brt_context* c, int kind, void* out) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
     if (!out) invalid("get_aov: null");
-    if (!c->frame_w) bad_state("get_aov: no frame rendered");
+    wait_all_frames(c);
+    FrameSlot* f = &c->slots[c->last_slot];
+    if (!f->frame_w) bad_state("get_aov: no frame rendered");
     BRT_CUDA(cudaSetDevice(c->device));
-    const size_t n = (size_t)c->frame_w * c->frame_h;
+    const size_t n = (size_t)f->frame_w * f->frame_h;
     const void* src = nullptr;
     switch (kind) {
-      case BRT_AOV_PRIM_ID: src = c->d_aov_prim.ptr(); break;
-      case BRT_AOV_INST_ID: src = c->d_aov_inst.ptr(); break;
-      case BRT_AOV_HIT_T: src = c->d_aov_t.ptr(); break;
+      case BRT_AOV_PRIM_ID: src = f->d_aov_prim.ptr(); break;
+      case BRT_AOV_INST_ID: src = f->d_aov_inst.ptr(); break;
+      case BRT_AOV_HIT_T: src = f->d_aov_t.ptr(); break;
       default: invalid("get_aov: bad kind");
     }
     BRT_CUDA(cudaMemcpyAsync(out, src, n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1181,9 +1289,11 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
     if (!rays || !out) invalid("trace_rays: null");
     if (!c->built) bad_state("trace_rays: scene not built");
     BRT_CUDA(cudaSetDevice(c->device));
+    wait_all_frames(c);
     if (c->tlas_dirty) build_tlas(c);
     if (n == 0) return;
     cudaStream_t s = c->stream;
+    FrameSlot* f = &c->slots[0];
     // split the interleaved rays into the two float4 arrays the kernels read
     std::vector<float> o4((size_t)n * 4), d4((size_t)n * 4);
     for (uint32_t i = 0; i < n; ++i) {
@@ -1192,8 +1302,8 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
     }
     c->d_rays.ensure((size_t)n * 32);
     c->d_ray_out.ensure((size_t)n * 16 + (size_t)n * 4 + (size_t)n * 4);
-    c->d_counters.ensure(sizeof(FrameCounters) + 2 * sizeof(ShadowCounters));
-    c->d_fstats.ensure(sizeof(FrameStats));
+    f->d_counters.ensure(sizeof(FrameCounters) + 2 * sizeof(ShadowCounters));
+    f->d_fstats.ensure(sizeof(FrameStats));
     float4* d_o = c->d_rays.as<float4>();
     float4* d_d = d_o + n;
     float4* d_hit = c->d_ray_out.as<float4>();
@@ -1201,16 +1311,16 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
     uint32_t* d_target = d_inst + n;
     BRT_CUDA(cudaMemcpyAsync(d_o, o4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s));
     BRT_CUDA(cudaMemcpyAsync(d_d, d4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s));
-    BRT_CUDA(cudaMemsetAsync(c->d_counters.ptr(), 0, sizeof(FrameCounters) + 2 * sizeof(ShadowCounters), s));
-    BRT_CUDA(cudaMemsetAsync(c->d_fstats.ptr(), 0, sizeof(FrameStats), s));
-    FrameCounters* ctr = c->d_counters.as<FrameCounters>();
+    BRT_CUDA(cudaMemsetAsync(f->d_counters.ptr(), 0, sizeof(FrameCounters) + 2 * sizeof(ShadowCounters), s));
+    BRT_CUDA(cudaMemsetAsync(f->d_fstats.ptr(), 0, sizeof(FrameStats), s));
+    FrameCounters* ctr = f->d_counters.as<FrameCounters>();
     TraceParams tp{};
     tp.count = n;
     tp.tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
     tp.insts = c->d_tlas_inst.as<InstRec>();
     tp.o = d_o;
     tp.d = d_d;
-    tp.stats = c->d_fstats.as<FrameStats>();
+    tp.stats = f->d_fstats.as<FrameStats>();
     std::vector<float> hit((size_t)n * 4);
     std::vector<uint32_t> inst(n);
     if (closest) {
@@ -1250,7 +1360,7 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
       }
     }
     FrameStats fs;
-    BRT_CUDA(cudaMemcpy(&fs, c->d_fstats.ptr(), sizeof(fs), cudaMemcpyDeviceToHost));
+    BRT_CUDA(cudaMemcpy(&fs, f->d_fstats.ptr(), sizeof(fs), cudaMemcpyDeviceToHost));
     c->stats.rays_closest = fs.rays_closest;
     c->stats.rays_occlusion = fs.rays_occlusion;
     c->stats.nodes_visited_closest = fs.nodes_c;

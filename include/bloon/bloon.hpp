@@ -280,7 +280,28 @@ class Pipeline {
     o.width = width; o.height = height; o.spp = spp; o.flags = renderFlags;
     bloon::check(brt_render_frame(device.getDevice(), &uniforms[current], &o, storageImage.data()), device.getDevice(), "traceRays");
   }
-  void rebuildRenderOutput(Extent2D e) { extent = e; storageImage.assign((size_t)e.width * e.height * 4, 0.0f); }  // RT/RTPipeline.cpp:49-55
+  // Two frames in flight, as RTApp::beginFrame / endFrame over SwapChain::MAX_FRAMES_IN_FLIGHT = 2 (RT/RTApp.cpp:171-212,
+  // vulkan_core/SwapChain.h:8): submitFrame(frameIndex) = bindDescriptorSets(cmd, frameIndex) + traceRays + submitCommandBuffers
+  // with the uniform written for that index; waitFrame(frameIndex) = the slot's fence, returns that slot's image.
+  void submitFrame(uint32_t frameIndex, uint32_t width, uint32_t height, uint32_t spp = 1, uint32_t renderFlags = 0) {
+    if (width != extent.width || height != extent.height) rebuildRenderOutput({width, height});
+    const uint32_t k = frameIndex % 2;
+    bloon::check(brt_frame_wait(device.getDevice(), k), device.getDevice(), "submitFrame");  // the image below is about to be rewritten
+    inFlight[k].assign((size_t)width * height * 4, 0.0f);
+    brt_render_opts o{};
+    o.width = width; o.height = height; o.spp = spp; o.flags = renderFlags;
+    bloon::check(brt_render_frame_async(device.getDevice(), &uniforms[k], &o, k, inFlight[k].data()), device.getDevice(), "submitFrame");
+  }
+  std::vector<float>& waitFrame(uint32_t frameIndex) {
+    bloon::check(brt_frame_wait(device.getDevice(), frameIndex % 2), device.getDevice(), "waitFrame");
+    return inFlight[frameIndex % 2];
+  }
+  void rebuildRenderOutput(Extent2D e) {  // RT/RTPipeline.cpp:49-55
+    brt_frame_wait(device.getDevice(), 0);
+    brt_frame_wait(device.getDevice(), 1);
+    extent = e;
+    storageImage.assign((size_t)e.width * e.height * 4, 0.0f);
+  }
   void updateTopLevelAS() {}                                                                                       // empty in the reference (RT/RTPipeline.cpp:57-59)
   std::vector<float>& getRenderOutput() { return storageImage; }  // linear RGBA32F, row-major (outImage, SH/raytracing.slang:132)
   brt_stats getStats() { brt_stats s{}; brt_get_stats(device.getDevice(), &s); return s; }
@@ -292,6 +313,7 @@ class Pipeline {
   Uniform uniforms[2]{};  // MAX_FRAMES_IN_FLIGHT = 2 (vulkan_core/SwapChain.h:8)
   uint32_t current = 0;
   std::vector<float> storageImage;
+  std::vector<float> inFlight[2];
 };
 
 }  // namespace RayTracing

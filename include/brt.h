@@ -212,6 +212,20 @@ BRT_API int brt_get_visibility(brt_context* ctx, uint8_t* out, uint32_t n);
  * major, alpha = 1) back to host memory — the reference's outImage (SH/raytracing.slang:132).
  * With tile_world > 1 only the pixels of this rank's tiles are written, the rest stays 0. */
 BRT_API int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, float* rgba_host);
+/* Frames in flight. The reference records frame k+1 while frame k is still on the GPU: MAX_FRAMES_IN_FLIGHT = 2
+ * (VK/SwapChain.h:8), one fence per frame slot waited in acquireNextImage (VK/SwapChain.cpp:45-60) and signalled by
+ * submitCommandBuffers (VK/SwapChain.cpp:92-131), one uniform buffer and descriptor set per slot
+ * (RT/RTPipeline.cpp:44-47, bindDescriptorSets(cmd, frameIndex)). brt_render_frame_async is that submit: it first waits
+ * for the slot's previous frame (the fence), enqueues the whole frame on the slot's own streams and buffers — including
+ * the copy to rgba_host (pinned memory for a truly asynchronous copy; NULL = leave it on the device) — and returns.
+ * brt_frame_wait(slot) returns when that frame and its copy are complete and folds its timings into brt_get_stats.
+ * The latency-bound tail of one frame's wavefronts then overlaps the head of the next one. Scene-changing calls
+ * (build, mesh update, Smart Culling) drain all slots first. Single-GPU contexts only (tile_world == 1). */
+#define BRT_FRAMES_IN_FLIGHT 2
+BRT_API int brt_render_frame_async(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, uint32_t slot, float* rgba_host);
+BRT_API int brt_frame_wait(brt_context* ctx, uint32_t slot);
+/* the cudaStream_t a slot's frame is enqueued on (slot 0: the context's stream), e.g. to order caller work after it */
+BRT_API void* brt_frame_stream(brt_context* ctx, uint32_t slot);
 /* Same, but leaves the result on the device: d_tiles (device pointer, may be NULL) receives this
  * rank's tiles packed tile-major (brt_tile_buffer_bytes bytes) for the NCCL gather. */
 BRT_API int brt_render_frame_tiles(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, void* d_tiles);
@@ -233,7 +247,7 @@ BRT_API int brt_gather_image_export(brt_context* ctx, uint32_t width, uint32_t h
 BRT_API int brt_gather_image_open(brt_context* ctx, const void* handles, uint32_t world);
 BRT_API int brt_render_frame_peers(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts);
 BRT_API void* brt_gather_image(brt_context* ctx);
-/* device pointer of the context's own full-frame RGBA32F image of the last frame */
+/* device pointer of the context's own full-frame RGBA32F image of the last frame (the slot last waited for) */
 BRT_API void* brt_device_image(brt_context* ctx);
 
 /* ---- test / measurement only ---------------------------------------------------------------- */

@@ -267,3 +267,44 @@ def general_transforms_and_many_lights(pkg, orc_mod, make):
     assert r["id_agreement"] == 1.0 and r["bit_exact"] and r["t_agreement"] == 1.0
     assert r["stats"].rays_occlusion > 16 * 1000
     return r
+
+
+def frames_in_flight(pkg, orc_mod, make):
+    """brt_render_frame_async / brt_frame_wait (the reference's MAX_FRAMES_IN_FLIGHT = 2, VK/SwapChain.h:8): frames
+    enqueued on the two slots, different cameras and sizes, give the bits of the synchronous call and of the oracle;
+    a scene change drains the slots."""
+    import ctypes as C
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    shapes = [(160, 90, 0), (128, 72, 3), (160, 90, 7), (96, 54, 1)]
+    uni = [scene.uniform(a, w, h, fr, 3) for (w, h, fr) in shapes]
+    for k, u in enumerate(uni):
+        u.viewInverse[3] += 0.3 * k  # move the eye sideways a little from frame to frame
+    ref = [b.render_frame(u, b.opts(w, h, 2, R | T | J)).copy() for u, (w, h, _) in zip(uni, shapes)]
+    out = [np.zeros((h, w, 4), np.float32) for (w, h, _) in shapes]
+    for k, (u, (w, h, _)) in enumerate(zip(uni, shapes)):
+        a.render_frame_async(u, a.opts(w, h, 2, R | T | J), k % 2, out[k].ctypes.data)  # waits for frame k-2 first
+    a.frame_wait(0)
+    a.frame_wait(1)
+    for k in range(len(shapes)):
+        assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), k
+    st = a.get_stats()
+    assert st.rays_closest > 0 and st.launches_total > 0
+    # statistics and AOVs refer to the frame waited for last (slot 1 = frame 3)
+    w, h, _ = shapes[3]
+    assert np.array_equal(a.get_aov(pkg.AOV_PRIM_ID, w, h), b.get_aov(pkg.AOV_PRIM_ID, w, h))
+    # a scene change between asynchronous frames: the build drains the frame in flight, the next frame sees the new scene
+    w, h, _ = shapes[0]
+    a.render_frame_async(uni[0], a.opts(w, h, 1, 0), 0, out[0].ctypes.data)
+    for api in (a, b):
+        api.light_create((0.0, -6.0, 0.0), (0.3, 0.9, 0.4), 30.0)
+        api.scene_build()
+    first = out[0].copy()  # complete: brt_scene_build waited for slot 0
+    a.render_frame_async(uni[0], a.opts(w, h, 1, 0), 1, out[2].ctypes.data)
+    a.frame_wait(1)
+    assert np.array_equal(out[2].view(np.uint32), b.render_frame(uni[0], b.opts(w, h, 1, 0)).view(np.uint32))
+    assert not np.array_equal(first, out[2])
+    with pytest.raises(pkg.BrtError):
+        a.render_frame_async(uni[0], a.opts(w, h, 1, 0), 2, None)  # slot out of range

@@ -28,9 +28,11 @@ def test_facade_compiles_and_fails_loudly_without_gpu(pkg, tmp_path):
 
 
 @pytest.mark.gpu
-def test_rtapp_demo_matches_oracle(pkg, orc_mod, tmp_path):
+@pytest.mark.parametrize("mode", ["sync", "async"])
+def test_rtapp_demo_matches_oracle(pkg, orc_mod, tmp_path, mode):
+    """sync: Pipeline::traceRays per frame; async: two frames in flight (Pipeline::submitFrame / waitFrame)."""
     exe = _build(tmp_path)
-    out = subprocess.run([exe, str(tmp_path / "out"), "2"], capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([exe, str(tmp_path / "out"), "2"] + (["async"] if mode == "async" else []), capture_output=True, text=True, check=True).stdout
     assert "rtapp_demo: 800x600" in out
     img = np.fromfile(tmp_path / "out.rgba32f", dtype=np.float32).reshape(600, 800, 4)
     scene = pkg.scenes.rtapp_demo()
