@@ -35,10 +35,10 @@ static void k_trace(const TraceParams p) {
   TraceCounters c{0, 0, 0};
   unsigned long long rays = 0;
   Traversal<ANY, COUNT> t;
-  uint2 stack[BRT_STACK_SIZE];
+  uint2 stack[BRT_STACK_ALLOC];
   for (uint32_t w = 0; w < n; ++w) {
     const uint32_t i = trace_slot(p, w);
-    if (!trace_load(p, i, t)) continue;
+    if (!trace_load(p, i, t, stack)) continue;
     rays++;
     while (!t.step(stack, c)) {}
     trace_store(p, i, t);
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const Trace
   TraceCounters c{0, 0, 0};
   uint32_t rays = 0;
   Traversal<ANY, COUNT> t;
-  uint2 stack[BRT_STACK_SIZE];
+  uint2 stack[BRT_STACK_ALLOC];
   bool active = false;
   bool exhausted = false;  // warp-uniform
   uint32_t ray = 0;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const Trace
         const uint32_t w = base + (uint32_t)__popc(idle & lt);
         if (w < n) {
           const uint32_t i = trace_slot(p, w);
-          if (trace_load(p, i, t)) {
+          if (trace_load(p, i, t, stack)) {
             active = true;
             ray = i;
             rays++;

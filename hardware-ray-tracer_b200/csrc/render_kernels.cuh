@@ -162,13 +162,13 @@ BRT_HD uint32_t trace_slot(const TraceParams& p, uint32_t w) {
 }
 // load ray i into a traversal; false for a padding slot (its miss is written right away)
 template <bool ANY, bool COUNT>
-BRT_HD bool trace_load(const TraceParams& p, uint32_t i, Traversal<ANY, COUNT>& t) {
+BRT_HD bool trace_load(const TraceParams& p, uint32_t i, Traversal<ANY, COUNT>& t, uint2* __restrict__ stack) {
   if (!ANY && p.px && p.px[i] == BRT_MISS) {
     p.hit_inst[i] = BRT_MISS;
     return false;
   }
   const float4 o = p.o[i], d = p.d[i];
-  t.init(p.tlas, p.insts, F3(o.x, o.y, o.z), F3(d.x, d.y, d.z), o.w, d.w);
+  t.init(stack, p.tlas, p.insts, F3(o.x, o.y, o.z), F3(d.x, d.y, d.z), o.w, d.w);
   return true;
 }
 template <bool ANY, bool COUNT>

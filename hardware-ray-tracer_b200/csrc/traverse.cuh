@@ -127,7 +127,6 @@ template <bool ANY, bool COUNT>
 struct Traversal {
   const Node8* tlas;
   const InstRec* insts;
-  f3 o, d;  // world ray
   float tmin;
   f3 co;    // origin in the current space (world, or the object space of cur_inst)
   RayBox rb;
@@ -139,14 +138,25 @@ struct Traversal {
   int sp, blas_sp;  // blas_sp >= 0 while inside a BLAS: stack height at entry
   bool found;
   Hit best;
-  // the stack itself (uint2[BRT_STACK_SIZE]) is a separate local array owned by the caller: keeping the
-  // dynamically indexed array out of this struct lets the compiler hold every other member in registers
+  // The stack (uint2[BRT_STACK_ALLOC]) is a separate local array owned by the caller: keeping the dynamically indexed
+  // array out of this struct lets the compiler hold every other member in registers. Its last three entries hold the
+  // WORLD ray (origin, direction): it is only needed when an instance is entered or left, so it lives in local memory
+  // instead of six registers (the kernel runs at the register limit of 7 blocks per SM).
+  static BRT_HDM void store_world(uint2* __restrict__ stack, f3 o_, f3 d_) {
+    stack[BRT_STACK_SIZE + 0] = make_uint2(f2u(o_.x), f2u(o_.y));
+    stack[BRT_STACK_SIZE + 1] = make_uint2(f2u(o_.z), f2u(d_.x));
+    stack[BRT_STACK_SIZE + 2] = make_uint2(f2u(d_.y), f2u(d_.z));
+  }
+  static BRT_HDM void load_world(const uint2* __restrict__ stack, f3& o_, f3& d_) {
+    const uint2 a = stack[BRT_STACK_SIZE + 0], b = stack[BRT_STACK_SIZE + 1], c = stack[BRT_STACK_SIZE + 2];
+    o_ = F3(u2f(a.x), u2f(a.y), u2f(b.x));
+    d_ = F3(u2f(b.y), u2f(c.x), u2f(c.y));
+  }
 
-  BRT_HDM void init(const Node8* tlas_, const InstRec* insts_, f3 o_, f3 d_, float tmin_, float tmax_) {
+  BRT_HDM void init(uint2* __restrict__ stack, const Node8* tlas_, const InstRec* insts_, f3 o_, f3 d_, float tmin_, float tmax_) {
     tlas = tlas_;
     insts = insts_;
-    o = o_;
-    d = d_;
+    store_world(stack, o_, d_);
     tmin = tmin_;
     best.t = tmax_;
     best.u = 0.0f;
@@ -204,6 +214,8 @@ struct Traversal {
         const float4 m0 = ldg4(&ir->w2o[0]), m1 = ldg4(&ir->w2o[1]), m2 = ldg4(&ir->w2o[2]);
         const uint4 tail = ldg4(reinterpret_cast<const uint4*>(&ir->kind));
         const float4 m[3] = {m0, m1, m2};
+        f3 o, d;
+        load_world(stack, o, d);
         const f3 oo = xform_point(m, o), od = xform_dir(m, d);
         if (tail.x == 1u) {  // analytic sphere
           const float4 s = ldg4(&ir->sphere);
@@ -238,7 +250,8 @@ struct Traversal {
       if (blas_sp >= 0 && sp == blas_sp) {  // BLAS exhausted: back to the world ray
         blas_sp = -1;
         nodes = tlas;
-        co = o;
+        f3 d;
+        load_world(stack, co, d);
         rb = make_raybox(d);
       }
       if (sp == 0) return true;
