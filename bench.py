@@ -253,7 +253,7 @@ def run_product(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
-    def timed_pipelined(to_host, steps, warmup, collect=None):
+    def timed_pipelined(to_host, steps, warmup, collect=None, opts=opts):
         """N = 1 product schedule: two frames in flight (brt_render_frame_async / brt_frame_wait — the reference's
         MAX_FRAMES_IN_FLIGHT = 2, VK/SwapChain.h:8). K frames are enqueued alternately on the two frame slots; ONE timed
         region brackets all K steps (synchronize on both sides, CUDA events on the slots' streams). The L2 flush (a write
@@ -319,6 +319,9 @@ def run_product(args):
         ms_e2e = timed_pipelined(True, args.steps, max(2, args.warmup // 2))
         # one frame alone, nothing else in flight: the latency a single brt_render_frame call sees
         frame_latency = {"device_ms": timed(step_device, min(args.steps, 5), 1), "e2e_ms": timed(step_e2e, min(args.steps, 5), 1)}
+        # the same end-to-end step with the framebuffer in the 8-bit swapchain format the reference presents (B8G8R8A8_UNORM):
+        # conversion kernel on the GPU, 4 bytes per pixel over PCIe instead of 16
+        ms_e2e_bgra8 = timed_pipelined(True, args.steps, 2, opts=ctx.opts(w, h, spp, flags | pkg.render_format(pkg.FORMAT_BGRA8_UNORM)))
     else:
         ms_dev = timed(step_device, args.steps, args.warmup, count_launches)
         clocks = sampler.stop() if sampler else None
@@ -408,6 +411,8 @@ def run_product(args):
                  "schedule": "K frames alternate over 2 frame slots (brt_render_frame_async / brt_frame_wait, as the reference's "
                              "MAX_FRAMES_IN_FLIGHT = 2); one timed region around all K steps"} if pipelined else {"frames_in_flight": 1})),
             "rays_per_step": int(rays), "single_frame_latency": frame_latency,
+            "e2e_bgra8": ({"value": rays / (ms_e2e_bgra8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e_bgra8,
+                           "d2h_bytes_per_step": w * h * 4, "format": "B8G8R8A8_UNORM"} if pipelined else None),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 140 + 32,
                     "d2h_bytes_per_step": w * h * 16},
             "gpu_launches": int(launches["n"]),

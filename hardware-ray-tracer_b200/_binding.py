@@ -64,6 +64,13 @@ CFG_NO_TREELET = 2
 CFG_TREELET_ON_REBUILD = 4
 CFG_NO_OVERLAP = 8
 BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY = 1, 2, 4, 8, 16
+FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_BGRA8_UNORM, FORMAT_RGBA8_SRGB, FORMAT_BGRA8_SRGB = 0, 1, 2, 3, 4
+FORMAT_SHIFT, FORMAT_MASK = 8, 0x700
+
+
+def render_format(fmt):
+    """flag bits selecting the output format of the render entry points (BRT_RENDER_FORMAT)"""
+    return fmt << FORMAT_SHIFT
 AOV_PRIM_ID, AOV_INST_ID, AOV_HIT_T = 0, 1, 2
 AOV_MISS = 0xFFFFFFFF
 
@@ -75,7 +82,7 @@ BRT_SYMBOLS = [
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
-    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream",
+    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs",
 ]
 
 
@@ -130,6 +137,7 @@ class SceneApi:
             "trace_rays": (C.c_int, [vp, P(f32), u32, C.c_int, P(u32)]),
             "debug_sort_pairs": (C.c_int, [vp, P(u32), P(u32), u32, C.c_int]),
             "camera_uniform": (None, [P(f32), P(f32), f32, f32, f32, f32, u32, u32, P(Uniform)]),
+            "camera_handle_inputs": (None, [u32, f32, P(f32), P(f32)]),
         }
         device_side = {  # entry points that take device pointers / streams
             "set_stream": (C.c_int, [vp, vp]),
@@ -246,6 +254,12 @@ class SceneApi:
         self._f("camera_uniform")((f32 * 3)(*pos), (f32 * 3)(*rot), fovy, aspect, znear, zfar, frame, depth_max, C.byref(u))
         return u
 
+    def camera_handle_inputs(self, keys, dt, position, rotation):
+        """Camera::handleInputs (Graphics/Camera.cpp:26-61): returns the updated (position, rotation)."""
+        p, r = (f32 * 3)(*position), (f32 * 3)(*rotation)
+        self._f("camera_handle_inputs")(keys, dt, p, r)
+        return np.array(p, dtype=np.float32), np.array(r, dtype=np.float32)
+
     @staticmethod
     def opts(width, height, spp=1, flags=0, crop=None):
         o = RenderOpts(width, height, spp, flags, 0, 0, 0, 0)
@@ -254,11 +268,12 @@ class SceneApi:
         return o
 
     def render_frame(self, uniform, opts, out=None, want_image=True):
-        """Returns the RGBA32F image as an (h, w, 4) array (or None with want_image=False)."""
+        """Returns the image as an (h, w, 4) array — float32, or uint8 when opts.flags carries an 8-bit BRT_RENDER_FORMAT —
+        (or None with want_image=False)."""
         ptr = None
         if want_image:
             if out is None:
-                out = np.zeros((opts.height, opts.width, 4), dtype=np.float32)
+                out = np.zeros((opts.height, opts.width, 4), dtype=np.uint8 if opts.flags & FORMAT_MASK else np.float32)
             ptr = out.ctypes.data_as(C.c_void_p)
         self._ck(self._f("render_frame")(self.ctx, C.byref(uniform), C.byref(opts), ptr))
         return out

@@ -26,6 +26,7 @@ BRT_KERNEL_1D(k_accumulate, AccumParams, accumulate_body)
 BRT_KERNEL_1D(k_sum_samples, SumSamplesParams, sum_samples_body)
 BRT_KERNEL_1D(k_resolve, ResolveParams, resolve_body)
 BRT_KERNEL_1D(k_untile, UntileParams, untile_body)
+BRT_KERNEL_1D(k_present, PresentParams, present_body)
 BRT_KERNEL_1D(k_cull, CullParams, cull_body)
 
 #ifdef BRT_EMU
@@ -182,6 +183,7 @@ struct FrameSlot {
   uint64_t frame_key[4] = {0, 0, 0, 0};
   uint32_t frame_w = 0, frame_h = 0;
   DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
+  DevBuf d_image8;  // the frame in an 8-bit present format (BRT_RENDER_FORMAT)
   DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   std::deque<EventPair> events;  // deque: references stay valid while the pool grows
   size_t events_used = 0;
@@ -735,6 +737,17 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
     BRT_CHECK_LAUNCH();
     launches++;
   }
+  const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
+  if (format > BRT_FORMAT_B8G8R8A8_SRGB) invalid("render_frame: unknown BRT_RENDER_FORMAT");
+  if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {
+    if (c->tile_world > 1) invalid("render_frame: 8-bit output formats need tile_world == 1");
+    f->d_image8.ensure(npx * 4);
+    PresentParams pp{(uint32_t)npx, nullptr, format, f->d_image.as<float4>(), f->d_image8.as<uint32_t>()};
+    Timed t(f, CLS_RESOLVE, s);
+    BRT_LAUNCH_1D(k_present, pp, grid_for(c, (uint32_t)npx, 256, 8), 256, s);
+    BRT_CHECK_LAUNCH();
+    launches++;
+  }
   BRT_CUDA(cudaEventRecord(whole.b, s));
   if (!rounds) BRT_CUDA(cudaEventRecord(f->ev_head, s));
   c->prev_head = f->ev_head;
@@ -790,6 +803,13 @@ void finish_frame(brt_context* c, FrameSlot* f) {
   st.ms_resolve = ms[CLS_RESOLVE];
   st.ms_total = ms[CLS_COUNT];
   c->last_slot = (uint32_t)(f - c->slots);
+}
+
+// the frame's image to host memory in the format the caller asked for, on the frame's stream
+void copy_out(FrameSlot* f, const brt_render_opts& o, void* host) {
+  const size_t npx = (size_t)o.width * o.height;
+  if (o.flags & BRT_RENDER_FORMAT_MASK) BRT_CUDA(cudaMemcpyAsync(host, f->d_image8.ptr(), npx * 4, cudaMemcpyDeviceToHost, f->stream));
+  else BRT_CUDA(cudaMemcpyAsync(host, f->d_image.ptr(), npx * 16, cudaMemcpyDeviceToHost, f->stream));
 }
 
 // scene changes (builds, uploads, culling) and the synchronous entry points first drain every frame in flight
@@ -1117,8 +1137,7 @@ int brt_render_frame(brt_context* c, const brt_uniform* u, const brt_render_opts
     FrameSlot* f = &c->slots[0];
     ensure_slot(c, f);
     render_frame_device(c, f, *u, *o, nullptr);
-    if (rgba_host)
-      BRT_CUDA(cudaMemcpyAsync(rgba_host, f->d_image.ptr(), (size_t)o->width * o->height * 16, cudaMemcpyDeviceToHost, f->stream));
+    if (rgba_host) copy_out(f, *o, rgba_host);
     finish_frame(c, f);
   });
 }
@@ -1135,8 +1154,7 @@ int brt_render_frame_async(brt_context* c, const brt_uniform* u, const brt_rende
     if (c->tables_dirty || c->tlas_dirty) wait_all_frames(c);  // the scene tables are about to be rewritten
     ensure_slot(c, f);
     render_frame_device(c, f, *u, *o, nullptr);
-    if (rgba_host)
-      BRT_CUDA(cudaMemcpyAsync(rgba_host, f->d_image.ptr(), (size_t)o->width * o->height * 16, cudaMemcpyDeviceToHost, f->stream));
+    if (rgba_host) copy_out(f, *o, rgba_host);
   });
 }
 
@@ -1440,6 +1458,43 @@ void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, floa
   out->frame = frame;
   out->depthMax = depth_max;
   out->lightThreshold = 0.0001f;
+}
+
+// Camera::handleInputs (Graphics/Camera.cpp:26-61) with the key state passed in instead of polled from GLFW.
+void brt_camera_handle_inputs(uint32_t keys, float dt, float position[3], float rotation[3]) {
+  auto key = [&](uint32_t k) { return (keys & k) != 0u; };
+  const float eps = 1.1920929e-07f;  // std::numeric_limits<float>::epsilon()
+  float rx = 0.0f, ry = 0.0f;
+  if (key(BRT_KEY_LOOK_RIGHT)) ry += 1.0f;
+  if (key(BRT_KEY_LOOK_LEFT)) ry -= 1.0f;
+  if (key(BRT_KEY_LOOK_UP)) rx += 1.0f;
+  if (key(BRT_KEY_LOOK_DOWN)) rx -= 1.0f;
+  const float rr = rx * rx + ry * ry;
+  if (rr > eps) {
+    const float inv = 1.0f / std::sqrt(rr);
+    rotation[0] += 1.5f * dt * (rx * inv);
+    rotation[1] += 1.5f * dt * (ry * inv);
+  }
+  rotation[0] = std::fmin(std::fmax(rotation[0], -1.5f), 1.5f);
+  const float two_pi = 6.28318530717958647692f;
+  rotation[1] = rotation[1] - two_pi * std::floor(rotation[1] / two_pi);  // glm::mod
+  const float yaw = rotation[1];
+  const float fwd[3] = {std::sin(yaw), 0.0f, std::cos(yaw)};
+  const float right[3] = {fwd[2], 0.0f, -fwd[0]};
+  const float up[3] = {0.0f, -1.0f, 0.0f};
+  float mv[3] = {0.0f, 0.0f, 0.0f};
+  auto add = [&](const float* d, float sgn) { for (int k = 0; k < 3; ++k) mv[k] += sgn * d[k]; };
+  if (key(BRT_KEY_MOVE_FORWARD)) add(fwd, 1.0f);
+  if (key(BRT_KEY_MOVE_BACKWARD)) add(fwd, -1.0f);
+  if (key(BRT_KEY_MOVE_RIGHT)) add(right, 1.0f);
+  if (key(BRT_KEY_MOVE_LEFT)) add(right, -1.0f);
+  if (key(BRT_KEY_MOVE_UP)) add(up, 1.0f);
+  if (key(BRT_KEY_MOVE_DOWN)) add(up, -1.0f);
+  const float mm = mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2];
+  if (mm > eps) {
+    const float inv = 1.0f / std::sqrt(mm);
+    for (int k = 0; k < 3; ++k) position[k] += 3.0f * dt * (mv[k] * inv);
+  }
 }
 
 }  // extern "C"

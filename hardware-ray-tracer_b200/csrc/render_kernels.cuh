@@ -461,6 +461,25 @@ BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
     for (uint32_t k = 0; k < p.n_peers; ++k) p.peers[k][(size_t)y * p.map.width + x] = out;  // st.global to mapped peer pointers
 }
 
+// ---- present: the render output in the swapchain's format (RT/RTPipeline.cpp:49-55, RT/RTApp.cpp:87-152) ---------
+struct PresentParams {
+  uint32_t count;  // width * height
+  const uint32_t* count_ptr;
+  uint32_t format;  // BRT_FORMAT_*
+  const float4* image;
+  uint32_t* image8;  // one packed texel per pixel, byte 0 first in memory
+};
+BRT_HD void present_body(const PresentParams& p, uint32_t i) {
+  const float4 c = p.image[i];
+  const bool srgb = p.format == BRT_FORMAT_R8G8B8A8_SRGB || p.format == BRT_FORMAT_B8G8R8A8_SRGB;
+  const bool bgra = p.format == BRT_FORMAT_B8G8R8A8_UNORM || p.format == BRT_FORMAT_B8G8R8A8_SRGB;
+  const uint32_t r = float_to_unorm8(srgb ? linear_to_srgb(c.x) : c.x);
+  const uint32_t g = float_to_unorm8(srgb ? linear_to_srgb(c.y) : c.y);
+  const uint32_t b = float_to_unorm8(srgb ? linear_to_srgb(c.z) : c.z);
+  const uint32_t a = float_to_unorm8(c.w);
+  p.image8[i] = (bgra ? b : r) | (g << 8) | ((bgra ? r : b) << 16) | (a << 24);
+}
+
 // ---- un-tile after the framebuffer gather (root rank) ----------------------------------------------------
 struct UntileParams {
   uint32_t count;  // width * height

@@ -127,6 +127,32 @@ BRT_HD float det_log2(float x) {
   float ln_m = (2.0f * t) * p;
   return (float)e + ln_m * 1.44269502f;
 }
+// exp2 for |y| <= 120: y = k + f with k = floor(y + 1/2), f in [-1/2, 1/2); e^(f ln 2) by its series to z^7, scaled by 2^k
+// through the exponent field. (exp2 / pow are implementation-defined in SPIR-V; the spec here fixes them)
+BRT_HD float det_exp2(float y) {
+  const float kf = floorf(y + 0.5f);
+  const float z = (y - kf) * 0.693147182f;
+  float p = fma_rn(z, 1.98412701e-4f, 1.38888892e-3f);
+  p = fma_rn(p, z, 8.33333377e-3f);
+  p = fma_rn(p, z, 4.16666679e-2f);
+  p = fma_rn(p, z, 0.166666672f);
+  p = fma_rn(p, z, 0.5f);
+  p = fma_rn(p, z, 1.0f);
+  p = fma_rn(p, z, 1.0f);
+  return u2f(f2u(p) + ((uint32_t)(int)kf << 23));
+}
+// Storage-image format conversion of the present path (Pipeline::rebuildRenderOutput(format, extent), RT/RTPipeline.cpp:49-55;
+// copyImageToSwapchain, RT/RTApp.cpp:87-152). UNORM8: clamp to [0, 1] (NaN -> 0), scale by 255, round to nearest even.
+// SRGB: the sRGB transfer function first (alpha stays linear).
+BRT_HD uint32_t float_to_unorm8(float f) {
+  const float c = f > 0.0f ? (f < 1.0f ? f : 1.0f) : 0.0f;  // NaN fails f > 0
+  return (uint32_t)rintf(c * 255.0f);
+}
+BRT_HD float linear_to_srgb(float c) {
+  if (!(c > 0.0031308f)) return c > 0.0f ? c * 12.92f : 0.0f;
+  if (c >= 1.0f) return 1.0f;
+  return 1.055f * det_exp2(det_log2(c) * 0.416666657f) - 0.055f;
+}
 // pow(x, 5) := (x*x)*(x*x)*x   (SH/disney.slang:11)
 BRT_HD float pow5(float x) {
   float x2 = x * x;

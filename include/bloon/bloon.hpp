@@ -56,13 +56,21 @@ class Device {
 };
 
 // Core::Camera (GFX/Camera.h:8-17): setView / setPerspectiveProjection keep the reference's conventions
-// (Y down, +Z forward, Tait-Bryan Y-X-Z, Vulkan 0..1 depth). handleInputs (GLFW) is out of scope.
+// (Y down, +Z forward, Tait-Bryan Y-X-Z, Vulkan 0..1 depth). handleInputs takes the key state as a BRT_KEY_* mask instead of a
+// GLFWwindow to poll.
 class Camera {
  public:
   void setPerspectiveProjection(float fovy, float aspectRatio, float near_, float far_) {
     fovy_ = fovy; aspect_ = aspectRatio; near_z_ = near_; far_z_ = far_;
   }
   void setView(bloon::vec3 position, bloon::vec3 rotation) { position_ = position; rotation_ = rotation; }
+  // Camera::handleInputs(GLFWwindow*, float dt), Graphics/Camera.cpp:26-61 — keys = BRT_KEY_* bits of the pressed keys
+  void handleInputs(uint32_t keys, float dt) {
+    float p[3] = {position_.x, position_.y, position_.z}, r[3] = {rotation_.x, rotation_.y, rotation_.z};
+    brt_camera_handle_inputs(keys, dt, p, r);
+    position_ = bloon::vec3(p[0], p[1], p[2]);
+    rotation_ = bloon::vec3(r[0], r[1], r[2]);
+  }
   bloon::vec3 getPosition() const { return position_; }
   bloon::vec3 getRotation() const { return rotation_; }
   // glm-style column-major matrices (GFX/Camera.cpp:8-17, 71-95)
@@ -277,8 +285,9 @@ class Pipeline {
   void traceRays(uint32_t width, uint32_t height, uint32_t /*depth*/ = 1, uint32_t spp = 1, uint32_t renderFlags = 0) {
     if (width != extent.width || height != extent.height) rebuildRenderOutput({width, height});
     brt_render_opts o{};
-    o.width = width; o.height = height; o.spp = spp; o.flags = renderFlags;
-    bloon::check(brt_render_frame(device.getDevice(), &uniforms[current], &o, storageImage.data()), device.getDevice(), "traceRays");
+    o.width = width; o.height = height; o.spp = spp; o.flags = renderFlags | BRT_RENDER_FORMAT(format);
+    void* dst = format == BRT_FORMAT_R32G32B32A32_SFLOAT ? (void*)storageImage.data() : (void*)storageImage8.data();
+    bloon::check(brt_render_frame(device.getDevice(), &uniforms[current], &o, static_cast<float*>(dst)), device.getDevice(), "traceRays");
   }
   // Two frames in flight, as RTApp::beginFrame / endFrame over SwapChain::MAX_FRAMES_IN_FLIGHT = 2 (RT/RTApp.cpp:171-212,
   // vulkan_core/SwapChain.h:8): submitFrame(frameIndex) = bindDescriptorSets(cmd, frameIndex) + traceRays + submitCommandBuffers
@@ -296,12 +305,18 @@ class Pipeline {
     bloon::check(brt_frame_wait(device.getDevice(), frameIndex % 2), device.getDevice(), "waitFrame");
     return inFlight[frameIndex % 2];
   }
-  void rebuildRenderOutput(Extent2D e) {  // RT/RTPipeline.cpp:49-55
+  void rebuildRenderOutput(Extent2D e) { rebuildRenderOutput(format, e); }
+  // Pipeline::rebuildRenderOutput(VkFormat format, VkExtent2D extent), RT/RTPipeline.cpp:49-55: the storage image is created in the
+  // swapchain's format (BRT_FORMAT_*: R32G32B32A32_SFLOAT, or an 8-bit RGBA / BGRA UNORM / SRGB format)
+  void rebuildRenderOutput(uint32_t fmt, Extent2D e) {
     brt_frame_wait(device.getDevice(), 0);
     brt_frame_wait(device.getDevice(), 1);
     extent = e;
-    storageImage.assign((size_t)e.width * e.height * 4, 0.0f);
+    format = fmt;
+    storageImage.assign(fmt == BRT_FORMAT_R32G32B32A32_SFLOAT ? (size_t)e.width * e.height * 4 : 0, 0.0f);
+    storageImage8.assign(fmt == BRT_FORMAT_R32G32B32A32_SFLOAT ? 0 : (size_t)e.width * e.height * 4, 0);
   }
+  std::vector<uint8_t>& getRenderOutput8() { return storageImage8; }  // the 8-bit formats: 4 bytes per texel, row-major
   void updateTopLevelAS() {}                                                                                       // empty in the reference (RT/RTPipeline.cpp:57-59)
   std::vector<float>& getRenderOutput() { return storageImage; }  // linear RGBA32F, row-major (outImage, SH/raytracing.slang:132)
   brt_stats getStats() { brt_stats s{}; brt_get_stats(device.getDevice(), &s); return s; }
@@ -312,7 +327,9 @@ class Pipeline {
   Scene& scene;
   Uniform uniforms[2]{};  // MAX_FRAMES_IN_FLIGHT = 2 (vulkan_core/SwapChain.h:8)
   uint32_t current = 0;
+  uint32_t format = BRT_FORMAT_R32G32B32A32_SFLOAT;
   std::vector<float> storageImage;
+  std::vector<uint8_t> storageImage8;
   std::vector<float> inFlight[2];
 };
 

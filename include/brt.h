@@ -129,10 +129,22 @@ typedef struct brt_config {
 #define BRT_RENDER_JITTER 8u         /* use the sub-pixel jitter the shader computes but drops (SH/raytracing.slang:96-98) */
 #define BRT_RENDER_SKY 16u           /* miss returns a sky gradient instead of black (SH/raytracing.slang:173-176) */
 
+/* Output format of the image handed back by the render entry points (bits 8..10 of brt_render_opts.flags): the format
+ * Pipeline::rebuildRenderOutput(format, extent) creates the storage image in — the swapchain's (RT/RTPipeline.cpp:49-55,
+ * VK/SwapChain.cpp:384-392 prefers R32G32B32A32_SFLOAT and falls back to what the surface offers, in practice 8-bit BGRA) —
+ * so that copyImageToSwapchain (RT/RTApp.cpp:87-152) is a plain copy. 8-bit formats: 4 bytes per pixel; UNORM = clamp to
+ * [0, 1], x255, round to nearest even; SRGB additionally applies the sRGB transfer function to R, G, B. The conversion runs
+ * on the GPU after the resolve; the library keeps the linear RGBA32F image as well (brt_device_image, AOVs). */
+enum { BRT_FORMAT_R32G32B32A32_SFLOAT = 0, BRT_FORMAT_R8G8B8A8_UNORM = 1, BRT_FORMAT_B8G8R8A8_UNORM = 2,
+       BRT_FORMAT_R8G8B8A8_SRGB = 3, BRT_FORMAT_B8G8R8A8_SRGB = 4 };
+#define BRT_RENDER_FORMAT_SHIFT 8
+#define BRT_RENDER_FORMAT_MASK 0x700u
+#define BRT_RENDER_FORMAT(fmt) ((uint32_t)(fmt) << BRT_RENDER_FORMAT_SHIFT)
+
 typedef struct brt_render_opts {
   uint32_t width, height;   /* vkCmdTraceRaysKHR(w, h, 1), RT/RTPipeline.cpp:41-43 */
   uint32_t spp;             /* SAMPLES (SH/constants.slang:23-25); sample s uses frame + s as RNG frame */
-  uint32_t flags;           /* BRT_RENDER_* */
+  uint32_t flags;           /* BRT_RENDER_* | BRT_RENDER_FORMAT(BRT_FORMAT_*) */
   uint32_t crop_x0, crop_y0, crop_w, crop_h; /* crop_w == 0: whole image; else only this window is traced */
 } brt_render_opts;
 
@@ -208,8 +220,9 @@ BRT_API int brt_smart_cull(brt_context* ctx, const brt_uniform* u, uint32_t widt
 BRT_API int brt_get_visibility(brt_context* ctx, uint8_t* out, uint32_t n);
 
 /* ---- render-frame entry (Pipeline::writeToUniformBuffer + traceRays, RT/RTPipeline.cpp:41-47) - */
-/* Traces the frame and, when rgba_host != NULL, copies the linear RGBA32F image (w*h*16 bytes, row
- * major, alpha = 1) back to host memory — the reference's outImage (SH/raytracing.slang:132).
+/* Traces the frame and, when rgba_host != NULL, copies the image back to host memory — the reference's outImage
+ * (SH/raytracing.slang:132): linear RGBA32F (w*h*16 bytes, row major, alpha = 1) by default, or w*h*4 bytes in the 8-bit
+ * format selected with BRT_RENDER_FORMAT (tile_world == 1 only).
  * With tile_world > 1 only the pixels of this rank's tiles are written, the rest stays 0. */
 BRT_API int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, float* rgba_host);
 /* Frames in flight. The reference records frame k+1 while frame k is still on the GPU: MAX_FRAMES_IN_FLIGHT = 2
@@ -270,6 +283,21 @@ BRT_API int brt_debug_sort_pairs(brt_context* ctx, uint32_t* keys_host, uint32_t
  * depthMax} (RT/RTApp.cpp:44-49). rot = (pitch x, yaw y, roll z), Tait-Bryan Y-X-Z. Pure host code. */
 BRT_API void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar,
                         uint32_t frame, uint32_t depth_max, brt_uniform* out);
+
+/* Camera::handleInputs (Graphics/Camera.cpp:26-61) with the key state as a bit mask instead of glfwGetKey: arrow keys turn the
+ * camera at 1.5 rad/s (pitch clamped to +-1.5, yaw wrapped to [0, 2 pi)), W/S/D/A/E/Q move it at 3 units/s along the yaw-forward,
+ * right and up (0,-1,0) axes. Updates position and rotation in place. Pure host code. */
+#define BRT_KEY_MOVE_LEFT 1u      /* GLFW_KEY_A, Graphics/Camera.h:24-35 */
+#define BRT_KEY_MOVE_RIGHT 2u     /* D */
+#define BRT_KEY_MOVE_FORWARD 4u   /* W */
+#define BRT_KEY_MOVE_BACKWARD 8u  /* S */
+#define BRT_KEY_MOVE_UP 16u       /* E */
+#define BRT_KEY_MOVE_DOWN 32u     /* Q */
+#define BRT_KEY_LOOK_RIGHT 64u    /* arrow keys */
+#define BRT_KEY_LOOK_LEFT 128u
+#define BRT_KEY_LOOK_UP 256u
+#define BRT_KEY_LOOK_DOWN 512u
+BRT_API void brt_camera_handle_inputs(uint32_t keys, float dt, float position[3], float rotation[3]);
 
 #ifdef __cplusplus
 }

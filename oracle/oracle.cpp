@@ -620,10 +620,34 @@ int orc_get_visibility(orc_context* c, uint8_t* out, uint32_t n) {
   return BRT_OK;
 }
 
-int orc_render_frame(orc_context* c, const brt_uniform* u, const brt_render_opts* o, float* rgba) {
-  if (!c || !u || !o || !rgba || !o->width || !o->height || !o->spp) return fail(c, BRT_ERR_INVALID, "render_frame: bad arguments");
+// rebuildRenderOutput(format, extent) + copyImageToSwapchain (RT/RTPipeline.cpp:49-55, RT/RTApp.cpp:87-152): the linear frame
+// stored in an 8-bit swapchain format, one packed texel per pixel
+static void present_convert(const float* rgba, size_t npx, uint32_t format, uint8_t* out) {
+  const bool srgb = format == BRT_FORMAT_R8G8B8A8_SRGB || format == BRT_FORMAT_B8G8R8A8_SRGB;
+  const bool bgra = format == BRT_FORMAT_B8G8R8A8_UNORM || format == BRT_FORMAT_B8G8R8A8_SRGB;
+  for (size_t i = 0; i < npx; ++i) {
+    const float* px = rgba + 4 * i;
+    uint32_t ch[3];
+    for (int k = 0; k < 3; ++k) ch[k] = float_to_unorm8(srgb ? linear_to_srgb(px[k]) : px[k]);
+    out[4 * i + 0] = (uint8_t)(bgra ? ch[2] : ch[0]);
+    out[4 * i + 1] = (uint8_t)ch[1];
+    out[4 * i + 2] = (uint8_t)(bgra ? ch[0] : ch[2]);
+    out[4 * i + 3] = (uint8_t)float_to_unorm8(px[3]);
+  }
+}
+
+int orc_render_frame(orc_context* c, const brt_uniform* u, const brt_render_opts* o, float* rgba_out) {
+  if (!c || !u || !o || !rgba_out || !o->width || !o->height || !o->spp) return fail(c, BRT_ERR_INVALID, "render_frame: bad arguments");
   if (!c->built) return fail(c, BRT_ERR_STATE, "render_frame: scene not built");
   size_t npx = (size_t)o->width * o->height;
+  const uint32_t format = (o->flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
+  if (format > BRT_FORMAT_B8G8R8A8_SRGB) return fail(c, BRT_ERR_INVALID, "render_frame: unknown BRT_RENDER_FORMAT");
+  std::vector<float> linear;
+  float* rgba = rgba_out;
+  if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {
+    linear.resize(npx * 4);
+    rgba = linear.data();
+  }
   c->fw = o->width;
   c->fh = o->height;
   c->aov_prim.assign(npx, BRT_AOV_MISS);
@@ -665,6 +689,7 @@ int orc_render_frame(orc_context* c, const brt_uniform* u, const brt_render_opts
   c->stats.nodes_visited_occlusion = s.nodes_o;
   c->stats.prims_tested_occlusion = s.prims_o;
   c->stats.spheres_tested_occlusion = s.sph_o;
+  if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) present_convert(rgba, npx, format, reinterpret_cast<uint8_t*>(rgba_out));
   return BRT_OK;
 }
 
@@ -756,6 +781,37 @@ float orc_kat_log2(float x) { return det_log2(x); }
 int orc_kat_intersect_tri(const float o[3], const float d[3], float tmin, float tmax, const float v0[3], const float v1[3], const float v2[3], float tuv[3]) {
   RayShear s = make_shear(V3(d[0], d[1], d[2]));
   return intersect_tri(V3(o[0], o[1], o[2]), s, tmin, tmax, V3(v0[0], v0[1], v0[2]), V3(v1[0], v1[1], v1[2]), V3(v2[0], v2[1], v2[2]), tuv[0], tuv[1], tuv[2]) ? 1 : 0;
+}
+
+// Camera::handleInputs (Graphics/Camera.cpp:26-61), GLFW polling replaced by a key mask (bits as BRT_KEY_*)
+void orc_camera_handle_inputs(uint32_t keys, float dt, float position[3], float rotation[3]) {
+  vec3 rotate = V3(0.0f);
+  if (keys & BRT_KEY_LOOK_RIGHT) rotate.y += 1.f;                                   // :29
+  if (keys & BRT_KEY_LOOK_LEFT) rotate.y -= 1.f;                                    // :30
+  if (keys & BRT_KEY_LOOK_UP) rotate.x += 1.f;                                      // :32
+  if (keys & BRT_KEY_LOOK_DOWN) rotate.x -= 1.f;                                    // :33
+  vec3 rot = V3(rotation[0], rotation[1], rotation[2]);
+  if (dot(rotate, rotate) > std::numeric_limits<float>::epsilon())                  // :35-36
+    rot = rot + (rotate * (1.0f / std::sqrt(dot(rotate, rotate)))) * (1.5f * dt);
+  rot.x = std::fmin(std::fmax(rot.x, -1.5f), 1.5f);                                 // :38
+  const float two_pi = 6.28318530717958647692f;
+  rot.y = rot.y - two_pi * std::floor(rot.y / two_pi);                              // :39 glm::mod
+  float yaw = rot.y;
+  const vec3 forwardDir = V3(std::sin(yaw), 0.f, std::cos(yaw));                    // :42
+  const vec3 rightDir = V3(forwardDir.z, 0.f, -forwardDir.x);                       // :43
+  const vec3 upDir = V3(0.0f, -1.0f, 0.0f);                                         // :44
+  vec3 moveDir = V3(0.0f);
+  if (keys & BRT_KEY_MOVE_FORWARD) moveDir = moveDir + forwardDir;                  // :48-58
+  if (keys & BRT_KEY_MOVE_BACKWARD) moveDir = moveDir - forwardDir;
+  if (keys & BRT_KEY_MOVE_RIGHT) moveDir = moveDir + rightDir;
+  if (keys & BRT_KEY_MOVE_LEFT) moveDir = moveDir - rightDir;
+  if (keys & BRT_KEY_MOVE_UP) moveDir = moveDir + upDir;
+  if (keys & BRT_KEY_MOVE_DOWN) moveDir = moveDir - upDir;
+  vec3 pos = V3(position[0], position[1], position[2]);
+  if (dot(moveDir, moveDir) > std::numeric_limits<float>::epsilon())                // :60-61
+    pos = pos + (moveDir * (1.0f / std::sqrt(dot(moveDir, moveDir)))) * (3.f * dt);
+  position[0] = pos.x; position[1] = pos.y; position[2] = pos.z;
+  rotation[0] = rot.x; rotation[1] = rot.y; rotation[2] = rot.z;
 }
 
 void orc_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar, uint32_t frame,

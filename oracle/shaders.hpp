@@ -109,6 +109,36 @@ static inline float det_log2(float x) {
   float ln_m = (2.0f * t) * p;
   return (float)e + ln_m * 1.44269502f;
 }
+// exp2 for |y| <= 120 (implementation-defined in SPIR-V, fixed by DESIGN.md §3): y = k + f, k = floor(y + 1/2);
+// e^(f ln 2) by the exponential series to the 7th power, times 2^k through the exponent bits.
+static inline float det_exp2(float y) {
+  float kf = std::floor(y + 0.5f);
+  float z = (y - kf) * 0.693147182f;
+  float p = std::fma(z, 1.98412701e-4f, 1.38888892e-3f);
+  p = std::fma(p, z, 8.33333377e-3f);
+  p = std::fma(p, z, 4.16666679e-2f);
+  p = std::fma(p, z, 0.166666672f);
+  p = std::fma(p, z, 0.5f);
+  p = std::fma(p, z, 1.0f);
+  p = std::fma(p, z, 1.0f);
+  uint32_t bits;
+  std::memcpy(&bits, &p, 4);
+  bits += (uint32_t)((int)kf) << 23;
+  std::memcpy(&p, &bits, 4);
+  return p;
+}
+// Present path: what storing a float4 into a storage image of the swapchain's format does (Pipeline::rebuildRenderOutput(format,
+// extent), RT/RTPipeline.cpp:49-55; the image is then copied texel by texel, RT/RTApp.cpp:87-152). Vulkan's float -> UNORM8
+// conversion: clamp to [0, 1] (NaN -> 0), x 255, round to nearest even; SRGB formats encode R, G, B with the sRGB curve first.
+static inline uint32_t float_to_unorm8(float f) {
+  float c = f > 0.0f ? (f < 1.0f ? f : 1.0f) : 0.0f;
+  return (uint32_t)std::nearbyint(c * 255.0f);
+}
+static inline float linear_to_srgb(float c) {
+  if (!(c > 0.0031308f)) return c > 0.0f ? c * 12.92f : 0.0f;
+  if (c >= 1.0f) return 1.0f;
+  return 1.055f * det_exp2(det_log2(c) * 0.416666657f) - 0.055f;
+}
 // pow(x, 5) := (x*x)*(x*x)*x
 static inline float pow5(float x) {
   float x2 = x * x;

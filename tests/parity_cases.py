@@ -308,3 +308,42 @@ def frames_in_flight(pkg, orc_mod, make):
     assert not np.array_equal(first, out[2])
     with pytest.raises(pkg.BrtError):
         a.render_frame_async(uni[0], a.opts(w, h, 1, 0), 2, None)  # slot out of range
+
+
+def present_formats(pkg, orc_mod, make):
+    """Present path (Pipeline::rebuildRenderOutput(format, extent) + copyImageToSwapchain, RT/RTPipeline.cpp:49-55,
+    RT/RTApp.cpp:87-152): the frame in the 8-bit swapchain formats is byte-identical to the oracle's, agrees with the
+    textbook conversion of the float frame to within one code, and BGRA is RGBA with R and B swapped."""
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    w, h = 96, 80
+    u = scene.uniform(a, w, h, 0, 3)
+    lin = a.render_frame(u, a.opts(w, h, 2, R | T | J)).copy()
+    assert lin.dtype == np.float32 and lin[..., :3].max() > 1.0 and (lin[..., :3] == 0).any()  # exercises both clamps
+    got = {}
+    for fmt in (pkg.FORMAT_RGBA8_UNORM, pkg.FORMAT_BGRA8_UNORM, pkg.FORMAT_RGBA8_SRGB, pkg.FORMAT_BGRA8_SRGB):
+        flags = R | T | J | pkg.render_format(fmt)
+        img = a.render_frame(u, a.opts(w, h, 2, flags))
+        ref = b.render_frame(u, b.opts(w, h, 2, flags))
+        assert img.dtype == np.uint8 and img.shape == (h, w, 4)
+        assert np.array_equal(img, ref), fmt
+        got[fmt] = img
+    c = np.clip(lin[..., :3].astype(np.float64), 0.0, 1.0)
+    unorm = np.rint(c * 255.0)
+    srgb = np.rint(np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055) * 255.0)
+    assert np.abs(got[pkg.FORMAT_RGBA8_UNORM][..., :3].astype(np.float64) - unorm).max() <= 1
+    assert (got[pkg.FORMAT_RGBA8_UNORM][..., :3] == unorm).mean() > 0.999
+    assert np.abs(got[pkg.FORMAT_RGBA8_SRGB][..., :3].astype(np.float64) - srgb).max() <= 1
+    assert (got[pkg.FORMAT_RGBA8_SRGB][..., :3] == srgb).mean() > 0.99
+    for rgba, bgra in ((pkg.FORMAT_RGBA8_UNORM, pkg.FORMAT_BGRA8_UNORM), (pkg.FORMAT_RGBA8_SRGB, pkg.FORMAT_BGRA8_SRGB)):
+        assert np.array_equal(got[rgba][..., [2, 1, 0, 3]], got[bgra])
+        assert (got[rgba][..., 3] == 255).all()
+    # the asynchronous entry point honours the format too, and the linear image stays available on the device
+    out = np.zeros((h, w, 4), np.uint8)
+    a.render_frame_async(u, a.opts(w, h, 2, R | T | J | pkg.render_format(pkg.FORMAT_BGRA8_SRGB)), 1, out.ctypes.data)
+    a.frame_wait(1)
+    assert np.array_equal(out, got[pkg.FORMAT_BGRA8_SRGB])
+    with pytest.raises(pkg.BrtError):
+        a.render_frame(u, a.opts(w, h, 1, pkg.render_format(7)))

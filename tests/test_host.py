@@ -53,3 +53,48 @@ def test_scene_generators(pkg):
     assert np.array_equal(S.heightfield(16)[0], hv)
     for name, cfg in S.CONFIGS.items():
         assert cfg["width"] * cfg["height"] > 0 and cfg["depth_max"] >= 1
+
+
+def test_camera_handle_inputs(pkg, orc_mod):
+    """Camera::handleInputs (Graphics/Camera.cpp:26-61): product host code == oracle restatement == the rule written out."""
+    import ctypes as C
+    lib, olib = pkg.load(), orc_mod.load()
+    sig = [C.c_uint32, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for f in (lib.brt_camera_handle_inputs, olib.orc_camera_handle_inputs):
+        f.restype, f.argtypes = None, sig
+    rng = np.random.default_rng(7)
+    pos = np.array([0.0, 0.0, -2.0], np.float32)  # RTApp::RTApp, RT/RTApp.cpp:25
+    rot = np.zeros(3, np.float32)
+    for k in range(400):
+        keys = int(rng.integers(0, 1024)) if k % 5 else 0
+        dt = float(np.float32(rng.random() * 0.05))
+        pa, ra = (C.c_float * 3)(*pos), (C.c_float * 3)(*rot)
+        pb, rb = (C.c_float * 3)(*pos), (C.c_float * 3)(*rot)
+        lib.brt_camera_handle_inputs(keys, dt, pa, ra)
+        olib.orc_camera_handle_inputs(keys, dt, pb, rb)
+        assert list(pa) == list(pb) and list(ra) == list(rb), (k, keys)
+        # the rule, in float64
+        key = lambda b: bool(keys & b)
+        rx = key(256) - key(512)
+        ry = key(64) - key(128)
+        r = rot.astype(np.float64)
+        if rx or ry:
+            n = np.hypot(rx, ry)
+            r[0] += 1.5 * dt * rx / n
+            r[1] += 1.5 * dt * ry / n
+        r[0] = np.clip(r[0], -1.5, 1.5)
+        r[1] = np.mod(r[1], 2 * np.pi)
+        fwd = np.array([np.sin(r[1]), 0.0, np.cos(r[1])])
+        right = np.array([fwd[2], 0.0, -fwd[0]])
+        up = np.array([0.0, -1.0, 0.0])
+        mv = fwd * (key(4) - key(8)) + right * (key(2) - key(1)) + up * (key(16) - key(32))
+        p = pos.astype(np.float64)
+        if np.dot(mv, mv) > 1.2e-7:
+            p += 3.0 * dt * mv / np.linalg.norm(mv)
+        assert np.allclose(np.array(pa), p, atol=1e-5) and np.allclose(np.array(ra), r, atol=1e-5), (k, keys)
+        pos, rot = np.array(pa, np.float32), np.array(ra, np.float32)
+        assert -1.5 <= rot[0] <= 1.5 and 0.0 <= rot[1] < 2 * np.pi + 1e-6
+    # no key: nothing moves
+    pa, ra = (C.c_float * 3)(1, 2, 3), (C.c_float * 3)(0.1, 0.2, 0.3)
+    lib.brt_camera_handle_inputs(0, 0.016, pa, ra)
+    assert np.allclose(list(pa), [1, 2, 3]) and np.allclose(list(ra), [0.1, 0.2, 0.3])
