@@ -38,6 +38,11 @@ class Config(C.Structure):
     _fields_ = [("struct_size", u32), ("device", i32), ("tile_rank", u32), ("tile_world", u32), ("flags", u32)]
 
 
+class DenoiseOpts(C.Structure):
+    _fields_ = [("struct_size", u32), ("flags", u32), ("iterations", u32), ("sigma_n_log2", u32), ("sigma_z", f32), ("sigma_l", f32),
+                ("clamp_gamma", f32), ("max_history", f32)]
+
+
 class RenderOpts(C.Structure):
     _fields_ = [(n, u32) for n in ("width", "height", "spp", "flags", "crop_x0", "crop_y0", "crop_w", "crop_h")]
 
@@ -50,7 +55,8 @@ class Stats(C.Structure):
         (n, u32) for n in ("launches_trace_closest", "launches_trace_occlusion", "launches_total")] + [
         (n, f32) for n in ("ms_blas_build", "ms_tlas_build", "ms_cull")] + [("blas_built", u32)] + [
         (n, u64) for n in ("total_triangles", "bvh_nodes", "bvh_bytes")] + [
-        ("sah_cost", f32), ("sah_cost_lbvh", f32), ("instances_visible", u32), ("instances_total", u32)]
+        ("sah_cost", f32), ("sah_cost_lbvh", f32), ("instances_visible", u32), ("instances_total", u32),
+        ("ms_denoise", f32), ("launches_denoise", u32)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,7 +69,9 @@ CFG_COUNTERS = 1
 CFG_NO_TREELET = 2
 CFG_TREELET_ON_REBUILD = 4
 CFG_NO_OVERLAP = 8
-BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY = 1, 2, 4, 8, 16
+BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY, GBUFFER = 1, 2, 4, 8, 16, 32
+AOV_POSITION, AOV_NORMAL = 3, 4
+DENOISE_RESET, DENOISE_BILATERAL = 1, 2
 FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_BGRA8_UNORM, FORMAT_RGBA8_SRGB, FORMAT_BGRA8_SRGB = 0, 1, 2, 3, 4
 FORMAT_SHIFT, FORMAT_MASK = 8, 0x700
 
@@ -82,7 +90,7 @@ BRT_SYMBOLS = [
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
-    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs",
+    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image",
 ]
 
 
@@ -138,6 +146,7 @@ class SceneApi:
             "debug_sort_pairs": (C.c_int, [vp, P(u32), P(u32), u32, C.c_int]),
             "camera_uniform": (None, [P(f32), P(f32), f32, f32, f32, f32, u32, u32, P(Uniform)]),
             "camera_handle_inputs": (None, [u32, f32, P(f32), P(f32)]),
+            "denoise": (C.c_int, [vp, P(Uniform), P(DenoiseOpts), vp]),
         }
         device_side = {  # entry points that take device pointers / streams
             "set_stream": (C.c_int, [vp, vp]),
@@ -281,7 +290,21 @@ class SceneApi:
     def render_frame_ptr(self, uniform, opts, host_ptr):
         self._ck(self._f("render_frame")(self.ctx, C.byref(uniform), C.byref(opts), C.c_void_p(host_ptr)))
 
+    @staticmethod
+    def denoise_opts(iterations=4, sigma_n_log2=5, sigma_z=0.02, sigma_l=4.0, clamp_gamma=0.0, max_history=32.0, flags=0):
+        return DenoiseOpts(C.sizeof(DenoiseOpts), flags, iterations, sigma_n_log2, sigma_z, sigma_l, clamp_gamma, max_history)
+
+    def denoise(self, uniform, dopts, width, height, want_image=True):
+        """Extensions::Denoiser::denoise (Graphics/Denoiser/Denoiser.h:5-20) on the frame rendered last (BRT_RENDER_GBUFFER)."""
+        out = np.zeros((height, width, 4), dtype=np.float32) if want_image else None
+        self._ck(self._f("denoise")(self.ctx, C.byref(uniform), C.byref(dopts), out.ctypes.data_as(C.c_void_p) if want_image else None))
+        return out
+
     def get_aov(self, kind, width, height):
+        if kind in (AOV_POSITION, AOV_NORMAL):
+            out = np.zeros((height, width, 4), dtype=np.float32)
+            self._ck(self._f("get_aov")(self.ctx, kind, out.ctypes.data_as(C.c_void_p)))
+            return out
         out = np.zeros((height, width), dtype=np.float32 if kind == AOV_HIT_T else np.uint32)
         self._ck(self._f("get_aov")(self.ctx, kind, out.ctypes.data_as(C.c_void_p)))
         return out

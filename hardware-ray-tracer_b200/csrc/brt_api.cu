@@ -13,6 +13,7 @@
 #include "../../include/brt.h"
 #include "builder.h"
 #include "render_kernels.cuh"
+#include "denoise.cuh"
 
 namespace brt {
 
@@ -27,6 +28,8 @@ BRT_KERNEL_1D(k_sum_samples, SumSamplesParams, sum_samples_body)
 BRT_KERNEL_1D(k_resolve, ResolveParams, resolve_body)
 BRT_KERNEL_1D(k_untile, UntileParams, untile_body)
 BRT_KERNEL_1D(k_present, PresentParams, present_body)
+BRT_KERNEL_1D(k_dn_temporal, DnTemporalParams, dn_temporal_body)
+BRT_KERNEL_1D(k_dn_atrous, DnAtrousParams, dn_atrous_body)
 BRT_KERNEL_1D(k_cull, CullParams, cull_body)
 
 #ifdef BRT_EMU
@@ -184,6 +187,9 @@ struct FrameSlot {
   uint32_t frame_w = 0, frame_h = 0;
   DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
   DevBuf d_image8;  // the frame in an 8-bit present format (BRT_RENDER_FORMAT)
+  DevBuf d_aov_pos, d_aov_nrm;  // BRT_RENDER_GBUFFER
+  bool has_gbuffer = false;
+  uint32_t render_flags = 0;  // of the frame rendered last on this slot
   DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   std::deque<EventPair> events;  // deque: references stay valid while the pool grows
   size_t events_used = 0;
@@ -231,6 +237,11 @@ struct brt_context {
   uint32_t gather_w = 0, gather_h = 0, n_peers = 0;
   void* peer_images[BRT_MAX_PEERS] = {nullptr};
   bool peer_opened[BRT_MAX_PEERS] = {false};
+  // denoiser history (Graphics/Denoiser/Denoiser.h): accumulated colour + history length, luminance moments, last G-buffer, camera
+  DevBuf dn_work[2], dn_hist_color[2], dn_hist_mom[2], dn_h_nrm, dn_h_inst, dn_h_t;
+  uint32_t dn_w = 0, dn_h = 0, dn_parity = 0, dn_result = 0;
+  bool dn_have_history = false;
+  float dn_prev_vp[16] = {0}, dn_prev_eye[3] = {0, 0, 0};
   brt_stats stats{};
 };
 
@@ -552,6 +563,14 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   BRT_CUDA(cudaMemsetAsync(f->d_aov_inst.ptr(), 0xff, npx * 4, s));
   BRT_CUDA(cudaMemsetAsync(f->d_aov_t.ptr(), 0, npx * 4, s));
   if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(f->d_image.ptr(), 0, npx * 16, s));
+  f->has_gbuffer = (o.flags & BRT_RENDER_GBUFFER) != 0u;
+  f->render_flags = o.flags;
+  if (f->has_gbuffer) {
+    f->d_aov_pos.ensure(npx * 16);
+    f->d_aov_nrm.ensure(npx * 16);
+    BRT_CUDA(cudaMemsetAsync(f->d_aov_pos.ptr(), 0, npx * 16, s));
+    BRT_CUDA(cudaMemsetAsync(f->d_aov_nrm.ptr(), 0, npx * 16, s));
+  }
   uint32_t launches = 0, l_closest = 0, l_occl = 0;
   const Node8* tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
   const InstRec* insts = c->d_tlas_inst.as<InstRec>();
@@ -645,6 +664,8 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
         sp.aov_prim = f->d_aov_prim.as<uint32_t>();
         sp.aov_inst = f->d_aov_inst.as<uint32_t>();
         sp.aov_t = f->d_aov_t.as<float>();
+        sp.aov_pos = f->has_gbuffer ? f->d_aov_pos.as<float4>() : nullptr;
+        sp.aov_nrm = f->has_gbuffer ? f->d_aov_nrm.as<float4>() : nullptr;
         sp.sky = c->sky;
         Timed t(f, CLS_SHADE, s);
         BRT_LAUNCH_1D(k_shade, sp, grid_for(c, capw, 128, 16), 128, s);
@@ -1284,13 +1305,20 @@ int brt_get_aov(brt_context* c, int kind, void* out) {
     BRT_CUDA(cudaSetDevice(c->device));
     const size_t n = (size_t)f->frame_w * f->frame_h;
     const void* src = nullptr;
+    size_t bytes = 4;
     switch (kind) {
       case BRT_AOV_PRIM_ID: src = f->d_aov_prim.ptr(); break;
       case BRT_AOV_INST_ID: src = f->d_aov_inst.ptr(); break;
       case BRT_AOV_HIT_T: src = f->d_aov_t.ptr(); break;
+      case BRT_AOV_POSITION:
+      case BRT_AOV_NORMAL:
+        if (!f->has_gbuffer) bad_state("get_aov: the frame was not rendered with BRT_RENDER_GBUFFER");
+        src = kind == BRT_AOV_POSITION ? f->d_aov_pos.ptr() : f->d_aov_nrm.ptr();
+        bytes = 16;
+        break;
       default: invalid("get_aov: bad kind");
     }
-    BRT_CUDA(cudaMemcpyAsync(out, src, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    BRT_CUDA(cudaMemcpyAsync(out, src, n * bytes, cudaMemcpyDeviceToHost, c->stream));
     BRT_CUDA(cudaStreamSynchronize(c->stream));
   });
 }
@@ -1496,5 +1524,124 @@ void brt_camera_handle_inputs(uint32_t keys, float dt, float position[3], float 
     for (int k = 0; k < 3; ++k) position[k] += 3.0f * dt * (mv[k] * inv);
   }
 }
+
+// Extensions::Denoiser::denoise (Graphics/Denoiser/Denoiser.h:5-20): temporal accumulation with reprojection, history clamping,
+// variance estimation (k_dn_temporal), a-trous wavelet iterations and the bilateral pass (k_dn_atrous). DESIGN.md §12.
+int brt_denoise(brt_context* c, const brt_uniform* u, const brt_denoise_opts* d, float* rgba_host) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!u || !d || d->struct_size != sizeof(brt_denoise_opts)) invalid("denoise: null / struct_size mismatch");
+    if (d->iterations > 6 || d->sigma_n_log2 > 8) invalid("denoise: iterations <= 6, sigma_n_log2 <= 8");
+    BRT_CUDA(cudaSetDevice(c->device));
+    wait_all_frames(c);
+    FrameSlot* f = &c->slots[c->last_slot];
+    if (!f->frame_w || !f->has_gbuffer) bad_state("denoise: render the frame with BRT_RENDER_GBUFFER first");
+    if (c->tile_world > 1) bad_state("denoise: single-GPU contexts only (tile_world == 1)");
+    const uint32_t W = f->frame_w, H = f->frame_h;
+    const size_t npx = (size_t)W * H;
+    cudaStream_t s = c->stream;
+    if (c->dn_w != W || c->dn_h != H || (d->flags & BRT_DENOISE_RESET)) c->dn_have_history = false;
+    c->dn_w = W;
+    c->dn_h = H;
+    for (int k = 0; k < 2; ++k) {
+      c->dn_work[k].ensure(npx * 16);
+      c->dn_hist_color[k].ensure(npx * 16);
+      c->dn_hist_mom[k].ensure(npx * 8);
+    }
+    c->dn_h_nrm.ensure(npx * 16);
+    c->dn_h_inst.ensure(npx * 4);
+    c->dn_h_t.ensure(npx * 4);
+    // this frame's camera: world -> clip = P V = (V^-1 P^-1)^-1 from the two inverses the uniform carries (RT/RTApp.cpp:44-49)
+    double vi[16], pi[16], a[16], vp[16];
+    for (int i = 0; i < 16; ++i) { vi[i] = u->viewInverse[i]; pi[i] = u->projInverse[i]; }
+    for (int r = 0; r < 4; ++r)
+      for (int k = 0; k < 4; ++k) {
+        double acc = 0.0;
+        for (int j = 0; j < 4; ++j) acc += vi[4 * r + j] * pi[4 * j + k];
+        a[4 * r + k] = acc;
+      }
+    invert4x4(a, vp);
+    const GBuffer g{f->d_aov_pos.as<float4>(), f->d_aov_nrm.as<float4>(), f->d_aov_inst.as<uint32_t>(), f->d_aov_t.as<float>()};
+    const GBuffer hg{nullptr, c->dn_h_nrm.as<float4>(), c->dn_h_inst.as<uint32_t>(), c->dn_h_t.as<float>()};
+    const uint32_t par = c->dn_parity;
+    const uint32_t grid = grid_for(c, (uint32_t)npx, 256, 8);
+    uint32_t launches = 0;
+    BRT_CUDA(cudaEventRecord(c->ev_t[0], s));
+    {
+      DnTemporalParams tp{};
+      tp.count = (uint32_t)npx;
+      tp.width = W;
+      tp.height = H;
+      tp.color = f->d_image.as<float4>();
+      tp.g = g;
+      tp.hg = hg;
+      tp.h_color = c->dn_hist_color[par].as<float4>();
+      tp.h_moments = c->dn_hist_mom[par].as<float2>();
+      std::memcpy(tp.prev_vp, c->dn_prev_vp, sizeof(tp.prev_vp));
+      std::memcpy(tp.prev_eye, c->dn_prev_eye, sizeof(tp.prev_eye));
+      tp.pixel_offset = (f->render_flags & BRT_RENDER_JITTER) ? 0.0f : 0.5f;
+      tp.have_history = c->dn_have_history ? 1u : 0u;
+      tp.clamp_gamma = d->clamp_gamma;
+      tp.max_history = d->max_history >= 1.0f ? d->max_history : 1.0f;
+      tp.out = c->dn_work[0].as<float4>();
+      tp.out_h_color = c->dn_hist_color[par ^ 1].as<float4>();
+      tp.out_h_moments = c->dn_hist_mom[par ^ 1].as<float2>();
+      BRT_LAUNCH_1D(k_dn_temporal, tp, grid, 256, s);
+      BRT_CHECK_LAUNCH();
+      launches++;
+    }
+    uint32_t cur = 0;
+    const uint32_t passes = d->iterations + ((d->flags & BRT_DENOISE_BILATERAL) ? 1u : 0u);
+    for (uint32_t it = 0; it < passes; ++it) {
+      const bool bilateral = it >= d->iterations;
+      DnAtrousParams ap{};
+      ap.count = (uint32_t)npx;
+      ap.width = W;
+      ap.height = H;
+      ap.step = bilateral ? 1 : (1 << it);
+      ap.radius = bilateral ? 1 : 2;
+      ap.sigma_z = d->sigma_z;
+      ap.sigma_l = d->sigma_l;
+      ap.sigma_n_log2 = d->sigma_n_log2;
+      ap.final_pass = it + 1 == passes ? 1u : 0u;
+      ap.in = c->dn_work[cur].as<float4>();
+      ap.g = g;
+      ap.out = c->dn_work[cur ^ 1].as<float4>();
+      BRT_LAUNCH_1D(k_dn_atrous, ap, grid, 256, s);
+      BRT_CHECK_LAUNCH();
+      launches++;
+      cur ^= 1;
+    }
+    if (passes == 0) {  // accumulation only: alpha = 1 through a zero-radius pass
+      DnAtrousParams ap{};
+      ap.count = (uint32_t)npx; ap.width = W; ap.height = H; ap.step = 1; ap.radius = 0; ap.sigma_z = d->sigma_z; ap.sigma_l = d->sigma_l;
+      ap.final_pass = 1u; ap.in = c->dn_work[0].as<float4>(); ap.g = g; ap.out = c->dn_work[1].as<float4>();
+      BRT_LAUNCH_1D(k_dn_atrous, ap, grid, 256, s);
+      BRT_CHECK_LAUNCH();
+      launches++;
+      cur = 1;
+    }
+    BRT_CUDA(cudaEventRecord(c->ev_t[1], s));
+    // this frame becomes the history of the next call
+    BRT_CUDA(cudaMemcpyAsync(c->dn_h_nrm.ptr(), f->d_aov_nrm.ptr(), npx * 16, cudaMemcpyDeviceToDevice, s));
+    BRT_CUDA(cudaMemcpyAsync(c->dn_h_inst.ptr(), f->d_aov_inst.ptr(), npx * 4, cudaMemcpyDeviceToDevice, s));
+    BRT_CUDA(cudaMemcpyAsync(c->dn_h_t.ptr(), f->d_aov_t.ptr(), npx * 4, cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i < 16; ++i) c->dn_prev_vp[i] = (float)vp[i];
+    c->dn_prev_eye[0] = u->viewInverse[3];
+    c->dn_prev_eye[1] = u->viewInverse[7];
+    c->dn_prev_eye[2] = u->viewInverse[11];
+    c->dn_have_history = true;
+    c->dn_parity = par ^ 1;
+    c->dn_result = cur;
+    if (rgba_host) BRT_CUDA(cudaMemcpyAsync(rgba_host, c->dn_work[cur].ptr(), npx * 16, cudaMemcpyDeviceToHost, s));
+    BRT_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[1]);
+    c->stats.ms_denoise = ms;
+    c->stats.launches_denoise = launches;
+  });
+}
+
+void* brt_denoised_image(brt_context* c) { return c && c->dn_w ? c->dn_work[c->dn_result].ptr() : nullptr; }
 
 }  // extern "C"

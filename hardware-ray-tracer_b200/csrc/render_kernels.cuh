@@ -209,6 +209,8 @@ struct ShadeParams {
   uint32_t* aov_prim;
   uint32_t* aov_inst;
   float* aov_t;
+  float4* aov_pos;  // BRT_RENDER_GBUFFER: world position (w = 1) and shading normal of the primary hit, else null
+  float4* aov_nrm;
   brt_sky sky;
 };
 
@@ -304,6 +306,13 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   const f3 V = ray_d;             // :155
   bool flipped = false;
   if (dot(N, -V) < 0.0f) { N = -N; flipped = true; }  // :157-158
+  if (p.write_aov && p.aov_pos && (px >> BRT_SLOT_BITS) == 0u) {
+    uint32_t x, y;
+    slot_to_pixel(p.map, px & BRT_SLOT_MASK, x, y);
+    const size_t pix = (size_t)y * p.map.width + x;
+    p.aov_pos[pix] = make_float4(worldPos.x, worldPos.y, worldPos.z, 1.0f);
+    p.aov_nrm[pix] = make_float4(N.x, N.y, N.z, 0.0f);
+  }
   const Frame fr = make_frame(N);
   const BrdfSetup bs = brdf_setup(mat);
   const f3 Vout = -V;

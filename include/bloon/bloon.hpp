@@ -334,3 +334,45 @@ class Pipeline {
 };
 
 }  // namespace RayTracing
+
+namespace Extensions {
+
+// Extensions::Denoiser (Graphics/Denoiser/Denoiser.h:14-20 declares the class without a body; the stages listed at :5-12 are what
+// brt_denoise runs). denoise() filters the frame the pipeline traced last — trace it with BRT_RENDER_GBUFFER — and keeps the
+// temporal history in the device context.
+class Denoiser {
+ public:
+  explicit Denoiser(Core::Device& device) : device(device) {
+    opts.struct_size = sizeof(opts);
+    opts.flags = BRT_DENOISE_BILATERAL;
+    opts.iterations = 4;
+    opts.sigma_n_log2 = 5;
+    opts.sigma_z = 0.05f;
+    opts.sigma_l = 4.0f;
+    opts.clamp_gamma = 0.0f;
+    opts.max_history = 32.0f;
+  }
+  ~Denoiser() = default;
+  Denoiser(const Denoiser&) = delete;
+  Denoiser& operator=(const Denoiser&) = delete;
+  brt_denoise_opts& options() { return opts; }
+  void reset() { resetNext = true; }
+  // returns the filtered linear RGBA32F image
+  const std::vector<float>& denoise(const RayTracing::Uniform& uniform, uint32_t width, uint32_t height) {
+    out.assign((size_t)width * height * 4, 0.0f);
+    brt_denoise_opts o = opts;
+    if (resetNext) o.flags |= BRT_DENOISE_RESET;
+    resetNext = false;
+    bloon::check(brt_denoise(device.getDevice(), &uniform, &o, out.data()), device.getDevice(), "Denoiser::denoise");
+    return out;
+  }
+
+ private:
+  Core::Device& device;
+  brt_denoise_opts opts{};
+  bool resetNext = false;
+  std::vector<float> out;
+};
+
+}  // namespace Extensions
+

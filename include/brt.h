@@ -128,6 +128,7 @@ typedef struct brt_config {
 #define BRT_RENDER_BOUNCE_DIFFUSE 4u /* extension: cosine-hemisphere GI bounce (SH/sampler.slang:53-65 + toWorld) */
 #define BRT_RENDER_JITTER 8u         /* use the sub-pixel jitter the shader computes but drops (SH/raytracing.slang:96-98) */
 #define BRT_RENDER_SKY 16u           /* miss returns a sky gradient instead of black (SH/raytracing.slang:173-176) */
+#define BRT_RENDER_GBUFFER 32u       /* also keep world position + shading normal of the primary hit (input of brt_denoise) */
 
 /* Output format of the image handed back by the render entry points (bits 8..10 of brt_render_opts.flags): the format
  * Pipeline::rebuildRenderOutput(format, extent) creates the storage image in — the swapchain's (RT/RTPipeline.cpp:49-55,
@@ -148,7 +149,8 @@ typedef struct brt_render_opts {
   uint32_t crop_x0, crop_y0, crop_w, crop_h; /* crop_w == 0: whole image; else only this window is traced */
 } brt_render_opts;
 
-enum { BRT_AOV_PRIM_ID = 0, BRT_AOV_INST_ID = 1, BRT_AOV_HIT_T = 2 };
+enum { BRT_AOV_PRIM_ID = 0, BRT_AOV_INST_ID = 1, BRT_AOV_HIT_T = 2,
+       BRT_AOV_POSITION = 3, BRT_AOV_NORMAL = 4 /* 4 floats per pixel, frames rendered with BRT_RENDER_GBUFFER */ };
 #define BRT_AOV_MISS 0xffffffffu
 
 typedef struct brt_stats {
@@ -171,6 +173,9 @@ typedef struct brt_stats {
   float sah_cost;           /* SAH cost of the largest BLAS (binary tree, after refinement) */
   float sah_cost_lbvh;      /* same before refinement */
   uint32_t instances_visible, instances_total;
+  /* last brt_denoise: device time of all its kernels (ms) and how many were launched */
+  float ms_denoise;
+  uint32_t launches_denoise;
 } brt_stats;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -262,6 +267,28 @@ BRT_API int brt_render_frame_peers(brt_context* ctx, const brt_uniform* u, const
 BRT_API void* brt_gather_image(brt_context* ctx);
 /* device pointer of the context's own full-frame RGBA32F image of the last frame (the slot last waited for) */
 BRT_API void* brt_device_image(brt_context* ctx);
+
+/* ---- denoiser slot (Graphics/Denoiser/Denoiser.h:5-20) -------------------------------------------------------
+ * The reference declares Extensions::Denoiser::denoise() without a body; the comment above it lists the stages: temporal
+ * accumulation (with reprojection), history clamping (to prevent ghosting), variance estimation, a-trous wavelet denoiser,
+ * bilateral pass. (The README's DLSS Ray Reconstruction is proprietary: out of scope.) brt_denoise runs those stages on the
+ * frame rendered last with BRT_RENDER_GBUFFER — `u` is that frame's uniform — keeps the history (accumulated colour, luminance
+ * moments, G-buffer, camera) in the context for the next call, and copies the filtered linear RGBA32F image to rgba_host
+ * (may be NULL; brt_denoised_image() is the device copy). The arithmetic is specified in DESIGN.md §12. */
+typedef struct brt_denoise_opts {
+  uint32_t struct_size;   /* sizeof(brt_denoise_opts) */
+  uint32_t flags;         /* BRT_DENOISE_* */
+  uint32_t iterations;    /* a-trous iterations, hole size 2^i, 0..6 */
+  uint32_t sigma_n_log2;  /* normal edge-stopping weight max(0, N.N')^(2^k), 0..8 */
+  float sigma_z;          /* depth edge-stopping, relative to hit distance x hole size */
+  float sigma_l;          /* luminance edge-stopping, in standard deviations */
+  float clamp_gamma;      /* history clamped to mean +- gamma sigma of the 3x3 neighbourhood; <= 0: no clamping */
+  float max_history;      /* frames a pixel accumulates at most */
+} brt_denoise_opts;
+#define BRT_DENOISE_RESET 1u      /* drop the history first (camera cut, scene change) */
+#define BRT_DENOISE_BILATERAL 2u  /* final 3x3 joint-bilateral pass */
+BRT_API int brt_denoise(brt_context* ctx, const brt_uniform* u, const brt_denoise_opts* opts, float* rgba_host);
+BRT_API void* brt_denoised_image(brt_context* ctx);
 
 /* ---- test / measurement only ---------------------------------------------------------------- */
 /* primary-hit AOVs of sample 0 of the last frame: uint32 prim id, uint32 instance id

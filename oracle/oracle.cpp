@@ -11,6 +11,7 @@
 
 #include "bvh.hpp"
 #include "shaders.hpp"
+#include "denoise.hpp"
 
 using namespace orc;
 
@@ -63,6 +64,10 @@ struct orc_context {
   uint32_t fw = 0, fh = 0;
   std::vector<uint32_t> aov_prim, aov_inst;
   std::vector<float> aov_t;
+  std::vector<Px4> aov_pos, aov_nrm, last_image;  // BRT_RENDER_GBUFFER + the linear frame (inputs of orc_denoise)
+  bool has_gbuffer = false;
+  uint32_t render_flags = 0;
+  DenoiseState dn;
   brt_stats stats{};
 };
 
@@ -371,6 +376,11 @@ void render_pixel(orc_context* c, const brt_uniform& u, const brt_render_opts& o
       vec3 V = ray.d;                   // :155
       bool flipped = false;
       if (dot(N, -V) < 0.0f) { N = -N; flipped = true; }  // :157-158
+      if (s == 0 && depth == 0 && c->has_gbuffer) {
+        size_t pi = (size_t)py * o.width + px;
+        c->aov_pos[pi] = Px4{worldPos.x, worldPos.y, worldPos.z, 1.0f};
+        c->aov_nrm[pi] = Px4{N.x, N.y, N.z, 0.0f};
+      }
       vec3 color = calculate_color(c, mat, N, -V, worldPos, k);  // :160
       depth++;                                                   // :164
       csum = csum + color * prevWeight;                          // :122
@@ -653,6 +663,12 @@ int orc_render_frame(orc_context* c, const brt_uniform* u, const brt_render_opts
   c->aov_prim.assign(npx, BRT_AOV_MISS);
   c->aov_inst.assign(npx, BRT_AOV_MISS);
   c->aov_t.assign(npx, 0.0f);
+  c->has_gbuffer = (o->flags & BRT_RENDER_GBUFFER) != 0;
+  c->render_flags = o->flags;
+  if (c->has_gbuffer) {
+    c->aov_pos.assign(npx, Px4{0, 0, 0, 0});
+    c->aov_nrm.assign(npx, Px4{0, 0, 0, 0});
+  }
   std::memset(rgba, 0, npx * 16);
   uint32_t x0 = 0, y0 = 0, x1 = o->width, y1 = o->height;
   if (o->crop_w) {
@@ -689,6 +705,8 @@ int orc_render_frame(orc_context* c, const brt_uniform* u, const brt_render_opts
   c->stats.nodes_visited_occlusion = s.nodes_o;
   c->stats.prims_tested_occlusion = s.prims_o;
   c->stats.spheres_tested_occlusion = s.sph_o;
+  c->last_image.resize(npx);
+  std::memcpy(c->last_image.data(), rgba, npx * 16);
   if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) present_convert(rgba, npx, format, reinterpret_cast<uint8_t*>(rgba_out));
   return BRT_OK;
 }
@@ -700,10 +718,66 @@ int orc_get_aov(orc_context* c, int kind, void* out) {
     case BRT_AOV_PRIM_ID: std::memcpy(out, c->aov_prim.data(), n * 4); break;
     case BRT_AOV_INST_ID: std::memcpy(out, c->aov_inst.data(), n * 4); break;
     case BRT_AOV_HIT_T: std::memcpy(out, c->aov_t.data(), n * 4); break;
+    case BRT_AOV_POSITION:
+    case BRT_AOV_NORMAL:
+      if (!c->has_gbuffer) return fail(c, BRT_ERR_STATE, "get_aov: the frame was not rendered with BRT_RENDER_GBUFFER");
+      std::memcpy(out, kind == BRT_AOV_POSITION ? (const void*)c->aov_pos.data() : (const void*)c->aov_nrm.data(), n * 16);
+      break;
     default: return fail(c, BRT_ERR_INVALID, "get_aov: bad kind");
   }
   return BRT_OK;
 }
+// Extensions::Denoiser::denoise (Graphics/Denoiser/Denoiser.h:5-20), stages of oracle/denoise.hpp on the frame rendered last
+int orc_denoise(orc_context* c, const brt_uniform* u, const brt_denoise_opts* d, float* rgba) {
+  if (!c || !u || !d || d->struct_size != sizeof(brt_denoise_opts)) return fail(c, BRT_ERR_INVALID, "denoise: null / struct_size mismatch");
+  if (d->iterations > 6 || d->sigma_n_log2 > 8) return fail(c, BRT_ERR_INVALID, "denoise: iterations <= 6, sigma_n_log2 <= 8");
+  if (!c->fw || !c->has_gbuffer) return fail(c, BRT_ERR_STATE, "denoise: render the frame with BRT_RENDER_GBUFFER first");
+  const uint32_t W = c->fw, H = c->fh;
+  const size_t npx = (size_t)W * H;
+  if (c->dn.w != W || c->dn.h != H || (d->flags & BRT_DENOISE_RESET)) c->dn.have = false;
+  c->dn.w = W;
+  c->dn.h = H;
+  // world -> clip of this frame = (V^-1 P^-1)^-1 (the uniform carries the inverses, RT/RTApp.cpp:44-49)
+  double vi[16], pi[16], a[16], vp[16];
+  for (int i = 0; i < 16; ++i) { vi[i] = u->viewInverse[i]; pi[i] = u->projInverse[i]; }
+  for (int r = 0; r < 4; ++r)
+    for (int k = 0; k < 4; ++k) {
+      double acc = 0.0;
+      for (int j = 0; j < 4; ++j) acc += vi[4 * r + j] * pi[4 * j + k];
+      a[4 * r + k] = acc;
+    }
+  invert4x4(a, vp);
+  DenoiseState next;
+  std::vector<Px4> work[2];
+  dn_temporal(c->last_image.data(), c->aov_pos.data(), c->aov_nrm.data(), c->aov_inst.data(), c->dn, W, H, d->clamp_gamma,
+              d->max_history >= 1.0f ? d->max_history : 1.0f, (c->render_flags & BRT_RENDER_JITTER) ? 0.0f : 0.5f, work[0], next);
+  int cur = 0;
+  const uint32_t passes = d->iterations + ((d->flags & BRT_DENOISE_BILATERAL) ? 1u : 0u);
+  for (uint32_t it = 0; it < passes; ++it) {
+    const bool bilateral = it >= d->iterations;
+    dn_atrous(work[cur], c->aov_nrm.data(), c->aov_inst.data(), c->aov_t.data(), W, H, bilateral ? 1 : (1 << it), bilateral ? 1 : 2, d->sigma_z,
+              d->sigma_l, d->sigma_n_log2, it + 1 == passes, work[cur ^ 1]);
+    cur ^= 1;
+  }
+  if (passes == 0) {
+    dn_atrous(work[0], c->aov_nrm.data(), c->aov_inst.data(), c->aov_t.data(), W, H, 1, 0, d->sigma_z, d->sigma_l, 0, true, work[1]);
+    cur = 1;
+  }
+  next.w = W;
+  next.h = H;
+  next.have = true;
+  next.nrm = c->aov_nrm;
+  next.inst = c->aov_inst;
+  next.t = c->aov_t;
+  for (int i = 0; i < 16; ++i) next.vp[i] = (float)vp[i];
+  next.eye[0] = u->viewInverse[3];
+  next.eye[1] = u->viewInverse[7];
+  next.eye[2] = u->viewInverse[11];
+  c->dn = std::move(next);
+  if (rgba) std::memcpy(rgba, work[cur].data(), npx * 16);
+  return BRT_OK;
+}
+
 int orc_get_stats(orc_context* c, brt_stats* out) {
   if (!c || !out) return BRT_ERR_INVALID;
   *out = c->stats;

@@ -347,3 +347,69 @@ def present_formats(pkg, orc_mod, make):
     assert np.array_equal(out, got[pkg.FORMAT_BGRA8_SRGB])
     with pytest.raises(pkg.BrtError):
         a.render_frame(u, a.opts(w, h, 1, pkg.render_format(7)))
+
+
+def denoiser(pkg, orc_mod, make, w=96, h=96):
+    """The denoiser slot (Graphics/Denoiser/Denoiser.h:5-20: temporal accumulation with reprojection, history clamping, variance
+    estimation, a-trous wavelet, bilateral pass): G-buffer AOVs and every denoised frame of a short sequence — static camera, then
+    a camera move (reprojection), then a reset — are bit-identical to the oracle's; and it denoises: the (tone-mapped) error
+    against a many-sample reference drops."""
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    flags = R | T | D | J | pkg.GBUFFER
+    depth = 5
+    tm = lambda img: img / (1.0 + img)
+    u0 = scene.uniform(a, w, h, 0, depth)
+    truth = tm(b.render_frame(u0, b.opts(w, h, 256, R | T | D | J))[..., :3].astype(np.float64))
+    err = lambda img: float(np.sqrt(((tm(img[..., :3].astype(np.float64)) - truth) ** 2).mean()))
+    dop = a.denoise_opts(iterations=4, sigma_n_log2=5, sigma_z=0.05, sigma_l=4.0, clamp_gamma=0.0, max_history=32.0, flags=pkg.DENOISE_BILATERAL)
+    err_noisy, err_dn = [], []
+    for frame in range(6):
+        u = scene.uniform(a, w, h, frame * 7 + 1, depth)
+        if frame >= 4:
+            u.viewInverse[3] += 0.05 * (frame - 3)  # the eye moves: history is found through reprojection
+        ia = a.render_frame(u, a.opts(w, h, 1, flags))
+        ib = b.render_frame(u, b.opts(w, h, 1, flags))
+        assert np.array_equal(ia.view(np.uint32), ib.view(np.uint32))
+        if frame == 0:
+            for kind in (pkg.AOV_POSITION, pkg.AOV_NORMAL):
+                ga, gb = a.get_aov(kind, w, h), b.get_aov(kind, w, h)
+                assert np.array_equal(ga.view(np.uint32), gb.view(np.uint32)), kind
+            hit = a.get_aov(pkg.AOV_INST_ID, w, h) != pkg.AOV_MISS
+            nrm = a.get_aov(pkg.AOV_NORMAL, w, h)
+            assert np.allclose(np.linalg.norm(nrm[hit][:, :3], axis=1), 1.0, atol=1e-5) and (nrm[~hit] == 0).all()
+        da = a.denoise(u, dop, w, h)
+        db = b.denoise(u, dop, w, h)
+        assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), frame
+        assert (da[..., 3] == 1.0).all() and np.isfinite(da).all()
+        if frame < 4:
+            err_noisy.append(err(ia))
+            err_dn.append(err(da))
+    assert all(d < 0.65 * n for d, n in zip(err_dn, err_noisy)), (err_dn, err_noisy)
+    assert a.get_stats().launches_denoise == 6 and a.get_stats().ms_denoise >= 0.0
+    # temporal accumulation alone (clamped history, no wavelet passes): identical too, and the error keeps falling
+    dop2 = a.denoise_opts(iterations=0, clamp_gamma=4.0, max_history=8.0, flags=pkg.DENOISE_RESET)
+    acc = []
+    for frame in range(5):
+        u = scene.uniform(a, w, h, 100 + frame, depth)
+        for api in (a, b):
+            api.render_frame(u, api.opts(w, h, 1, flags))
+        da, db = a.denoise(u, dop2, w, h), b.denoise(u, dop2, w, h)
+        dop2.flags = 0
+        assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), frame
+        acc.append(err(da))
+    assert acc[4] < 0.8 * acc[0], acc
+    # reset drops the history: with no filter either, the result is the frame itself
+    dop3 = a.denoise_opts(iterations=0, flags=pkg.DENOISE_RESET)
+    ia = a.render_frame(u, a.opts(w, h, 1, flags))
+    da = a.denoise(u, dop3, w, h)
+    assert np.array_equal(da[..., :3].view(np.uint32), ia[..., :3].view(np.uint32))
+    # a frame without the G-buffer cannot be denoised; bad options are rejected
+    a.render_frame(u, a.opts(w, h, 1, R))
+    with pytest.raises(pkg.BrtError):
+        a.denoise(u, dop, w, h)
+    a.render_frame(u, a.opts(w, h, 1, flags))
+    with pytest.raises(pkg.BrtError):
+        a.denoise(u, a.denoise_opts(iterations=9), w, h)

@@ -61,6 +61,10 @@ def test_present_formats(pkg, orc_mod, make):
     pc.present_formats(pkg, orc_mod, make)
 
 
+def test_denoiser(pkg, orc_mod, make):
+    pc.denoiser(pkg, orc_mod, make)
+
+
 def test_counters_flag(pkg, orc_mod, make):
     """BRT_CFG_COUNTERS fills the node / primitive visit counters that feed the roofline's algorithmic bytes."""
     scene = pkg.scenes.make_scene("terrain", small=True)
