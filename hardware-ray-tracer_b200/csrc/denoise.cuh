@@ -19,7 +19,7 @@ BRT_HD float exp_neg(float x) { return det_exp2(-fminf(x, 60.0f) * 1.44269502f);
 
 struct GBuffer {          // primary-hit attributes of sample 0 (written by k_shade with BRT_RENDER_GBUFFER)
   const float4* pos;      // world position xyz, w = 1 on a hit, 0 on a miss
-  const float4* nrm;      // shading normal xyz (after the flip towards the viewer)
+  const float4* nrm;      // shading normal xyz (after the flip towards the viewer), w = hit distance; all 0 on a miss
   const uint32_t* inst;   // instance id, BRT_MISS on a miss
   const float* t;         // hit distance
 };
@@ -118,8 +118,8 @@ BRT_HD void dn_temporal_body(const DnTemporalParams& p, uint32_t i) {
 }
 
 // ---- edge-avoiding a-trous wavelet iteration (5x5 B3 spline, holes of `step` pixels) ------------------------------------------
-// per pixel: 25 taps x (16 colour/variance + 16 normal + 4 depth + 4 id) read (neighbouring lanes share them through L1/L2:
-// 40 B of DRAM traffic per pixel), 16 written
+// per pixel: 25 taps x (16 colour/variance + 16 normal/depth) read (neighbouring lanes share them through L1/L2: 36 B of DRAM
+// traffic per pixel with the 4-byte id of the centre), 16 written
 struct DnAtrousParams {
   uint32_t count;
   const uint32_t* count_ptr;
@@ -142,11 +142,12 @@ BRT_HD void dn_atrous_body(const DnAtrousParams& p, uint32_t i) {
     p.out[i] = p.final_pass ? make_float4(c.x, c.y, c.z, 1.0f) : c;
     return;
   }
-  const float4 N = p.g.nrm[i];
-  const float T = p.g.t[i];
+  const float4 N = p.g.nrm[i];  // w = hit distance
+  const float T = N.w;
   const float Lp = luminance(c.x, c.y, c.z);
-  const float den_l = p.sigma_l * sqrtf(fmaxf(c.w, 0.0f)) + 1e-6f;
-  const float den_z = (p.sigma_z * (float)p.step) * T + 1e-6f;
+  // both exponential edge-stopping terms share one exponential: exp(-dz / (sigma_z step T)) exp(-dl / (sigma_l sqrt(var)))
+  const float rcp_l = 1.0f / (p.sigma_l * sqrtf(fmaxf(c.w, 0.0f)) + 1e-6f);
+  const float rcp_z = p.radius == 2 ? 1.0f / ((p.sigma_z * (float)p.step) * T + 1e-6f) : 0.0f;  // the bilateral pass has no depth term
   const float kern[3] = {0.375f, 0.25f, 0.0625f};
   const float w0 = kern[0] * kern[0];
   float sw = w0, sc[3] = {c.x * w0, c.y * w0, c.z * w0}, sv = c.w * (w0 * w0);
@@ -156,14 +157,13 @@ BRT_HD void dn_atrous_body(const DnAtrousParams& p, uint32_t i) {
       const int qx = x + dx * p.step, qy = y + dy * p.step;
       if (qx < 0 || qy < 0 || qx >= W || qy >= H) continue;
       const size_t q = (size_t)qy * p.width + qx;
-      if (p.g.inst[q] == BRT_MISS) continue;
-      const float4 cq = p.in[q];
-      const float4 Nq = p.g.nrm[q];
+      const float4 Nq = p.g.nrm[q];  // a miss has a zero normal: weight 0
       float wn = fmaxf(((N.x * Nq.x + N.y * Nq.y) + N.z * Nq.z), 0.0f);
+      if (!(wn > 0.0f)) continue;
       for (uint32_t k = 0; k < p.sigma_n_log2; ++k) wn = wn * wn;
-      const float wz = p.radius == 2 ? exp_neg(fabsf(p.g.t[q] - T) / den_z) : 1.0f;
-      const float wl = exp_neg(fabsf(luminance(cq.x, cq.y, cq.z) - Lp) / den_l);
-      const float w = ((kern[dx < 0 ? -dx : dx] * kern[dy < 0 ? -dy : dy]) * wn) * (wz * wl);
+      const float4 cq = p.in[q];
+      const float e = fabsf(Nq.w - T) * rcp_z + fabsf(luminance(cq.x, cq.y, cq.z) - Lp) * rcp_l;
+      const float w = ((kern[dx < 0 ? -dx : dx] * kern[dy < 0 ? -dy : dy]) * wn) * exp_neg(e);
       sc[0] = sc[0] + cq.x * w; sc[1] = sc[1] + cq.y * w; sc[2] = sc[2] + cq.z * w;
       sv = sv + cq.w * (w * w);
       sw = sw + w;

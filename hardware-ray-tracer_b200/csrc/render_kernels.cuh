@@ -209,7 +209,7 @@ struct ShadeParams {
   uint32_t* aov_prim;
   uint32_t* aov_inst;
   float* aov_t;
-  float4* aov_pos;  // BRT_RENDER_GBUFFER: world position (w = 1) and shading normal of the primary hit, else null
+  float4* aov_pos;  // BRT_RENDER_GBUFFER: world position (w = 1) and shading normal (w = hit distance) of the primary hit, else null
   float4* aov_nrm;
   brt_sky sky;
 };
@@ -311,7 +311,7 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
     slot_to_pixel(p.map, px & BRT_SLOT_MASK, x, y);
     const size_t pix = (size_t)y * p.map.width + x;
     p.aov_pos[pix] = make_float4(worldPos.x, worldPos.y, worldPos.z, 1.0f);
-    p.aov_nrm[pix] = make_float4(N.x, N.y, N.z, 0.0f);
+    p.aov_nrm[pix] = make_float4(N.x, N.y, N.z, hit.x);
   }
   const Frame fr = make_frame(N);
   const BrdfSetup bs = brdf_setup(mat);

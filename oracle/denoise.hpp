@@ -110,7 +110,7 @@ static void dn_temporal(const Px4* color, const Px4* pos, const Px4* nrm, const 
 }
 
 // stage 4 / 5: one edge-avoiding a-trous iteration (radius 2, holes of `step`), or the final 3x3 bilateral pass (radius 1) (§12.2-3)
-static void dn_atrous(const std::vector<Px4>& in, const Px4* nrm, const uint32_t* inst, const float* t, uint32_t W, uint32_t H, int step, int radius,
+static void dn_atrous(const std::vector<Px4>& in, const Px4* nrm, const uint32_t* inst, uint32_t W, uint32_t H, int step, int radius,
                       float sigma_z, float sigma_l, uint32_t sigma_n_log2, bool final_pass, std::vector<Px4>& out) {
   out.resize(in.size());
   const float kern[3] = {0.375f, 0.25f, 0.0625f};
@@ -122,11 +122,11 @@ static void dn_atrous(const std::vector<Px4>& in, const Px4* nrm, const uint32_t
         out[i] = final_pass ? Px4{c.x, c.y, c.z, 1.0f} : c;
         continue;
       }
-      const Px4 N = nrm[i];
-      const float T = t[i];
+      const Px4 N = nrm[i];  // w = hit distance
+      const float T = N.w;
       const float Lp = dn_luminance(c.x, c.y, c.z);
-      const float den_l = sigma_l * std::sqrt(std::fmax(c.w, 0.0f)) + 1e-6f;
-      const float den_z = (sigma_z * (float)step) * T + 1e-6f;
+      const float rcp_l = 1.0f / (sigma_l * std::sqrt(std::fmax(c.w, 0.0f)) + 1e-6f);
+      const float rcp_z = radius == 2 ? 1.0f / ((sigma_z * (float)step) * T + 1e-6f) : 0.0f;
       const float w0 = kern[0] * kern[0];
       float sw = w0, sc[3] = {c.x * w0, c.y * w0, c.z * w0}, sv = c.w * (w0 * w0);
       for (int dy = -radius; dy <= radius; ++dy)
@@ -135,13 +135,13 @@ static void dn_atrous(const std::vector<Px4>& in, const Px4* nrm, const uint32_t
           const int qx = x + dx * step, qy = y + dy * step;
           if (qx < 0 || qy < 0 || qx >= (int)W || qy >= (int)H) continue;
           const size_t q = (size_t)qy * W + qx;
-          if (inst[q] == BRT_AOV_MISS) continue;
-          const Px4 cq = in[q], Nq = nrm[q];
+          const Px4 Nq = nrm[q];
           float wn = std::fmax(((N.x * Nq.x + N.y * Nq.y) + N.z * Nq.z), 0.0f);
+          if (!(wn > 0.0f)) continue;  // includes misses: their normal is zero
           for (uint32_t k = 0; k < sigma_n_log2; ++k) wn = wn * wn;
-          const float wz = radius == 2 ? dn_exp_neg(std::fabs(t[q] - T) / den_z) : 1.0f;
-          const float wl = dn_exp_neg(std::fabs(dn_luminance(cq.x, cq.y, cq.z) - Lp) / den_l);
-          const float w = ((kern[dx < 0 ? -dx : dx] * kern[dy < 0 ? -dy : dy]) * wn) * (wz * wl);
+          const Px4 cq = in[q];
+          const float e = std::fabs(Nq.w - T) * rcp_z + std::fabs(dn_luminance(cq.x, cq.y, cq.z) - Lp) * rcp_l;
+          const float w = ((kern[dx < 0 ? -dx : dx] * kern[dy < 0 ? -dy : dy]) * wn) * dn_exp_neg(e);
           sc[0] = sc[0] + cq.x * w; sc[1] = sc[1] + cq.y * w; sc[2] = sc[2] + cq.z * w;
           sv = sv + cq.w * (w * w);
           sw = sw + w;

@@ -379,7 +379,7 @@ void render_pixel(orc_context* c, const brt_uniform& u, const brt_render_opts& o
       if (s == 0 && depth == 0 && c->has_gbuffer) {
         size_t pi = (size_t)py * o.width + px;
         c->aov_pos[pi] = Px4{worldPos.x, worldPos.y, worldPos.z, 1.0f};
-        c->aov_nrm[pi] = Px4{N.x, N.y, N.z, 0.0f};
+        c->aov_nrm[pi] = Px4{N.x, N.y, N.z, h.t};
       }
       vec3 color = calculate_color(c, mat, N, -V, worldPos, k);  // :160
       depth++;                                                   // :164
@@ -755,12 +755,12 @@ int orc_denoise(orc_context* c, const brt_uniform* u, const brt_denoise_opts* d,
   const uint32_t passes = d->iterations + ((d->flags & BRT_DENOISE_BILATERAL) ? 1u : 0u);
   for (uint32_t it = 0; it < passes; ++it) {
     const bool bilateral = it >= d->iterations;
-    dn_atrous(work[cur], c->aov_nrm.data(), c->aov_inst.data(), c->aov_t.data(), W, H, bilateral ? 1 : (1 << it), bilateral ? 1 : 2, d->sigma_z,
+    dn_atrous(work[cur], c->aov_nrm.data(), c->aov_inst.data(), W, H, bilateral ? 1 : (1 << it), bilateral ? 1 : 2, d->sigma_z,
               d->sigma_l, d->sigma_n_log2, it + 1 == passes, work[cur ^ 1]);
     cur ^= 1;
   }
   if (passes == 0) {
-    dn_atrous(work[0], c->aov_nrm.data(), c->aov_inst.data(), c->aov_t.data(), W, H, 1, 0, d->sigma_z, d->sigma_l, 0, true, work[1]);
+    dn_atrous(work[0], c->aov_nrm.data(), c->aov_inst.data(), W, H, 1, 0, d->sigma_z, d->sigma_l, 0, true, work[1]);
     cur = 1;
   }
   next.w = W;
