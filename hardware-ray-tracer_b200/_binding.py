@@ -38,6 +38,10 @@ class Config(C.Structure):
     _fields_ = [("struct_size", u32), ("device", i32), ("tile_rank", u32), ("tile_world", u32), ("flags", u32)]
 
 
+class LightBvhNode(C.Structure):  # RT/Scene.h:123-130
+    _fields_ = [("bBoxMin", f32 * 3), ("bBoxMax", f32 * 3), ("totalFlux", f32), ("coneAxis", f32 * 3), ("coneAngle", f32), ("childIndex", i32)]
+
+
 class DenoiseOpts(C.Structure):
     _fields_ = [("struct_size", u32), ("flags", u32), ("iterations", u32), ("sigma_n_log2", u32), ("sigma_z", f32), ("sigma_l", f32),
                 ("clamp_gamma", f32), ("max_history", f32)]
@@ -63,13 +67,13 @@ class Stats(C.Structure):
 
 
 assert C.sizeof(Vertex) == 32 and C.sizeof(Material) == 52 and C.sizeof(Light) == 32
-assert C.sizeof(Uniform) == 140 and C.sizeof(Sky) == 88
+assert C.sizeof(Uniform) == 140 and C.sizeof(Sky) == 88 and C.sizeof(LightBvhNode) == 48
 
 CFG_COUNTERS = 1
 CFG_NO_TREELET = 2
 CFG_TREELET_ON_REBUILD = 4
 CFG_NO_OVERLAP = 8
-BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY, GBUFFER = 1, 2, 4, 8, 16, 32
+BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY, GBUFFER, LIGHT_BVH = 1, 2, 4, 8, 16, 32, 64
 AOV_POSITION, AOV_NORMAL = 3, 4
 DENOISE_RESET, DENOISE_BILATERAL = 1, 2
 FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_BGRA8_UNORM, FORMAT_RGBA8_SRGB, FORMAT_BGRA8_SRGB = 0, 1, 2, 3, 4
@@ -90,7 +94,7 @@ BRT_SYMBOLS = [
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
-    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image",
+    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_get_light_bvh",
 ]
 
 
@@ -147,6 +151,7 @@ class SceneApi:
             "camera_uniform": (None, [P(f32), P(f32), f32, f32, f32, f32, u32, u32, P(Uniform)]),
             "camera_handle_inputs": (None, [u32, f32, P(f32), P(f32)]),
             "denoise": (C.c_int, [vp, P(Uniform), P(DenoiseOpts), vp]),
+            "get_light_bvh": (C.c_int, [vp, P(LightBvhNode), u32, P(u32)]),
         }
         device_side = {  # entry points that take device pointers / streams
             "set_stream": (C.c_int, [vp, vp]),
@@ -299,6 +304,14 @@ class SceneApi:
         out = np.zeros((height, width, 4), dtype=np.float32) if want_image else None
         self._ck(self._f("denoise")(self.ctx, C.byref(uniform), C.byref(dopts), out.ctypes.data_as(C.c_void_p) if want_image else None))
         return out
+
+    def get_light_bvh(self):
+        """The light BVH (RT/Scene.h:123-130) as a list of LightBvhNode."""
+        n = u32()
+        self._ck(self._f("get_light_bvh")(self.ctx, None, 0, C.byref(n)))
+        arr = (LightBvhNode * max(n.value, 1))()
+        self._ck(self._f("get_light_bvh")(self.ctx, arr, n.value, C.byref(n)))
+        return list(arr)[: n.value]
 
     def get_aov(self, kind, width, height):
         if kind in (AOV_POSITION, AOV_NORMAL):

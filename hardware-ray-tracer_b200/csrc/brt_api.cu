@@ -221,6 +221,8 @@ struct brt_context {
   bool tables_dirty = true, tlas_dirty = true;
 
   // scene (device)
+  std::vector<brt_light_bvh_node> light_bvh;  // RT/Scene.h:123-130, built on the host by build_tables
+  DevBuf d_light_bvh;
   DevBuf d_materials, d_mat_ext, d_lights, d_inst_shade, d_inst_src, d_inst_ids, d_mesh_bounds, d_visible;
   DevBuf d_tlas_nodes, d_tlas_inst;
   uint32_t tlas_count = 0;  // visible, non-empty instances in the TLAS
@@ -302,9 +304,65 @@ struct Timed {  // brackets one launch with events of class `cls` on the stream 
   ~Timed() { cudaEventRecord(e->b, s); }
 };
 
+// ---- light BVH (RT/Scene.h:123-130) ---------------------------------------------------------
+// Median split along the widest axis of the light positions, ties broken by light index; children are allocated in pairs
+// (left, right = left + 1) and built depth-first, so the node order is fully determined by the light list.
+void build_light_bvh(const std::vector<brt_light>& lights, std::vector<brt_light_bvh_node>& nodes) {
+  nodes.clear();
+  const uint32_t n = (uint32_t)lights.size();
+  if (!n) return;
+  nodes.reserve(2 * (size_t)n);
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  struct Task { uint32_t node, first, count; };
+  std::vector<Task> stack;
+  nodes.push_back(brt_light_bvh_node{});
+  stack.push_back({0u, 0u, n});
+  while (!stack.empty()) {
+    const Task t = stack.back();
+    stack.pop_back();
+    brt_light_bvh_node nd{};
+    float flux = 0.0f;
+    for (int k = 0; k < 3; ++k) { nd.bBoxMin[k] = INFINITY; nd.bBoxMax[k] = -INFINITY; }
+    for (uint32_t i = t.first; i < t.first + t.count; ++i) {
+      const brt_light& l = lights[order[i]];
+      for (int k = 0; k < 3; ++k) {
+        nd.bBoxMin[k] = std::fmin(nd.bBoxMin[k], l.pos[k]);
+        nd.bBoxMax[k] = std::fmax(nd.bBoxMax[k], l.pos[k]);
+      }
+      flux = flux + std::fabs(l.intensity * ((0.2126f * l.color[0] + 0.7152f * l.color[1]) + 0.0722f * l.color[2]));
+    }
+    nd.totalFlux = flux;
+    nd.coneAxis[0] = 0.0f; nd.coneAxis[1] = 0.0f; nd.coneAxis[2] = 1.0f;
+    nd.coneAngle = 3.14159274f;
+    if (t.count == 1) {
+      nd.childIndex = -1 - (int32_t)order[t.first];
+    } else {
+      int axis = 0;
+      float best = nd.bBoxMax[0] - nd.bBoxMin[0];
+      for (int k = 1; k < 3; ++k)
+        if (nd.bBoxMax[k] - nd.bBoxMin[k] > best) { best = nd.bBoxMax[k] - nd.bBoxMin[k]; axis = k; }
+      std::sort(order.begin() + t.first, order.begin() + t.first + t.count, [&](uint32_t a, uint32_t b) {
+        const float pa = lights[a].pos[axis], pb = lights[b].pos[axis];
+        return pa < pb || (pa == pb && a < b);
+      });
+      const uint32_t mid = t.count / 2;
+      const uint32_t left = (uint32_t)nodes.size();
+      nd.childIndex = (int32_t)left;
+      nodes.push_back(brt_light_bvh_node{});
+      nodes.push_back(brt_light_bvh_node{});
+      stack.push_back({left + 1, t.first + mid, t.count - mid});  // popped second: the left subtree is built first
+      stack.push_back({left, t.first, mid});
+    }
+    nodes[t.node] = nd;
+  }
+}
+
 // ---- scene tables ------------------------------------------------------------------------------------
 void build_tables(brt_context* c) {
   cudaStream_t s = c->stream;
+  build_light_bvh(c->lights, c->light_bvh);
+  upload(s, c->d_light_bvh, c->light_bvh.data(), c->light_bvh.size() * sizeof(brt_light_bvh_node));
   upload(s, c->d_materials, c->materials.data(), c->materials.size() * sizeof(brt_material));
   upload(s, c->d_mat_ext, c->mat_ext.data(), c->mat_ext.size() * 4);
   upload(s, c->d_lights, c->lights.data(), c->lights.size() * sizeof(brt_light));
@@ -461,9 +519,10 @@ uint32_t tiles_per_rank(uint32_t width, uint32_t height, uint32_t world) {
 // more samples share a launch, the less the latency-bound tail of every launch costs — this is what keeps the tile-parallel
 // multi-GPU frames efficient, where each rank only has 1/N of the pixels.
 void ensure_frame_buffers(brt_context* c, FrameSlot* f, const brt_render_opts& o, uint32_t rounds) {
+  const bool lbvh = (o.flags & BRT_RENDER_LIGHT_BVH) != 0u;
   const uint32_t cap = tiles_per_rank(o.width, o.height, c->tile_world) * 1024u;
   const size_t npx = (size_t)o.width * o.height;
-  const uint32_t L = std::max<uint32_t>(1, (uint32_t)c->lights.size());
+  const uint32_t L = lbvh ? 1u : std::max<uint32_t>(1, (uint32_t)c->lights.size());  // segments per path
   const uint32_t R = std::max(1u, rounds);
   const uint64_t key[4] = {((uint64_t)o.width << 32) | o.height, ((uint64_t)o.spp << 32) | R, L, c->target_wavefront};
   if (f->frame_bytes && std::memcmp(key, f->frame_key, sizeof(key)) == 0) return;  // same frame shape as last time
@@ -534,7 +593,11 @@ void launch_trace(brt_context* c, const TraceParams& p, cudaStream_t stream) {
 void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, const brt_render_opts& o, void* d_tiles_out, bool to_peers = false) {
   if (!c->built) bad_state("render_frame: scene not built (call brt_scene_build)");
   if (!o.width || !o.height || !o.spp) invalid("render_frame: width, height and spp must be non-zero");
-  if (c->lights.size() > BRT_MAX_LIGHTS) throw LimitError("render_frame: more than BRT_MAX_LIGHTS lights");
+  const bool lbvh = (o.flags & BRT_RENDER_LIGHT_BVH) != 0u;
+  if (!lbvh && c->lights.size() > BRT_MAX_LIGHTS) throw LimitError("render_frame: more than BRT_MAX_LIGHTS lights (use BRT_RENDER_LIGHT_BVH)");
+  if (lbvh)
+    for (const brt_light& l : c->lights)
+      if (l.type != BRT_LIGHT_POINT) bad_state("render_frame: BRT_RENDER_LIGHT_BVH needs POINT lights only");
   if (c->tables_dirty) build_tables(c);
   if (c->tlas_dirty) build_tlas(c);
   const bool any_bounce = (o.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0;
@@ -546,7 +609,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   const uint32_t cap = f->cap;
   const size_t npx = (size_t)o.width * o.height;
   const uint32_t n_lights = (uint32_t)c->lights.size();
-  const uint32_t n_slots = std::max(1u, n_lights);
+  const uint32_t n_slots = lbvh ? 1u : std::max(1u, n_lights);  // contribution / shadow-queue segments per path
   f->events_used = 0;
   FrameCounters* ctr = f->d_counters.as<FrameCounters>();
   ShadowCounters* sctr = reinterpret_cast<ShadowCounters*>(ctr + 1);
@@ -652,6 +715,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
         sp.materials = c->d_materials.as<float>();
         sp.mat_ext = c->d_mat_ext.as<float2>();
         sp.lights = c->d_lights.as<LightRec>();
+        sp.light_bvh = c->d_light_bvh.as<float4>();
         sp.n_lights = n_lights;
         sp.contrib = f->d_contrib[par].as<float4>();
         sp.s_o = f->s_o[par].as<float4>();
@@ -680,7 +744,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
         TraceParams tp{};
         tp.count = 0;
         tp.seg_counts = sctr[par].n_shadow;
-        tp.n_segs = n_lights;
+        tp.n_segs = n_slots;
         tp.seg_stride = capw;
         tp.tlas = tlas;
         tp.insts = insts;
@@ -1639,6 +1703,17 @@ int brt_denoise(brt_context* c, const brt_uniform* u, const brt_denoise_opts* d,
     cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[1]);
     c->stats.ms_denoise = ms;
     c->stats.launches_denoise = launches;
+  });
+}
+
+int brt_get_light_bvh(brt_context* c, brt_light_bvh_node* out, uint32_t max_nodes, uint32_t* n_nodes) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!n_nodes) invalid("get_light_bvh: null");
+    if (!c->built) bad_state("get_light_bvh: scene not built");
+    if (c->tables_dirty) { wait_all_frames(c); build_tables(c); }
+    *n_nodes = (uint32_t)c->light_bvh.size();
+    if (out) std::memcpy(out, c->light_bvh.data(), std::min<size_t>(max_nodes, c->light_bvh.size()) * sizeof(brt_light_bvh_node));
   });
 }
 

@@ -197,6 +197,7 @@ struct ShadeParams {
   const float* materials;  // 13 floats each (brt_material)
   const float2* mat_ext;   // transmission, ior
   const LightRec* lights;
+  const float4* light_bvh;  // BRT_RENDER_LIGHT_BVH: brt_light_bvh_node[ ] as 3 x float4 per node
   uint32_t n_lights;
   float4* contrib;         // [n_lights (>= 1)][cap]
   float4* s_o;             // shadow queue
@@ -213,6 +214,40 @@ struct ShadeParams {
   float4* aov_nrm;
   brt_sky sky;
 };
+
+// Light BVH sampling (RT/Scene.h:123-130, SH/raytracing.slang:76; rule in DESIGN.md §13): stochastic descent from the root, a child
+// is taken with probability ~ totalFlux / max(squared distance to its box centre, squared half-diagonal of its box); the single
+// random number is rescaled at every level. Returns the light index, inv_pdf = 1 / (product of the branch probabilities).
+BRT_HD float light_node_importance(const float4 a, const float4 b, f3 P) {  // a = min.xyz, max.x   b = max.yz, flux, cone.x
+  const f3 lo = F3(a.x, a.y, a.z), hi = F3(a.w, b.x, b.y);
+  const f3 ctr = (lo + hi) * 0.5f, hd = (hi - lo) * 0.5f;
+  const f3 d = P - ctr;
+  return b.z / fmaxf(fmaxf(dot(d, d), dot(hd, hd)), 1e-12f);
+}
+BRT_HD uint32_t sample_light_bvh(const float4* __restrict__ nodes, f3 P, float r, float& inv_pdf) {
+  uint32_t node = 0;
+  float pdf = 1.0f;
+  for (int guard = 0; guard < 64; ++guard) {
+    const int child = (int)f2u(nodes[3 * (size_t)node + 2].w);
+    if (child < 0) break;
+    const float w0 = light_node_importance(nodes[3 * (size_t)child], nodes[3 * (size_t)child + 1], P);
+    const float w1 = light_node_importance(nodes[3 * (size_t)child + 3], nodes[3 * (size_t)child + 4], P);
+    const float sum = w0 + w1;
+    const float p0 = sum > 0.0f ? w0 / sum : 0.5f;
+    if (r < p0 || p0 >= 1.0f) {
+      node = (uint32_t)child;
+      pdf = pdf * p0;
+      r = r / p0;
+    } else {
+      const float q = 1.0f - p0;
+      node = (uint32_t)child + 1u;
+      pdf = pdf * q;
+      r = (r - p0) / q;
+    }
+  }
+  inv_pdf = 1.0f / pdf;
+  return (uint32_t)(-1 - (int)f2u(nodes[3 * (size_t)node + 2].w));
+}
 
 // Warp-aggregated append: the lanes that execute this together AND target the same counter share one atomic.
 // (Grouping by address matters: with independent thread scheduling, lanes that are in different iterations of
@@ -253,7 +288,8 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
     p.aux[i] = make_float4(w.x, w.y, w.z, u2f(px));
   }
   if (px == BRT_MISS) return;
-  const uint32_t n_slots = p.n_lights ? p.n_lights : 1u;
+  const bool lbvh = (p.flags & BRT_RENDER_LIGHT_BVH) != 0u;  // one stochastically chosen light per hit instead of the loop
+  const uint32_t n_slots = (p.n_lights && !lbvh) ? p.n_lights : 1u;
   const float4 ro = p.cur.o[i], rd = p.cur.d[i];
   const f3 ray_o = F3(ro.x, ro.y, ro.z), ray_d = F3(rd.x, rd.y, rd.z);
   const uint32_t inst_id = p.hit_inst[i];
@@ -319,10 +355,14 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   // calculateColor :72-88 — the unshadowed contribution of each light goes to contrib[l][slot]; lights
   // whose contribution is not exactly zero get a shadow ray (a zero times the shadow factor is zero
   // either way), which blanks the entry when it is blocked.
+  uint32_t seed = p.cur.seed[i];
   for (uint32_t l = 0; l < n_slots; ++l) {
     f3 contrib = F3(0.0f);
-    if (l < p.n_lights) {
-      const LightRec lr = p.lights[l];
+    uint32_t li = l;
+    float inv_pdf = 1.0f;
+    if (lbvh && p.n_lights) li = sample_light_bvh(p.light_bvh, worldPos, rnd(seed), inv_pdf);
+    if (li < p.n_lights) {
+      const LightRec lr = p.lights[li];
       f3 ldir;
       float intensity = lr.intensity;
       if ((lr.type & 0xffu) == BRT_LIGHT_POINT) {  // SH/light.slang:23-39
@@ -336,6 +376,7 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
         const f3 L = normalize(ldir);
         const f3 color = BRDF(mat, bs, fr, Vout, L);
         contrib = color * F3(lr.pos_colr.w, lr.color_g, lr.color_b) * intensity;  // :83
+        if (lbvh) contrib = contrib * inv_pdf;
         if (!(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f)) {
           const f3 so = worldPos + N * 0.0001f;  // testShadow :56-70
           const uint32_t k = l * p.cap + append_slot(&p.sctr->n_shadow[l]);
@@ -350,7 +391,6 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   // bounce (:161-168). With no BOUNCE flag this is the reference verbatim: weight = 0, the path ends.
   const bool any_bounce = (p.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0u;
   if (!any_bounce || p.last_round) return;
-  uint32_t seed = p.cur.seed[i];
   const float r1 = rnd(seed), r2 = rnd(seed), r3 = rnd(seed);
   const float4 w4 = p.cur.w[i];
   f3 weight = F3(w4.x, w4.y, w4.z);

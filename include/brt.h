@@ -128,6 +128,12 @@ typedef struct brt_config {
 #define BRT_RENDER_BOUNCE_DIFFUSE 4u /* extension: cosine-hemisphere GI bounce (SH/sampler.slang:53-65 + toWorld) */
 #define BRT_RENDER_JITTER 8u         /* use the sub-pixel jitter the shader computes but drops (SH/raytracing.slang:96-98) */
 #define BRT_RENDER_SKY 16u           /* miss returns a sky gradient instead of black (SH/raytracing.slang:173-176) */
+/* Light BVH (the reference declares LightBVHNode, RT/Scene.h:123-130, and announces it at SH/raytracing.slang:76: "This will
+ * later be replaced with a light bounding volume hierarchy system"): instead of looping over all lights, every hit samples ONE
+ * light by a stochastic descent of the light BVH (child chosen with probability ~ totalFlux / distance^2) and divides its
+ * contribution by the probability — unbiased, one shadow ray per hit whatever the light count, no BRT_MAX_LIGHTS limit.
+ * All lights must be POINT lights (the only kind Scene::createLight creates, RT/Scene.cpp:88-97). */
+#define BRT_RENDER_LIGHT_BVH 64u
 #define BRT_RENDER_GBUFFER 32u       /* also keep world position + shading normal of the primary hit (input of brt_denoise) */
 
 /* Output format of the image handed back by the render entry points (bits 8..10 of brt_render_opts.flags): the format
@@ -177,6 +183,17 @@ typedef struct brt_stats {
   float ms_denoise;
   uint32_t launches_denoise;
 } brt_stats;
+
+/* RT/Scene.h:123-130, 48 bytes. Binary tree: childIndex >= 0: index of the left child (the right one follows it);
+ * childIndex < 0: leaf holding light -1 - childIndex. Point lights emit in every direction: coneAngle = pi. */
+typedef struct brt_light_bvh_node {
+  float bBoxMin[3];
+  float bBoxMax[3];
+  float totalFlux; /* sum of intensity * luminance(color) below this node */
+  float coneAxis[3];
+  float coneAngle;
+  int32_t childIndex;
+} brt_light_bvh_node;
 
 /* ---- context ------------------------------------------------------------------------------- */
 typedef struct brt_context brt_context;
@@ -289,6 +306,10 @@ typedef struct brt_denoise_opts {
 #define BRT_DENOISE_BILATERAL 2u  /* final 3x3 joint-bilateral pass */
 BRT_API int brt_denoise(brt_context* ctx, const brt_uniform* u, const brt_denoise_opts* opts, float* rgba_host);
 BRT_API void* brt_denoised_image(brt_context* ctx);
+
+/* copies the light BVH built by the last brt_scene_build to the host: up to max_nodes nodes, returns the node count in *n_nodes
+ * (2 * lights - 1; 0 without lights). Built on the host (lights are few), deterministic. */
+BRT_API int brt_get_light_bvh(brt_context* ctx, brt_light_bvh_node* out, uint32_t max_nodes, uint32_t* n_nodes);
 
 /* ---- test / measurement only ---------------------------------------------------------------- */
 /* primary-hit AOVs of sample 0 of the last frame: uint32 prim id, uint32 instance id

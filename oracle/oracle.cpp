@@ -53,6 +53,7 @@ struct orc_context {
   std::vector<Material> mats;
   std::vector<MatExt> mat_ext;
   std::vector<brt_light> lights;
+  std::vector<brt_light_bvh_node> light_bvh;  // RT/Scene.h:123-130
   brt_sky sky{};
   BVH tlas;                        // over the visible instances
   std::vector<uint32_t> tlas_ids;  // tlas primitive -> instance index
@@ -279,34 +280,121 @@ vec3 sky_color(const brt_sky& s, vec3 dir) {
 // calculateColor (SH/raytracing.slang:72-88) + processLight (SH/light.slang:23-39) + testShadow (:56-70).
 // Deviation that cannot change the image: the shadow ray is skipped when the unshadowed
 // contribution is exactly zero (0 * shadowFactor == 0 either way); it is then not counted as a ray.
-vec3 calculate_color(const orc_context* c, const Material& mat, vec3 normal, vec3 view, vec3 worldPos, Counters& k) {
-  vec3 acc = V3(0.0f);
-  for (size_t i = 0; i < c->lights.size(); ++i) {
-    const brt_light& l = c->lights[i];
-    vec3 ldir;
-    float intensity = l.intensity;
-    if (l.type == BRT_LIGHT_POINT) {
-      ldir = V3(l.pos[0], l.pos[1], l.pos[2]) - worldPos;
-      float d = length(ldir);
-      intensity /= (d * d);
-    } else {
-      ldir = V3(0.9f, -0.1f, 0.0f);
+// ---- light BVH (the reference declares LightBVHNode, RT/Scene.h:123-130, and names its purpose at SH/raytracing.slang:76;
+// there is no code to follow: the rule is DESIGN.md §13) -------------------------------------------------------
+// build: recursive median split on the widest axis of the positions, ties by light index; children adjacent, left subtree first
+void light_bvh_build_node(const std::vector<brt_light>& lights, std::vector<uint32_t>& order, std::vector<brt_light_bvh_node>& nodes, uint32_t node,
+                          uint32_t first, uint32_t count) {
+  brt_light_bvh_node nd{};
+  for (int k = 0; k < 3; ++k) { nd.bBoxMin[k] = INFINITY; nd.bBoxMax[k] = -INFINITY; }
+  float flux = 0.0f;
+  for (uint32_t i = first; i < first + count; ++i) {
+    const brt_light& l = lights[order[i]];
+    for (int k = 0; k < 3; ++k) {
+      nd.bBoxMin[k] = std::fmin(nd.bBoxMin[k], l.pos[k]);
+      nd.bBoxMax[k] = std::fmax(nd.bBoxMax[k], l.pos[k]);
     }
-    if (intensity < kLIGHT_TRESHOLD) continue;
-    vec3 L = normalize(ldir);
-    vec3 color = BRDF(mat, normal, view, L);
-    vec3 contrib = color * V3(l.color[0], l.color[1], l.color[2]) * intensity;
-    float shadow = 1.0f;
-    if (!is_zero(contrib)) {
-      Ray sr;
-      sr.o = worldPos + normal * 0.0001f;
-      sr.d = normalize(ldir);
-      sr.tmin = 0.001f;
-      sr.tmax = length(ldir);
-      shadow = trace_occluded(c, sr, k) ? 0.0f : 1.0f;
-    }
-    acc = acc + contrib * shadow;
+    flux = flux + std::fabs(l.intensity * ((0.2126f * l.color[0] + 0.7152f * l.color[1]) + 0.0722f * l.color[2]));
   }
+  nd.totalFlux = flux;
+  nd.coneAxis[2] = 1.0f;      // point lights radiate everywhere: cone = the whole sphere
+  nd.coneAngle = 3.14159274f;
+  if (count == 1) {
+    nd.childIndex = -1 - (int32_t)order[first];
+    nodes[node] = nd;
+    return;
+  }
+  int axis = 0;
+  for (int k = 1; k < 3; ++k)
+    if (nd.bBoxMax[k] - nd.bBoxMin[k] > nd.bBoxMax[axis] - nd.bBoxMin[axis]) axis = k;
+  std::stable_sort(order.begin() + first, order.begin() + first + count, [&](uint32_t a, uint32_t b) {
+    if (lights[a].pos[axis] != lights[b].pos[axis]) return lights[a].pos[axis] < lights[b].pos[axis];
+    return a < b;
+  });
+  const uint32_t mid = count / 2, left = (uint32_t)nodes.size();
+  nd.childIndex = (int32_t)left;
+  nodes[node] = nd;
+  nodes.resize(nodes.size() + 2);
+  light_bvh_build_node(lights, order, nodes, left, first, mid);
+  light_bvh_build_node(lights, order, nodes, left + 1, first + mid, count - mid);
+}
+void light_bvh_build(orc_context* c) {
+  c->light_bvh.clear();
+  if (c->lights.empty()) return;
+  std::vector<uint32_t> order(c->lights.size());
+  for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+  c->light_bvh.resize(1);
+  light_bvh_build_node(c->lights, order, c->light_bvh, 0, 0, (uint32_t)order.size());
+}
+float light_bvh_importance(const brt_light_bvh_node& n, vec3 P) {
+  vec3 lo = V3(n.bBoxMin[0], n.bBoxMin[1], n.bBoxMin[2]), hi = V3(n.bBoxMax[0], n.bBoxMax[1], n.bBoxMax[2]);
+  vec3 ctr = (lo + hi) * 0.5f, hd = (hi - lo) * 0.5f;
+  vec3 d = P - ctr;
+  return n.totalFlux / std::fmax(std::fmax(dot(d, d), dot(hd, hd)), 1e-12f);
+}
+// one light by stochastic descent; r is rescaled at every level; returns the light index and 1 / probability
+uint32_t light_bvh_sample(const orc_context* c, vec3 P, float r, float& inv_pdf) {
+  uint32_t node = 0;
+  float pdf = 1.0f;
+  for (int guard = 0; guard < 64; ++guard) {
+    int child = c->light_bvh[node].childIndex;
+    if (child < 0) break;
+    float w0 = light_bvh_importance(c->light_bvh[child], P), w1 = light_bvh_importance(c->light_bvh[child + 1], P);
+    float sum = w0 + w1;
+    float p0 = sum > 0.0f ? w0 / sum : 0.5f;
+    if (r < p0 || p0 >= 1.0f) {
+      node = (uint32_t)child;
+      pdf = pdf * p0;
+      r = r / p0;
+    } else {
+      float q = 1.0f - p0;
+      node = (uint32_t)child + 1u;
+      pdf = pdf * q;
+      r = (r - p0) / q;
+    }
+  }
+  inv_pdf = 1.0f / pdf;
+  return (uint32_t)(-1 - c->light_bvh[node].childIndex);
+}
+
+// one light of calculateColor's loop body (SH/raytracing.slang:77-84); scale = 1 in the loop, 1 / pdf for a sampled light
+vec3 light_contribution(const orc_context* c, const brt_light& l, float scale, bool scaled, const Material& mat, vec3 normal, vec3 view, vec3 worldPos,
+                        Counters& k) {
+  vec3 ldir;
+  float intensity = l.intensity;
+  if (l.type == BRT_LIGHT_POINT) {
+    ldir = V3(l.pos[0], l.pos[1], l.pos[2]) - worldPos;
+    float d = length(ldir);
+    intensity /= (d * d);
+  } else {
+    ldir = V3(0.9f, -0.1f, 0.0f);
+  }
+  if (intensity < kLIGHT_TRESHOLD) return V3(0.0f);
+  vec3 L = normalize(ldir);
+  vec3 color = BRDF(mat, normal, view, L);
+  vec3 contrib = color * V3(l.color[0], l.color[1], l.color[2]) * intensity;
+  if (scaled) contrib = contrib * scale;
+  float shadow = 1.0f;
+  if (!is_zero(contrib)) {
+    Ray sr;
+    sr.o = worldPos + normal * 0.0001f;
+    sr.d = normalize(ldir);
+    sr.tmin = 0.001f;
+    sr.tmax = length(ldir);
+    shadow = trace_occluded(c, sr, k) ? 0.0f : 1.0f;
+  }
+  return contrib * shadow;
+}
+
+vec3 calculate_color(const orc_context* c, const Material& mat, vec3 normal, vec3 view, vec3 worldPos, Counters& k, bool light_bvh, uint32_t& seed) {
+  vec3 acc = V3(0.0f);
+  if (light_bvh) {  // SH/raytracing.slang:76: "later be replaced with a light bounding volume hierarchy system"
+    if (c->lights.empty()) return acc;
+    float inv_pdf;
+    uint32_t li = light_bvh_sample(c, worldPos, rnd(seed), inv_pdf);
+    return acc + light_contribution(c, c->lights[li], inv_pdf, true, mat, normal, view, worldPos, k);
+  }
+  for (size_t i = 0; i < c->lights.size(); ++i) acc = acc + light_contribution(c, c->lights[i], 1.0f, false, mat, normal, view, worldPos, k);
   return acc;
 }
 
@@ -381,7 +469,7 @@ void render_pixel(orc_context* c, const brt_uniform& u, const brt_render_opts& o
         c->aov_pos[pi] = Px4{worldPos.x, worldPos.y, worldPos.z, 1.0f};
         c->aov_nrm[pi] = Px4{N.x, N.y, N.z, h.t};
       }
-      vec3 color = calculate_color(c, mat, N, -V, worldPos, k);  // :160
+      vec3 color = calculate_color(c, mat, N, -V, worldPos, k, (o.flags & BRT_RENDER_LIGHT_BVH) != 0, seed);  // :160
       depth++;                                                   // :164
       csum = csum + color * prevWeight;                          // :122
       // bounce (SH/raytracing.slang:161-168). Verbatim: weight = 0 (indirect illumination deactivated).
@@ -652,6 +740,11 @@ int orc_render_frame(orc_context* c, const brt_uniform* u, const brt_render_opts
   size_t npx = (size_t)o->width * o->height;
   const uint32_t format = (o->flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
   if (format > BRT_FORMAT_B8G8R8A8_SRGB) return fail(c, BRT_ERR_INVALID, "render_frame: unknown BRT_RENDER_FORMAT");
+  if (o->flags & BRT_RENDER_LIGHT_BVH) {
+    for (const brt_light& l : c->lights)
+      if (l.type != BRT_LIGHT_POINT) return fail(c, BRT_ERR_STATE, "render_frame: BRT_RENDER_LIGHT_BVH needs POINT lights only");
+    light_bvh_build(c);
+  }
   std::vector<float> linear;
   float* rgba = rgba_out;
   if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {
@@ -775,6 +868,15 @@ int orc_denoise(orc_context* c, const brt_uniform* u, const brt_denoise_opts* d,
   next.eye[2] = u->viewInverse[11];
   c->dn = std::move(next);
   if (rgba) std::memcpy(rgba, work[cur].data(), npx * 16);
+  return BRT_OK;
+}
+
+int orc_get_light_bvh(orc_context* c, brt_light_bvh_node* out, uint32_t max_nodes, uint32_t* n_nodes) {
+  if (!c || !n_nodes) return fail(c, BRT_ERR_INVALID, "get_light_bvh: null");
+  if (!c->built) return fail(c, BRT_ERR_STATE, "get_light_bvh: scene not built");
+  light_bvh_build(c);
+  *n_nodes = (uint32_t)c->light_bvh.size();
+  if (out) std::memcpy(out, c->light_bvh.data(), std::min<size_t>(max_nodes, c->light_bvh.size()) * sizeof(brt_light_bvh_node));
   return BRT_OK;
 }
 

@@ -413,3 +413,60 @@ def denoiser(pkg, orc_mod, make, w=96, h=96):
     a.render_frame(u, a.opts(w, h, 1, flags))
     with pytest.raises(pkg.BrtError):
         a.denoise(u, a.denoise_opts(iterations=9), w, h)
+
+
+def light_bvh(pkg, orc_mod, make):
+    """Light BVH (LightBVHNode, RT/Scene.h:123-130; announced at SH/raytracing.slang:76): the tree is the oracle's, node for node;
+    frames lit by ONE importance-sampled light per hit are bit-identical to the oracle's — with far more lights than the loop
+    allows — and the estimator is unbiased: many samples converge to the full loop over the lights."""
+    LB = pkg.LIGHT_BVH
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    rng = np.random.default_rng(5)
+    extra = [((rng.random(3) * 1.6 - 0.8).tolist(), (0.2 + 0.8 * rng.random(3)).tolist(), float(0.02 + 0.2 * rng.random())) for _ in range(11)]
+    a, b = make(), orc_mod.Oracle(pkg)
+    for api in (a, b):
+        scene.upload(api, build=False)
+        for pos, col, inten in extra:
+            api.light_create(pos, col, inten)
+        api.scene_build()
+    n_lights = len(scene.lights) + len(extra)
+    assert n_lights <= 16
+    ta, tb = a.get_light_bvh(), b.get_light_bvh()
+    assert len(ta) == len(tb) == 2 * n_lights - 1
+    for x, y in zip(ta, tb):
+        assert bytes(x) == bytes(y)
+    leaves = sorted(-1 - n.childIndex for n in ta if n.childIndex < 0)
+    assert leaves == list(range(n_lights))  # every light in exactly one leaf
+    for n in ta:
+        if n.childIndex >= 0:
+            l, r = ta[n.childIndex], ta[n.childIndex + 1]
+            assert abs(n.totalFlux - (l.totalFlux + r.totalFlux)) <= 1e-5 * n.totalFlux
+            assert all(n.bBoxMin[k] <= min(l.bBoxMin[k], r.bBoxMin[k]) and n.bBoxMax[k] >= max(l.bBoxMax[k], r.bBoxMax[k]) for k in range(3))
+    w, h = 64, 64
+    u = scene.uniform(a, w, h, 3, 3)
+    for flags, spp in ((LB, 1), (LB | R | T | D | J, 2)):
+        r = compare_frames(pkg, a, b, u, w, h, flags, spp)
+        assert r["bit_exact"] and r["id_agreement"] == 1.0, flags
+        assert r["stats"].rays_occlusion == r["ref_stats"].rays_occlusion <= r["stats"].rays_closest  # at most one shadow ray per hit
+    # unbiased: 512 sampled frames average to the loop over all lights (direct light only, no other randomness)
+    full = a.render_frame(u, a.opts(w, h, 1, 0))[..., :3].astype(np.float64)
+    est = a.render_frame(u, a.opts(w, h, 512, LB))[..., :3].astype(np.float64)
+    tm = lambda x: x / (1.0 + x)
+    assert np.sqrt(((tm(est) - tm(full)) ** 2).mean()) < 0.02 * max(tm(full).mean(), 1e-6) + 0.004
+    one = a.render_frame(u, a.opts(w, h, 1, LB))[..., :3].astype(np.float64)
+    assert np.sqrt(((tm(one) - tm(full)) ** 2).mean()) > 4 * np.sqrt(((tm(est) - tm(full)) ** 2).mean())  # and it is an estimator
+    # more lights than BRT_MAX_LIGHTS: the loop refuses, the light BVH renders (and still matches the oracle)
+    for api in (a, b):
+        for k in range(40):
+            api.light_create(((k % 8) * 0.2 - 0.7, -0.6 + 0.03 * k, (k // 8) * 0.3 - 0.6), (1.0, 0.9 - 0.01 * k, 0.5 + 0.01 * k), 0.05)
+        api.scene_build()
+    with pytest.raises(pkg.BrtError):
+        a.render_frame(u, a.opts(w, h, 1, 0))
+    r = compare_frames(pkg, a, b, u, w, h, LB | D | J, 2)
+    assert r["bit_exact"]
+    assert len(a.get_light_bvh()) == 2 * (n_lights + 40) - 1
+    # a non-point light cannot go into the tree
+    a.light_create((0, 0, 0), (1, 1, 1), 1.0, type=2)
+    a.scene_build()
+    with pytest.raises(pkg.BrtError):
+        a.render_frame(u, a.opts(w, h, 1, LB))

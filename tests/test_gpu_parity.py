@@ -68,6 +68,10 @@ def test_denoiser(pkg, orc_mod, make):
     pc.denoiser(pkg, orc_mod, make)
 
 
+def test_light_bvh(pkg, orc_mod, make):
+    pc.light_bvh(pkg, orc_mod, make)
+
+
 def test_counters_match_plain_run(pkg, make):
     """The instrumented kernels (BRT_CFG_COUNTERS) produce the same image as the plain ones."""
     scene = pkg.scenes.make_scene("terrain", small=True)
