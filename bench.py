@@ -268,7 +268,7 @@ def run_product(args):
                 flush_small.fill_(i & 0xff)
             ctx.render_frame_async(u, opts, k, hosts[k].data_ptr() if to_host else None)
 
-        for i in range(warmup):
+        for i in range(max(warmup, 2)):  # at least one untimed frame per slot: a slot allocates its wavefront buffers on first use
             submit(i)
         ctx.frame_wait(0)
         ctx.frame_wait(1)

@@ -59,8 +59,8 @@ def main():
         print("|---|" + "---|" * len(cols))
         for label, cands, scale in ROWS:
             idx = None
-            for c in cands:
-                m = [i for i, h in enumerate(hdr) if h == c or h.endswith("." + c)]
+            for c in cands:  # several sections can carry a metric of the same name: take the first column that has values
+                m = [i for i, h in enumerate(hdr) if (h == c or h.endswith("." + c)) and any(r[i].strip() for r in data)]
                 if m:
                     idx = m[0]
                     break
