@@ -280,18 +280,19 @@ BRT_HD f3 sky_color(const brt_sky& s, f3 dir) {
   return c * s.brightness;
 }
 
-BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
+// Shading is split in two so that the CUDA kernel can compact the hits of a block before the expensive part (brt_api.cu):
+//   shade_prologue  every path slot: bookkeeping, primary-hit AOVs, and the whole miss shader; returns true for a hit
+//   shade_hit       rchitMain: geometry fetch, BRDF x lights, shadow rays, bounce
+BRT_HD bool shade_prologue(const ShadeParams& p, uint32_t i) {
   const uint32_t px = p.cur.px[i];
   if (i == 0) p.sctr->n_items = p.count_ptr ? *p.count_ptr : p.count;
   {
     const float4 w = p.cur.w[i];
     p.aux[i] = make_float4(w.x, w.y, w.z, u2f(px));
   }
-  if (px == BRT_MISS) return;
+  if (px == BRT_MISS) return false;
   const bool lbvh = (p.flags & BRT_RENDER_LIGHT_BVH) != 0u;  // one stochastically chosen light per hit instead of the loop
   const uint32_t n_slots = (p.n_lights && !lbvh) ? p.n_lights : 1u;
-  const float4 ro = p.cur.o[i], rd = p.cur.d[i];
-  const f3 ray_o = F3(ro.x, ro.y, ro.z), ray_d = F3(rd.x, rd.y, rd.z);
   const uint32_t inst_id = p.hit_inst[i];
   const float4 hit = p.hit[i];
   if (p.write_aov && (px >> BRT_SLOT_BITS) == 0u) {
@@ -304,11 +305,25 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   }
   if (inst_id == BRT_MISS) {  // rmissMain :172-176
     f3 c = F3(0.0f);
-    if (p.flags & BRT_RENDER_SKY) c = sky_color(p.sky, ray_d);
+    if (p.flags & BRT_RENDER_SKY) {
+      const float4 rd = p.cur.d[i];
+      c = sky_color(p.sky, F3(rd.x, rd.y, rd.z));
+    }
     p.contrib[i] = make_float4(c.x, c.y, c.z, 0.0f);
     for (uint32_t l = 1; l < n_slots; ++l) p.contrib[(size_t)l * p.cap + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    return;
+    return false;
   }
+  return true;
+}
+
+BRT_HD void shade_hit(const ShadeParams& p, uint32_t i) {
+  const uint32_t px = p.cur.px[i];
+  const bool lbvh = (p.flags & BRT_RENDER_LIGHT_BVH) != 0u;
+  const uint32_t n_slots = (p.n_lights && !lbvh) ? p.n_lights : 1u;
+  const float4 ro = p.cur.o[i], rd = p.cur.d[i];
+  const f3 ray_o = F3(ro.x, ro.y, ro.z), ray_d = F3(rd.x, rd.y, rd.z);
+  const uint32_t inst_id = p.hit_inst[i];
+  const float4 hit = p.hit[i];
   // rchitMain :136-169
   const InstShade& in = p.inst[inst_id];
   const float4 o2w[3] = {in.o2w[0], in.o2w[1], in.o2w[2]};
@@ -432,6 +447,10 @@ BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   p.next.w[k] = make_float4(weight.x, weight.y, weight.z, 0.0f);
   p.next.px[k] = px;
   p.next.seed[k] = seed;
+}
+
+BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
+  if (shade_prologue(p, i)) shade_hit(p, i);
 }
 
 // ---- accumulate ------------------------------------------------------------------------------------
