@@ -237,6 +237,7 @@ struct FrameSlot {
   DevBuf d_aov_pos, d_aov_nrm;  // BRT_RENDER_GBUFFER
   bool has_gbuffer = false;
   uint32_t render_flags = 0;  // of the frame rendered last on this slot
+  DevBuf d_alive;  // rounds that contributed per (sample in batch, slot)
   DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   std::deque<EventPair> events;  // deque: references stay valid while the pool grows
   size_t events_used = 0;
@@ -602,6 +603,7 @@ void ensure_frame_buffers(brt_context* c, FrameSlot* f, const brt_render_opts& o
   f->d_hit.ensure(capw * 16);
   f->d_hit_inst.ensure(capw * 4);
   f->d_rad.ensure(capw * 16 * R);
+  f->d_alive.ensure(capw * 4);
   f->d_accum.ensure((size_t)cap * 16);
   f->d_image.ensure(npx * 16);
   f->d_tiles.ensure((size_t)cap * 16);
@@ -691,7 +693,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   for (uint32_t sample = 0; sample < o.spp; sample += f->batch) {
     const uint32_t nb = std::min(f->batch, o.spp - sample);  // samples in this wavefront
     const uint32_t capw = cap * nb;                          // its path slots
-    if (rounds) BRT_CUDA(cudaMemsetAsync(f->d_rad.ptr(), 0, (size_t)capw * rounds * 16, s));
+    if (rounds) BRT_CUDA(cudaMemsetAsync(f->d_alive.ptr(), 0, (size_t)capw * 4, s));  // (the radiance terms themselves need no clearing)
     {
       RaygenParams rp;
       rp.count = capw;
@@ -825,6 +827,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
         ap.rounds = rounds;
         ap.round = round;
         ap.rad = f->d_rad.as<float4>();
+        ap.alive = f->d_alive.as<uint32_t>();
         Timed t(f, CLS_ACCUM, s2);
         BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, capw, 256, 8), 256, s2);
         BRT_CHECK_LAUNCH();
@@ -846,6 +849,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
       sp.samples = nb;
       sp.rounds = rounds;
       sp.rad = f->d_rad.as<float4>();
+      sp.alive = f->d_alive.as<uint32_t>();
       sp.accum = f->d_accum.as<float4>();
       Timed t(f, CLS_ACCUM, s);
       BRT_LAUNCH_1D(k_sum_samples, sp, grid_for(c, cap, 256, 8), 256, s);

@@ -465,6 +465,7 @@ struct AccumParams {
   uint32_t n_slots, cap;   // light slots; stride of contrib per light (= slots of the whole batch)
   uint32_t slots, rounds, round;  // path slots per sample, depth rounds per sample, this round
   float4* rad;        // [sample in batch][round][slot]
+  uint32_t* alive;    // [sample in batch][slot]: rounds that wrote a term so far (rad is NOT cleared: k_sum_samples reads only these)
 };
 BRT_HD void accumulate_body(const AccumParams& p, uint32_t i) {
   const float4 w = p.aux[i];
@@ -478,6 +479,7 @@ BRT_HD void accumulate_body(const AccumParams& p, uint32_t i) {
   }
   const uint32_t sib = id >> BRT_SLOT_BITS, slot = id & BRT_SLOT_MASK;
   p.rad[((size_t)sib * p.rounds + p.round) * p.slots + slot] = make_float4(c.x * w.x, c.y * w.y, c.z * w.z, 0.0f);
+  p.alive[(size_t)sib * p.slots + slot] = p.round + 1u;  // a path is in the queue of every round up to its last: rounds arrive in order
 }
 
 struct SumSamplesParams {
@@ -485,17 +487,20 @@ struct SumSamplesParams {
   const uint32_t* count_ptr;
   uint32_t samples, rounds;
   const float4* rad;
+  const uint32_t* alive;  // rounds of (sample, slot) that wrote a term
   float4* accum;   // per slot running sum over all samples so far
 };
 BRT_HD void sum_samples_body(const SumSamplesParams& p, uint32_t i) {
   float4 a = p.accum[i];
-  for (uint32_t s = 0; s < p.samples; ++s)
-    for (uint32_t r = 0; r < p.rounds; ++r) {
+  for (uint32_t s = 0; s < p.samples; ++s) {
+    const uint32_t n = p.alive[(size_t)s * p.count + i];  // terms of dead rounds would be + 0: skipped, never written, never cleared
+    for (uint32_t r = 0; r < n; ++r) {
       const float4 t = p.rad[((size_t)s * p.rounds + r) * p.count + i];
       a.x = a.x + t.x;  // :122
       a.y = a.y + t.y;
       a.z = a.z + t.z;
     }
+  }
   p.accum[i] = a;
 }
 
