@@ -385,6 +385,11 @@ def run_product(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per step of this kernel from the committed ncu capture
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.config, {}).get(which)
+        issue = None
+        ipath = os.path.join(ROOT, "profiles", "issue.json")  # issue-slot utilisation of the same kernels from the committed ncu capture
+        if os.path.exists(ipath):
+            ij = json.load(open(ipath))
+            issue = {"pct_of_peak_issue_slots": ij.get(args.config, {}).get(which), "metric": ij.get("metric"), "source": ij.get("source")}
         roofline = {"bound": "hbm", "kernel": f"k_trace<{'false' if which == 'closest' else 'true'}> ({which}-hit traversal)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                     "traffic": traffic, "algorithmic_bytes_per_step": int(kbytes), "kernel_ms_per_step": kms,
@@ -394,6 +399,7 @@ def run_product(args):
                     "prims_per_ray": (cst.prims_tested_closest / max(cst.rays_closest, 1)) if which == "closest"
                     else (cst.prims_tested_occlusion / max(cst.rays_occlusion, 1)),
                     "serial_schedule_ms_per_step": ms_serial,
+                    "binding_resource": "instruction issue (not bytes): see issue_ncu", "issue_ncu": issue,
                     "l2_read_gbs_measured": l2_best, "frac_of_l2_read": achieved / l2_best if l2_best > 0 else None,
                     "note": "kernel time from the serial-schedule pass (see kernel_ms_per_step); the BVH (nodes + triangle records) fits "
                             "the 126 MB L2, so these fetches are served by L1/L2 after first touch and the kernel is bound by instruction "
