@@ -185,7 +185,7 @@ struct Traversal {
       const uint32_t slot = (uint32_t)(bit - 24) ^ rb.octinv;
       const uint32_t rel = popc(G.y & ~(0xffffffffu << slot));
       if (COUNT) ctr.nodes++;
-      intersect_node(nodes + G.x + rel, rb, co, tmin, best.t, G, Gt);
+      intersect_node(nodes + (uint32_t)(G.x + rel), rb, co, tmin, best.t, G, Gt);  // 32-bit index: one IMAD.WIDE
     } else {
       Gt = G;
       G = make_uint2(0u, 0u);
@@ -197,7 +197,7 @@ struct Traversal {
       Gt.y &= Gt.y - 1u;
       const uint32_t rank = (uint32_t)popc((Gt.y >> 8) & ~(0xffffffffu << slot));
       if (blas_sp >= 0) {
-        const TriRec* tr = tris + Gt.x + rank;
+        const TriRec* tr = tris + (uint32_t)(Gt.x + rank);
         const float4 a = ldg4(&tr->v0), b = ldg4(&tr->v1), c = ldg4(&tr->v2);
         if (COUNT) ctr.prims++;
         float t, u, v;
@@ -210,7 +210,7 @@ struct Traversal {
           }
         }
       } else {
-        const InstRec* ir = insts + Gt.x + rank;
+        const InstRec* ir = insts + (uint32_t)(Gt.x + rank);
         const float4 m0 = ldg4(&ir->w2o[0]), m1 = ldg4(&ir->w2o[1]), m2 = ldg4(&ir->w2o[2]);
         const uint4 tail = ldg4(reinterpret_cast<const uint4*>(&ir->kind));
         const float4 m[3] = {m0, m1, m2};
