@@ -58,6 +58,77 @@ BRT_HD void mesh_bounds_body(const MeshBoundsParams& p, uint32_t) {
 }
 BRT_KERNEL_1D(k_mesh_bounds, MeshBoundsParams, mesh_bounds_body)
 
+#ifndef BRT_EMU
+#define BRT_SMALL_BUILD_MAX 4096u
+#define BRT_SMALL_BUILD_THREADS 512
+struct SmallBuildParams {
+  uint32_t n;
+  MortonParams morton;     // writes keys / vals (unsorted)
+  uint32_t* keys_sorted;
+  uint32_t* vals_sorted;
+  HierarchyParams hier;
+  RefitParams refit;
+  CollapseParams collapse; // level / queues / count_ptr are set per level by the kernel
+  uint2* queue[2];
+  float4* mesh_bounds;     // may be null
+};
+__global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const SmallBuildParams p) {
+  __shared__ unsigned long long sk[BRT_SMALL_BUILD_MAX];  // (Morton key << 32 | primitive): unique, so the sort is stable by construction
+  const uint32_t tid = threadIdx.x, nt = blockDim.x, n = p.n;
+  uint32_t np2 = 2;
+  while (np2 < n) np2 <<= 1;
+  for (uint32_t i = tid; i < np2; i += nt) {
+    if (i < n) {
+      morton_body(p.morton, i);
+      sk[i] = ((unsigned long long)p.morton.keys[i] << 32) | i;
+    } else {
+      sk[i] = ~0ull;
+    }
+  }
+  for (uint32_t i = tid; i < 2 * n; i += nt) p.hier.parent[i] = 0xffffffffu;
+  for (uint32_t i = tid; i < n; i += nt) p.refit.arrive[i] = 0u;
+  __syncthreads();
+  for (uint32_t k = 2; k <= np2; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < np2; i += nt) {
+        const uint32_t l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = sk[i], b = sk[l];
+          if ((a > b) == ((i & k) == 0u)) { sk[i] = b; sk[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t i = tid; i < n; i += nt) {
+    p.keys_sorted[i] = (uint32_t)(sk[i] >> 32);
+    p.vals_sorted[i] = (uint32_t)sk[i];
+  }
+  __threadfence();
+  __syncthreads();
+  for (uint32_t i = tid; i + 1 < n; i += nt) hierarchy_body(p.hier, i);
+  __threadfence();
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nt) refit_body(p.refit, i);
+  __threadfence();
+  __syncthreads();
+  CollapseParams cp = p.collapse;
+  for (uint32_t level = 0; level < 62; ++level) {
+    const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&cp.g->level_count[level]);
+    if (count == 0u) break;  // block-uniform
+    cp.level = level;
+    cp.queue_in = p.queue[level & 1];
+    cp.queue_out = p.queue[(level + 1) & 1];
+    for (uint32_t i = tid; i < count; i += nt) collapse_body(cp, i);
+    __threadfence();
+    __syncthreads();
+  }
+  if (p.mesh_bounds && tid == 0) {
+    MeshBoundsParams mb{1, nullptr, cp.g, p.mesh_bounds};
+    mesh_bounds_body(mb, 0);
+  }
+}
+#endif
+
 void Builder::ensure_scratch(uint32_t n) {
   const size_t N = n;
   globals_.ensure(sizeof(BuildGlobals));
@@ -82,101 +153,142 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
   // prim_lo_/prim_hi_ and globals_->bounds have been filled by the caller
   BuildGlobals* g = globals_.as<BuildGlobals>();
   const uint32_t grid_n = std::max(1u, std::min(div_up(n, 256u), (uint32_t)sm_count_ * 8u));
-  {
-    MortonParams p{n, nullptr, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g, keys_[0].as<uint32_t>(), vals_[0].as<uint32_t>()};
-    BRT_LAUNCH_1D(k_morton, p, grid_n, 256, stream);
-    BRT_CHECK_LAUNCH();
-  }
-  uint32_t* keys = keys_[0].as<uint32_t>();
-  uint32_t* vals = vals_[0].as<uint32_t>();
-  if (n > 1) {
-    int out = radix_sort_pairs(stream, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(), vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), n,
-                               30, sort_tmp_.ptr(), sort_tmp_.capacity(), sm_count_);
-    keys = keys_[out].as<uint32_t>();
-    vals = vals_[out].as<uint32_t>();
-  }
-  BNode* nodes = nodes_.as<BNode>();
-  uint32_t* parent = parent_.as<uint32_t>();
-  uint32_t* sub_count = sub_count_.as<uint32_t>();
-  BRT_CUDA(cudaMemsetAsync(parent, 0xff, (size_t)(2 * n) * 4, stream));
-  if (n > 1) {
-    BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
-    HierarchyParams p{n - 1, nullptr, n, keys, nodes, parent};
-    BRT_LAUNCH_1D(k_hierarchy, p, grid_n, 256, stream);
-    BRT_CHECK_LAUNCH();
-  }
-  {
-    RefitParams p{n, nullptr, vals, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes, parent, arrive_.as<uint32_t>(), sub_count};
-    BRT_LAUNCH_1D(k_refit, p, grid_n, 256, stream);
-    BRT_CHECK_LAUNCH();
-  }
-  // SAH cost of the LBVH, then SAH treelet restructuring (triangle BLAS only)
   float cost_before = 0.0f, cost_after = 0.0f;
   BNode root_before{}, root_after{};
   const bool want_sah = out_tris != nullptr && n > 1;
-  const bool do_treelets = treelets && want_sah && n >= 2 * BRT_TREELET_LEAVES;
-  if (want_sah) {
-    float* cost = treelet_.as<float>();
-    const uint32_t grid_t = std::max(1u, std::min(div_up(n, 64u), (uint32_t)sm_count_ * 16u));
-    const int passes = do_treelets ? 3 : 0;
-    for (int pass = 0; pass <= passes; ++pass) {
-      BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
-      TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, pass == 0 ? 0u : 1u};
-#ifdef BRT_EMU
-      BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);
-#else
-      if (pass == 0) BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);  // cost only: one thread per leaf is enough
-      else k_treelet_warp<<<std::max(1u, std::min(div_up(n, 128u), (uint32_t)sm_count_ * 8u)), 128, 0, stream>>>(tp);
-#endif
-      BRT_CHECK_LAUNCH();
-      if (pass == 0) {
-        BRT_CUDA(cudaMemcpyAsync(&cost_before, cost, 4, cudaMemcpyDeviceToHost, stream));
-        BRT_CUDA(cudaMemcpyAsync(&root_before, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
-      }
-    }
-    BRT_CUDA(cudaMemcpyAsync(&cost_after, cost, 4, cudaMemcpyDeviceToHost, stream));
-    BRT_CUDA(cudaMemcpyAsync(&root_after, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
-  }
-  // collapse, level by level; the per-level work count lives on the device
-  const uint32_t node_cap = node_capacity(n);
-  const uint32_t queue_cap = n / 2 + 8;
-  CollapseParams cp{};
-  cp.n = n;
-  cp.max_leaf = max_leaf;
-  cp.nodes = nodes;
-  cp.sub_count = sub_count;
-  cp.queue_cap = queue_cap;
-  cp.g = g;
-  cp.out_nodes = out_nodes;
-  cp.node_cap = node_cap;
-  cp.vertices = d_vertices;
-  cp.indices = d_indices;
-  cp.out_tris = out_tris;
-  cp.src_inst = d_src;
-  cp.out_inst = out_inst;
   BuildGlobals hg;
   uint32_t level = 0;
-  for (;;) {
-    const uint32_t chunk_end = level + 8;
-    for (; level < chunk_end && level < 62; ++level) {
-      cp.level = level;
-      cp.count = 0;
-      cp.count_ptr = &g->level_count[level];
-      cp.queue_in = queue_[level & 1].as<uint2>();
-      cp.queue_out = queue_[(level + 1) & 1].as<uint2>();
-      // level L has at most min(8^L, queue_cap) items
-      uint64_t max_items = 1;
-      for (uint32_t k = 0; k < level && max_items < queue_cap; ++k) max_items *= 8;
-      max_items = std::min<uint64_t>(max_items, queue_cap);
-      const uint32_t grid = std::max(1u, std::min(div_up((uint32_t)max_items, 64u), (uint32_t)sm_count_ * 16u));
-      BRT_LAUNCH_1D(k_collapse, cp, grid, 64, stream);
-      BRT_CHECK_LAUNCH();
-    }
+  bool small = false;
+#ifndef BRT_EMU
+  // Small builds (the per-frame TLAS over a few hundred instances): the ~30 dependent launches of the general path cost far more
+  // in launch latency than in work, so ONE block runs the whole pipeline — Morton codes, a bitonic sort of (key, index) pairs in
+  // shared memory, Karras hierarchy, bottom-up refit, level-by-level collapse — with __syncthreads() between the phases.
+  if (out_tris == nullptr && n >= 2 && n <= BRT_SMALL_BUILD_MAX) {
+    SmallBuildParams sp{};
+    sp.n = n;
+    sp.morton = MortonParams{n, nullptr, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g, keys_[0].as<uint32_t>(), vals_[0].as<uint32_t>()};
+    sp.keys_sorted = keys_[1].as<uint32_t>();
+    sp.vals_sorted = vals_[1].as<uint32_t>();
+    sp.hier = HierarchyParams{n - 1, nullptr, n, sp.keys_sorted, nodes_.as<BNode>(), parent_.as<uint32_t>()};
+    sp.refit = RefitParams{n, nullptr, sp.vals_sorted, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes_.as<BNode>(), parent_.as<uint32_t>(),
+                           arrive_.as<uint32_t>(), sub_count_.as<uint32_t>()};
+    CollapseParams& cp = sp.collapse;
+    cp.n = n;
+    cp.max_leaf = max_leaf;
+    cp.nodes = nodes_.as<BNode>();
+    cp.sub_count = sub_count_.as<uint32_t>();
+    cp.queue_cap = n / 2 + 8;
+    cp.g = g;
+    cp.out_nodes = out_nodes;
+    cp.node_cap = node_capacity(n);
+    cp.vertices = d_vertices;
+    cp.indices = d_indices;
+    cp.out_tris = out_tris;
+    cp.src_inst = d_src;
+    cp.out_inst = out_inst;
+    sp.queue[0] = queue_[0].as<uint2>();
+    sp.queue[1] = queue_[1].as<uint2>();
+    sp.mesh_bounds = d_mesh_bounds;
+    k_build_small<<<1, BRT_SMALL_BUILD_THREADS, 0, stream>>>(sp);
+    BRT_CHECK_LAUNCH();
     BRT_CUDA(cudaMemcpyAsync(&hg, g, sizeof(hg), cudaMemcpyDeviceToHost, stream));
     BRT_CUDA(cudaStreamSynchronize(stream));
-    if (level >= 62 || hg.level_count[level] == 0) break;
+    for (level = 0; level < 62 && hg.level_count[level] != 0; ++level) {}
+    small = true;
   }
-  if (d_mesh_bounds) {
+#endif
+  if (!small) {
+    {
+      MortonParams p{n, nullptr, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g, keys_[0].as<uint32_t>(), vals_[0].as<uint32_t>()};
+      BRT_LAUNCH_1D(k_morton, p, grid_n, 256, stream);
+      BRT_CHECK_LAUNCH();
+    }
+    uint32_t* keys = keys_[0].as<uint32_t>();
+    uint32_t* vals = vals_[0].as<uint32_t>();
+    if (n > 1) {
+      int out = radix_sort_pairs(stream, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(), vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), n,
+                                 30, sort_tmp_.ptr(), sort_tmp_.capacity(), sm_count_);
+      keys = keys_[out].as<uint32_t>();
+      vals = vals_[out].as<uint32_t>();
+    }
+    BNode* nodes = nodes_.as<BNode>();
+    uint32_t* parent = parent_.as<uint32_t>();
+    uint32_t* sub_count = sub_count_.as<uint32_t>();
+    BRT_CUDA(cudaMemsetAsync(parent, 0xff, (size_t)(2 * n) * 4, stream));
+    if (n > 1) {
+      BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
+      HierarchyParams p{n - 1, nullptr, n, keys, nodes, parent};
+      BRT_LAUNCH_1D(k_hierarchy, p, grid_n, 256, stream);
+      BRT_CHECK_LAUNCH();
+    }
+    {
+      RefitParams p{n, nullptr, vals, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes, parent, arrive_.as<uint32_t>(), sub_count};
+      BRT_LAUNCH_1D(k_refit, p, grid_n, 256, stream);
+      BRT_CHECK_LAUNCH();
+    }
+    // SAH cost of the LBVH, then SAH treelet restructuring (triangle BLAS only)
+    const bool do_treelets = treelets && want_sah && n >= 2 * BRT_TREELET_LEAVES;
+    if (want_sah) {
+      float* cost = treelet_.as<float>();
+      const uint32_t grid_t = std::max(1u, std::min(div_up(n, 64u), (uint32_t)sm_count_ * 16u));
+      const int passes = do_treelets ? 3 : 0;
+      for (int pass = 0; pass <= passes; ++pass) {
+        BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
+        TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, pass == 0 ? 0u : 1u};
+  #ifdef BRT_EMU
+        BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);
+  #else
+        if (pass == 0) BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);  // cost only: one thread per leaf is enough
+        else k_treelet_warp<<<std::max(1u, std::min(div_up(n, 128u), (uint32_t)sm_count_ * 8u)), 128, 0, stream>>>(tp);
+  #endif
+        BRT_CHECK_LAUNCH();
+        if (pass == 0) {
+          BRT_CUDA(cudaMemcpyAsync(&cost_before, cost, 4, cudaMemcpyDeviceToHost, stream));
+          BRT_CUDA(cudaMemcpyAsync(&root_before, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
+        }
+      }
+      BRT_CUDA(cudaMemcpyAsync(&cost_after, cost, 4, cudaMemcpyDeviceToHost, stream));
+      BRT_CUDA(cudaMemcpyAsync(&root_after, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
+    }
+    // collapse, level by level; the per-level work count lives on the device
+    const uint32_t node_cap = node_capacity(n);
+    const uint32_t queue_cap = n / 2 + 8;
+    CollapseParams cp{};
+    cp.n = n;
+    cp.max_leaf = max_leaf;
+    cp.nodes = nodes;
+    cp.sub_count = sub_count;
+    cp.queue_cap = queue_cap;
+    cp.g = g;
+    cp.out_nodes = out_nodes;
+    cp.node_cap = node_cap;
+    cp.vertices = d_vertices;
+    cp.indices = d_indices;
+    cp.out_tris = out_tris;
+    cp.src_inst = d_src;
+    cp.out_inst = out_inst;
+    for (;;) {
+      const uint32_t chunk_end = level + 8;
+      for (; level < chunk_end && level < 62; ++level) {
+        cp.level = level;
+        cp.count = 0;
+        cp.count_ptr = &g->level_count[level];
+        cp.queue_in = queue_[level & 1].as<uint2>();
+        cp.queue_out = queue_[(level + 1) & 1].as<uint2>();
+        // level L has at most min(8^L, queue_cap) items
+        uint64_t max_items = 1;
+        for (uint32_t k = 0; k < level && max_items < queue_cap; ++k) max_items *= 8;
+        max_items = std::min<uint64_t>(max_items, queue_cap);
+        const uint32_t grid = std::max(1u, std::min(div_up((uint32_t)max_items, 64u), (uint32_t)sm_count_ * 16u));
+        BRT_LAUNCH_1D(k_collapse, cp, grid, 64, stream);
+        BRT_CHECK_LAUNCH();
+      }
+      BRT_CUDA(cudaMemcpyAsync(&hg, g, sizeof(hg), cudaMemcpyDeviceToHost, stream));
+      BRT_CUDA(cudaStreamSynchronize(stream));
+      if (level >= 62 || hg.level_count[level] == 0) break;
+    }
+  }
+  if (d_mesh_bounds && !small) {
     MeshBoundsParams p{1, nullptr, g, d_mesh_bounds};
     BRT_LAUNCH_1D(k_mesh_bounds, p, 1, 32, stream);
     BRT_CHECK_LAUNCH();
