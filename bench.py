@@ -461,8 +461,8 @@ def run_product(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default=None, choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE config; default: c2 (1080p, the single-GPU headline) at N=1, c3 (4K, 16 spp, 4-bounce GI: the "

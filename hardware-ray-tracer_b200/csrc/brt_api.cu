@@ -28,26 +28,30 @@ BRT_KERNEL_1D(k_raygen, RaygenParams, raygen_body)
 #ifdef BRT_EMU
 BRT_KERNEL_1D_LB(k_shade, ShadeParams, shade_body, 128, BRT_SHADE_MIN_BLOCKS)
 #else
+// primary round: the wavefront is in pixel order, hits and misses come in large coherent runs — one path per thread, no compaction
+BRT_KERNEL_1D_LB(k_shade_primary, ShadeParams, shade_body, 128, BRT_SHADE_MIN_BLOCKS)
 // Shade with block-level hit compaction. After the first bounce the hits and misses of a wavefront are interleaved at random, and the
 // hit shader (geometry fetch, BRDF per light, shadow-ray emission, bounce sampling: ~95 % of the kernel's instructions) ran with ~6 of
 // 32 lanes active (ncu, profiles/). Each block therefore first runs the cheap prologue for its 128 path slots (bookkeeping, AOVs, the
-// whole miss shader) — K times: the primary round (coherent, mostly hits) uses K = 1, the bounce rounds K = BRT_SHADE_WINDOW so that
-// the window is 512 slots and the dependent-load latency of the hit shader is paid once per window —, compacts the indices of the hits into shared memory (ballot + per-warp prefix), and then shades the compacted list with
+// whole miss shader) — K = BRT_SHADE_WINDOW times, so that the window is 512 slots and the dependent-load latency of the hit shader is
+// paid once per window —, compacts the indices of the hits into shared memory (ballot + per-warp prefix), and then shades the compacted list with
 // full warps. Which thread shades which path is irrelevant: every output is addressed by the path slot.
 template <uint32_t K>
 __global__ void __launch_bounds__(128, BRT_SHADE_MIN_BLOCKS) k_shade(const ShadeParams p) {
-  constexpr uint32_t SLOTS = 128u * K;
-  __shared__ uint32_t s_idx[SLOTS];
+  __shared__ uint32_t s_idx[128u * K];
   __shared__ uint32_t s_warp[4 * K];
   const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
+  // a short queue (fewer than K chunks per block) is latency-bound on the number of blocks in flight: window of one chunk then
+  const uint32_t kk = n >= K * 128u * gridDim.x ? K : 1u;
+  const uint32_t slots = 128u * kk;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t base = blockIdx.x * SLOTS; base < n; base += gridDim.x * SLOTS) {  // block-uniform trip count
+  for (uint32_t base = blockIdx.x * slots; base < n; base += gridDim.x * slots) {  // block-uniform trip count
     bool is_hit[K];
     unsigned m[K];
 #pragma unroll
     for (uint32_t k = 0; k < K; ++k) {
       const uint32_t i = base + k * 128u + threadIdx.x;
-      is_hit[k] = i < n && shade_prologue(p, i);
+      is_hit[k] = k < kk && i < n && shade_prologue(p, i);
       m[k] = __ballot_sync(0xffffffffu, is_hit[k]);
       if (lane == 0) s_warp[k * 4 + warp] = (uint32_t)__popc(m[k]);
     }
@@ -784,8 +788,8 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
 #ifdef BRT_EMU
         BRT_LAUNCH_1D(k_shade, sp, 1, 128, s);
 #else
-        if (round == 0) k_shade<1><<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
-        else k_shade<BRT_SHADE_WINDOW><<<grid_for(c, capw, 128 * BRT_SHADE_WINDOW, 16), 128, 0, s>>>(sp);
+        if (round == 0) k_shade_primary<<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
+        else k_shade<BRT_SHADE_WINDOW><<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
 #endif
         BRT_CHECK_LAUNCH();
         launches++;

@@ -124,3 +124,22 @@ def test_radix_sort_pairs(pkg, make, n, bits):
     order = np.argsort(keys & mask, kind="stable")
     assert np.array_equal(v, order.astype(np.uint32))
     assert np.array_equal(k, keys[order])
+
+
+@pytest.mark.parametrize("n_side", [2, 16, 17])
+def test_tlas_sizes_vs_brute_force(pkg, orc_mod, make, n_side):
+    """TLAS builds on both sides of the single-block small-build limit (4096 instances; 17^3 = 4913 takes the general path, 2^3 and
+    16^3 = 4096 the one-launch path): closest and any-hit queries equal the oracle's brute force over all instances."""
+    from util import random_rays
+    scene = pkg.scenes.instanced_lattice(n_side, 0, animated=False)
+    a, b = make(), orc_mod.Oracle(pkg, brute_force=True)
+    scene.upload(a)
+    scene.upload(b)
+    assert a.get_stats().instances_visible == n_side ** 3
+    half = n_side * 1.6 + 1.0
+    rays = random_rays(6000, 21 + n_side, (-half, -half, 14.0 - half), (half, half, 14.0 + half))
+    rays[::4, 7] = np.random.default_rng(9).random(len(rays[::4])).astype(np.float32) * 10.0
+    ha, hb = a.trace_rays(rays, True), b.trace_rays(rays, True)
+    assert np.array_equal(ha, hb)
+    assert hb[:, 3].sum() > 300
+    assert np.array_equal(a.trace_rays(rays, False)[:, 3], b.trace_rays(rays, False)[:, 3])
