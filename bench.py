@@ -209,7 +209,8 @@ def run_product(args):
         frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="nccl")
     host_image = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    pipelined = world == 1 and args.frames_in_flight == 2
+    pipelined = world == 1 and args.frames_in_flight >= 2
+    n_slots = args.frames_in_flight
 
     def step_device():
         """one frame, result left in HBM (un-tiled full frame on every rank)"""
@@ -258,32 +259,32 @@ def run_product(args):
         MAX_FRAMES_IN_FLIGHT = 2, VK/SwapChain.h:8). K frames are enqueued alternately on the two frame slots; ONE timed
         region brackets all K steps (synchronize on both sides, CUDA events on the slots' streams). The L2 flush (a write
         larger than L2) of every step is enqueued on the frame's stream right before the frame, INSIDE the timed region."""
-        streams = [torch.cuda.ExternalStream(ctx.frame_stream(k), device=dev) for k in range(2)]
-        hosts = [host_image, host_image2]
+        streams = [torch.cuda.ExternalStream(ctx.frame_stream(k), device=dev) for k in range(n_slots)]
+        hosts = host_images
 
         def submit(i):
-            k = i % 2
-            ctx.frame_wait(k)  # the slot's fence: frame i-2 (and its copy to the host) is complete
+            k = i % n_slots
+            ctx.frame_wait(k)  # the slot's fence: frame i - n_slots (and its copy to the host) is complete
             with torch.cuda.stream(streams[k]):
                 flush_small.fill_(i & 0xff)
             ctx.render_frame_async(u, opts, k, hosts[k].data_ptr() if to_host else None)
 
-        for i in range(max(warmup, 2)):  # at least one untimed frame per slot: a slot allocates its wavefront buffers on first use
+        for i in range(max(warmup, n_slots)):  # at least one untimed frame per slot: a slot allocates its wavefront buffers on first use
             submit(i)
-        ctx.frame_wait(0)
-        ctx.frame_wait(1)
+        for k in range(n_slots):
+            ctx.frame_wait(k)
         sync_all()
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record(streams[0])
         for i in range(steps):
             submit(i)
         ends = []
-        for k in range(2):
+        for k in range(n_slots):
             e = torch.cuda.Event(enable_timing=True)
             e.record(streams[k])
             ends.append(e)
-        ctx.frame_wait(0)
-        ctx.frame_wait(1)
+        for k in range(n_slots):
+            ctx.frame_wait(k)
         torch.cuda.synchronize()
         if collect is not None:
             for _ in range(steps):
@@ -291,7 +292,7 @@ def run_product(args):
         return max(e0.elapsed_time(e) for e in ends) / steps
 
     if pipelined:
-        host_image2 = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
+        host_images = [host_image] + [torch.empty(h * w * 4, dtype=torch.float32).pin_memory() for _ in range(n_slots - 1)]
         flush_small = torch.empty(160 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     kstats = {"closest": 0.0, "occl": 0.0, "shade": 0.0, "other": 0.0, "n": 0, "launches": 0, "rays": 0}
@@ -413,9 +414,9 @@ def run_product(args):
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(bench_config(scene, cfg, args), exchange=exchange, **(
-                {"frames_in_flight": 2, "l2": "flushed before every frame (160 MiB write enqueued on the frame's stream, inside the timed region)",
-                 "schedule": "K frames alternate over 2 frame slots (brt_render_frame_async / brt_frame_wait, as the reference's "
-                             "MAX_FRAMES_IN_FLIGHT = 2); one timed region around all K steps"} if pipelined else {"frames_in_flight": 1})),
+                {"frames_in_flight": n_slots, "l2": "flushed before every frame (160 MiB write enqueued on the frame's stream, inside the timed region)",
+                 "schedule": f"K frames rotate over {n_slots} frame slots (brt_render_frame_async / brt_frame_wait; the reference keeps "
+                             "MAX_FRAMES_IN_FLIGHT = 2 frames in flight); one timed region around all K steps"} if pipelined else {"frames_in_flight": 1})),
             "rays_per_step": int(rays), "single_frame_latency": frame_latency,
             "e2e_bgra8": ({"value": rays / (ms_e2e_bgra8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e_bgra8,
                            "d2h_bytes_per_step": w * h * 4, "format": "B8G8R8A8_UNORM"} if pipelined else None),
@@ -468,8 +469,9 @@ def main():
                     help="BASELINE config; default: c2 (1080p, the single-GPU headline) at N=1, c3 (4K, 16 spp, 4-bounce GI: the "
                          "configuration BASELINE.json quotes for 1/2/4/8 GPUs) at N>1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
-                    help="N = 1: 2 = frames alternate over two frame slots (default, the reference keeps 2 frames in flight); "
+    ap.add_argument("--frames-in-flight", type=int, default=3, choices=[1, 2, 3],
+                    help="N = 1: frames rotate over this many frame slots (the reference keeps 2 frames in flight over a swapchain of "
+                         "typically 3 images; the third slot lets the copy-out of frame k-2 finish while frame k is submitted); "
                          "1 = every step is one synchronous brt_render_frame call")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: framebuffer exchange — p2p = resolve kernel stores into every rank's frame through NVLink peer memory "

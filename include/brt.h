@@ -256,7 +256,7 @@ BRT_API int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_r
  * brt_frame_wait(slot) returns when that frame and its copy are complete and folds its timings into brt_get_stats.
  * The latency-bound tail of one frame's wavefronts then overlaps the head of the next one. Scene-changing calls
  * (build, mesh update, Smart Culling) drain all slots first. Single-GPU contexts only (tile_world == 1). */
-#define BRT_FRAMES_IN_FLIGHT 2
+#define BRT_FRAMES_IN_FLIGHT 3 /* slots available; the reference uses 2, a third lets the copy-out of frame k-2 finish while k is submitted */
 BRT_API int brt_render_frame_async(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, uint32_t slot, float* rgba_host);
 BRT_API int brt_frame_wait(brt_context* ctx, uint32_t slot);
 /* the cudaStream_t a slot's frame is enqueued on (slot 0: the context's stream), e.g. to order caller work after it */
