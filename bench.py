@@ -254,6 +254,35 @@ def run_product(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    def timed_e2e_multi(steps, warmup):
+        """N > 1, fused exchange: ONE timed region around K frames. Every frame: in-stream L2 flush, trace own tiles + peer stores +
+        barrier (frame.render), and on rank 0 the copy of the complete frame to pinned host memory, started asynchronously on a side
+        stream: the library alternates between two gather images, so the copy of frame k runs while frame k+1 is traced and is waited
+        for before the barrier of frame k+1 (and at the end, inside the timed region)."""
+        hosts = [host_image, torch.empty(h * w * 4, dtype=torch.float32).pin_memory()]
+        small = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
+
+        def one(i):
+            small.fill_(i & 0xff)
+            frame.render(u, opts)
+            if rank == 0:
+                frame.to_host_async(hosts[i % 2])
+
+        for i in range(warmup):
+            one(i)
+        frame.wait_host()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            one(i)
+        frame.wait_host()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
     def timed_pipelined(to_host, steps, warmup, collect=None, opts=opts):
         """N = 1 product schedule: two frames in flight (brt_render_frame_async / brt_frame_wait — the reference's
         MAX_FRAMES_IN_FLIGHT = 2, VK/SwapChain.h:8). K frames are enqueued alternately on the two frame slots; ONE timed
@@ -326,7 +355,10 @@ def run_product(args):
     else:
         ms_dev = timed(step_device, args.steps, args.warmup, count_launches)
         clocks = sampler.stop() if sampler else None
-        ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+        if world > 1 and frame.mode == "p2p":
+            ms_e2e = timed_e2e_multi(args.steps, max(2, args.warmup // 2))
+        else:
+            ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
     rays_t = torch.tensor([kstats["rays"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -416,7 +448,8 @@ def run_product(args):
             "config": dict(bench_config(scene, cfg, args), exchange=exchange, **(
                 {"frames_in_flight": n_slots, "l2": "flushed before every frame (160 MiB write enqueued on the frame's stream, inside the timed region)",
                  "schedule": f"K frames rotate over {n_slots} frame slots (brt_render_frame_async / brt_frame_wait; the reference keeps "
-                             "MAX_FRAMES_IN_FLIGHT = 2 frames in flight); one timed region around all K steps"} if pipelined else {"frames_in_flight": 1})),
+                             "MAX_FRAMES_IN_FLIGHT = 2 frames in flight); one timed region around all K steps"} if pipelined else {"frames_in_flight": 1, "e2e_schedule": "one timed region around all K steps; rank 0 copies frame k to the host on a side stream while "
+                    "frame k+1 is traced (two gather images), L2 flushed in-stream before every frame" if (world > 1 and frame.mode == "p2p") else "per-step"})),
             "rays_per_step": int(rays), "single_frame_latency": frame_latency,
             "e2e_bgra8": ({"value": rays / (ms_e2e_bgra8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e_bgra8,
                            "d2h_bytes_per_step": w * h * 4, "format": "B8G8R8A8_UNORM"} if pipelined else None),

@@ -287,8 +287,9 @@ struct brt_context {
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
   // fused resolve + exchange: own gather image and the peers' (opened through cudaIpc)
-  DevBuf d_gather;
+  DevBuf d_gather;  // TWO full frames back to back (one allocation, one IPC handle): frames alternate between them
   uint32_t gather_w = 0, gather_h = 0, n_peers = 0;
+  uint32_t gather_next = 0, gather_last = 0;  // image the next brt_render_frame_peers writes / the last one wrote
   void* peer_images[BRT_MAX_PEERS] = {nullptr};
   bool peer_opened[BRT_MAX_PEERS] = {false};
   // denoiser history (Graphics/Denoiser/Denoiser.h): accumulated colour + history length, luminance moments, last G-buffer, camera
@@ -875,7 +876,9 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
       if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
       rp.tiles = nullptr;
       rp.n_peers = c->n_peers;
-      for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]);
+      for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]) + (size_t)c->gather_next * npx;
+      c->gather_last = c->gather_next;
+      c->gather_next ^= 1u;
     }
     Timed t(f, CLS_RESOLVE, s);
     BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
@@ -1368,8 +1371,9 @@ int brt_gather_image_export(brt_context* c, uint32_t width, uint32_t height, voi
     BRT_CUDA(cudaSetDevice(c->device));
     close_peers(c);
     c->d_gather.release();  // a fresh allocation: an exported handle stays tied to its allocation
-    c->d_gather.ensure((size_t)width * height * 16);
-    BRT_CUDA(cudaMemset(c->d_gather.ptr(), 0, (size_t)width * height * 16));
+    c->d_gather.ensure((size_t)width * height * 16 * 2);
+    BRT_CUDA(cudaMemset(c->d_gather.ptr(), 0, (size_t)width * height * 16 * 2));
+    c->gather_next = c->gather_last = 0;
     cudaIpcMemHandle_t h;
     BRT_CUDA(cudaIpcGetMemHandle(&h, c->d_gather.ptr()));
     std::memcpy(handle_out, &h, sizeof(h));
@@ -1417,7 +1421,10 @@ int brt_render_frame_peers(brt_context* c, const brt_uniform* u, const brt_rende
   });
 }
 
-void* brt_gather_image(brt_context* c) { return c ? c->d_gather.ptr() : nullptr; }
+void* brt_gather_image(brt_context* c) {
+  if (!c || !c->d_gather.ptr()) return nullptr;
+  return static_cast<char*>(c->d_gather.ptr()) + (size_t)c->gather_last * c->gather_w * c->gather_h * 16;
+}
 
 int brt_get_aov(brt_context* c, int kind, void* out) {
   if (!c) return BRT_ERR_INVALID;

@@ -32,6 +32,9 @@ class TiledFrame:
             ctx.gather_image_open(handles)
             dist.barrier(group=group)
             self._barrier_token = torch.zeros(1, dtype=torch.int32, device=device)
+            self._rt = ctypes.CDLL("libcudart.so")
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._copy_pending = False
         n = ctx.tile_buffer_bytes(width, height, world) // 4
         self.tiles = torch.zeros(n, dtype=torch.float32, device=device)
         self.gathered = torch.zeros(n * world, dtype=torch.float32, device=device) if world > 1 else self.tiles
@@ -42,6 +45,8 @@ class TiledFrame:
         assert opts.width == self.width and opts.height == self.height
         if self.mode == "p2p":
             self.ctx.render_frame_peers(uniform, opts)               # returns when this rank's peer stores have landed
+            self.wait_host()  # an asynchronous copy-out of the previous frame must be done before anybody may pass the barrier:
+            #                   the frame after this one overwrites that gather image
             dist.all_reduce(self._barrier_token, group=self.group)  # barrier: everybody's have
             torch.cuda.current_stream().synchronize()
             return None  # the frame is brt_gather_image(ctx) (device memory owned by the library); see frame_ptr()
@@ -54,6 +59,22 @@ class TiledFrame:
     def frame_ptr(self):
         """Device pointer of the complete row-major RGBA32F frame of the last render()."""
         return self.ctx.gather_image() if self.mode == "p2p" else self.image.data_ptr()
+
+    def to_host_async(self, host):
+        """p2p mode: starts copying the complete frame of the last render() into `host` (pinned) on a side stream and returns; the
+        library alternates between two gather images, so the copy may run while the next frame is traced. wait_host() (also
+        called by the next render() before its barrier) completes it."""
+        assert self.mode == "p2p"
+        rc = self._rt.cudaMemcpyAsync(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(self.ctx.gather_image()),
+                                      ctypes.c_size_t(self.height * self.width * 16), 2, ctypes.c_void_p(self._copy_stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"cudaMemcpyAsync failed: {rc}")
+        self._copy_pending = True
+
+    def wait_host(self):
+        if self.mode == "p2p" and self._copy_pending:
+            self._copy_stream.synchronize()
+            self._copy_pending = False
 
     def to_host(self, host):
         """Copies the complete frame of the last render() into `host` (a pinned float32 tensor of h*w*4 elements)."""

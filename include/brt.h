@@ -274,8 +274,9 @@ BRT_API int brt_untile(brt_context* ctx, const void* d_all, uint32_t width, uint
  * full-frame "gather image" (cudaIpc handle), opens everybody else's, and the resolve kernel of brt_render_frame_peers
  * stores each pixel this rank owns straight into ALL ranks' gather images (row-major RGBA32F, the final layout) with
  * peer stores — the exchange happens inside the producing kernel, no collective, no un-tile pass. After the call returns
- * this rank's stores have landed; a barrier among the ranks (any kind) makes every gather image complete, and another one
- * is needed before the next frame overwrites it. */
+ * this rank's stores have landed; a barrier among the ranks (any kind) makes every gather image complete. Every rank keeps TWO
+ * gather images (one allocation, one handle) and consecutive frames alternate between them, so the frame of call k stays valid —
+ * e.g. while it is copied to the host — until call k+2; the barrier of call k+1 must not be entered before such a reader is done. */
 #define BRT_IPC_HANDLE_BYTES 64
 BRT_API int brt_gather_image_export(brt_context* ctx, uint32_t width, uint32_t height, void* handle_out);
 /* handles: tile_world x BRT_IPC_HANDLE_BYTES, in rank order (this rank's own entry is ignored) */

@@ -49,6 +49,21 @@ def _worker(rank, world, port, out_dir):
             torch.cuda.synchronize()
             dist.barrier()  # nobody may start the next frame before everybody has read this one
         np.save(os.path.join(out_dir, f"{mode}{rank}.npy"), img.cpu().numpy().reshape(h, w, 4))
+        if mode == "p2p":
+            # pipelined copy-out: rank 0 copies frame k to the host on a side stream while frame k+1 is traced (the library
+            # alternates between two gather images; render() completes the previous copy before its barrier)
+            hosts = [torch.empty(h * w * 4, dtype=torch.float32).pin_memory() for _ in range(2)]
+            got = []
+            for k in range(3):
+                frame.render(scene.uniform(ctx, w, h, 10 + k, 3), opts)
+                if rank == 0:
+                    if k > 0:
+                        got.append(hosts[(k - 1) % 2].numpy().reshape(h, w, 4).copy())
+                    frame.to_host_async(hosts[k % 2])
+            if rank == 0:
+                frame.wait_host()
+                got.append(hosts[2 % 2].numpy().reshape(h, w, 4).copy())
+                np.save(os.path.join(out_dir, "pipelined.npy"), np.stack(got))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,3 +82,7 @@ def test_two_gpu_exchange_modes(pkg, tmp_path):
         for r in range(world):
             img = np.load(tmp_path / f"{mode}{r}.npy")
             assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)), (mode, r)
+    piped = np.load(tmp_path / "pipelined.npy")
+    for k in range(3):
+        ref = single.render_frame(scene.uniform(single, w, h, 10 + k, 3), single.opts(w, h, 2, 3))
+        assert np.array_equal(piped[k].view(np.uint32), ref.view(np.uint32)), k
