@@ -215,7 +215,9 @@ struct EventPair {
   int cls = 0;
 };
 
+#ifndef BRT_REFILL_LANES_INCOHERENT
 #define BRT_REFILL_LANES_INCOHERENT 16u
+#endif
 enum { CLS_RAYGEN = 0, CLS_CLOSEST, CLS_SHADE, CLS_OCCL, CLS_ACCUM, CLS_RESOLVE, CLS_COUNT };
 
 }  // namespace brt
