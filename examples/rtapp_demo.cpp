@@ -4,6 +4,7 @@
 //
 //   g++ -std=c++17 -O2 -Iinclude examples/rtapp_demo.cpp -Lhardware-ray-tracer_b200/lib -lbrt -Wl,-rpath,... -o rtapp_demo
 //   ./rtapp_demo out_prefix [frames] [async]      (async: two frames in flight, RTApp::beginFrame / endFrame)
+//   ./rtapp_demo out_prefix [frames] post         (camera walk with Camera::handleInputs, denoised frames, BGRA8 present image)
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -24,6 +25,7 @@ int main(int argc, char** argv) {
   const std::string prefix = argc > 1 ? argv[1] : "rtapp_demo";
   const int frames = argc > 2 ? std::atoi(argv[2]) : 1;
   const bool async = argc > 3 && std::string(argv[3]) == "async";
+  const bool post = argc > 3 && std::string(argv[3]) == "post";
   try {
     const uint32_t width = 800, height = 600;  // Window({800, 600, ...}), RT/RTApp.cpp:3
     Core::Device device(0);
@@ -42,6 +44,31 @@ int main(int argc, char** argv) {
     Core::Camera camera;
     camera.setView(vec3(0.0f, 0.0f, -2.0f), vec3());                           // :25
 
+    if (post) {
+      // the parts of RTApp::run the plain path above leaves out: keyboard camera (Camera::handleInputs, :39), the denoiser slot
+      // (Graphics/Denoiser/Denoiser.h) and a storage image in the swapchain's 8-bit format (rebuildRenderOutput(format, extent))
+      Extensions::Denoiser denoiser(device);
+      std::vector<float> denoised;
+      for (int frame = 0; frame < frames; ++frame) {
+        camera.handleInputs(BRT_KEY_MOVE_FORWARD | BRT_KEY_LOOK_RIGHT, 1.0f / 60.0f);
+        camera.setPerspectiveProjection(1.0471975512f, (float)width / (float)height, 0.001f, 100000.f);
+        RayTracing::Uniform uniform = camera.uniform((uint32_t)frame, 2);
+        rtPipeline->writeToUniformBuffer(&uniform, (uint32_t)frame % 2);
+        rtPipeline->traceRays(width, height, 1, 1, BRT_RENDER_GBUFFER);
+        denoised = denoiser.denoise(uniform, width, height);
+      }
+      rtPipeline->rebuildRenderOutput(BRT_FORMAT_B8G8R8A8_UNORM, {width, height});
+      rtPipeline->traceRays(width, height, 1);
+      const std::vector<uint8_t>& bgra = rtPipeline->getRenderOutput8();
+      std::ofstream raw(prefix + ".denoised.rgba32f", std::ios::binary);
+      raw.write(reinterpret_cast<const char*>(denoised.data()), (std::streamsize)(denoised.size() * sizeof(float)));
+      std::ofstream raw8(prefix + ".bgra8", std::ios::binary);
+      raw8.write(reinterpret_cast<const char*>(bgra.data()), (std::streamsize)bgra.size());
+      const bloon::vec3 p = camera.getPosition(), r = camera.getRotation();
+      std::printf("rtapp_demo post: camera %.6f %.6f %.6f rot %.6f %.6f %.6f, %zu denoised floats, %zu present bytes, denoise %.3f ms\n", p.x, p.y, p.z,
+                  r.x, r.y, r.z, denoised.size(), bgra.size(), rtPipeline->getStats().ms_denoise);
+      return EXIT_SUCCESS;
+    }
     for (int frame = 0; frame < frames; ++frame) {                             // RTApp::run, :29-59
       camera.setPerspectiveProjection(1.0471975512f /* glm::radians(60.f) */, (float)width / (float)height, 0.001f, 100000.f);  // :41
       RayTracing::Uniform uniform = camera.uniform(/*frame = imageIndex*/ (uint32_t)frame % 2, /*depthMax*/ 2);  // :44-49

@@ -42,3 +42,31 @@ def test_rtapp_demo_matches_oracle(pkg, orc_mod, tmp_path, mode):
     ref = orc.render_frame(u, orc.opts(800, 600))
     assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
     assert (img[..., :3] > 0).mean() > 0.05
+
+
+@pytest.mark.gpu
+def test_rtapp_demo_post_path(pkg, orc_mod, tmp_path):
+    """The facade's Camera::handleInputs, Extensions::Denoiser and rebuildRenderOutput(format, extent): the demo walks the camera for three
+    frames, denoises each and renders a B8G8R8A8_UNORM frame; camera pose, denoised frame and present image equal the oracle's."""
+    exe = _build(tmp_path)
+    out = subprocess.run([exe, str(tmp_path / "out"), "3", "post"], capture_output=True, text=True, check=True).stdout
+    assert "rtapp_demo post:" in out
+    w, h = 800, 600
+    scene = pkg.scenes.rtapp_demo()
+    orc = orc_mod.Oracle(pkg)
+    scene.upload(orc)
+    host = pkg.Context(device=0)  # for the product's host-side camera maths (what the facade calls)
+    pos, rot = np.array([0.0, 0.0, -2.0], np.float32), np.zeros(3, np.float32)
+    dop = orc.denoise_opts(iterations=4, sigma_n_log2=5, sigma_z=0.05, sigma_l=4.0, clamp_gamma=0.0, max_history=32.0, flags=pkg.DENOISE_BILATERAL)
+    for frame in range(3):
+        pos, rot = orc.camera_handle_inputs(4 | 64, 1.0 / 60.0, pos, rot)  # BRT_KEY_MOVE_FORWARD | BRT_KEY_LOOK_RIGHT
+        u = host.camera_uniform(pos, rot, 1.0471975512, w / h, 0.001, 100000.0, frame, 2)
+        orc.render_frame(u, orc.opts(w, h, 1, pkg.GBUFFER))
+        den = orc.denoise(u, dop, w, h)
+    vals = [float(x) for x in out.split("camera")[1].split(",")[0].replace("rot", "").split()]
+    assert np.allclose(vals, list(pos) + list(rot), atol=2e-6)
+    got = np.fromfile(tmp_path / "out.denoised.rgba32f", dtype=np.float32).reshape(h, w, 4)
+    assert np.array_equal(got.view(np.uint32), den.view(np.uint32))
+    ref8 = orc.render_frame(u, orc.opts(w, h, 1, pkg.render_format(pkg.FORMAT_BGRA8_UNORM)))
+    got8 = np.fromfile(tmp_path / "out.bgra8", dtype=np.uint8).reshape(h, w, 4)
+    assert np.array_equal(got8, ref8)
