@@ -188,7 +188,7 @@ def run_product(args):
     scene, cfg = workload(pkg, args.config)
     w, h, spp, flags = cfg["width"], cfg["height"], cfg["spp"], cfg["flags"]
 
-    ctx = pkg.Context(device=local, tile_rank=rank, tile_world=world)
+    ctx = pkg.Context(device=local, tile_rank=rank, tile_world=world, flags=pkg.CFG_NO_GRAPH if args.no_graph else 0)
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # a real (non-default) stream for torch work and frame slot 0
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -502,6 +502,7 @@ def main():
                     help="BASELINE config; default: c2 (1080p, the single-GPU headline) at N=1, c3 (4K, 16 spp, 4-bounce GI: the "
                          "configuration BASELINE.json quotes for 1/2/4/8 GPUs) at N>1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels of every frame individually (default: replay the frame's CUDA graph)")
     ap.add_argument("--frames-in-flight", type=int, default=3, choices=[1, 2, 3],
                     help="N = 1: frames rotate over this many frame slots (the reference keeps 2 frames in flight over a swapchain of "
                          "typically 3 images; the third slot lets the copy-out of frame k-2 finish while frame k is submitted); "

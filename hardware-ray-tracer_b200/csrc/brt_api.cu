@@ -250,7 +250,14 @@ struct FrameSlot {
   uint32_t launches = 0, l_closest = 0, l_occl = 0;
   FrameStats* fs_host = nullptr;  // pinned: device-side statistics of the frame, copied back on the frame's stream
   bool in_flight = false;
-  bool ready = false;  // streams / events / pinned block created
+  bool ready = false;
+  FrameConsts* h_consts = nullptr;  // pinned staging of the per-frame constants
+  DevBuf d_consts;
+  uint32_t generation = 0;          // bumped whenever the wavefront buffers are reallocated (invalidates the graph)
+#ifndef BRT_EMU
+  cudaGraphExec_t graph_exec = nullptr;  // the whole frame, captured once per frame shape and replayed
+  uint64_t graph_key[16] = {0};
+#endif  // streams / events / pinned block created
 };
 
 struct brt_context {
@@ -352,11 +359,34 @@ EventPair& next_events(FrameSlot* c, int cls) {
   e.cls = cls;
   return e;
 }
+// Events that must really be recorded when a captured frame graph is replayed (timing, the head event other slots wait for) are
+// "external" event-record nodes; outside a capture the flag must not be used.
+thread_local bool g_capturing = false;
+void record_event_nothrow(cudaEvent_t e, cudaStream_t s) {
+#ifdef BRT_EMU
+  cudaEventRecord(e, s);
+#else
+  cudaEventRecordWithFlags(e, s, g_capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+#endif
+}
+void record_event(cudaEvent_t e, cudaStream_t s) {
+#ifdef BRT_EMU
+  BRT_CUDA(cudaEventRecord(e, s));
+#else
+  BRT_CUDA(cudaEventRecordWithFlags(e, s, g_capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+#endif
+}
 struct Timed {  // brackets one launch with events of class `cls` on the stream it is launched on
   cudaStream_t s;
   EventPair* e;
-  Timed(FrameSlot* ctx, int cls, cudaStream_t stream) : s(stream), e(&next_events(ctx, cls)) { BRT_CUDA(cudaEventRecord(e->a, s)); }
-  ~Timed() { cudaEventRecord(e->b, s); }
+  // (not inside a captured frame graph: ~60 event-record nodes would cost more than the launch gaps the graph saves; a graph
+  // frame reports its total time only, per-class times need BRT_CFG_NO_GRAPH / BRT_CFG_NO_OVERLAP)
+  Timed(FrameSlot* ctx, int cls, cudaStream_t stream) : s(stream), e(g_capturing ? nullptr : &next_events(ctx, cls)) {
+    if (e) record_event(e->a, s);
+  }
+  ~Timed() {
+    if (e) record_event_nothrow(e->b, s);
+  }
 };
 
 // ---- light BVH (RT/Scene.h:123-130) ---------------------------------------------------------
@@ -582,6 +612,7 @@ void ensure_frame_buffers(brt_context* c, FrameSlot* f, const brt_render_opts& o
   const uint64_t key[4] = {((uint64_t)o.width << 32) | o.height, ((uint64_t)o.spp << 32) | R, L, c->target_wavefront};
   if (f->frame_bytes && std::memcmp(key, f->frame_key, sizeof(key)) == 0) return;  // same frame shape as last time
   std::memcpy(f->frame_key, key, sizeof(key));
+  f->generation++;  // buffers below may move: a captured frame graph of this slot is stale
   // bytes per sample of the batch: two path queues, hits, and per round parity: contributions, weights, shadow queue; + radiance terms
   const size_t per_sample = (size_t)cap * (2 * 56 + 20 + 2 * (16 * L + 16 + 36 * L) + 16 * R);
   size_t free_b = 0, total_b = 0;
@@ -666,246 +697,307 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   const size_t npx = (size_t)o.width * o.height;
   const uint32_t n_lights = (uint32_t)c->lights.size();
   const uint32_t n_slots = lbvh ? 1u : std::max(1u, n_lights);  // contribution / shadow-queue segments per path
-  f->events_used = 0;
-  FrameCounters* ctr = f->d_counters.as<FrameCounters>();
-  ShadowCounters* sctr = reinterpret_cast<ShadowCounters*>(ctr + 1);
-  FrameStats* fst = f->d_fstats.as<FrameStats>();
+  // buffers that only some frames need are sized before any stream work (nothing below may allocate: the frame may be captured)
+  const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
+  if (format > BRT_FORMAT_B8G8R8A8_SRGB) invalid("render_frame: unknown BRT_RENDER_FORMAT");
+  if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && c->tile_world > 1) invalid("render_frame: 8-bit output formats need tile_world == 1");
+  f->has_gbuffer = (o.flags & BRT_RENDER_GBUFFER) != 0u;
+  f->render_flags = o.flags;
+  {
+    const void* before[3] = {f->d_aov_pos.ptr(), f->d_aov_nrm.ptr(), f->d_image8.ptr()};
+    if (f->has_gbuffer) {
+      f->d_aov_pos.ensure(npx * 16);
+      f->d_aov_nrm.ensure(npx * 16);
+    }
+    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) f->d_image8.ensure(npx * 4);
+    if (before[0] != f->d_aov_pos.ptr() || before[1] != f->d_aov_nrm.ptr() || before[2] != f->d_image8.ptr()) f->generation++;
+  }
+  // per-frame constants: staged in pinned memory, copied by the first node of the frame
+  f->d_consts.ensure(sizeof(FrameConsts));
+  std::memcpy(f->h_consts->Vi, u.viewInverse, 64);
+  std::memcpy(f->h_consts->Pi, u.projInverse, 64);
+  f->h_consts->frame = u.frame;
+  f->h_consts->sky = c->sky;
   // Frames in flight are staggered: this frame starts when the previous one has traced its last full-width wavefront, so
   // that its saturating head overlaps the latency-bound tail (bounce rounds, resolve, copy-out) of the previous frame
   // instead of running in lockstep with it.
   if (c->prev_head && c->prev_head != f->ev_head) BRT_CUDA(cudaStreamWaitEvent(s, c->prev_head, 0));
-  EventPair& whole = next_events(f, CLS_COUNT);
-  BRT_CUDA(cudaEventRecord(whole.a, s));
-  BRT_CUDA(cudaMemsetAsync(f->d_accum.ptr(), 0, (size_t)cap * 16, s));
-  BRT_CUDA(cudaMemsetAsync(fst, 0, sizeof(FrameStats), s));
-  BRT_CUDA(cudaMemsetAsync(f->d_aov_prim.ptr(), 0xff, npx * 4, s));
-  BRT_CUDA(cudaMemsetAsync(f->d_aov_inst.ptr(), 0xff, npx * 4, s));
-  BRT_CUDA(cudaMemsetAsync(f->d_aov_t.ptr(), 0, npx * 4, s));
-  if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(f->d_image.ptr(), 0, npx * 16, s));
-  f->has_gbuffer = (o.flags & BRT_RENDER_GBUFFER) != 0u;
-  f->render_flags = o.flags;
-  if (f->has_gbuffer) {
-    f->d_aov_pos.ensure(npx * 16);
-    f->d_aov_nrm.ensure(npx * 16);
-    BRT_CUDA(cudaMemsetAsync(f->d_aov_pos.ptr(), 0, npx * 16, s));
-    BRT_CUDA(cudaMemsetAsync(f->d_aov_nrm.ptr(), 0, npx * 16, s));
-  }
-  uint32_t launches = 0, l_closest = 0, l_occl = 0;
-  const Node8* tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
-  const InstRec* insts = c->d_tlas_inst.as<InstRec>();
-  bool acc_pending[2] = {false, false};  // ev_acc[p] has been recorded and not yet waited for by the main stream
-  uint32_t global_round = 0;
 
-  const uint32_t c_batch = f->batch;
-  for (uint32_t sample = 0; sample < o.spp; sample += f->batch) {
-    const uint32_t nb = std::min(f->batch, o.spp - sample);  // samples in this wavefront
-    const uint32_t capw = cap * nb;                          // its path slots
-    if (rounds) BRT_CUDA(cudaMemsetAsync(f->d_alive.ptr(), 0, (size_t)capw * 4, s));  // (the radiance terms themselves need no clearing)
-    {
-      RaygenParams rp;
-      rp.count = capw;
-      rp.count_ptr = nullptr;
-      rp.map = map;
-      std::memcpy(rp.Vi, u.viewInverse, 64);
-      std::memcpy(rp.Pi, u.projInverse, 64);
-      rp.frame = u.frame + sample;
-      rp.flags = o.flags;
-      rp.cap = cap;
-      rp.q = queue_of(f, 0);
-      Timed t(f, CLS_RAYGEN, s);
-      BRT_LAUNCH_1D(k_raygen, rp, grid_for(c, capw, 256, 8), 256, s);
-      BRT_CHECK_LAUNCH();
-      launches++;
+  // The stream work of the frame (about 45 dependent kernel launches, memsets and event records for C2) is captured into a CUDA
+  // graph the first time a frame shape is seen on this slot and replayed afterwards: everything that changes from frame to frame
+  // travels through FrameConsts, queue sizes already live on the device.
+  auto enqueue = [&]() {
+    BRT_CUDA(cudaMemcpyAsync(f->d_consts.ptr(), f->h_consts, sizeof(FrameConsts), cudaMemcpyHostToDevice, s));
+    f->events_used = 0;
+    FrameCounters* ctr = f->d_counters.as<FrameCounters>();
+    ShadowCounters* sctr = reinterpret_cast<ShadowCounters*>(ctr + 1);
+    FrameStats* fst = f->d_fstats.as<FrameStats>();
+    EventPair& whole = next_events(f, CLS_COUNT);
+    record_event(whole.a, s);
+    BRT_CUDA(cudaMemsetAsync(f->d_accum.ptr(), 0, (size_t)cap * 16, s));
+    BRT_CUDA(cudaMemsetAsync(fst, 0, sizeof(FrameStats), s));
+    BRT_CUDA(cudaMemsetAsync(f->d_aov_prim.ptr(), 0xff, npx * 4, s));
+    BRT_CUDA(cudaMemsetAsync(f->d_aov_inst.ptr(), 0xff, npx * 4, s));
+    BRT_CUDA(cudaMemsetAsync(f->d_aov_t.ptr(), 0, npx * 4, s));
+    if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(f->d_image.ptr(), 0, npx * 16, s));
+    if (f->has_gbuffer) {
+      BRT_CUDA(cudaMemsetAsync(f->d_aov_pos.ptr(), 0, npx * 16, s));
+      BRT_CUDA(cudaMemsetAsync(f->d_aov_nrm.ptr(), 0, npx * 16, s));
     }
-    int cur = 0;
-    for (uint32_t round = 0; round < rounds; ++round, ++global_round) {
-      const int par = (int)(global_round & 1u);
-      // main-chain counters: n_paths[cur] is live (round 0 walks all `capw` slots, padding slots carry id == BRT_MISS)
-      if (round == 0) {
-        BRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
-      } else {
-        BRT_CUDA(cudaMemsetAsync(&ctr->n_paths[cur ^ 1], 0, 4, s));
-        BRT_CUDA(cudaMemsetAsync(&ctr->work_closest, 0, 4, s));
-      }
-      const uint32_t* count_ptr = round == 0 ? nullptr : &ctr->n_paths[cur];
-      const PathQueue qc = queue_of(f, cur), qn = queue_of(f, cur ^ 1);
+    uint32_t launches = 0, l_closest = 0, l_occl = 0;
+    const Node8* tlas = c->tlas_count ? c->d_tlas_nodes.as<Node8>() : nullptr;
+    const InstRec* insts = c->d_tlas_inst.as<InstRec>();
+    bool acc_pending[2] = {false, false};  // ev_acc[p] has been recorded and not yet waited for by the main stream
+    uint32_t global_round = 0;
+
+    const uint32_t c_batch = f->batch;
+    for (uint32_t sample = 0; sample < o.spp; sample += f->batch) {
+      const uint32_t nb = std::min(f->batch, o.spp - sample);  // samples in this wavefront
+      const uint32_t capw = cap * nb;                          // its path slots
+      if (rounds) BRT_CUDA(cudaMemsetAsync(f->d_alive.ptr(), 0, (size_t)capw * 4, s));  // (the radiance terms themselves need no clearing)
       {
-        TraceParams tp{};
-        tp.count = capw;
-        tp.count_ptr = count_ptr;
-        tp.tlas = tlas;
-        tp.insts = insts;
-        tp.o = qc.o;
-        tp.d = qc.d;
-        tp.px = qc.px;
-        tp.hit = f->d_hit.as<float4>();
-        tp.hit_inst = f->d_hit_inst.as<uint32_t>();
-        tp.work = &ctr->work_closest;
-        tp.stats = fst;
-        tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;  // measured: refill pays for bounce rays only
-        Timed t(f, CLS_CLOSEST, s);
-        launch_trace<false>(c, tp, s);
+        RaygenParams rp;
+        rp.count = capw;
+        rp.count_ptr = nullptr;
+        rp.map = map;
+        rp.fc = f->d_consts.as<FrameConsts>();
+        rp.sample0 = sample;
+        rp.flags = o.flags;
+        rp.cap = cap;
+        rp.q = queue_of(f, 0);
+        Timed t(f, CLS_RAYGEN, s);
+        BRT_LAUNCH_1D(k_raygen, rp, grid_for(c, capw, 256, 8), 256, s);
+        BRT_CHECK_LAUNCH();
         launches++;
-        l_closest++;
       }
-      // the shadow-chain buffers of this parity were last used two rounds ago: wait for that accumulate
-      if (acc_pending[par]) {
-        if (s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, f->ev_acc[par], 0));
+      int cur = 0;
+      for (uint32_t round = 0; round < rounds; ++round, ++global_round) {
+        const int par = (int)(global_round & 1u);
+        // main-chain counters: n_paths[cur] is live (round 0 walks all `capw` slots, padding slots carry id == BRT_MISS)
+        if (round == 0) {
+          BRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
+        } else {
+          BRT_CUDA(cudaMemsetAsync(&ctr->n_paths[cur ^ 1], 0, 4, s));
+          BRT_CUDA(cudaMemsetAsync(&ctr->work_closest, 0, 4, s));
+        }
+        const uint32_t* count_ptr = round == 0 ? nullptr : &ctr->n_paths[cur];
+        const PathQueue qc = queue_of(f, cur), qn = queue_of(f, cur ^ 1);
+        {
+          TraceParams tp{};
+          tp.count = capw;
+          tp.count_ptr = count_ptr;
+          tp.tlas = tlas;
+          tp.insts = insts;
+          tp.o = qc.o;
+          tp.d = qc.d;
+          tp.px = qc.px;
+          tp.hit = f->d_hit.as<float4>();
+          tp.hit_inst = f->d_hit_inst.as<uint32_t>();
+          tp.work = &ctr->work_closest;
+          tp.stats = fst;
+          tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;  // measured: refill pays for bounce rays only
+          Timed t(f, CLS_CLOSEST, s);
+          launch_trace<false>(c, tp, s);
+          launches++;
+          l_closest++;
+        }
+        // the shadow-chain buffers of this parity were last used two rounds ago: wait for that accumulate
+        if (acc_pending[par]) {
+          if (s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, f->ev_acc[par], 0));
+          acc_pending[par] = false;
+        }
+        BRT_CUDA(cudaMemsetAsync(&sctr[par], 0, sizeof(ShadowCounters), s));
+        {
+          ShadeParams sp{};
+          sp.count = capw;
+          sp.count_ptr = count_ptr;
+          sp.cur = qc;
+          sp.next = qn;
+          sp.hit = f->d_hit.as<float4>();
+          sp.hit_inst = f->d_hit_inst.as<uint32_t>();
+          sp.ctr = ctr;
+          sp.sctr = &sctr[par];
+          sp.aux = f->d_aux[par].as<float4>();
+          sp.next_slot = (uint32_t)(cur ^ 1);
+          sp.cap = capw;
+          sp.inst = c->d_inst_shade.as<InstShade>();
+          sp.materials = c->d_materials.as<float>();
+          sp.mat_ext = c->d_mat_ext.as<float2>();
+          sp.lights = c->d_lights.as<LightRec>();
+          sp.light_bvh = c->d_light_bvh.as<float4>();
+          sp.n_lights = n_lights;
+          sp.contrib = f->d_contrib[par].as<float4>();
+          sp.s_o = f->s_o[par].as<float4>();
+          sp.s_d = f->s_d[par].as<float4>();
+          sp.s_target = f->s_target[par].as<uint32_t>();
+          sp.flags = o.flags;
+          sp.last_round = round + 1 == rounds ? 1u : 0u;
+          sp.write_aov = (sample == 0 && round == 0) ? 1u : 0u;
+          sp.map = map;
+          sp.aov_prim = f->d_aov_prim.as<uint32_t>();
+          sp.aov_inst = f->d_aov_inst.as<uint32_t>();
+          sp.aov_t = f->d_aov_t.as<float>();
+          sp.aov_pos = f->has_gbuffer ? f->d_aov_pos.as<float4>() : nullptr;
+          sp.aov_nrm = f->has_gbuffer ? f->d_aov_nrm.as<float4>() : nullptr;
+          sp.fc = f->d_consts.as<FrameConsts>();
+          Timed t(f, CLS_SHADE, s);
+  #ifdef BRT_EMU
+          BRT_LAUNCH_1D(k_shade, sp, 1, 128, s);
+  #else
+          if (round == 0) k_shade_primary<<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
+          else k_shade<BRT_SHADE_WINDOW><<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
+  #endif
+          BRT_CHECK_LAUNCH();
+          launches++;
+        }
+        if (s2 != s) {
+          BRT_CUDA(cudaEventRecord(f->ev_shade, s));
+          BRT_CUDA(cudaStreamWaitEvent(s2, f->ev_shade, 0));
+        }
+        if (n_lights) {
+          TraceParams tp{};
+          tp.count = 0;
+          tp.seg_counts = sctr[par].n_shadow;
+          tp.n_segs = n_slots;
+          tp.seg_stride = capw;
+          tp.tlas = tlas;
+          tp.insts = insts;
+          tp.o = f->s_o[par].as<float4>();
+          tp.d = f->s_d[par].as<float4>();
+          tp.target = f->s_target[par].as<uint32_t>();
+          tp.contrib = f->d_contrib[par].as<float4>();
+          tp.work = &sctr[par].work_occl;
+          tp.stats = fst;
+          tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;
+          Timed t(f, CLS_OCCL, s2);
+          launch_trace<true>(c, tp, s2);
+          launches++;
+          l_occl++;
+        }
+        if (round == 0 && sample + c_batch >= o.spp) record_event(f->ev_head, s2);
+        {
+          AccumParams ap{};
+          ap.count = 0;
+          ap.count_ptr = &sctr[par].n_items;
+          ap.aux = f->d_aux[par].as<float4>();
+          ap.contrib = f->d_contrib[par].as<float4>();
+          ap.n_slots = n_slots;
+          ap.cap = capw;
+          ap.slots = cap;
+          ap.rounds = rounds;
+          ap.round = round;
+          ap.rad = f->d_rad.as<float4>();
+          ap.alive = f->d_alive.as<uint32_t>();
+          Timed t(f, CLS_ACCUM, s2);
+          BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, capw, 256, 8), 256, s2);
+          BRT_CHECK_LAUNCH();
+          launches++;
+        }
+        if (s2 != s) BRT_CUDA(cudaEventRecord(f->ev_acc[par], s2));
+        acc_pending[par] = true;
+        cur ^= 1;
+      }
+      // join the shadow chain, then add this batch's radiance terms to the per-slot sums in the shader's order
+      for (int par = 0; par < 2; ++par) {
+        if (acc_pending[par] && s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, f->ev_acc[par], 0));
         acc_pending[par] = false;
       }
-      BRT_CUDA(cudaMemsetAsync(&sctr[par], 0, sizeof(ShadowCounters), s));
-      {
-        ShadeParams sp{};
-        sp.count = capw;
-        sp.count_ptr = count_ptr;
-        sp.cur = qc;
-        sp.next = qn;
-        sp.hit = f->d_hit.as<float4>();
-        sp.hit_inst = f->d_hit_inst.as<uint32_t>();
-        sp.ctr = ctr;
-        sp.sctr = &sctr[par];
-        sp.aux = f->d_aux[par].as<float4>();
-        sp.next_slot = (uint32_t)(cur ^ 1);
-        sp.cap = capw;
-        sp.inst = c->d_inst_shade.as<InstShade>();
-        sp.materials = c->d_materials.as<float>();
-        sp.mat_ext = c->d_mat_ext.as<float2>();
-        sp.lights = c->d_lights.as<LightRec>();
-        sp.light_bvh = c->d_light_bvh.as<float4>();
-        sp.n_lights = n_lights;
-        sp.contrib = f->d_contrib[par].as<float4>();
-        sp.s_o = f->s_o[par].as<float4>();
-        sp.s_d = f->s_d[par].as<float4>();
-        sp.s_target = f->s_target[par].as<uint32_t>();
-        sp.flags = o.flags;
-        sp.last_round = round + 1 == rounds ? 1u : 0u;
-        sp.write_aov = (sample == 0 && round == 0) ? 1u : 0u;
-        sp.map = map;
-        sp.aov_prim = f->d_aov_prim.as<uint32_t>();
-        sp.aov_inst = f->d_aov_inst.as<uint32_t>();
-        sp.aov_t = f->d_aov_t.as<float>();
-        sp.aov_pos = f->has_gbuffer ? f->d_aov_pos.as<float4>() : nullptr;
-        sp.aov_nrm = f->has_gbuffer ? f->d_aov_nrm.as<float4>() : nullptr;
-        sp.sky = c->sky;
-        Timed t(f, CLS_SHADE, s);
-#ifdef BRT_EMU
-        BRT_LAUNCH_1D(k_shade, sp, 1, 128, s);
-#else
-        if (round == 0) k_shade_primary<<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
-        else k_shade<BRT_SHADE_WINDOW><<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
-#endif
+      if (rounds) {
+        SumSamplesParams sp{};
+        sp.count = cap;
+        sp.count_ptr = nullptr;
+        sp.samples = nb;
+        sp.rounds = rounds;
+        sp.rad = f->d_rad.as<float4>();
+        sp.alive = f->d_alive.as<uint32_t>();
+        sp.accum = f->d_accum.as<float4>();
+        Timed t(f, CLS_ACCUM, s);
+        BRT_LAUNCH_1D(k_sum_samples, sp, grid_for(c, cap, 256, 8), 256, s);
         BRT_CHECK_LAUNCH();
         launches++;
       }
-      if (s2 != s) {
-        BRT_CUDA(cudaEventRecord(f->ev_shade, s));
-        BRT_CUDA(cudaStreamWaitEvent(s2, f->ev_shade, 0));
-      }
-      if (n_lights) {
-        TraceParams tp{};
-        tp.count = 0;
-        tp.seg_counts = sctr[par].n_shadow;
-        tp.n_segs = n_slots;
-        tp.seg_stride = capw;
-        tp.tlas = tlas;
-        tp.insts = insts;
-        tp.o = f->s_o[par].as<float4>();
-        tp.d = f->s_d[par].as<float4>();
-        tp.target = f->s_target[par].as<uint32_t>();
-        tp.contrib = f->d_contrib[par].as<float4>();
-        tp.work = &sctr[par].work_occl;
-        tp.stats = fst;
-        tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;
-        Timed t(f, CLS_OCCL, s2);
-        launch_trace<true>(c, tp, s2);
-        launches++;
-        l_occl++;
-      }
-      if (round == 0 && sample + c_batch >= o.spp) BRT_CUDA(cudaEventRecord(f->ev_head, s2));
-      {
-        AccumParams ap{};
-        ap.count = 0;
-        ap.count_ptr = &sctr[par].n_items;
-        ap.aux = f->d_aux[par].as<float4>();
-        ap.contrib = f->d_contrib[par].as<float4>();
-        ap.n_slots = n_slots;
-        ap.cap = capw;
-        ap.slots = cap;
-        ap.rounds = rounds;
-        ap.round = round;
-        ap.rad = f->d_rad.as<float4>();
-        ap.alive = f->d_alive.as<uint32_t>();
-        Timed t(f, CLS_ACCUM, s2);
-        BRT_LAUNCH_1D(k_accumulate, ap, grid_for(c, capw, 256, 8), 256, s2);
-        BRT_CHECK_LAUNCH();
-        launches++;
-      }
-      if (s2 != s) BRT_CUDA(cudaEventRecord(f->ev_acc[par], s2));
-      acc_pending[par] = true;
-      cur ^= 1;
     }
-    // join the shadow chain, then add this batch's radiance terms to the per-slot sums in the shader's order
-    for (int par = 0; par < 2; ++par) {
-      if (acc_pending[par] && s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, f->ev_acc[par], 0));
-      acc_pending[par] = false;
-    }
-    if (rounds) {
-      SumSamplesParams sp{};
-      sp.count = cap;
-      sp.count_ptr = nullptr;
-      sp.samples = nb;
-      sp.rounds = rounds;
-      sp.rad = f->d_rad.as<float4>();
-      sp.alive = f->d_alive.as<uint32_t>();
-      sp.accum = f->d_accum.as<float4>();
-      Timed t(f, CLS_ACCUM, s);
-      BRT_LAUNCH_1D(k_sum_samples, sp, grid_for(c, cap, 256, 8), 256, s);
+    {
+      ResolveParams rp{};
+      rp.count = cap;
+      rp.count_ptr = nullptr;
+      rp.map = map;
+      rp.spp = (float)o.spp;
+      rp.accum = f->d_accum.as<float4>();
+      rp.image = f->d_image.as<float4>();
+      rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : f->d_tiles.as<float4>();
+      rp.n_peers = 0;
+      if (to_peers) {
+        if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
+        rp.tiles = nullptr;
+        rp.n_peers = c->n_peers;
+        for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]) + (size_t)c->gather_next * npx;
+        c->gather_last = c->gather_next;
+        c->gather_next ^= 1u;
+      }
+      Timed t(f, CLS_RESOLVE, s);
+      BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
       BRT_CHECK_LAUNCH();
       launches++;
     }
-  }
-  {
-    ResolveParams rp{};
-    rp.count = cap;
-    rp.count_ptr = nullptr;
-    rp.map = map;
-    rp.spp = (float)o.spp;
-    rp.accum = f->d_accum.as<float4>();
-    rp.image = f->d_image.as<float4>();
-    rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : f->d_tiles.as<float4>();
-    rp.n_peers = 0;
-    if (to_peers) {
-      if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
-      rp.tiles = nullptr;
-      rp.n_peers = c->n_peers;
-      for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]) + (size_t)c->gather_next * npx;
-      c->gather_last = c->gather_next;
-      c->gather_next ^= 1u;
+    const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
+    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {
+      PresentParams pp{(uint32_t)npx, nullptr, format, f->d_image.as<float4>(), f->d_image8.as<uint32_t>()};
+      Timed t(f, CLS_RESOLVE, s);
+      BRT_LAUNCH_1D(k_present, pp, grid_for(c, (uint32_t)npx, 256, 8), 256, s);
+      BRT_CHECK_LAUNCH();
+      launches++;
     }
-    Timed t(f, CLS_RESOLVE, s);
-    BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
-    BRT_CHECK_LAUNCH();
-    launches++;
+    record_event(whole.b, s);
+    if (!rounds) record_event(f->ev_head, s);
+    f->launches = launches;
+    f->l_closest = l_closest;
+    f->l_occl = l_occl;
+    // device-side statistics of this frame travel back on its stream (read by finish_frame)
+    BRT_CUDA(cudaMemcpyAsync(f->fs_host, f->d_fstats.ptr(), sizeof(FrameStats), cudaMemcpyDeviceToHost, s));
+  };
+#ifdef BRT_EMU
+  enqueue();
+#else
+  const bool use_graph = !(c->flags & (BRT_CFG_NO_GRAPH | BRT_CFG_NO_OVERLAP | BRT_CFG_COUNTERS)) && c->tile_world == 1 && !to_peers;
+  const uint64_t key[16] = {((uint64_t)o.width << 32) | o.height, ((uint64_t)o.spp << 32) | o.flags, ((uint64_t)o.crop_x0 << 32) | o.crop_y0,
+                            ((uint64_t)o.crop_w << 32) | o.crop_h, ((uint64_t)rounds << 32) | n_lights, ((uint64_t)f->generation << 32) | c->tlas_count,
+                            (uint64_t)c->d_tlas_nodes.ptr(), (uint64_t)c->d_tlas_inst.ptr(), (uint64_t)c->d_inst_shade.ptr(), (uint64_t)c->d_materials.ptr(),
+                            (uint64_t)c->d_mat_ext.ptr(), (uint64_t)c->d_lights.ptr(), (uint64_t)c->d_light_bvh.ptr(), (uint64_t)d_tiles_out, (uint64_t)s,
+                            (uint64_t)f->d_consts.ptr()};
+  if (use_graph && f->graph_exec && std::memcmp(key, f->graph_key, sizeof(key)) == 0) {
+    BRT_CUDA(cudaGraphLaunch(f->graph_exec, s));
+  } else if (use_graph) {
+    if (f->graph_exec) {
+      cudaGraphExecDestroy(f->graph_exec);
+      f->graph_exec = nullptr;
+    }
+    BRT_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    g_capturing = true;
+    cudaGraph_t graph = nullptr;
+    try {
+      enqueue();
+    } catch (...) {
+      g_capturing = false;
+      cudaStreamEndCapture(s, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    g_capturing = false;
+    BRT_CUDA(cudaStreamEndCapture(s, &graph));
+    const cudaError_t ie = cudaGraphInstantiate(&f->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      f->graph_exec = nullptr;
+      BRT_CUDA(ie);
+    }
+    std::memcpy(f->graph_key, key, sizeof(key));
+    BRT_CUDA(cudaGraphLaunch(f->graph_exec, s));
+  } else {
+    enqueue();
   }
-  const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
-  if (format > BRT_FORMAT_B8G8R8A8_SRGB) invalid("render_frame: unknown BRT_RENDER_FORMAT");
-  if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {
-    if (c->tile_world > 1) invalid("render_frame: 8-bit output formats need tile_world == 1");
-    f->d_image8.ensure(npx * 4);
-    PresentParams pp{(uint32_t)npx, nullptr, format, f->d_image.as<float4>(), f->d_image8.as<uint32_t>()};
-    Timed t(f, CLS_RESOLVE, s);
-    BRT_LAUNCH_1D(k_present, pp, grid_for(c, (uint32_t)npx, 256, 8), 256, s);
-    BRT_CHECK_LAUNCH();
-    launches++;
-  }
-  BRT_CUDA(cudaEventRecord(whole.b, s));
-  if (!rounds) BRT_CUDA(cudaEventRecord(f->ev_head, s));
+#endif
   c->prev_head = f->ev_head;
-  f->launches = launches;
-  f->l_closest = l_closest;
-  f->l_occl = l_occl;
-  // device-side statistics of this frame travel back on its stream (read by finish_frame)
-  BRT_CUDA(cudaMemcpyAsync(f->fs_host, f->d_fstats.ptr(), sizeof(FrameStats), cudaMemcpyDeviceToHost, s));
   f->in_flight = true;
 }
 
@@ -981,6 +1073,7 @@ void ensure_slot(brt_context* c, FrameSlot* f) {
   BRT_CUDA(cudaEventCreateWithFlags(&f->ev_acc[1], cudaEventDisableTiming));
   BRT_CUDA(cudaEventCreateWithFlags(&f->ev_head, cudaEventDisableTiming));
   BRT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&f->fs_host), sizeof(FrameStats)));
+  BRT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&f->h_consts), sizeof(FrameConsts)));
   f->ready = true;
 }
 
@@ -999,6 +1092,10 @@ void destroy_slot(FrameSlot* f) {
   for (int k = 0; k < 2; ++k)
     if (f->ev_acc[k]) cudaEventDestroy(f->ev_acc[k]);
   if (f->fs_host) cudaFreeHost(f->fs_host);
+  if (f->h_consts) cudaFreeHost(f->h_consts);
+#ifndef BRT_EMU
+  if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+#endif
 }
 
 }  // namespace

@@ -80,12 +80,21 @@ BRT_HD uint32_t pixel_to_slot(const TileMap& m, uint32_t x, uint32_t y) {
 }
 
 // ---- raygen --------------------------------------------------------------------------------------
+// Values that change from frame to frame (camera, frame counter, sky) are read through a pointer instead of being kernel parameters:
+// a captured CUDA graph of the frame can then be replayed with new ones (brt_api.cu).
+struct FrameConsts {
+  float Vi[16], Pi[16];  // brt_uniform.viewInverse / projInverse, read as row-major M^-1 (RT/RTApp.cpp:44-49)
+  uint32_t frame;        // uniform.frame
+  uint32_t pad[3];
+  brt_sky sky;
+};
+
 struct RaygenParams {
   uint32_t count;
   const uint32_t* count_ptr;
   TileMap map;
-  float Vi[16], Pi[16];  // brt_uniform.viewInverse / projInverse, read as row-major M^-1 (RT/RTApp.cpp:44-49)
-  uint32_t frame;        // uniform.frame + index of the first sample of this batch
+  const FrameConsts* fc;
+  uint32_t sample0;      // index of the first sample of this batch: sample s of the batch uses RNG frame fc->frame + sample0 + s
   uint32_t flags;
   uint32_t cap;          // path slots per sample; the batch traces count = cap * samples paths at once
   PathQueue q;
@@ -97,15 +106,15 @@ BRT_HD void raygen_body(const RaygenParams& p, uint32_t i) {
     p.q.px[i] = BRT_MISS;
     return;
   }
-  const uint32_t frame = p.frame + sib;
+  const uint32_t frame = p.fc->frame + p.sample0 + sib;
   uint32_t seed = hash3(px, py, frame);  // :96
   float jx = 0.0f, jy = 0.0f;
   if (p.flags & BRT_RENDER_JITTER) {  // :97-98 (the shader computes it and then drops it at :100)
     if (frame == 0u) { jx = 0.5f; jy = 0.5f; }
     else { jx = rnd(seed); jy = rnd(seed); }
   }
-  const float* Pi = p.Pi;
-  const float* Vi = p.Vi;
+  const float* Pi = p.fc->Pi;
+  const float* Vi = p.fc->Vi;
   const float cx = ((float)px + jx) / (float)p.map.width * 2.0f - 1.0f;  // :100
   const float cy = ((float)py + jy) / (float)p.map.height * 2.0f - 1.0f;
   const f3 vc = F3(((Pi[0] * cx + Pi[1] * cy) + Pi[2] * 1.0f) + Pi[3] * 1.0f, ((Pi[4] * cx + Pi[5] * cy) + Pi[6] * 1.0f) + Pi[7] * 1.0f,
@@ -212,7 +221,7 @@ struct ShadeParams {
   float* aov_t;
   float4* aov_pos;  // BRT_RENDER_GBUFFER: world position (w = 1) and shading normal (w = hit distance) of the primary hit, else null
   float4* aov_nrm;
-  brt_sky sky;
+  const FrameConsts* fc;  // sky
 };
 
 // Light BVH sampling (RT/Scene.h:123-130, SH/raytracing.slang:76; rule in DESIGN.md §13): stochastic descent from the root, a child
@@ -307,7 +316,7 @@ BRT_HD bool shade_prologue(const ShadeParams& p, uint32_t i) {
     f3 c = F3(0.0f);
     if (p.flags & BRT_RENDER_SKY) {
       const float4 rd = p.cur.d[i];
-      c = sky_color(p.sky, F3(rd.x, rd.y, rd.z));
+      c = sky_color(p.fc->sky, F3(rd.x, rd.y, rd.z));
     }
     p.contrib[i] = make_float4(c.x, c.y, c.z, 0.0f);
     for (uint32_t l = 1; l < n_slots; ++l) p.contrib[(size_t)l * p.cap + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);

@@ -120,6 +120,10 @@ typedef struct brt_config {
 /* run every kernel of a frame on one stream (default: the shadow chain of a round overlaps the next round's
  * closest-hit traversal on a second stream). Same results; used when per-kernel event times must not overlap. */
 #define BRT_CFG_NO_OVERLAP 8u
+/* launch every kernel of every frame individually instead of replaying the CUDA graph captured for the frame shape (single-GPU
+ * contexts capture one graph per frame slot and shape). A replayed frame reports ms_total only: the per-class kernel times of
+ * brt_stats need this flag (BRT_CFG_NO_OVERLAP and BRT_CFG_COUNTERS imply it). */
+#define BRT_CFG_NO_GRAPH 16u
 
 /* render mode flags. With none of the BOUNCE flags set the behaviour is the reference's live path:
  * direct light + hard shadows, weight = 0 after the first hit (SH/raytracing.slang:168). */
@@ -166,7 +170,8 @@ typedef struct brt_stats {
   /* counters, only with BRT_CFG_COUNTERS */
   uint64_t nodes_visited_closest, prims_tested_closest, spheres_tested_closest;
   uint64_t nodes_visited_occlusion, prims_tested_occlusion, spheres_tested_occlusion;
-  /* device time of the last frame per kernel class, CUDA events on the library's stream (ms) */
+  /* device time of the last frame per kernel class, CUDA events on the library's stream (ms); frames replayed from a CUDA graph
+   * fill ms_total only (see BRT_CFG_NO_GRAPH) */
   float ms_raygen, ms_trace_closest, ms_shade, ms_trace_occlusion, ms_accumulate, ms_resolve, ms_total;
   uint32_t launches_trace_closest, launches_trace_occlusion, launches_total;
   /* last brt_scene_build / brt_smart_cull */

@@ -25,7 +25,7 @@ def main():
     pkg = importlib.import_module("hardware-ray-tracer_b200")
     cfg = dict(pkg.scenes.CONFIGS[args.config])
     scene = pkg.scenes.make_scene(cfg.pop("scene"), small=args.small)
-    flags = (pkg.CFG_COUNTERS if args.counters else 0) | (pkg.CFG_NO_TREELET if args.no_treelet else 0) | (pkg.CFG_NO_OVERLAP if args.no_overlap else 0)
+    flags = pkg.CFG_NO_GRAPH | (pkg.CFG_COUNTERS if args.counters else 0)  # per-kernel event times need individually launched kernels | (pkg.CFG_NO_TREELET if args.no_treelet else 0) | (pkg.CFG_NO_OVERLAP if args.no_overlap else 0)
     ctx = pkg.Context(device=0, flags=flags)
     t0 = time.perf_counter()
     scene.upload(ctx)
