@@ -143,3 +143,33 @@ def test_tlas_sizes_vs_brute_force(pkg, orc_mod, make, n_side):
     assert np.array_equal(ha, hb)
     assert hb[:, 3].sum() > 300
     assert np.array_equal(a.trace_rays(rays, False)[:, 3], b.trace_rays(rays, False)[:, 3])
+
+
+def test_frame_graph_replay(pkg, orc_mod, make):
+    """The captured CUDA graph of a frame shape is replayed with new per-frame values (camera, frame counter, sky travel through
+    FrameConsts): a sequence of frames with moving camera, a changing sky and changing frame shapes equals the same sequence
+    rendered with individually launched kernels (BRT_CFG_NO_GRAPH) and the oracle's last frame."""
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a, b, o = make(), make(pkg.CFG_NO_GRAPH), orc_mod.Oracle(pkg)
+    for api in (a, b, o):
+        scene.upload(api)
+    sky = pkg.Sky()
+    sky.horizonColor[:] = (0.8, 0.8, 0.7)
+    sky.groundColor[:] = (0.2, 0.15, 0.1)
+    sky.upDirection[:] = (0.0, -1.0, 0.0)
+    sky.brightness, sky.horizonSize = 1.0, 0.4
+    shapes = [(160, 90, 3, 3), (160, 90, 3, 3), (160, 90, 3, 3), (128, 72, 2, 3 | 16), (160, 90, 3, 3), (160, 90, 3, 3 | 16)]
+    for k, (w, h, depth, flags) in enumerate(shapes):
+        u = scene.uniform(a, w, h, k, depth)
+        u.viewInverse[3] += 0.2 * k
+        sky.skyColor[:] = (0.1 * k, 0.4, 0.9 - 0.1 * k)
+        for api in (a, b, o):
+            api.sky_set(sky)
+        ia = a.render_frame(u, a.opts(w, h, 2, flags))
+        ib = b.render_frame(u, b.opts(w, h, 2, flags))
+        assert np.array_equal(ia.view(np.uint32), ib.view(np.uint32)), k
+        assert a.get_stats().rays_closest == b.get_stats().rays_closest and a.get_stats().ms_total > 0.0
+    io = o.render_frame(u, o.opts(w, h, 2, flags))
+    assert np.array_equal(ia.view(np.uint32), io.view(np.uint32))
+    # per-class kernel times exist only for individually launched kernels
+    assert b.get_stats().ms_trace_closest > 0.0 and a.get_stats().ms_trace_closest == 0.0
