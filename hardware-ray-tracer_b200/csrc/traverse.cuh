@@ -201,7 +201,8 @@ struct Traversal {
         const float4 a = ldg4(&tr->v0), b = ldg4(&tr->v1), c = ldg4(&tr->v2);
         if (COUNT) ctr.prims++;
         float t, u, v;
-        if (intersect_tri(co, sh, tmin, best.t, found, xyz(a), xyz(b), xyz(c), t, u, v)) {
+        // (an occlusion query ends at its first hit, so `found` is still false here: the interval test is a compile-time choice)
+        if (intersect_tri(co, sh, tmin, best.t, ANY ? false : found, xyz(a), xyz(b), xyz(c), t, u, v)) {
           found = true;  // (for ANY this is the answer)
           if (ANY) return true;
           const uint32_t prim = f2u(a.w);
@@ -221,7 +222,7 @@ struct Traversal {
           const float4 s = ldg4(&ir->sphere);
           if (COUNT) ctr.spheres++;
           float t;
-          if (intersect_sphere(oo, od, tmin, best.t, found, xyz(s), s.w, t)) {
+          if (intersect_sphere(oo, od, tmin, best.t, ANY ? false : found, xyz(s), s.w, t)) {
             found = true;
             if (ANY) return true;
             if (best.inst == BRT_MISS || t < best.t || tail.y < best.inst) {
