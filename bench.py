@@ -352,6 +352,9 @@ def run_product(args):
         # the same end-to-end step with the framebuffer in the 8-bit swapchain format the reference presents (B8G8R8A8_UNORM):
         # conversion kernel on the GPU, 4 bytes per pixel over PCIe instead of 16
         ms_e2e_bgra8 = timed_pipelined(True, args.steps, 2, opts=ctx.opts(w, h, spp, flags | pkg.render_format(pkg.FORMAT_BGRA8_UNORM)))
+        # ... and with the denoiser stages of Graphics/Denoiser/Denoiser.h in the frame (temporal accumulation, 4 a-trous iterations,
+        # bilateral pass) before the conversion: trace -> denoise -> present image -> host
+        ms_e2e_dn = timed_pipelined(True, args.steps, 3, opts=ctx.opts(w, h, spp, flags | pkg.DENOISE | pkg.render_format(pkg.FORMAT_BGRA8_UNORM)))
     else:
         ms_dev = timed(step_device, args.steps, args.warmup, count_launches)
         clocks = sampler.stop() if sampler else None
@@ -453,6 +456,9 @@ def run_product(args):
             "rays_per_step": int(rays), "single_frame_latency": frame_latency,
             "e2e_bgra8": ({"value": rays / (ms_e2e_bgra8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e_bgra8,
                            "d2h_bytes_per_step": w * h * 4, "format": "B8G8R8A8_UNORM"} if pipelined else None),
+            "e2e_denoised_bgra8": ({"value": rays / (ms_e2e_dn * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e_dn,
+                                    "d2h_bytes_per_step": w * h * 4, "stages": "trace, denoise (temporal + 4 a-trous + bilateral), B8G8R8A8_UNORM, copy"}
+                                   if pipelined else None),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 140 + 32,
                     "d2h_bytes_per_step": w * h * 16},
             "gpu_launches": int(launches["n"]),

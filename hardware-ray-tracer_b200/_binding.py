@@ -74,7 +74,7 @@ CFG_NO_TREELET = 2
 CFG_TREELET_ON_REBUILD = 4
 CFG_NO_OVERLAP = 8
 CFG_NO_GRAPH = 16
-BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY, GBUFFER, LIGHT_BVH = 1, 2, 4, 8, 16, 32, 64
+BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY, GBUFFER, LIGHT_BVH, DENOISE = 1, 2, 4, 8, 16, 32, 64, 128
 AOV_POSITION, AOV_NORMAL = 3, 4
 DENOISE_RESET, DENOISE_BILATERAL = 1, 2
 FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_BGRA8_UNORM, FORMAT_RGBA8_SRGB, FORMAT_BGRA8_SRGB = 0, 1, 2, 3, 4
@@ -95,7 +95,7 @@ BRT_SYMBOLS = [
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
-    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_get_light_bvh",
+    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_denoise_configure", "brt_get_light_bvh",
 ]
 
 
@@ -164,6 +164,7 @@ class SceneApi:
             "gather_image_open": (C.c_int, [vp, vp, u32]),
             "render_frame_peers": (C.c_int, [vp, P(Uniform), P(RenderOpts)]),
             "gather_image": (vp, [vp]),
+            "denoise_configure": (C.c_int, [vp, P(DenoiseOpts)]),
             "render_frame_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32, vp]),
             "frame_wait": (C.c_int, [vp, u32]),
             "frame_stream": (vp, [vp, u32]),
@@ -305,6 +306,10 @@ class SceneApi:
         out = np.zeros((height, width, 4), dtype=np.float32) if want_image else None
         self._ck(self._f("denoise")(self.ctx, C.byref(uniform), C.byref(dopts), out.ctypes.data_as(C.c_void_p) if want_image else None))
         return out
+
+    def denoise_configure(self, dopts):
+        """options of the denoiser stages run by frames rendered with the DENOISE flag"""
+        self._ck(self._f("denoise_configure")(self.ctx, C.byref(dopts)))
 
     def get_light_bvh(self):
         """The light BVH (RT/Scene.h:123-130) as a list of LightBvhNode."""

@@ -241,6 +241,10 @@ struct FrameSlot {
   DevBuf q_o[2], q_d[2], q_w[2], q_px[2], q_seed[2], d_hit, d_hit_inst, d_contrib[2], d_aux[2], s_o[2], s_d[2], s_target[2];
   DevBuf d_image8;  // the frame in an 8-bit present format (BRT_RENDER_FORMAT)
   DevBuf d_aov_pos, d_aov_nrm;  // BRT_RENDER_GBUFFER
+  DevBuf d_denoised;            // output of the denoiser stages for this slot's frame (brt_denoise / BRT_RENDER_DENOISE)
+  cudaEvent_t ev_dn[2] = {nullptr, nullptr};
+  bool has_denoised = false;
+  uint32_t dn_launches = 0;
   bool has_gbuffer = false;
   uint32_t render_flags = 0;  // of the frame rendered last on this slot
   DevBuf d_alive;  // rounds that contributed per (sample in batch, slot)
@@ -303,11 +307,40 @@ struct brt_context {
   bool peer_opened[BRT_MAX_PEERS] = {false};
   // denoiser history (Graphics/Denoiser/Denoiser.h): accumulated colour + history length, luminance moments, last G-buffer, camera
   DevBuf dn_work[2], dn_hist_color[2], dn_hist_mom[2], dn_h_nrm, dn_h_inst, dn_h_t;
-  uint32_t dn_w = 0, dn_h = 0, dn_parity = 0, dn_result = 0;
+  uint32_t dn_w = 0, dn_h = 0, dn_parity = 0;
+  brt_denoise_opts dn_opts{sizeof(brt_denoise_opts), BRT_DENOISE_BILATERAL, 4u, 5u, 0.05f, 4.0f, 0.0f, 32.0f};  // brt_denoise_configure
+  cudaEvent_t dn_event = nullptr;  // recorded after the denoiser stages of a frame: the next frame's stages read its history
+  bool dn_event_recorded = false;
   bool dn_have_history = false;
   float dn_prev_vp[16] = {0}, dn_prev_eye[3] = {0, 0, 0};
   brt_stats stats{};
 };
+
+// general 4x4 inverse in double (camera matrices)
+static void invert4x4(const double m[16], double inv[16]) {
+  const double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];
+  const double s3 = m[1] * m[6] - m[5] * m[2], s4 = m[1] * m[7] - m[5] * m[3], s5 = m[2] * m[7] - m[6] * m[3];
+  const double c5 = m[10] * m[15] - m[14] * m[11], c4 = m[9] * m[15] - m[13] * m[11], c3 = m[9] * m[14] - m[13] * m[10];
+  const double c2 = m[8] * m[15] - m[12] * m[11], c1 = m[8] * m[14] - m[12] * m[10], c0 = m[8] * m[13] - m[12] * m[9];
+  const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+  const double id = 1.0 / det;
+  inv[0] = (m[5] * c5 - m[6] * c4 + m[7] * c3) * id;
+  inv[1] = (-m[1] * c5 + m[2] * c4 - m[3] * c3) * id;
+  inv[2] = (m[13] * s5 - m[14] * s4 + m[15] * s3) * id;
+  inv[3] = (-m[9] * s5 + m[10] * s4 - m[11] * s3) * id;
+  inv[4] = (-m[4] * c5 + m[6] * c2 - m[7] * c1) * id;
+  inv[5] = (m[0] * c5 - m[2] * c2 + m[3] * c1) * id;
+  inv[6] = (-m[12] * s5 + m[14] * s2 - m[15] * s1) * id;
+  inv[7] = (m[8] * s5 - m[10] * s2 + m[11] * s1) * id;
+  inv[8] = (m[4] * c4 - m[5] * c2 + m[7] * c0) * id;
+  inv[9] = (-m[0] * c4 + m[1] * c2 - m[3] * c0) * id;
+  inv[10] = (m[12] * s4 - m[13] * s2 + m[15] * s0) * id;
+  inv[11] = (-m[8] * s4 + m[9] * s2 - m[11] * s0) * id;
+  inv[12] = (-m[4] * c3 + m[5] * c1 - m[6] * c0) * id;
+  inv[13] = (m[0] * c3 - m[1] * c1 + m[2] * c0) * id;
+  inv[14] = (-m[12] * s3 + m[13] * s1 - m[14] * s0) * id;
+  inv[15] = (m[8] * s3 - m[9] * s1 + m[10] * s0) * id;
+}
 
 namespace {
 
@@ -669,6 +702,112 @@ void launch_trace(brt_context* c, const TraceParams& p, cudaStream_t stream) {
   BRT_CHECK_LAUNCH();
 }
 
+// ---- denoiser stages (Graphics/Denoiser/Denoiser.h:5-20) ------------------------------------------------------
+void check_denoise_opts(const brt_denoise_opts& d) {
+  if (d.struct_size != sizeof(brt_denoise_opts)) invalid("denoise: struct_size mismatch");
+  if (d.iterations > 6 || d.sigma_n_log2 > 8) invalid("denoise: iterations <= 6, sigma_n_log2 <= 8");
+}
+
+// Enqueues temporal accumulation with reprojection + history clamping + variance estimation (k_dn_temporal), the a-trous wavelet
+// iterations and the bilateral pass (k_dn_atrous) for the frame of slot `f` on stream `s`; the result lands in f->d_denoised. The
+// history (accumulated colour, moments, last G-buffer, camera) lives in the context: frames must be enqueued in display order, and
+// the stages of a frame start behind those of the previous one (dn_event) whichever slot / stream that frame used.
+void enqueue_denoise(brt_context* c, FrameSlot* f, const brt_uniform& u, const brt_denoise_opts& d, cudaStream_t s) {
+  const uint32_t W = f->frame_w, H = f->frame_h;
+  const size_t npx = (size_t)W * H;
+  if (c->dn_w != W || c->dn_h != H || (d.flags & BRT_DENOISE_RESET)) c->dn_have_history = false;
+  c->dn_w = W;
+  c->dn_h = H;
+  for (int k = 0; k < 2; ++k) {
+    c->dn_work[k].ensure(npx * 16);
+    c->dn_hist_color[k].ensure(npx * 16);
+    c->dn_hist_mom[k].ensure(npx * 8);
+  }
+  c->dn_h_nrm.ensure(npx * 16);
+  c->dn_h_inst.ensure(npx * 4);
+  c->dn_h_t.ensure(npx * 4);
+  f->d_denoised.ensure(npx * 16);
+  // this frame's camera: world -> clip = P V = (V^-1 P^-1)^-1 from the two inverses the uniform carries (RT/RTApp.cpp:44-49)
+  double vi[16], pi[16], a[16], vp[16];
+  for (int i = 0; i < 16; ++i) { vi[i] = u.viewInverse[i]; pi[i] = u.projInverse[i]; }
+  for (int r = 0; r < 4; ++r)
+    for (int k = 0; k < 4; ++k) {
+      double acc = 0.0;
+      for (int j = 0; j < 4; ++j) acc += vi[4 * r + j] * pi[4 * j + k];
+      a[4 * r + k] = acc;
+    }
+  invert4x4(a, vp);
+  const GBuffer g{f->d_aov_pos.as<float4>(), f->d_aov_nrm.as<float4>(), f->d_aov_inst.as<uint32_t>(), f->d_aov_t.as<float>()};
+  const GBuffer hg{nullptr, c->dn_h_nrm.as<float4>(), c->dn_h_inst.as<uint32_t>(), c->dn_h_t.as<float>()};
+  const uint32_t par = c->dn_parity;
+  const uint32_t grid = grid_for(c, (uint32_t)npx, 256, 8);
+  uint32_t launches = 0;
+  if (c->dn_event_recorded) BRT_CUDA(cudaStreamWaitEvent(s, c->dn_event, 0));
+  BRT_CUDA(cudaEventRecord(f->ev_dn[0], s));
+  {
+    DnTemporalParams tp{};
+    tp.count = (uint32_t)npx;
+    tp.width = W;
+    tp.height = H;
+    tp.color = f->d_image.as<float4>();
+    tp.g = g;
+    tp.hg = hg;
+    tp.h_color = c->dn_hist_color[par].as<float4>();
+    tp.h_moments = c->dn_hist_mom[par].as<float2>();
+    std::memcpy(tp.prev_vp, c->dn_prev_vp, sizeof(tp.prev_vp));
+    std::memcpy(tp.prev_eye, c->dn_prev_eye, sizeof(tp.prev_eye));
+    tp.pixel_offset = (f->render_flags & BRT_RENDER_JITTER) ? 0.0f : 0.5f;
+    tp.have_history = c->dn_have_history ? 1u : 0u;
+    tp.clamp_gamma = d.clamp_gamma;
+    tp.max_history = d.max_history >= 1.0f ? d.max_history : 1.0f;
+    tp.out = c->dn_work[0].as<float4>();
+    tp.out_h_color = c->dn_hist_color[par ^ 1].as<float4>();
+    tp.out_h_moments = c->dn_hist_mom[par ^ 1].as<float2>();
+    BRT_LAUNCH_1D(k_dn_temporal, tp, grid, 256, s);
+    BRT_CHECK_LAUNCH();
+    launches++;
+  }
+  uint32_t cur = 0;
+  const uint32_t passes = std::max(1u, d.iterations + ((d.flags & BRT_DENOISE_BILATERAL) ? 1u : 0u));
+  for (uint32_t it = 0; it < passes; ++it) {
+    const bool none = d.iterations == 0 && !(d.flags & BRT_DENOISE_BILATERAL);  // accumulation only: alpha = 1 through a zero-radius pass
+    const bool bilateral = it >= d.iterations;
+    const bool last = it + 1 == passes;
+    DnAtrousParams ap{};
+    ap.count = (uint32_t)npx;
+    ap.width = W;
+    ap.height = H;
+    ap.step = bilateral ? 1 : (1 << it);
+    ap.radius = none ? 0 : (bilateral ? 1 : 2);
+    ap.sigma_z = d.sigma_z;
+    ap.sigma_l = d.sigma_l;
+    ap.sigma_n_log2 = d.sigma_n_log2;
+    ap.final_pass = last ? 1u : 0u;
+    ap.in = c->dn_work[cur].as<float4>();
+    ap.g = g;
+    ap.out = last ? f->d_denoised.as<float4>() : c->dn_work[cur ^ 1].as<float4>();  // the result belongs to the slot (its copy-out may
+    BRT_LAUNCH_1D(k_dn_atrous, ap, grid, 256, s);                                    // still run when the next frame is filtered)
+    BRT_CHECK_LAUNCH();
+    launches++;
+    cur ^= 1;
+  }
+  BRT_CUDA(cudaEventRecord(f->ev_dn[1], s));
+  // this frame becomes the history of the next one
+  BRT_CUDA(cudaMemcpyAsync(c->dn_h_nrm.ptr(), f->d_aov_nrm.ptr(), npx * 16, cudaMemcpyDeviceToDevice, s));
+  BRT_CUDA(cudaMemcpyAsync(c->dn_h_inst.ptr(), f->d_aov_inst.ptr(), npx * 4, cudaMemcpyDeviceToDevice, s));
+  BRT_CUDA(cudaMemcpyAsync(c->dn_h_t.ptr(), f->d_aov_t.ptr(), npx * 4, cudaMemcpyDeviceToDevice, s));
+  BRT_CUDA(cudaEventRecord(c->dn_event, s));
+  c->dn_event_recorded = true;
+  for (int i = 0; i < 16; ++i) c->dn_prev_vp[i] = (float)vp[i];
+  c->dn_prev_eye[0] = u.viewInverse[3];
+  c->dn_prev_eye[1] = u.viewInverse[7];
+  c->dn_prev_eye[2] = u.viewInverse[11];
+  c->dn_have_history = true;
+  c->dn_parity = par ^ 1;
+  f->has_denoised = true;
+  f->dn_launches = launches;
+}
+
 // Renders into d_image (and d_tiles); no host synchronisation except the final stats read-back.
 //
 // Two streams. The closest-hit chain  raygen -> { k_trace<closest> -> k_shade } per round  runs on the main stream; the
@@ -701,7 +840,10 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
   if (format > BRT_FORMAT_B8G8R8A8_SRGB) invalid("render_frame: unknown BRT_RENDER_FORMAT");
   if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && c->tile_world > 1) invalid("render_frame: 8-bit output formats need tile_world == 1");
-  f->has_gbuffer = (o.flags & BRT_RENDER_GBUFFER) != 0u;
+  const bool denoise = (o.flags & BRT_RENDER_DENOISE) != 0u;
+  if (denoise && c->tile_world > 1) invalid("render_frame: BRT_RENDER_DENOISE needs tile_world == 1");
+  f->has_gbuffer = (o.flags & (BRT_RENDER_GBUFFER | BRT_RENDER_DENOISE)) != 0u;
+  f->has_denoised = false;
   f->render_flags = o.flags;
   {
     const void* before[3] = {f->d_aov_pos.ptr(), f->d_aov_nrm.ptr(), f->d_image8.ptr()};
@@ -941,7 +1083,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
       launches++;
     }
     const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
-    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {
+    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && !denoise) {
       PresentParams pp{(uint32_t)npx, nullptr, format, f->d_image.as<float4>(), f->d_image8.as<uint32_t>()};
       Timed t(f, CLS_RESOLVE, s);
       BRT_LAUNCH_1D(k_present, pp, grid_for(c, (uint32_t)npx, 256, 8), 256, s);
@@ -998,6 +1140,16 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   }
 #endif
   c->prev_head = f->ev_head;
+  // Denoiser stages and the present conversion of a denoised frame follow the (replayed) frame as ordinary stream work: their
+  // history is shared by all slots, so they wait for the previous frame's stages with stream semantics.
+  if (denoise) {
+    enqueue_denoise(c, f, u, c->dn_opts, s);
+    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {
+      PresentParams pp{(uint32_t)npx, nullptr, format, f->d_denoised.as<float4>(), f->d_image8.as<uint32_t>()};
+      BRT_LAUNCH_1D(k_present, pp, grid_for(c, (uint32_t)npx, 256, 8), 256, s);
+      BRT_CHECK_LAUNCH();
+    }
+  }
   f->in_flight = true;
 }
 
@@ -1044,6 +1196,12 @@ void finish_frame(brt_context* c, FrameSlot* f) {
   st.ms_accumulate = ms[CLS_ACCUM];
   st.ms_resolve = ms[CLS_RESOLVE];
   st.ms_total = ms[CLS_COUNT];
+  if (f->has_denoised) {
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, f->ev_dn[0], f->ev_dn[1]);
+    st.ms_denoise = t;
+    st.launches_denoise = f->dn_launches;
+  }
   c->last_slot = (uint32_t)(f - c->slots);
 }
 
@@ -1051,7 +1209,7 @@ void finish_frame(brt_context* c, FrameSlot* f) {
 void copy_out(FrameSlot* f, const brt_render_opts& o, void* host) {
   const size_t npx = (size_t)o.width * o.height;
   if (o.flags & BRT_RENDER_FORMAT_MASK) BRT_CUDA(cudaMemcpyAsync(host, f->d_image8.ptr(), npx * 4, cudaMemcpyDeviceToHost, f->stream));
-  else BRT_CUDA(cudaMemcpyAsync(host, f->d_image.ptr(), npx * 16, cudaMemcpyDeviceToHost, f->stream));
+  else BRT_CUDA(cudaMemcpyAsync(host, f->has_denoised ? f->d_denoised.ptr() : f->d_image.ptr(), npx * 16, cudaMemcpyDeviceToHost, f->stream));
 }
 
 // scene changes (builds, uploads, culling) and the synchronous entry points first drain every frame in flight
@@ -1072,6 +1230,8 @@ void ensure_slot(brt_context* c, FrameSlot* f) {
   BRT_CUDA(cudaEventCreateWithFlags(&f->ev_acc[0], cudaEventDisableTiming));
   BRT_CUDA(cudaEventCreateWithFlags(&f->ev_acc[1], cudaEventDisableTiming));
   BRT_CUDA(cudaEventCreateWithFlags(&f->ev_head, cudaEventDisableTiming));
+  BRT_CUDA(cudaEventCreate(&f->ev_dn[0]));
+  BRT_CUDA(cudaEventCreate(&f->ev_dn[1]));
   BRT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&f->fs_host), sizeof(FrameStats)));
   BRT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&f->h_consts), sizeof(FrameConsts)));
   f->ready = true;
@@ -1089,6 +1249,8 @@ void destroy_slot(FrameSlot* f) {
   if (f->stream2) cudaStreamDestroy(f->stream2);
   if (f->ev_shade) cudaEventDestroy(f->ev_shade);
   if (f->ev_head) cudaEventDestroy(f->ev_head);
+  for (int k = 0; k < 2; ++k)
+    if (f->ev_dn[k]) cudaEventDestroy(f->ev_dn[k]);
   for (int k = 0; k < 2; ++k)
     if (f->ev_acc[k]) cudaEventDestroy(f->ev_acc[k]);
   if (f->fs_host) cudaFreeHost(f->fs_host);
@@ -1122,6 +1284,7 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     BRT_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     BRT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int k = 0; k < 3; ++k) BRT_CUDA(cudaEventCreate(&c->ev_t[k]));
+    BRT_CUDA(cudaEventCreateWithFlags(&c->dn_event, cudaEventDisableTiming));
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count));
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
@@ -1146,6 +1309,7 @@ void brt_destroy(brt_context* c) {
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   for (int k = 0; k < 3; ++k)
     if (c->ev_t[k]) cudaEventDestroy(c->ev_t[k]);
+  if (c->dn_event) cudaEventDestroy(c->dn_event);
   delete c;
 }
 
@@ -1659,30 +1823,6 @@ int brt_debug_sort_pairs(brt_context* c, uint32_t* keys, uint32_t* vals, uint32_
 }
 
 // 4x4 inverse in double (cofactor expansion along 2x2 minors), row-major in/out
-static void invert4x4(const double m[16], double inv[16]) {
-  const double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];
-  const double s3 = m[1] * m[6] - m[5] * m[2], s4 = m[1] * m[7] - m[5] * m[3], s5 = m[2] * m[7] - m[6] * m[3];
-  const double c5 = m[10] * m[15] - m[14] * m[11], c4 = m[9] * m[15] - m[13] * m[11], c3 = m[9] * m[14] - m[13] * m[10];
-  const double c2 = m[8] * m[15] - m[12] * m[11], c1 = m[8] * m[14] - m[12] * m[10], c0 = m[8] * m[13] - m[12] * m[9];
-  const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
-  const double id = 1.0 / det;
-  inv[0] = (m[5] * c5 - m[6] * c4 + m[7] * c3) * id;
-  inv[1] = (-m[1] * c5 + m[2] * c4 - m[3] * c3) * id;
-  inv[2] = (m[13] * s5 - m[14] * s4 + m[15] * s3) * id;
-  inv[3] = (-m[9] * s5 + m[10] * s4 - m[11] * s3) * id;
-  inv[4] = (-m[4] * c5 + m[6] * c2 - m[7] * c1) * id;
-  inv[5] = (m[0] * c5 - m[2] * c2 + m[3] * c1) * id;
-  inv[6] = (-m[12] * s5 + m[14] * s2 - m[15] * s1) * id;
-  inv[7] = (m[8] * s5 - m[10] * s2 + m[11] * s1) * id;
-  inv[8] = (m[4] * c4 - m[5] * c2 + m[7] * c0) * id;
-  inv[9] = (-m[0] * c4 + m[1] * c2 - m[3] * c0) * id;
-  inv[10] = (m[12] * s4 - m[13] * s2 + m[15] * s0) * id;
-  inv[11] = (-m[8] * s4 + m[9] * s2 - m[11] * s0) * id;
-  inv[12] = (-m[4] * c3 + m[5] * c1 - m[6] * c0) * id;
-  inv[13] = (m[0] * c3 - m[1] * c1 + m[2] * c0) * id;
-  inv[14] = (-m[12] * s3 + m[13] * s1 - m[14] * s0) * id;
-  inv[15] = (m[8] * s3 - m[9] * s1 + m[10] * s0) * id;
-}
 
 void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar, uint32_t frame,
                         uint32_t depth_max, brt_uniform* out) {
@@ -1755,120 +1895,38 @@ void brt_camera_handle_inputs(uint32_t keys, float dt, float position[3], float 
   }
 }
 
-// Extensions::Denoiser::denoise (Graphics/Denoiser/Denoiser.h:5-20): temporal accumulation with reprojection, history clamping,
-// variance estimation (k_dn_temporal), a-trous wavelet iterations and the bilateral pass (k_dn_atrous). DESIGN.md §12.
+// Extensions::Denoiser::denoise (Graphics/Denoiser/Denoiser.h:5-20) on the frame rendered last; DESIGN.md §12.
 int brt_denoise(brt_context* c, const brt_uniform* u, const brt_denoise_opts* d, float* rgba_host) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
-    if (!u || !d || d->struct_size != sizeof(brt_denoise_opts)) invalid("denoise: null / struct_size mismatch");
-    if (d->iterations > 6 || d->sigma_n_log2 > 8) invalid("denoise: iterations <= 6, sigma_n_log2 <= 8");
+    if (!u || !d) invalid("denoise: null");
+    check_denoise_opts(*d);
     BRT_CUDA(cudaSetDevice(c->device));
     wait_all_frames(c);
     FrameSlot* f = &c->slots[c->last_slot];
     if (!f->frame_w || !f->has_gbuffer) bad_state("denoise: render the frame with BRT_RENDER_GBUFFER first");
     if (c->tile_world > 1) bad_state("denoise: single-GPU contexts only (tile_world == 1)");
-    const uint32_t W = f->frame_w, H = f->frame_h;
-    const size_t npx = (size_t)W * H;
+    ensure_slot(c, f);
     cudaStream_t s = c->stream;
-    if (c->dn_w != W || c->dn_h != H || (d->flags & BRT_DENOISE_RESET)) c->dn_have_history = false;
-    c->dn_w = W;
-    c->dn_h = H;
-    for (int k = 0; k < 2; ++k) {
-      c->dn_work[k].ensure(npx * 16);
-      c->dn_hist_color[k].ensure(npx * 16);
-      c->dn_hist_mom[k].ensure(npx * 8);
-    }
-    c->dn_h_nrm.ensure(npx * 16);
-    c->dn_h_inst.ensure(npx * 4);
-    c->dn_h_t.ensure(npx * 4);
-    // this frame's camera: world -> clip = P V = (V^-1 P^-1)^-1 from the two inverses the uniform carries (RT/RTApp.cpp:44-49)
-    double vi[16], pi[16], a[16], vp[16];
-    for (int i = 0; i < 16; ++i) { vi[i] = u->viewInverse[i]; pi[i] = u->projInverse[i]; }
-    for (int r = 0; r < 4; ++r)
-      for (int k = 0; k < 4; ++k) {
-        double acc = 0.0;
-        for (int j = 0; j < 4; ++j) acc += vi[4 * r + j] * pi[4 * j + k];
-        a[4 * r + k] = acc;
-      }
-    invert4x4(a, vp);
-    const GBuffer g{f->d_aov_pos.as<float4>(), f->d_aov_nrm.as<float4>(), f->d_aov_inst.as<uint32_t>(), f->d_aov_t.as<float>()};
-    const GBuffer hg{nullptr, c->dn_h_nrm.as<float4>(), c->dn_h_inst.as<uint32_t>(), c->dn_h_t.as<float>()};
-    const uint32_t par = c->dn_parity;
-    const uint32_t grid = grid_for(c, (uint32_t)npx, 256, 8);
-    uint32_t launches = 0;
-    BRT_CUDA(cudaEventRecord(c->ev_t[0], s));
-    {
-      DnTemporalParams tp{};
-      tp.count = (uint32_t)npx;
-      tp.width = W;
-      tp.height = H;
-      tp.color = f->d_image.as<float4>();
-      tp.g = g;
-      tp.hg = hg;
-      tp.h_color = c->dn_hist_color[par].as<float4>();
-      tp.h_moments = c->dn_hist_mom[par].as<float2>();
-      std::memcpy(tp.prev_vp, c->dn_prev_vp, sizeof(tp.prev_vp));
-      std::memcpy(tp.prev_eye, c->dn_prev_eye, sizeof(tp.prev_eye));
-      tp.pixel_offset = (f->render_flags & BRT_RENDER_JITTER) ? 0.0f : 0.5f;
-      tp.have_history = c->dn_have_history ? 1u : 0u;
-      tp.clamp_gamma = d->clamp_gamma;
-      tp.max_history = d->max_history >= 1.0f ? d->max_history : 1.0f;
-      tp.out = c->dn_work[0].as<float4>();
-      tp.out_h_color = c->dn_hist_color[par ^ 1].as<float4>();
-      tp.out_h_moments = c->dn_hist_mom[par ^ 1].as<float2>();
-      BRT_LAUNCH_1D(k_dn_temporal, tp, grid, 256, s);
-      BRT_CHECK_LAUNCH();
-      launches++;
-    }
-    uint32_t cur = 0;
-    const uint32_t passes = d->iterations + ((d->flags & BRT_DENOISE_BILATERAL) ? 1u : 0u);
-    for (uint32_t it = 0; it < passes; ++it) {
-      const bool bilateral = it >= d->iterations;
-      DnAtrousParams ap{};
-      ap.count = (uint32_t)npx;
-      ap.width = W;
-      ap.height = H;
-      ap.step = bilateral ? 1 : (1 << it);
-      ap.radius = bilateral ? 1 : 2;
-      ap.sigma_z = d->sigma_z;
-      ap.sigma_l = d->sigma_l;
-      ap.sigma_n_log2 = d->sigma_n_log2;
-      ap.final_pass = it + 1 == passes ? 1u : 0u;
-      ap.in = c->dn_work[cur].as<float4>();
-      ap.g = g;
-      ap.out = c->dn_work[cur ^ 1].as<float4>();
-      BRT_LAUNCH_1D(k_dn_atrous, ap, grid, 256, s);
-      BRT_CHECK_LAUNCH();
-      launches++;
-      cur ^= 1;
-    }
-    if (passes == 0) {  // accumulation only: alpha = 1 through a zero-radius pass
-      DnAtrousParams ap{};
-      ap.count = (uint32_t)npx; ap.width = W; ap.height = H; ap.step = 1; ap.radius = 0; ap.sigma_z = d->sigma_z; ap.sigma_l = d->sigma_l;
-      ap.final_pass = 1u; ap.in = c->dn_work[0].as<float4>(); ap.g = g; ap.out = c->dn_work[1].as<float4>();
-      BRT_LAUNCH_1D(k_dn_atrous, ap, grid, 256, s);
-      BRT_CHECK_LAUNCH();
-      launches++;
-      cur = 1;
-    }
-    BRT_CUDA(cudaEventRecord(c->ev_t[1], s));
-    // this frame becomes the history of the next call
-    BRT_CUDA(cudaMemcpyAsync(c->dn_h_nrm.ptr(), f->d_aov_nrm.ptr(), npx * 16, cudaMemcpyDeviceToDevice, s));
-    BRT_CUDA(cudaMemcpyAsync(c->dn_h_inst.ptr(), f->d_aov_inst.ptr(), npx * 4, cudaMemcpyDeviceToDevice, s));
-    BRT_CUDA(cudaMemcpyAsync(c->dn_h_t.ptr(), f->d_aov_t.ptr(), npx * 4, cudaMemcpyDeviceToDevice, s));
-    for (int i = 0; i < 16; ++i) c->dn_prev_vp[i] = (float)vp[i];
-    c->dn_prev_eye[0] = u->viewInverse[3];
-    c->dn_prev_eye[1] = u->viewInverse[7];
-    c->dn_prev_eye[2] = u->viewInverse[11];
-    c->dn_have_history = true;
-    c->dn_parity = par ^ 1;
-    c->dn_result = cur;
-    if (rgba_host) BRT_CUDA(cudaMemcpyAsync(rgba_host, c->dn_work[cur].ptr(), npx * 16, cudaMemcpyDeviceToHost, s));
+    enqueue_denoise(c, f, *u, *d, s);
+    const size_t npx = (size_t)f->frame_w * f->frame_h;
+    if (rgba_host) BRT_CUDA(cudaMemcpyAsync(rgba_host, f->d_denoised.ptr(), npx * 16, cudaMemcpyDeviceToHost, s));
     BRT_CUDA(cudaStreamSynchronize(s));
     float ms = 0.0f;
-    cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[1]);
+    cudaEventElapsedTime(&ms, f->ev_dn[0], f->ev_dn[1]);
     c->stats.ms_denoise = ms;
-    c->stats.launches_denoise = launches;
+    c->stats.launches_denoise = f->dn_launches;
+  });
+}
+
+/* options used by frames rendered with BRT_RENDER_DENOISE */
+int brt_denoise_configure(brt_context* c, const brt_denoise_opts* d) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!d) invalid("denoise_configure: null");
+    check_denoise_opts(*d);
+    wait_all_frames(c);
+    c->dn_opts = *d;
   });
 }
 
@@ -1883,6 +1941,6 @@ int brt_get_light_bvh(brt_context* c, brt_light_bvh_node* out, uint32_t max_node
   });
 }
 
-void* brt_denoised_image(brt_context* c) { return c && c->dn_w ? c->dn_work[c->dn_result].ptr() : nullptr; }
+void* brt_denoised_image(brt_context* c) { return c && c->dn_w ? c->slots[c->last_slot].d_denoised.ptr() : nullptr; }
 
 }  // extern "C"

@@ -138,6 +138,9 @@ typedef struct brt_config {
  * contribution by the probability — unbiased, one shadow ray per hit whatever the light count, no BRT_MAX_LIGHTS limit.
  * All lights must be POINT lights (the only kind Scene::createLight creates, RT/Scene.cpp:88-97). */
 #define BRT_RENDER_LIGHT_BVH 64u
+/* run the denoiser stages (brt_denoise_configure) right after the resolve, on the frame's own stream: the image handed back (and
+ * converted to the present format) is the denoised one. Implies BRT_RENDER_GBUFFER. Frames must be submitted in display order. */
+#define BRT_RENDER_DENOISE 128u
 #define BRT_RENDER_GBUFFER 32u       /* also keep world position + shading normal of the primary hit (input of brt_denoise) */
 
 /* Output format of the image handed back by the render entry points (bits 8..10 of brt_render_opts.flags): the format
@@ -311,6 +314,10 @@ typedef struct brt_denoise_opts {
 #define BRT_DENOISE_RESET 1u      /* drop the history first (camera cut, scene change) */
 #define BRT_DENOISE_BILATERAL 2u  /* final 3x3 joint-bilateral pass */
 BRT_API int brt_denoise(brt_context* ctx, const brt_uniform* u, const brt_denoise_opts* opts, float* rgba_host);
+/* options of the denoiser stages that frames rendered with BRT_RENDER_DENOISE run (default: 4 a-trous iterations + bilateral pass,
+ * sigma_n 2^5, sigma_z 0.05, sigma_l 4, no history clamping, 32 frames of history); BRT_DENOISE_RESET in flags is honoured by every
+ * such frame until it is configured away */
+BRT_API int brt_denoise_configure(brt_context* ctx, const brt_denoise_opts* opts);
 BRT_API void* brt_denoised_image(brt_context* ctx);
 
 /* copies the light BVH built by the last brt_scene_build to the host: up to max_nodes nodes, returns the node count in *n_nodes

@@ -470,3 +470,46 @@ def light_bvh(pkg, orc_mod, make):
     a.scene_build()
     with pytest.raises(pkg.BrtError):
         a.render_frame(u, a.opts(w, h, 1, LB))
+
+
+def denoise_in_flight(pkg, orc_mod, make, w=96, h=96):
+    """BRT_RENDER_DENOISE: the denoiser stages run on the frame's own stream right after the resolve, also for frames in flight on
+    rotating slots (their shared history is handed from frame to frame in submission order); the images handed back — linear
+    float and the 8-bit present format — equal the oracle's render + denoise (+ present conversion) of the same sequence."""
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    base = R | T | D | J
+    dop = a.denoise_opts(iterations=3, sigma_n_log2=4, sigma_z=0.05, sigma_l=4.0, clamp_gamma=2.0, max_history=16.0, flags=pkg.DENOISE_BILATERAL)
+    a.denoise_configure(dop)
+    n = 7
+    unis = []
+    for k in range(n):
+        u = scene.uniform(a, w, h, 3 * k + 1, 4)
+        u.viewInverse[3] += 0.02 * k
+        unis.append(u)
+    outs = [np.zeros((h, w, 4), np.float32) for _ in range(n)]
+    for k in range(n):
+        a.render_frame_async(unis[k], a.opts(w, h, 1, base | pkg.DENOISE), k % 3, outs[k].ctypes.data)
+    for slot in range(3):
+        a.frame_wait(slot)
+    for k in range(n):
+        b.render_frame(unis[k], b.opts(w, h, 1, base | pkg.GBUFFER))
+        ref = b.denoise(unis[k], dop, w, h)
+        assert np.array_equal(outs[k].view(np.uint32), ref.view(np.uint32)), k
+    st = a.get_stats()
+    assert st.launches_denoise == 5 and st.ms_denoise >= 0.0
+    # synchronous call, present format: the denoised frame converted on the GPU
+    u = scene.uniform(a, w, h, 40, 4)
+    img8 = a.render_frame(u, a.opts(w, h, 1, base | pkg.DENOISE | pkg.render_format(pkg.FORMAT_BGRA8_SRGB)))
+    b.render_frame(u, b.opts(w, h, 1, base | pkg.GBUFFER))
+    ref = b.denoise(u, dop, w, h)
+    c = np.clip(ref[..., :3].astype(np.float64), 0.0, 1.0)
+    srgb = np.rint(np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055) * 255.0)
+    assert img8.dtype == np.uint8 and np.abs(img8[..., [2, 1, 0]].astype(np.float64) - srgb).max() <= 1
+    assert (img8[..., [2, 1, 0]] == srgb).mean() > 0.99 and (img8[..., 3] == 255).all()
+    # the separate entry point continues the same history
+    a.render_frame(unis[0], a.opts(w, h, 1, base | pkg.GBUFFER))
+    b.render_frame(unis[0], b.opts(w, h, 1, base | pkg.GBUFFER))
+    assert np.array_equal(a.denoise(unis[0], dop, w, h).view(np.uint32), b.denoise(unis[0], dop, w, h).view(np.uint32))
