@@ -259,8 +259,9 @@ struct FrameSlot {
   DevBuf d_consts;
   uint32_t generation = 0;          // bumped whenever the wavefront buffers are reallocated (invalidates the graph)
 #ifndef BRT_EMU
-  cudaGraphExec_t graph_exec = nullptr;  // the whole frame, captured once per frame shape and replayed
-  uint64_t graph_key[16] = {0};
+  // the whole frame, captured once per frame shape and replayed ([1]: the second gather image of the fused multi-GPU exchange)
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  uint64_t graph_key[2][18] = {{0}, {0}};
 #endif  // streams / events / pinned block created
 };
 
@@ -868,6 +869,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   // The stream work of the frame (about 45 dependent kernel launches, memsets and event records for C2) is captured into a CUDA
   // graph the first time a frame shape is seen on this slot and replayed afterwards: everything that changes from frame to frame
   // travels through FrameConsts, queue sizes already live on the device.
+  const uint32_t gimg = to_peers ? c->gather_next : 0u;  // gather image this frame's resolve stores into (two alternate)
   auto enqueue = [&]() {
     BRT_CUDA(cudaMemcpyAsync(f->d_consts.ptr(), f->h_consts, sizeof(FrameConsts), cudaMemcpyHostToDevice, s));
     f->events_used = 0;
@@ -1073,9 +1075,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
         if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
         rp.tiles = nullptr;
         rp.n_peers = c->n_peers;
-        for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]) + (size_t)c->gather_next * npx;
-        c->gather_last = c->gather_next;
-        c->gather_next ^= 1u;
+        for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]) + (size_t)gimg * npx;
       }
       Timed t(f, CLS_RESOLVE, s);
       BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
@@ -1101,18 +1101,22 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
 #ifdef BRT_EMU
   enqueue();
 #else
-  const bool use_graph = !(c->flags & (BRT_CFG_NO_GRAPH | BRT_CFG_NO_OVERLAP | BRT_CFG_COUNTERS)) && c->tile_world == 1 && !to_peers;
-  const uint64_t key[16] = {((uint64_t)o.width << 32) | o.height, ((uint64_t)o.spp << 32) | o.flags, ((uint64_t)o.crop_x0 << 32) | o.crop_y0,
+  // (the legacy default stream a caller may hand to brt_set_stream cannot be captured)
+  const bool use_graph = !(c->flags & (BRT_CFG_NO_GRAPH | BRT_CFG_NO_OVERLAP | BRT_CFG_COUNTERS)) && (c->tile_world == 1 || to_peers) &&
+                         s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  const uint64_t key[18] = {((uint64_t)o.width << 32) | o.height, ((uint64_t)o.spp << 32) | o.flags, ((uint64_t)o.crop_x0 << 32) | o.crop_y0,
                             ((uint64_t)o.crop_w << 32) | o.crop_h, ((uint64_t)rounds << 32) | n_lights, ((uint64_t)f->generation << 32) | c->tlas_count,
                             (uint64_t)c->d_tlas_nodes.ptr(), (uint64_t)c->d_tlas_inst.ptr(), (uint64_t)c->d_inst_shade.ptr(), (uint64_t)c->d_materials.ptr(),
                             (uint64_t)c->d_mat_ext.ptr(), (uint64_t)c->d_lights.ptr(), (uint64_t)c->d_light_bvh.ptr(), (uint64_t)d_tiles_out, (uint64_t)s,
-                            (uint64_t)f->d_consts.ptr()};
-  if (use_graph && f->graph_exec && std::memcmp(key, f->graph_key, sizeof(key)) == 0) {
-    BRT_CUDA(cudaGraphLaunch(f->graph_exec, s));
+                            (uint64_t)f->d_consts.ptr(), ((uint64_t)to_peers << 32) | gimg,
+                            to_peers ? (uint64_t)c->peer_images[0] ^ ((uint64_t)c->peer_images[c->n_peers - 1] << 1) : 0};
+  cudaGraphExec_t& gexec = f->graph_exec[gimg];
+  if (use_graph && gexec && std::memcmp(key, f->graph_key[gimg], sizeof(key)) == 0) {
+    BRT_CUDA(cudaGraphLaunch(gexec, s));
   } else if (use_graph) {
-    if (f->graph_exec) {
-      cudaGraphExecDestroy(f->graph_exec);
-      f->graph_exec = nullptr;
+    if (gexec) {
+      cudaGraphExecDestroy(gexec);
+      gexec = nullptr;
     }
     BRT_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
     g_capturing = true;
@@ -1127,18 +1131,22 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
     }
     g_capturing = false;
     BRT_CUDA(cudaStreamEndCapture(s, &graph));
-    const cudaError_t ie = cudaGraphInstantiate(&f->graph_exec, graph, 0);
+    const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) {
-      f->graph_exec = nullptr;
+      gexec = nullptr;
       BRT_CUDA(ie);
     }
-    std::memcpy(f->graph_key, key, sizeof(key));
-    BRT_CUDA(cudaGraphLaunch(f->graph_exec, s));
+    std::memcpy(f->graph_key[gimg], key, sizeof(key));
+    BRT_CUDA(cudaGraphLaunch(gexec, s));
   } else {
     enqueue();
   }
 #endif
+  if (to_peers) {
+    c->gather_last = gimg;
+    c->gather_next = gimg ^ 1u;
+  }
   c->prev_head = f->ev_head;
   // Denoiser stages and the present conversion of a denoised frame follow the (replayed) frame as ordinary stream work: their
   // history is shared by all slots, so they wait for the previous frame's stages with stream semantics.
@@ -1256,7 +1264,8 @@ void destroy_slot(FrameSlot* f) {
   if (f->fs_host) cudaFreeHost(f->fs_host);
   if (f->h_consts) cudaFreeHost(f->h_consts);
 #ifndef BRT_EMU
-  if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+  for (int k = 0; k < 2; ++k)
+    if (f->graph_exec[k]) cudaGraphExecDestroy(f->graph_exec[k]);
 #endif
 }
 

@@ -31,6 +31,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     pkg = importlib.import_module("hardware-ray-tracer_b200")
     ctx = pkg.Context(device=rank, tile_rank=rank, tile_world=world)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # a real stream: frames are captured into CUDA graphs (two per slot, one per gather image)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     scene = pkg.scenes.make_scene("terrain", small=True)
     scene.upload(ctx)
