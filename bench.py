@@ -283,6 +283,43 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    def timed_multi_pipelined(to_host, steps, warmup, collect=None):
+        """N > 1, fused exchange, TWO frames in flight per rank (the two gather images): frame i is submitted on slot i % 2 before
+        frame i-1 is completed (stores landed + barrier), so the latency-bound tail of one frame overlaps the head of the next on
+        every rank. ONE timed region around all K frames; L2 flush enqueued on the frame's stream before every frame; with
+        `to_host` rank 0 copies every completed frame to pinned host memory on a side stream (waited for inside the region)."""
+        streams = [torch.cuda.ExternalStream(ctx.frame_stream(k), device=dev) for k in range(2)]
+        hosts = [host_image, torch.empty(h * w * 4, dtype=torch.float32).pin_memory()] if to_host else None
+        small = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
+
+        def run(n):
+            for i in range(n):
+                with torch.cuda.stream(streams[i % 2]):
+                    small.fill_(i & 0xff)
+                frame.submit(u, opts, i % 2)
+                if i > 0:
+                    frame.complete((i - 1) % 2)
+                    if to_host and rank == 0:
+                        frame.to_host_async(hosts[(i - 1) % 2])
+            frame.complete((n - 1) % 2)
+            if to_host and rank == 0:
+                frame.to_host_async(hosts[(n - 1) % 2])
+            frame.wait_host()
+
+        run(max(warmup, 2))
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if collect is not None:
+            for _ in range(steps):
+                collect(ctx.get_stats())
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
     def timed_pipelined(to_host, steps, warmup, collect=None, opts=opts):
         """N = 1 product schedule: two frames in flight (brt_render_frame_async / brt_frame_wait — the reference's
         MAX_FRAMES_IN_FLIGHT = 2, VK/SwapChain.h:8). K frames are enqueued alternately on the two frame slots; ONE timed
@@ -355,6 +392,11 @@ def run_product(args):
         # ... and with the denoiser stages of Graphics/Denoiser/Denoiser.h in the frame (temporal accumulation, 4 a-trous iterations,
         # bilateral pass) before the conversion: trace -> denoise -> present image -> host
         ms_e2e_dn = timed_pipelined(True, args.steps, 3, opts=ctx.opts(w, h, spp, flags | pkg.DENOISE | pkg.render_format(pkg.FORMAT_BGRA8_UNORM)))
+    elif world > 1 and frame.mode == "p2p" and args.frames_in_flight >= 2:
+        ms_dev = timed_multi_pipelined(False, args.steps, args.warmup, count_launches)
+        clocks = sampler.stop() if sampler else None
+        ms_e2e = timed_multi_pipelined(True, args.steps, max(2, args.warmup // 2))
+        frame_latency = {"device_ms": timed(step_device, min(args.steps, 5), 1), "e2e_ms": timed_e2e_multi(min(args.steps, 5), 2)}
     else:
         ms_dev = timed(step_device, args.steps, args.warmup, count_launches)
         clocks = sampler.stop() if sampler else None
@@ -451,8 +493,10 @@ def run_product(args):
             "config": dict(bench_config(scene, cfg, args), exchange=exchange, **(
                 {"frames_in_flight": n_slots, "l2": "flushed before every frame (160 MiB write enqueued on the frame's stream, inside the timed region)",
                  "schedule": f"K frames rotate over {n_slots} frame slots (brt_render_frame_async / brt_frame_wait; the reference keeps "
-                             "MAX_FRAMES_IN_FLIGHT = 2 frames in flight); one timed region around all K steps"} if pipelined else {"frames_in_flight": 1, "e2e_schedule": "one timed region around all K steps; rank 0 copies frame k to the host on a side stream while "
-                    "frame k+1 is traced (two gather images), L2 flushed in-stream before every frame" if (world > 1 and frame.mode == "p2p") else "per-step"})),
+                             "MAX_FRAMES_IN_FLIGHT = 2 frames in flight); one timed region around all K steps"} if pipelined else {"frames_in_flight": 2 if (world > 1 and frame.mode == "p2p" and args.frames_in_flight >= 2) else 1,
+                 "schedule": "one timed region around all K steps: two frames in flight per rank (fused exchange, two gather images), frame i is "
+                             "submitted before frame i-1 is completed (stores landed + barrier); rank 0 copies frame k to the host on a side stream; "
+                             "L2 flushed in-stream before every frame" if (world > 1 and frame.mode == "p2p") else "per-step"})),
             "rays_per_step": int(rays), "single_frame_latency": frame_latency,
             "e2e_bgra8": ({"value": rays / (ms_e2e_bgra8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e_bgra8,
                            "d2h_bytes_per_step": w * h * 4, "format": "B8G8R8A8_UNORM"} if pipelined else None),

@@ -95,7 +95,7 @@ BRT_SYMBOLS = [
     "brt_scene_build", "brt_smart_cull", "brt_get_visibility", "brt_render_frame", "brt_render_frame_tiles",
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
-    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_denoise_configure", "brt_get_light_bvh",
+    "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_denoise_configure", "brt_render_frame_peers_async", "brt_get_light_bvh",
 ]
 
 
@@ -164,6 +164,7 @@ class SceneApi:
             "gather_image_open": (C.c_int, [vp, vp, u32]),
             "render_frame_peers": (C.c_int, [vp, P(Uniform), P(RenderOpts)]),
             "gather_image": (vp, [vp]),
+            "render_frame_peers_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32]),
             "denoise_configure": (C.c_int, [vp, P(DenoiseOpts)]),
             "render_frame_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32, vp]),
             "frame_wait": (C.c_int, [vp, u32]),
@@ -385,6 +386,9 @@ class SceneApi:
 
     def render_frame_peers(self, uniform, opts):
         self._ck(self._f("render_frame_peers")(self.ctx, C.byref(uniform), C.byref(opts)))
+
+    def render_frame_peers_async(self, uniform, opts, slot):
+        self._ck(self._f("render_frame_peers_async")(self.ctx, C.byref(uniform), C.byref(opts), slot))
 
     def gather_image(self):
         return self._f("gather_image")(self.ctx)

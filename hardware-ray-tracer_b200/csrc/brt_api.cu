@@ -245,6 +245,7 @@ struct FrameSlot {
   cudaEvent_t ev_dn[2] = {nullptr, nullptr};
   bool has_denoised = false;
   uint32_t dn_launches = 0;
+  uint32_t gather_img = 0;  // fused multi-GPU exchange: the gather image this slot's frame stored into
   bool has_gbuffer = false;
   uint32_t render_flags = 0;  // of the frame rendered last on this slot
   DevBuf d_alive;  // rounds that contributed per (sample in batch, slot)
@@ -1144,6 +1145,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   }
 #endif
   if (to_peers) {
+    f->gather_img = gimg;
     c->gather_last = gimg;
     c->gather_next = gimg ^ 1u;
   }
@@ -1693,9 +1695,25 @@ int brt_render_frame_peers(brt_context* c, const brt_uniform* u, const brt_rende
   });
 }
 
+// Two frames of the fused exchange in flight (the two gather images): submit on a slot, brt_frame_wait(slot) returns when this
+// rank's stores of that frame have landed; brt_gather_image then refers to the frame waited for last.
+int brt_render_frame_peers_async(brt_context* c, const brt_uniform* u, const brt_render_opts* o, uint32_t slot) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!u || !o) invalid("render_frame_peers_async: null");
+    if (slot >= 2) invalid("render_frame_peers_async: slot must be 0 or 1 (two gather images)");
+    BRT_CUDA(cudaSetDevice(c->device));
+    FrameSlot* f = &c->slots[slot];
+    finish_frame(c, f);
+    if (c->tables_dirty || c->tlas_dirty) wait_all_frames(c);
+    ensure_slot(c, f);
+    render_frame_device(c, f, *u, *o, nullptr, true);
+  });
+}
+
 void* brt_gather_image(brt_context* c) {
   if (!c || !c->d_gather.ptr()) return nullptr;
-  return static_cast<char*>(c->d_gather.ptr()) + (size_t)c->gather_last * c->gather_w * c->gather_h * 16;
+  return static_cast<char*>(c->d_gather.ptr()) + (size_t)c->slots[c->last_slot].gather_img * c->gather_w * c->gather_h * 16;
 }
 
 int brt_get_aov(brt_context* c, int kind, void* out) {

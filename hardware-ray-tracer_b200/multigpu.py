@@ -56,6 +56,20 @@ class TiledFrame:
         self.ctx.untile(self.gathered.data_ptr(), self.width, self.height, self.world, self.image.data_ptr())
         return self.image.view(self.height, self.width, 4)
 
+    def submit(self, uniform, opts, slot):
+        """p2p mode, two frames in flight: enqueues the frame on slot 0 / 1 (it stores into the gather image of that parity on every
+        rank) and returns. Every rank must submit the same frames in the same order and complete() them in that order."""
+        assert self.mode == "p2p" and opts.width == self.width and opts.height == self.height
+        self.ctx.render_frame_peers_async(uniform, opts, slot)
+
+    def complete(self, slot):
+        """Waits for this rank's stores of the slot's frame, then the barrier that makes every rank's gather image of that frame
+        complete (an asynchronous copy-out of the frame before it — the image the NEXT submit will overwrite — is finished first)."""
+        self.ctx.frame_wait(slot)
+        self.wait_host()
+        dist.all_reduce(self._barrier_token, group=self.group)
+        torch.cuda.current_stream().synchronize()
+
     def frame_ptr(self):
         """Device pointer of the complete row-major RGBA32F frame of the last render()."""
         return self.ctx.gather_image() if self.mode == "p2p" else self.image.data_ptr()

@@ -290,6 +290,10 @@ BRT_API int brt_gather_image_export(brt_context* ctx, uint32_t width, uint32_t h
 /* handles: tile_world x BRT_IPC_HANDLE_BYTES, in rank order (this rank's own entry is ignored) */
 BRT_API int brt_gather_image_open(brt_context* ctx, const void* handles, uint32_t world);
 BRT_API int brt_render_frame_peers(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts);
+/* the same on frame slot 0 or 1 without waiting: two frames (the two gather images) may be in flight; brt_frame_wait(slot) returns
+ * when this rank's stores of the slot's frame have landed. Ranks must submit the same frames in the same order. */
+BRT_API int brt_render_frame_peers_async(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, uint32_t slot);
+/* device pointer of the complete gathered frame of the slot waited for last */
 BRT_API void* brt_gather_image(brt_context* ctx);
 /* device pointer of the context's own full-frame RGBA32F image of the last frame (the slot last waited for) */
 BRT_API void* brt_device_image(brt_context* ctx);

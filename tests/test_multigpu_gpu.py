@@ -65,6 +65,21 @@ def _worker(rank, world, port, out_dir):
                 frame.wait_host()
                 got.append(hosts[2 % 2].numpy().reshape(h, w, 4).copy())
                 np.save(os.path.join(out_dir, "pipelined.npy"), np.stack(got))
+            # two frames in flight: frame k+1 is submitted before frame k is completed
+            got = []
+            n = 5
+            for k in range(n):
+                frame.submit(scene.uniform(ctx, w, h, 20 + k, 3), opts, k % 2)
+                if k > 0:
+                    frame.complete((k - 1) % 2)
+                    if rank == 0:
+                        frame.to_host(hosts[0])
+                        got.append(hosts[0].numpy().reshape(h, w, 4).copy())
+            frame.complete((n - 1) % 2)
+            if rank == 0:
+                frame.to_host(hosts[0])
+                got.append(hosts[0].numpy().reshape(h, w, 4).copy())
+                np.save(os.path.join(out_dir, "inflight.npy"), np.stack(got))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -83,6 +98,10 @@ def test_two_gpu_exchange_modes(pkg, tmp_path):
         for r in range(world):
             img = np.load(tmp_path / f"{mode}{r}.npy")
             assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)), (mode, r)
+    inflight = np.load(tmp_path / "inflight.npy")
+    for k in range(5):
+        ref = single.render_frame(scene.uniform(single, w, h, 20 + k, 3), single.opts(w, h, 2, 3))
+        assert np.array_equal(inflight[k].view(np.uint32), ref.view(np.uint32)), ("in flight", k)
     piped = np.load(tmp_path / "pipelined.npy")
     for k in range(3):
         ref = single.render_frame(scene.uniform(single, w, h, 10 + k, 3), single.opts(w, h, 2, 3))
