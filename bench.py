@@ -3,12 +3,20 @@
 
 A *step* is one frame of the workload: every ray query (primary, bounce, shadow) of the frame traced and
 shaded by the CUDA path, the scene (BVH, tables) already resident in HBM. `value` = rays of all ranks per
-second of device time. `e2e` = the same through the reference-facing C-ABI call brt_render_frame with a
-HOST framebuffer (uniform from host memory in, RGBA32F image copied back to pinned host memory inside the
-timed region). N > 1 (torchrun, one process per GPU): the frame is split into 32x32 tiles round-robin over
-the ranks, scene replicated, one NCCL all-gather of the packed tile buffers per frame, un-tile on every rank.
+second of device time. `e2e` = the same through the reference-facing C-ABI calls with a HOST framebuffer
+(uniform from host memory in, RGBA32F image copied back to pinned host memory inside the timed region).
 
-  python bench.py --gpus 1 --steps 10 --warmup 3              # product arm (C2: 1M-tri scene, 1080p, 2 bounces)
+N = 1 (C2: 1M triangles, 1080p, 2 bounces): K frames rotate over the library's frame slots
+(brt_render_frame_async / brt_frame_wait — the reference keeps MAX_FRAMES_IN_FLIGHT = 2 frames in flight),
+every frame a replayed CUDA graph; ONE timed region around all K steps, the L2 flush of every step enqueued
+in-stream inside it. `single_frame_latency` is one synchronous brt_render_frame at a time.
+N > 1 (torchrun, one process per GPU; C3: 4K, 16 spp, 4-bounce GI): the frame is split into 32x32 tiles
+round-robin over the ranks, scene replicated; the resolve kernel of every rank stores its pixels into all
+ranks' gather images through NVLink peer memory (--exchange p2p, default; two frames in flight per rank) or
+the packed tiles are all-gathered with NCCL and un-tiled (--exchange nccl).
+
+  python bench.py                                             # product arm, N = 1
+  torchrun --nproc-per-node 8 bench.py --gpus 8               # C3 on eight GPUs
   python bench.py --impl reference --steps 2 --warmup 1       # CPU arm: the oracle (kind "port") on all host threads
 
 Only the cpu_baseline leg and --impl reference touch oracle/ (the checker); the product arm needs
@@ -321,10 +329,10 @@ def run_product(args):
         return float(t.item()) / steps
 
     def timed_pipelined(to_host, steps, warmup, collect=None, opts=opts):
-        """N = 1 product schedule: two frames in flight (brt_render_frame_async / brt_frame_wait — the reference's
-        MAX_FRAMES_IN_FLIGHT = 2, VK/SwapChain.h:8). K frames are enqueued alternately on the two frame slots; ONE timed
-        region brackets all K steps (synchronize on both sides, CUDA events on the slots' streams). The L2 flush (a write
-        larger than L2) of every step is enqueued on the frame's stream right before the frame, INSIDE the timed region."""
+        """N = 1 product schedule: frames in flight (brt_render_frame_async / brt_frame_wait — the reference's
+        MAX_FRAMES_IN_FLIGHT, VK/SwapChain.h:8). K frames rotate over the frame slots; ONE timed region brackets all K
+        steps (synchronize on both sides, CUDA events on the slots' streams). The L2 flush (a write larger than L2) of
+        every step is enqueued on the frame's stream right before the frame, INSIDE the timed region."""
         streams = [torch.cuda.ExternalStream(ctx.frame_stream(k), device=dev) for k in range(n_slots)]
         hosts = host_images
 
