@@ -954,6 +954,37 @@ void orc_kat_sample_cosine(float r1, float r2, float out[3], float* pdf) {
 }
 void orc_kat_sincos(float x, float* s, float* c) { det_sincos(x, s, c); }
 float orc_kat_log2(float x) { return det_log2(x); }
+float orc_kat_exp2(float x) { return det_exp2(x); }
+float orc_kat_srgb(float x) { return linear_to_srgb(x); }
+uint32_t orc_kat_unorm8(float x) { return float_to_unorm8(x); }
+// probability with which the light BVH descent ends at each light for a shading point P: the products of the branch
+// probabilities along every root-to-leaf path, computed by exhaustive recursion (test infrastructure for the sampler's pdf)
+int orc_kat_light_pdfs(orc_context* c, const float P[3], float* out, uint32_t n) {
+  if (!c || !out || n != c->lights.size()) return BRT_ERR_INVALID;
+  light_bvh_build(c);
+  for (uint32_t i = 0; i < n; ++i) out[i] = 0.0f;
+  if (c->light_bvh.empty()) return BRT_OK;
+  struct Item { uint32_t node; float p; };
+  std::vector<Item> st{{0u, 1.0f}};
+  vec3 p = V3(P[0], P[1], P[2]);
+  while (!st.empty()) {
+    Item it = st.back();
+    st.pop_back();
+    int child = c->light_bvh[it.node].childIndex;
+    if (child < 0) { out[-1 - child] = it.p; continue; }
+    float w0 = light_bvh_importance(c->light_bvh[child], p), w1 = light_bvh_importance(c->light_bvh[child + 1], p);
+    float sum = w0 + w1;
+    float p0 = sum > 0.0f ? w0 / sum : 0.5f;
+    st.push_back({(uint32_t)child, it.p * p0});
+    st.push_back({(uint32_t)child + 1u, it.p * (1.0f - p0)});
+  }
+  return BRT_OK;
+}
+// one draw of the sampler: light index and 1 / pdf for random number r
+uint32_t orc_kat_light_sample(orc_context* c, const float P[3], float r, float* inv_pdf) {
+  light_bvh_build(c);
+  return light_bvh_sample(c, V3(P[0], P[1], P[2]), r, *inv_pdf);
+}
 int orc_kat_intersect_tri(const float o[3], const float d[3], float tmin, float tmax, const float v0[3], const float v1[3], const float v2[3], float tuv[3]) {
   RayShear s = make_shear(V3(d[0], d[1], d[2]));
   return intersect_tri(V3(o[0], o[1], o[2]), s, tmin, tmax, V3(v0[0], v0[1], v0[2]), V3(v1[0], v1[1], v1[2]), V3(v2[0], v2[1], v2[2]), tuv[0], tuv[1], tuv[2]) ? 1 : 0;

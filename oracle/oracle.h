@@ -58,6 +58,11 @@ float orc_kat_log2(float x);
 int orc_kat_intersect_tri(const float o[3], const float d[3], float tmin, float tmax, const float v0[3], const float v1[3], const float v2[3], float tuv[3]);
 /* Camera::setPerspectiveProjection + setView (Graphics/Camera.cpp:8-17,71-95) and the uniform
  * block of RTApp::run (RT/RTApp.cpp:44-49) */
+float orc_kat_exp2(float x);
+float orc_kat_srgb(float x);
+uint32_t orc_kat_unorm8(float x);
+int orc_kat_light_pdfs(orc_context* c, const float P[3], float* out, uint32_t n);
+uint32_t orc_kat_light_sample(orc_context* c, const float P[3], float r, float* inv_pdf);
 int orc_get_light_bvh(orc_context* c, brt_light_bvh_node* out, uint32_t max_nodes, uint32_t* n_nodes);
 int orc_denoise(orc_context* c, const brt_uniform* u, const brt_denoise_opts* opts, float* rgba_host);
 void orc_camera_handle_inputs(uint32_t keys, float dt, float position[3], float rotation[3]);

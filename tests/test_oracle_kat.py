@@ -186,3 +186,57 @@ def test_oracle_error_behaviour(pkg, orc_mod):
     with pytest.raises(pkg.BrtError):
         u = o.camera_uniform((0, 0, 0), (0, 0, 0), 1.0, 1.0)
         o.render_frame(u, o.opts(4, 4))  # scene not built
+
+
+def test_det_exp2_srgb_unorm8(orc_mod):
+    """The explicit exp2 polynomial (sRGB curve, denoiser weights), the sRGB transfer function and Vulkan's float -> UNORM8 rule."""
+    import ctypes as C
+    lib = orc_mod.load()
+    lib.orc_kat_exp2.restype, lib.orc_kat_exp2.argtypes = C.c_float, [C.c_float]
+    lib.orc_kat_srgb.restype, lib.orc_kat_srgb.argtypes = C.c_float, [C.c_float]
+    lib.orc_kat_unorm8.restype, lib.orc_kat_unorm8.argtypes = C.c_uint32, [C.c_float]
+    xs = np.concatenate([np.linspace(-100, 100, 4001), np.arange(-20, 21), np.array([0.5, -0.5, 1e-3, -1e-3])]).astype(np.float32)
+    got = np.array([lib.orc_kat_exp2(float(x)) for x in xs], dtype=np.float64)
+    want = np.exp2(xs.astype(np.float64))
+    assert np.max(np.abs(got / want - 1.0)) < 4e-7          # a few ulp over the whole range the denoiser / sRGB curve use
+    assert all(lib.orc_kat_exp2(float(k)) == 2.0 ** k for k in range(-20, 21))  # exact at integers
+    cs = np.linspace(0.0, 1.0, 2001).astype(np.float32)
+    s = np.array([lib.orc_kat_srgb(float(c)) for c in cs], dtype=np.float64)
+    ref = np.where(cs <= 0.0031308, 12.92 * cs, 1.055 * np.power(cs.astype(np.float64), 1 / 2.4) - 0.055)
+    assert np.max(np.abs(s - ref)) < 2e-6 and np.all(np.diff(s) >= 0.0) and s[0] == 0.0 and s[-1] == 1.0
+    assert lib.orc_kat_srgb(-1.0) == 0.0 and lib.orc_kat_srgb(7.0) == 1.0 and lib.orc_kat_srgb(float("nan")) == 0.0
+    # UNORM8: clamp, NaN -> 0, round to nearest even
+    for f, q in ((-0.1, 0), (0.0, 0), (1.0, 255), (3.0, 255), (float("nan"), 0), (0.5 / 255, 0), (1.5 / 255, 2), (2.5 / 255, 2), (0.5, 128), (254.5 / 255, 254)):
+        assert lib.orc_kat_unorm8(f) == q, (f, q)
+
+
+def test_light_bvh_sampler_pdf(pkg, orc_mod):
+    """Light BVH descent: for any shading point the leaf probabilities sum to one, every light with flux can be
+    reached, the sampler's 1 / pdf is the reciprocal of that probability, and drawing with a stratified random number reproduces it."""
+    import ctypes as C
+    lib = orc_mod.load()
+    f3 = C.POINTER(C.c_float)
+    lib.orc_kat_light_pdfs.restype, lib.orc_kat_light_pdfs.argtypes = C.c_int, [C.c_void_p, f3, f3, C.c_uint32]
+    lib.orc_kat_light_sample.restype, lib.orc_kat_light_sample.argtypes = C.c_uint32, [C.c_void_p, f3, C.c_float, f3]
+    orc = orc_mod.Oracle(pkg)
+    pkg.scenes.cornell().upload(orc, build=False)
+    rng = np.random.default_rng(3)
+    n = 1 + 37
+    for _ in range(37):
+        orc.light_create((rng.random(3) * 4 - 2).tolist(), (rng.random(3) + 0.05).tolist(), float(0.1 + rng.random() * 3))
+    orc.scene_build()
+    for P in ([0.0, 0.0, 0.0], [1.9, -1.9, 0.3], [40.0, 5.0, -30.0]):
+        p = (C.c_float * 3)(*P)
+        pdf = (C.c_float * n)()
+        assert lib.orc_kat_light_pdfs(orc.ctx, p, pdf, n) == 0
+        pdf = np.array(pdf, dtype=np.float64)
+        assert abs(pdf.sum() - 1.0) < 1e-5 and (pdf > 0).all()
+        m = 20000
+        counts = np.zeros(n)
+        inv = C.c_float()
+        for k in range(m):
+            li = lib.orc_kat_light_sample(orc.ctx, p, (k + 0.5) / m, C.byref(inv))
+            counts[li] += 1
+            if k % 997 == 0:
+                assert abs(inv.value * pdf[li] - 1.0) < 1e-4
+        assert np.abs(counts / m - pdf).max() < 2.0 / m * n  # stratified draws: each leaf interval is hit to within its two ends
