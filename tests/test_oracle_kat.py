@@ -240,3 +240,30 @@ def test_light_bvh_sampler_pdf(pkg, orc_mod):
             if k % 997 == 0:
                 assert abs(inv.value * pdf[li] - 1.0) < 1e-4
         assert np.abs(counts / m - pdf).max() < 2.0 / m * n  # stratified draws: each leaf interval is hit to within its two ends
+
+
+def test_math_golden_bits(orc_mod):
+    """tests/golden/math_kat.json (generator: tests/golden/make_math_kat.py): the deterministic elementary functions keep their bits."""
+    import ctypes as C
+    import json
+    import os
+    import struct
+    lib = orc_mod.load()
+    for name in ("orc_kat_exp2", "orc_kat_srgb", "orc_kat_log2"):
+        getattr(lib, name).restype, getattr(lib, name).argtypes = C.c_float, [C.c_float]
+    lib.orc_kat_unorm8.restype, lib.orc_kat_unorm8.argtypes = C.c_uint32, [C.c_float]
+    kat = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "math_kat.json")))
+    f = lambda h: struct.unpack("<f", struct.pack("<I", int(h, 16)))[0]
+    b = lambda v: "%08x" % struct.unpack("<I", struct.pack("<f", v))[0]
+    for e in kat["exp2"]:
+        assert b(lib.orc_kat_exp2(f(e["x"]))) == e["y"]
+    for e in kat["log2"]:
+        assert b(lib.orc_kat_log2(f(e["x"]))) == e["y"]
+    for e in kat["srgb"]:
+        assert b(lib.orc_kat_srgb(f(e["x"]))) == e["y"]
+    for e in kat["sincos"]:
+        s, c = C.c_float(), C.c_float()
+        lib.orc_kat_sincos(f(e["x"]), C.byref(s), C.byref(c))
+        assert (b(s.value), b(c.value)) == (e["s"], e["c"])
+    for e in kat["unorm8"]:
+        assert lib.orc_kat_unorm8(f(e["x"])) == e["q"]
