@@ -52,6 +52,35 @@ def render_all(pkg, orc_mod):
         u = scene.uniform(o, w, h, 0, depth)
         img = o.render_frame(u, o.opts(w, h, spp, flags))
         out[name] = (img, o.get_aov(pkg.AOV_PRIM_ID, w, h), o.get_aov(pkg.AOV_INST_ID, w, h))
+    out.update(render_widened(pkg, orc_mod))
+    return out
+
+
+def render_widened(pkg, orc_mod):
+    """The rows beyond the hot path: a light-BVH frame, a present-format frame (the uint8 image is stored
+    widened to float32 so that all pins share one comparison) and the third frame of a denoised sequence."""
+    out = {}
+    w, h = 48, 48
+    scene = pkg.scenes.make_scene("cornell", small=True)
+    o = orc_mod.Oracle(pkg)
+    scene.upload(o, build=False)
+    for k in range(6):
+        o.light_create((0.5 - 0.2 * k, -0.7, 0.1 * k - 0.3), (1.0, 0.8 - 0.1 * k, 0.4 + 0.1 * k), 0.1 + 0.05 * k)
+    o.scene_build()
+    u = scene.uniform(o, w, h, 2, 3)
+    img = o.render_frame(u, o.opts(w, h, 2, pkg.LIGHT_BVH | pkg.BOUNCE_DIFFUSE | pkg.JITTER))
+    out["cornell_light_bvh"] = (img, o.get_aov(pkg.AOV_PRIM_ID, w, h), o.get_aov(pkg.AOV_INST_ID, w, h))
+    img8 = o.render_frame(u, o.opts(w, h, 1, pkg.render_format(pkg.FORMAT_BGRA8_SRGB)))
+    out["cornell_bgra8_srgb"] = (img8.astype(np.float32), o.get_aov(pkg.AOV_PRIM_ID, w, h), o.get_aov(pkg.AOV_INST_ID, w, h))
+    dop = o.denoise_opts(iterations=3, sigma_n_log2=5, sigma_z=0.05, sigma_l=4.0, clamp_gamma=1.5, max_history=8.0,
+                         flags=pkg.DENOISE_BILATERAL | pkg.DENOISE_RESET)
+    for k in range(3):
+        uk = scene.uniform(o, w, h, 5 + k, 4)
+        uk.viewInverse[3] += 0.03 * k
+        o.render_frame(uk, o.opts(w, h, 1, pkg.BOUNCE_DIFFUSE | pkg.JITTER | pkg.GBUFFER))
+        den = o.denoise(uk, dop, w, h)
+        dop.flags = pkg.DENOISE_BILATERAL
+    out["cornell_denoised_3"] = (den, o.get_aov(pkg.AOV_PRIM_ID, w, h), o.get_aov(pkg.AOV_INST_ID, w, h))
     return out
 
 
