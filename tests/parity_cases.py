@@ -513,3 +513,25 @@ def denoise_in_flight(pkg, orc_mod, make, w=96, h=96):
     a.render_frame(unis[0], a.opts(w, h, 1, base | pkg.GBUFFER))
     b.render_frame(unis[0], b.opts(w, h, 1, base | pkg.GBUFFER))
     assert np.array_equal(a.denoise(unis[0], dop, w, h).view(np.uint32), b.denoise(unis[0], dop, w, h).view(np.uint32))
+
+
+def golden_frames(pkg, make):
+    """The committed golden fixtures (tests/golden/oracle_frames.npz, generator make_golden.py) reproduced by the implementation under
+    test WITHOUT the oracle in the loop: radiance, primitive and instance ids bit for bit — including the light-BVH frame, the 8-bit
+    present frame and the third frame of the denoised sequence."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, "golden", "oracle_frames.npz"))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+
+    class _Mod:  # make_golden.render_all builds its contexts through `orc_mod.Oracle(pkg)`: hand it the implementation under test
+        @staticmethod
+        def Oracle(_pkg):
+            return make()
+
+    for name, (img, prim, inst) in make_golden.render_all(pkg, _Mod).items():
+        assert np.array_equal(g[name + "_prim"], prim), name
+        assert np.array_equal(g[name + "_inst"], inst), name
+        assert np.array_equal(g[name + "_img"].view(np.uint32), np.ascontiguousarray(img).view(np.uint32)), name

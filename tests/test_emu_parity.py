@@ -73,6 +73,10 @@ def test_denoise_in_flight(pkg, orc_mod, make):
     pc.denoise_in_flight(pkg, orc_mod, make)
 
 
+def test_golden_frames(pkg, make):
+    pc.golden_frames(pkg, make)
+
+
 def test_counters_flag(pkg, orc_mod, make):
     """BRT_CFG_COUNTERS fills the node / primitive visit counters that feed the roofline's algorithmic bytes."""
     scene = pkg.scenes.make_scene("terrain", small=True)

@@ -76,6 +76,10 @@ def test_denoise_in_flight(pkg, orc_mod, make):
     pc.denoise_in_flight(pkg, orc_mod, make)
 
 
+def test_golden_frames(pkg, make):
+    pc.golden_frames(pkg, make)
+
+
 def test_counters_match_plain_run(pkg, make):
     """The instrumented kernels (BRT_CFG_COUNTERS) produce the same image as the plain ones."""
     scene = pkg.scenes.make_scene("terrain", small=True)
