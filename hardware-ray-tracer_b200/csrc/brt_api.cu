@@ -1297,7 +1297,7 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     for (int k = 0; k < 3; ++k) BRT_CUDA(cudaEventCreate(&c->ev_t[k]));
     BRT_CUDA(cudaEventCreateWithFlags(&c->dn_event, cudaEventDisableTiming));
     c->own_stream = true;
-    c->builder.reset(new Builder(c->sm_count));
+    c->builder.reset(new Builder(c->sm_count, (c->flags & BRT_CFG_GREEDY_COLLAPSE) != 0));
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
   });
   if (rc != BRT_OK) {

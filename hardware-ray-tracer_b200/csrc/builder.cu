@@ -20,6 +20,7 @@ BRT_KERNEL_1D(k_inst_bounds, InstBoundsParams, inst_bounds_body)
 BRT_KERNEL_1D(k_morton, MortonParams, morton_body)
 BRT_KERNEL_1D(k_hierarchy, HierarchyParams, hierarchy_body)
 BRT_KERNEL_1D(k_refit, RefitParams, refit_body)
+BRT_KERNEL_1D(k_wide_cost, WideCostParams, wide_cost_body)
 BRT_KERNEL_1D(k_collapse, CollapseParams, collapse_body)
 BRT_KERNEL_1D(k_treelet, TreeletParams, treelet_body)
 
@@ -68,6 +69,7 @@ struct SmallBuildParams {
   uint32_t* vals_sorted;
   HierarchyParams hier;
   RefitParams refit;
+  WideCostParams wide;
   CollapseParams collapse; // level / queues / count_ptr are set per level by the kernel
   uint2* queue[2];
   float4* mesh_bounds;     // may be null
@@ -111,6 +113,12 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
   for (uint32_t i = tid; i < n; i += nt) refit_body(p.refit, i);
   __threadfence();
   __syncthreads();
+  for (uint32_t i = tid; i < n; i += nt) p.wide.arrive[i] = 0u;
+  __threadfence();
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nt) wide_cost_body(p.wide, i);
+  __threadfence();
+  __syncthreads();
   CollapseParams cp = p.collapse;
   for (uint32_t level = 0; level < 62; ++level) {
     const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&cp.g->level_count[level]);
@@ -145,6 +153,7 @@ void Builder::ensure_scratch(uint32_t n) {
   arrive_.ensure(N * 4);
   sub_count_.ensure(2 * N * 4);
   treelet_.ensure(2 * N * 4 + 16);  // SAH cost per binary node
+  wcost_.ensure(N * BRT_WCOST_STRIDE * 4);  // collapse cost table per internal binary node
 }
 
 void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treelets, Node8* out_nodes, const float* d_vertices,
@@ -172,11 +181,13 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     sp.hier = HierarchyParams{n - 1, nullptr, n, sp.keys_sorted, nodes_.as<BNode>(), parent_.as<uint32_t>()};
     sp.refit = RefitParams{n, nullptr, sp.vals_sorted, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes_.as<BNode>(), parent_.as<uint32_t>(),
                            arrive_.as<uint32_t>(), sub_count_.as<uint32_t>()};
+    sp.wide = WideCostParams{n, nullptr, nodes_.as<BNode>(), parent_.as<uint32_t>(), arrive_.as<uint32_t>(), wcost_.as<float>()};
     CollapseParams& cp = sp.collapse;
     cp.n = n;
     cp.max_leaf = max_leaf;
     cp.nodes = nodes_.as<BNode>();
     cp.sub_count = sub_count_.as<uint32_t>();
+    cp.wcost = greedy_collapse_ ? nullptr : wcost_.as<float>();
     cp.queue_cap = n / 2 + 8;
     cp.g = g;
     cp.out_nodes = out_nodes;
@@ -250,6 +261,13 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
       BRT_CUDA(cudaMemcpyAsync(&cost_after, cost, 4, cudaMemcpyDeviceToHost, stream));
       BRT_CUDA(cudaMemcpyAsync(&root_after, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
     }
+    // cost table of the collapse (which binary nodes become wide nodes), on the final binary topology
+    if (n > 1) {
+      BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
+      WideCostParams p{n, nullptr, nodes, parent, arrive_.as<uint32_t>(), wcost_.as<float>()};
+      BRT_LAUNCH_1D(k_wide_cost, p, grid_n, 256, stream);
+      BRT_CHECK_LAUNCH();
+    }
     // collapse, level by level; the per-level work count lives on the device
     const uint32_t node_cap = node_capacity(n);
     const uint32_t queue_cap = n / 2 + 8;
@@ -258,6 +276,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     cp.max_leaf = max_leaf;
     cp.nodes = nodes;
     cp.sub_count = sub_count;
+    cp.wcost = n > 1 && !greedy_collapse_ ? wcost_.as<float>() : nullptr;
     cp.queue_cap = queue_cap;
     cp.g = g;
     cp.out_nodes = out_nodes;

@@ -16,7 +16,7 @@ struct BuildResult {
 
 class Builder {
  public:
-  explicit Builder(int sm_count) : sm_count_(sm_count) {}
+  explicit Builder(int sm_count, bool greedy_collapse = false) : sm_count_(sm_count), greedy_collapse_(greedy_collapse) {}
   // BLAS over an indexed triangle mesh (brt_vertex stride). out_nodes must hold node_capacity(n_tris)
   // nodes, out_tris n_tris records. d_mesh_bounds (2 x float4, may be null) receives the exact mesh box.
   // Synchronises `stream` once at the end to read the result back.
@@ -34,7 +34,8 @@ class Builder {
            const uint32_t* d_indices, TriRec* out_tris, const InstRec* d_src, InstRec* out_inst, float4* d_mesh_bounds, BuildResult* res);
   void ensure_scratch(uint32_t n);
   int sm_count_;
-  DevBuf globals_, prim_lo_, prim_hi_, keys_[2], vals_[2], sort_tmp_, nodes_, parent_, arrive_, sub_count_, queue_[2], treelet_;
+  bool greedy_collapse_;  // BRT_CFG_GREEDY_COLLAPSE
+  DevBuf globals_, prim_lo_, prim_hi_, keys_[2], vals_[2], sort_tmp_, nodes_, parent_, arrive_, sub_count_, queue_[2], treelet_, wcost_;
   friend struct BuilderAccess;
 };
 

@@ -124,6 +124,10 @@ typedef struct brt_config {
  * contexts capture one graph per frame slot and shape). A replayed frame reports ms_total only: the per-class kernel times of
  * brt_stats need this flag (BRT_CFG_NO_OVERLAP and BRT_CFG_COUNTERS imply it). */
 #define BRT_CFG_NO_GRAPH 16u
+/* measurement only: collapse the binary hierarchy into 8-wide nodes by opening the child with the largest area until the 8 slots
+ * are full (the builder's first rule) instead of the area-optimal choice of wide nodes (build_kernels.cuh, wide_cost_body).
+ * Same frames (results never depend on the BVH's shape), more and emptier nodes. */
+#define BRT_CFG_GREEDY_COLLAPSE 32u
 
 /* render mode flags. With none of the BOUNCE flags set the behaviour is the reference's live path:
  * direct light + hard shadows, weight = 0 after the first hit (SH/raytracing.slang:168). */

@@ -74,6 +74,26 @@ def random_rays_vs_brute_force(pkg, orc_mod, make, kind="terrain"):
     assert np.array_equal(oa[:, 3], ob_[:, 3])
 
 
+def collapse_rules(pkg, make):
+    """The area-optimal choice of 8-wide nodes (wide_cost_body) against the greedy rule (BRT_CFG_GREEDY_COLLAPSE): identical hits and
+    frames (results never depend on the BVH's shape), fewer nodes, fewer node visits."""
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a, b = make(pkg.CFG_COUNTERS), make(pkg.CFG_COUNTERS | pkg.CFG_GREEDY_COLLAPSE)
+    scene.upload(a)
+    scene.upload(b)
+    rays = random_rays(20000, 23, (-8, -4, -8), (8, 2, 8))
+    assert np.array_equal(a.trace_rays(rays, True), b.trace_rays(rays, True))
+    assert np.array_equal(a.trace_rays(rays, False)[:, 3], b.trace_rays(rays, False)[:, 3])
+    u = scene.uniform(a, 96, 64, 0, 3)
+    fl = pkg.BOUNCE_REFLECT | pkg.BOUNCE_REFRACT
+    ia, ib = a.render_frame(u, a.opts(96, 64, 1, fl)), b.render_frame(u, b.opts(96, 64, 1, fl))
+    assert np.array_equal(ia.view(np.uint32), ib.view(np.uint32))
+    sa, sb = a.get_stats(), b.get_stats()
+    assert sa.rays_closest == sb.rays_closest and sa.rays_occlusion == sb.rays_occlusion
+    assert sa.bvh_nodes < 0.75 * sb.bvh_nodes
+    assert sa.nodes_visited_closest <= sb.nodes_visited_closest and sa.nodes_visited_occlusion <= sb.nodes_visited_occlusion
+
+
 def grazing_and_axis_aligned_rays(pkg, orc_mod, make):
     """Rays with zero direction components, rays inside box faces and along triangle edges of the Cornell box."""
     scene = pkg.scenes.make_scene("cornell", small=True)

@@ -28,6 +28,10 @@ def test_random_rays_vs_brute_force(pkg, orc_mod, make, kind):
     pc.random_rays_vs_brute_force(pkg, orc_mod, make, kind)
 
 
+def test_collapse_rules(pkg, make):
+    pc.collapse_rules(pkg, make)
+
+
 def test_grazing_and_axis_aligned_rays(pkg, orc_mod, make):
     pc.grazing_and_axis_aligned_rays(pkg, orc_mod, make)
 

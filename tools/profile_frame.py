@@ -21,11 +21,14 @@ def main():
     ap.add_argument("--no-treelet", action="store_true")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--greedy-collapse", action="store_true")
     args = ap.parse_args()
     pkg = importlib.import_module("hardware-ray-tracer_b200")
     cfg = dict(pkg.scenes.CONFIGS[args.config])
     scene = pkg.scenes.make_scene(cfg.pop("scene"), small=args.small)
-    flags = pkg.CFG_NO_GRAPH | (pkg.CFG_COUNTERS if args.counters else 0)  # per-kernel event times need individually launched kernels | (pkg.CFG_NO_TREELET if args.no_treelet else 0) | (pkg.CFG_NO_OVERLAP if args.no_overlap else 0)
+    # per-kernel event times need individually launched kernels
+    flags = (pkg.CFG_NO_GRAPH | (pkg.CFG_COUNTERS if args.counters else 0) | (pkg.CFG_NO_TREELET if args.no_treelet else 0)
+             | (pkg.CFG_NO_OVERLAP if args.no_overlap else 0) | (pkg.CFG_GREEDY_COLLAPSE if args.greedy_collapse else 0))
     ctx = pkg.Context(device=0, flags=flags)
     t0 = time.perf_counter()
     scene.upload(ctx)
