@@ -111,3 +111,23 @@ def test_c4_instanced_10m(pkg, orc_mod):
         assert va == vb and np.array_equal(a.get_visibility(513), b.get_visibility(513))
         r = compare_frames(pkg, a, b, u, w, h, 0, 1, (800, 400, 320, 200))
         assert r["id_agreement"] >= 0.9999 and r["rmse"] <= 1e-3
+
+
+def test_large_scene_outside_l2_matches_oracle(pkg, orc_mod):
+    """8.9 M unique triangles (terrain 2048^2 quads + the icospheres): node and triangle records (~0.5 GB) exceed the 126 MB L2.
+    A 1080p window and incoherent rays against the oracle's independent binary SAH BVH."""
+    scene = pkg.scenes.terrain_icospheres(n=2048)
+    a, b = pkg.Context(device=0), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    st = a.get_stats()
+    assert st.total_triangles == scene.triangles() == 2 * 2048 * 2048 + 24 * 20480
+    assert st.bvh_bytes > 3 * 126 * 2 ** 20
+    w, h = 1920, 1080
+    u = scene.uniform(a, w, h, 0, 3)
+    r = compare_frames(pkg, a, b, u, w, h, R | T, 1, (832, 476, 192, 96))
+    assert r["id_agreement"] >= 0.9999 and r["rmse"] <= 1e-3
+    assert r["bit_exact"] and r["t_agreement"] == 1.0
+    rays = random_rays(100000, 29, (-8, -4, -8), (8, 1, 8))
+    assert np.array_equal(a.trace_rays(rays, True), b.trace_rays(rays, True))
+    assert np.array_equal(a.trace_rays(rays, False)[:, 3], b.trace_rays(rays, False)[:, 3])
