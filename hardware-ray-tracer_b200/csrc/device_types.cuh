@@ -77,7 +77,7 @@ struct __align__(16) LightRec {
 static_assert(sizeof(LightRec) == 32, "light record must be 32 bytes");
 
 #define BRT_STACK_SIZE 64       // traversal stack entries (8 B each)
-#define BRT_STACK_ALLOC (BRT_STACK_SIZE + 3)  // + the world ray parked behind the stack (traverse.cuh)
+#define BRT_STACK_ALLOC (BRT_STACK_SIZE + 5)  // + the world ray and its slab-test constants parked behind the stack (traverse.cuh)
 #define BRT_MAX_TREE_LEVELS 28  // TLAS + deepest BLAS levels the traversal stack is guaranteed to hold (see traverse.cuh)
 #define BRT_MAX_LIGHTS 16
 #define BRT_MISS 0xffffffffu

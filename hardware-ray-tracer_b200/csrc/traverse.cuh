@@ -152,6 +152,19 @@ struct Traversal {
     o_ = F3(u2f(a.x), u2f(a.y), u2f(b.x));
     d_ = F3(u2f(b.y), u2f(c.x), u2f(c.y));
   }
+  // ... and so do the world ray's slab-test constants: leaving a BLAS reloads them (two 8-byte loads) instead of recomputing
+  // three reciprocals and the octant
+  static BRT_HDM void store_world_raybox(uint2* __restrict__ stack, const RayBox& rb_) {
+    stack[BRT_STACK_SIZE + 3] = make_uint2(f2u(rb_.idir.x), f2u(rb_.idir.y));
+    stack[BRT_STACK_SIZE + 4] = make_uint2(f2u(rb_.idir.z), rb_.octinv);
+  }
+  BRT_HDM void restore_world(const uint2* __restrict__ stack) {
+    const uint2 a = stack[BRT_STACK_SIZE + 0], b = stack[BRT_STACK_SIZE + 1];
+    const uint2 e = stack[BRT_STACK_SIZE + 3], f = stack[BRT_STACK_SIZE + 4];
+    co = F3(u2f(a.x), u2f(a.y), u2f(b.x));
+    rb.idir = F3(u2f(e.x), u2f(e.y), u2f(f.x));
+    rb.octinv = f.y;
+  }
 
   BRT_HDM void init(uint2* __restrict__ stack, const Node8* tlas_, const InstRec* insts_, f3 o_, f3 d_, float tmin_, float tmax_) {
     tlas = tlas_;
@@ -168,7 +181,10 @@ struct Traversal {
     blas_sp = -1;
     co = o_;
     rb = make_raybox(d_);
-    sh = make_shear(d_);
+    store_world_raybox(stack, rb);
+    // (no shear constants for the world ray: triangles are only tested inside a BLAS, whose entry computes them for the object-space ray)
+    sh.kz = 0;
+    sh.Sx = sh.Sy = sh.Sz = 0.0f;
     nodes = tlas_;
     tris = nullptr;
     cur_inst = 0;
@@ -251,9 +267,7 @@ struct Traversal {
       if (blas_sp >= 0 && sp == blas_sp) {  // BLAS exhausted: back to the world ray
         blas_sp = -1;
         nodes = tlas;
-        f3 d;
-        load_world(stack, co, d);
-        rb = make_raybox(d);
+        restore_world(stack);
       }
       if (sp == 0) return true;
       G = stack[--sp];
