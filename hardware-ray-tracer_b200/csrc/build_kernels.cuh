@@ -182,7 +182,20 @@ BRT_HD void hierarchy_body(const HierarchyParams& p, uint32_t ui) {
   if (i == 0) p.parent[0] = BRT_MISS;
 }
 
+#define BRT_SAH_CI 1.2f  // cost of visiting an internal node
+#define BRT_SAH_CT 1.0f  // cost of one primitive test
+#define BRT_WCOST_STRIDE 8
+BRT_HD float box_area(f3 lo, f3 hi) {
+  const f3 e = hi - lo;
+  return 2.0f * ((e.x * e.y + e.y * e.z) + e.z * e.x);
+}
+BRT_HD void wide_cost_node(float* wcost, uint32_t par, uint32_t l, uint32_t r, uint32_t n_int, float area);
+
 // ---- bottom-up refit ---------------------------------------------------------------------------------
+// One walk from every leaf towards the root (the second thread to arrive at a node owns it) fills the boxes and the
+// primitive counts and, when asked to, the SAH cost of every subtree (the statistic of brt_get_stats) and the cost table
+// of the collapse (wide_cost_node): a build without treelet restructuring — a re-built dynamic mesh, the per-frame TLAS —
+// has its final topology here, and each separate bottom-up pass costs a chain of ~depth x 2 us of dependent atomics.
 struct RefitParams {
   uint32_t count;  // n leaves
   const uint32_t* count_ptr;
@@ -193,6 +206,8 @@ struct RefitParams {
   const uint32_t* parent;
   uint32_t* arrive;     // n-1, zeroed
   uint32_t* sub_count;  // 2n-1: primitives below each node
+  float* cost;          // 2n-1 or null: SAH cost of every subtree
+  float* wcost;         // n-1 rows or null: cost table of the collapse
 };
 BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
   const uint32_t n_int = p.count - 1;
@@ -203,6 +218,7 @@ BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
   p.nodes[n_int + i].lo = lo;
   p.nodes[n_int + i].hi = hi;
   p.sub_count[n_int + i] = 1;
+  if (p.cost) p.cost[n_int + i] = BRT_SAH_CT * box_area(xyz(lo), xyz(hi));
   uint32_t cur = n_int + i;
   for (;;) {
     const uint32_t par = p.parent[cur];
@@ -222,15 +238,18 @@ BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
     nd->hi.z = fmaxf(a->hi.z, b->hi.z);
     volatile uint32_t* sc = p.sub_count;
     sc[par] = sc[l] + sc[r];
+    if (p.cost || p.wcost) {
+      const float area = box_area(F3(nd->lo.x, nd->lo.y, nd->lo.z), F3(nd->hi.x, nd->hi.y, nd->hi.z));
+      if (p.cost) {
+        volatile float* c = p.cost;
+        c[par] = BRT_SAH_CI * area + c[l] + c[r];
+      }
+      if (p.wcost) wide_cost_node(p.wcost, par, l, r, n_int, area);
+    }
     cur = par;
   }
 }
 
-// ---- SAH cost of the binary tree (statistics only) ----------------------------------------------------
-BRT_HD float box_area(f3 lo, f3 hi) {
-  const f3 e = hi - lo;
-  return 2.0f * ((e.x * e.y + e.y * e.z) + e.z * e.x);
-}
 
 // ---- cost table for the collapse: which binary nodes become 8-wide nodes ---------------------------------
 // The collapse decides which binary nodes become 8-wide nodes. Every triangle is its own leaf slot, so the primitive
@@ -243,7 +262,6 @@ BRT_HD float box_area(f3 lo, f3 hi) {
 // One bottom-up pass (arrival counters, as the refit) stores C(n, 1..7); the collapse re-derives the choices from the
 // stored costs. (Opening the child with the largest area until 8 slots are full — the previous rule — left the nodes
 // half empty: 4.0 of 8 slots on the 1M-triangle scene, 9.3 node visits per primary ray against 7.1 now.)
-#define BRT_WCOST_STRIDE 8
 struct WideCostParams {
   uint32_t count;  // n leaves
   const uint32_t* count_ptr;
@@ -270,6 +288,20 @@ BRT_HD void wide_cost_load(const float* wcost, uint32_t id, uint32_t n_int, floa
   volatile const float* w = wcost + (size_t)id * BRT_WCOST_STRIDE;
   for (int k = 0; k < 7; ++k) out[k] = id < n_int ? w[k] : 0.0f;
 }
+// C(par, 1..7) from the finished tables of its children l, r
+BRT_HD void wide_cost_node(float* wcost, uint32_t par, uint32_t l, uint32_t r, uint32_t n_int, float area) {
+  float L[7], R[7], D[9];
+  wide_cost_load(wcost, l, n_int, L);
+  wide_cost_load(wcost, r, n_int, R);
+  wide_distribute(L, R, D, nullptr);
+  volatile float* w = wcost + (size_t)par * BRT_WCOST_STRIDE;
+  float c = area + D[8];
+  w[0] = c;
+  for (int k = 2; k <= 7; ++k) {
+    c = fminf(D[k], c);
+    w[k - 1] = c;
+  }
+}
 BRT_HD void wide_cost_body(const WideCostParams& p, uint32_t i) {
   const uint32_t n_int = p.count - 1;
   uint32_t cur = n_int + i;
@@ -281,18 +313,7 @@ BRT_HD void wide_cost_body(const WideCostParams& p, uint32_t i) {
     fence();
     volatile const BNode* nd = p.nodes + par;
     const uint32_t l = f2u(nd->lo.w), r = f2u(nd->hi.w);
-    float L[7], R[7], D[9];
-    wide_cost_load(p.wcost, l, n_int, L);
-    wide_cost_load(p.wcost, r, n_int, R);
-    wide_distribute(L, R, D, nullptr);
-    const float a = box_area(F3(nd->lo.x, nd->lo.y, nd->lo.z), F3(nd->hi.x, nd->hi.y, nd->hi.z));
-    volatile float* w = p.wcost + (size_t)par * BRT_WCOST_STRIDE;
-    float c = a + D[8];
-    w[0] = c;
-    for (int k = 2; k <= 7; ++k) {
-      c = fminf(D[k], c);
-      w[k - 1] = c;
-    }
+    wide_cost_node(p.wcost, par, l, r, n_int, box_area(F3(nd->lo.x, nd->lo.y, nd->lo.z), F3(nd->hi.x, nd->hi.y, nd->hi.z)));
     cur = par;
   }
 }
@@ -362,24 +383,33 @@ BRT_HD uint32_t quant_hi(float p, float s, float v) {
   return (uint32_t)q;
 }
 
-BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
-  const uint2 work = p.queue_in[item];
-  const uint32_t n_int = p.n - 1;
-  uint32_t ch[8];
-  float area[8];  // < 0: not expandable (becomes a leaf slot)
-  int n = 1;
-  ch[0] = work.x;
-  {
-    const bool expandable = work.x < n_int && p.sub_count[work.x] > p.max_leaf;
-    area[0] = expandable ? 1.0f : -1.0f;
+// plain (cacheable) loads of a finished cost table
+BRT_HD void wide_cost_fetch(const float* wcost, uint32_t id, uint32_t n_int, float* out) {
+  if (id < n_int) {
+    const float4 a = *reinterpret_cast<const float4*>(wcost + (size_t)id * BRT_WCOST_STRIDE);
+    const float4 b = *reinterpret_cast<const float4*>(wcost + (size_t)id * BRT_WCOST_STRIDE + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z;
+  } else {
+    for (int k = 0; k < 7; ++k) out[k] = 0.0f;
   }
-  if (p.wcost && area[0] >= 0.0f) {
+}
+
+// Which binary nodes become the (up to 8) children of the wide node made from binary node `root`: ch[0..n), bit k of
+// `inner`: child k becomes a wide node itself (otherwise it is a leaf slot). Returns n.
+BRT_HD int collapse_select(const CollapseParams& p, uint32_t root, uint32_t* ch, uint32_t& inner) {
+  const uint32_t n_int = p.n - 1;
+  int n = 1;
+  ch[0] = root;
+  inner = (root < n_int && p.sub_count[root] > p.max_leaf) ? 1u : 0u;
+  if (!inner) return n;
+  if (p.wcost) {
     // follow the dynamic programme: spread the subtree over the 8 slots with the splits that realise D(root, 8)
     uint32_t st_id[8];
     int st_budget[8];
     int sp = 0;
     n = 0;
-    st_id[sp] = work.x;
+    inner = 0u;
+    st_id[sp] = root;
     st_budget[sp] = 8;
     sp++;
     while (sp) {
@@ -390,8 +420,8 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
       const uint32_t c2[2] = {f2u(nd.lo.w), f2u(nd.hi.w)};
       float L[7], R[7], D[9];
       int split[9];
-      wide_cost_load(p.wcost, c2[0], n_int, L);
-      wide_cost_load(p.wcost, c2[1], n_int, R);
+      wide_cost_fetch(p.wcost, c2[0], n_int, L);
+      wide_cost_fetch(p.wcost, c2[1], n_int, R);
       wide_distribute(L, R, D, split);
       const int budget[2] = {split[j], j - split[j]};
       for (int s = 0; s < 2; ++s) {
@@ -402,7 +432,7 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
         else while (b > 1 && T[b - 1] == T[b - 2]) b--;  // C(c, b) = C(c, b - 1): the extra slot buys nothing
         if (b <= 1) {
           ch[n] = c;
-          area[n] = b == 1 ? 1.0f : -1.0f;
+          if (b == 1) inner |= 1u << n;
           n++;
         } else {
           st_id[sp] = c;
@@ -413,6 +443,8 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
     }
   } else {
     // greedy: always open the expandable child with the largest surface area
+    float area[8];  // < 0: not expandable (becomes a leaf slot)
+    area[0] = 1.0f;
     while (n < 8) {
       int best = -1;
       float ba = 0.0f;
@@ -434,7 +466,21 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
       }
       n++;
     }
+    inner = 0u;
+    for (int k = 0; k < n; ++k)
+      if (area[k] >= 0.0f) inner |= 1u << k;
   }
+  return n;
+}
+
+BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
+  const uint2 work = p.queue_in[item];
+  const uint32_t n_int = p.n - 1;
+  uint32_t ch[8];
+  uint32_t inner_mask;
+  const int n = collapse_select(p, work.x, ch, inner_mask);
+  float area[8];  // < 0: not expandable (becomes a leaf slot)
+  for (int k = 0; k < 8; ++k) area[k] = (inner_mask >> k) & 1u ? 1.0f : -1.0f;
   // child boxes, node box
   f3 clo[8], chi[8];
   f3 nlo = F3(INFINITY), nhi = F3(-INFINITY);
@@ -546,5 +592,169 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
   if (work.y < p.node_cap) p.out_nodes[work.y] = out;
   if (item == 0) atomic_max(&p.g->levels, p.level + 1u);
 }
+
+#ifndef BRT_EMU
+// ---- warp-cooperative collapse (device only) ------------------------------------------------------------
+// collapse_body with the 32 lanes of a warp sharing ONE work item: a single thread spends ~50 us on an item (the children's
+// boxes, the 64 (child, slot) scores of the octant-ordered assignment, 48 quantisations with directed rounding and up to eight
+// dependent index -> vertex fetches for the triangle records, one after the other), and a build has one level-synchronous
+// step per tree level, so small builds (the per-frame TLAS, a re-built dynamic BLAS) and the top levels of large ones
+// were bound by that latency. Here lane k owns child k, then lane s owns slot s; the choice of the children
+// (collapse_select) is evaluated redundantly by all lanes. Same node as collapse_body produces for the same item.
+__device__ __forceinline__ float warp_min_f(float v) { return ordered_to_float(__reduce_min_sync(0xffffffffu, float_to_ordered(v))); }
+__device__ __forceinline__ float warp_max_f(float v) { return ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(v))); }
+
+__device__ __forceinline__ void collapse_warp(const CollapseParams& p, uint32_t item, unsigned lane) {
+  const unsigned FULL = 0xffffffffu;
+  const uint2 work = p.queue_in[item];
+  const uint32_t n_int = p.n - 1;
+  uint32_t ch[8];
+  uint32_t inner_mask;
+  const int n = collapse_select(p, work.x, ch, inner_mask);  // warp-uniform
+  // lane k < n: box of child k
+  uint32_t my_ch = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if ((int)lane == k) my_ch = ch[k];
+  f3 blo = F3(INFINITY), bhi = F3(-INFINITY);
+  if ((int)lane < n) {
+    const BNode cn = p.nodes[my_ch];
+    blo = xyz(cn.lo);
+    bhi = xyz(cn.hi);
+  }
+  const f3 nlo = F3(warp_min_f(blo.x), warp_min_f(blo.y), warp_min_f(blo.z));
+  const f3 nhi = F3(warp_max_f(bhi.x), warp_max_f(bhi.y), warp_max_f(bhi.z));
+  // octant-ordered slot assignment: lane L scores the pairs (child L >> 2, slots 2 (L & 3) and 2 (L & 3) + 1); every round takes the
+  // pair with the highest score, ties to the lowest (child, slot) — the order collapse_body scans them in
+  const f3 nc = (nlo + nhi) * 0.5f;
+  const int pk = (int)(lane >> 2);
+  const f3 off = F3(__shfl_sync(FULL, (blo.x + bhi.x) * 0.5f - nc.x, pk), __shfl_sync(FULL, (blo.y + bhi.y) * 0.5f - nc.y, pk),
+                    __shfl_sync(FULL, (blo.z + bhi.z) * 0.5f - nc.z, pk));
+  float score[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int sl = (int)(lane & 3u) * 2 + e;
+    score[e] = ((sl & 1) ? off.x : -off.x) + ((sl & 2) ? off.y : -off.y) + ((sl & 4) ? off.z : -off.z);
+  }
+  uint32_t child_done = 0, slot_used = 0;
+  int my_child = -1;  // lane s < 8: the child in slot s
+  for (int round = 0; round < n; ++round) {
+    float bs = -INFINITY;
+    int bi = 64;  // pair index = child * 8 + slot
+    if (pk < n && !((child_done >> pk) & 1u)) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int sl = (int)(lane & 3u) * 2 + e;
+        if (!((slot_used >> sl) & 1u) && score[e] > bs) { bs = score[e]; bi = pk * 8 + sl; }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const float os = __shfl_xor_sync(FULL, bs, d);
+      const int oi = __shfl_xor_sync(FULL, bi, d);
+      if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    int bk, bsl;
+    if (bi < 64) {
+      bk = bi >> 3;
+      bsl = bi & 7;
+    } else {  // NaN / infinite boxes: first free child, first free slot
+      bk = __ffs(~child_done & 0xffu) - 1;
+      bsl = __ffs(~slot_used & 0xffu) - 1;
+    }
+    child_done |= 1u << bk;
+    slot_used |= 1u << bsl;
+    if ((int)lane == bsl) my_child = bk;
+  }
+  // lane s < 8 owns slot s from here on
+  const bool owner = lane < 8u && my_child >= 0;
+  const int src = owner ? my_child : 0;
+  const f3 clo = F3(__shfl_sync(FULL, blo.x, src), __shfl_sync(FULL, blo.y, src), __shfl_sync(FULL, blo.z, src));
+  const f3 chi = F3(__shfl_sync(FULL, bhi.x, src), __shfl_sync(FULL, bhi.y, src), __shfl_sync(FULL, bhi.z, src));
+  const uint32_t cid = __shfl_sync(FULL, my_ch, src);
+  const bool is_inner = owner && ((inner_mask >> my_child) & 1u);
+  const bool is_leaf = owner && !is_inner;
+  const uint32_t cnt = is_leaf ? p.sub_count[cid] : 0u;
+  const uint32_t inner_slots = __ballot_sync(FULL, is_inner);
+  uint32_t n_inner = (uint32_t)__popc(inner_slots);
+  const uint32_t n_prims = __reduce_add_sync(FULL, cnt);
+  uint32_t prim_off = 0;  // primitives in the leaf slots below this one
+#pragma unroll
+  for (int s2 = 0; s2 < 8; ++s2) {
+    const uint32_t c2 = __shfl_sync(FULL, cnt, s2);
+    if ((int)lane > s2) prim_off += c2;
+  }
+  uint32_t child_base = 0, prim_base = 0, queue_base = 0, drop = 0;
+  if (lane == 0) {
+    if (n_inner) child_base = atomic_add(&p.g->node_count, n_inner);
+    if (n_prims) prim_base = atomic_add(&p.g->prim_count, n_prims);
+    if (n_inner) {
+      queue_base = atomic_add(&p.g->level_count[p.level + 1], n_inner);
+      if (child_base + n_inner > p.node_cap || queue_base + n_inner > p.queue_cap) {
+        p.g->overflow = 1u;
+        drop = 1u;  // drop the subtree rather than write out of bounds; the host reports the error
+      }
+    }
+  }
+  child_base = __shfl_sync(FULL, child_base, 0);
+  prim_base = __shfl_sync(FULL, prim_base, 0);
+  queue_base = __shfl_sync(FULL, queue_base, 0);
+  drop = __shfl_sync(FULL, drop, 0);
+  const bool keep_inner = is_inner && !drop;
+  const uint32_t imask = __ballot_sync(FULL, keep_inner) & 0xffu;
+  const uint32_t leafmask = __ballot_sync(FULL, is_leaf) & 0xffu;
+  // grid (warp-uniform), quantised bounds per slot
+  const uint32_t ex = grid_exponent(nlo.x, nhi.x), ey = grid_exponent(nlo.y, nhi.y), ez = grid_exponent(nlo.z, nhi.z);
+  const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+  uint32_t q[6] = {255u, 255u, 255u, 0u, 0u, 0u};  // lo xyz, hi xyz
+  if (keep_inner || is_leaf) {
+    q[0] = quant_lo(nlo.x, sx, clo.x); q[1] = quant_lo(nlo.y, sy, clo.y); q[2] = quant_lo(nlo.z, sz, clo.z);
+    q[3] = quant_hi(nlo.x, sx, chi.x); q[4] = quant_hi(nlo.y, sy, chi.y); q[5] = quant_hi(nlo.z, sz, chi.z);
+  }
+  if (keep_inner) {
+    const uint32_t inner_i = (uint32_t)__popc(imask & ((1u << lane) - 1u));
+    p.queue_out[queue_base + inner_i] = make_uint2(cid, child_base + inner_i);
+  }
+  if (is_leaf) {
+    // a leaf slot holds exactly one primitive (max_leaf == 1); the walk tolerates a larger subtree only to stay in bounds
+    uint32_t st[4];
+    int sp = 0;
+    st[sp++] = cid;
+    uint32_t w = 0;
+    while (sp) {
+      const uint32_t id = st[--sp];
+      const BNode bn = p.nodes[id];
+      if (id >= n_int) {
+        emit_prim(p, f2u(bn.lo.w), prim_base + prim_off + w);
+        w++;
+      } else {
+        st[sp++] = f2u(bn.hi.w);
+        st[sp++] = f2u(bn.lo.w);
+      }
+    }
+  }
+  // pack: word h (slots 4h .. 4h+3) of bound b
+  uint32_t words[12];
+#pragma unroll
+  for (int b = 0; b < 6; ++b)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      words[2 * b + h] = __reduce_or_sync(FULL, (lane < 8u && (int)(lane >> 2) == h) ? q[b] << (8u * (lane & 3u)) : 0u);
+  // byte x of iperm / lperm = inner / leaf mask with the two low bits of every slot index XORed with x (traverse.cuh)
+  const uint32_t pj = (lane & 7u) ^ (lane >> 3);
+  const uint32_t iperm = __ballot_sync(FULL, (imask >> pj) & 1u);
+  const uint32_t lperm = __ballot_sync(FULL, (leafmask >> pj) & 1u);
+  if (work.y < p.node_cap && lane < 5u) {
+    uint4 v;
+    if (lane == 0) v = make_uint4(f2u(nlo.x), f2u(nlo.y), f2u(nlo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
+    else if (lane == 1) v = make_uint4(child_base, prim_base, iperm, lperm);
+    else if (lane == 2) v = make_uint4(words[0], words[1], words[2], words[3]);    // lo x, lo y
+    else if (lane == 3) v = make_uint4(words[4], words[5], words[6], words[7]);    // lo z, hi x
+    else v = make_uint4(words[8], words[9], words[10], words[11]);                 // hi y, hi z
+    p.out_nodes[work.y].q[lane] = v;
+  }
+  if (item == 0 && lane == 0) atomic_max(&p.g->levels, p.level + 1u);
+}
+#endif
 
 }  // namespace brt

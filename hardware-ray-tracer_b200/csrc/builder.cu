@@ -21,7 +21,22 @@ BRT_KERNEL_1D(k_morton, MortonParams, morton_body)
 BRT_KERNEL_1D(k_hierarchy, HierarchyParams, hierarchy_body)
 BRT_KERNEL_1D(k_refit, RefitParams, refit_body)
 BRT_KERNEL_1D(k_wide_cost, WideCostParams, wide_cost_body)
+#ifdef BRT_EMU
 BRT_KERNEL_1D(k_collapse, CollapseParams, collapse_body)
+#else
+// One level of the collapse. Levels of up to BRT_COLLAPSE_WARP_MAX items (the top of every tree, all of a small one) are
+// latency-bound: one warp per item (collapse_warp); wide levels are throughput-bound: one thread per item (collapse_body).
+#define BRT_COLLAPSE_WARP_MAX 8192u
+__global__ void __launch_bounds__(64) k_collapse(const CollapseParams p) {
+  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (n <= BRT_COLLAPSE_WARP_MAX) {
+    for (uint32_t i = tid >> 5; i < n; i += nt >> 5) collapse_warp(p, i, threadIdx.x & 31u);
+  } else {
+    for (uint32_t i = tid; i < n; i += nt) collapse_body(p, i);
+  }
+}
+#endif
 BRT_KERNEL_1D(k_treelet, TreeletParams, treelet_body)
 
 struct InitGlobalsParams {
@@ -68,8 +83,7 @@ struct SmallBuildParams {
   uint32_t* keys_sorted;
   uint32_t* vals_sorted;
   HierarchyParams hier;
-  RefitParams refit;
-  WideCostParams wide;
+  RefitParams refit;  // also fills the cost table of the collapse
   CollapseParams collapse; // level / queues / count_ptr are set per level by the kernel
   uint2* queue[2];
   float4* mesh_bounds;     // may be null
@@ -113,12 +127,6 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
   for (uint32_t i = tid; i < n; i += nt) refit_body(p.refit, i);
   __threadfence();
   __syncthreads();
-  for (uint32_t i = tid; i < n; i += nt) p.wide.arrive[i] = 0u;
-  __threadfence();
-  __syncthreads();
-  for (uint32_t i = tid; i < n; i += nt) wide_cost_body(p.wide, i);
-  __threadfence();
-  __syncthreads();
   CollapseParams cp = p.collapse;
   for (uint32_t level = 0; level < 62; ++level) {
     const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&cp.g->level_count[level]);
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
     cp.level = level;
     cp.queue_in = p.queue[level & 1];
     cp.queue_out = p.queue[(level + 1) & 1];
-    for (uint32_t i = tid; i < count; i += nt) collapse_body(cp, i);
+    for (uint32_t i = tid >> 5; i < count; i += nt >> 5) collapse_warp(cp, i, tid & 31u);
     __threadfence();
     __syncthreads();
   }
@@ -180,8 +188,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     sp.vals_sorted = vals_[1].as<uint32_t>();
     sp.hier = HierarchyParams{n - 1, nullptr, n, sp.keys_sorted, nodes_.as<BNode>(), parent_.as<uint32_t>()};
     sp.refit = RefitParams{n, nullptr, sp.vals_sorted, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes_.as<BNode>(), parent_.as<uint32_t>(),
-                           arrive_.as<uint32_t>(), sub_count_.as<uint32_t>()};
-    sp.wide = WideCostParams{n, nullptr, nodes_.as<BNode>(), parent_.as<uint32_t>(), arrive_.as<uint32_t>(), wcost_.as<float>()};
+                           arrive_.as<uint32_t>(), sub_count_.as<uint32_t>(), nullptr, greedy_collapse_ ? nullptr : wcost_.as<float>()};
     CollapseParams& cp = sp.collapse;
     cp.n = n;
     cp.max_leaf = max_leaf;
@@ -232,41 +239,45 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
       BRT_LAUNCH_1D(k_hierarchy, p, grid_n, 256, stream);
       BRT_CHECK_LAUNCH();
     }
+    // The refit also leaves the SAH cost of the LBVH (statistic) and, when no treelet pass is going to change the topology, the
+    // cost table of the collapse: a fast build walks the tree bottom-up once.
+    const bool do_treelets = treelets && want_sah && n >= 2 * BRT_TREELET_LEAVES;
+    const bool want_wcost = n > 1 && !greedy_collapse_;
+    float* cost = treelet_.as<float>();
     {
-      RefitParams p{n, nullptr, vals, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes, parent, arrive_.as<uint32_t>(), sub_count};
+      RefitParams p{n, nullptr, vals, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes, parent, arrive_.as<uint32_t>(), sub_count,
+                    want_sah ? cost : nullptr, want_wcost && !do_treelets ? wcost_.as<float>() : nullptr};
       BRT_LAUNCH_1D(k_refit, p, grid_n, 256, stream);
       BRT_CHECK_LAUNCH();
     }
-    // SAH cost of the LBVH, then SAH treelet restructuring (triangle BLAS only)
-    const bool do_treelets = treelets && want_sah && n >= 2 * BRT_TREELET_LEAVES;
     if (want_sah) {
-      float* cost = treelet_.as<float>();
+      BRT_CUDA(cudaMemcpyAsync(&cost_before, cost, 4, cudaMemcpyDeviceToHost, stream));
+      BRT_CUDA(cudaMemcpyAsync(&root_before, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
+    }
+    // SAH treelet restructuring (first builds of a triangle BLAS), then the cost table of the collapse on the final topology
+    if (do_treelets) {
       const uint32_t grid_t = std::max(1u, std::min(div_up(n, 64u), (uint32_t)sm_count_ * 16u));
-      const int passes = do_treelets ? 3 : 0;
-      for (int pass = 0; pass <= passes; ++pass) {
+      (void)grid_t;
+      for (int pass = 1; pass <= 3; ++pass) {
         BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
-        TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, pass == 0 ? 0u : 1u};
+        TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, 1u};
   #ifdef BRT_EMU
         BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);
   #else
-        if (pass == 0) BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);  // cost only: one thread per leaf is enough
-        else k_treelet_warp<<<std::max(1u, std::min(div_up(n, 128u), (uint32_t)sm_count_ * 8u)), 128, 0, stream>>>(tp);
+        k_treelet_warp<<<std::max(1u, std::min(div_up(n, 128u), (uint32_t)sm_count_ * 8u)), 128, 0, stream>>>(tp);
   #endif
         BRT_CHECK_LAUNCH();
-        if (pass == 0) {
-          BRT_CUDA(cudaMemcpyAsync(&cost_before, cost, 4, cudaMemcpyDeviceToHost, stream));
-          BRT_CUDA(cudaMemcpyAsync(&root_before, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
-        }
       }
+      if (want_wcost) {
+        BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
+        WideCostParams p{n, nullptr, nodes, parent, arrive_.as<uint32_t>(), wcost_.as<float>()};
+        BRT_LAUNCH_1D(k_wide_cost, p, grid_n, 256, stream);
+        BRT_CHECK_LAUNCH();
+      }
+    }
+    if (want_sah) {
       BRT_CUDA(cudaMemcpyAsync(&cost_after, cost, 4, cudaMemcpyDeviceToHost, stream));
       BRT_CUDA(cudaMemcpyAsync(&root_after, nodes, sizeof(BNode), cudaMemcpyDeviceToHost, stream));
-    }
-    // cost table of the collapse (which binary nodes become wide nodes), on the final binary topology
-    if (n > 1) {
-      BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
-      WideCostParams p{n, nullptr, nodes, parent, arrive_.as<uint32_t>(), wcost_.as<float>()};
-      BRT_LAUNCH_1D(k_wide_cost, p, grid_n, 256, stream);
-      BRT_CHECK_LAUNCH();
     }
     // collapse, level by level; the per-level work count lives on the device
     const uint32_t node_cap = node_capacity(n);
@@ -298,7 +309,10 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
         uint64_t max_items = 1;
         for (uint32_t k = 0; k < level && max_items < queue_cap; ++k) max_items *= 8;
         max_items = std::min<uint64_t>(max_items, queue_cap);
-        const uint32_t grid = std::max(1u, std::min(div_up((uint32_t)max_items, 64u), (uint32_t)sm_count_ * 16u));
+        uint32_t grid = std::max(1u, std::min(div_up((uint32_t)max_items, 64u), (uint32_t)sm_count_ * 16u));
+#ifndef BRT_EMU
+        grid = std::max(grid, div_up((uint32_t)std::min<uint64_t>(max_items, BRT_COLLAPSE_WARP_MAX), 2u));  // two warps per block
+#endif
         BRT_LAUNCH_1D(k_collapse, cp, grid, 64, stream);
         BRT_CHECK_LAUNCH();
       }

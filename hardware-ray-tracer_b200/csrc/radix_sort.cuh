@@ -14,22 +14,31 @@
 namespace brt {
 
 #define BRT_SORT_THREADS 256
+// keys per thread: 16 for large inputs; 4 below BRT_SORT_SMALL_N keys, where the tiles of 4096 keys would occupy a handful of
+// SMs and every pass would be bound by the 16 dependent ranking rounds of its few blocks (the re-built dynamic BLAS of C4:
+// 20,480 keys were 5 blocks, 23 us per scatter)
 #define BRT_SORT_ITEMS 16
-#define BRT_SORT_TILE (BRT_SORT_THREADS * BRT_SORT_ITEMS)
+#define BRT_SORT_ITEMS_SMALL 4
+#define BRT_SORT_SMALL_N 262144u
+inline uint32_t radix_sort_items(uint32_t n) { return n <= BRT_SORT_SMALL_N ? BRT_SORT_ITEMS_SMALL : BRT_SORT_ITEMS; }
 
-inline uint32_t radix_sort_tiles(uint32_t n) { return n ? (n + BRT_SORT_TILE - 1) / BRT_SORT_TILE : 1; }
+inline uint32_t radix_sort_tiles(uint32_t n) {
+  const uint32_t tile = BRT_SORT_THREADS * radix_sort_items(n);
+  return n ? (n + tile - 1) / tile : 1;
+}
 // scratch: the digit-major histogram table, 256 x tiles counters
 inline size_t radix_sort_temp_bytes(uint32_t n) { return (size_t)radix_sort_tiles(n) * 256 * 4 + 16; }
 
 #ifndef BRT_EMU
+template <int ITEMS>
 __global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t dmask,
                                                                  uint32_t* __restrict__ hist, uint32_t tiles) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t base = blockIdx.x * BRT_SORT_TILE;
+  const uint32_t base = blockIdx.x * (BRT_SORT_THREADS * ITEMS);
 #pragma unroll
-  for (int k = 0; k < BRT_SORT_ITEMS; ++k) {
+  for (int k = 0; k < ITEMS; ++k) {
     const uint32_t i = base + k * BRT_SORT_THREADS + threadIdx.x;
     if (i < n) atomicAdd(&h[(keys[i] >> shift) & dmask], 1u);
   }
@@ -74,6 +83,7 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t* __restrict__ hist
   (void)carry;
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                                                                     int shift, uint32_t dmask, const uint32_t* __restrict__ hist, uint32_t tiles) {
@@ -83,10 +93,10 @@ __global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_scatter(const uint32
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const uint32_t warp_base = blockIdx.x * BRT_SORT_TILE + warp * (BRT_SORT_ITEMS * 32);
-  uint32_t key[BRT_SORT_ITEMS], val[BRT_SORT_ITEMS], rank[BRT_SORT_ITEMS];
+  const uint32_t warp_base = blockIdx.x * (BRT_SORT_THREADS * ITEMS) + warp * (ITEMS * 32);
+  uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
 #pragma unroll
-  for (int k = 0; k < BRT_SORT_ITEMS; ++k) {
+  for (int k = 0; k < ITEMS; ++k) {
     const uint32_t i = warp_base + k * 32 + lane;
     const bool valid = i < n;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_scatter(const uint32
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < BRT_SORT_ITEMS; ++k) {
+  for (int k = 0; k < ITEMS; ++k) {
     const uint32_t i = warp_base + k * 32 + lane;
     if (i < n) {
       const uint32_t pos = warp_count[warp][(key[k] >> shift) & dmask] + rank[k];
@@ -155,9 +165,15 @@ inline int radix_sort_pairs(cudaStream_t stream, uint32_t* keys0, uint32_t* keys
   int cur = 0;
   for (int shift = 0; shift < bits; shift += 8) {
     const uint32_t dmask = bits - shift >= 8 ? 0xffu : ((1u << (bits - shift)) - 1u);  // the last digit may be narrower
-    k_radix_hist<<<tiles, BRT_SORT_THREADS, 0, stream>>>(k[cur], n, shift, dmask, hist, tiles);
-    k_radix_scan<<<1, 1024, 0, stream>>>(hist, tiles * 256u);
-    k_radix_scatter<<<tiles, BRT_SORT_THREADS, 0, stream>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, shift, dmask, hist, tiles);
+    if (radix_sort_items(n) == BRT_SORT_ITEMS_SMALL) {
+      k_radix_hist<BRT_SORT_ITEMS_SMALL><<<tiles, BRT_SORT_THREADS, 0, stream>>>(k[cur], n, shift, dmask, hist, tiles);
+      k_radix_scan<<<1, 1024, 0, stream>>>(hist, tiles * 256u);
+      k_radix_scatter<BRT_SORT_ITEMS_SMALL><<<tiles, BRT_SORT_THREADS, 0, stream>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, shift, dmask, hist, tiles);
+    } else {
+      k_radix_hist<BRT_SORT_ITEMS><<<tiles, BRT_SORT_THREADS, 0, stream>>>(k[cur], n, shift, dmask, hist, tiles);
+      k_radix_scan<<<1, 1024, 0, stream>>>(hist, tiles * 256u);
+      k_radix_scatter<BRT_SORT_ITEMS><<<tiles, BRT_SORT_THREADS, 0, stream>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, shift, dmask, hist, tiles);
+    }
     BRT_CHECK_LAUNCH();
     cur ^= 1;
   }

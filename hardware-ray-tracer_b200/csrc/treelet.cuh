@@ -14,8 +14,7 @@
 namespace brt {
 
 #define BRT_TREELET_LEAVES 7
-#define BRT_SAH_CI 1.2f  // cost of visiting an internal node
-#define BRT_SAH_CT 1.0f  // cost of one primitive test
+// (BRT_SAH_CI / BRT_SAH_CT: build_kernels.cuh)
 
 struct TreeletParams {
   uint32_t count;  // n leaves

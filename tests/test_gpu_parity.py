@@ -123,7 +123,7 @@ def test_repeatable(pkg, make):
     assert np.array_equal(i1.view(np.uint32), i2.view(np.uint32))
 
 
-@pytest.mark.parametrize("n,bits", [(1, 30), (2, 30), (31, 8), (4096, 30), (4097, 30), (100003, 30), (1 << 20, 32), (333333, 16)])
+@pytest.mark.parametrize("n,bits", [(1, 30), (2, 30), (31, 8), (4096, 30), (4097, 30), (100003, 30), (262144, 30), (262145, 30), (1 << 20, 32), (333333, 16)])
 def test_radix_sort_pairs(pkg, make, n, bits):
     """The builder's own radix sort: sorted by the low `bits` bits, stable, a permutation of the input."""
     rng = np.random.default_rng(n)
