@@ -573,7 +573,8 @@ void refresh_scene_stats(brt_context* c) {
   c->stats.instances_visible = c->tlas_count;
 }
 
-void scene_build(brt_context* c) {
+// with_tlas = false: the caller builds the TLAS itself right afterwards (brt_smart_cull, once the visibility is known)
+void scene_build(brt_context* c, bool with_tlas = true) {
   cudaStream_t s = c->stream;
   cudaEvent_t e0 = c->ev_t[0], e1 = c->ev_t[1], e2 = c->ev_t[2];
   BRT_CUDA(cudaEventRecord(e0, s));
@@ -598,7 +599,7 @@ void scene_build(brt_context* c) {
   }
   BRT_CUDA(cudaEventRecord(e1, s));
   build_tables(c);
-  build_tlas(c);
+  if (with_tlas) build_tlas(c);
   BRT_CUDA(cudaEventRecord(e2, s));
   BRT_CUDA(cudaStreamSynchronize(s));
   float ms = 0.0f;
@@ -607,7 +608,7 @@ void scene_build(brt_context* c) {
   cudaEventElapsedTime(&ms, e1, e2);
   c->stats.ms_tlas_build = ms;
   c->stats.blas_built = rebuilt;
-  if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) throw LimitError("scene_build: BVH deeper than the traversal stack allows");
+  if (with_tlas && c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) throw LimitError("scene_build: BVH deeper than the traversal stack allows");
   c->built = true;
   refresh_scene_stats(c);
 }
@@ -1497,7 +1498,7 @@ int brt_smart_cull(brt_context* c, const brt_uniform* u, uint32_t width, uint32_
     BRT_CUDA(cudaSetDevice(c->device));
     bool dirty_mesh = false;
     for (const auto& m : c->meshes) dirty_mesh |= m->dirty;
-    if (dirty_mesh || !c->built) scene_build(c);
+    if (dirty_mesh || !c->built) scene_build(c, false);  // BLASes of updated meshes; the TLAS follows below, once
     if (c->tables_dirty) build_tables(c);
     cudaStream_t s = c->stream;
     const uint32_t n = (uint32_t)c->instances.size();

@@ -189,7 +189,7 @@ BRT_HD float box_area(f3 lo, f3 hi) {
   const f3 e = hi - lo;
   return 2.0f * ((e.x * e.y + e.y * e.z) + e.z * e.x);
 }
-BRT_HD void wide_cost_node(float* wcost, uint32_t par, uint32_t l, uint32_t r, uint32_t n_int, float area);
+BRT_HD void wide_cost_node(float* wcost, unsigned long long* wplan, uint32_t par, uint32_t l, uint32_t r, uint32_t n_int, float area);
 
 // ---- bottom-up refit ---------------------------------------------------------------------------------
 // One walk from every leaf towards the root (the second thread to arrive at a node owns it) fills the boxes and the
@@ -208,6 +208,7 @@ struct RefitParams {
   uint32_t* sub_count;  // 2n-1: primitives below each node
   float* cost;          // 2n-1 or null: SAH cost of every subtree
   float* wcost;         // n-1 rows or null: cost table of the collapse
+  unsigned long long* wplan;  // n-1: the choices that realise it (with wcost)
 };
 BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
   const uint32_t n_int = p.count - 1;
@@ -244,7 +245,7 @@ BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
         volatile float* c = p.cost;
         c[par] = BRT_SAH_CI * area + c[l] + c[r];
       }
-      if (p.wcost) wide_cost_node(p.wcost, par, l, r, n_int, area);
+      if (p.wcost) wide_cost_node(p.wcost, p.wplan, par, l, r, n_int, area);
     }
     cur = par;
   }
@@ -259,8 +260,9 @@ BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
 //   C(n, 1) = area(n) + D(n, 8)                      n becomes a wide node, its subtree is spread over 8 slots
 //   C(n, i) = min(D(n, i), C(n, i - 1))              n's subtree occupies at most i slots of an ancestor's wide node
 //   D(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k),      C(leaf, .) = 0
-// One bottom-up pass (arrival counters, as the refit) stores C(n, 1..7); the collapse re-derives the choices from the
-// stored costs. (Opening the child with the largest area until 8 slots are full — the previous rule — left the nodes
+// One bottom-up pass (arrival counters, as the refit) stores C(n, 1..7) and, per node, the choices that realise D(n, 2..8)
+// (how many slots each child really uses: 0 = it is a primitive, 1 = it becomes a wide node, b > 1 = it is opened further
+// over b slots), 6 bits per j in one 64-bit word; the collapse only follows them (collapse_select). (Opening the child with the largest area until 8 slots are full — the previous rule — left the nodes
 // half empty: 4.0 of 8 slots on the 1M-triangle scene, 9.3 node visits per primary ray against 7.1 now.)
 struct WideCostParams {
   uint32_t count;  // n leaves
@@ -269,6 +271,7 @@ struct WideCostParams {
   const uint32_t* parent;
   uint32_t* arrive;  // n-1, zeroed before the pass
   float* wcost;      // BRT_WCOST_STRIDE floats per internal node: C(n, 1..7)
+  unsigned long long* wplan;  // per internal node: slots used by the left / right child for j = 2..8
 };
 // D(n, j) for j = 2..8 from the children's tables (index i-1 holds C(., i)); returns the arg-min split in `split[j]`
 BRT_HD void wide_distribute(const float* L, const float* R, float* D, int* split) {
@@ -288,12 +291,27 @@ BRT_HD void wide_cost_load(const float* wcost, uint32_t id, uint32_t n_int, floa
   volatile const float* w = wcost + (size_t)id * BRT_WCOST_STRIDE;
   for (int k = 0; k < 7; ++k) out[k] = id < n_int ? w[k] : 0.0f;
 }
-// C(par, 1..7) from the finished tables of its children l, r
-BRT_HD void wide_cost_node(float* wcost, uint32_t par, uint32_t l, uint32_t r, uint32_t n_int, float area) {
+// slots a child really uses when it is offered b: none of its own if it is a primitive (0 = leaf slot), fewer if the extra
+// ones buy nothing (C(c, b) = C(c, b - 1)), 1 = it becomes a wide node
+BRT_HD int wide_effective(const float* T, bool leaf, int b) {
+  if (leaf) return 0;
+  if (b > 7) b = 7;
+  while (b > 1 && T[b - 1] == T[b - 2]) b--;
+  return b;
+}
+// C(par, 1..7) and the plan of par from the finished tables of its children l, r
+BRT_HD void wide_cost_node(float* wcost, unsigned long long* wplan, uint32_t par, uint32_t l, uint32_t r, uint32_t n_int, float area) {
   float L[7], R[7], D[9];
+  int split[9];
   wide_cost_load(wcost, l, n_int, L);
   wide_cost_load(wcost, r, n_int, R);
-  wide_distribute(L, R, D, nullptr);
+  wide_distribute(L, R, D, split);
+  unsigned long long plan = 0ull;
+  for (int j = 2; j <= 8; ++j) {
+    const unsigned bl = (unsigned)wide_effective(L, l >= n_int, split[j]), br = (unsigned)wide_effective(R, r >= n_int, j - split[j]);
+    plan |= (unsigned long long)(bl | (br << 3)) << (6 * (j - 2));
+  }
+  wplan[par] = plan;
   volatile float* w = wcost + (size_t)par * BRT_WCOST_STRIDE;
   float c = area + D[8];
   w[0] = c;
@@ -313,7 +331,7 @@ BRT_HD void wide_cost_body(const WideCostParams& p, uint32_t i) {
     fence();
     volatile const BNode* nd = p.nodes + par;
     const uint32_t l = f2u(nd->lo.w), r = f2u(nd->hi.w);
-    wide_cost_node(p.wcost, par, l, r, n_int, box_area(F3(nd->lo.x, nd->lo.y, nd->lo.z), F3(nd->hi.x, nd->hi.y, nd->hi.z)));
+    wide_cost_node(p.wcost, p.wplan, par, l, r, n_int, box_area(F3(nd->lo.x, nd->lo.y, nd->lo.z), F3(nd->hi.x, nd->hi.y, nd->hi.z)));
     cur = par;
   }
 }
@@ -328,6 +346,7 @@ struct CollapseParams {
   const BNode* nodes;
   const uint32_t* sub_count;
   const float* wcost;         // C(n, 1..7) of wide_cost_body; null: greedy largest-area opening
+  const unsigned long long* wplan;  // the choices behind wcost
   const uint2* queue_in;      // (binary node id, wide node index)
   uint2* queue_out;
   uint32_t queue_cap;
@@ -383,17 +402,6 @@ BRT_HD uint32_t quant_hi(float p, float s, float v) {
   return (uint32_t)q;
 }
 
-// plain (cacheable) loads of a finished cost table
-BRT_HD void wide_cost_fetch(const float* wcost, uint32_t id, uint32_t n_int, float* out) {
-  if (id < n_int) {
-    const float4 a = *reinterpret_cast<const float4*>(wcost + (size_t)id * BRT_WCOST_STRIDE);
-    const float4 b = *reinterpret_cast<const float4*>(wcost + (size_t)id * BRT_WCOST_STRIDE + 4);
-    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z;
-  } else {
-    for (int k = 0; k < 7; ++k) out[k] = 0.0f;
-  }
-}
-
 // Which binary nodes become the (up to 8) children of the wide node made from binary node `root`: ch[0..n), bit k of
 // `inner`: child k becomes a wide node itself (otherwise it is a leaf slot). Returns n.
 BRT_HD int collapse_select(const CollapseParams& p, uint32_t root, uint32_t* ch, uint32_t& inner) {
@@ -403,7 +411,7 @@ BRT_HD int collapse_select(const CollapseParams& p, uint32_t root, uint32_t* ch,
   inner = (root < n_int && p.sub_count[root] > p.max_leaf) ? 1u : 0u;
   if (!inner) return n;
   if (p.wcost) {
-    // follow the dynamic programme: spread the subtree over the 8 slots with the splits that realise D(root, 8)
+    // follow the dynamic programme's plan: spread the subtree over the 8 slots with the splits that realise D(root, 8)
     uint32_t st_id[8];
     int st_budget[8];
     int sp = 0;
@@ -417,19 +425,12 @@ BRT_HD int collapse_select(const CollapseParams& p, uint32_t root, uint32_t* ch,
       const uint32_t id = st_id[sp];
       const int j = st_budget[sp];
       const BNode nd = p.nodes[id];
+      const unsigned bits = (unsigned)(p.wplan[id] >> (6 * (j - 2))) & 63u;
       const uint32_t c2[2] = {f2u(nd.lo.w), f2u(nd.hi.w)};
-      float L[7], R[7], D[9];
-      int split[9];
-      wide_cost_fetch(p.wcost, c2[0], n_int, L);
-      wide_cost_fetch(p.wcost, c2[1], n_int, R);
-      wide_distribute(L, R, D, split);
-      const int budget[2] = {split[j], j - split[j]};
+      const int budget[2] = {(int)(bits & 7u), (int)(bits >> 3)};
       for (int s = 0; s < 2; ++s) {
         const uint32_t c = c2[s];
-        const float* T = s == 0 ? L : R;
-        int b = budget[s] < 7 ? budget[s] : 7;
-        if (c >= n_int) b = 0;                        // a primitive: leaf slot
-        else while (b > 1 && T[b - 1] == T[b - 2]) b--;  // C(c, b) = C(c, b - 1): the extra slot buys nothing
+        const int b = budget[s];  // 0: a primitive (leaf slot), 1: becomes a wide node, else: opened over b slots
         if (b <= 1) {
           ch[n] = c;
           if (b == 1) inner |= 1u << n;

@@ -76,7 +76,7 @@ BRT_KERNEL_1D(k_mesh_bounds, MeshBoundsParams, mesh_bounds_body)
 
 #ifndef BRT_EMU
 #define BRT_SMALL_BUILD_MAX 4096u
-#define BRT_SMALL_BUILD_THREADS 512
+#define BRT_SMALL_BUILD_THREADS 1024
 struct SmallBuildParams {
   uint32_t n;
   MortonParams morton;     // writes keys / vals (unsorted)
@@ -162,6 +162,7 @@ void Builder::ensure_scratch(uint32_t n) {
   sub_count_.ensure(2 * N * 4);
   treelet_.ensure(2 * N * 4 + 16);  // SAH cost per binary node
   wcost_.ensure(N * BRT_WCOST_STRIDE * 4);  // collapse cost table per internal binary node
+  wplan_.ensure(N * 8);                      // ... and the choices behind it
 }
 
 void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treelets, Node8* out_nodes, const float* d_vertices,
@@ -188,13 +189,15 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     sp.vals_sorted = vals_[1].as<uint32_t>();
     sp.hier = HierarchyParams{n - 1, nullptr, n, sp.keys_sorted, nodes_.as<BNode>(), parent_.as<uint32_t>()};
     sp.refit = RefitParams{n, nullptr, sp.vals_sorted, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes_.as<BNode>(), parent_.as<uint32_t>(),
-                           arrive_.as<uint32_t>(), sub_count_.as<uint32_t>(), nullptr, greedy_collapse_ ? nullptr : wcost_.as<float>()};
+                           arrive_.as<uint32_t>(), sub_count_.as<uint32_t>(), nullptr, greedy_collapse_ ? nullptr : wcost_.as<float>(),
+                           wplan_.as<unsigned long long>()};
     CollapseParams& cp = sp.collapse;
     cp.n = n;
     cp.max_leaf = max_leaf;
     cp.nodes = nodes_.as<BNode>();
     cp.sub_count = sub_count_.as<uint32_t>();
     cp.wcost = greedy_collapse_ ? nullptr : wcost_.as<float>();
+    cp.wplan = wplan_.as<unsigned long long>();
     cp.queue_cap = n / 2 + 8;
     cp.g = g;
     cp.out_nodes = out_nodes;
@@ -246,7 +249,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     float* cost = treelet_.as<float>();
     {
       RefitParams p{n, nullptr, vals, prim_lo_.as<float4>(), prim_hi_.as<float4>(), nodes, parent, arrive_.as<uint32_t>(), sub_count,
-                    want_sah ? cost : nullptr, want_wcost && !do_treelets ? wcost_.as<float>() : nullptr};
+                    want_sah ? cost : nullptr, want_wcost && !do_treelets ? wcost_.as<float>() : nullptr, wplan_.as<unsigned long long>()};
       BRT_LAUNCH_1D(k_refit, p, grid_n, 256, stream);
       BRT_CHECK_LAUNCH();
     }
@@ -270,7 +273,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
       }
       if (want_wcost) {
         BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
-        WideCostParams p{n, nullptr, nodes, parent, arrive_.as<uint32_t>(), wcost_.as<float>()};
+        WideCostParams p{n, nullptr, nodes, parent, arrive_.as<uint32_t>(), wcost_.as<float>(), wplan_.as<unsigned long long>()};
         BRT_LAUNCH_1D(k_wide_cost, p, grid_n, 256, stream);
         BRT_CHECK_LAUNCH();
       }
@@ -288,6 +291,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     cp.nodes = nodes;
     cp.sub_count = sub_count;
     cp.wcost = n > 1 && !greedy_collapse_ ? wcost_.as<float>() : nullptr;
+    cp.wplan = wplan_.as<unsigned long long>();
     cp.queue_cap = queue_cap;
     cp.g = g;
     cp.out_nodes = out_nodes;

@@ -35,7 +35,7 @@ class Builder {
   void ensure_scratch(uint32_t n);
   int sm_count_;
   bool greedy_collapse_;  // BRT_CFG_GREEDY_COLLAPSE
-  DevBuf globals_, prim_lo_, prim_hi_, keys_[2], vals_[2], sort_tmp_, nodes_, parent_, arrive_, sub_count_, queue_[2], treelet_, wcost_;
+  DevBuf globals_, prim_lo_, prim_hi_, keys_[2], vals_[2], sort_tmp_, nodes_, parent_, arrive_, sub_count_, queue_[2], treelet_, wcost_, wplan_;
   friend struct BuilderAccess;
 };
 

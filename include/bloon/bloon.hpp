@@ -258,9 +258,10 @@ class Scene {
   // (RT/Scene.cpp:135-138). Here it is the per-frame entry: rebuild the BLAS of updated meshes with the GPU LBVH
   // builder, and — when a threshold is given — run Smart Culling (README.md:15-18) and rebuild the TLAS.
   uint32_t prepareRendering(const Uniform* uniform = nullptr, Extent2D extent = {0, 0}, float thresholdPx2 = 0.0f, float hysteresis = 0.25f) {
-    build();
     uint32_t visible = (uint32_t)instances.size();
+    // brt_smart_cull rebuilds the BLAS of updated meshes itself and builds the TLAS once, after the visibility is known
     if (uniform) bloon::check(brt_smart_cull(ctx(), uniform, extent.width, extent.height, thresholdPx2, hysteresis, &visible), ctx(), "prepareRendering");
+    else build();
     return visible;
   }
   Core::Device& getDeviceRef() { return device; }

@@ -199,6 +199,16 @@ def smart_culling(pkg, orc_mod, make):
         assert r["id_agreement"] == 1.0 and r["bit_exact"], step
         assert a.get_stats().instances_visible == va
     assert len(seen) > 1 and n in seen  # culling removed something, threshold 0 restored everything
+    # the per-frame entry (Scene::prepareRendering): new vertices, then smart_cull alone rebuilds that BLAS and builds the TLAS once
+    v = pkg.scenes.animate_icosphere(scene.meshes[1][1], 5)
+    a.mesh_update_vertices(1, v)
+    b.mesh_update_vertices(1, v)
+    b.scene_build()
+    u = a.camera_uniform((0.0, 0.0, -26.0), (0, 0, 0), scene.fovy, w / h, frame=9, depth_max=1)
+    assert a.smart_cull(u, w, h, 40.0, 0.25) == b.smart_cull(u, w, h, 40.0, 0.25)
+    assert a.get_stats().blas_built == 1
+    r = compare_frames(pkg, a, b, u, w, h)
+    assert r["id_agreement"] == 1.0 and r["bit_exact"]
 
 
 def tiles_and_crop(pkg, orc_mod, make_ranked):

@@ -33,11 +33,9 @@ for name in ("c1", "c2", "c3", "c4", "c5"):
         cull, tlas, blas = [], [], []
         for f in range(4):
             ctx.mesh_update_vertices(1, pkg.scenes.animate_icosphere(base, f))
-            ctx.scene_build()
-            s1 = ctx.get_stats()
-            vis = ctx.smart_cull(u, w, h, 4.0, 0.25)
+            vis = ctx.smart_cull(u, w, h, 4.0, 0.25)  # one call: BLAS of the updated mesh, footprints, TLAS (Scene::prepareRendering)
             s2 = ctx.get_stats()
-            blas.append(s1.ms_blas_build); cull.append(s2.ms_cull); tlas.append(s2.ms_tlas_build)
+            blas.append(s2.ms_blas_build); cull.append(s2.ms_cull); tlas.append(s2.ms_tlas_build)
         extra = {"blas_rebuild_ms(20480 tris)": round(float(np.median(blas)), 3), "cull_ms(513 inst)": round(float(np.median(cull)), 3),
                  "tlas_ms": round(float(np.median(tlas)), 3), "visible": vis}
     ms, rays = [], 0
