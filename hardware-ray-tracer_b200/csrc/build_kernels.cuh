@@ -4,7 +4,7 @@
 //
 // Pipeline (one launch each, no host synchronisation in between):
 //   prim_bounds  : primitive AABBs (+ exact mesh bounds via warp-reduced atomics)
-//   morton       : 30-bit Morton code of the AABB centre inside the centroid... scene bounds
+//   morton       : 32-bit extent-adaptive Morton code of the AABB centre inside the scene bounds
 //   radix sort   : (code, primitive) pairs                                  (radix_sort.cuh)
 //   hierarchy    : Karras 2012 — one thread per internal node, binary radix tree over the sorted codes
 //   refit        : bottom-up AABBs + subtree primitive counts, atomic arrival counters
@@ -109,13 +109,7 @@ BRT_HD void inst_bounds_body(const InstBoundsParams& p, uint32_t i) {
 }
 
 // ---- Morton codes ------------------------------------------------------------------------------------
-BRT_HD uint32_t expand_bits10(uint32_t v) {  // 10 bits -> every third bit
-  v = (v * 0x00010001u) & 0xFF0000FFu;
-  v = (v * 0x00000101u) & 0x0F00F00Fu;
-  v = (v * 0x00000011u) & 0xC30C30C3u;
-  v = (v * 0x00000005u) & 0x49249249u;
-  return v;
-}
+#define BRT_MORTON_BITS 32
 struct MortonParams {
   uint32_t count;
   const uint32_t* count_ptr;
@@ -133,10 +127,25 @@ BRT_HD void morton_body(const MortonParams& p, uint32_t i) {
   const float fx = ext.x > 0.0f ? (c.x - blo.x) / ext.x : 0.0f;
   const float fy = ext.y > 0.0f ? (c.y - blo.y) / ext.y : 0.0f;
   const float fz = ext.z > 0.0f ? (c.z - blo.z) / ext.z : 0.0f;
-  const uint32_t x = (uint32_t)fminf(fmaxf(fx * 1024.0f, 0.0f), 1023.0f);
-  const uint32_t y = (uint32_t)fminf(fmaxf(fy * 1024.0f, 0.0f), 1023.0f);
-  const uint32_t z = (uint32_t)fminf(fmaxf(fz * 1024.0f, 0.0f), 1023.0f);
-  p.keys[i] = (expand_bits10(x) << 2) | (expand_bits10(y) << 1) | expand_bits10(z);
+  // 32 code bits, most significant first; each bit halves the axis whose cells are currently the longest (ties: x, y, z), so a
+  // flat or elongated mesh does not waste a third of its bits on an axis that has nothing to separate: a 16 x 1.6 x 16 terrain gets
+  // 12 + 8 + 12 bits instead of 10 + 10 + 10 (for a cube this is the usual x, y, z interleave)
+  const uint32_t qx = (uint32_t)fminf(fmaxf(fx * 65536.0f, 0.0f), 65535.0f);
+  const uint32_t qy = (uint32_t)fminf(fmaxf(fy * 65536.0f, 0.0f), 65535.0f);
+  const uint32_t qz = (uint32_t)fminf(fmaxf(fz * 65536.0f, 0.0f), 65535.0f);
+  float cx = ext.x, cy = ext.y, cz = ext.z;
+  int bx = 15, by = 15, bz = 15;  // next bit of each 16-bit coordinate
+  uint32_t code = 0;
+  for (int b = 0; b < BRT_MORTON_BITS; ++b) {
+    uint32_t bit;
+    if (cx >= cy && cx >= cz && bx >= 0) { bit = (qx >> bx) & 1u; bx--; cx *= 0.5f; }
+    else if (cy >= cz && by >= 0) { bit = (qy >> by) & 1u; by--; cy *= 0.5f; }
+    else if (bz >= 0) { bit = (qz >> bz) & 1u; bz--; cz *= 0.5f; }
+    else if (bx >= 0) { bit = (qx >> bx) & 1u; bx--; cx *= 0.5f; }
+    else { bit = (qy >> by) & 1u; by--; cy *= 0.5f; }
+    code = (code << 1) | bit;
+  }
+  p.keys[i] = code;
   p.vals[i] = i;
 }
 

@@ -228,7 +228,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     uint32_t* vals = vals_[0].as<uint32_t>();
     if (n > 1) {
       int out = radix_sort_pairs(stream, keys_[0].as<uint32_t>(), keys_[1].as<uint32_t>(), vals_[0].as<uint32_t>(), vals_[1].as<uint32_t>(), n,
-                                 30, sort_tmp_.ptr(), sort_tmp_.capacity(), sm_count_);
+                                 BRT_MORTON_BITS, sort_tmp_.ptr(), sort_tmp_.capacity(), sm_count_);
       keys = keys_[out].as<uint32_t>();
       vals = vals_[out].as<uint32_t>();
     }
