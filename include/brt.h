@@ -247,7 +247,10 @@ BRT_API int brt_instance_destroy(brt_context* ctx, uint32_t instance_id);
  * TLAS over the visible instances, material/light/instance tables. */
 BRT_API int brt_scene_build(brt_context* ctx);
 /* README.md:15-18 "Smart Culling": screen-space footprint per instance, hysteresis, then TLAS rebuild
- * over the survivors. threshold_px2 <= 0 makes every instance visible again. */
+ * over the survivors. threshold_px2 <= 0 makes every instance visible again.
+ * This is also the per-frame entry (Scene::prepareRendering, RT/Scene.cpp:135-138): meshes updated since the last build
+ * (brt_mesh_update_vertices) get their BLAS rebuilt here, and the TLAS is built once, after the visibility is known —
+ * no brt_scene_build is needed in between. */
 BRT_API int brt_smart_cull(brt_context* ctx, const brt_uniform* u, uint32_t width, uint32_t height,
                    float threshold_px2, float hysteresis, uint32_t* visible_count);
 /* copy the per-instance visibility flags (1 byte each) of the last brt_smart_cull to the host */
