@@ -176,7 +176,11 @@ def bench_config(scene, cfg, args):
     return {"workload": f"{args.config}: {scene.name} {scene.triangles()} triangles, {cfg['width']}x{cfg['height']}, {cfg['spp']} spp, "
                         f"depthMax {cfg['depth_max']} (primary + {cfg['depth_max'] - 1} bounces), shadow ray per light per hit",
             "render_flags": cfg["flags"], "lights": len(scene.lights), "instances": len(scene.instances),
-            "l2": "flushed between steps (256 MiB write)", "parallelism": f"image tiles 32x32 round-robin over {args.gpus} GPU(s), scene replicated"}
+            "l2": "flushed between steps (256 MiB write)", "parallelism": f"image tiles 32x32 round-robin over {args.gpus} GPU(s), scene replicated",
+            "workload_choice": ("default: c2 (1080p, configs[1]) at N = 1, c3 (4K, 16 spp, 4-bounce GI: the configuration BASELINE.json quotes "
+                                "for 1/2/4/8 GPUs, configs[2]) at N > 1; `--config c3 --gpus 1` gives the one-GPU time of the N > 1 workload "
+                                "(122.4 ms per frame, 3637 Mrays/s, profiles/r1c_configs.md)") if getattr(args, "config_defaulted", False)
+                               else f"--config {args.config}"}
 
 
 def run_product(args):
@@ -570,6 +574,7 @@ def main():
                          "(fused, default); nccl = all-gather of packed tiles + un-tile kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    args.config_defaulted = args.config is None
     if args.config is None:
         args.config = "c2" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c3"
     if args.impl == "reference":
