@@ -117,6 +117,51 @@ def grazing_and_axis_aligned_rays(pkg, orc_mod, make):
     assert np.array_equal(a.trace_rays(rays, False)[:, 3], b.trace_rays(rays, False)[:, 3])
 
 
+def degenerate_extents(pkg, orc_mod, make):
+    """Meshes whose bounds have no extent along one or two axes, or none at all (the extent-adaptive Morton code hands every bit to
+    the axes that have some), many coincident triangles (equal codes: the hierarchy falls back to the index), one long strip:
+    BVH == brute force for rays from all sides."""
+    S = pkg.scenes
+    rng = np.random.default_rng(41)
+
+    def grid(nx, nz, sx, sz, y=0.0):  # planar grid in the plane y = const
+        gx, gz = np.meshgrid(np.arange(nx + 1), np.arange(nz + 1), indexing="xy")
+        v = np.zeros(((nx + 1) * (nz + 1), 8), np.float32)
+        v[:, 0], v[:, 1], v[:, 2] = (gx.ravel() / max(nx, 1) - 0.5) * sx, y, (gz.ravel() / max(nz, 1) - 0.5) * sz
+        v[:, 4] = -1.0
+        i, j = np.meshgrid(np.arange(nx), np.arange(nz), indexing="xy")
+        v00 = (j * (nx + 1) + i).ravel()
+        idx = np.stack([v00, v00 + 1, v00 + nx + 2, v00, v00 + nx + 2, v00 + nx + 1], axis=1).astype(np.uint32).reshape(-1)
+        return v, idx
+
+    plane = grid(48, 48, 4.0, 4.0)                      # no extent in y
+    strip = grid(3000, 1, 300.0, 0.01)                  # 6000 triangles, 30000 : 1
+    tri = np.zeros((3, 8), np.float32)
+    tri[:, 0:3] = [(-0.5, 0.3, -0.5), (0.5, 0.3, -0.5), (0.0, 0.3, 0.5)]
+    tri[:, 4] = -1.0
+    same = (np.tile(tri, (200, 1)), np.arange(600, dtype=np.uint32))  # 200 coincident triangles: no extent between the centres
+    a, b = make(), orc_mod.Oracle(pkg, brute_force=True)
+    for api in (a, b):
+        mat = api.material_create((0.7, 0.7, 0.7))
+        api.light_create((0, -3, 0), (1, 1, 1), 5.0)
+        for k, (v, idx) in enumerate((plane, strip, same)):
+            api.instance_create(api.mesh_create(v, idx), mat, S.xform(translate=(0.0, 0.5 * k, 0.0)))
+        api.scene_build()
+    n = 6000
+    o = (rng.random((n, 3), dtype=np.float32) * 2 - 1) * np.array([3.0, 2.0, 3.0], np.float32)
+    o[: n // 4, 0] *= 50.0  # along the strip
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3], rays[:, 3], rays[:, 4:7], rays[:, 7] = o, 0.001, d, 1e32
+    ha, hb = a.trace_rays(rays, True), b.trace_rays(rays, True)
+    assert np.array_equal(ha, hb)
+    assert hb[:, 3].sum() > 500
+    assert np.array_equal(a.trace_rays(rays, False)[:, 3], b.trace_rays(rays, False)[:, 3])
+    st = a.get_stats()
+    assert st.total_triangles == 48 * 48 * 2 + 6000 + 200 and 0 < st.bvh_nodes < st.total_triangles
+
+
 def edge_cases(pkg, orc_mod, make):
     """Empty scene, empty mesh, single triangle, duplicate triangles (tie-break), tiny and huge coordinates."""
     S = pkg.scenes

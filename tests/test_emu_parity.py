@@ -33,6 +33,10 @@ def test_grazing_and_axis_aligned_rays(pkg, orc_mod, make):
     pc.grazing_and_axis_aligned_rays(pkg, orc_mod, make)
 
 
+def test_degenerate_extents(pkg, orc_mod, make):
+    pc.degenerate_extents(pkg, orc_mod, make)
+
+
 def test_edge_cases(pkg, orc_mod, make):
     pc.edge_cases(pkg, orc_mod, make)
 
