@@ -18,6 +18,21 @@ def test_exports_every_declared_symbol(pkg):
         assert hasattr(lib, name), name
 
 
+def test_flag_constants_match_header(pkg):
+    """BRT_CFG_* / BRT_RENDER_* values of the ctypes view against the #defines of include/brt.h."""
+    header = open(os.path.join(ROOT, "include", "brt.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+BRT_(CFG_[A-Z_]+|RENDER_[A-Z_]+)\s+(\d+)u\b", header)}
+    B = pkg.binding
+    cfg = {k: v for k, v in defs.items() if k.startswith("CFG_")}
+    assert set(cfg) >= {"CFG_COUNTERS", "CFG_NO_TREELET", "CFG_TREELET_ON_REBUILD", "CFG_NO_OVERLAP", "CFG_NO_GRAPH", "CFG_GREEDY_COLLAPSE"}
+    for name, value in cfg.items():
+        assert getattr(B, name) == value, name
+    for name in ("BOUNCE_REFLECT", "BOUNCE_REFRACT", "BOUNCE_DIFFUSE", "JITTER", "SKY", "GBUFFER", "LIGHT_BVH", "DENOISE"):
+        assert getattr(B, name) == defs["RENDER_" + name], name
+    values = sorted(cfg.values())
+    assert values == [1 << i for i in range(len(values))]  # distinct bits, none skipped
+
+
 def test_pod_layouts(pkg):
     B = pkg.binding
     assert C.sizeof(B.Vertex) == 32 and B.Vertex.normal.offset == 12 and B.Vertex.uv.offset == 24
