@@ -97,6 +97,7 @@ BRT_SYMBOLS = [
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
     "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_denoise_configure", "brt_render_frame_peers_async", "brt_get_light_bvh",
+    "brt_debug_get_blas",
 ]
 
 
@@ -155,7 +156,8 @@ class SceneApi:
             "denoise": (C.c_int, [vp, P(Uniform), P(DenoiseOpts), vp]),
             "get_light_bvh": (C.c_int, [vp, P(LightBvhNode), u32, P(u32)]),
         }
-        device_side = {  # entry points that take device pointers / streams
+        device_side = {  # entry points that take device pointers / streams, or that only the product has
+            "debug_get_blas": (C.c_int, [vp, u32, vp, u32, vp, u32, P(u32), P(u32)]),
             "set_stream": (C.c_int, [vp, vp]),
             "render_frame_tiles": (C.c_int, [vp, P(Uniform), P(RenderOpts), vp]),
             "tile_buffer_bytes": (C.c_size_t, [u32, u32, u32]),
@@ -320,6 +322,16 @@ class SceneApi:
         arr = (LightBvhNode * max(n.value, 1))()
         self._ck(self._f("get_light_bvh")(self.ctx, arr, n.value, C.byref(n)))
         return list(arr)[: n.value]
+
+    def debug_get_blas(self, mesh_id):
+        """(nodes, tris) of a mesh's BLAS: uint32 array [n_nodes, 20] (80-byte compressed 8-wide nodes) and float32 array [n_tris, 12]."""
+        nn, nt = u32(), u32()
+        self._ck(self._f("debug_get_blas")(self.ctx, mesh_id, None, 0, None, 0, C.byref(nn), C.byref(nt)))
+        nodes = np.zeros((nn.value, 20), np.uint32)
+        tris = np.zeros((nt.value, 12), np.float32)
+        self._ck(self._f("debug_get_blas")(self.ctx, mesh_id, nodes.ctypes.data_as(C.c_void_p), nn.value, tris.ctypes.data_as(C.c_void_p), nt.value,
+                                           C.byref(nn), C.byref(nt)))
+        return nodes, tris
 
     def get_aov(self, kind, width, height):
         if kind in (AOV_POSITION, AOV_NORMAL):

@@ -1850,6 +1850,27 @@ int brt_debug_sort_pairs(brt_context* c, uint32_t* keys, uint32_t* vals, uint32_
   });
 }
 
+int brt_debug_get_blas(brt_context* c, uint32_t mesh_id, void* nodes_out, uint32_t node_capacity, void* tris_out, uint32_t tri_capacity,
+                       uint32_t* n_nodes, uint32_t* n_tris) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!n_nodes || !n_tris) invalid("debug_get_blas: null");
+    if (mesh_id >= c->meshes.size()) invalid("debug_get_blas: no such mesh");
+    const MeshData& m = *c->meshes[mesh_id];
+    if (m.sphere) invalid("debug_get_blas: an analytic sphere has no BLAS");
+    if (m.dirty) bad_state("debug_get_blas: mesh not built (call brt_scene_build)");
+    wait_all_frames(c);
+    BRT_CUDA(cudaSetDevice(c->device));
+    const uint32_t nt = m.n_indices / 3;
+    *n_nodes = nt ? m.blas.n_nodes : 0u;
+    *n_tris = nt;
+    const size_t kn = std::min<size_t>(node_capacity, *n_nodes), kt = std::min<size_t>(tri_capacity, nt);
+    if (nodes_out && kn) BRT_CUDA(cudaMemcpyAsync(nodes_out, m.nodes.ptr(), kn * sizeof(Node8), cudaMemcpyDeviceToHost, c->stream));
+    if (tris_out && kt) BRT_CUDA(cudaMemcpyAsync(tris_out, m.tris.ptr(), kt * sizeof(TriRec), cudaMemcpyDeviceToHost, c->stream));
+    BRT_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 // 4x4 inverse in double (cofactor expansion along 2x2 minors), row-major in/out
 
 void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar, uint32_t frame,

@@ -348,6 +348,12 @@ BRT_API int brt_trace_rays(brt_context* ctx, const float* rays_host, uint32_t n_
 /* Sorts n (key, value) pairs in place (host arrays) by the low `bits` bits of the key with the LBVH builder's own GPU
  * radix sort; stable. Exposed so that the sort can be tested on its own. */
 BRT_API int brt_debug_sort_pairs(brt_context* ctx, uint32_t* keys_host, uint32_t* vals_host, uint32_t n, int bits);
+/* Copies the BLAS of a triangle mesh to the host: compressed 8-wide nodes (80 bytes each, layout in DESIGN.md §4) and triangle records
+ * (48 bytes each: three float4 = the vertices, primitive index in the bits of the first w), up to the given capacities; the counts
+ * come back in *n_nodes / *n_tris (null pointers: counts only). Used by the structural tests of the builder (every primitive once, every
+ * quantised child box contains what is below it); the driver's acceleration structures the reference uses are opaque. */
+BRT_API int brt_debug_get_blas(brt_context* ctx, uint32_t mesh_id, void* nodes_out, uint32_t node_capacity, void* tris_out, uint32_t tri_capacity,
+                               uint32_t* n_nodes, uint32_t* n_tris);
 
 /* ---- host helper: Core::Camera + the uniform block of RTApp::run ---------------------------- */
 /* Camera::setView/updateView (Graphics/Camera.cpp:19-24,71-95), Camera::setPerspectiveProjection

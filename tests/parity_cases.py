@@ -94,6 +94,104 @@ def collapse_rules(pkg, make):
     assert sa.nodes_visited_closest <= sb.nodes_visited_closest and sa.nodes_visited_occlusion <= sb.nodes_visited_occlusion
 
 
+def check_blas_structure(nodes, tris, n_tris_expected):
+    """Structural invariants of a compressed 8-wide BLAS: every node reachable exactly once, every primitive in exactly one
+    leaf slot, every slot's dequantised box contains everything below it, empty slots can never be hit, permuted masks consistent.
+    Returns (mean used slots per node, depth)."""
+    n_nodes = len(nodes)
+    assert len(tris) == n_tris_expected
+    prim_ids = tris[:, 3].copy().view(np.uint32)
+    assert np.array_equal(np.sort(prim_ids), np.arange(n_tris_expected, dtype=np.uint32))  # every primitive exactly once
+    verts = tris.reshape(-1, 3, 4)[:, :, :3].astype(np.float64)
+    tlo, thi = verts.min(axis=1), verts.max(axis=1)
+    p = nodes[:, 0:3].copy().view(np.float32).astype(np.float64)
+    ew = nodes[:, 3]
+    step = np.stack([((ew >> (8 * k)) & 0xFF).astype(np.uint32) << 23 for k in range(3)], axis=1).view(np.float32).astype(np.float64)
+    imask, child_base, prim_base, iperm, lperm = ew >> 24, nodes[:, 4], nodes[:, 5], nodes[:, 6], nodes[:, 7]
+    leafmask = lperm & 0xFF
+    assert np.array_equal(iperm & 0xFF, imask) and not (imask & leafmask).any()
+    for x in range(1, 4):  # byte x = the mask with the two low bits of every slot index XORed with x
+        for j in range(8):
+            assert np.array_equal((iperm >> (8 * x + j)) & 1, (imask >> (j ^ x)) & 1)
+            assert np.array_equal((lperm >> (8 * x + j)) & 1, (leafmask >> (j ^ x)) & 1)
+
+    def qbytes(w0, w1):  # two words -> [n, 8] bytes
+        return np.stack([(w0 >> (8 * k)) & 0xFF for k in range(4)] + [(w1 >> (8 * k)) & 0xFF for k in range(4)], axis=1).astype(np.float64)
+
+    qlo = np.stack([qbytes(nodes[:, 8], nodes[:, 9]), qbytes(nodes[:, 10], nodes[:, 11]), qbytes(nodes[:, 12], nodes[:, 13])], axis=2)  # [n, 8, 3]
+    qhi = np.stack([qbytes(nodes[:, 14], nodes[:, 15]), qbytes(nodes[:, 16], nodes[:, 17]), qbytes(nodes[:, 18], nodes[:, 19])], axis=2)
+    blo = p[:, None, :] + qlo * step[:, None, :]
+    bhi = p[:, None, :] + qhi * step[:, None, :]
+    used = imask | leafmask
+    for sl in range(8):
+        empty = ((used >> sl) & 1) == 0
+        assert (qlo[empty, sl, :] > qhi[empty, sl, :]).all()  # inverted box: no ray can hit it
+    # bottom-up over a depth-first order: actual bounds of every node's subtree
+    sub_lo, sub_hi = np.full((n_nodes, 3), np.inf), np.full((n_nodes, 3), -np.inf)
+    seen = np.zeros(n_nodes, bool)
+    seen_prim = np.zeros(n_tris_expected, bool)
+    order, stack, depth = [], [(0, 1)], 0
+    while stack:
+        i, d = stack.pop()
+        assert not seen[i]
+        seen[i] = True
+        depth = max(depth, d)
+        order.append(i)
+        k = 0
+        for sl in range(8):
+            if (imask[i] >> sl) & 1:
+                c = int(child_base[i]) + k
+                assert 0 < c < n_nodes
+                stack.append((c, d + 1))
+                k += 1
+    assert seen.all()
+    for i in reversed(order):
+        ki = kl = 0
+        for sl in range(8):
+            if (imask[i] >> sl) & 1:
+                c = int(child_base[i]) + ki
+                ki += 1
+                lo, hi = sub_lo[c], sub_hi[c]
+            elif (leafmask[i] >> sl) & 1:
+                r = int(prim_base[i]) + kl
+                kl += 1
+                assert r < n_tris_expected and not seen_prim[r]
+                seen_prim[r] = True
+                lo, hi = tlo[r], thi[r]
+            else:
+                continue
+            assert (blo[i, sl] <= lo).all() and (bhi[i, sl] >= hi).all(), (i, sl)  # the quantised box contains what is below the slot
+            sub_lo[i], sub_hi[i] = np.minimum(sub_lo[i], lo), np.maximum(sub_hi[i], hi)
+    assert seen_prim.all()
+    fill = float(np.mean([bin(int(u)).count("1") for u in used]))
+    return fill, depth
+
+
+def blas_structure(pkg, make):
+    """The builder's output, node by node (brt_debug_get_blas), for both collapse rules, a treelet and a plain LBVH build, a rebuild."""
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    fills = {}
+    for name, flags in (("optimal", 0), ("greedy", pkg.CFG_GREEDY_COLLAPSE), ("lbvh", pkg.CFG_NO_TREELET)):
+        a = make(flags)
+        scene.upload(a)
+        for mesh_id, (_, v, idx) in enumerate(scene.meshes):
+            nodes, tris = a.debug_get_blas(mesh_id)
+            fill, depth = check_blas_structure(nodes, tris, len(idx) // 3)
+            assert depth <= 24
+            fills[(name, mesh_id)] = (fill, len(nodes))
+        if name == "optimal":  # rebuild after a vertex update ("fast build" path: cost table filled by the refit walk)
+            v2 = scene.meshes[1][1].copy()
+            v2[:, 0:3] *= 1.25
+            a.mesh_update_vertices(1, v2)
+            a.scene_build()
+            nodes, tris = a.debug_get_blas(1)
+            check_blas_structure(nodes, tris, len(scene.meshes[1][2]) // 3)
+    for mesh_id in range(len(scene.meshes)):  # the area-optimal choice: fuller nodes, fewer of them
+        assert fills[("optimal", mesh_id)][0] > fills[("greedy", mesh_id)][0]
+        assert fills[("optimal", mesh_id)][1] < fills[("greedy", mesh_id)][1]
+    assert fills[("optimal", 0)][0] > 7.0 and fills[("optimal", 0)][1] < 0.5 * fills[("greedy", 0)][1]  # the 8192-triangle terrain
+
+
 def grazing_and_axis_aligned_rays(pkg, orc_mod, make):
     """Rays with zero direction components, rays inside box faces and along triangle edges of the Cornell box."""
     scene = pkg.scenes.make_scene("cornell", small=True)

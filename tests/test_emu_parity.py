@@ -29,6 +29,10 @@ def test_collapse_rules(pkg, make):
     pc.collapse_rules(pkg, make)
 
 
+def test_blas_structure(pkg, make):
+    pc.blas_structure(pkg, make)
+
+
 def test_grazing_and_axis_aligned_rays(pkg, orc_mod, make):
     pc.grazing_and_axis_aligned_rays(pkg, orc_mod, make)
 
