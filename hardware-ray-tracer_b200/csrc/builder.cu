@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(64) k_collapse(const CollapseParams p) {
   }
 }
 #endif
-BRT_KERNEL_1D(k_treelet, TreeletParams, treelet_body)
+#ifdef BRT_EMU
+BRT_KERNEL_1D(k_treelet, TreeletParams, treelet_body)  // the device runs the warp-cooperative k_treelet_warp (treelet.cuh)
+#endif
 
 struct InitGlobalsParams {
   uint32_t count;
@@ -259,13 +261,11 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     }
     // SAH treelet restructuring (first builds of a triangle BLAS), then the cost table of the collapse on the final topology
     if (do_treelets) {
-      const uint32_t grid_t = std::max(1u, std::min(div_up(n, 64u), (uint32_t)sm_count_ * 16u));
-      (void)grid_t;
       for (int pass = 1; pass <= 3; ++pass) {
         BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
         TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, 1u};
   #ifdef BRT_EMU
-        BRT_LAUNCH_1D(k_treelet, tp, grid_t, 64, stream);
+        BRT_LAUNCH_1D(k_treelet, tp, 1, 64, stream);
   #else
         k_treelet_warp<<<std::max(1u, std::min(div_up(n, 128u), (uint32_t)sm_count_ * 8u)), 128, 0, stream>>>(tp);
   #endif
