@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Runs the five BASELINE.json configurations on one GPU and prints the table BASELINE.md §3 asks for
-(ms/frame, Mrays/s, build / cull times for C4, the CPU oracle on a bounded crop, parity on that crop)."""
+"""TEST INFRASTRUCTURE (it uses the oracle as the checker, which only tests/ may do): runs the five BASELINE.json configurations on one
+GPU and prints the table BASELINE.md §3 asks for (ms/frame, Mrays/s, build / cull times for C4, the CPU oracle on a bounded crop, parity
+on that crop).   python tests/report_configs.py"""
 import importlib
 import json
 import os
