@@ -260,6 +260,25 @@ def degenerate_extents(pkg, orc_mod, make):
     assert st.total_triangles == 48 * 48 * 2 + 6000 + 200 and 0 < st.bvh_nodes < st.total_triangles
 
 
+def nonfinite_vertices(pkg, make):
+    """A NaN and an infinite coordinate in a mesh: the build terminates (no endless loop in the Morton code, the cost table, the
+    collapse or the quantisation), the frame renders, the finite triangles are still found."""
+    v, idx = pkg.scenes.heightfield(16)
+    v = v.copy()
+    v[7, 0] = np.nan
+    v[40, 1] = np.inf
+    a = make()
+    m = a.mesh_create(v, idx)
+    a.instance_create(m, a.material_create((0.5, 0.5, 0.5)), pkg.scenes.xform())
+    a.light_create((0, -3, 0), (1, 1, 1), 5.0)
+    a.scene_build()
+    st = a.get_stats()
+    assert st.total_triangles == len(idx) // 3 and 0 < st.bvh_nodes < st.total_triangles
+    u = a.camera_uniform((0, -3, -8), (-0.3, 0, 0), 1.0, 1.5, frame=0, depth_max=2)
+    a.render_frame(u, a.opts(48, 32, 1, pkg.BOUNCE_REFLECT | pkg.BOUNCE_REFRACT))
+    assert (a.get_aov(pkg.AOV_INST_ID, 48, 32) != pkg.AOV_MISS).mean() > 0.2
+
+
 def edge_cases(pkg, orc_mod, make):
     """Empty scene, empty mesh, single triangle, duplicate triangles (tie-break), tiny and huge coordinates."""
     S = pkg.scenes

@@ -41,6 +41,10 @@ def test_degenerate_extents(pkg, orc_mod, make):
     pc.degenerate_extents(pkg, orc_mod, make)
 
 
+def test_nonfinite_vertices(pkg, make):
+    pc.nonfinite_vertices(pkg, make)
+
+
 def test_edge_cases(pkg, orc_mod, make):
     pc.edge_cases(pkg, orc_mod, make)
 
