@@ -279,6 +279,23 @@ def nonfinite_vertices(pkg, make):
     assert (a.get_aov(pkg.AOV_INST_ID, 48, 32) != pkg.AOV_MISS).mean() > 0.2
 
 
+def bvh_quality_guard(pkg, make):
+    """Regression guard for what the frame time follows (profiles/r1c_large_scenes.md: -8 % node visits = -8 % traversal time): node visits
+    and primitive tests per ray and the SAH cost of the small terrain scene stay at what the extent-adaptive Morton code + treelets +
+    area-optimal collapse deliver (measured 5.85 / 7.73 node visits per closest-hit / occlusion ray, SAH 22.9, 1299 nodes)."""
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a = make(pkg.CFG_COUNTERS)
+    scene.upload(a)
+    u = scene.uniform(a, 192, 108, 0, 3)
+    a.render_frame(u, a.opts(192, 108, 1, pkg.BOUNCE_REFLECT | pkg.BOUNCE_REFRACT), want_image=False)
+    s = a.get_stats()
+    assert s.nodes_visited_closest / s.rays_closest < 6.1
+    assert s.nodes_visited_occlusion / s.rays_occlusion < 8.1
+    assert s.prims_tested_closest / s.rays_closest < 2.25
+    assert s.sah_cost < 24.0 and s.sah_cost <= s.sah_cost_lbvh
+    assert s.bvh_nodes < 1400
+
+
 def edge_cases(pkg, orc_mod, make):
     """Empty scene, empty mesh, single triangle, duplicate triangles (tie-break), tiny and huge coordinates."""
     S = pkg.scenes

@@ -45,6 +45,10 @@ def test_nonfinite_vertices(pkg, make):
     pc.nonfinite_vertices(pkg, make)
 
 
+def test_bvh_quality_guard(pkg, make):
+    pc.bvh_quality_guard(pkg, make)
+
+
 def test_edge_cases(pkg, orc_mod, make):
     pc.edge_cases(pkg, orc_mod, make)
 
