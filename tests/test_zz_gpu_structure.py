@@ -31,3 +31,12 @@ def test_blas_structure_131k_triangles(pkg, make):
         fill, depth = pc.check_blas_structure(nodes, tris, len(idx) // 3)
         assert fill > 6.5 and depth <= 12
         assert a.get_stats().bvh_nodes >= len(nodes)
+
+
+def test_degenerate_extents(pkg, orc_mod, make):
+    """Planar grid, 30000 : 1 strip, 200 coincident triangles (equal Morton codes) through the device's sort / hierarchy / collapse."""
+    pc.degenerate_extents(pkg, orc_mod, make)
+
+
+def test_nonfinite_vertices(pkg, make):
+    pc.nonfinite_vertices(pkg, make)
