@@ -36,7 +36,3 @@ def test_blas_structure_131k_triangles(pkg, make):
 def test_degenerate_extents(pkg, orc_mod, make):
     """Planar grid, 30000 : 1 strip, 200 coincident triangles (equal Morton codes) through the device's sort / hierarchy / collapse."""
     pc.degenerate_extents(pkg, orc_mod, make)
-
-
-def test_nonfinite_vertices(pkg, make):
-    pc.nonfinite_vertices(pkg, make)
