@@ -603,7 +603,7 @@ BRT_HD void collapse_body(const CollapseParams& p, uint32_t item) {
   if (item == 0) atomic_max(&p.g->levels, p.level + 1u);
 }
 
-#ifndef BRT_EMU
+#if !defined(BRT_EMU) || defined(BRT_EMU_WARP)  // (BRT_EMU_WARP: the test-only lock-step warp of tests/emu/warp_emu.h)
 // ---- warp-cooperative collapse (device only) ------------------------------------------------------------
 // collapse_body with the 32 lanes of a warp sharing ONE work item: a single thread spends ~50 us on an item (the children's
 // boxes, the 64 (child, slot) scores of the octant-ordered assignment, 48 quantisations with directed rounding and up to eight

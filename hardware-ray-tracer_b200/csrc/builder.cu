@@ -2,6 +2,8 @@
 #include "builder.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "build_kernels.cuh"
@@ -21,7 +23,48 @@ BRT_KERNEL_1D(k_morton, MortonParams, morton_body)
 BRT_KERNEL_1D(k_hierarchy, HierarchyParams, hierarchy_body)
 BRT_KERNEL_1D(k_refit, RefitParams, refit_body)
 BRT_KERNEL_1D(k_wide_cost, WideCostParams, wide_cost_body)
-#ifdef BRT_EMU
+#if defined(BRT_EMU) && defined(BRT_EMU_WARP)
+// Host emulation, test only: every item is collapsed by the scalar collapse_body and then again — with the builder's counters put
+// back — by the device's warp-cooperative collapse_warp on 32 lock-stepped host threads (tests/emu/warp_emu.h); the node, the queue
+// entries and the primitive records the two wrote are compared byte for byte. brt_emu_warp_collapse_stats reports the totals.
+static unsigned long long g_warp_items = 0, g_warp_mismatches = 0;
+extern "C" __attribute__((visibility("default"))) void brt_emu_warp_collapse_stats(unsigned long long* items, unsigned long long* mismatches) {
+  *items = g_warp_items;
+  *mismatches = g_warp_mismatches;
+}
+static void k_collapse(const CollapseParams p) {
+  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
+  const bool check = getenv("BRT_EMU_WARP_CHECK") != nullptr;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!check) {
+      collapse_body(p, i);
+      continue;
+    }
+    const BuildGlobals before = *p.g;
+    collapse_body(p, i);
+    const BuildGlobals after = *p.g;
+    const uint2 work = p.queue_in[i];
+    const uint32_t q0 = before.level_count[p.level + 1], q1 = after.level_count[p.level + 1];
+    const uint32_t r0 = before.prim_count, r1 = after.prim_count;
+    const size_t rec = p.out_tris ? sizeof(TriRec) : sizeof(InstRec);
+    char* recs = p.out_tris ? reinterpret_cast<char*>(p.out_tris) : reinterpret_cast<char*>(p.out_inst);
+    const Node8 node_a = p.out_nodes[work.y];
+    std::vector<uint2> queue_a(p.queue_out + q0, p.queue_out + q1);
+    std::vector<char> recs_a(recs + r0 * rec, recs + r1 * rec);
+    memset(&p.out_nodes[work.y], 0xcd, sizeof(Node8));
+    if (q1 > q0) memset(p.queue_out + q0, 0xcd, (q1 - q0) * sizeof(uint2));
+    if (r1 > r0) memset(recs + r0 * rec, 0xcd, (r1 - r0) * rec);
+    *p.g = before;
+    brt_warp_emu::run_warp([&](unsigned lane) { collapse_warp(p, i, lane); });
+    const BuildGlobals redo = *p.g;
+    bool same = memcmp(&redo, &after, sizeof(BuildGlobals)) == 0 && memcmp(&p.out_nodes[work.y], &node_a, sizeof(Node8)) == 0;
+    same = same && (q1 == q0 || memcmp(p.queue_out + q0, queue_a.data(), (q1 - q0) * sizeof(uint2)) == 0);
+    same = same && (r1 == r0 || memcmp(recs + r0 * rec, recs_a.data(), (r1 - r0) * rec) == 0);
+    g_warp_items++;
+    if (!same) g_warp_mismatches++;
+  }
+}
+#elif defined(BRT_EMU)
 BRT_KERNEL_1D(k_collapse, CollapseParams, collapse_body)
 #else
 // One level of the collapse. Levels of up to BRT_COLLAPSE_WARP_MAX items (the top of every tree, all of a small one) are

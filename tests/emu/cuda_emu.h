@@ -9,6 +9,9 @@
 #include <string.h>
 
 #define __align__(n) alignas(n)
+#ifdef BRT_EMU_WARP
+#include "warp_emu.h"  // lock-step stand-in for the warp intrinsics of collapse_warp
+#endif
 
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) float2 { float x, y; };

@@ -108,3 +108,37 @@ def test_counters_flag(pkg, orc_mod, make):
     assert st.nodes_visited_closest > st.rays_closest > 0 and st.prims_tested_closest > 0
     assert st.nodes_visited_occlusion > 0 and st.total_triangles == scene.triangles()
     assert st.bvh_nodes > 0 and st.bvh_bytes > st.total_triangles
+
+
+def test_warp_collapse_equals_scalar(pkg, emu_lib, monkeypatch):
+    """The device's warp-cooperative collapse (collapse_warp, build_kernels.cuh) on 32 lock-stepped host threads (tests/emu/warp_emu.h)
+    against the scalar collapse_body, item by item while real BVHs are built: same node bytes, same queue entries, same primitive
+    records, same allocation counters — for both collapse rules, triangle BLASes and an instance TLAS."""
+    import ctypes as C
+    import numpy as np
+
+    def stats():
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        emu_lib.brt_emu_warp_collapse_stats(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    monkeypatch.setenv("BRT_EMU_WARP_CHECK", "1")
+    items0, bad0 = stats()
+    S = pkg.scenes
+    hv, hi = S.heightfield(6)
+    sv, si = S.icosphere(1)
+    for flags in (0, pkg.CFG_GREEDY_COLLAPSE):
+        a = pkg.binding.SceneApi(emu_lib, "brt_", 0, 0, 1, flags)
+        mat = a.material_create((0.6, 0.6, 0.6))
+        terrain, ball = a.mesh_create(hv, hi), a.mesh_create(sv, si)
+        a.instance_create(terrain, mat, S.xform())
+        rng = np.random.default_rng(3)
+        for k in range(19):  # TLAS of 20 instances + a sphere
+            px, py, pz = (rng.random(3) * 2 - 1) * (6.0, 1.0, 6.0)
+            a.instance_create(ball, mat, S.xform((0.3, 0.3, 0.3), (px, py - 1.5, pz)))
+        a.instance_create(a.sphere_create((0.0, -2.0, 0.0), 0.5), mat, S.xform())
+        a.scene_build()
+        a.close()
+    items, bad = stats()
+    assert items - items0 > 60
+    assert bad == bad0 == 0
