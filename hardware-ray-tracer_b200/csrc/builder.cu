@@ -2,6 +2,7 @@
 #include "builder.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -31,6 +32,48 @@ static unsigned long long g_warp_items = 0, g_warp_mismatches = 0;
 extern "C" __attribute__((visibility("default"))) void brt_emu_warp_collapse_stats(unsigned long long* items, unsigned long long* mismatches) {
   *items = g_warp_items;
   *mismatches = g_warp_mismatches;
+}
+// Same idea for the treelet passes: the device's k_treelet_warp runs on a copy of the binary tree (warps one after the other, 32
+// lock-stepped host threads each); its result must be a valid tree (parents, boxes, counts and costs consistent, every leaf once) whose
+// SAH cost is close to the scalar passes' (ties between equally good treelet topologies are broken differently, so the trees — and
+// with them the later treelets — can differ: the largest relative deviation is reported).
+static unsigned long long g_treelet_checks = 0, g_treelet_bad = 0;
+static float g_treelet_max_dev = 0.0f;
+extern "C" __attribute__((visibility("default"))) void brt_emu_warp_treelet_stats(unsigned long long* checks, unsigned long long* invalid,
+                                                                                  float* max_cost_deviation) {
+  *checks = g_treelet_checks;
+  *invalid = g_treelet_bad;
+  *max_cost_deviation = g_treelet_max_dev;
+}
+static bool emu_valid_binary_tree(const std::vector<BNode>& nodes, const std::vector<uint32_t>& parent, const std::vector<uint32_t>& sub_count,
+                                  const std::vector<float>& cost, uint32_t n) {
+  const uint32_t n_int = n - 1;
+  std::vector<uint8_t> seen(2 * n - 1, 0);
+  std::vector<uint32_t> stack{0u};
+  uint32_t leaves = 0;
+  if (parent[0] != BRT_MISS) return false;
+  while (!stack.empty()) {
+    const uint32_t id = stack.back();
+    stack.pop_back();
+    if (id >= 2 * n - 1 || seen[id]) return false;
+    seen[id] = 1;
+    if (id >= n_int) {
+      leaves++;
+      continue;
+    }
+    const uint32_t c[2] = {f2u(nodes[id].lo.w), f2u(nodes[id].hi.w)};
+    if (c[0] >= 2 * n - 1 || c[1] >= 2 * n - 1 || parent[c[0]] != id || parent[c[1]] != id) return false;
+    const BNode &a = nodes[c[0]], &b = nodes[c[1]], &m = nodes[id];
+    if (m.lo.x != fminf(a.lo.x, b.lo.x) || m.lo.y != fminf(a.lo.y, b.lo.y) || m.lo.z != fminf(a.lo.z, b.lo.z)) return false;
+    if (m.hi.x != fmaxf(a.hi.x, b.hi.x) || m.hi.y != fmaxf(a.hi.y, b.hi.y) || m.hi.z != fmaxf(a.hi.z, b.hi.z)) return false;
+    if (sub_count[id] != sub_count[c[0]] + sub_count[c[1]]) return false;
+    const float lo[3] = {m.lo.x, m.lo.y, m.lo.z}, hi[3] = {m.hi.x, m.hi.y, m.hi.z};
+    const float want = BRT_SAH_CI * area_of(lo, hi) + cost[c[0]] + cost[c[1]];
+    if (fabsf(cost[id] - want) > 1e-4f * fabsf(want)) return false;
+    stack.push_back(c[0]);
+    stack.push_back(c[1]);
+  }
+  return leaves == n;
 }
 static void k_collapse(const CollapseParams p) {
   const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
@@ -304,6 +347,18 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     }
     // SAH treelet restructuring (first builds of a triangle BLAS), then the cost table of the collapse on the final topology
     if (do_treelets) {
+#if defined(BRT_EMU) && defined(BRT_EMU_WARP)
+      std::vector<BNode> w_nodes;
+      std::vector<uint32_t> w_parent, w_sub, w_arrive;
+      std::vector<float> w_cost;
+      const bool warp_check = getenv("BRT_EMU_WARP_CHECK") != nullptr;
+      if (warp_check) {
+        w_nodes.assign(nodes, nodes + (2 * n - 1));
+        w_parent.assign(parent, parent + 2 * n);
+        w_sub.assign(sub_count, sub_count + 2 * n);
+        w_cost.assign(cost, cost + 2 * n);
+      }
+#endif
       for (int pass = 1; pass <= 3; ++pass) {
         BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
         TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, 1u};
@@ -314,6 +369,19 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
   #endif
         BRT_CHECK_LAUNCH();
       }
+#if defined(BRT_EMU) && defined(BRT_EMU_WARP)
+      if (warp_check) {
+        for (int pass = 1; pass <= 3; ++pass) {
+          w_arrive.assign(n, 0u);
+          const TreeletParams tp{n, nullptr, w_nodes.data(), w_parent.data(), w_sub.data(), w_arrive.data(), w_cost.data(), 1u};
+          brt_warp_emu::run_kernel_warps(std::max(1u, div_up(n, 128u)), 128u, [&] { k_treelet_warp(tp); });
+        }
+        const float cs = cost[0], cw = w_cost[0];
+        g_treelet_checks++;
+        g_treelet_max_dev = std::max(g_treelet_max_dev, fabsf(cw - cs) / std::max(fabsf(cs), 1e-30f));
+        if (!emu_valid_binary_tree(w_nodes, w_parent, w_sub, w_cost, n) || !(cw == cw)) g_treelet_bad++;
+      }
+#endif
       if (want_wcost) {
         BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
         WideCostParams p{n, nullptr, nodes, parent, arrive_.as<uint32_t>(), wcost_.as<float>(), wplan_.as<unsigned long long>()};

@@ -185,7 +185,7 @@ BRT_HD void treelet_body(const TreeletParams& p, uint32_t i) {
 }
 
 
-#ifndef BRT_EMU
+#if !defined(BRT_EMU) || defined(BRT_EMU_WARP)  // (BRT_EMU_WARP: the test-only lock-step warp of tests/emu/warp_emu.h)
 // ---- warp-cooperative version (device only) ------------------------------------------------------------------
 // Same algorithm, but the 32 lanes of a warp share the dynamic programme of ONE treelet at a time (areas of the
 // 127 subsets, then optimal costs by subset size with the partitions of the large subsets spread over the lanes).

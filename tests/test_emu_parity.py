@@ -110,7 +110,7 @@ def test_counters_flag(pkg, orc_mod, make):
     assert st.bvh_nodes > 0 and st.bvh_bytes > st.total_triangles
 
 
-def test_warp_collapse_equals_scalar(pkg, emu_lib, monkeypatch):
+def test_warp_kernels_equal_scalar(pkg, emu_lib, monkeypatch):
     """The device's warp-cooperative collapse (collapse_warp, build_kernels.cuh) on 32 lock-stepped host threads (tests/emu/warp_emu.h)
     against the scalar collapse_body, item by item while real BVHs are built: same node bytes, same queue entries, same primitive
     records, same allocation counters — for both collapse rules, triangle BLASes and an instance TLAS."""
@@ -142,3 +142,9 @@ def test_warp_collapse_equals_scalar(pkg, emu_lib, monkeypatch):
     items, bad = stats()
     assert items - items0 > 60
     assert bad == bad0 == 0
+    # ... and the device's warp-cooperative treelet kernel (k_treelet_warp) on a copy of every binary tree that gets treelet passes:
+    # a valid tree (parents, boxes, counts, costs consistent, every leaf once) with about the SAH cost of the scalar passes
+    checks, invalid, dev = C.c_ulonglong(), C.c_ulonglong(), C.c_float()
+    emu_lib.brt_emu_warp_treelet_stats(C.byref(checks), C.byref(invalid), C.byref(dev))
+    assert checks.value >= 4 and invalid.value == 0
+    assert dev.value < 0.05  # equal on the terrain; the icosphere's many ties let the two versions settle on slightly different trees
