@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Traversal outside the L2: the C2 frame (1920x1080, primary + 2 bounces, 3 lights) on terrains of 8.9 M and 34 M unique
-triangles, whose node and triangle records (0.5 / 1.9 GB) do not fit the 126 MB L2 — the regime where the traversal roofline of
-SURVEY.md §8(d) is the HBM and not the instruction issue of the cache-resident 1M-triangle scene.
+triangles, whose node and triangle records (0.5 / 2.0 GB) do not fit the 126 MB L2 — the regime where SURVEY.md §8(d) expects the
+traversal to be bound by HBM. (Measured, profiles/r1c_large_scenes.md: it is not — the rays of a frame share enough of the tree that
+DRAM runs at 9-12 % of its peak and the kernels stay bound by instruction issue; the frame costs 25-40 % more than on the 1M scene.)
 
   python tools/bench_large.py [--n 2048 4096] [--frames 5]
 
