@@ -10,7 +10,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <fstream>
+#include <map>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -30,6 +32,226 @@ inline void check(int status, brt_context* ctx, const char* what) {
   if (status != BRT_OK) throw std::runtime_error(std::string(what) + ": " + brt_last_error(ctx));
 }
 }  // namespace bloon
+
+// ---- OBJ ingestion: what Scene::loadModel (RT/Scene.cpp:29-74) does with tinyobjloader 1.0.6 (libs/tinyobj/tiny_obj_loader.h) ----
+// Host-only (no GPU needed). The behaviour below is tinyobj 1.0.6's published behaviour, restated: LF / CR / CRLF line ends; `v`,
+// `vn`, `vt`, `f`, `g`, `o`, `usemtl`, `mtllib` records (everything else ignored); missing numbers default to 0; its own decimal
+// parser (digits accumulated in double, value = mantissa x 5^e x 2^e, then narrowed to float — not correctly rounded, and results
+// must match it bit for bit); 1-based, 0 and negative (relative) indices; polygons fan-triangulated; faces collected per shape, a
+// `usemtl` that changes the material moves the pending faces into the current shape, `g` / `o` close the shape — and drop it when
+// no face followed the last material change (a quirk of that version, kept); material names come from the `mtllib` files, looked
+// up relative to the working directory as the reference's call (no base directory) does. tests/test_ref_pin.py compares the
+// result with the reference's own loadModel + tinyobj (oracle/_ref/libref_obj.so) on fuzzed files, byte for byte.
+namespace bloon { namespace obj {
+
+struct Mesh {
+  std::vector<brt_vertex> vertices;
+  std::vector<uint32_t> indices;
+};
+struct Corner { int v, vt, vn; };  // resolved zero-based indices, -1 = absent
+
+inline bool isSpace(char c) { return c == ' ' || c == '\t'; }
+inline bool isDigit(char c) { return (unsigned)(c - '0') < 10u; }
+inline bool isLineEnd(char c) { return c == '\r' || c == '\n' || c == '\0'; }
+
+// One line without its terminator; accepts "\n", "\r\n" and a lone "\r". False once the stream is exhausted.
+inline bool getLine(std::istream& in, std::string& t) {
+  t.clear();
+  std::streambuf* sb = in.rdbuf();
+  if (sb->sgetc() == std::char_traits<char>::eof()) return false;
+  for (;;) {
+    const int c = sb->sbumpc();
+    if (c == '\n' || c == std::char_traits<char>::eof()) return true;
+    if (c == '\r') { if (sb->sgetc() == '\n') sb->sbumpc(); return true; }
+    t += (char)c;
+  }
+}
+
+// [sign] digits ["." digits] [("e"|"E") [sign] digits]; greedy; false on a malformed number (the caller then keeps its default).
+inline bool parseDouble(const char* s, const char* end, double* result) {
+  if (s >= end) return false;
+  double mantissa = 0.0;
+  int exponent = 0, read = 0;
+  char sign = '+', expSign = '+';
+  const char* c = s;
+  if (*c == '+' || *c == '-') sign = *c++;
+  else if (!isDigit(*c)) return false;
+  while (c != end && isDigit(*c)) { mantissa *= 10; mantissa += (int)(*c - '0'); ++c; ++read; }
+  if (read == 0) return false;
+  bool more = c != end;
+  if (more && *c == '.') {
+    static const double lut[] = {1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001};
+    ++c;
+    read = 1;
+    while (c != end && isDigit(*c)) {
+      mantissa += (int)(*c - '0') * (read < 8 ? lut[read] : std::pow(10.0, -read));
+      ++read; ++c;
+    }
+    more = c != end;
+  } else if (more && !(*c == 'e' || *c == 'E')) {
+    more = false;  // trailing garbage ends the number
+  }
+  if (more && (*c == 'e' || *c == 'E')) {
+    ++c;
+    if (c != end && (*c == '+' || *c == '-')) expSign = *c++;
+    else if (!isDigit(*c)) return false;  // "1e" alone is malformed
+    read = 0;
+    while (c != end && isDigit(*c)) { exponent *= 10; exponent += (int)(*c - '0'); ++c; ++read; }
+    if (expSign == '-') exponent = -exponent;
+    if (read == 0) return false;
+  }
+  *result = (sign == '+' ? 1 : -1) * (exponent ? std::ldexp(mantissa * std::pow(5.0, exponent), exponent) : mantissa);
+  return true;
+}
+
+inline float parseReal(const char** tok, double dflt = 0.0) {
+  *tok += std::strspn(*tok, " \t");
+  const char* end = *tok + std::strcspn(*tok, " \t\r");
+  double v = dflt;
+  parseDouble(*tok, end, &v);
+  *tok = end;
+  return (float)v;
+}
+
+inline int fixIndex(int idx, int n) { return idx > 0 ? idx - 1 : (idx == 0 ? 0 : n + idx); }
+
+// i, i/j, i//k, i/j/k
+inline Corner parseCorner(const char** tok, int nv, int nvn, int nvt) {
+  Corner c{-1, -1, -1};
+  c.v = fixIndex(std::atoi(*tok), nv);
+  *tok += std::strcspn(*tok, "/ \t\r");
+  if (**tok != '/') return c;
+  ++*tok;
+  if (**tok == '/') {
+    ++*tok;
+    c.vn = fixIndex(std::atoi(*tok), nvn);
+    *tok += std::strcspn(*tok, "/ \t\r");
+    return c;
+  }
+  c.vt = fixIndex(std::atoi(*tok), nvt);
+  *tok += std::strcspn(*tok, "/ \t\r");
+  if (**tok != '/') return c;
+  ++*tok;
+  c.vn = fixIndex(std::atoi(*tok), nvn);
+  *tok += std::strcspn(*tok, "/ \t\r");
+  return c;
+}
+
+inline std::string firstWord(const char* s) {  // what sscanf("%s") reads
+  s += std::strspn(s, " \t\n\v\f\r");
+  return std::string(s, std::strcspn(s, " \t\n\v\f\r"));
+}
+
+// Material names of one .mtl file, numbered as tinyobj numbers them (a named material is registered when the next `newmtl` or the
+// end of the file closes it; the last one is registered even when it has no name).
+inline bool readMaterialNames(const std::string& file, std::map<std::string, int>& ids, int& count) {
+  std::ifstream in(file.c_str());
+  if (!in) return false;
+  std::string line, name;
+  while (getLine(in, line)) {
+    const size_t last = line.find_last_not_of(" \t");
+    line = last == std::string::npos ? std::string() : line.substr(0, last + 1);
+    const char* tok = line.c_str();
+    tok += std::strspn(tok, " \t");
+    if (*tok == '\0' || *tok == '#') continue;
+    if (std::strncmp(tok, "newmtl", 6) == 0 && isSpace(tok[6])) {
+      if (!name.empty()) { ids.insert(std::make_pair(name, count)); ++count; }
+      name = firstWord(tok + 7);
+    }
+  }
+  ids.insert(std::make_pair(name, count));
+  ++count;
+  return true;
+}
+
+// The corner list of every shape of the file, in tinyobj's shape order (triangulated).
+inline std::vector<Corner> parse(std::istream& in, std::vector<float>& v, std::vector<float>& vn, std::vector<float>& vt) {
+  std::vector<Corner> out;              // shapes already closed, concatenated (loadModel walks them in order)
+  std::vector<Corner> shape;            // the open shape
+  std::vector<std::vector<Corner>> faceGroup;  // faces not yet moved into the open shape
+  std::map<std::string, int> materialIds;
+  int materialCount = 0, material = -1;
+  auto flush = [&]() {  // faces -> open shape, fan-triangulated; false when there was nothing to move
+    if (faceGroup.empty()) return false;
+    for (const std::vector<Corner>& face : faceGroup)
+      for (size_t k = 2; k < face.size(); ++k) { shape.push_back(face[0]); shape.push_back(face[k - 1]); shape.push_back(face[k]); }
+    return true;
+  };
+  std::string line;
+  while (getLine(in, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    const char* tok = line.c_str();
+    tok += std::strspn(tok, " \t");
+    if (*tok == '\0' || *tok == '#') continue;
+    if (tok[0] == 'v' && isSpace(tok[1])) {
+      tok += 2;
+      for (int k = 0; k < 3; ++k) v.push_back(parseReal(&tok));
+    } else if (tok[0] == 'v' && tok[1] == 'n' && isSpace(tok[2])) {
+      tok += 3;
+      for (int k = 0; k < 3; ++k) vn.push_back(parseReal(&tok));
+    } else if (tok[0] == 'v' && tok[1] == 't' && isSpace(tok[2])) {
+      tok += 3;
+      for (int k = 0; k < 2; ++k) vt.push_back(parseReal(&tok));
+    } else if (tok[0] == 'f' && isSpace(tok[1])) {
+      tok += 2;
+      tok += std::strspn(tok, " \t");
+      std::vector<Corner> face;
+      while (!isLineEnd(*tok)) {
+        face.push_back(parseCorner(&tok, (int)(v.size() / 3), (int)(vn.size() / 3), (int)(vt.size() / 2)));
+        tok += std::strspn(tok, " \t\r");
+      }
+      faceGroup.push_back(std::move(face));
+    } else if (std::strncmp(tok, "usemtl", 6) == 0 && isSpace(tok[6])) {
+      const auto it = materialIds.find(firstWord(tok + 7));
+      const int id = it == materialIds.end() ? -1 : it->second;
+      if (id != material) { flush(); faceGroup.clear(); material = id; }
+    } else if (std::strncmp(tok, "mtllib", 6) == 0 && isSpace(tok[6])) {
+      std::stringstream names(std::string(tok + 7));
+      std::string file;
+      while (std::getline(names, file, ' '))
+        if (readMaterialNames(file, materialIds, materialCount)) break;
+    } else if ((tok[0] == 'g' || tok[0] == 'o') && isSpace(tok[1])) {
+      if (flush()) out.insert(out.end(), shape.begin(), shape.end());
+      shape.clear();  // a shape whose last faces were already moved by a material change is dropped here, as in tinyobj 1.0.6
+      faceGroup.clear();
+    }
+  }
+  if (flush() || !shape.empty()) out.insert(out.end(), shape.begin(), shape.end());
+  return out;
+}
+
+inline Mesh load(std::istream& in) {
+  std::vector<float> v, vn, vt;
+  const std::vector<Corner> corners = parse(in, v, vn, vt);
+  Mesh m;
+  // key: the 8 floats with -0 folded onto +0 (the reference compares with ==, RT/Scene.h:33-37); the first vertex seen is kept
+  std::unordered_map<std::string, uint32_t> unique;
+  auto inRange = [](int i, size_t n, const char* what) {
+    if ((size_t)i >= n) throw std::runtime_error(std::string("OBJ: ") + what + " index out of range");
+  };
+  for (const Corner& c : corners) {
+    brt_vertex x{};
+    if (c.v >= 0) { inRange(c.v, v.size() / 3, "vertex"); x.pos[0] = v[3 * c.v]; x.pos[1] = -v[3 * c.v + 1]; x.pos[2] = v[3 * c.v + 2]; }                 // :47-51
+    if (c.vn >= 0) { inRange(c.vn, vn.size() / 3, "normal"); x.normal[0] = vn[3 * c.vn]; x.normal[1] = -vn[3 * c.vn + 1]; x.normal[2] = vn[3 * c.vn + 2]; }  // :53-57
+    if (c.vt >= 0) { inRange(c.vt, vt.size() / 2, "texcoord"); x.uv[0] = vt[2 * c.vt]; x.uv[1] = vt[2 * c.vt + 1]; }                                       // :59-62
+    float k[8];
+    std::memcpy(k, &x, sizeof(k));
+    for (float& f : k) if (f == 0.0f) f = 0.0f;
+    const std::string key(reinterpret_cast<const char*>(k), sizeof(k));
+    auto it = unique.find(key);
+    if (it == unique.end()) { it = unique.emplace(key, (uint32_t)m.vertices.size()).first; m.vertices.push_back(x); }  // :64-67
+    m.indices.push_back(it->second);                                                                                  // :69
+  }
+  return m;
+}
+
+inline Mesh load(const std::string& path) {
+  std::ifstream in(path.c_str());
+  if (!in) throw std::runtime_error("Cannot open file [" + path + "]\n");  // tinyobj's message, thrown at RT/Scene.cpp:38-41
+  return load(in);
+}
+
+}}  // namespace bloon::obj
 
 namespace Core {
 
@@ -157,48 +379,12 @@ class Scene {
   Scene(const Scene&) = delete;
   Scene& operator=(const Scene&) = delete;
 
-  // RT/Scene.cpp:29-74: OBJ -> flip Y of positions and normals -> de-duplicate identical vertices -> indexed mesh.
-  // (The reference parses with tinyobjloader 1.0.6; this reads the v / vn / vt / f records that loader feeds it,
-  // fan-triangulating polygons.)
+  // RT/Scene.cpp:29-74: OBJ -> flip Y of positions and normals -> de-duplicate identical vertices -> ONE indexed mesh over all
+  // shapes of the file. Parsing follows tinyobjloader 1.0.6, the reference's parser (bloon::obj below); returns the mesh id
+  // (the reference returns void and the id is the running mesh count — the same number).
   uint32_t loadModel(const std::string& path) {
-    std::ifstream in(path);
-    if (!in) throw std::runtime_error("Cannot open file [" + path + "]");
-    std::vector<float> pos, nrm, tex;
-    std::vector<Vertex> vertices;
-    std::vector<uint32_t> indices;
-    std::unordered_map<std::string, uint32_t> unique;
-    std::string line;
-    auto resolve = [](int i, size_t n) { return i > 0 ? i - 1 : (i < 0 ? (int)n + i : -1); };
-    while (std::getline(in, line)) {
-      std::istringstream ss(line);
-      std::string tag;
-      ss >> tag;
-      if (tag == "v") { float a, b, c; ss >> a >> b >> c; pos.insert(pos.end(), {a, b, c}); }
-      else if (tag == "vn") { float a, b, c; ss >> a >> b >> c; nrm.insert(nrm.end(), {a, b, c}); }
-      else if (tag == "vt") { float a = 0, b = 0; ss >> a >> b; tex.insert(tex.end(), {a, b}); }
-      else if (tag == "f") {
-        std::vector<uint32_t> face;
-        std::string tok;
-        while (ss >> tok) {
-          int vi = 0, ti = 0, ni = 0;
-          if (std::sscanf(tok.c_str(), "%d/%d/%d", &vi, &ti, &ni) == 3) {}
-          else if (std::sscanf(tok.c_str(), "%d//%d", &vi, &ni) == 2) { ti = 0; }
-          else if (std::sscanf(tok.c_str(), "%d/%d", &vi, &ti) == 2) { ni = 0; }
-          else { std::sscanf(tok.c_str(), "%d", &vi); ti = ni = 0; }
-          Vertex v{};
-          const int pv = resolve(vi, pos.size() / 3), pt = resolve(ti, tex.size() / 2), pn = resolve(ni, nrm.size() / 3);
-          if (pv >= 0) { v.pos[0] = pos[3 * pv]; v.pos[1] = -pos[3 * pv + 1]; v.pos[2] = pos[3 * pv + 2]; }          // :47-51
-          if (pn >= 0) { v.normal[0] = nrm[3 * pn]; v.normal[1] = -nrm[3 * pn + 1]; v.normal[2] = nrm[3 * pn + 2]; }  // :53-57
-          if (pt >= 0) { v.uv[0] = tex[2 * pt]; v.uv[1] = tex[2 * pt + 1]; }                                           // :59-62
-          std::string key(reinterpret_cast<const char*>(&v), sizeof(v));  // equality on all 8 floats (RT/Scene.h:33-37)
-          auto it = unique.find(key);
-          if (it == unique.end()) { it = unique.emplace(key, (uint32_t)vertices.size()).first; vertices.push_back(v); }
-          face.push_back(it->second);
-        }
-        for (size_t k = 2; k < face.size(); ++k) { indices.push_back(face[0]); indices.push_back(face[k - 1]); indices.push_back(face[k]); }
-      }
-    }
-    return createMesh(vertices, indices);
+    const bloon::obj::Mesh m = bloon::obj::load(path);
+    return createMesh(m.vertices, m.indices);
   }
   // Mesh::Mesh (RT/Scene.cpp:419-458) for procedural geometry
   uint32_t createMesh(const std::vector<Vertex>& vertices, const std::vector<uint32_t>& indices) {
