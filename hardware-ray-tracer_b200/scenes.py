@@ -43,7 +43,7 @@ class SceneDesc:
     name: str
     meshes: list = field(default_factory=list)      # ("tri", vertices[n,8] f32, indices u32) | ("sphere", center, radius)
     materials: list = field(default_factory=list)   # MaterialDesc
-    lights: list = field(default_factory=list)      # (pos, color, intensity)
+    lights: list = field(default_factory=list)      # (pos, color, intensity[, type])
     instances: list = field(default_factory=list)   # (mesh, material, xform 3x4)
     cam_pos: tuple = (0.0, 0.0, -2.0)
     cam_rot: tuple = (0.0, 0.0, 0.0)
@@ -64,8 +64,8 @@ class SceneDesc:
             mid = api.material_create(md.color, md.metallic, md.roughness, md.specular, **md.extra)
             if md.transmission > 0.0:
                 api.material_set_transmission(mid, md.transmission, md.ior)
-        for pos, color, inten in self.lights:
-            api.light_create(pos, color, inten)
+        for light in self.lights:  # (pos, color, intensity[, type]); Scene::createLight always makes POINT lights (RT/Scene.cpp:88-97)
+            api.light_create(*light)
         for mesh, mat, x in self.instances:
             api.instance_create(ids[mesh], mat, x)
         if build:

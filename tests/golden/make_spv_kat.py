@@ -1,0 +1,324 @@
+"""Generates tests/golden/spv_kat.json: frames computed by EXECUTING the reference's shipped shader binary
+(`/root/reference/Hardware Ray Tracer/shaders/raytracing.slang.spv`, loaded by the app at RT/RTPipeline.cpp:168) with
+oracle/ref/spv_interp.py, driven by the reference's own host code (oracle/_ref/libref_host.so: Camera.cpp + glm give the
+140-byte Uniform of RT/RTApp.cpp:44-49, MeshInstance.h gives the instance transforms).
+
+Run in the build container (needs /root/reference):  python tests/golden/make_spv_kat.py
+The GPU box has no /root/reference: tests read only the committed JSON.
+
+What is the reference's and what is the harness's:
+* reference: every arithmetic step of rgenMain / rchitMain / rmissMain / rmissShadowMain (ray generation, geometry fetch through
+  the 64-bit buffer addresses, barycentric interpolation, normal transform, processLight, the whole Disney BRDF, the shadow-ray
+  set-up, the path loop, the image write), the byte layouts the shaders read (SceneInfo, InstanceInfo, Material, Light, Vertex),
+  the Uniform block.
+* harness (the Vulkan driver / RT cores in the real application — no source in the reference): `TraceRay`. Closest and any hit
+  are found here by brute force in float64 over the instanced triangles (Moeller-Trumbore), barycentrics rounded to binary32;
+  miss index 0 runs rmissMain, miss index 2 runs rmissShadowMain, a shadow hit runs nothing
+  (SKIP_CLOSEST_HIT_SHADER). ObjectToWorld / WorldToObject are the instance's 3x4 and its inverse (float64, rounded once).
+  `slack` (per pixel) is how far the closest-hit shader's radiance moves when those implementation-defined inputs move by
+  what a binary32 intersector leaves open (barycentrics +-4e-6, ray direction 2e-7; seven one-at-a-time probes, summed): the
+  conditioning of the pixel (a GGX lobe of small roughness amplifies an ulp a thousandfold); the tests widen their bar by it.
+  A pixel is flagged `fragile` when one of its rays passes within 1e-5 (barycentric units) of a triangle edge or within a relative
+  1e-5 of an interval end: there a different (equally valid) intersector may decide differently, tests skip those pixels.
+
+Scenes obey `instances[m].meshId == m` for every used mesh id so that the shader's meshID-indexed address lookup
+(SH/raytracing.slang:143-144) reads the intended mesh.
+"""
+import ctypes as C
+import json
+import os
+import struct
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ref"))
+from spv_interp import F32, Interpreter, Memory, Module  # noqa: E402
+
+SPV = "/root/reference/Hardware Ray Tracer/shaders/raytracing.slang.spv"
+F3 = C.c_float * 3
+MAT_FIELDS = ["subsurface", "metallic", "roughness", "specular", "specularTint", "anisotropic", "sheen", "sheenTint", "clearCoat", "clearCoatGloss"]
+
+
+def ref_host():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle", "ref")])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_host.so"))
+    lib.ref_camera_new.restype = C.c_void_p
+    lib.ref_camera_set_view.argtypes = [C.c_void_p, F3, F3]
+    lib.ref_camera_set_perspective.argtypes = [C.c_void_p] + [C.c_float] * 4
+    lib.ref_uniform.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char * 140]
+    lib.ref_instance_transform.argtypes = [F3, F3, F3, C.c_float * 12]
+    return lib
+
+
+def quad(p0, p1, p2, p3, n=None):
+    p = np.array([p0, p1, p2, p3], np.float32)
+    if n is None:
+        n = np.cross(p[1] - p[0], p[3] - p[0])
+        n = n / np.linalg.norm(n)
+    v = np.zeros((4, 8), np.float32)
+    v[:, 0:3], v[:, 3:6], v[:, 6:8] = p, np.asarray(n, np.float32), [[0, 0], [1, 0], [1, 1], [0, 1]]
+    return v, np.array([0, 1, 2, 0, 2, 3], np.uint32)
+
+
+def material(color, **kw):
+    m = dict(color=[float(np.float32(c)) for c in color], subsurface=0.0, metallic=0.0, roughness=1.0, specular=0.5, specularTint=0.0,
+             anisotropic=0.0, sheen=0.0, sheenTint=0.0, clearCoat=0.0, clearCoatGloss=0.0)
+    m.update({k: float(np.float32(v)) for k, v in kw.items()})
+    return m
+
+
+def scenes():
+    out = []
+    # 1. the application's own scene (RT/RTApp.cpp:3-26): models/Plane.obj is not in the repository, a 2 x 2 quad in the XZ plane stands in
+    plane = quad((-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1))
+    out.append(dict(
+        name="rtapp_demo", width=40, height=30, depth_max=2, meshes=[plane],
+        materials=[material((1, 1, 1), metallic=1.0), material((1, 1, 1), metallic=1.0, roughness=0.0)],
+        lights=[((1, 0, 0), (0, 0, 1), 2.0, 0), ((-1, 0, 0), (0, 1, 0), 2.0, 0), ((0, 0, -1), (1, 0, 0), 2.0, 0)],
+        instances=[(0, 1, (0, -1, 0), (1, 1, 1)), (0, 0, (0, 1, 0), (4, 1, 4))],
+        cam_pos=(0, 0, -2), cam_rot=(0, 0, 0), fovy=float(np.float32(np.radians(60.0)))))
+    # 2.-5. material sweeps: a floor, a back wall and a row of tilted panels with smooth (non-flat) normals, each panel its own
+    # random Disney material (all 13 fields), instances scaled anisotropically; point lights + the constant-direction branch of
+    # processLight (types 1 and 2) + a light below LIGHT_TRESHOLD; rotated cameras, non-square images.
+    rng = np.random.default_rng(20261018)
+    for s in range(4):
+        floor = quad((-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1))
+        wall = quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0))
+        panel_v, panel_i = quad((-0.5, -0.5, 0), (0.5, -0.5, 0), (0.5, 0.5, 0), (-0.5, 0.5, 0))
+        # bend the normals so that the interpolated normal varies over the panel and needs its renormalisation
+        panel_v[:, 3:6] += (rng.random((4, 3)).astype(np.float32) - 0.5) * np.float32(0.8)
+        panel_v[:, 3:6] /= np.linalg.norm(panel_v[:, 3:6], axis=1, keepdims=True)
+        tri_v = np.zeros((3, 8), np.float32)
+        tri_v[:, 0:3] = [(-0.6, 0.4, 0.1), (0.6, 0.5, -0.1), (0.0, -0.7, 0.0)]
+        tri_v[:, 3:6] = [(0.2, 0.1, -1), (-0.2, 0.1, -1), (0, -0.3, -1)]  # deliberately not unit length
+        tri = (tri_v, np.array([0, 1, 2], np.uint32))
+        meshes = [floor, wall, (panel_v, panel_i), tri]
+        mats = [material((0.8, 0.8, 0.8)), material((0.6, 0.7, 0.9), roughness=0.6, specular=0.3)]
+        for _ in range(8):
+            kw = {k: float(rng.random()) for k in MAT_FIELDS}
+            kw["roughness"] = float(0.15 + 0.85 * rng.random())
+            if rng.random() < 0.3:
+                kw["metallic"] = float(rng.integers(0, 2))
+            if rng.random() < 0.3:
+                kw["anisotropic"] = 0.0
+            mats.append(material(rng.random(3) * 0.9 + 0.05, **kw))
+        mats.append(material((0, 0, 0), roughness=0.5))  # black: calculateTint's l > 0 branch takes the other side
+        lights = [((float(rng.normal() * 1.5), -2.5, -1.5), tuple(float(x) for x in rng.random(3) * 0.8 + 0.2), 6.0, 0),
+                  ((2.0, -1.0, float(-2 + rng.normal() * 0.3)), tuple(float(x) for x in rng.random(3) * 0.8 + 0.2), 4.0, 0),
+                  ((0.0, 0.0, 0.0), (0.3, 0.25, 0.2), 0.5, int(1 + s % 2)),   # SPOT / DIRECTIONAL: constant direction, no falloff
+                  ((0.0, -50.0, 0.0), (1, 1, 1), 0.2, 0)]                      # 0.2 / 2500 < 1e-4: skipped
+        inst = [(0, 0, (0, 1.0, 1.0), (3.0, 1.0, 3.0)),       # floor (mesh 0 at instance 0)
+                (1, 1, (0, -0.5, 2.5), (3.0, 1.5, 1.0)),      # wall  (mesh 1 at instance 1)
+                (2, 2, (-1.6, 0.2, 1.2), (0.9, 1.3, 1.0)),    # panel (mesh 2 at instance 2)
+                (3, 3, (1.7, 0.1, 1.0), (1.0, 1.2, 1.0))]     # triangle (mesh 3 at instance 3)
+        for k in range(6):
+            inst.append((2 if k % 2 == 0 else 3, 4 + k, (float(-1.0 + 0.55 * k + rng.normal() * 0.05), float(0.3 - 0.25 * (k % 3)), float(0.6 + 0.2 * (k % 2))),
+                         (float(0.5 + 0.4 * rng.random()), float(0.5 + 0.6 * rng.random()), 1.0)))
+        inst.append((2, 10, (0.0, -1.2, 1.8), (0.8, 0.5, 1.0)))
+        w, h = [(36, 24), (24, 32), (32, 32), (40, 20)][s]
+        out.append(dict(name=f"disney_sweep_{s}", width=w, height=h, depth_max=2, meshes=meshes, materials=mats, lights=lights, instances=inst,
+                        cam_pos=(float(rng.normal() * 0.3), float(-0.6 + rng.normal() * 0.2), -2.6),
+                        cam_rot=(float(-0.15 + rng.normal() * 0.05), float(rng.normal() * 0.1), float(rng.normal() * 0.05) if s >= 2 else 0.0),
+                        fovy=float(np.float32(np.radians([60.0, 45.0, 75.0, 50.0][s])))))
+    return out
+
+
+class World:
+    """Instanced triangles in float64 for the stand-in of TraceRay."""
+
+    def __init__(self, sc, xforms):
+        tris, owner = [], []
+        for i, (mesh, _mat, _p, _s) in enumerate(sc["instances"]):
+            v, idx = sc["meshes"][mesh]
+            m = np.asarray(xforms[i], np.float64).reshape(3, 4)
+            p = v[:, 0:3].astype(np.float64) @ m[:, :3].T + m[:, 3]
+            t = p[idx.reshape(-1, 3)]
+            tris.append(t)
+            owner += [(i, k) for k in range(len(t))]
+        self.t = np.concatenate(tris)
+        self.owner = owner
+
+    def hits(self, o, d, tmin, tmax):
+        """All (t, u, v, instance, prim) with tmin < t < tmax, plus the fragility of this ray."""
+        o, d = np.asarray(o, np.float64), np.asarray(d, np.float64)
+        v0, e1, e2 = self.t[:, 0], self.t[:, 1] - self.t[:, 0], self.t[:, 2] - self.t[:, 0]
+        p = np.cross(d, e2)
+        det = (e1 * p).sum(1)
+        ok = np.abs(det) > 1e-300
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        s = o - v0
+        u = (s * p).sum(1) * inv
+        q = np.cross(s, e1)
+        v = (q * d).sum(1) * inv
+        t = (q * e2).sum(1) * inv
+        w = 1.0 - u - v
+        tmin, tmax = float(tmin), float(tmax)
+        inside = ok & (u >= 0) & (v >= 0) & (w >= 0)
+        inrange = (t > tmin) & (t < tmax)
+        edge = np.minimum(np.minimum(np.abs(u), np.abs(v)), np.abs(w))
+        near_end = (np.abs(t - tmin) <= 1e-5 * max(abs(tmin), 1e-3)) | (np.abs(t - tmax) <= 1e-5 * abs(tmax))
+        loose = ok & (u >= -1e-5) & (v >= -1e-5) & (w >= -1e-5) & (t > tmin * 0.5) & (t < tmax * 1.5 + 1e-3)
+        fragile = bool((loose & ((edge < 1e-5) | near_end)).any()) or bool((~ok & (np.abs(det) > 0)).any())
+        hit = np.nonzero(inside & inrange)[0]
+        return [(t[k], u[k], v[k]) + self.owner[k] for k in hit], fragile
+
+
+def run_scene(mod, host, sc):
+    mem = Memory()
+    it = Interpreter(mod, mem)
+    # --- host side, as Scene::build lays it out (RT/Scene.cpp:313-403) ---
+    vaddr, iaddr = [], []
+    for v, idx in sc["meshes"]:
+        vaddr.append(mem.alloc(v.astype("<f4").tobytes()))
+        iaddr.append(mem.alloc(idx.astype("<u4").tobytes()))
+    mat_bytes = b"".join(struct.pack("<13f", *m["color"], *[m[k] for k in MAT_FIELDS]) for m in sc["materials"])
+    light_bytes = b"".join(struct.pack("<7fB3x", *p, *c, i, t) for p, c, i, t in sc["lights"])
+    inst_bytes = b"".join(struct.pack("<QQI4x", vaddr[mesh], iaddr[mesh], mat) for mesh, mat, _p, _s in sc["instances"])
+    sky_addr = mem.alloc(bytes(88))
+    m_addr, l_addr, i_addr = mem.alloc(mat_bytes), mem.alloc(light_bytes), mem.alloc(inst_bytes)
+    info = struct.pack("<10Q", m_addr, 52, l_addr, 32, len(sc["lights"]), 32, i_addr, 24, sky_addr, 88)
+    it.bindings[(0, 3)] = mem.alloc(info)
+    cam = host.ref_camera_new()
+    host.ref_camera_set_view(cam, F3(*sc["cam_pos"]), F3(*sc["cam_rot"]))
+    host.ref_camera_set_perspective(cam, sc["fovy"], sc["width"] / sc["height"], 0.001, 100000.0)
+    raw = (C.c_char * 140)()
+    host.ref_uniform(cam, 0, sc["depth_max"], raw)
+    it.bindings[(0, 2)] = mem.alloc(bytes(raw))
+    xforms = []
+    for mesh, mat, pos, scale in sc["instances"]:
+        out = (C.c_float * 12)()
+        host.ref_instance_transform(F3(*pos), F3(0, 0, 0), F3(*scale), out)
+        xforms.append(np.array(out, np.float32))
+    world = World(sc, xforms)
+    o2w, w2o = [], []
+    for x in xforms:
+        m = np.eye(4)
+        m[:3, :] = np.asarray(x, np.float64).reshape(3, 4)
+        inv = np.linalg.inv(m)
+        # SPIR-V mat4x3: four columns of three rows
+        o2w.append([[F32(m[r, c]) for r in range(3)] for c in range(4)])
+        w2o.append([[F32(inv[r, c]) for r in range(3)] for c in range(4)])
+
+    state = {}
+
+    def trace(call):
+        hits, fragile = world.hits(call.origin, call.direction, call.tmin, call.tmax)
+        if state.get("probing"):  # shadow queries of the conditioning probe: answered, not counted
+            if call.flags == 12 and not hits:
+                it.run("rmissShadowMain", incoming_payload=call.payload_ref)
+            return
+        first = call.flags == 0 and state["depth"] == 0
+        state["fragile"] |= fragile
+        state["rays"] += 1
+        if call.flags == 0:  # closest hit (SH/raytracing.slang:121)
+            if call.miss_index != 0:
+                raise AssertionError("closest-hit query with a miss index other than 0")
+            if not hits:
+                it.run("rmissMain", incoming_payload=call.payload_ref)
+                if state["depth"] == 0:
+                    state["prim"], state["inst"], state["t"] = -1, -1, -1.0
+                state["depth"] += 1
+                return
+            hits.sort(key=lambda h: (h[0], h[3], h[4]))
+            if len(hits) > 1 and abs(hits[1][0] - hits[0][0]) <= 1e-6 * abs(hits[0][0]):
+                state["fragile"] = True
+            t, u, v, inst, prim = hits[0]
+            if state["depth"] == 0:
+                state["prim"], state["inst"], state["t"] = prim, inst, float(t)
+            state["depth"] += 1
+            mesh = sc["instances"][inst][0]
+            builtins = {"InstanceId": inst, "InstanceCustomIndexKHR": mesh, "PrimitiveId": prim, "ObjectToWorldKHR": o2w[inst],
+                        "WorldToObjectKHR": w2o[inst], "WorldRayDirectionKHR": list(call.direction)}
+            probes = []
+            if first:
+                # conditioning of this pixel: the closest-hit shader again with ONE of its implementation-defined inputs moved —
+                # u, v by 4e-6 (a binary32 ray/triangle test resolves barycentrics to ~1e-7 x (distance / triangle size)^2; RT hardware
+                # is no better), each ray-direction component by 2e-7 relative; the sum of the radiance changes is recorded as `slack`
+                import copy as _copy
+                state["probing"] = True
+                for du, dv, dd in ((4e-6, 0, (0, 0, 0)), (-4e-6, 0, (0, 0, 0)), (0, 4e-6, (0, 0, 0)), (0, -4e-6, (0, 0, 0)),
+                                   (0, 0, (2e-7, 0, 0)), (0, 0, (0, 2e-7, 0)), (0, 0, (0, 0, 2e-7))):
+                    probe = _copy.deepcopy(call.payload_ref)
+                    b2 = dict(builtins)
+                    b2["WorldRayDirectionKHR"] = [F32(float(c) * (1.0 + e)) for c, e in zip(call.direction, dd)]
+                    it.run("rchitMain", b2, incoming_payload=probe, hit_attribute=[[F32(u + du), F32(v + dv)]])
+                    probes.append(probe)
+                state["probing"] = False
+            it.run("rchitMain", builtins, incoming_payload=call.payload_ref, hit_attribute=[[F32(u), F32(v)]])
+            if first:
+                state["slack"] = sum(max(abs(float(a) - float(b)) for a, b in zip(p[0][0], call.payload_ref[0][0])) for p in probes)
+        elif call.flags == 12:  # ACCEPT_FIRST_HIT_AND_END_SEARCH | SKIP_CLOSEST_HIT_SHADER (SH/raytracing.slang:67)
+            if call.miss_index != 2:
+                raise AssertionError("shadow query with a miss index other than 2")
+            state["shadow_rays"] += 1
+            if not hits:
+                it.run("rmissShadowMain", incoming_payload=call.payload_ref)
+        else:
+            raise AssertionError(f"unexpected ray flags {call.flags}")
+        if call.mask != 255 or call.sbt_offset != 0 or call.sbt_stride != 0:
+            raise AssertionError("unexpected TraceRay arguments")
+
+    it.trace = trace
+    w, h = sc["width"], sc["height"]
+    rgba = np.zeros((h, w, 4), np.float32)
+    prim = np.zeros((h, w), np.int32)
+    inst = np.zeros((h, w), np.int32)
+    tt = np.zeros((h, w), np.float32)
+    frag = np.zeros((h, w), np.uint8)
+    slack = np.zeros((h, w), np.float32)
+    rays = shadow = 0
+    for y in range(h):
+        for x in range(w):
+            state.update(fragile=False, rays=0, shadow_rays=0, depth=0, prim=-1, inst=-1, t=-1.0, slack=0.0, probing=False)
+            it.image_writes.clear()
+            it.run("rgenMain", {"LaunchIdKHR": [x, y, 0], "LaunchSizeKHR": [w, h, 1]})
+            (coord, texel), = it.image_writes
+            assert coord == (x, y)
+            rgba[y, x] = texel
+            prim[y, x], inst[y, x], tt[y, x], frag[y, x] = state["prim"], state["inst"], state["t"], state["fragile"]
+            slack[y, x] = state["slack"]
+            rays += state["rays"]
+            shadow += state["shadow_rays"]
+    return dict(rgba=rgba, prim=prim, inst=inst, t=tt, fragile=frag, slack=slack, rays=rays, shadow_rays=shadow, uniform=bytes(raw), xforms=xforms)
+
+
+def main():
+    mod = Module(SPV)
+    host = ref_host()
+    cases = []
+    for sc in scenes():
+        t0 = time.time()
+        r = run_scene(mod, host, sc)
+        print(f"{sc['name']}: {sc['width']}x{sc['height']}, {r['rays']} rays ({r['shadow_rays']} shadow), "
+              f"{int(r['fragile'].sum())} fragile pixels, lit {float((r['rgba'][..., :3].sum(-1) > 0).mean()):.2f}, {time.time() - t0:.1f} s", flush=True)
+        cases.append(dict(
+            name=sc["name"], width=sc["width"], height=sc["height"], depth_max=sc["depth_max"],
+            cam_pos=list(sc["cam_pos"]), cam_rot=list(sc["cam_rot"]), fovy=sc["fovy"],
+            meshes=[dict(vertices=v.view(np.uint32).reshape(-1).tolist(), indices=i.tolist()) for v, i in sc["meshes"]],
+            materials=sc["materials"],
+            lights=[dict(pos=list(p), color=list(c), intensity=i, type=t) for p, c, i, t in sc["lights"]],
+            instances=[dict(mesh=m, material=mat, position=list(p), scale=list(s)) for m, mat, p, s in sc["instances"]],
+            uniform_hex=r["uniform"].hex(),
+            xforms=[x.view(np.uint32).tolist() for x in r["xforms"]],
+            rgba_bits=r["rgba"].view(np.uint32).reshape(-1).tolist(),
+            prim=r["prim"].reshape(-1).tolist(), inst=r["inst"].reshape(-1).tolist(),
+            hit_t=[float(x) for x in r["t"].reshape(-1)], fragile=r["fragile"].reshape(-1).tolist(),
+            slack=[float(x) for x in r["slack"].reshape(-1)],
+            rays=r["rays"], shadow_rays=r["shadow_rays"]))
+    out = dict(
+        source="/root/reference/Hardware Ray Tracer/shaders/raytracing.slang.spv executed by oracle/ref/spv_interp.py; "
+               "Uniform and instance transforms from oracle/_ref/libref_host.so (the reference's Camera.cpp, MeshInstance.h, glm)",
+        generator="tests/golden/make_spv_kat.py", spv_sha256=__import__("hashlib").sha256(open(SPV, "rb").read()).hexdigest(),
+        float_encoding="binary32 bit patterns (uint32) for vertices, rgba, xforms", cases=cases)
+    path = os.path.join(ROOT, "tests", "golden", "spv_kat.json")
+    with open(path, "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
