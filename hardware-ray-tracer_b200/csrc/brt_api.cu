@@ -47,11 +47,14 @@ __global__ void __launch_bounds__(128, BRT_SHADE_MIN_BLOCKS) k_shade(const Shade
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t base = blockIdx.x * slots; base < n; base += gridDim.x * slots) {  // block-uniform trip count
     bool is_hit[K];
+    uint32_t slot[K];
     unsigned m[K];
 #pragma unroll
     for (uint32_t k = 0; k < K; ++k) {
-      const uint32_t i = base + k * 128u + threadIdx.x;
-      is_hit[k] = k < kk && i < n && shade_prologue(p, i);
+      const uint32_t w = base + k * 128u + threadIdx.x;
+      const bool live = k < kk && w < n;
+      slot[k] = live && p.order ? p.order[w] : w;  // hit-sorted order of a bounce round (render_kernels.cuh), else queue order
+      is_hit[k] = live && shade_prologue(p, slot[k]);
       m[k] = __ballot_sync(0xffffffffu, is_hit[k]);
       if (lane == 0) s_warp[k * 4 + warp] = (uint32_t)__popc(m[k]);
     }
@@ -67,12 +70,63 @@ __global__ void __launch_bounds__(128, BRT_SHADE_MIN_BLOCKS) k_shade(const Shade
     }
 #pragma unroll
     for (uint32_t k = 0; k < K; ++k)
-      if (is_hit[k]) s_idx[off[k] + (uint32_t)__popc(m[k] & ((1u << lane) - 1u))] = base + k * 128u + threadIdx.x;
+      if (is_hit[k]) s_idx[off[k] + (uint32_t)__popc(m[k] & ((1u << lane) - 1u))] = slot[k];
     __syncthreads();
     for (uint32_t t = threadIdx.x; t < total; t += 128u) shade_hit(p, s_idx[t]);
     __syncthreads();  // s_idx / s_warp are rewritten by the next window
   }
 }
+#endif
+#ifndef BRT_EMU
+// hit sort of the bounce rounds (render_kernels.cuh): keys + per-cell arrival ranks, scan of the cell counters, scatter
+__global__ void __launch_bounds__(256) k_hit_keys(const HitSortParams p) {
+  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t key = hit_sort_key(p, i);
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&p.bins[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    p.key[i] = key;
+    p.rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  }
+}
+// in-place exclusive scan of `count` counters by one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_bins_scan(uint32_t* __restrict__ bins, uint32_t count) {
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t per = (count + 1023u) / 1024u;
+  const uint32_t begin = min(threadIdx.x * per, count), end = min(begin + per, count);
+  uint32_t sum = 0;
+  for (uint32_t i = begin; i < end; ++i) sum += bins[i];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t incl = sum;
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((int)lane >= off) incl += v;
+  }
+  if (lane == 31u) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = warp_sums[lane];
+    uint32_t wi = w;
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, off);
+      if ((int)lane >= off) wi += v;
+    }
+    warp_sums[lane] = wi - w;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[warp] + incl - sum;
+  for (uint32_t i = begin; i < end; ++i) {
+    const uint32_t v = bins[i];
+    bins[i] = run;
+    run += v;
+  }
+}
+BRT_KERNEL_1D(k_hit_order, HitSortParams, hit_order_body)
 #endif
 BRT_KERNEL_1D(k_accumulate, AccumParams, accumulate_body)
 BRT_KERNEL_1D(k_sum_samples, SumSamplesParams, sum_samples_body)
@@ -248,6 +302,7 @@ struct FrameSlot {
   uint32_t gather_img = 0;  // fused multi-GPU exchange: the gather image this slot's frame stored into
   bool has_gbuffer = false;
   uint32_t render_flags = 0;  // of the frame rendered last on this slot
+  DevBuf d_sort_key, d_sort_rank, d_sort_order, d_sort_bins;  // hit sort of the bounce rounds
   DevBuf d_alive;  // rounds that contributed per (sample in batch, slot)
   DevBuf d_rad, d_accum, d_image, d_tiles, d_aov_prim, d_aov_inst, d_aov_t, d_counters, d_fstats;
   std::deque<EventPair> events;  // deque: references stay valid while the pool grows
@@ -292,6 +347,7 @@ struct brt_context {
   DevBuf d_light_bvh;
   DevBuf d_materials, d_mat_ext, d_lights, d_inst_shade, d_inst_src, d_inst_ids, d_mesh_bounds, d_visible;
   DevBuf d_tlas_nodes, d_tlas_inst;
+  float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};  // world box of all instances (grid of the hit sort)
   uint32_t tlas_count = 0;  // visible, non-empty instances in the TLAS
   BuildResult tlas{};
 
@@ -510,6 +566,24 @@ void build_tables(brt_context* c) {
     r.mesh = in.mesh;
   }
   upload(s, c->d_inst_shade, shade.data(), shade.size() * sizeof(InstShade));
+  // world box of all instances (centre / extent form of |M| box): the grid of the bounce rounds' hit sort
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (const InstanceData& in : c->instances) {
+    const MeshData& m = *c->meshes[in.mesh];
+    for (int r = 0; r < 3; ++r) {
+      float ctr = in.o2w[4 * r + 3], ext = 0.0f;
+      for (int k = 0; k < 3; ++k) {
+        ctr += in.o2w[4 * r + k] * 0.5f * (m.lo[k] + m.hi[k]);
+        ext += std::fabs(in.o2w[4 * r + k]) * 0.5f * (m.hi[k] - m.lo[k]);
+      }
+      lo[r] = std::fmin(lo[r], ctr - ext);
+      hi[r] = std::fmax(hi[r], ctr + ext);
+    }
+  }
+  for (int k = 0; k < 3; ++k) {
+    c->scene_lo[k] = c->instances.empty() ? 0.0f : lo[k];
+    c->scene_hi[k] = c->instances.empty() ? 0.0f : hi[k];
+  }
   c->tables_dirty = false;
 }
 
@@ -678,6 +752,12 @@ void ensure_frame_buffers(brt_context* c, FrameSlot* f, const brt_render_opts& o
   f->d_hit_inst.ensure(capw * 4);
   f->d_rad.ensure(capw * 16 * R);
   f->d_alive.ensure(capw * 4);
+  if (R > 1 && (c->flags & BRT_CFG_HIT_SORT)) {
+    f->d_sort_key.ensure(capw * 4);
+    f->d_sort_rank.ensure(capw * 4);
+    f->d_sort_order.ensure(capw * 4);
+    f->d_sort_bins.ensure((size_t)BRT_HITSORT_BINS * 4);
+  }
   f->d_accum.ensure((size_t)cap * 16);
   f->d_image.ensure(npx * 16);
   f->d_tiles.ensure((size_t)cap * 16);
@@ -827,8 +907,19 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   if (lbvh)
     for (const brt_light& l : c->lights)
       if (l.type != BRT_LIGHT_POINT) bad_state("render_frame: BRT_RENDER_LIGHT_BVH needs POINT lights only");
-  if (c->tables_dirty) build_tables(c);
-  if (c->tlas_dirty) build_tlas(c);
+  if (c->tables_dirty || c->tlas_dirty) {
+    // the tables are uploaded (and the TLAS built) on the context's stream; frames of slots >= 1 run on their own non-blocking
+    // streams, so the scene must be in place before any of them is enqueued (a scene change is rare: a plain wait is enough)
+    if (c->tables_dirty) build_tables(c);
+    if (c->tlas_dirty) build_tlas(c);
+    BRT_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) {
+      c->built = false;
+      throw LimitError("render_frame: BVH deeper than the traversal stack allows");
+    }
+  }
+  if ((uint64_t)tiles_per_rank(o.width, o.height, c->tile_world) * 1024u > (1ull << BRT_SLOT_BITS))
+    throw LimitError("render_frame: more than 2^26 pixels per rank (path ids carry the pixel slot in 26 bits)");
   const bool any_bounce = (o.flags & (BRT_RENDER_BOUNCE_REFLECT | BRT_RENDER_BOUNCE_REFRACT | BRT_RENDER_BOUNCE_DIFFUSE)) != 0;
   const uint32_t rounds = any_bounce ? u.depthMax : std::min(u.depthMax, 1u);
   ensure_frame_buffers(c, f, o, rounds);
@@ -863,6 +954,11 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   std::memcpy(f->h_consts->Pi, u.projInverse, 64);
   f->h_consts->frame = u.frame;
   f->h_consts->sky = c->sky;
+  for (int k = 0; k < 3; ++k) {
+    const float ext = c->scene_hi[k] - c->scene_lo[k];
+    f->h_consts->scene_lo[k] = c->scene_lo[k];
+    f->h_consts->scene_inv[k] = ext > 0.0f ? (float)(1u << BRT_HITSORT_CELL_BITS) / ext : 0.0f;
+  }
   // Frames in flight are staggered: this frame starts when the previous one has traced its last full-width wavefront, so
   // that its saturating head overlaps the latency-bound tail (bounce rounds, resolve, copy-out) of the previous frame
   // instead of running in lockstep with it.
@@ -947,6 +1043,32 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           launches++;
           l_closest++;
         }
+        const uint32_t* order = nullptr;
+#ifndef BRT_EMU
+        if (round > 0 && (c->flags & BRT_CFG_HIT_SORT)) {  // hit sort (render_kernels.cuh): shade this bounce round in the order of the hit positions
+          HitSortParams hp{};
+          hp.count = capw;
+          hp.count_ptr = count_ptr;
+          hp.o = qc.o;
+          hp.d = qc.d;
+          hp.px = qc.px;
+          hp.hit = f->d_hit.as<float4>();
+          hp.hit_inst = f->d_hit_inst.as<uint32_t>();
+          hp.fc = f->d_consts.as<FrameConsts>();
+          hp.key = f->d_sort_key.as<uint32_t>();
+          hp.rank = f->d_sort_rank.as<uint32_t>();
+          hp.bins = f->d_sort_bins.as<uint32_t>();
+          hp.order = f->d_sort_order.as<uint32_t>();
+          BRT_CUDA(cudaMemsetAsync(hp.bins, 0, (size_t)BRT_HITSORT_BINS * 4, s));
+          Timed t(f, CLS_SHADE, s);
+          k_hit_keys<<<grid_for(c, capw, 256, 8), 256, 0, s>>>(hp);
+          k_bins_scan<<<1, 1024, 0, s>>>(hp.bins, BRT_HITSORT_BINS);
+          BRT_LAUNCH_1D(k_hit_order, hp, grid_for(c, capw, 256, 8), 256, s);
+          BRT_CHECK_LAUNCH();
+          launches += 3;
+          order = hp.order;
+        }
+#endif
         // the shadow-chain buffers of this parity were last used two rounds ago: wait for that accumulate
         if (acc_pending[par]) {
           if (s2 != s) BRT_CUDA(cudaStreamWaitEvent(s, f->ev_acc[par], 0));
@@ -986,6 +1108,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           sp.aov_pos = f->has_gbuffer ? f->d_aov_pos.as<float4>() : nullptr;
           sp.aov_nrm = f->has_gbuffer ? f->d_aov_nrm.as<float4>() : nullptr;
           sp.fc = f->d_consts.as<FrameConsts>();
+          sp.order = order;
           Timed t(f, CLS_SHADE, s);
   #ifdef BRT_EMU
           BRT_LAUNCH_1D(k_shade, sp, 1, 128, s);
@@ -1533,7 +1656,10 @@ int brt_smart_cull(brt_context* c, const brt_uniform* u, uint32_t width, uint32_
     c->stats.ms_cull = ms;
     cudaEventElapsedTime(&ms, e1, e2);
     c->stats.ms_tlas_build = ms;
-    if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) throw LimitError("smart_cull: BVH deeper than the traversal stack allows");
+    if (c->tlas.levels + max_blas_levels(c) > BRT_MAX_TREE_LEVELS) {
+      c->built = false;  // (scene_build above set it: a later render must not traverse this tree with the fixed-size stack)
+      throw LimitError("smart_cull: BVH deeper than the traversal stack allows");
+    }
     refresh_scene_stats(c);
     if (visible_count) {
       uint32_t k = 0;

@@ -87,6 +87,8 @@ struct FrameConsts {
   uint32_t frame;        // uniform.frame
   uint32_t pad[3];
   brt_sky sky;
+  float scene_lo[4];     // world bounds of the scene's instances and 64 / extent per axis: the grid of the hit sort (below)
+  float scene_inv[4];
 };
 
 struct RaygenParams {
@@ -222,6 +224,7 @@ struct ShadeParams {
   float4* aov_pos;  // BRT_RENDER_GBUFFER: world position (w = 1) and shading normal (w = hit distance) of the primary hit, else null
   float4* aov_nrm;
   const FrameConsts* fc;  // sky
+  const uint32_t* order;  // bounce rounds: path slots in the order of their hit positions (hit sort, below); null = queue order
 };
 
 // Light BVH sampling (RT/Scene.h:123-130, SH/raytracing.slang:76; rule in DESIGN.md §13): stochastic descent from the root, a child
@@ -461,6 +464,51 @@ BRT_HD void shade_hit(const ShadeParams& p, uint32_t i) {
 BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
   if (shade_prologue(p, i)) shade_hit(p, i);
 }
+
+// ---- hit sort (bounce rounds) -------------------------------------------------------------------------
+// OPT-IN (BRT_CFG_HIT_SORT), measured and found slower on B200 (profiles/r2_traversal.md). After the first bounce the paths of a
+// wavefront hit the scene at unrelated places: the shadow rays and the next bounce rays that the shade kernel emits then start at
+// unrelated origins. With this flag the hits of a bounce round are counting-sorted by the cell of their world position (64^3 grid over the
+// scene, Morton order, misses last) and the shade kernel walks the paths in that order: neighbouring threads shade neighbouring
+// surface points, and both queues it appends to come out in runs of rays with neighbouring origins. Nothing but the ORDER of
+// work changes — every result is addressed by its path slot —, so frames stay bit-identical.
+//   k_hit_keys  key = cell of the hit, rank = arrival number inside the cell (one warp-aggregated atomic per distinct cell and warp)
+//   k_bins_scan exclusive scan of the cell counters (brt_api.cu)
+//   k_hit_order order[start(cell) + rank] = path slot
+#define BRT_HITSORT_CELL_BITS 6
+#define BRT_HITSORT_BINS ((1u << (3 * BRT_HITSORT_CELL_BITS)) + 1u)  // + one bin for misses and padding slots
+struct HitSortParams {
+  uint32_t count;
+  const uint32_t* count_ptr;
+  const float4* o;
+  const float4* d;
+  const uint32_t* px;
+  const float4* hit;
+  const uint32_t* hit_inst;
+  const FrameConsts* fc;
+  uint32_t* key;    // per path slot
+  uint32_t* rank;   // per path slot
+  uint32_t* bins;   // BRT_HITSORT_BINS counters, zeroed before k_hit_keys, scanned before k_hit_order
+  uint32_t* order;  // out
+};
+BRT_HD uint32_t spread_bits3(uint32_t v) {  // 10 bits -> every third bit
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+BRT_HD uint32_t hit_sort_key(const HitSortParams& p, uint32_t i) {
+  if (p.px[i] == BRT_MISS || p.hit_inst[i] == BRT_MISS) return BRT_HITSORT_BINS - 1u;
+  const float4 o = p.o[i], d = p.d[i];
+  const float t = p.hit[i].x;
+  const float top = (float)((1u << BRT_HITSORT_CELL_BITS) - 1u);
+  const float cx = fminf(fmaxf((o.x + d.x * t - p.fc->scene_lo[0]) * p.fc->scene_inv[0], 0.0f), top);
+  const float cy = fminf(fmaxf((o.y + d.y * t - p.fc->scene_lo[1]) * p.fc->scene_inv[1], 0.0f), top);
+  const float cz = fminf(fmaxf((o.z + d.z * t - p.fc->scene_lo[2]) * p.fc->scene_inv[2], 0.0f), top);
+  return spread_bits3((uint32_t)cx) | (spread_bits3((uint32_t)cy) << 1) | (spread_bits3((uint32_t)cz) << 2);
+}
+BRT_HD void hit_order_body(const HitSortParams& p, uint32_t i) { p.order[p.bins[p.key[i]] + p.rank[i]] = i; }
 
 // ---- accumulate ------------------------------------------------------------------------------------
 // `c += payload.color * weight` (SH/raytracing.slang:122), deferred: round r of sample-in-batch s of a slot writes its

@@ -128,6 +128,10 @@ typedef struct brt_config {
  * are full (the builder's first rule) instead of the area-optimal choice of wide nodes (build_kernels.cuh, wide_cost_body).
  * Same frames (results never depend on the BVH's shape), more and emptier nodes. */
 #define BRT_CFG_GREEDY_COLLAPSE 32u
+/* Opt-in: bounce rounds shade their paths in the order of the hit positions (counting sort by the cell of the hit on a 64^3 grid
+ * over the scene), so that the shadow and bounce rays they emit start at neighbouring origins. Frames are bit-identical either way.
+ * Measured on B200 (profiles/r2_traversal.md): traversal -0..4 %, shade + sort +2 ms on C5 — a loss, hence off by default. */
+#define BRT_CFG_HIT_SORT 64u
 
 /* render mode flags. With none of the BOUNCE flags set the behaviour is the reference's live path:
  * direct light + hard shadows, weight = 0 after the first hit (SH/raytracing.slang:168). */

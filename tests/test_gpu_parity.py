@@ -123,6 +123,22 @@ def test_repeatable(pkg, make):
     assert np.array_equal(i1.view(np.uint32), i2.view(np.uint32))
 
 
+def test_hit_sort_changes_nothing_but_the_order_of_work(pkg, make):
+    """BRT_CFG_HIT_SORT (bounce rounds shaded in the order of their hit positions): same bits, same ray counts, with and without a frame graph."""
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a, b, c = make(), make(pkg.CFG_HIT_SORT), make(pkg.CFG_HIT_SORT | pkg.CFG_NO_GRAPH)
+    for x in (a, b, c):
+        scene.upload(x)
+    u = scene.uniform(a, 192, 108, 3, 6)
+    flags = pkg.BOUNCE_REFLECT | pkg.BOUNCE_REFRACT | pkg.BOUNCE_DIFFUSE | pkg.JITTER
+    ia = a.render_frame(u, a.opts(192, 108, 3, flags))
+    for x in (b, c, b):
+        ix = x.render_frame(u, x.opts(192, 108, 3, flags))
+        assert np.array_equal(ia.view(np.uint32), ix.view(np.uint32))
+        sa, sx = a.get_stats(), x.get_stats()
+        assert (sa.rays_closest, sa.rays_occlusion) == (sx.rays_closest, sx.rays_occlusion)
+
+
 @pytest.mark.parametrize("n,bits", [(1, 30), (2, 30), (31, 8), (4096, 30), (4097, 30), (100003, 30), (262144, 30), (262145, 30), (1 << 20, 32), (333333, 16)])
 def test_radix_sort_pairs(pkg, make, n, bits):
     """The builder's own radix sort: sorted by the low `bits` bits, stable, a permutation of the input."""

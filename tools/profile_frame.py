@@ -22,12 +22,15 @@ def main():
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--greedy-collapse", action="store_true")
+    ap.add_argument("--hit-sort", action="store_true", help="bounce rounds shaded in the order of their hit positions (BRT_CFG_HIT_SORT)")
+    ap.add_argument("--graph", action="store_true", help="product schedule: two streams + replayed frame graph (total time only)")
+    ap.add_argument("--spp", type=int, default=0, help="override the config's samples per pixel")
     args = ap.parse_args()
     pkg = importlib.import_module("hardware-ray-tracer_b200")
     cfg = dict(pkg.scenes.CONFIGS[args.config])
     scene = pkg.scenes.make_scene(cfg.pop("scene"), small=args.small)
     # per-kernel event times need individually launched kernels
-    flags = (pkg.CFG_NO_GRAPH | (pkg.CFG_COUNTERS if args.counters else 0) | (pkg.CFG_NO_TREELET if args.no_treelet else 0)
+    flags = ((0 if args.graph else pkg.CFG_NO_GRAPH) | (pkg.CFG_HIT_SORT if args.hit_sort else 0) | (pkg.CFG_COUNTERS if args.counters else 0) | (pkg.CFG_NO_TREELET if args.no_treelet else 0)
              | (pkg.CFG_NO_OVERLAP if args.no_overlap else 0) | (pkg.CFG_GREEDY_COLLAPSE if args.greedy_collapse else 0))
     ctx = pkg.Context(device=0, flags=flags)
     t0 = time.perf_counter()
@@ -38,6 +41,8 @@ def main():
            "sah": st.sah_cost, "sah_lbvh": st.sah_cost_lbvh, "frames": []}
     w, h = cfg["width"], cfg["height"]
     u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
+    if args.spp:
+        cfg["spp"] = args.spp
     for f in range(args.frames):
         ctx.render_frame(u, ctx.opts(w, h, cfg["spp"], cfg["flags"]), want_image=False)
         s = ctx.get_stats()
