@@ -98,7 +98,7 @@ BRT_SYMBOLS = [
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
     "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_denoise_configure", "brt_render_frame_peers_async", "brt_get_light_bvh",
-    "brt_debug_get_blas",
+    "brt_debug_get_blas", "brt_gather_configure", "brt_gather_wait", "brt_gather_release", "brt_gather_copy_to_host", "brt_gather_timed_out",
 ]
 
 
@@ -167,7 +167,12 @@ class SceneApi:
             "gather_image_export": (C.c_int, [vp, u32, u32, vp]),
             "gather_image_open": (C.c_int, [vp, vp, u32]),
             "render_frame_peers": (C.c_int, [vp, P(Uniform), P(RenderOpts)]),
-            "gather_image": (vp, [vp]),
+            "gather_image": (vp, [vp, u32]),
+            "gather_configure": (C.c_int, [vp, u32, u32]),
+            "gather_wait": (C.c_int, [vp, u32, vp]),
+            "gather_release": (C.c_int, [vp, u32, vp]),
+            "gather_copy_to_host": (C.c_int, [vp, u32, vp, vp]),
+            "gather_timed_out": (C.c_int, [vp]),
             "render_frame_peers_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32]),
             "denoise_configure": (C.c_int, [vp, P(DenoiseOpts)]),
             "render_frame_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32, vp]),
@@ -404,5 +409,20 @@ class SceneApi:
     def render_frame_peers_async(self, uniform, opts, slot):
         self._ck(self._f("render_frame_peers_async")(self.ctx, C.byref(uniform), C.byref(opts), slot))
 
-    def gather_image(self):
-        return self._f("gather_image")(self.ctx)
+    def gather_image(self, slot):
+        return self._f("gather_image")(self.ctx, slot)
+
+    def gather_configure(self, root_only, root=0):
+        self._ck(self._f("gather_configure")(self.ctx, 1 if root_only else 0, root))
+
+    def gather_wait(self, slot, stream_ptr=None):
+        self._ck(self._f("gather_wait")(self.ctx, slot, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def gather_release(self, slot, stream_ptr=None):
+        self._ck(self._f("gather_release")(self.ctx, slot, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def gather_copy_to_host(self, slot, host_ptr, stream_ptr=None):
+        self._ck(self._f("gather_copy_to_host")(self.ctx, slot, C.c_void_p(host_ptr), C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def gather_timed_out(self):
+        return self._f("gather_timed_out")(self.ctx)

@@ -132,6 +132,69 @@ BRT_KERNEL_1D(k_accumulate, AccumParams, accumulate_body)
 BRT_KERNEL_1D(k_sum_samples, SumSamplesParams, sum_samples_body)
 BRT_KERNEL_1D(k_resolve, ResolveParams, resolve_body)
 BRT_KERNEL_1D(k_untile, UntileParams, untile_body)
+#ifndef BRT_EMU
+// ---- fused multi-GPU exchange: resolve + peer stores + device-side completion flags (GatherFlags, render_kernels.cuh) -------------
+#ifndef BRT_GATHER_TIMEOUT_NS
+#define BRT_GATHER_TIMEOUT_NS 20000000000ull  // a wait gives up after 20 s (a rank died or never submitted the frame) instead of hanging the GPU
+#endif
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// lane k < n spins until flags[k] has reached seq (sequence numbers compared modulo 2^32)
+__device__ void wait_flags(const uint32_t* flags, uint32_t n, uint32_t seq, uint32_t* timeout_flag) {
+  if (threadIdx.x < n) {
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - seq) < 0) {
+      if (global_ns() - t0 > BRT_GATHER_TIMEOUT_NS) {
+        *timeout_flag = 1u;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+}
+// producer, inside the frame: the receivers [first, first + n) must have released the previous frame of this gather image
+__global__ void __launch_bounds__(32) k_gather_wait_consumed(GatherFlags* mine, uint32_t img, const FrameConsts* fc, uint32_t first, uint32_t n) {
+  wait_flags(&mine->consumed[img][first], n, fc->gather_seq - 1u, &mine->timeout);
+}
+// receiver, on the stream that reads the image: every rank's pixels of frame `seq` of this gather image have landed
+__global__ void __launch_bounds__(32) k_gather_wait_arrive(GatherFlags* mine, uint32_t img, uint32_t seq, uint32_t n_src) {
+  wait_flags(&mine->arrive[img][0], n_src, seq, &mine->timeout);
+}
+struct GatherReleaseParams {
+  GatherFlags* peer_flags[BRT_MAX_PEERS];
+  uint32_t n, img, seq, me;
+};
+// receiver: frame `seq` of this gather image has been read, the producers may overwrite it
+__global__ void __launch_bounds__(32) k_gather_release(const GatherReleaseParams p) {
+  if (threadIdx.x < p.n) st_release_sys(&p.peer_flags[threadIdx.x]->consumed[p.img][p.me], p.seq);
+}
+// resolve + exchange in one kernel: every owned pixel goes to the local image and, through NVLink peer stores, to the receivers' gather
+// images; the block that finishes last publishes arrive[img][rank] = seq in every receiver's flag block.
+__global__ void __launch_bounds__(256) k_resolve_peers(const ResolveParams p) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.count; i += stride) resolve_body(p, i);
+  __threadfence_system();  // this thread's peer stores are ordered before the block's arrival below, at system scope
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(p.done, 1u);
+    if (prev == gridDim.x - 1u) {
+      __threadfence_system();
+      *p.done = 0u;  // for the next frame of this slot (replayed graph)
+      const uint32_t seq = p.fc->gather_seq;
+      for (uint32_t k = 0; k < p.n_peers; ++k) st_release_sys(&p.peer_flags[k]->arrive[p.img][p.rank], seq);
+    }
+  }
+}
+#endif
 BRT_KERNEL_1D(k_present, PresentParams, present_body)
 BRT_KERNEL_1D(k_dn_temporal, DnTemporalParams, dn_temporal_body)
 BRT_KERNEL_1D(k_dn_atrous, DnAtrousParams, dn_atrous_body)
@@ -299,7 +362,10 @@ struct FrameSlot {
   cudaEvent_t ev_dn[2] = {nullptr, nullptr};
   bool has_denoised = false;
   uint32_t dn_launches = 0;
-  uint32_t gather_img = 0;  // fused multi-GPU exchange: the gather image this slot's frame stored into
+  uint32_t gather_img = 0;  // fused multi-GPU exchange: the gather image this slot's frame stored into (= the slot's index)
+  uint32_t gather_seq = 0;  // ... and that frame's sequence number on the image
+  uint32_t gather_format = 0;
+  DevBuf d_resolve_done;    // block arrival counter of k_resolve_peers
   bool has_gbuffer = false;
   uint32_t render_flags = 0;  // of the frame rendered last on this slot
   DevBuf d_sort_key, d_sort_rank, d_sort_order, d_sort_bins;  // hit sort of the bounce rounds
@@ -358,11 +424,14 @@ struct brt_context {
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
   // fused resolve + exchange: own gather image and the peers' (opened through cudaIpc)
-  DevBuf d_gather;  // TWO full frames back to back (one allocation, one IPC handle): frames alternate between them
+  DevBuf d_gather;  // BRT_GATHER_IMAGES full frames back to back + one GatherFlags block (one allocation, one IPC handle): slot k uses image k
   uint32_t gather_w = 0, gather_h = 0, n_peers = 0;
-  uint32_t gather_next = 0, gather_last = 0;  // image the next brt_render_frame_peers writes / the last one wrote
+  uint32_t gather_next = 0;                       // slot the next synchronous brt_render_frame_peers uses
+  uint32_t gather_seq[BRT_GATHER_IMAGES] = {0};   // frames submitted so far per gather image (every rank counts the same)
+  uint32_t gather_root_only = 0, gather_root = 0; // brt_gather_configure: who receives the pixels
   void* peer_images[BRT_MAX_PEERS] = {nullptr};
   bool peer_opened[BRT_MAX_PEERS] = {false};
+  cudaStream_t gather_stream = nullptr;           // default stream of brt_gather_wait / release / copy_to_host
   // denoiser history (Graphics/Denoiser/Denoiser.h): accumulated colour + history length, luminance moments, last G-buffer, camera
   DevBuf dn_work[2], dn_hist_color[2], dn_hist_mom[2], dn_h_nrm, dn_h_inst, dn_h_t;
   uint32_t dn_w = 0, dn_h = 0, dn_parity = 0;
@@ -933,7 +1002,8 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   // buffers that only some frames need are sized before any stream work (nothing below may allocate: the frame may be captured)
   const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
   if (format > BRT_FORMAT_B8G8R8A8_SRGB) invalid("render_frame: unknown BRT_RENDER_FORMAT");
-  if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && c->tile_world > 1) invalid("render_frame: 8-bit output formats need tile_world == 1");
+  if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && c->tile_world > 1 && !to_peers)
+    invalid("render_frame: with tile_world > 1 the 8-bit output formats need the fused exchange (brt_render_frame_peers*)");
   const bool denoise = (o.flags & BRT_RENDER_DENOISE) != 0u;
   if (denoise && c->tile_world > 1) invalid("render_frame: BRT_RENDER_DENOISE needs tile_world == 1");
   f->has_gbuffer = (o.flags & (BRT_RENDER_GBUFFER | BRT_RENDER_DENOISE)) != 0u;
@@ -945,7 +1015,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
       f->d_aov_pos.ensure(npx * 16);
       f->d_aov_nrm.ensure(npx * 16);
     }
-    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) f->d_image8.ensure(npx * 4);
+    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && !to_peers) f->d_image8.ensure(npx * 4);
     if (before[0] != f->d_aov_pos.ptr() || before[1] != f->d_aov_nrm.ptr() || before[2] != f->d_image8.ptr()) f->generation++;
   }
   // per-frame constants: staged in pinned memory, copied by the first node of the frame
@@ -967,7 +1037,17 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   // The stream work of the frame (about 45 dependent kernel launches, memsets and event records for C2) is captured into a CUDA
   // graph the first time a frame shape is seen on this slot and replayed afterwards: everything that changes from frame to frame
   // travels through FrameConsts, queue sizes already live on the device.
-  const uint32_t gimg = to_peers ? c->gather_next : 0u;  // gather image this frame's resolve stores into (two alternate)
+  const uint32_t gimg = to_peers ? (uint32_t)(f - c->slots) : 0u;  // gather image this frame's resolve stores into: the slot's own
+  if (to_peers) {
+    if (gimg >= BRT_GATHER_IMAGES) invalid("render_frame_peers: slot >= BRT_GATHER_IMAGES");
+    if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
+    if (!f->d_resolve_done.ptr()) {
+      f->d_resolve_done.ensure(16);
+      BRT_CUDA(cudaMemsetAsync(f->d_resolve_done.ptr(), 0, 16, c->stream));
+      BRT_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    f->h_consts->gather_seq = ++c->gather_seq[gimg];
+  }
   auto enqueue = [&]() {
     BRT_CUDA(cudaMemcpyAsync(f->d_consts.ptr(), f->h_consts, sizeof(FrameConsts), cudaMemcpyHostToDevice, s));
     f->events_used = 0;
@@ -1196,19 +1276,41 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
       rp.image = f->d_image.as<float4>();
       rp.tiles = d_tiles_out ? static_cast<float4*>(d_tiles_out) : f->d_tiles.as<float4>();
       rp.n_peers = 0;
+      rp.format = BRT_FORMAT_R32G32B32A32_SFLOAT;
+#ifndef BRT_EMU
       if (to_peers) {
-        if (!c->n_peers || c->gather_w != o.width || c->gather_h != o.height) bad_state("render_frame_peers: gather images not exported / opened for this frame size");
+        // receivers: rank gather_root alone, or everybody (brt_gather_configure)
+        const uint32_t first = c->gather_root_only ? c->gather_root : 0u, n_dst = c->gather_root_only ? 1u : c->n_peers;
+        const size_t img_bytes = npx * 16;
         rp.tiles = nullptr;
-        rp.n_peers = c->n_peers;
-        for (uint32_t k = 0; k < c->n_peers; ++k) rp.peers[k] = static_cast<float4*>(c->peer_images[k]) + (size_t)gimg * npx;
+        rp.n_peers = n_dst;
+        for (uint32_t k = 0; k < n_dst; ++k) {
+          rp.peers[k] = static_cast<char*>(c->peer_images[first + k]) + (size_t)gimg * img_bytes;
+          rp.peer_flags[k] = reinterpret_cast<GatherFlags*>(static_cast<char*>(c->peer_images[first + k]) + (size_t)BRT_GATHER_IMAGES * img_bytes);
+        }
+        rp.format = format;
+        rp.img = gimg;
+        rp.rank = c->tile_rank;
+        rp.done = f->d_resolve_done.as<uint32_t>();
+        rp.fc = f->d_consts.as<FrameConsts>();
+        GatherFlags* mine = reinterpret_cast<GatherFlags*>(static_cast<char*>(c->d_gather.ptr()) + (size_t)BRT_GATHER_IMAGES * img_bytes);
+        Timed t(f, CLS_RESOLVE, s);
+        // the receivers must have released the previous frame of this image before its pixels are overwritten (device-side wait)
+        k_gather_wait_consumed<<<1, 32, 0, s>>>(mine, gimg, rp.fc, first, n_dst);
+        k_resolve_peers<<<grid_for(c, cap, 256, 8), 256, 0, s>>>(rp);
+        BRT_CHECK_LAUNCH();
+        launches += 2;
+      } else
+#endif
+      {
+        Timed t(f, CLS_RESOLVE, s);
+        BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
+        BRT_CHECK_LAUNCH();
+        launches++;
       }
-      Timed t(f, CLS_RESOLVE, s);
-      BRT_LAUNCH_1D(k_resolve, rp, grid_for(c, cap, 256, 8), 256, s);
-      BRT_CHECK_LAUNCH();
-      launches++;
     }
     const uint32_t format = (o.flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
-    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && !denoise) {
+    if (format != BRT_FORMAT_R32G32B32A32_SFLOAT && !denoise && !to_peers) {
       PresentParams pp{(uint32_t)npx, nullptr, format, f->d_image.as<float4>(), f->d_image8.as<uint32_t>()};
       Timed t(f, CLS_RESOLVE, s);
       BRT_LAUNCH_1D(k_present, pp, grid_for(c, (uint32_t)npx, 256, 8), 256, s);
@@ -1233,10 +1335,11 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
                             ((uint64_t)o.crop_w << 32) | o.crop_h, ((uint64_t)rounds << 32) | n_lights, ((uint64_t)f->generation << 32) | c->tlas_count,
                             (uint64_t)c->d_tlas_nodes.ptr(), (uint64_t)c->d_tlas_inst.ptr(), (uint64_t)c->d_inst_shade.ptr(), (uint64_t)c->d_materials.ptr(),
                             (uint64_t)c->d_mat_ext.ptr(), (uint64_t)c->d_lights.ptr(), (uint64_t)c->d_light_bvh.ptr(), (uint64_t)d_tiles_out, (uint64_t)s,
-                            (uint64_t)f->d_consts.ptr(), ((uint64_t)to_peers << 32) | gimg,
-                            to_peers ? (uint64_t)c->peer_images[0] ^ ((uint64_t)c->peer_images[c->n_peers - 1] << 1) : 0};
-  cudaGraphExec_t& gexec = f->graph_exec[gimg];
-  if (use_graph && gexec && std::memcmp(key, f->graph_key[gimg], sizeof(key)) == 0) {
+                            (uint64_t)f->d_consts.ptr(), ((uint64_t)to_peers << 32) | gimg | (c->gather_root_only << 8) | (c->gather_root << 16),
+                            to_peers ? (uint64_t)c->peer_images[0] ^ ((uint64_t)c->peer_images[c->n_peers - 1] << 1) ^ ((uint64_t)f->d_resolve_done.ptr() << 2) : 0};
+  const int gslot = to_peers ? 1 : 0;  // a slot keeps one graph for plain frames and one for frames of the fused exchange
+  cudaGraphExec_t& gexec = f->graph_exec[gslot];
+  if (use_graph && gexec && std::memcmp(key, f->graph_key[gslot], sizeof(key)) == 0) {
     BRT_CUDA(cudaGraphLaunch(gexec, s));
   } else if (use_graph) {
     if (gexec) {
@@ -1262,7 +1365,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
       gexec = nullptr;
       BRT_CUDA(ie);
     }
-    std::memcpy(f->graph_key[gimg], key, sizeof(key));
+    std::memcpy(f->graph_key[gslot], key, sizeof(key));
     BRT_CUDA(cudaGraphLaunch(gexec, s));
   } else {
     enqueue();
@@ -1270,8 +1373,8 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
 #endif
   if (to_peers) {
     f->gather_img = gimg;
-    c->gather_last = gimg;
-    c->gather_next = gimg ^ 1u;
+    f->gather_seq = c->gather_seq[gimg];
+    f->gather_format = format;
   }
   c->prev_head = f->ev_head;
   // Denoiser stages and the present conversion of a denoised frame follow the (replayed) frame as ordinary stream work: their
@@ -1445,6 +1548,7 @@ void brt_destroy(brt_context* c) {
   for (int k = 0; k < 3; ++k)
     if (c->ev_t[k]) cudaEventDestroy(c->ev_t[k]);
   if (c->dn_event) cudaEventDestroy(c->dn_event);
+  if (c->gather_stream) cudaStreamDestroy(c->gather_stream);
   delete c;
 }
 
@@ -1696,7 +1800,6 @@ int brt_render_frame_async(brt_context* c, const brt_uniform* u, const brt_rende
   return guarded(c, [&] {
     if (!u || !o) invalid("render_frame_async: null");
     if (slot >= BRT_FRAMES_IN_FLIGHT) invalid("render_frame_async: slot >= BRT_FRAMES_IN_FLIGHT");
-    if (c->tile_world > 1) bad_state("render_frame_async: single-GPU contexts only (tile_world == 1)");
     BRT_CUDA(cudaSetDevice(c->device));
     FrameSlot* f = &c->slots[slot];
     finish_frame(c, f);  // the fence of this slot (VK/SwapChain.cpp:45-60): its previous frame must be complete
@@ -1770,11 +1873,14 @@ int brt_gather_image_export(brt_context* c, uint32_t width, uint32_t height, voi
 #else
     static_assert(sizeof(cudaIpcMemHandle_t) == BRT_IPC_HANDLE_BYTES, "ipc handle size");
     BRT_CUDA(cudaSetDevice(c->device));
+    wait_all_frames(c);
     close_peers(c);
     c->d_gather.release();  // a fresh allocation: an exported handle stays tied to its allocation
-    c->d_gather.ensure((size_t)width * height * 16 * 2);
-    BRT_CUDA(cudaMemset(c->d_gather.ptr(), 0, (size_t)width * height * 16 * 2));
-    c->gather_next = c->gather_last = 0;
+    const size_t bytes = (size_t)width * height * 16 * BRT_GATHER_IMAGES + sizeof(GatherFlags);
+    c->d_gather.ensure(bytes);
+    BRT_CUDA(cudaMemset(c->d_gather.ptr(), 0, bytes));
+    for (uint32_t k = 0; k < BRT_GATHER_IMAGES; ++k) c->gather_seq[k] = 0;
+    c->gather_next = 0;
     cudaIpcMemHandle_t h;
     BRT_CUDA(cudaIpcGetMemHandle(&h, c->d_gather.ptr()));
     std::memcpy(handle_out, &h, sizeof(h));
@@ -1809,26 +1915,39 @@ int brt_gather_image_open(brt_context* c, const void* handles, uint32_t world) {
   });
 }
 
+int brt_gather_configure(brt_context* c, uint32_t root_only, uint32_t root) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (root >= c->tile_world) invalid("gather_configure: root >= tile_world");
+    for (uint32_t k = 0; k < BRT_GATHER_IMAGES; ++k)
+      if (c->gather_seq[k]) bad_state("gather_configure: call it before the first frame of the exchange (after brt_gather_image_export)");
+    c->gather_root_only = root_only ? 1u : 0u;
+    c->gather_root = root;
+  });
+}
+
 int brt_render_frame_peers(brt_context* c, const brt_uniform* u, const brt_render_opts* o) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
     if (!u || !o) invalid("render_frame_peers: null");
     BRT_CUDA(cudaSetDevice(c->device));
-    wait_all_frames(c);
-    FrameSlot* f = &c->slots[0];
+    FrameSlot* f = &c->slots[c->gather_next];
+    c->gather_next = (c->gather_next + 1u) % BRT_GATHER_IMAGES;
+    finish_frame(c, f);
+    if (c->tables_dirty || c->tlas_dirty) wait_all_frames(c);
     ensure_slot(c, f);
     render_frame_device(c, f, *u, *o, nullptr, true);
     finish_frame(c, f);
   });
 }
 
-// Two frames of the fused exchange in flight (the two gather images): submit on a slot, brt_frame_wait(slot) returns when this
-// rank's stores of that frame have landed; brt_gather_image then refers to the frame waited for last.
+// Frames of the fused exchange in flight: slot k stores into gather image k. brt_frame_wait(slot) returns when this rank's stores of
+// that frame have landed (local completion); whether EVERY rank's have is known on the device (brt_gather_wait).
 int brt_render_frame_peers_async(brt_context* c, const brt_uniform* u, const brt_render_opts* o, uint32_t slot) {
   if (!c) return BRT_ERR_INVALID;
   return guarded(c, [&] {
     if (!u || !o) invalid("render_frame_peers_async: null");
-    if (slot >= 2) invalid("render_frame_peers_async: slot must be 0 or 1 (two gather images)");
+    if (slot >= BRT_GATHER_IMAGES || slot >= BRT_FRAMES_IN_FLIGHT) invalid("render_frame_peers_async: slot >= BRT_GATHER_IMAGES");
     BRT_CUDA(cudaSetDevice(c->device));
     FrameSlot* f = &c->slots[slot];
     finish_frame(c, f);
@@ -1838,9 +1957,100 @@ int brt_render_frame_peers_async(brt_context* c, const brt_uniform* u, const brt
   });
 }
 
-void* brt_gather_image(brt_context* c) {
-  if (!c || !c->d_gather.ptr()) return nullptr;
-  return static_cast<char*>(c->d_gather.ptr()) + (size_t)c->slots[c->last_slot].gather_img * c->gather_w * c->gather_h * 16;
+void* brt_gather_image(brt_context* c, uint32_t slot) {
+  if (!c || !c->d_gather.ptr() || slot >= BRT_GATHER_IMAGES) return nullptr;
+  return static_cast<char*>(c->d_gather.ptr()) + (size_t)slot * c->gather_w * c->gather_h * 16;
+}
+
+#ifndef BRT_EMU
+namespace {
+cudaStream_t gather_stream_of(brt_context* c, void* stream) {
+  if (stream) return static_cast<cudaStream_t>(stream);
+  if (!c->gather_stream) BRT_CUDA(cudaStreamCreateWithFlags(&c->gather_stream, cudaStreamNonBlocking));
+  return c->gather_stream;
+}
+GatherFlags* my_gather_flags(brt_context* c) {
+  return reinterpret_cast<GatherFlags*>(static_cast<char*>(c->d_gather.ptr()) + (size_t)BRT_GATHER_IMAGES * c->gather_w * c->gather_h * 16);
+}
+bool is_receiver(const brt_context* c) { return !c->gather_root_only || c->gather_root == c->tile_rank; }
+void enqueue_gather_wait(brt_context* c, uint32_t slot, cudaStream_t s) {
+  if (slot >= BRT_GATHER_IMAGES || !c->n_peers) invalid("gather_wait: bad slot / gather images not opened");
+  if (!is_receiver(c)) bad_state("gather_wait: this rank does not receive the frame (brt_gather_configure)");
+  k_gather_wait_arrive<<<1, 32, 0, s>>>(my_gather_flags(c), slot, c->gather_seq[slot], c->n_peers);
+  BRT_CHECK_LAUNCH();
+}
+void enqueue_gather_release(brt_context* c, uint32_t slot, cudaStream_t s) {
+  if (slot >= BRT_GATHER_IMAGES || !c->n_peers) invalid("gather_release: bad slot / gather images not opened");
+  if (!is_receiver(c)) bad_state("gather_release: this rank does not receive the frame (brt_gather_configure)");
+  GatherReleaseParams p{};
+  p.n = c->n_peers;
+  p.img = slot;
+  p.seq = c->gather_seq[slot];
+  p.me = c->tile_rank;
+  const size_t off = (size_t)BRT_GATHER_IMAGES * c->gather_w * c->gather_h * 16;
+  for (uint32_t k = 0; k < c->n_peers; ++k) p.peer_flags[k] = reinterpret_cast<GatherFlags*>(static_cast<char*>(c->peer_images[k]) + off);
+  k_gather_release<<<1, 32, 0, s>>>(p);
+  BRT_CHECK_LAUNCH();
+}
+}  // namespace
+#endif
+
+int brt_gather_wait(brt_context* c, uint32_t slot, void* stream) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+#ifdef BRT_EMU
+    (void)slot; (void)stream;
+    bad_state("gather_wait: peer memory needs CUDA devices");
+#else
+    BRT_CUDA(cudaSetDevice(c->device));
+    enqueue_gather_wait(c, slot, gather_stream_of(c, stream));
+#endif
+  });
+}
+
+int brt_gather_release(brt_context* c, uint32_t slot, void* stream) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+#ifdef BRT_EMU
+    (void)slot; (void)stream;
+    bad_state("gather_release: peer memory needs CUDA devices");
+#else
+    BRT_CUDA(cudaSetDevice(c->device));
+    enqueue_gather_release(c, slot, gather_stream_of(c, stream));
+#endif
+  });
+}
+
+int brt_gather_copy_to_host(brt_context* c, uint32_t slot, void* host, void* stream) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+#ifdef BRT_EMU
+    (void)slot; (void)host; (void)stream;
+    bad_state("gather_copy_to_host: peer memory needs CUDA devices");
+#else
+    if (!host) invalid("gather_copy_to_host: null");
+    BRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = gather_stream_of(c, stream);
+    enqueue_gather_wait(c, slot, s);
+    const size_t npx = (size_t)c->gather_w * c->gather_h;
+    const size_t bytes = c->slots[slot].gather_format == BRT_FORMAT_R32G32B32A32_SFLOAT ? npx * 16 : npx * 4;
+    BRT_CUDA(cudaMemcpyAsync(host, brt_gather_image(c, slot), bytes, cudaMemcpyDeviceToHost, s));
+    enqueue_gather_release(c, slot, s);
+#endif
+  });
+}
+
+int brt_gather_timed_out(brt_context* c) {
+#ifdef BRT_EMU
+  (void)c;
+  return 0;
+#else
+  if (!c || !c->d_gather.ptr()) return 0;
+  uint32_t v = 0;
+  cudaSetDevice(c->device);
+  if (cudaMemcpy(&v, &my_gather_flags(c)->timeout, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int)v;
+#endif
 }
 
 int brt_get_aov(brt_context* c, int kind, void* out) {

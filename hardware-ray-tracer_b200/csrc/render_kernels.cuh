@@ -87,6 +87,8 @@ struct FrameConsts {
   uint32_t frame;        // uniform.frame
   uint32_t pad[3];
   brt_sky sky;
+  uint32_t gather_seq;   // fused multi-GPU exchange: number of this frame on its gather image (1, 2, ...), see GatherFlags
+  uint32_t pad2[3];
   float scene_lo[4];     // world bounds of the scene's instances and 64 / extent per axis: the grid of the hit sort (below)
   float scene_inv[4];
 };
@@ -561,7 +563,32 @@ BRT_HD void sum_samples_body(const SumSamplesParams& p, uint32_t i) {
   p.accum[i] = a;
 }
 
+// float4 -> one packed 8-bit texel of a present format (RT/RTPipeline.cpp:49-55), byte 0 first in memory
+BRT_HD uint32_t pack_present(float4 c, uint32_t format) {
+  const bool srgb = format == BRT_FORMAT_R8G8B8A8_SRGB || format == BRT_FORMAT_B8G8R8A8_SRGB;
+  const bool bgra = format == BRT_FORMAT_B8G8R8A8_UNORM || format == BRT_FORMAT_B8G8R8A8_SRGB;
+  const uint32_t r = float_to_unorm8(srgb ? linear_to_srgb(c.x) : c.x);
+  const uint32_t g = float_to_unorm8(srgb ? linear_to_srgb(c.y) : c.y);
+  const uint32_t b = float_to_unorm8(srgb ? linear_to_srgb(c.z) : c.z);
+  const uint32_t a = float_to_unorm8(c.w);
+  return (bgra ? b : r) | (g << 8) | ((bgra ? r : b) << 16) | (a << 24);
+}
+
 // ---- resolve ---------------------------------------------------------------------------------------
+// Fused multi-GPU exchange, completion without the host. Every rank's gather allocation ends in one GatherFlags block that the
+// OTHER ranks write through peer memory:
+//   arrive[img][src]   = n  once rank `src` has stored all its pixels of the n-th frame on gather image `img` into this rank's image
+//                           (written by the last block of src's resolve kernel, release at system scope after every block's fence)
+//   consumed[img][dst] = n  once receiver `dst` has finished reading the n-th frame of image `img` (written by dst's release kernel):
+//                           frame n + 1 of that image waits for it on the device before its resolve kernel may overwrite the pixels
+// A receiver waits for arrive[img][*] >= n with a one-warp kernel on the stream that reads the image (k_gather_wait_arrive). No
+// collective, no host barrier, no stream synchronisation per frame.
+struct GatherFlags {
+  uint32_t arrive[BRT_GATHER_IMAGES][BRT_MAX_PEERS];
+  uint32_t consumed[BRT_GATHER_IMAGES][BRT_MAX_PEERS];
+  uint32_t timeout;  // set by a wait that gave up (a rank died or never submitted the frame)
+  uint32_t pad[3];
+};
 struct ResolveParams {
   uint32_t count;  // slots (tiles owned * 1024)
   const uint32_t* count_ptr;
@@ -570,8 +597,13 @@ struct ResolveParams {
   const float4* accum;  // per slot
   float4* image;   // full frame, row major
   float4* tiles;   // this rank's tiles packed tile-major, row-major inside a tile (may be null)
-  float4* peers[BRT_MAX_PEERS];  // fused exchange: every rank's gather image (peer memory over NVLink), n_peers of them
+  void* peers[BRT_MAX_PEERS];  // fused exchange: the receivers' gather images (peer memory over NVLink), n_peers of them
+  GatherFlags* peer_flags[BRT_MAX_PEERS];  // ... and their flag blocks
   uint32_t n_peers;
+  uint32_t format;       // of the gather images: BRT_FORMAT_R32G32B32A32_SFLOAT or an 8-bit present format (4 bytes per pixel over NVLink)
+  uint32_t img, rank;    // gather image this frame stores into; this rank
+  uint32_t* done;        // block arrival counter of k_resolve_peers
+  const FrameConsts* fc; // gather_seq
 };
 BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
   // unlike the path slots this walks the tile row by row so that both stores coalesce
@@ -587,8 +619,15 @@ BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
   }
   if (inside) p.image[(size_t)y * p.map.width + x] = out;
   if (p.tiles) p.tiles[i] = out;
-  if (inside)
-    for (uint32_t k = 0; k < p.n_peers; ++k) p.peers[k][(size_t)y * p.map.width + x] = out;  // st.global to mapped peer pointers
+  if (inside && p.n_peers) {  // st.global to mapped peer pointers
+    const size_t pix = (size_t)y * p.map.width + x;
+    if (p.format == BRT_FORMAT_R32G32B32A32_SFLOAT) {
+      for (uint32_t k = 0; k < p.n_peers; ++k) static_cast<float4*>(p.peers[k])[pix] = out;
+    } else {
+      const uint32_t texel = pack_present(out, p.format);
+      for (uint32_t k = 0; k < p.n_peers; ++k) static_cast<uint32_t*>(p.peers[k])[pix] = texel;
+    }
+  }
 }
 
 // ---- present: the render output in the swapchain's format (RT/RTPipeline.cpp:49-55, RT/RTApp.cpp:87-152) ---------
@@ -600,14 +639,7 @@ struct PresentParams {
   uint32_t* image8;  // one packed texel per pixel, byte 0 first in memory
 };
 BRT_HD void present_body(const PresentParams& p, uint32_t i) {
-  const float4 c = p.image[i];
-  const bool srgb = p.format == BRT_FORMAT_R8G8B8A8_SRGB || p.format == BRT_FORMAT_B8G8R8A8_SRGB;
-  const bool bgra = p.format == BRT_FORMAT_B8G8R8A8_UNORM || p.format == BRT_FORMAT_B8G8R8A8_SRGB;
-  const uint32_t r = float_to_unorm8(srgb ? linear_to_srgb(c.x) : c.x);
-  const uint32_t g = float_to_unorm8(srgb ? linear_to_srgb(c.y) : c.y);
-  const uint32_t b = float_to_unorm8(srgb ? linear_to_srgb(c.z) : c.z);
-  const uint32_t a = float_to_unorm8(c.w);
-  p.image8[i] = (bgra ? b : r) | (g << 8) | ((bgra ? r : b) << 16) | (a << 24);
+  p.image8[i] = pack_present(p.image[i], p.format);
 }
 
 // ---- un-tile after the framebuffer gather (root rank) ----------------------------------------------------

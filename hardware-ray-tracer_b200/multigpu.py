@@ -1,103 +1,132 @@
 """Tile-parallel rendering over the GPUs of one box.
 
-Every rank (one process per GPU, torch.distributed) holds a replica of the scene and a `brt_context`
-created with (tile_rank, tile_world) = (rank, world): it traces only the 32x32 tiles with
-tile_id % world == rank and packs them tile-major. One collective per frame — an all-gather of the
-equal-sized packed tile buffers (NCCL over NVLink on GPUs; gloo in the CPU tests) — then the un-tile
-kernel rebuilds the row-major RGBA32F frame on every rank. Smart-Culling results and the BVH are identical
-on every rank by construction (same inputs, deterministic builder), so nothing else is exchanged.
+Every rank (one process per GPU, torch.distributed) holds a replica of the scene and a `brt_context` created with
+(tile_rank, tile_world) = (rank, world): it traces only the 32x32 tiles with tile_id % world == rank. Smart-Culling results and
+the BVH are identical on every rank by construction (same inputs, deterministic builder), so only finished pixels cross GPUs.
 
 Two exchange modes:
-  "nccl"  brt_render_frame_tiles -> all_gather_into_tensor (NCCL over NVLink; gloo in the CPU tests) -> brt_untile
-  "p2p"   brt_render_frame_peers: the resolve kernel itself stores every owned pixel into all ranks' gather images through
-          cudaIpc-mapped peer memory (NVLink stores inside the producing kernel), then one barrier. No collective moves
-          pixels, no un-tile pass.
+  "nccl"  brt_render_frame_tiles packs the rank's tiles tile-major -> all_gather_into_tensor (NCCL over NVLink; gloo in the CPU
+          tests) -> brt_untile rebuilds the row-major frame on every rank.
+  "p2p"   fused: the resolve kernel of brt_render_frame_peers_async stores every owned pixel straight into the RECEIVERS' gather
+          images through cudaIpc-mapped peer memory (NVLink stores inside the producing kernel; RGBA32F or the 8-bit present
+          format), and publishes a per-frame sequence number in their flag blocks. Receivers = rank `root` only (root_only=True,
+          what the north star asks for: "gather the framebuffer") or every rank. Completion is checked ON THE DEVICE: a receiver
+          enqueues a one-warp wait kernel on the stream that reads the image and a release kernel behind its read; a producer's
+          resolve kernel waits on the device for the release of the frame it is about to overwrite. No collective, no host
+          barrier, no stream synchronisation per frame; up to N_IMAGES frames in flight per rank (slot k <-> gather image k).
+          Rule: every rank submits the same frames on the same slots in the same order; a receiver fetches or releases every frame.
 """
 import ctypes
 
 import torch
 import torch.distributed as dist
 
+N_IMAGES = 4  # BRT_GATHER_IMAGES (include/brt.h)
+
 
 class TiledFrame:
-    """Per-rank buffers + the gather / un-tile step for frames of one size."""
+    """Per-rank buffers + the exchange step for frames of one size."""
 
-    def __init__(self, ctx, width, height, rank, world, device, group=None, mode="nccl"):
+    def __init__(self, ctx, width, height, rank, world, device, group=None, mode="nccl", root_only=False, root=0):
         self.ctx, self.width, self.height, self.rank, self.world, self.group = ctx, width, height, rank, world, group
         self.mode = mode if world > 1 else "nccl"
+        self.root_only, self.root = bool(root_only), root
+        self.device = device
         if self.mode == "p2p":
             mine = ctx.gather_image_export(width, height)
             handles = [None] * world
             dist.all_gather_object(handles, mine, group=group)
             ctx.gather_image_open(handles)
-            dist.barrier(group=group)
-            self._barrier_token = torch.zeros(1, dtype=torch.int32, device=device)
-            self._rt = ctypes.CDLL("libcudart.so")
+            ctx.gather_configure(root_only, root)
+            dist.barrier(group=group)  # set-up only: everybody's images are mapped before the first peer store
             self._copy_stream = torch.cuda.Stream(device=device)
-            self._copy_pending = False
-        n = ctx.tile_buffer_bytes(width, height, world) // 4
-        self.tiles = torch.zeros(n, dtype=torch.float32, device=device)
-        self.gathered = torch.zeros(n * world, dtype=torch.float32, device=device) if world > 1 else self.tiles
-        self.image = torch.zeros(height * width * 4, dtype=torch.float32, device=device)
+            self._fetch_events = {}
+            self._next = 0
+            self._held = None
+        else:
+            if device.type == "cuda":
+                # brt_untile and the tile packing run on the library's stream, the all-gather on torch's current stream: make them
+                # the same stream so that pack -> all-gather -> un-tile -> consumer are ordered without host synchronisation
+                ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
+            n = ctx.tile_buffer_bytes(width, height, world) // 4
+            self.tiles = torch.zeros(n, dtype=torch.float32, device=device)
+            self.gathered = torch.zeros(n * world, dtype=torch.float32, device=device) if world > 1 else self.tiles
+            self.image = torch.zeros(height * width * 4, dtype=torch.float32, device=device)
 
+    @property
+    def receives(self):
+        return self.mode != "p2p" or not self.root_only or self.rank == self.root
+
+    # ---- synchronous convenience (tests, single frames) ---------------------------------------------------------------------
     def render(self, uniform, opts):
-        """Traces this rank's tiles, gathers everybody's, returns the full (H, W, 4) frame (a view of self.image)."""
+        """Traces this rank's tiles and exchanges them. nccl: returns the full (H, W, 4) frame (a view of self.image). p2p: returns
+        None; on a receiver the complete frame is at frame_ptr() until the next render() (which releases it)."""
         assert opts.width == self.width and opts.height == self.height
         if self.mode == "p2p":
-            self.ctx.render_frame_peers(uniform, opts)               # returns when this rank's peer stores have landed
-            self.wait_host()  # an asynchronous copy-out of the previous frame must be done before anybody may pass the barrier:
-            #                   the frame after this one overwrites that gather image
-            dist.all_reduce(self._barrier_token, group=self.group)  # barrier: everybody's have
-            torch.cuda.current_stream().synchronize()
-            return None  # the frame is brt_gather_image(ctx) (device memory owned by the library); see frame_ptr()
+            if self._held is not None and self.receives:
+                self.ctx.gather_release(self._held)
+            slot = self._next
+            self._next = (self._next + 1) % N_IMAGES
+            self.ctx.render_frame_peers_async(uniform, opts, slot)
+            self.ctx.frame_wait(slot)  # this rank's stores have landed
+            if self.receives:
+                s = torch.cuda.current_stream(self.device)
+                self.ctx.gather_wait(slot, s.cuda_stream)  # ... and, on the device, everybody's
+                s.synchronize()
+            self._held = slot
+            return None
         self.ctx.render_frame_tiles(uniform, opts, self.tiles.data_ptr())
         if self.world > 1:
             dist.all_gather_into_tensor(self.gathered, self.tiles, group=self.group)
         self.ctx.untile(self.gathered.data_ptr(), self.width, self.height, self.world, self.image.data_ptr())
         return self.image.view(self.height, self.width, 4)
 
-    def submit(self, uniform, opts, slot):
-        """p2p mode, two frames in flight: enqueues the frame on slot 0 / 1 (it stores into the gather image of that parity on every
-        rank) and returns. Every rank must submit the same frames in the same order and complete() them in that order."""
-        assert self.mode == "p2p" and opts.width == self.width and opts.height == self.height
-        self.ctx.render_frame_peers_async(uniform, opts, slot)
-
-    def complete(self, slot):
-        """Waits for this rank's stores of the slot's frame, then the barrier that makes every rank's gather image of that frame
-        complete (an asynchronous copy-out of the frame before it — the image the NEXT submit will overwrite — is finished first)."""
-        self.ctx.frame_wait(slot)
-        self.wait_host()
-        dist.all_reduce(self._barrier_token, group=self.group)
-        torch.cuda.current_stream().synchronize()
-
     def frame_ptr(self):
-        """Device pointer of the complete row-major RGBA32F frame of the last render()."""
-        return self.ctx.gather_image() if self.mode == "p2p" else self.image.data_ptr()
-
-    def to_host_async(self, host):
-        """p2p mode: starts copying the complete frame of the last render() into `host` (pinned) on a side stream and returns; the
-        library alternates between two gather images, so the copy may run while the next frame is traced. wait_host() (also
-        called by the next render() before its barrier) completes it."""
-        assert self.mode == "p2p"
-        rc = self._rt.cudaMemcpyAsync(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(self.ctx.gather_image()),
-                                      ctypes.c_size_t(self.height * self.width * 16), 2, ctypes.c_void_p(self._copy_stream.cuda_stream))
-        if rc != 0:
-            raise RuntimeError(f"cudaMemcpyAsync failed: {rc}")
-        self._copy_pending = True
-
-    def wait_host(self):
-        if self.mode == "p2p" and self._copy_pending:
-            self._copy_stream.synchronize()
-            self._copy_pending = False
+        """Device pointer of the complete row-major frame of the last render()."""
+        return self.ctx.gather_image(self._held) if self.mode == "p2p" else self.image.data_ptr()
 
     def to_host(self, host):
-        """Copies the complete frame of the last render() into `host` (a pinned float32 tensor of h*w*4 elements)."""
+        """Copies the complete frame of the last render() into `host` (pinned tensor: RGBA32F, or 4 bytes per pixel for an 8-bit format)."""
         if self.mode == "p2p":
             rt = ctypes.CDLL("libcudart.so")
-            rc = rt.cudaMemcpy(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(self.ctx.gather_image()),
-                               ctypes.c_size_t(self.height * self.width * 16), 2)  # cudaMemcpyDeviceToHost
+            rc = rt.cudaMemcpy(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(self.frame_ptr()), ctypes.c_size_t(host.numel() * host.element_size()), 2)
             if rc != 0:
                 raise RuntimeError(f"cudaMemcpy failed: {rc}")
         else:
             host.copy_(self.image, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+
+    # ---- frames in flight (p2p) ----------------------------------------------------------------------------------------------
+    def submit(self, uniform, opts, slot):
+        """Enqueues the frame on slot 0 .. N_IMAGES-1 (it stores into gather image `slot` of every receiver) and returns. The slot's
+        previous frame must have been fetched / released by the receivers — the resolve kernel waits for that on the device."""
+        assert self.mode == "p2p" and opts.width == self.width and opts.height == self.height
+        self.ctx.render_frame_peers_async(uniform, opts, slot)
+
+    def fetch_async(self, slot, host):
+        """Receiver: on the copy stream, wait (device-side) until every rank's pixels of the slot's latest frame have landed, copy the
+        frame to `host` (pinned), release the image. Returns at once; wait_fetch(slot) completes it."""
+        assert self.mode == "p2p" and self.receives
+        with torch.cuda.stream(self._copy_stream):
+            self.ctx.gather_copy_to_host(slot, host.data_ptr(), self._copy_stream.cuda_stream)
+            e = torch.cuda.Event()
+            e.record(self._copy_stream)
+        self._fetch_events[slot] = e
+
+    def release(self, slot):
+        """Receiver that does not copy the frame out: wait for it and release it (on the copy stream)."""
+        assert self.mode == "p2p" and self.receives
+        self.ctx.gather_wait(slot, self._copy_stream.cuda_stream)
+        self.ctx.gather_release(slot, self._copy_stream.cuda_stream)
+
+    def wait_fetch(self, slot=None):
+        if self.mode != "p2p":
+            return
+        for k in ([slot] if slot is not None else list(self._fetch_events)):
+            e = self._fetch_events.pop(k, None)
+            if e is not None:
+                e.synchronize()
+
+    def check(self):
+        if self.mode == "p2p" and self.ctx.gather_timed_out():
+            raise RuntimeError("fused exchange: a device-side wait timed out (a rank did not submit or release a frame)")

@@ -274,8 +274,8 @@ BRT_API int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_r
  * the copy to rgba_host (pinned memory for a truly asynchronous copy; NULL = leave it on the device) — and returns.
  * brt_frame_wait(slot) returns when that frame and its copy are complete and folds its timings into brt_get_stats.
  * The latency-bound tail of one frame's wavefronts then overlaps the head of the next one. Scene-changing calls
- * (build, mesh update, Smart Culling) drain all slots first. Single-GPU contexts only (tile_world == 1). */
-#define BRT_FRAMES_IN_FLIGHT 3 /* slots available; the reference uses 2, a third lets the copy-out of frame k-2 finish while k is submitted */
+ * (build, mesh update, Smart Culling) drain all slots first. With tile_world > 1 the image holds this rank's tiles only. */
+#define BRT_FRAMES_IN_FLIGHT 4 /* slots available; the reference uses 2; more let the latency-bound tail of small frames (one rank's share of a tiled frame) overlap */
 BRT_API int brt_render_frame_async(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, uint32_t slot, float* rgba_host);
 BRT_API int brt_frame_wait(brt_context* ctx, uint32_t slot);
 /* the cudaStream_t a slot's frame is enqueued on (slot 0: the context's stream), e.g. to order caller work after it */
@@ -288,24 +288,36 @@ BRT_API size_t brt_tile_buffer_bytes(uint32_t width, uint32_t height, uint32_t t
 /* after the gather: d_all = tile_world packed buffers back to back (device) -> row-major RGBA32F
  * image at d_rgba (device). */
 BRT_API int brt_untile(brt_context* ctx, const void* d_all, uint32_t width, uint32_t height, uint32_t tile_world, void* d_rgba);
-/* ---- fused resolve + framebuffer exchange over NVLink peer memory -------------------------------------
- * Alternative to brt_render_frame_tiles + NCCL all-gather + brt_untile for the ranks of one box: every rank exports its
- * full-frame "gather image" (cudaIpc handle), opens everybody else's, and the resolve kernel of brt_render_frame_peers
- * stores each pixel this rank owns straight into ALL ranks' gather images (row-major RGBA32F, the final layout) with
- * peer stores — the exchange happens inside the producing kernel, no collective, no un-tile pass. After the call returns
- * this rank's stores have landed; a barrier among the ranks (any kind) makes every gather image complete. Every rank keeps TWO
- * gather images (one allocation, one handle) and consecutive frames alternate between them, so the frame of call k stays valid —
- * e.g. while it is copied to the host — until call k+2; the barrier of call k+1 must not be entered before such a reader is done. */
-#define BRT_IPC_HANDLE_BYTES 64
+/* Fused framebuffer exchange for the ranks of one box (the alternative to brt_render_frame_tiles + NCCL all-gather + brt_untile):
+ * every rank exports one allocation holding BRT_GATHER_IMAGES full-frame "gather images" and a block of completion flags (a cudaIpc
+ * handle), opens everybody else's, and the resolve kernel of brt_render_frame_peers* stores each pixel this rank owns straight into
+ * the RECEIVERS' gather images — row-major, the final layout, RGBA32F or the 8-bit present format of opts.flags — with st.global on
+ * the mapped peer pointers over NVLink. Receivers are all ranks (default) or one root rank (brt_gather_configure; the north star only
+ * asks for the frame on one rank). Completion needs no collective and no host barrier: the last block of a rank's resolve kernel
+ * publishes a sequence number in every receiver's flag block (release at system scope); a receiver enqueues brt_gather_wait on the
+ * stream that reads the image, reads it, and enqueues brt_gather_release, which lets the producers overwrite that image BRT_GATHER_IMAGES
+ * frames later (their resolve kernels wait for it on the device). Slot k of brt_render_frame_peers_async uses gather image k, so up to
+ * BRT_GATHER_IMAGES frames are in flight per rank. Every rank must submit the same frames on the same slots in the same order; a
+ * receiver must release every frame it receives. A wait gives up after 20 s (brt_gather_timed_out) instead of hanging the GPU.
+ * Replaces nothing in the reference (single GPU, VK/Device.cpp:388-389); it is the tile split the north star names. */
+#define BRT_GATHER_IMAGES 4
+#define BRT_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 BRT_API int brt_gather_image_export(brt_context* ctx, uint32_t width, uint32_t height, void* handle_out);
-/* handles: tile_world x BRT_IPC_HANDLE_BYTES, in rank order (this rank's own entry is ignored) */
+/* handles: tile_world handles of BRT_IPC_HANDLE_BYTES bytes each, in rank order (the own one is ignored) */
 BRT_API int brt_gather_image_open(brt_context* ctx, const void* handles, uint32_t world);
+/* root_only != 0: only rank `root` receives the pixels; before the first frame of the exchange */
+BRT_API int brt_gather_configure(brt_context* ctx, uint32_t root_only, uint32_t root);
+/* synchronous: next slot in turn, returns when this rank's stores have landed (the receivers' view: brt_gather_wait) */
 BRT_API int brt_render_frame_peers(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts);
-/* the same on frame slot 0 or 1 without waiting: two frames (the two gather images) may be in flight; brt_frame_wait(slot) returns
- * when this rank's stores of the slot's frame have landed. Ranks must submit the same frames in the same order. */
 BRT_API int brt_render_frame_peers_async(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, uint32_t slot);
-/* device pointer of the complete gathered frame of the slot waited for last */
-BRT_API void* brt_gather_image(brt_context* ctx);
+/* receiver side, for the frame submitted last on `slot`; stream = a cudaStream_t, NULL = the library's own gather stream */
+BRT_API int brt_gather_wait(brt_context* ctx, uint32_t slot, void* stream);
+BRT_API int brt_gather_release(brt_context* ctx, uint32_t slot, void* stream);
+/* wait + copy of the gather image (16 or 4 bytes per pixel) to host memory + release, all on `stream` */
+BRT_API int brt_gather_copy_to_host(brt_context* ctx, uint32_t slot, void* host, void* stream);
+BRT_API int brt_gather_timed_out(brt_context* ctx);
+/* device pointer of gather image `slot` (complete once brt_gather_wait has passed on the reading stream) */
+BRT_API void* brt_gather_image(brt_context* ctx, uint32_t slot);
 /* device pointer of the context's own full-frame RGBA32F image of the last frame (the slot last waited for) */
 BRT_API void* brt_device_image(brt_context* ctx);
 

@@ -1,5 +1,7 @@
-"""N = 2 on real GPUs (skipped on a single-GPU box): both exchange modes of TiledFrame — NCCL all-gather + un-tile, and
-the fused resolve with peer-memory stores — must reproduce the single-GPU frame bit for bit."""
+"""N >= 2 on real GPUs (skipped on a single-GPU box; `gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py`, log kept under
+profiles/): both exchange modes of TiledFrame — NCCL all-gather + un-tile, and the fused resolve with peer-memory stores and
+device-side completion flags (every rank receives / root only, RGBA32F / 8-bit, four frames in flight, every frame different) —
+must reproduce the single-GPU frames bit for bit."""
 import os
 import socket
 import sys
@@ -30,79 +32,98 @@ def _worker(rank, world, port, out_dir):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     pkg = importlib.import_module("hardware-ray-tracer_b200")
-    ctx = pkg.Context(device=rank, tile_rank=rank, tile_world=world)
-    torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # a real stream: frames are captured into CUDA graphs (two per slot, one per gather image)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # a real stream: frames are captured into CUDA graphs
     scene = pkg.scenes.make_scene("terrain", small=True)
-    scene.upload(ctx)
     w, h = 500, 300
-    u = scene.uniform(ctx, w, h, 0, 3)
-    opts = ctx.opts(w, h, 2, 3)
-    for mode in ("nccl", "p2p"):
-        frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode=mode)
-        for it in range(2):  # twice: the second frame overwrites the first in the same buffers
-            frame.render(u, opts)
-            img = torch.empty(h * w * 4, dtype=torch.float32, device=dev)
-            # copy the frame out through a raw device pointer
-            import ctypes
-            cudart = ctypes.CDLL("libcudart.so")
-            cudart.cudaMemcpy(ctypes.c_void_p(img.data_ptr()), ctypes.c_void_p(frame.frame_ptr()), ctypes.c_size_t(h * w * 16), 3)
-            torch.cuda.synchronize()
-            dist.barrier()  # nobody may start the next frame before everybody has read this one
-        np.save(os.path.join(out_dir, f"{mode}{rank}.npy"), img.cpu().numpy().reshape(h, w, 4))
-        if mode == "p2p":
-            # pipelined copy-out: rank 0 copies frame k to the host on a side stream while frame k+1 is traced (the library
-            # alternates between two gather images; render() completes the previous copy before its barrier)
-            hosts = [torch.empty(h * w * 4, dtype=torch.float32).pin_memory() for _ in range(2)]
-            got = []
-            for k in range(3):
-                frame.render(scene.uniform(ctx, w, h, 10 + k, 3), opts)
-                if rank == 0:
-                    if k > 0:
-                        got.append(hosts[(k - 1) % 2].numpy().reshape(h, w, 4).copy())
-                    frame.to_host_async(hosts[k % 2])
+    flags = 3
+    n_frames = 9  # more than two rounds over the four gather images: every image is overwritten twice
+
+    def uniform(ctx, k):
+        return scene.uniform(ctx, w, h, k, 3)  # the frame number seeds the bounce sampling: every frame is different
+
+    # ---- NCCL all-gather + un-tile: every rank gets every frame
+    ctx = pkg.Context(device=rank, tile_rank=rank, tile_world=world)
+    scene.upload(ctx)
+    frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="nccl")
+    imgs = []
+    for k in range(3):
+        imgs.append(frame.render(uniform(ctx, k), ctx.opts(w, h, 2, flags)).clone())
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, f"nccl{rank}.npy"), torch.stack(imgs).cpu().numpy())
+    ctx.close()
+
+    # ---- fused exchange, every rank receives, synchronous calls
+    ctx = pkg.Context(device=rank, tile_rank=rank, tile_world=world)
+    scene.upload(ctx)
+    frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="p2p")
+    host = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
+    imgs = []
+    for k in range(6):
+        frame.render(uniform(ctx, k), ctx.opts(w, h, 2, flags))
+        frame.to_host(host)
+        imgs.append(host.numpy().reshape(h, w, 4).copy())
+    np.save(os.path.join(out_dir, f"p2p_all{rank}.npy"), np.stack(imgs))
+    frame.check()
+    ctx.close()
+
+    # ---- fused exchange, root only, FOUR frames in flight, no host barrier anywhere: RGBA32F, then B8G8R8A8_UNORM
+    for name, fmt, dtype, per_px in (("f32", 0, torch.float32, 4), ("bgra8", pkg.render_format(pkg.FORMAT_BGRA8_UNORM), torch.uint8, 4)):
+        ctx = pkg.Context(device=rank, tile_rank=rank, tile_world=world)
+        scene.upload(ctx)
+        frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="p2p", root_only=True, root=0)
+        hosts = [torch.empty(h * w * per_px, dtype=dtype).pin_memory() for _ in range(4)]
+        got = [None] * n_frames
+        opts = ctx.opts(w, h, 2, flags | fmt)
+        for k in range(n_frames):
+            slot = k % 4
+            if rank == 0 and k >= 4:  # the host buffer of this slot still holds frame k - 4
+                frame.wait_fetch(slot)
+                got[k - 4] = hosts[slot].numpy().reshape(h, w, per_px).copy()
+            frame.submit(uniform(ctx, 20 + k), opts, slot)
             if rank == 0:
-                frame.wait_host()
-                got.append(hosts[2 % 2].numpy().reshape(h, w, 4).copy())
-                np.save(os.path.join(out_dir, "pipelined.npy"), np.stack(got))
-            # two frames in flight: frame k+1 is submitted before frame k is completed
-            got = []
-            n = 5
-            for k in range(n):
-                frame.submit(scene.uniform(ctx, w, h, 20 + k, 3), opts, k % 2)
-                if k > 0:
-                    frame.complete((k - 1) % 2)
-                    if rank == 0:
-                        frame.to_host(hosts[0])
-                        got.append(hosts[0].numpy().reshape(h, w, 4).copy())
-            frame.complete((n - 1) % 2)
-            if rank == 0:
-                frame.to_host(hosts[0])
-                got.append(hosts[0].numpy().reshape(h, w, 4).copy())
-                np.save(os.path.join(out_dir, "inflight.npy"), np.stack(got))
+                frame.fetch_async(slot, hosts[slot])
+        if rank == 0:
+            for k in range(max(0, n_frames - 4), n_frames):
+                frame.wait_fetch(k % 4)
+                got[k] = hosts[k % 4].numpy().reshape(h, w, per_px).copy()
+            np.save(os.path.join(out_dir, f"root_{name}.npy"), np.stack(got))
+        for k in range(4):
+            ctx.frame_wait(k)
+        frame.check()
+        dist.barrier()
+        ctx.close()
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_gpu_exchange_modes(pkg, tmp_path):
-    world = 2
+    world = min(torch.cuda.device_count(), 4)
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     single = pkg.Context(device=0)
     scene = pkg.scenes.make_scene("terrain", small=True)
     scene.upload(single)
     w, h = 500, 300
-    u = scene.uniform(single, w, h, 0, 3)
-    ref = single.render_frame(u, single.opts(w, h, 2, 3))
-    for mode in ("nccl", "p2p"):
-        for r in range(world):
-            img = np.load(tmp_path / f"{mode}{r}.npy")
-            assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)), (mode, r)
-    inflight = np.load(tmp_path / "inflight.npy")
-    for k in range(5):
-        ref = single.render_frame(scene.uniform(single, w, h, 20 + k, 3), single.opts(w, h, 2, 3))
-        assert np.array_equal(inflight[k].view(np.uint32), ref.view(np.uint32)), ("in flight", k)
-    piped = np.load(tmp_path / "pipelined.npy")
-    for k in range(3):
-        ref = single.render_frame(scene.uniform(single, w, h, 10 + k, 3), single.opts(w, h, 2, 3))
-        assert np.array_equal(piped[k].view(np.uint32), ref.view(np.uint32)), k
+
+    def ref(k, fmt=0):
+        return single.render_frame(scene.uniform(single, w, h, k, 3), single.opts(w, h, 2, 3 | fmt))
+
+    for r in range(world):
+        nccl = np.load(tmp_path / f"nccl{r}.npy")
+        for k in range(3):
+            assert np.array_equal(nccl[k].reshape(h, w, 4).view(np.uint32), ref(k).view(np.uint32)), ("nccl", r, k)
+        p2p = np.load(tmp_path / f"p2p_all{r}.npy")
+        for k in range(6):
+            assert np.array_equal(p2p[k].view(np.uint32), ref(k).view(np.uint32)), ("p2p, every rank receives", r, k)
+    root = np.load(tmp_path / "root_f32.npy")
+    assert len(root) == 9
+    distinct = 0
+    for k in range(9):
+        want = ref(20 + k)
+        assert np.array_equal(root[k].view(np.uint32), want.view(np.uint32)), ("root only, four frames in flight", k)
+        distinct += k > 0 and not np.array_equal(root[k], root[k - 1])
+    assert distinct == 8  # the frames really differ, so a stale or half-overwritten gather image would have been seen
+    root8 = np.load(tmp_path / "root_bgra8.npy")
+    for k in range(9):
+        want = ref(20 + k, pkg.render_format(pkg.FORMAT_BGRA8_UNORM))
+        assert np.array_equal(root8[k], want), ("root only, B8G8R8A8_UNORM", k)

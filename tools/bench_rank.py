@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""ONE rank's share of a tiled multi-GPU frame, measured on one GPU: the context is created as rank 0 of `--world` ranks, so it traces
+every `world`-th 32x32 tile. K frames rotate over `--slots` frame slots (frames in flight), one timed region (CUDA events on the slots'
+streams). Shows what bounds a rank of an N-GPU job once its wavefronts are small, without needing N GPUs.
+
+  python tools/bench_rank.py --config c5 --world 8 --slots 1 2 3 4
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c5")
+    ap.add_argument("--world", type=int, default=8)
+    ap.add_argument("--slots", type=int, nargs="+", default=[1, 2, 3, 4])
+    ap.add_argument("--frames", type=int, default=40)
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    pkg = importlib.import_module("hardware-ray-tracer_b200")
+    cfg = dict(pkg.scenes.CONFIGS[args.config])
+    scene = pkg.scenes.make_scene(cfg.pop("scene"))
+    dev = torch.device("cuda", 0)
+    ctx = pkg.Context(device=0, tile_rank=0, tile_world=args.world, flags=pkg.CFG_NO_GRAPH if args.no_graph else 0)
+    scene.upload(ctx)
+    w, h = cfg["width"], cfg["height"]
+    u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
+    opts = ctx.opts(w, h, cfg["spp"], cfg["flags"])
+    out = {"config": args.config, "world": args.world, "graph": not args.no_graph, "runs": []}
+    for n_slots in args.slots:
+        streams = [torch.cuda.ExternalStream(ctx.frame_stream(k), device=dev) for k in range(n_slots)]
+
+        def submit(i):
+            k = i % n_slots
+            ctx.frame_wait(k)
+            ctx.render_frame_async(u, opts, k, None)
+
+        for i in range(2 * n_slots):
+            submit(i)
+        for k in range(n_slots):
+            ctx.frame_wait(k)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(streams[0])
+        for i in range(args.frames):
+            submit(i)
+        ends = []
+        for k in range(n_slots):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(streams[k])
+            ends.append(e)
+        for k in range(n_slots):
+            ctx.frame_wait(k)
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e) for e in ends) / args.frames
+        st = ctx.get_stats()
+        rays = st.rays_closest + st.rays_occlusion
+        out["runs"].append({"slots": n_slots, "ms_per_frame": ms, "rays": int(rays), "mrays_rank": rays / ms / 1e3, "launches": st.launches_total})
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
