@@ -98,7 +98,7 @@ BRT_SYMBOLS = [
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
     "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_denoise_configure", "brt_render_frame_peers_async", "brt_get_light_bvh",
-    "brt_debug_get_blas", "brt_gather_configure", "brt_gather_wait", "brt_gather_release", "brt_gather_copy_to_host", "brt_gather_timed_out",
+    "brt_debug_get_blas", "brt_gather_configure", "brt_gather_wait", "brt_gather_release", "brt_gather_copy_to_host", "brt_gather_timed_out", "brt_debug_l2_read_gbs",
 ]
 
 
@@ -173,6 +173,7 @@ class SceneApi:
             "gather_release": (C.c_int, [vp, u32, vp]),
             "gather_copy_to_host": (C.c_int, [vp, u32, vp, vp]),
             "gather_timed_out": (C.c_int, [vp]),
+            "debug_l2_read_gbs": (C.c_int, [vp, C.c_size_t, u32, P(C.c_float)]),
             "render_frame_peers_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32]),
             "denoise_configure": (C.c_int, [vp, P(DenoiseOpts)]),
             "render_frame_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32, vp]),
@@ -423,6 +424,11 @@ class SceneApi:
 
     def gather_copy_to_host(self, slot, host_ptr, stream_ptr=None):
         self._ck(self._f("gather_copy_to_host")(self.ctx, slot, C.c_void_p(host_ptr), C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def debug_l2_read_gbs(self, nbytes=64 << 20, iters=10):
+        out = C.c_float()
+        self._ck(self._f("debug_l2_read_gbs")(self.ctx, nbytes, iters, C.byref(out)))
+        return out.value
 
     def gather_timed_out(self):
         return self._f("gather_timed_out")(self.ctx)

@@ -133,6 +133,22 @@ BRT_KERNEL_1D(k_sum_samples, SumSamplesParams, sum_samples_body)
 BRT_KERNEL_1D(k_resolve, ResolveParams, resolve_body)
 BRT_KERNEL_1D(k_untile, UntileParams, untile_body)
 #ifndef BRT_EMU
+// measurement aid (brt_debug_l2_read_gbs): streaming read of a buffer that fits the L2 with 16-byte loads, four in flight per thread
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ p, uint32_t n16, uint32_t* __restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 a = make_uint4(0, 0, 0, 0);
+  for (; i + 3u * stride < n16; i += 4u * stride) {
+    const uint4 v0 = ldg4(p + i), v1 = ldg4(p + i + stride), v2 = ldg4(p + i + 2u * stride), v3 = ldg4(p + i + 3u * stride);
+    a.x ^= v0.x ^ v1.x ^ v2.x ^ v3.x; a.y ^= v0.y ^ v1.y ^ v2.y ^ v3.y;
+    a.z ^= v0.z ^ v1.z ^ v2.z ^ v3.z; a.w ^= v0.w ^ v1.w ^ v2.w ^ v3.w;
+  }
+  for (; i < n16; i += stride) {
+    const uint4 v = ldg4(p + i);
+    a.x ^= v.x; a.y ^= v.y; a.z ^= v.z; a.w ^= v.w;
+  }
+  if ((a.x ^ a.y ^ a.z ^ a.w) == 0x9e3779b9u) *out = a.x;  // keeps the loads alive; practically never true
+}
 // ---- fused multi-GPU exchange: resolve + peer stores + device-side completion flags (GatherFlags, render_kernels.cuh) -------------
 #ifndef BRT_GATHER_TIMEOUT_NS
 #define BRT_GATHER_TIMEOUT_NS 20000000000ull  // a wait gives up after 20 s (a rank died or never submitted the frame) instead of hanging the GPU
@@ -2208,6 +2224,39 @@ int brt_debug_get_blas(brt_context* c, uint32_t mesh_id, void* nodes_out, uint32
 }
 
 // 4x4 inverse in double (cofactor expansion along 2x2 minors), row-major in/out
+
+// Measurement aid for the roofline context of bench.py: GB/s of a read-only pass with 16-byte loads over `bytes` of device memory
+// (64 MiB fits the 126 MB L2: after the warm-up pass the loads are L2 hits), best of `iters`, CUDA events on the context's stream.
+int brt_debug_l2_read_gbs(brt_context* c, size_t bytes, uint32_t iters, float* gbs_out) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+#ifdef BRT_EMU
+    (void)bytes; (void)iters; (void)gbs_out;
+    bad_state("debug_l2_read_gbs: needs a CUDA device");
+#else
+    if (!gbs_out || bytes < 4096 || !iters) invalid("debug_l2_read_gbs: bad arguments");
+    BRT_CUDA(cudaSetDevice(c->device));
+    wait_all_frames(c);
+    DevBuf buf, out;
+    buf.ensure(bytes);
+    out.ensure(16);
+    BRT_CUDA(cudaMemsetAsync(buf.ptr(), 1, bytes, c->stream));
+    const uint32_t n16 = (uint32_t)(bytes / 16);
+    const uint32_t grid = (uint32_t)c->sm_count * 8u;
+    float best = 0.0f;
+    for (uint32_t k = 0; k <= iters; ++k) {  // pass 0 warms the L2
+      BRT_CUDA(cudaEventRecord(c->ev_t[0], c->stream));
+      k_l2_read<<<grid, 256, 0, c->stream>>>(buf.as<uint4>(), n16, out.as<uint32_t>());
+      BRT_CUDA(cudaEventRecord(c->ev_t[1], c->stream));
+      BRT_CUDA(cudaStreamSynchronize(c->stream));
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[1]);
+      if (k && ms > 0.0f) best = std::max(best, (float)((double)n16 * 16.0 / (ms * 1e-3) / 1e9));
+    }
+    *gbs_out = best;
+#endif
+  });
+}
 
 void brt_camera_uniform(const float pos[3], const float rot[3], float fovy, float aspect, float znear, float zfar, uint32_t frame,
                         uint32_t depth_max, brt_uniform* out) {

@@ -372,6 +372,9 @@ BRT_API int brt_debug_get_blas(brt_context* ctx, uint32_t mesh_id, void* nodes_o
                                uint32_t* n_nodes, uint32_t* n_tris);
 
 /* ---- host helper: Core::Camera + the uniform block of RTApp::run ---------------------------- */
+/* measurement aid (bench.py's roofline context): GB/s of a hand-written read-only pass (16-byte loads) over `bytes` of device memory,
+ * best of `iters` after a warm-up pass; 64 MiB stays in the 126 MB L2 */
+BRT_API int brt_debug_l2_read_gbs(brt_context* ctx, size_t bytes, uint32_t iters, float* gbs_out);
 /* Camera::setView/updateView (Graphics/Camera.cpp:19-24,71-95), Camera::setPerspectiveProjection
  * (Graphics/Camera.cpp:8-17) and Uniform{inverse(transpose(view)), inverse(transpose(proj)), frame,
  * depthMax} (RT/RTApp.cpp:44-49). rot = (pitch x, yaw y, roll z), Tait-Bryan Y-X-Z. Pure host code. */

@@ -21,7 +21,8 @@ def test_reference_arm_json_line(orc_mod):
     assert len(lines) == 1
     b = json.loads(lines[0])
     assert b["impl"] == "reference" and b["metric"] == "Mrays/s" and b["unit"] == "Mrays/s" and b["higher_is_better"] is True
-    assert b["n_gpus"] == 1 and b["steps"] == 2 and b["warmup"] == 1 and b["vs_baseline"] is None and b["data"] == "synthetic"
+    assert b["n_gpus"] == 1 and b["steps"] == 2 and b["vs_baseline"] is None and b["data"] == "synthetic"
+    assert b["warmup"] == 3  # W >= 3 is enforced (timing rules): the line reports the warm-up steps actually done
     assert b["value"] > 0 and b["ms_per_step"] > 0
     assert b["config"]["workload"].startswith("c1:")
     cb = b["cpu_baseline"]
