@@ -76,6 +76,7 @@ CFG_NO_OVERLAP = 8
 CFG_NO_GRAPH = 16
 CFG_GREEDY_COLLAPSE = 32
 CFG_HIT_SORT = 64
+CFG_TREELET_PASSES_3 = 128
 BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY, GBUFFER, LIGHT_BVH, DENOISE = 1, 2, 4, 8, 16, 32, 64, 128
 AOV_POSITION, AOV_NORMAL = 3, 4
 DENOISE_RESET, DENOISE_BILATERAL = 1, 2

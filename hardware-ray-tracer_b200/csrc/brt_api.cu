@@ -252,6 +252,14 @@ __global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const Trace
   uint32_t rays = 0;
   Traversal<ANY, COUNT> t;
   uint2 stack[BRT_STACK_ALLOC];
+#ifdef BRT_SMEM_STACK
+  __shared__ uint2 s_stack[BRT_SMEM_STACK * 128];
+  t.sst = s_stack + threadIdx.x;
+#endif
+#ifdef BRT_NODE_PREFETCH
+  __shared__ uint4 s_node[5 * 128];
+  t.snode = s_node + threadIdx.x;
+#endif
   bool active = false;
   bool exhausted = false;  // warp-uniform
   uint32_t ray = 0;
@@ -1540,7 +1548,7 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     for (int k = 0; k < 3; ++k) BRT_CUDA(cudaEventCreate(&c->ev_t[k]));
     BRT_CUDA(cudaEventCreateWithFlags(&c->dn_event, cudaEventDisableTiming));
     c->own_stream = true;
-    c->builder.reset(new Builder(c->sm_count, (c->flags & BRT_CFG_GREEDY_COLLAPSE) != 0));
+    c->builder.reset(new Builder(c->sm_count, (c->flags & BRT_CFG_GREEDY_COLLAPSE) != 0, (c->flags & BRT_CFG_TREELET_PASSES_3) != 0));
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
   });
   if (rc != BRT_OK) {
@@ -1594,6 +1602,11 @@ int brt_mesh_create(brt_context* c, const brt_vertex* v, uint32_t nv, const uint
     m->n_indices = ni;
     upload(c->stream, m->vertices, v, (size_t)nv * sizeof(brt_vertex));
     upload(c->stream, m->indices, idx, (size_t)ni * 4);
+    if (ni) {  // everything the first build of this mesh needs is allocated here, not inside the build (it was 128 ms cold)
+      c->builder->reserve(ni / 3);
+      m->nodes.ensure((size_t)Builder::node_capacity(ni / 3) * sizeof(Node8));
+      m->tris.ensure((size_t)(ni / 3) * sizeof(TriRec));
+    }
     BRT_CUDA(cudaStreamSynchronize(c->stream));  // "the library copies all input arrays during the call"
     c->meshes.push_back(std::move(m));
     if (mesh_id) *mesh_id = (uint32_t)c->meshes.size() - 1;

@@ -359,7 +359,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
         w_cost.assign(cost, cost + 2 * n);
       }
 #endif
-      for (int pass = 1; pass <= 3; ++pass) {
+      for (int pass = 1; pass <= treelet_passes_; ++pass) {
         BRT_CUDA(cudaMemsetAsync(arrive_.ptr(), 0, (size_t)n * 4, stream));
         TreeletParams tp{n, nullptr, nodes, parent, sub_count, arrive_.as<uint32_t>(), cost, 1u};
   #ifdef BRT_EMU
@@ -371,7 +371,7 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
       }
 #if defined(BRT_EMU) && defined(BRT_EMU_WARP)
       if (warp_check) {
-        for (int pass = 1; pass <= 3; ++pass) {
+        for (int pass = 1; pass <= treelet_passes_; ++pass) {
           w_arrive.assign(n, 0u);
           const TreeletParams tp{n, nullptr, w_nodes.data(), w_parent.data(), w_sub.data(), w_arrive.data(), w_cost.data(), 1u};
           brt_warp_emu::run_kernel_warps(std::max(1u, div_up(n, 128u)), 128u, [&] { k_treelet_warp(tp); });

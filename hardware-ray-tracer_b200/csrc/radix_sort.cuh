@@ -30,20 +30,27 @@ inline uint32_t radix_sort_tiles(uint32_t n) {
 inline size_t radix_sort_temp_bytes(uint32_t n) { return (size_t)radix_sort_tiles(n) * 256 * 4 + 16; }
 
 #ifndef BRT_EMU
+// digit histogram of tile `tile` (block-cooperative, BRT_SORT_THREADS threads; ends with a barrier so that it can be called in a loop)
 template <int ITEMS>
-__global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t dmask,
-                                                                 uint32_t* __restrict__ hist, uint32_t tiles) {
+__device__ __forceinline__ void radix_hist_tile(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t dmask,
+                                                uint32_t* __restrict__ hist, uint32_t tiles, uint32_t tile) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t base = blockIdx.x * (BRT_SORT_THREADS * ITEMS);
+  const uint32_t base = tile * (BRT_SORT_THREADS * ITEMS);
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     const uint32_t i = base + k * BRT_SORT_THREADS + threadIdx.x;
     if (i < n) atomicAdd(&h[(keys[i] >> shift) & dmask], 1u);
   }
   __syncthreads();
-  hist[threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
+  hist[threadIdx.x * tiles + tile] = h[threadIdx.x];
+  __syncthreads();
+}
+template <int ITEMS>
+__global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t dmask,
+                                                                 uint32_t* __restrict__ hist, uint32_t tiles) {
+  radix_hist_tile<ITEMS>(keys, n, shift, dmask, hist, tiles, blockIdx.x);
 }
 
 // exclusive scan of `count` counters in place, one block of 1024 threads (the table is at most a few 100k entries)
@@ -84,16 +91,16 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t* __restrict__ hist
 }
 
 template <int ITEMS>
-__global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
-                                                                    int shift, uint32_t dmask, const uint32_t* __restrict__ hist, uint32_t tiles) {
+__device__ __forceinline__ void radix_scatter_tile(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                                                   uint32_t dmask, const uint32_t* __restrict__ hist, uint32_t tiles, uint32_t tile) {
   constexpr int WARPS = BRT_SORT_THREADS / 32;
   __shared__ uint32_t warp_count[WARPS][256];
   for (int k = threadIdx.x; k < WARPS * 256; k += BRT_SORT_THREADS) (&warp_count[0][0])[k] = 0;
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const uint32_t warp_base = blockIdx.x * (BRT_SORT_THREADS * ITEMS) + warp * (ITEMS * 32);
+  const uint32_t warp_base = tile * (BRT_SORT_THREADS * ITEMS) + warp * (ITEMS * 32);
   uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_scatter(const uint32
   __syncthreads();
   {  // thread d turns the per-warp counts of digit d into start offsets (global base of this tile + earlier warps)
     const uint32_t d = threadIdx.x;
-    uint32_t run = hist[d * tiles + blockIdx.x];
+    uint32_t run = hist[d * tiles + tile];
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) {
       const uint32_t c = warp_count[w][d];
@@ -138,6 +145,49 @@ __global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_scatter(const uint32
       vals_out[pos] = val[k];
     }
   }
+  __syncthreads();  // (callable in a loop: warp_count is rewritten by the next tile)
+}
+template <int ITEMS>
+__global__ void __launch_bounds__(BRT_SORT_THREADS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                                                                    int shift, uint32_t dmask, const uint32_t* __restrict__ hist, uint32_t tiles) {
+  radix_scatter_tile<ITEMS>(keys_in, vals_in, keys_out, vals_out, n, shift, dmask, hist, tiles, blockIdx.x);
+}
+// in-place exclusive scan of `count` counters by ONE block of any size (<= 1024 threads)
+__device__ __forceinline__ void radix_scan_block(uint32_t* __restrict__ hist, uint32_t count) {
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t nt = blockDim.x;
+  const uint32_t per = (count + nt - 1u) / nt;
+  const uint32_t begin = min(threadIdx.x * per, count), end = min(begin + per, count);
+  uint32_t sum = 0;
+  for (uint32_t i = begin; i < end; ++i) sum += hist[i];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t incl = sum;
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((int)lane >= off) incl += v;
+  }
+  if (threadIdx.x < 32u) warp_sums[threadIdx.x] = 0u;
+  __syncthreads();
+  if (lane == 31u) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = warp_sums[lane];
+    uint32_t wi = w;
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, off);
+      if ((int)lane >= off) wi += v;
+    }
+    warp_sums[lane] = wi - w;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[warp] + incl - sum;
+  for (uint32_t i = begin; i < end; ++i) {
+    const uint32_t v = hist[i];
+    hist[i] = run;
+    run += v;
+  }
+  __syncthreads();
 }
 #endif  // !BRT_EMU
 

@@ -65,12 +65,8 @@ BRT_HD float magic_byte(uint32_t w, uint32_t sel) { return u2f(byte_perm(w, 0x47
 // the two low bits of octinv pick which byte of each 4-slot word a PRMT converts (a per-ray selector, no extra
 // instruction), the node stores its slot masks pre-permuted for the four possible values (iperm / lperm), and bit 2
 // swaps the two 4-slot halves of the result. The eight comparisons then land on constant bit positions.
-BRT_HD void intersect_node(const Node8* __restrict__ node, const RayBox& rb, f3 o, float tmin, float tmax, uint2& G, uint2& Gt) {
-  const uint4 n0 = ldg4(&node->q[0]);
-  const uint4 n1 = ldg4(&node->q[1]);
-  const uint4 n2 = ldg4(&node->q[2]);
-  const uint4 n3 = ldg4(&node->q[3]);
-  const uint4 n4 = ldg4(&node->q[4]);
+BRT_HD void intersect_node(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const RayBox& rb, f3 o, float tmin,
+                           float tmax, uint2& G, uint2& Gt) {
   const float px = u2f(n0.x) - o.x, py = u2f(n0.y) - o.y, pz = u2f(n0.z) - o.z;
   const float sx = u2f((n0.w & 0xffu) << 23), sy = u2f(((n0.w >> 8) & 0xffu) << 23), sz = u2f(((n0.w >> 16) & 0xffu) << 23);
   const float idx = sx * rb.idir.x, idy = sy * rb.idir.y, idz = sz * rb.idir.z;
@@ -169,6 +165,57 @@ struct Traversal {
     rb.octinv = f.y;
   }
 
+  // Experiment (profiles/r2_traversal.md): -DBRT_SMEM_STACK=K keeps the K bottom entries of every lane's stack in shared memory
+  // (column threadIdx.x of a [K][128] array of 8-byte words: conflict-free), deeper entries stay in local memory.
+#if defined(BRT_SMEM_STACK) && !defined(BRT_EMU)
+  uint2* sst;  // this lane's column
+  BRT_HDM void push(uint2* __restrict__ stack, uint2 v) {
+    if (sp < BRT_SMEM_STACK) sst[sp * 128] = v;
+    else stack[sp] = v;
+    ++sp;
+  }
+  BRT_HDM uint2 pop(const uint2* __restrict__ stack) {
+    --sp;
+    return sp < BRT_SMEM_STACK ? sst[sp * 128] : stack[sp];
+  }
+#else
+  BRT_HDM void push(uint2* __restrict__ stack, uint2 v) { stack[sp++] = v; }
+  BRT_HDM uint2 pop(const uint2* __restrict__ stack) { return stack[--sp]; }
+#endif
+
+  // Experiment (profiles/r2_traversal.md): -DBRT_NODE_PREFETCH stages the NEXT node through shared memory. As soon as a node test has
+  // produced its hit groups the node visited next is known (the nearest hit inner child, else the nearest child of the group on top
+  // of the stack): its 80 bytes are requested with five 16-byte cp.async into this lane's column of a [5][128] shared array while the
+  // lane runs its primitive tests, and the next step reads them with LDS.128 instead of waiting for five dependent LDG.128.
+#if defined(BRT_NODE_PREFETCH) && !defined(BRT_EMU)
+  uint4* snode;         // this lane's column of the staging array
+  const Node8* pf_node;  // node whose words are (being) staged, or null
+  BRT_HDM void prefetch_node(const Node8* np) {
+    asm volatile("cp.async.wait_all;" ::: "memory");  // an older request into the same column must have landed
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(snode);
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s0 + (unsigned)j * 2048u), "l"(&np->q[j]) : "memory");
+    pf_node = np;
+  }
+  // the node the next step will visit, given the groups as they stand (null: a leaf group, or nothing left)
+  BRT_HDM const Node8* next_node(const uint2* __restrict__ stack) const {
+    uint2 g = G;
+    const Node8* base = nodes;
+    if (!(g.y & 0xff000000u)) {
+      if (sp == 0) return nullptr;
+      if (blas_sp >= 0 && sp == blas_sp) base = tlas;  // the BLAS is exhausted: the pop returns to the TLAS
+      g = stack[sp - 1];
+      if (!(g.y & 0xff000000u)) return nullptr;
+    }
+    const int bit = 31 - clz32(g.y);
+    const uint32_t slot = (uint32_t)(bit - 24) ^ ((blas_sp >= 0 && base == tlas) ? f2u_octinv_world(stack) : rb.octinv);
+    const uint32_t rel = popc((g.y & ~(1u << bit)) & ~(0xffffffffu << slot));
+    return base + (uint32_t)(g.x + rel);
+  }
+  static BRT_HDM uint32_t f2u_octinv_world(const uint2* __restrict__ stack) { return stack[BRT_STACK_SIZE + 4].y; }
+#endif
+
   BRT_HDM void init(uint2* __restrict__ stack, const Node8* tlas_, const InstRec* insts_, f3 o_, f3 d_, float tmin_, float tmax_) {
     tlas = tlas_;
     insts = insts_;
@@ -182,6 +229,9 @@ struct Traversal {
     found = false;
     sp = 0;
     blas_sp = -1;
+#if defined(BRT_NODE_PREFETCH) && !defined(BRT_EMU)
+    pf_node = nullptr;
+#endif
     co = o_;
     rb = make_raybox(d_);
     store_world_raybox(stack, rb);
@@ -200,11 +250,27 @@ struct Traversal {
     if (G.y & 0xff000000u) {
       const int bit = 31 - clz32(G.y);
       G.y &= ~(1u << bit);
-      if (G.y & 0xff000000u) stack[sp++] = G;
+      if (G.y & 0xff000000u) push(stack, G);
       const uint32_t slot = (uint32_t)(bit - 24) ^ rb.octinv;
       const uint32_t rel = popc(G.y & ~(0xffffffffu << slot));
       if (COUNT) ctr.nodes++;
-      intersect_node(nodes + (uint32_t)(G.x + rel), rb, co, tmin, best.t, G, Gt);  // 32-bit index: one IMAD.WIDE
+      const Node8* np = nodes + (uint32_t)(G.x + rel);  // 32-bit index: one IMAD.WIDE
+#if defined(BRT_NODE_PREFETCH) && !defined(BRT_EMU)
+      uint4 n0, n1, n2, n3, n4;
+      if (pf_node == np) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        n0 = snode[0]; n1 = snode[128]; n2 = snode[256]; n3 = snode[384]; n4 = snode[512];
+      } else {
+        n0 = ldg4(&np->q[0]); n1 = ldg4(&np->q[1]); n2 = ldg4(&np->q[2]); n3 = ldg4(&np->q[3]); n4 = ldg4(&np->q[4]);
+      }
+      intersect_node(n0, n1, n2, n3, n4, rb, co, tmin, best.t, G, Gt);
+      if (!(Gt.y & 0xffu) || blas_sp >= 0) {  // (an instance leaf may enter a BLAS and change everything: no request then)
+        const Node8* nx = next_node(stack);
+        if (nx) prefetch_node(nx);
+      }
+#else
+      intersect_node(ldg4(&np->q[0]), ldg4(&np->q[1]), ldg4(&np->q[2]), ldg4(&np->q[3]), ldg4(&np->q[4]), rb, co, tmin, best.t, G, Gt);
+#endif
     } else {
       Gt = G;
       G = make_uint2(0u, 0u);
@@ -250,8 +316,8 @@ struct Traversal {
           }
         } else {
           // enter the BLAS: keep the TLAS continuation on the stack
-          if (Gt.y & 0xffu) stack[sp++] = Gt;
-          if (G.y & 0xff000000u) stack[sp++] = G;
+          if (Gt.y & 0xffu) push(stack, Gt);
+          if (G.y & 0xff000000u) push(stack, G);
           blas_sp = sp;
           const uint4 ptrs = ldg4(reinterpret_cast<const uint4*>(&ir->nodes));
           nodes = reinterpret_cast<const Node8*>(((uint64_t)ptrs.y << 32) | ptrs.x);
@@ -273,7 +339,7 @@ struct Traversal {
         restore_world(stack);
       }
       if (sp == 0) return true;
-      G = stack[--sp];
+      G = pop(stack);
     }
     return false;
   }

@@ -132,6 +132,9 @@ typedef struct brt_config {
  * over the scene), so that the shadow and bounce rays they emit start at neighbouring origins. Frames are bit-identical either way.
  * Measured on B200 (profiles/r2_traversal.md): traversal -0..4 %, shade + sort +2 ms on C5 — a loss, hence off by default. */
 #define BRT_CFG_HIT_SORT 64u
+/* First ("fast trace") builds run ONE SAH treelet pass (1M triangles: 4.7 ms, SAH 35.56); with this flag three (9.5 ms, SAH 35.02,
+ * -0.7 % frame time on C5): for scenes built once and rendered for a long time. */
+#define BRT_CFG_TREELET_PASSES_3 128u
 
 /* render mode flags. With none of the BOUNCE flags set the behaviour is the reference's live path:
  * direct light + hard shadows, weight = 0 after the first hit (SH/raytracing.slang:168). */

@@ -516,7 +516,7 @@ def frames_in_flight(pkg, orc_mod, make):
     assert np.array_equal(out[2].view(np.uint32), b.render_frame(uni[0], b.opts(w, h, 1, 0)).view(np.uint32))
     assert not np.array_equal(first, out[2])
     with pytest.raises(pkg.BrtError):
-        a.render_frame_async(uni[0], a.opts(w, h, 1, 0), 3, None)  # slot out of range
+        a.render_frame_async(uni[0], a.opts(w, h, 1, 0), 4, None)  # slot out of range (BRT_FRAMES_IN_FLIGHT = 4)
 
 
 def present_formats(pkg, orc_mod, make):
