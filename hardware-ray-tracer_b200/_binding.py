@@ -78,6 +78,7 @@ CFG_GREEDY_COLLAPSE = 32
 CFG_HIT_SORT = 64
 CFG_TREELET_PASSES_3 = 128
 BOUNCE_REFLECT, BOUNCE_REFRACT, BOUNCE_DIFFUSE, JITTER, SKY, GBUFFER, LIGHT_BVH, DENOISE = 1, 2, 4, 8, 16, 32, 64, 128
+FAST_SHADING = 2048
 AOV_POSITION, AOV_NORMAL = 3, 4
 DENOISE_RESET, DENOISE_BILATERAL = 1, 2
 FORMAT_RGBA32F, FORMAT_RGBA8_UNORM, FORMAT_BGRA8_UNORM, FORMAT_RGBA8_SRGB, FORMAT_BGRA8_SRGB = 0, 1, 2, 3, 4
@@ -99,8 +100,20 @@ BRT_SYMBOLS = [
     "brt_tile_buffer_bytes", "brt_untile", "brt_device_image", "brt_get_aov", "brt_get_stats", "brt_trace_rays",
     "brt_camera_uniform", "brt_debug_sort_pairs", "brt_gather_image_export", "brt_gather_image_open",
     "brt_render_frame_peers", "brt_gather_image", "brt_render_frame_async", "brt_frame_wait", "brt_frame_stream", "brt_camera_handle_inputs", "brt_denoise", "brt_denoised_image", "brt_denoise_configure", "brt_render_frame_peers_async", "brt_get_light_bvh",
-    "brt_debug_get_blas", "brt_gather_configure", "brt_gather_wait", "brt_gather_release", "brt_gather_copy_to_host", "brt_gather_timed_out", "brt_debug_l2_read_gbs",
+    "brt_debug_get_blas", "brt_gather_configure", "brt_gather_wait", "brt_gather_release", "brt_gather_copy_to_host", "brt_gather_timed_out", "brt_debug_l2_read_gbs", "brt_get_scene_info_buffer", "brt_get_tlas",
 ]
+
+
+class InstanceInfo(C.Structure):  # RT/Scene.h:84-88
+    _fields_ = [("vertexAddress", C.c_uint64), ("indexAddress", C.c_uint64), ("materialId", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class SceneBufferInfo(C.Structure):  # RT/Scene.h:106-121
+    _fields_ = [(n, C.c_uint64) for n in ("mBuf", "mStride", "lBuf", "lStride", "lCount", "vStride", "sBuf", "sStride", "skyBuf", "skyStride")]
+
+
+class AccelInfo(C.Structure):  # RT/Scene.h:77-82 + counts
+    _fields_ = [("handle", C.c_uint64), ("buffer", C.c_uint64), ("memory", C.c_uint64), ("address", C.c_uint64), ("n_nodes", C.c_uint32), ("n_instances", C.c_uint32)]
 
 
 class BrtError(RuntimeError):
@@ -175,6 +188,8 @@ class SceneApi:
             "gather_copy_to_host": (C.c_int, [vp, u32, vp, vp]),
             "gather_timed_out": (C.c_int, [vp]),
             "debug_l2_read_gbs": (C.c_int, [vp, C.c_size_t, u32, P(C.c_float)]),
+            "get_scene_info_buffer": (C.c_int, [vp, P(SceneBufferInfo), P(C.c_uint64)]),
+            "get_tlas": (C.c_int, [vp, P(AccelInfo)]),
             "render_frame_peers_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32]),
             "denoise_configure": (C.c_int, [vp, P(DenoiseOpts)]),
             "render_frame_async": (C.c_int, [vp, P(Uniform), P(RenderOpts), u32, vp]),
@@ -430,6 +445,16 @@ class SceneApi:
         out = C.c_float()
         self._ck(self._f("debug_l2_read_gbs")(self.ctx, nbytes, iters, C.byref(out)))
         return out.value
+
+    def get_scene_info_buffer(self):
+        out, dptr = SceneBufferInfo(), C.c_uint64()
+        self._ck(self._f("get_scene_info_buffer")(self.ctx, C.byref(out), C.byref(dptr)))
+        return out, dptr.value
+
+    def get_tlas(self):
+        out = AccelInfo()
+        self._ck(self._f("get_tlas")(self.ctx, C.byref(out)))
+        return out
 
     def gather_timed_out(self):
         return self._f("gather_timed_out")(self.ctx)

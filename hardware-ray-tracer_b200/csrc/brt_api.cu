@@ -13,70 +13,17 @@
 #include "../../include/brt.h"
 #include "builder.h"
 #include "render_kernels.cuh"
+#include "shade_kernels.cuh"
 #include "denoise.cuh"
 
 namespace brt {
 
+#ifndef BRT_EMU
+void launch_shade_fast(const ShadeParams& sp, uint32_t grid, bool primary, cudaStream_t stream);  // shade_fast.cu
+#endif
+
 // ---- kernels ---------------------------------------------------------------------------------------
 BRT_KERNEL_1D(k_raygen, RaygenParams, raygen_body)
-#ifndef BRT_SHADE_MIN_BLOCKS
-#define BRT_SHADE_MIN_BLOCKS 5  // 96 registers, no spills: measured 1-1.5 % faster than 4 (118) on C3 / C5; 6 (80, spills) is slower
-#endif
-#ifndef BRT_SHADE_WINDOW
-#define BRT_SHADE_WINDOW 4  // x 128 path slots are classified before their hits are shaded together
-#endif
-#ifdef BRT_EMU
-BRT_KERNEL_1D_LB(k_shade, ShadeParams, shade_body, 128, BRT_SHADE_MIN_BLOCKS)
-#else
-// primary round: the wavefront is in pixel order, hits and misses come in large coherent runs — one path per thread, no compaction
-BRT_KERNEL_1D_LB(k_shade_primary, ShadeParams, shade_body, 128, BRT_SHADE_MIN_BLOCKS)
-// Shade with block-level hit compaction. After the first bounce the hits and misses of a wavefront are interleaved at random, and the
-// hit shader (geometry fetch, BRDF per light, shadow-ray emission, bounce sampling: ~95 % of the kernel's instructions) ran with ~6 of
-// 32 lanes active (ncu, profiles/). Each block therefore first runs the cheap prologue for its 128 path slots (bookkeeping, AOVs, the
-// whole miss shader) — K = BRT_SHADE_WINDOW times, so that the window is 512 slots and the dependent-load latency of the hit shader is
-// paid once per window —, compacts the indices of the hits into shared memory (ballot + per-warp prefix), and then shades the compacted list with
-// full warps. Which thread shades which path is irrelevant: every output is addressed by the path slot.
-template <uint32_t K>
-__global__ void __launch_bounds__(128, BRT_SHADE_MIN_BLOCKS) k_shade(const ShadeParams p) {
-  __shared__ uint32_t s_idx[128u * K];
-  __shared__ uint32_t s_warp[4 * K];
-  const uint32_t n = p.count_ptr ? *p.count_ptr : p.count;
-  // a short queue (fewer than K chunks per block) is latency-bound on the number of blocks in flight: window of one chunk then
-  const uint32_t kk = n >= K * 128u * gridDim.x ? K : 1u;
-  const uint32_t slots = 128u * kk;
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t base = blockIdx.x * slots; base < n; base += gridDim.x * slots) {  // block-uniform trip count
-    bool is_hit[K];
-    uint32_t slot[K];
-    unsigned m[K];
-#pragma unroll
-    for (uint32_t k = 0; k < K; ++k) {
-      const uint32_t w = base + k * 128u + threadIdx.x;
-      const bool live = k < kk && w < n;
-      slot[k] = live && p.order ? p.order[w] : w;  // hit-sorted order of a bounce round (render_kernels.cuh), else queue order
-      is_hit[k] = live && shade_prologue(p, slot[k]);
-      m[k] = __ballot_sync(0xffffffffu, is_hit[k]);
-      if (lane == 0) s_warp[k * 4 + warp] = (uint32_t)__popc(m[k]);
-    }
-    __syncthreads();
-    uint32_t total = 0, off[K];
-#pragma unroll
-    for (uint32_t j = 0; j < 4 * K; ++j) {
-      const uint32_t cnt = s_warp[j];
-#pragma unroll
-      for (uint32_t k = 0; k < K; ++k)
-        if (j == k * 4 + warp) off[k] = total;
-      total += cnt;
-    }
-#pragma unroll
-    for (uint32_t k = 0; k < K; ++k)
-      if (is_hit[k]) s_idx[off[k] + (uint32_t)__popc(m[k] & ((1u << lane) - 1u))] = slot[k];
-    __syncthreads();
-    for (uint32_t t = threadIdx.x; t < total; t += 128u) shade_hit(p, s_idx[t]);
-    __syncthreads();  // s_idx / s_warp are rewritten by the next window
-  }
-}
-#endif
 #ifndef BRT_EMU
 // hit sort of the bounce rounds (render_kernels.cuh): keys + per-cell arrival ranks, scan of the cell counters, scatter
 __global__ void __launch_bounds__(256) k_hit_keys(const HitSortParams p) {
@@ -243,7 +190,7 @@ static void k_trace(const TraceParams p) {
 // p.refill_lanes lanes of the warp are still busy (0 = only when all are done), the idle lanes claim the next rays of the queue from
 // a global cursor (one warp-aggregated atomic) so that the SIMD lanes stay occupied however uneven the
 // per-ray cost is. The first fetch of a warp is 32 consecutive rays = one 8x4 pixel block (coherent).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool DEFER>
 __global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const TraceParams p) {
   const uint32_t n = trace_total(p);
   const unsigned lane = threadIdx.x & 31u;
@@ -288,17 +235,37 @@ __global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const Trace
       if (exhausted) break;
       continue;  // only padding slots were fetched: fetch again
     }
-    if (active) {
+    if (DEFER) {
+      // Deferred-leaf mode (traverse.cuh): all 32 lanes stay in this loop; a lane visits nodes and parks its leaf hits, the warp votes,
+      // and the parked primitive tests run together once p.defer_lanes lanes have one (or nobody has node work left).
       for (;;) {
-        if (t.step(stack, c)) {
+        if (active && t.can_node()) t.node_visit(stack, c);
+        const unsigned pend = __ballot_sync(0xffffffffu, active && t.leaf_pending());
+        const unsigned cann = __ballot_sync(0xffffffffu, active && t.can_node());
+        bool finished = false;
+        if (__popc(pend) >= (int)p.defer_lanes || cann == 0u) {
+          if (active && t.leaf_pending()) finished = t.leaf_visit(stack, c);
+        }
+        if (active && (finished || t.advance(stack))) {
           trace_store(p, ray, t);
           active = false;
-          break;
         }
-        if (!exhausted && __popc(__activemask()) < (int)p.refill_lanes) break;
+        const int n_active = __popc(__ballot_sync(0xffffffffu, active));
+        if (n_active == 0 || (!exhausted && n_active < (int)p.refill_lanes)) break;
       }
+    } else {
+      if (active) {
+        for (;;) {
+          if (t.step(stack, c)) {
+            trace_store(p, ray, t);
+            active = false;
+            break;
+          }
+          if (!exhausted && __popc(__activemask()) < (int)p.refill_lanes) break;
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   rays = __reduce_add_sync(0xffffffffu, rays);
   if (COUNT) {
@@ -315,7 +282,11 @@ __global__ void __launch_bounds__(128, BRT_TRACE_MIN_BLOCKS) k_trace(const Trace
     }
   }
 }
-#define BRT_LAUNCH_TRACE(ANY, COUNT, params, grid, stream) k_trace<ANY, COUNT><<<(grid), 128, 0, (stream)>>>(params)
+#define BRT_LAUNCH_TRACE(ANY, COUNT, params, grid, stream)                                   \
+  do {                                                                                        \
+    if ((params).defer_lanes) k_trace<ANY, COUNT, true><<<(grid), 128, 0, (stream)>>>(params); \
+    else k_trace<ANY, COUNT, false><<<(grid), 128, 0, (stream)>>>(params);                     \
+  } while (0)
 #endif
 
 // ---- host-side scene ---------------------------------------------------------------------------------
@@ -436,6 +407,8 @@ struct brt_context {
   std::vector<brt_light_bvh_node> light_bvh;  // RT/Scene.h:123-130, built on the host by build_tables
   DevBuf d_light_bvh;
   DevBuf d_materials, d_mat_ext, d_lights, d_inst_shade, d_inst_src, d_inst_ids, d_mesh_bounds, d_visible;
+  DevBuf d_instance_info, d_sky, d_scene_info;  // the reference's InstanceInfo[] / SkyInfo / SceneBufferInfo (RT/Scene.h:84-121) for callers that bind them
+  brt_scene_buffer_info scene_info{};
   DevBuf d_tlas_nodes, d_tlas_inst;
   float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};  // world box of all instances (grid of the hit sort)
   uint32_t tlas_count = 0;  // visible, non-empty instances in the TLAS
@@ -446,6 +419,8 @@ struct brt_context {
   cudaEvent_t prev_head = nullptr;        // ev_head of the frame submitted last: the next frame starts behind it (staggered frames)
   uint32_t last_slot = 0;                 // slot of the frame most recently waited for (brt_get_aov / brt_device_image read it)
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
+  uint32_t refill_primary = 0, refill_bounce = BRT_REFILL_LANES_INCOHERENT;  // lanes still busy below which a warp refills its idle lanes
+  uint32_t defer_primary = 0, defer_bounce = 0;  // deferred-leaf traversal: lanes with a parked primitive test that trigger a pass (0 = off)
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
   // fused resolve + exchange: own gather image and the peers' (opened through cudaIpc)
   DevBuf d_gather;  // BRT_GATHER_IMAGES full frames back to back + one GatherFlags block (one allocation, one IPC handle): slot k uses image k
@@ -576,17 +551,15 @@ struct Timed {  // brackets one launch with events of class `cls` on the stream 
 // ---- light BVH (RT/Scene.h:123-130) ---------------------------------------------------------
 // Median split along the widest axis of the light positions, ties broken by light index; children are allocated in pairs
 // (left, right = left + 1) and built depth-first, so the node order is fully determined by the light list.
-void build_light_bvh(const std::vector<brt_light>& lights, std::vector<brt_light_bvh_node>& nodes) {
-  nodes.clear();
-  const uint32_t n = (uint32_t)lights.size();
-  if (!n) return;
-  nodes.reserve(2 * (size_t)n);
-  std::vector<uint32_t> order(n);
-  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+// Point lights and the lights of the shader's constant-direction branch (SPOT / DIRECTIONAL, SH/light.slang:33-36: direction (0.9, -0.1, 0),
+// no falloff) never share a subtree: when both kinds exist the root's left child holds the point lights, the right child the others.
+// The cone fields tell the kinds apart: point lights radiate everywhere (axis (0,0,1), angle pi), a constant-direction subtree has
+// angle 0 and the emission axis -normalize(0.9, -0.1, 0); its importance does not depend on the shading point.
+void build_light_subtree(const std::vector<brt_light>& lights, std::vector<uint32_t>& order, std::vector<brt_light_bvh_node>& nodes, uint32_t root,
+                         uint32_t first0, uint32_t count0, bool directional) {
   struct Task { uint32_t node, first, count; };
   std::vector<Task> stack;
-  nodes.push_back(brt_light_bvh_node{});
-  stack.push_back({0u, 0u, n});
+  stack.push_back({root, first0, count0});
   while (!stack.empty()) {
     const Task t = stack.back();
     stack.pop_back();
@@ -602,8 +575,13 @@ void build_light_bvh(const std::vector<brt_light>& lights, std::vector<brt_light
       flux = flux + std::fabs(l.intensity * ((0.2126f * l.color[0] + 0.7152f * l.color[1]) + 0.0722f * l.color[2]));
     }
     nd.totalFlux = flux;
-    nd.coneAxis[0] = 0.0f; nd.coneAxis[1] = 0.0f; nd.coneAxis[2] = 1.0f;
-    nd.coneAngle = 3.14159274f;
+    if (directional) {
+      nd.coneAxis[0] = -0.993883729f; nd.coneAxis[1] = 0.110431522f; nd.coneAxis[2] = 0.0f;  // -normalize(0.9, -0.1, 0)
+      nd.coneAngle = 0.0f;
+    } else {
+      nd.coneAxis[0] = 0.0f; nd.coneAxis[1] = 0.0f; nd.coneAxis[2] = 1.0f;
+      nd.coneAngle = 3.14159274f;
+    }
     if (t.count == 1) {
       nd.childIndex = -1 - (int32_t)order[t.first];
     } else {
@@ -625,6 +603,38 @@ void build_light_bvh(const std::vector<brt_light>& lights, std::vector<brt_light
     }
     nodes[t.node] = nd;
   }
+}
+void build_light_bvh(const std::vector<brt_light>& lights, std::vector<brt_light_bvh_node>& nodes) {
+  nodes.clear();
+  const uint32_t n = (uint32_t)lights.size();
+  if (!n) return;
+  nodes.reserve(2 * (size_t)n + 2);
+  std::vector<uint32_t> order;
+  for (uint32_t i = 0; i < n; ++i)
+    if (lights[i].type == BRT_LIGHT_POINT) order.push_back(i);
+  const uint32_t n_point = (uint32_t)order.size();
+  for (uint32_t i = 0; i < n; ++i)
+    if (lights[i].type != BRT_LIGHT_POINT) order.push_back(i);
+  nodes.push_back(brt_light_bvh_node{});
+  if (n_point == 0 || n_point == n) {
+    build_light_subtree(lights, order, nodes, 0, 0, n, n_point == 0);
+    return;
+  }
+  // both kinds: the root only separates them (left = point lights, right = constant-direction lights)
+  nodes.push_back(brt_light_bvh_node{});
+  nodes.push_back(brt_light_bvh_node{});
+  build_light_subtree(lights, order, nodes, 1, 0, n_point, false);
+  build_light_subtree(lights, order, nodes, 2, n_point, n - n_point, true);
+  brt_light_bvh_node root{};
+  for (int k = 0; k < 3; ++k) {
+    root.bBoxMin[k] = std::fmin(nodes[1].bBoxMin[k], nodes[2].bBoxMin[k]);
+    root.bBoxMax[k] = std::fmax(nodes[1].bBoxMax[k], nodes[2].bBoxMax[k]);
+  }
+  root.totalFlux = nodes[1].totalFlux + nodes[2].totalFlux;
+  root.coneAxis[2] = 1.0f;
+  root.coneAngle = 3.14159274f;
+  root.childIndex = 1;
+  nodes[0] = root;
 }
 
 // ---- scene tables ------------------------------------------------------------------------------------
@@ -659,6 +669,20 @@ void build_tables(brt_context* c) {
     r.mesh = in.mesh;
   }
   upload(s, c->d_inst_shade, shade.data(), shade.size() * sizeof(InstShade));
+  // the reference's own tables (RT/Scene.cpp:357-403): InstanceInfo per instance, SkyInfo, SceneBufferInfo
+  {
+    std::vector<brt_instance_info> info(std::max<size_t>(c->instances.size(), 1));
+    for (size_t i = 0; i < c->instances.size(); ++i) {
+      const MeshData& m = *c->meshes[c->instances[i].mesh];
+      info[i] = brt_instance_info{(uint64_t)m.vertices.ptr(), (uint64_t)m.indices.ptr(), c->instances[i].material, 0u};
+    }
+    upload(s, c->d_instance_info, info.data(), info.size() * sizeof(brt_instance_info));
+    upload(s, c->d_sky, &c->sky, sizeof(brt_sky));
+    c->scene_info = brt_scene_buffer_info{(uint64_t)c->d_materials.ptr(), sizeof(brt_material), (uint64_t)c->d_lights.ptr(), sizeof(brt_light),
+                                          (uint64_t)c->lights.size(), sizeof(brt_vertex), (uint64_t)c->d_instance_info.ptr(), sizeof(brt_instance_info),
+                                          (uint64_t)c->d_sky.ptr(), sizeof(brt_sky)};
+    upload(s, c->d_scene_info, &c->scene_info, sizeof(c->scene_info));
+  }
   // world box of all instances (centre / extent form of |M| box): the grid of the bounce rounds' hit sort
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (const InstanceData& in : c->instances) {
@@ -997,9 +1021,6 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   if (!o.width || !o.height || !o.spp) invalid("render_frame: width, height and spp must be non-zero");
   const bool lbvh = (o.flags & BRT_RENDER_LIGHT_BVH) != 0u;
   if (!lbvh && c->lights.size() > BRT_MAX_LIGHTS) throw LimitError("render_frame: more than BRT_MAX_LIGHTS lights (use BRT_RENDER_LIGHT_BVH)");
-  if (lbvh)
-    for (const brt_light& l : c->lights)
-      if (l.type != BRT_LIGHT_POINT) bad_state("render_frame: BRT_RENDER_LIGHT_BVH needs POINT lights only");
   if (c->tables_dirty || c->tlas_dirty) {
     // the tables are uploaded (and the TLAS built) on the context's stream; frames of slots >= 1 run on their own non-blocking
     // streams, so the scene must be in place before any of them is enqueued (a scene change is rare: a plain wait is enough)
@@ -1141,7 +1162,8 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           tp.hit_inst = f->d_hit_inst.as<uint32_t>();
           tp.work = &ctr->work_closest;
           tp.stats = fst;
-          tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;  // measured: refill pays for bounce rays only
+          tp.refill_lanes = round == 0 ? c->refill_primary : c->refill_bounce;  // measured: refill pays for bounce rays only
+          tp.defer_lanes = round == 0 ? c->defer_primary : c->defer_bounce;
           Timed t(f, CLS_CLOSEST, s);
           launch_trace<false>(c, tp, s);
           launches++;
@@ -1217,7 +1239,8 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   #ifdef BRT_EMU
           BRT_LAUNCH_1D(k_shade, sp, 1, 128, s);
   #else
-          if (round == 0) k_shade_primary<<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
+          if (o.flags & BRT_RENDER_FAST_SHADING) launch_shade_fast(sp, grid_for(c, capw, 128, 16), round == 0, s);
+          else if (round == 0) k_shade_primary<<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
           else k_shade<BRT_SHADE_WINDOW><<<grid_for(c, capw, 128, 16), 128, 0, s>>>(sp);
   #endif
           BRT_CHECK_LAUNCH();
@@ -1241,7 +1264,8 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           tp.contrib = f->d_contrib[par].as<float4>();
           tp.work = &sctr[par].work_occl;
           tp.stats = fst;
-          tp.refill_lanes = round == 0 ? 0u : BRT_REFILL_LANES_INCOHERENT;
+          tp.refill_lanes = round == 0 ? c->refill_primary : c->refill_bounce;
+          tp.defer_lanes = round == 0 ? c->defer_primary : c->defer_bounce;
           Timed t(f, CLS_OCCL, s2);
           launch_trace<true>(c, tp, s2);
           launches++;
@@ -1550,6 +1574,10 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count, (c->flags & BRT_CFG_GREEDY_COLLAPSE) != 0, (c->flags & BRT_CFG_TREELET_PASSES_3) != 0));
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
+    if (const char* e = getenv("BRT_REFILL_PRIMARY")) c->refill_primary = (uint32_t)std::max(0L, std::min(32L, atol(e)));
+    if (const char* e = getenv("BRT_REFILL_BOUNCE")) c->refill_bounce = (uint32_t)std::max(0L, std::min(32L, atol(e)));
+    if (const char* e = getenv("BRT_DEFER_PRIMARY")) c->defer_primary = (uint32_t)std::max(0L, std::min(32L, atol(e)));  // tuning aids
+    if (const char* e = getenv("BRT_DEFER_BOUNCE")) c->defer_bounce = (uint32_t)std::max(0L, std::min(32L, atol(e)));
   });
   if (rc != BRT_OK) {
     g_create_error = c->err;
@@ -1682,6 +1710,7 @@ int brt_sky_set(brt_context* c, const brt_sky* sky) {
   return guarded(c, [&] {
     if (!sky) invalid("sky_set: null");
     c->sky = *sky;
+    c->tables_dirty = true;  // (the device copy behind SceneBufferInfo.skyBuf)
   });
 }
 
@@ -1807,6 +1836,32 @@ int brt_get_visibility(brt_context* c, uint8_t* out, uint32_t n) {
   return guarded(c, [&] {
     if (!out || n != c->instances.size()) invalid("get_visibility: size mismatch");
     std::memcpy(out, c->visible.data(), n);
+  });
+}
+
+int brt_get_scene_info_buffer(brt_context* c, brt_scene_buffer_info* out, uint64_t* d_copy) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!out) invalid("get_scene_info_buffer: null");
+    if (!c->built) bad_state("get_scene_info_buffer: scene not built");
+    BRT_CUDA(cudaSetDevice(c->device));
+    if (c->tables_dirty) {
+      wait_all_frames(c);
+      build_tables(c);
+      BRT_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *out = c->scene_info;
+    if (d_copy) *d_copy = (uint64_t)c->d_scene_info.ptr();
+  });
+}
+
+int brt_get_tlas(brt_context* c, brt_accel_info* out) {
+  if (!c) return BRT_ERR_INVALID;
+  return guarded(c, [&] {
+    if (!out) invalid("get_tlas: null");
+    if (!c->built) bad_state("get_tlas: scene not built");
+    const uint64_t nodes = c->tlas_count ? (uint64_t)c->d_tlas_nodes.ptr() : 0;
+    *out = brt_accel_info{nodes, nodes, c->tlas_count ? (uint64_t)c->d_tlas_inst.ptr() : 0, nodes, c->tlas.n_nodes, c->tlas_count};
   });
 }
 
@@ -2154,6 +2209,8 @@ int brt_trace_rays(brt_context* c, const float* rays, uint32_t n, int closest, u
     tp.o = d_o;
     tp.d = d_d;
     tp.stats = f->d_fstats.as<FrameStats>();
+    tp.refill_lanes = BRT_REFILL_LANES_INCOHERENT;  // arbitrary rays: the schedule of the bounce rounds
+    tp.defer_lanes = c->defer_bounce;
     std::vector<float> hit((size_t)n * 4);
     std::vector<uint32_t> inst(n);
     if (closest) {

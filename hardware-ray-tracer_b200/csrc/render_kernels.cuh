@@ -153,6 +153,7 @@ struct TraceParams {
   const uint32_t* seg_counts;
   uint32_t n_segs, seg_stride;
   uint32_t refill_lanes;  // device kernel: idle lanes fetch new rays when fewer than this many lanes are still traversing
+  uint32_t defer_lanes;   // device kernel: > 0 = deferred-leaf mode, a pass of parked primitive tests runs once this many lanes have one
 };
 BRT_HD uint32_t trace_total(const TraceParams& p) {
   if (p.seg_counts) {
@@ -232,7 +233,8 @@ struct ShadeParams {
 // Light BVH sampling (RT/Scene.h:123-130, SH/raytracing.slang:76; rule in DESIGN.md §13): stochastic descent from the root, a child
 // is taken with probability ~ totalFlux / max(squared distance to its box centre, squared half-diagonal of its box); the single
 // random number is rescaled at every level. Returns the light index, inv_pdf = 1 / (product of the branch probabilities).
-BRT_HD float light_node_importance(const float4 a, const float4 b, f3 P) {  // a = min.xyz, max.x   b = max.yz, flux, cone.x
+BRT_HD float light_node_importance(const float4 a, const float4 b, const float4 c, f3 P) {  // a = min.xyz, max.x   b = max.yz, flux, cone.x   c = cone.yz, angle, child
+  if (c.z == 0.0f) return b.z;  // a subtree of constant-direction lights (cone angle 0): no falloff, the same from everywhere
   const f3 lo = F3(a.x, a.y, a.z), hi = F3(a.w, b.x, b.y);
   const f3 ctr = (lo + hi) * 0.5f, hd = (hi - lo) * 0.5f;
   const f3 d = P - ctr;
@@ -244,8 +246,8 @@ BRT_HD uint32_t sample_light_bvh(const float4* __restrict__ nodes, f3 P, float r
   for (int guard = 0; guard < 64; ++guard) {
     const int child = (int)f2u(nodes[3 * (size_t)node + 2].w);
     if (child < 0) break;
-    const float w0 = light_node_importance(nodes[3 * (size_t)child], nodes[3 * (size_t)child + 1], P);
-    const float w1 = light_node_importance(nodes[3 * (size_t)child + 3], nodes[3 * (size_t)child + 4], P);
+    const float w0 = light_node_importance(nodes[3 * (size_t)child], nodes[3 * (size_t)child + 1], nodes[3 * (size_t)child + 2], P);
+    const float w1 = light_node_importance(nodes[3 * (size_t)child + 3], nodes[3 * (size_t)child + 4], nodes[3 * (size_t)child + 5], P);
     const float sum = w0 + w1;
     const float p0 = sum > 0.0f ? w0 / sum : 0.5f;
     if (r < p0 || p0 >= 1.0f) {

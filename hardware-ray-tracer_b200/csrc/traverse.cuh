@@ -245,6 +245,106 @@ struct Traversal {
     Gt = make_uint2(0u, 0u);
   }
 
+  // Tests ONE pending leaf slot of Gt (a triangle, or an instance: sphere test / BLAS entry). Returns true when that ends the ray
+  // (an occlusion query found its hit).
+  BRT_HDM bool leaf_visit(uint2* __restrict__ stack, TraceCounters& ctr) {
+    // hit bit p <-> slot p ^ octinv; a leaf slot's record is prim_base + its rank among the node's leaf slots
+    const uint32_t slot = (uint32_t)(ffs32(Gt.y) - 1) ^ rb.octinv;
+    Gt.y &= Gt.y - 1u;
+    const uint32_t rank = (uint32_t)popc((Gt.y >> 8) & ~(0xffffffffu << slot));
+    if (blas_sp >= 0) {
+      const TriRec* tr = tris + (uint32_t)(Gt.x + rank);
+      const float4 a = ldg4(&tr->v0), b = ldg4(&tr->v1), c = ldg4(&tr->v2);
+      if (COUNT) ctr.prims++;
+      float t, u, v;
+      // (an occlusion query ends at its first hit, so `found` is still false here: the interval test is a compile-time choice)
+      if (intersect_tri(co, sh, tmin, best.t, ANY ? false : found, xyz(a), xyz(b), xyz(c), t, u, v)) {
+        found = true;  // (for ANY this is the answer)
+        if (ANY) return true;
+        const uint32_t prim = f2u(a.w);
+        if (best.inst == BRT_MISS || t < best.t || cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)) {
+          best.t = t; best.u = u; best.v = v; best.inst = cur_inst; best.prim = prim;
+        }
+      }
+    } else {
+      const InstRec* ir = insts + (uint32_t)(Gt.x + rank);
+      const float4 m0 = ldg4(&ir->w2o[0]), m1 = ldg4(&ir->w2o[1]), m2 = ldg4(&ir->w2o[2]);
+      const uint4 tail = ldg4(reinterpret_cast<const uint4*>(&ir->kind));
+      const float4 m[3] = {m0, m1, m2};
+      f3 o, d;
+      load_world(stack, o, d);
+      const f3 oo = xform_point(m, o), od = xform_dir(m, d);
+      if (tail.x == 1u) {  // analytic sphere
+        const float4 s = ldg4(&ir->sphere);
+        if (COUNT) ctr.spheres++;
+        float t;
+        if (intersect_sphere(oo, od, tmin, best.t, ANY ? false : found, xyz(s), s.w, t)) {
+          found = true;
+          if (ANY) return true;
+          if (best.inst == BRT_MISS || t < best.t || tail.y < best.inst) {
+            best.t = t; best.u = 0.0f; best.v = 0.0f; best.inst = tail.y; best.prim = 0u;
+          }
+        }
+      } else {
+        // enter the BLAS: keep the TLAS continuation on the stack
+        if (Gt.y & 0xffu) push(stack, Gt);
+        if (G.y & 0xff000000u) push(stack, G);
+        blas_sp = sp;
+        const uint4 ptrs = ldg4(reinterpret_cast<const uint4*>(&ir->nodes));
+        nodes = reinterpret_cast<const Node8*>(((uint64_t)ptrs.y << 32) | ptrs.x);
+        tris = reinterpret_cast<const TriRec*>(((uint64_t)ptrs.w << 32) | ptrs.z);
+        cur_inst = tail.y;
+        co = oo;
+        rb = make_raybox(od);
+        sh = make_shear(od);
+        G = make_uint2(0u, 0x80000000u);
+        Gt = make_uint2(0u, 0u);
+      }
+    }
+    return false;
+  }
+
+  // ---- deferred-leaf mode (the warp-synchronous loop of k_trace, bounce rounds) ---------------------------------------------------
+  // In an incoherent wavefront a lane reaches a leaf slot only every fourth node step, so the primitive tests of step() ran with 3 of 32
+  // lanes and took 37 % of the kernel's issue slots (ncu source view, profiles/r2_traversal.md). Here a lane PARKS its leaf hits in Gt
+  // and keeps visiting nodes; the warp votes, and once enough lanes have a parked leaf (or nobody has node work left) all of them test
+  // one primitive each in the same pass. Results do not depend on the order of the tests (closest hit = lexicographic minimum).
+  BRT_HDM bool can_node() const { return (G.y & 0xff000000u) != 0u; }
+  BRT_HDM bool leaf_pending() const { return (Gt.y & 0xffu) != 0u; }
+  BRT_HDM void node_visit(uint2* __restrict__ stack, TraceCounters& ctr) {
+    const int bit = 31 - clz32(G.y);
+    G.y &= ~(1u << bit);
+    if (G.y & 0xff000000u) push(stack, G);
+    const uint32_t slot = (uint32_t)(bit - 24) ^ rb.octinv;
+    const uint32_t rel = popc(G.y & ~(0xffffffffu << slot));
+    if (COUNT) ctr.nodes++;
+    const Node8* np = nodes + (uint32_t)(G.x + rel);
+    uint2 nGt;
+    intersect_node(ldg4(&np->q[0]), ldg4(&np->q[1]), ldg4(&np->q[2]), ldg4(&np->q[3]), ldg4(&np->q[4]), rb, co, tmin, best.t, G, nGt);
+    if (nGt.y & 0xffu) {
+      if (Gt.y & 0xffu) push(stack, Gt);  // an older parked group goes to the stack (it is popped before anything below it)
+      Gt = nGt;
+    }
+  }
+  // both registers empty: leave an exhausted BLAS, fetch the next group from the stack; true when nothing is left
+  BRT_HDM bool advance(uint2* __restrict__ stack) {
+    if ((G.y & 0xff000000u) || (Gt.y & 0xffu)) return false;
+    if (blas_sp >= 0 && sp == blas_sp) {
+      blas_sp = -1;
+      nodes = tlas;
+      restore_world(stack);
+    }
+    if (sp == 0) return true;
+    const uint2 g = pop(stack);
+    if (g.y & 0xff000000u) {
+      G = g;
+    } else {
+      Gt = g;
+      G = make_uint2(0u, 0u);
+    }
+    return false;
+  }
+
   // One round: visit at most one node, then the pending leaf group. Returns true when the ray is done.
   BRT_HDM bool step(uint2* __restrict__ stack, TraceCounters& ctr) {
     if (G.y & 0xff000000u) {
@@ -277,59 +377,7 @@ struct Traversal {
     }
 
     while (Gt.y & 0xffu) {
-      // hit bit p <-> slot p ^ octinv; a leaf slot's record is prim_base + its rank among the node's leaf slots
-      const uint32_t slot = (uint32_t)(ffs32(Gt.y) - 1) ^ rb.octinv;
-      Gt.y &= Gt.y - 1u;
-      const uint32_t rank = (uint32_t)popc((Gt.y >> 8) & ~(0xffffffffu << slot));
-      if (blas_sp >= 0) {
-        const TriRec* tr = tris + (uint32_t)(Gt.x + rank);
-        const float4 a = ldg4(&tr->v0), b = ldg4(&tr->v1), c = ldg4(&tr->v2);
-        if (COUNT) ctr.prims++;
-        float t, u, v;
-        // (an occlusion query ends at its first hit, so `found` is still false here: the interval test is a compile-time choice)
-        if (intersect_tri(co, sh, tmin, best.t, ANY ? false : found, xyz(a), xyz(b), xyz(c), t, u, v)) {
-          found = true;  // (for ANY this is the answer)
-          if (ANY) return true;
-          const uint32_t prim = f2u(a.w);
-          if (best.inst == BRT_MISS || t < best.t || cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)) {
-            best.t = t; best.u = u; best.v = v; best.inst = cur_inst; best.prim = prim;
-          }
-        }
-      } else {
-        const InstRec* ir = insts + (uint32_t)(Gt.x + rank);
-        const float4 m0 = ldg4(&ir->w2o[0]), m1 = ldg4(&ir->w2o[1]), m2 = ldg4(&ir->w2o[2]);
-        const uint4 tail = ldg4(reinterpret_cast<const uint4*>(&ir->kind));
-        const float4 m[3] = {m0, m1, m2};
-        f3 o, d;
-        load_world(stack, o, d);
-        const f3 oo = xform_point(m, o), od = xform_dir(m, d);
-        if (tail.x == 1u) {  // analytic sphere
-          const float4 s = ldg4(&ir->sphere);
-          if (COUNT) ctr.spheres++;
-          float t;
-          if (intersect_sphere(oo, od, tmin, best.t, ANY ? false : found, xyz(s), s.w, t)) {
-            found = true;
-            if (ANY) return true;
-            if (best.inst == BRT_MISS || t < best.t || tail.y < best.inst) {
-              best.t = t; best.u = 0.0f; best.v = 0.0f; best.inst = tail.y; best.prim = 0u;
-            }
-          }
-        } else {
-          // enter the BLAS: keep the TLAS continuation on the stack
-          if (Gt.y & 0xffu) push(stack, Gt);
-          if (G.y & 0xff000000u) push(stack, G);
-          blas_sp = sp;
-          const uint4 ptrs = ldg4(reinterpret_cast<const uint4*>(&ir->nodes));
-          nodes = reinterpret_cast<const Node8*>(((uint64_t)ptrs.y << 32) | ptrs.x);
-          tris = reinterpret_cast<const TriRec*>(((uint64_t)ptrs.w << 32) | ptrs.z);
-          cur_inst = tail.y;
-          co = oo;
-          rb = make_raybox(od);
-          sh = make_shear(od);
-          G = make_uint2(0u, 0x80000000u);
-          Gt = make_uint2(0u, 0u);
-        }
-      }
+      if (leaf_visit(stack, ctr)) return true;
     }
 
     if (!(G.y & 0xff000000u)) {

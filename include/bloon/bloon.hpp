@@ -450,6 +450,22 @@ class Scene {
     else build();
     return visible;
   }
+  // Scene::getTlas() / getSceneInfoBuffer() (RT/Scene.h:150-151): the reference hands out its Vulkan acceleration structure and the buffer
+  // behind descriptor binding 3; here the device arrays of the software TLAS and the 80-byte SceneBufferInfo (host copy + the
+  // address of its device copy), whose tables keep the reference's byte layouts.
+  using AccelerationStructure = brt_accel_info;
+  using SceneBufferInfo = brt_scene_buffer_info;
+  using InstanceInfo = brt_instance_info;
+  AccelerationStructure getTlas() {
+    AccelerationStructure a{};
+    bloon::check(brt_get_tlas(ctx(), &a), ctx(), "getTlas");
+    return a;
+  }
+  SceneBufferInfo getSceneInfoBuffer(uint64_t* deviceAddress = nullptr) {
+    SceneBufferInfo info{};
+    bloon::check(brt_get_scene_info_buffer(ctx(), &info, deviceAddress), ctx(), "getSceneInfoBuffer");
+    return info;
+  }
   Core::Device& getDeviceRef() { return device; }
 
  private:

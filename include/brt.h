@@ -101,6 +101,36 @@ typedef struct brt_sky {
   float lightRadiance;
 } brt_sky;
 
+/* RT/Scene.h:84-88, 24 bytes, one per instance: what SH/objects.slang:15-28 reads through instanceBuffer. Addresses are CUDA device
+ * pointers of the mesh's vertex (stride 32) and index buffers. */
+typedef struct brt_instance_info {
+  uint64_t vertexAddress;
+  uint64_t indexAddress;
+  uint32_t materialId;
+  uint32_t pad;
+} brt_instance_info;
+
+/* RT/Scene.h:106-121 = SceneInfo of SH/raytracing.slang:17-32 (descriptor binding 3), 80 bytes: device addresses and strides of the
+ * scene tables. The tables behind the addresses have the reference's byte layouts (brt_material 52 B, brt_light 32 B, brt_instance_info
+ * 24 B, brt_sky 88 B), so device code written against the reference's SceneInfo reads them unchanged. */
+typedef struct brt_scene_buffer_info {
+  uint64_t mBuf, mStride;         /* materials */
+  uint64_t lBuf, lStride, lCount; /* lights */
+  uint64_t vStride;               /* vertex stride (32) */
+  uint64_t sBuf, sStride;         /* brt_instance_info per instance */
+  uint64_t skyBuf, skyStride;
+} brt_scene_buffer_info;
+
+/* RT/Scene.h:77-82 AccelerationStructure {handle, buffer, memory, address} of Scene::getTlas(): here the device arrays of the software
+ * TLAS (compressed 8-wide nodes, 80 B each; instance records, 96 B each). */
+typedef struct brt_accel_info {
+  uint64_t handle;   /* = address */
+  uint64_t buffer;   /* device pointer of the node array */
+  uint64_t memory;   /* device pointer of the instance-record array */
+  uint64_t address;  /* device pointer of the root node */
+  uint32_t n_nodes, n_instances; /* extra */
+} brt_accel_info;
+
 /* ---- library-specific PODs ------------------------------------------------------------------ */
 
 typedef struct brt_config {
@@ -152,6 +182,8 @@ typedef struct brt_config {
 /* run the denoiser stages (brt_denoise_configure) right after the resolve, on the frame's own stream: the image handed back (and
  * converted to the present format) is the denoised one. Implies BRT_RENDER_GBUFFER. Frames must be submitted in display order. */
 #define BRT_RENDER_DENOISE 128u
+#define BRT_RENDER_FAST_SHADING 2048u /* opt-in: shade kernels with FMA contraction and approximate division / rsqrt (not bit-identical to the
+                                       * oracle any more; primary ids unchanged, radiance within the 1e-3 relative RMSE bar) */
 #define BRT_RENDER_GBUFFER 32u       /* also keep world position + shading normal of the primary hit (input of brt_denoise) */
 
 /* Output format of the image handed back by the render entry points (bits 8..10 of brt_render_opts.flags): the format
@@ -262,6 +294,12 @@ BRT_API int brt_smart_cull(brt_context* ctx, const brt_uniform* u, uint32_t widt
                    float threshold_px2, float hysteresis, uint32_t* visible_count);
 /* copy the per-instance visibility flags (1 byte each) of the last brt_smart_cull to the host */
 BRT_API int brt_get_visibility(brt_context* ctx, uint8_t* out, uint32_t n);
+/* Scene::getSceneInfoBuffer() (RT/Scene.h:151; built by createSceneInformation / createSceneInfoBuffer, RT/Scene.cpp:357-403): fills
+ * *out with the 80-byte table and, if d_copy is not NULL, stores the device address of its copy in device memory there (what
+ * binding 3 points at). The scene must be built. */
+BRT_API int brt_get_scene_info_buffer(brt_context* ctx, brt_scene_buffer_info* out, uint64_t* d_copy);
+/* Scene::getTlas() (RT/Scene.h:150) */
+BRT_API int brt_get_tlas(brt_context* ctx, brt_accel_info* out);
 
 /* ---- render-frame entry (Pipeline::writeToUniformBuffer + traceRays, RT/RTPipeline.cpp:41-47) - */
 /* Traces the frame and, when rgba_host != NULL, copies the image back to host memory — the reference's outImage

@@ -283,8 +283,10 @@ vec3 sky_color(const brt_sky& s, vec3 dir) {
 // ---- light BVH (the reference declares LightBVHNode, RT/Scene.h:123-130, and names its purpose at SH/raytracing.slang:76;
 // there is no code to follow: the rule is DESIGN.md §13) -------------------------------------------------------
 // build: recursive median split on the widest axis of the positions, ties by light index; children adjacent, left subtree first
+// Point lights and constant-direction lights (SPOT / DIRECTIONAL: SH/light.slang:33-36) never share a subtree; the cone fields tell them apart
+// (point: axis (0,0,1), angle pi; constant direction: axis -normalize(0.9, -0.1, 0), angle 0, importance independent of the shading point).
 void light_bvh_build_node(const std::vector<brt_light>& lights, std::vector<uint32_t>& order, std::vector<brt_light_bvh_node>& nodes, uint32_t node,
-                          uint32_t first, uint32_t count) {
+                          uint32_t first, uint32_t count, bool directional) {
   brt_light_bvh_node nd{};
   for (int k = 0; k < 3; ++k) { nd.bBoxMin[k] = INFINITY; nd.bBoxMax[k] = -INFINITY; }
   float flux = 0.0f;
@@ -297,8 +299,13 @@ void light_bvh_build_node(const std::vector<brt_light>& lights, std::vector<uint
     flux = flux + std::fabs(l.intensity * ((0.2126f * l.color[0] + 0.7152f * l.color[1]) + 0.0722f * l.color[2]));
   }
   nd.totalFlux = flux;
-  nd.coneAxis[2] = 1.0f;      // point lights radiate everywhere: cone = the whole sphere
-  nd.coneAngle = 3.14159274f;
+  if (directional) {
+    nd.coneAxis[0] = -0.993883729f; nd.coneAxis[1] = 0.110431522f; nd.coneAxis[2] = 0.0f;
+    nd.coneAngle = 0.0f;
+  } else {
+    nd.coneAxis[2] = 1.0f;      // point lights radiate everywhere: cone = the whole sphere
+    nd.coneAngle = 3.14159274f;
+  }
   if (count == 1) {
     nd.childIndex = -1 - (int32_t)order[first];
     nodes[node] = nd;
@@ -315,18 +322,40 @@ void light_bvh_build_node(const std::vector<brt_light>& lights, std::vector<uint
   nd.childIndex = (int32_t)left;
   nodes[node] = nd;
   nodes.resize(nodes.size() + 2);
-  light_bvh_build_node(lights, order, nodes, left, first, mid);
-  light_bvh_build_node(lights, order, nodes, left + 1, first + mid, count - mid);
+  light_bvh_build_node(lights, order, nodes, left, first, mid, directional);
+  light_bvh_build_node(lights, order, nodes, left + 1, first + mid, count - mid, directional);
 }
 void light_bvh_build(orc_context* c) {
   c->light_bvh.clear();
   if (c->lights.empty()) return;
-  std::vector<uint32_t> order(c->lights.size());
-  for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+  const uint32_t n = (uint32_t)c->lights.size();
+  std::vector<uint32_t> order;
+  for (uint32_t i = 0; i < n; ++i)
+    if (c->lights[i].type == BRT_LIGHT_POINT) order.push_back(i);
+  const uint32_t n_point = (uint32_t)order.size();
+  for (uint32_t i = 0; i < n; ++i)
+    if (c->lights[i].type != BRT_LIGHT_POINT) order.push_back(i);
   c->light_bvh.resize(1);
-  light_bvh_build_node(c->lights, order, c->light_bvh, 0, 0, (uint32_t)order.size());
+  if (n_point == 0 || n_point == n) {
+    light_bvh_build_node(c->lights, order, c->light_bvh, 0, 0, n, n_point == 0);
+    return;
+  }
+  c->light_bvh.resize(3);  // the root separates the kinds: left = point lights, right = constant-direction lights
+  light_bvh_build_node(c->lights, order, c->light_bvh, 1, 0, n_point, false);
+  light_bvh_build_node(c->lights, order, c->light_bvh, 2, n_point, n - n_point, true);
+  brt_light_bvh_node root{};
+  for (int k = 0; k < 3; ++k) {
+    root.bBoxMin[k] = std::fmin(c->light_bvh[1].bBoxMin[k], c->light_bvh[2].bBoxMin[k]);
+    root.bBoxMax[k] = std::fmax(c->light_bvh[1].bBoxMax[k], c->light_bvh[2].bBoxMax[k]);
+  }
+  root.totalFlux = c->light_bvh[1].totalFlux + c->light_bvh[2].totalFlux;
+  root.coneAxis[2] = 1.0f;
+  root.coneAngle = 3.14159274f;
+  root.childIndex = 1;
+  c->light_bvh[0] = root;
 }
 float light_bvh_importance(const brt_light_bvh_node& n, vec3 P) {
+  if (n.coneAngle == 0.0f) return n.totalFlux;  // constant-direction lights: no falloff
   vec3 lo = V3(n.bBoxMin[0], n.bBoxMin[1], n.bBoxMin[2]), hi = V3(n.bBoxMax[0], n.bBoxMax[1], n.bBoxMax[2]);
   vec3 ctr = (lo + hi) * 0.5f, hd = (hi - lo) * 0.5f;
   vec3 d = P - ctr;
@@ -740,11 +769,7 @@ int orc_render_frame(orc_context* c, const brt_uniform* u, const brt_render_opts
   size_t npx = (size_t)o->width * o->height;
   const uint32_t format = (o->flags & BRT_RENDER_FORMAT_MASK) >> BRT_RENDER_FORMAT_SHIFT;
   if (format > BRT_FORMAT_B8G8R8A8_SRGB) return fail(c, BRT_ERR_INVALID, "render_frame: unknown BRT_RENDER_FORMAT");
-  if (o->flags & BRT_RENDER_LIGHT_BVH) {
-    for (const brt_light& l : c->lights)
-      if (l.type != BRT_LIGHT_POINT) return fail(c, BRT_ERR_STATE, "render_frame: BRT_RENDER_LIGHT_BVH needs POINT lights only");
-    light_bvh_build(c);
-  }
+  if (o->flags & BRT_RENDER_LIGHT_BVH) light_bvh_build(c);
   std::vector<float> linear;
   float* rgba = rgba_out;
   if (format != BRT_FORMAT_R32G32B32A32_SFLOAT) {

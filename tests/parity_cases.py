@@ -674,11 +674,43 @@ def light_bvh(pkg, orc_mod, make):
     r = compare_frames(pkg, a, b, u, w, h, LB | D | J, 2)
     assert r["bit_exact"]
     assert len(a.get_light_bvh()) == 2 * (n_lights + 40) - 1
-    # a non-point light cannot go into the tree
-    a.light_create((0, 0, 0), (1, 1, 1), 1.0, type=2)
-    a.scene_build()
-    with pytest.raises(pkg.BrtError):
-        a.render_frame(u, a.opts(w, h, 1, LB))
+    # SPOT / DIRECTIONAL lights (the shader's constant-direction branch, SH/light.slang:33-36) go into their own subtree under the root:
+    # cone angle 0, importance independent of the shading point; tree and frames still equal the oracle's, the estimator stays unbiased
+    a2, b2 = make(), orc_mod.Oracle(pkg)
+    for api in (a2, b2):
+        scene.upload(api, build=False)
+        for k, (pos, col, inten) in enumerate(extra[:6]):
+            api.light_create(pos, col, inten)
+        api.light_create((0, 0, 0), (0.3, 0.25, 0.2), 0.4, type=2)
+        api.light_create((0.5, 0.5, 0.5), (0.1, 0.2, 0.3), 0.3, type=1)
+        api.light_create((0.1, -0.2, 0.3), (0.2, 0.1, 0.1), 0.2, type=2)
+        api.scene_build()
+    ta, tb = a2.get_light_bvh(), b2.get_light_bvh()
+    n2 = len(scene.lights) + 6 + 3
+    assert len(ta) == len(tb) == 2 * n2 - 1 and all(bytes(x) == bytes(y) for x, y in zip(ta, tb))
+    assert ta[0].childIndex == 1 and ta[1].coneAngle > 3.0 and ta[2].coneAngle == 0.0 and abs(ta[2].coneAxis[0] + 0.9938837) < 1e-6
+    assert sorted(-1 - n.childIndex for n in ta if n.childIndex < 0) == list(range(n2))
+    for flags, spp in ((LB, 1), (LB | R | T | D | J, 2)):
+        r = compare_frames(pkg, a2, b2, u, w, h, flags, spp)
+        assert r["bit_exact"] and r["id_agreement"] == 1.0, flags
+    full = a2.render_frame(u, a2.opts(w, h, 1, 0))[..., :3].astype(np.float64)
+    est = a2.render_frame(u, a2.opts(w, h, 512, LB))[..., :3].astype(np.float64)
+    assert np.sqrt(((tm(est) - tm(full)) ** 2).mean()) < 0.02 * max(tm(full).mean(), 1e-6) + 0.004
+    # only constant-direction lights: one subtree, no root split
+    a3, b3 = make(), orc_mod.Oracle(pkg)
+    for api in (a3, b3):
+        for mesh in scene.meshes:
+            api.sphere_create(mesh[1], mesh[2]) if mesh[0] == "sphere" else api.mesh_create(mesh[1], mesh[2])
+        for md in scene.materials:
+            api.material_create(md.color, md.metallic, md.roughness, md.specular, **md.extra)
+        api.light_create((0, 0, 0), (0.5, 0.5, 0.5), 0.5, type=2)
+        api.light_create((1, 0, 0), (0.2, 0.5, 0.1), 0.25, type=1)
+        for mesh, mat, x in scene.instances:
+            api.instance_create(mesh, mat, x)
+        api.scene_build()
+    ta, tb = a3.get_light_bvh(), b3.get_light_bvh()
+    assert len(ta) == len(tb) == 3 and all(bytes(x) == bytes(y) for x, y in zip(ta, tb)) and ta[0].coneAngle == 0.0
+    assert compare_frames(pkg, a3, b3, u, w, h, LB, 1)["bit_exact"]
 
 
 def denoise_in_flight(pkg, orc_mod, make, w=96, h=96):

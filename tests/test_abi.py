@@ -41,6 +41,9 @@ def test_pod_layouts(pkg):
     assert C.sizeof(B.Uniform) == 140 and B.Uniform.projInverse.offset == 64 and B.Uniform.frame.offset == 128
     assert B.Uniform.depthMax.offset == 132 and B.Uniform.lightThreshold.offset == 136
     assert C.sizeof(B.Sky) == 88
+    # RT/Scene.h:84-88 (24 B, materialId at 16) and RT/Scene.h:106-121 (10 x u64)
+    assert C.sizeof(B.InstanceInfo) == 24 and B.InstanceInfo.indexAddress.offset == 8 and B.InstanceInfo.materialId.offset == 16
+    assert C.sizeof(B.SceneBufferInfo) == 80 and B.SceneBufferInfo.lCount.offset == 32 and B.SceneBufferInfo.sBuf.offset == 48
 
 
 def test_no_cpu_fallback(pkg):

@@ -123,6 +123,68 @@ def test_repeatable(pkg, make):
     assert np.array_equal(i1.view(np.uint32), i2.view(np.uint32))
 
 
+def test_fast_shading(pkg, orc_mod, make):
+    """BRT_RENDER_FAST_SHADING (opt-in; shade kernels with FMA contraction and approximate division / rsqrt): primary ids and hit distances
+    unchanged, ray counts unchanged up to a handful of flipped stochastic branches, radiance within the north star's 1e-3 relative RMSE of the ORACLE."""
+    from util import rel_rmse
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a, b = make(), orc_mod.Oracle(pkg)
+    scene.upload(a)
+    scene.upload(b)
+    w, h = 256, 144
+    for depth, flags, spp in ((3, pkg.BOUNCE_REFLECT | pkg.BOUNCE_REFRACT, 1), (5, pkg.BOUNCE_REFLECT | pkg.BOUNCE_REFRACT | pkg.BOUNCE_DIFFUSE | pkg.JITTER, 4)):
+        u = scene.uniform(a, w, h, 0, depth)
+        fast = a.render_frame(u, a.opts(w, h, spp, flags | pkg.FAST_SHADING)).copy()
+        ids = (a.get_aov(pkg.AOV_PRIM_ID, w, h).copy(), a.get_aov(pkg.AOV_INST_ID, w, h).copy(), a.get_aov(pkg.AOV_HIT_T, w, h).copy())
+        rays = a.get_stats().rays_closest + a.get_stats().rays_occlusion
+        ref = b.render_frame(u, b.opts(w, h, spp, flags))
+        assert np.array_equal(ids[0], b.get_aov(pkg.AOV_PRIM_ID, w, h)) and np.array_equal(ids[1], b.get_aov(pkg.AOV_INST_ID, w, h))
+        assert np.array_equal(ids[2].view(np.uint32), b.get_aov(pkg.AOV_HIT_T, w, h).view(np.uint32))
+        rb = b.get_stats().rays_closest + b.get_stats().rays_occlusion
+        assert abs(int(rays) - int(rb)) <= 1e-4 * rb
+        e = rel_rmse(fast, ref)
+        print(f"fast shading, depth {depth}: relative RMSE vs the oracle {e:.2e}, rays {rays} vs {rb}")
+        assert e <= 1e-3
+        assert not np.array_equal(fast.view(np.uint32), ref.view(np.uint32))  # (it really is another arithmetic)
+
+
+def test_scene_info_buffer_and_tlas_handles(pkg, make):
+    """Scene::getSceneInfoBuffer() / getTlas() (RT/Scene.h:150-151, tables of RT/Scene.cpp:313-403): the 80-byte SceneBufferInfo, its device
+    copy and every table behind its addresses hold what was uploaded, in the reference's byte layouts (what SH/raytracing.slang:17-32,
+    SH/objects.slang:15-59 and SH/light.slang:18-39 read through the buffer addresses)."""
+    import ctypes as C
+    import torch
+    scene = pkg.scenes.make_scene("rtapp")
+    a = make()
+    scene.upload(a)
+    info, d_copy = a.get_scene_info_buffer()
+    rt = C.CDLL("libcudart.so")
+
+    def peek(addr, nbytes):
+        buf = (C.c_char * nbytes)()
+        assert rt.cudaMemcpy(buf, C.c_void_p(addr), C.c_size_t(nbytes), 2) == 0
+        return bytes(buf)
+
+    assert (info.mStride, info.lStride, info.vStride, info.sStride, info.skyStride) == (52, 32, 32, 24, 88)
+    assert info.lCount == len(scene.lights) == 3
+    assert peek(d_copy, 80) == bytes(info)  # descriptor binding 3
+    mats = np.frombuffer(peek(info.mBuf, 52 * len(scene.materials)), np.float32).reshape(-1, 13)
+    assert np.allclose(mats[0, :3], 1.0) and mats[0, 4] == 1.0 and mats[0, 5] == 1.0 and mats[1, 5] == 0.0 and mats[0, 6] == 0.5  # RT/RTApp.cpp:6-7
+    lights = np.frombuffer(peek(info.lBuf, 32 * 3), np.float32).reshape(3, 8)
+    assert np.allclose(lights[0, :7], [1, 0, 0, 0, 0, 1, 2]) and np.allclose(lights[2, :7], [0, 0, -1, 1, 0, 0, 2])  # RT/RTApp.cpp:9-11
+    inst = np.frombuffer(peek(info.sBuf, 24 * len(scene.instances)), np.uint64).reshape(-1, 3)
+    assert [int(x) & 0xFFFFFFFF for x in inst[:, 2]] == [1, 0]  # material ids of the two instances (RT/RTApp.cpp:13-14)
+    assert inst[0, 0] == inst[1, 0] and inst[0, 1] == inst[1, 1]  # both instances use mesh 0
+    v, idx = scene.meshes[0][1], scene.meshes[0][2]
+    assert peek(int(inst[0, 0]), v.nbytes) == v.tobytes() and peek(int(inst[0, 1]), idx.nbytes) == idx.tobytes()
+    assert len(peek(info.skyBuf, 88)) == 88
+    t = a.get_tlas()
+    assert t.n_instances == 2 and t.n_nodes >= 1 and t.address == t.buffer == t.handle != 0 and t.memory != 0
+    rec = np.frombuffer(peek(t.memory, 96 * 2), np.uint32).reshape(2, 24)
+    assert sorted(int(x) for x in rec[:, 21]) == [0, 1]  # InstRec.inst_id of the two TLAS leaves
+    torch.cuda.synchronize()
+
+
 def test_hit_sort_changes_nothing_but_the_order_of_work(pkg, make):
     """BRT_CFG_HIT_SORT (bounce rounds shaded in the order of their hit positions): same bits, same ray counts, with and without a frame graph."""
     scene = pkg.scenes.make_scene("terrain", small=True)

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--greedy-collapse", action="store_true")
     ap.add_argument("--hit-sort", action="store_true", help="bounce rounds shaded in the order of their hit positions (BRT_CFG_HIT_SORT)")
     ap.add_argument("--graph", action="store_true", help="product schedule: two streams + replayed frame graph (total time only)")
+    ap.add_argument("--fast-shading", action="store_true", help="BRT_RENDER_FAST_SHADING")
     ap.add_argument("--spp", type=int, default=0, help="override the config's samples per pixel")
     args = ap.parse_args()
     pkg = importlib.import_module("hardware-ray-tracer_b200")
@@ -43,6 +44,8 @@ def main():
     u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
     if args.spp:
         cfg["spp"] = args.spp
+    if args.fast_shading:
+        cfg["flags"] |= pkg.FAST_SHADING
     for f in range(args.frames):
         ctx.render_frame(u, ctx.opts(w, h, cfg["spp"], cfg["flags"]), want_image=False)
         s = ctx.get_stats()
