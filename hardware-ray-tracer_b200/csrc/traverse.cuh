@@ -76,9 +76,12 @@ BRT_HD void intersect_node(const uint4 n0, const uint4 n1, const uint4 n2, const
   // The 2^-8 grid-step term covers the rounding of the (origin - 32768 * step) constants below.
   const float mag = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz)) + 256.0f * fmaxf(fmaxf(sx, sy), sz);
   const float slack = mag * 4.76837158e-07f;
-  const float ex = fma_rn(fabsf(idx), 0.00390625f, slack * fabsf(rb.idir.x));
-  const float ey = fma_rn(fabsf(idy), 0.00390625f, slack * fabsf(rb.idir.y));
-  const float ez = fma_rn(fabsf(idz), 0.00390625f, slack * fabsf(rb.idir.z));
+#ifndef BRT_SLACK_STEPS
+#define BRT_SLACK_STEPS 0.00390625f  // 2^-8 grid steps (experiment: larger values emulate a less precise slab test, profiles/r2_traversal.md)
+#endif
+  const float ex = fma_rn(fabsf(idx), BRT_SLACK_STEPS, slack * fabsf(rb.idir.x));
+  const float ey = fma_rn(fabsf(idy), BRT_SLACK_STEPS, slack * fabsf(rb.idir.y));
+  const float ez = fma_rn(fabsf(idz), BRT_SLACK_STEPS, slack * fabsf(rb.idir.z));
   const float ox = px * rb.idir.x, oy = py * rb.idir.y, oz = pz * rb.idir.z;
   // t = (32768 + q) * step + (origin - 32768 * step)
   const float ox0 = fma_rn(-32768.0f, idx, ox - ex), ox1 = fma_rn(-32768.0f, idx, ox + ex);

@@ -167,7 +167,8 @@ class World:
         return [(t[k], u[k], v[k]) + self.owner[k] for k in hit], fragile
 
 
-def run_scene(mod, host, sc):
+def run_scene(mod, host, sc, pixels=None):
+    """pixels: optional list of (x, y) to run (the regeneration spot check of tests/test_spv_kat.py); default all."""
     mem = Memory()
     it = Interpreter(mod, mem)
     # --- host side, as Scene::build lays it out (RT/Scene.cpp:313-403) ---
@@ -273,6 +274,8 @@ def run_scene(mod, host, sc):
     rays = shadow = 0
     for y in range(h):
         for x in range(w):
+            if pixels is not None and (x, y) not in pixels:
+                continue
             state.update(fragile=False, rays=0, shadow_rays=0, depth=0, prim=-1, inst=-1, t=-1.0, slack=0.0, probing=False)
             it.image_writes.clear()
             it.run("rgenMain", {"LaunchIdKHR": [x, y, 0], "LaunchSizeKHR": [w, h, 1]})
