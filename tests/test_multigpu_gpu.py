@@ -127,3 +127,45 @@ def test_two_gpu_exchange_modes(pkg, tmp_path):
     for k in range(9):
         want = ref(20 + k, pkg.render_format(pkg.FORMAT_BGRA8_UNORM))
         assert np.array_equal(root8[k], want), ("root only, B8G8R8A8_UNORM", k)
+
+
+def test_flag_protocol_on_one_gpu(pkg):
+    """The fused exchange with a world of ONE rank (its own and only receiver): the same kernels as on N GPUs — resolve with peer stores into
+    gather image `slot`, arrival flag published by the last block, device-side wait before the copy-out, release, and the producer's
+    device-side wait for that release four frames later — run on the single-GPU test box. Nine different frames over the four slots, never
+    more than the copy stream between host and device: every frame equals a plain brt_render_frame, in RGBA32F and in B8G8R8A8."""
+    a = pkg.Context(device=0)
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    scene.upload(a)
+    w, h = 300, 200
+    a.gather_image_open([a.gather_image_export(w, h)])
+    a.gather_configure(True, 0)
+    copy_stream = torch.cuda.Stream()
+    for fmt, dtype in ((0, torch.float32), (pkg.render_format(pkg.FORMAT_BGRA8_UNORM), torch.uint8)):
+        hosts = [torch.empty(h * w * 4, dtype=dtype).pin_memory() for _ in range(4)]
+        got = []
+        n = 9
+        for k in range(n):
+            slot = k % 4
+            if k >= 4:
+                copy_stream.synchronize()  # (host buffer reuse; the device side needs no help)
+                got.append(hosts[slot].numpy().reshape(h, w, 4).copy())
+            a.render_frame_peers_async(scene.uniform(a, w, h, 30 + k, 3), a.opts(w, h, 2, 3 | fmt), slot)
+            a.gather_copy_to_host(slot, hosts[slot].data_ptr(), copy_stream.cuda_stream)
+        copy_stream.synchronize()
+        for k in range(max(0, n - 4), n):
+            got.append(hosts[k % 4].numpy().reshape(h, w, 4).copy())
+        for k in range(4):
+            a.frame_wait(k)
+        assert a.gather_timed_out() == 0
+        for k in range(n):
+            want = a.render_frame(scene.uniform(a, w, h, 30 + k, 3), a.opts(w, h, 2, 3 | fmt))
+            assert np.array_equal(got[k], want), (fmt, k)
+    # misuse is an error, not a crash
+    with pytest.raises(pkg.BrtError):
+        a.render_frame_peers_async(scene.uniform(a, w, h, 0, 3), a.opts(w, h, 2, 3), 4)       # slot >= BRT_GATHER_IMAGES
+    with pytest.raises(pkg.BrtError):
+        a.render_frame_peers_async(scene.uniform(a, w, h, 0, 3), a.opts(w + 32, h, 2, 3), 0)  # another frame size than exported
+    with pytest.raises(pkg.BrtError):
+        a.gather_configure(True, 0)                                                            # after the first frame
+    a.close()
