@@ -1,5 +1,9 @@
 /*
- * ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (the reference has no tests / CPU path).
+ * ORACLE — TEST INFRASTRUCTURE ONLY. Kind "port", PINNED to the reference itself: it reproduces frames computed by
+ * executing the reference's shipped shader binary (tests/golden/spv_kat.json, tests/test_spv_kat.py), its host maths agree with the
+ * reference's own Camera.cpp / MeshInstance.h / glm compiled into oracle/_ref (tests/test_ref_pin.py), its RNG with the integer
+ * KATs of SH/random.slang (tests/golden/rng_kat.json). Not pinnable by any reference artefact, because the reference has no source
+ * for them: BVH build, traversal, the ray/triangle test (brute force + analytic cases instead) and the extensions of DESIGN.md §7.
  *
  * C API of the CPU oracle (liboracle.so): a scalar, multithreaded C++ restatement of the
  * reference's shaders/ logic plus the driver pieces that have no source (BVH, ray/triangle test).
