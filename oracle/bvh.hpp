@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see shaders.hpp header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see shaders.hpp header). PARITY UNPINNED for this file: nothing in the reference can pin it.
 //
 // The reference has no BVH or intersection source: both live in the Vulkan driver / RT cores behind
 // vkCmdBuildAccelerationStructuresKHR (RT/Scene.cpp:304) and TraceRay (SH/raytracing.slang:67,121).

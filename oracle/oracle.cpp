@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see shaders.hpp header).
+// ORACLE — TEST INFRASTRUCTURE ONLY. Pinned to the reference's shader binary and host code where they exist (see shaders.hpp header).
 //
 // Scene container, two-level BVH queries, the path loop of SH/raytracing.slang and the C API of
 // oracle.h. Shorthand: SH/ = reference shaders/, RT/ = reference Graphics/RayTracing/.

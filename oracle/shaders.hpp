@@ -1,10 +1,12 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product; only tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs may load it.
 //
-// PARITY UNPINNED: the reference (CodingBloon/Hardware-Ray-Tracer) has no tests, golden vectors or
-// CPU path. This file is a scalar C++ restatement of the reference's Slang
-// shaders; the only independent pins are the integer KATs of SURVEY.md Appendix C (re-derived in
-// tests/test_oracle_rng.py) and analytic cases.
+// PINNED TO THE REFERENCE: the reference (CodingBloon/Hardware-Ray-Tracer) has no tests, golden vectors or
+// CPU path, but its shipped shader binary can be executed: this scalar C++ restatement of the Slang
+// shaders reproduces the frames that oracle/ref/spv_interp.py computes from shaders/raytracing.slang.spv
+// (tests/golden/spv_kat.json, tests/test_spv_kat.py: BRDF, processLight, calculateColor, geometry fetch, ray generation). hash / pcg /
+// rand are dead code in that binary: pinned by the integer KATs of SURVEY.md Appendix C (tests/test_oracle_kat.py); the samplers by
+// analytic cases.
 //
 // Shorthand: SH/ = /root/reference/Hardware Ray Tracer/shaders/
 //
