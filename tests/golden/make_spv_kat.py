@@ -16,10 +16,13 @@ What is the reference's and what is the harness's:
   miss index 0 runs rmissMain, miss index 2 runs rmissShadowMain, a shadow hit runs nothing
   (SKIP_CLOSEST_HIT_SHADER). ObjectToWorld / WorldToObject are the instance's 3x4 and its inverse (float64, rounded once).
   `slack` (per pixel) is how far the closest-hit shader's radiance moves when those implementation-defined inputs move by
-  what a binary32 intersector leaves open (barycentrics +-4e-6, ray direction 2e-7; seven one-at-a-time probes, summed): the
-  conditioning of the pixel (a GGX lobe of small roughness amplifies an ulp a thousandfold); the tests widen their bar by it.
+  what a binary32 intersector leaves open (barycentrics up to 4e-6: four axis shifts and nine random ones; ray direction 2e-7; the
+  largest change of the sixteen probes): the conditioning of the pixel, including the binary32 rounding noise of the evaluation
+  itself at the peak of a sharp lobe (a clear-coat or GGX lobe of small roughness amplifies an ulp a thousandfold); the tests widen
+  their bar by a multiple of it.
   A pixel is flagged `fragile` when one of its rays passes within 1e-5 (barycentric units) of a triangle edge or within a relative
-  1e-5 of an interval end: there a different (equally valid) intersector may decide differently, tests skip those pixels.
+  1e-5 of an interval end, or when a point light's intensity at the hit is within 0.5 % of LIGHT_TRESHOLD: there a different (equally
+  valid) intersector may decide differently, tests skip those pixels.
 
 Scenes obey `instances[m].meshId == m` for every used mesh id so that the shader's meshID-indexed address lookup
 (SH/raytracing.slang:143-144) reads the intended mesh.
@@ -124,6 +127,36 @@ def scenes():
                         cam_pos=(float(rng.normal() * 0.3), float(-0.6 + rng.normal() * 0.2), -2.6),
                         cam_rot=(float(-0.15 + rng.normal() * 0.05), float(rng.normal() * 0.1), float(rng.normal() * 0.05) if s >= 2 else 0.0),
                         fovy=float(np.float32(np.radians([60.0, 45.0, 75.0, 50.0][s])))))
+    # 6. eight lights (the loop bound numLights comes from the buffer, SH/raytracing.slang:77), three of them in the constant-direction branch,
+    # two under the threshold; a glossy floor so that every light leaves a visible lobe
+    floor = quad((-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1))
+    ball_v, ball_i = quad((-0.5, -0.5, 0), (0.5, -0.5, 0), (0.5, 0.5, 0), (-0.5, 0.5, 0))
+    ball_v[:, 3:6] = ball_v[:, 0:3] * np.float32(1.2) + np.array([0, 0, -1], np.float32)
+    ball_v[:, 3:6] /= np.linalg.norm(ball_v[:, 3:6], axis=1, keepdims=True)
+    lights = []
+    for k in range(8):
+        ang = 2 * np.pi * k / 8
+        lights.append(((float(2.2 * np.cos(ang)), float(-1.5 - 0.1 * k), float(1.0 + 2.2 * np.sin(ang))),
+                       (float(0.2 + 0.1 * k), float(0.9 - 0.1 * k), float(0.3 + 0.05 * k)),
+                       float([3.0, 2.5, 0.4, 2.0, 0.0004, 0.3, 1.5, 0.00002][k]), int([0, 0, 2, 0, 0, 1, 0, 2][k])))
+    out.append(dict(name="eight_lights", width=36, height=27, depth_max=2, meshes=[floor, (ball_v, ball_i)],
+                    materials=[material((0.7, 0.7, 0.7), roughness=0.35, metallic=0.5, specular=0.8), material((0.9, 0.4, 0.2), roughness=0.5, clearCoat=1.0, clearCoatGloss=0.8, sheen=1.0, sheenTint=0.5)],
+                    lights=lights, instances=[(0, 0, (0, 0.8, 1.0), (3.0, 1.0, 3.0)), (1, 1, (0.0, -0.1, 1.2), (1.4, 1.4, 1.0))],
+                    cam_pos=(0.2, -0.9, -2.2), cam_rot=(-0.25, -0.05, 0.0), fovy=float(np.float32(np.radians(55.0)))))
+    # 7. the extremes of the material fields (every field at 0 or 1, roughness down to the max(0.001, .) clamps of SH/disney.slang:71-77)
+    panel = quad((-0.5, -0.5, 0), (0.5, -0.5, 0), (0.5, 0.5, 0), (-0.5, 0.5, 0))
+    mats = [material((0.8, 0.8, 0.8))]
+    inst = [(0, 0, (0, 1.0, 1.0), (3.0, 1.0, 3.0)), (1, 1, (-1.35, 0.35, 1.2), (0.85, 0.85, 1.0))]
+    ext = [dict(metallic=1.0, roughness=0.0), dict(metallic=0.0, roughness=0.02, specular=1.0, specularTint=1.0), dict(anisotropic=1.0, roughness=0.3, metallic=1.0),
+           dict(clearCoat=1.0, clearCoatGloss=1.0, roughness=1.0), dict(sheen=1.0, sheenTint=1.0, subsurface=1.0, roughness=1.0), dict(subsurface=1.0, roughness=0.5, specular=0.0),
+           dict(metallic=1.0, roughness=1.0, anisotropic=1.0), dict(roughness=0.05, clearCoat=1.0, clearCoatGloss=0.0, specularTint=1.0)]
+    mats.append(material((0.9, 0.85, 0.7), **ext[0]))
+    for k, e in enumerate(ext[1:]):
+        mats.append(material((0.3 + 0.08 * k, 0.9 - 0.09 * k, 0.5), **e))
+        inst.append((1, 2 + k, (float(-1.35 + 0.9 * ((k + 1) % 4)), float(0.35 - 0.9 * ((k + 1) // 4)), 1.2), (0.85, 0.85, 1.0)))
+    out.append(dict(name="material_extremes", width=40, height=24, depth_max=2, meshes=[quad((-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1)), panel],
+                    materials=mats, lights=[((0.8, -1.2, -1.0), (1.0, 0.95, 0.9), 5.0, 0), ((-1.5, -0.4, -0.6), (0.6, 0.7, 1.0), 3.0, 0)], instances=inst,
+                    cam_pos=(0.0, -0.1, -2.4), cam_rot=(0.0, 0.0, 0.0), fovy=float(np.float32(np.radians(60.0)))))
     return out
 
 
@@ -230,19 +263,32 @@ def run_scene(mod, host, sc, pixels=None):
             t, u, v, inst, prim = hits[0]
             if state["depth"] == 0:
                 state["prim"], state["inst"], state["t"] = prim, inst, float(t)
+                # the light loop skips a light whose intensity at the hit is under LIGHT_TRESHOLD = 1e-4 (SH/raytracing.slang:79): a pixel
+                # where a light sits within 0.5 % of that threshold may legitimately include or skip it
+                P = np.asarray(call.origin, np.float64) + float(t) * np.asarray(call.direction, np.float64)
+                for lp, _lc, li, lt in sc["lights"]:
+                    if lt == 0:
+                        inten = li / max(float(((np.asarray(lp, np.float64) - P) ** 2).sum()), 1e-300)
+                        if abs(inten - 1e-4) < 5e-7:
+                            state["fragile"] = True
             state["depth"] += 1
             mesh = sc["instances"][inst][0]
             builtins = {"InstanceId": inst, "InstanceCustomIndexKHR": mesh, "PrimitiveId": prim, "ObjectToWorldKHR": o2w[inst],
                         "WorldToObjectKHR": w2o[inst], "WorldRayDirectionKHR": list(call.direction)}
             probes = []
             if first:
-                # conditioning of this pixel: the closest-hit shader again with ONE of its implementation-defined inputs moved —
-                # u, v by 4e-6 (a binary32 ray/triangle test resolves barycentrics to ~1e-7 x (distance / triangle size)^2; RT hardware
-                # is no better), each ray-direction component by 2e-7 relative; the sum of the radiance changes is recorded as `slack`
+                # conditioning of this pixel: the closest-hit shader again with its implementation-defined inputs moved — u, v by up to
+                # 4e-6 (a binary32 ray/triangle test resolves barycentrics to ~1e-7 x (distance / triangle size)^2; RT hardware is no
+                # better): the four axis shifts and nine random ones, because at the peak of a sharp lobe the first derivative vanishes
+                # and what is left is the binary32 rounding noise of the evaluation itself (a jump of 7e-5 between u - 2e-6 and u - 4e-6
+                # was seen on a clear-coat highlight); each ray-direction component by 2e-7 relative. `slack` = the largest radiance change
                 import copy as _copy
                 state["probing"] = True
-                for du, dv, dd in ((4e-6, 0, (0, 0, 0)), (-4e-6, 0, (0, 0, 0)), (0, 4e-6, (0, 0, 0)), (0, -4e-6, (0, 0, 0)),
-                                   (0, 0, (2e-7, 0, 0)), (0, 0, (0, 2e-7, 0)), (0, 0, (0, 0, 2e-7))):
+                prng = np.random.default_rng((state["px"] * 7919 + state["py"]) & 0xFFFFFFFF)
+                shifts = [(4e-6, 0, (0, 0, 0)), (-4e-6, 0, (0, 0, 0)), (0, 4e-6, (0, 0, 0)), (0, -4e-6, (0, 0, 0)),
+                          (0, 0, (2e-7, 0, 0)), (0, 0, (0, 2e-7, 0)), (0, 0, (0, 0, 2e-7))]
+                shifts += [(float(a), float(b), (0, 0, 0)) for a, b in prng.uniform(-4e-6, 4e-6, size=(9, 2))]
+                for du, dv, dd in shifts:
                     probe = _copy.deepcopy(call.payload_ref)
                     b2 = dict(builtins)
                     b2["WorldRayDirectionKHR"] = [F32(float(c) * (1.0 + e)) for c, e in zip(call.direction, dd)]
@@ -251,7 +297,7 @@ def run_scene(mod, host, sc, pixels=None):
                 state["probing"] = False
             it.run("rchitMain", builtins, incoming_payload=call.payload_ref, hit_attribute=[[F32(u), F32(v)]])
             if first:
-                state["slack"] = sum(max(abs(float(a) - float(b)) for a, b in zip(p[0][0], call.payload_ref[0][0])) for p in probes)
+                state["slack"] = max(max(abs(float(a) - float(b)) for a, b in zip(p[0][0], call.payload_ref[0][0])) for p in probes)
         elif call.flags == 12:  # ACCEPT_FIRST_HIT_AND_END_SEARCH | SKIP_CLOSEST_HIT_SHADER (SH/raytracing.slang:67)
             if call.miss_index != 2:
                 raise AssertionError("shadow query with a miss index other than 2")
@@ -276,7 +322,7 @@ def run_scene(mod, host, sc, pixels=None):
         for x in range(w):
             if pixels is not None and (x, y) not in pixels:
                 continue
-            state.update(fragile=False, rays=0, shadow_rays=0, depth=0, prim=-1, inst=-1, t=-1.0, slack=0.0, probing=False)
+            state.update(fragile=False, rays=0, shadow_rays=0, depth=0, prim=-1, inst=-1, t=-1.0, slack=0.0, probing=False, px=x, py=y)
             it.image_writes.clear()
             it.run("rgenMain", {"LaunchIdKHR": [x, y, 0], "LaunchSizeKHR": [w, h, 1]})
             (coord, texel), = it.image_writes

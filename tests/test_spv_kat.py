@@ -7,11 +7,12 @@ The same scenes go through the C ABI (`brt_*`, CUDA) and through the oracle; bot
 * primary (instance, primitive) ids identical on every non-fragile pixel (integers: exact),
 * radiance within REL = 2e-5 of the pixel's magnitude + 1e-7 absolute + SLACK x the pixel's measured conditioning. SPIR-V leaves
   sqrt / normalize / length / pow / log2 / division and FMA contraction to a few ulps and TraceRay's barycentrics are
-  implementation-defined (a binary32 ray/triangle test resolves them to ~4e-6 on these scenes); a GGX lobe of small roughness
-  amplifies that a thousandfold. The generator measured the amplification per pixel (`slack` = radiance change when the
-  barycentrics move by +-4e-6 and the ray direction by 2e-7, seven probes summed) and the bar widens by SLACK = 4 times it
-  (observed need: 1.35; worst-conditioned pixel: slack = 0.5 % of its radiance). A wrong constant, a swapped operand or a missing term is an error of percent,
-  orders of magnitude above the bar (the median pixel agrees to 1e-7; a third of the pixels are bit-identical).
+  implementation-defined (a binary32 ray/triangle test resolves them to ~4e-6 on these scenes); a clear-coat or GGX lobe of small
+  roughness amplifies that — and the binary32 rounding noise of the evaluation itself — a thousandfold. The generator measured the
+  amplification per pixel (`slack` = the largest radiance change over sixteen probes: barycentrics moved by up to 4e-6 along the axes and
+  at random, the ray direction by 2e-7) and the bar widens by SLACK = 6 times it (observed need: 2.3; the worst-conditioned pixel of the
+  seven scenes has slack = 0.18 % of its radiance, the median pixel 1e-6). A wrong constant, a swapped operand or a missing term is an error
+  of percent, orders of magnitude above the bar (the median pixel agrees to 1e-7; a third of the pixels are bit-identical).
 * `fragile` pixels (a ray within 1e-5 of a triangle edge or interval end: another valid intersector may decide differently) are
   skipped; they must stay below 2 % of any frame.
 """
@@ -22,7 +23,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REL, ABS, SLACK = 2e-5, 1e-7, 4.0
+REL, ABS, SLACK = 2e-5, 1e-7, 6.0
 
 
 @pytest.fixture(scope="module")
@@ -80,7 +81,7 @@ def _check(pkg, api, case, own_uniform):
 
 
 def test_golden_file_is_the_shipped_binary(kat):
-    assert len(kat["cases"]) >= 5 and kat["generator"] == "tests/golden/make_spv_kat.py"
+    assert len(kat["cases"]) >= 7 and kat["generator"] == "tests/golden/make_spv_kat.py"
     assert len(kat["spv_sha256"]) == 64
     spv = "/root/reference/Hardware Ray Tracer/shaders/raytracing.slang.spv"
     if os.path.exists(spv):  # in the build container the vectors must belong to the binary that is there
@@ -125,6 +126,18 @@ def test_oracle_reproduces_the_shader_binary(pkg, orc_mod, kat, own_uniform):
         worst = max(worst, rel)
         assert lit > 0.3
     print(f"oracle vs raytracing.slang.spv: worst relative radiance difference {worst:.2e}")
+
+
+def test_product_shading_code_reproduces_the_shader_binary_on_the_host_emulation(pkg, emu_lib, kat):
+    """The PRODUCT's own kernel bodies (csrc/shading.cuh, render_kernels.cuh, traverse.cuh, the builder) compiled as host loops
+    (tests/emu, test infrastructure) against the binary's frames: pins the product's restatement of the shaders in the CPU-only suite too
+    (the GPU test below runs the same source as CUDA)."""
+    worst = 0.0
+    for case in kat["cases"]:
+        emu = pkg.binding.SceneApi(emu_lib, "brt_", 0, 0, 1, 0)
+        rel, lit = _check(pkg, emu, case, own_uniform=False)
+        worst = max(worst, rel)
+    print(f"product kernel bodies (host emulation) vs raytracing.slang.spv: worst relative radiance difference {worst:.2e}")
 
 
 @pytest.mark.gpu
