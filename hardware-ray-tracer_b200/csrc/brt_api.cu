@@ -375,6 +375,7 @@ struct FrameSlot {
   FrameConsts* h_consts = nullptr;  // pinned staging of the per-frame constants
   DevBuf d_consts;
   uint32_t generation = 0;          // bumped whenever the wavefront buffers are reallocated (invalidates the graph)
+  uint64_t cleared_key[3] = {~0ull, 0, 0};  // (generation, traced window, size) the full-frame clears were last done for
 #ifndef BRT_EMU
   // the whole frame, captured once per frame shape and replayed ([1]: the second gather image of the fused multi-GPU exchange)
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
@@ -419,6 +420,7 @@ struct brt_context {
   cudaEvent_t prev_head = nullptr;        // ev_head of the frame submitted last: the next frame starts behind it (staggered frames)
   uint32_t last_slot = 0;                 // slot of the frame most recently waited for (brt_get_aov / brt_device_image read it)
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
+  uint32_t rays_per_warp = 0;  // 0 = full grid always; else bounce-round launches are sized for this many rays per warp (BRT_RAYS_PER_WARP)
   uint32_t refill_primary = 0, refill_bounce = BRT_REFILL_LANES_INCOHERENT;  // lanes still busy below which a warp refills its idle lanes
   uint32_t defer_primary = 0, defer_bounce = 0;  // deferred-leaf traversal: lanes with a parked primitive test that trigger a pass (0 = off)
   DevBuf d_rays, d_ray_out;  // brt_trace_rays staging
@@ -894,9 +896,16 @@ PathQueue queue_of(FrameSlot* f, int k) {
   return PathQueue{f->q_o[k].as<float4>(), f->q_d[k].as<float4>(), f->q_w[k].as<float4>(), f->q_px[k].as<uint32_t>(), f->q_seed[k].as<uint32_t>()};
 }
 
+// max_rays: upper bound of the queue this launch walks (the live count is on the device). A persistent warp claims 32 rays at a time and
+// refills idle lanes from the cursor; when the queue holds less than a few claims per warp there is nothing to refill from and the
+// lanes of a warp idle until its slowest ray is done — so small queues get a smaller grid (c->rays_per_warp claims' worth per warp).
 template <bool ANY>
-void launch_trace(brt_context* c, const TraceParams& p, cudaStream_t stream) {
-  const uint32_t grid = (uint32_t)c->sm_count * 8u;
+void launch_trace(brt_context* c, const TraceParams& p, cudaStream_t stream, uint64_t max_rays = ~0ull) {
+  uint32_t grid = (uint32_t)c->sm_count * 8u;
+  if (c->rays_per_warp && max_rays != ~0ull) {
+    const uint64_t warps = std::max<uint64_t>(1, max_rays / c->rays_per_warp);
+    grid = (uint32_t)std::max<uint64_t>((uint64_t)c->sm_count, std::min<uint64_t>(grid, (warps + 3) / 4));
+  }
   if (c->flags & BRT_CFG_COUNTERS) BRT_LAUNCH_TRACE(ANY, true, p, grid, stream);
   else BRT_LAUNCH_TRACE(ANY, false, p, grid, stream);
   BRT_CHECK_LAUNCH();
@@ -1079,6 +1088,21 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   // instead of running in lockstep with it.
   if (c->prev_head && c->prev_head != f->ev_head) BRT_CUDA(cudaStreamWaitEvent(s, c->prev_head, 0));
 
+  // Full-frame clears that only the pixels this slot never writes depend on (AOVs of pixels outside the crop / of other ranks' tiles,
+  // the local image outside this rank's tiles): every owned pixel inside the crop is rewritten by every frame, so they are done once per
+  // buffer generation and traced window instead of once per frame (at 4K they were 233 MB of memsets per frame on every rank).
+  {
+    const uint64_t ck[3] = {((uint64_t)f->generation << 32) | c->tile_world, ((uint64_t)map.crop_x0 << 48) | ((uint64_t)map.crop_y0 << 32) | ((uint64_t)map.crop_x1 << 16) | map.crop_y1,
+                            ((uint64_t)o.width << 32) | o.height};
+    if (std::memcmp(ck, f->cleared_key, sizeof(ck)) != 0) {
+      BRT_CUDA(cudaMemsetAsync(f->d_aov_prim.ptr(), 0xff, npx * 4, s));
+      BRT_CUDA(cudaMemsetAsync(f->d_aov_inst.ptr(), 0xff, npx * 4, s));
+      BRT_CUDA(cudaMemsetAsync(f->d_aov_t.ptr(), 0, npx * 4, s));
+      if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(f->d_image.ptr(), 0, npx * 16, s));
+      std::memcpy(f->cleared_key, ck, sizeof(ck));
+    }
+  }
+
   // The stream work of the frame (about 45 dependent kernel launches, memsets and event records for C2) is captured into a CUDA
   // graph the first time a frame shape is seen on this slot and replayed afterwards: everything that changes from frame to frame
   // travels through FrameConsts, queue sizes already live on the device.
@@ -1103,10 +1127,6 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
     record_event(whole.a, s);
     BRT_CUDA(cudaMemsetAsync(f->d_accum.ptr(), 0, (size_t)cap * 16, s));
     BRT_CUDA(cudaMemsetAsync(fst, 0, sizeof(FrameStats), s));
-    BRT_CUDA(cudaMemsetAsync(f->d_aov_prim.ptr(), 0xff, npx * 4, s));
-    BRT_CUDA(cudaMemsetAsync(f->d_aov_inst.ptr(), 0xff, npx * 4, s));
-    BRT_CUDA(cudaMemsetAsync(f->d_aov_t.ptr(), 0, npx * 4, s));
-    if (c->tile_world > 1) BRT_CUDA(cudaMemsetAsync(f->d_image.ptr(), 0, npx * 16, s));
     if (f->has_gbuffer) {
       BRT_CUDA(cudaMemsetAsync(f->d_aov_pos.ptr(), 0, npx * 16, s));
       BRT_CUDA(cudaMemsetAsync(f->d_aov_nrm.ptr(), 0, npx * 16, s));
@@ -1165,7 +1185,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           tp.refill_lanes = round == 0 ? c->refill_primary : c->refill_bounce;  // measured: refill pays for bounce rays only
           tp.defer_lanes = round == 0 ? c->defer_primary : c->defer_bounce;
           Timed t(f, CLS_CLOSEST, s);
-          launch_trace<false>(c, tp, s);
+          launch_trace<false>(c, tp, s, round == 0 ? ~0ull : (uint64_t)capw >> (round - 1));  // (a bounce round holds at most the previous round's hits)
           launches++;
           l_closest++;
         }
@@ -1267,7 +1287,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           tp.refill_lanes = round == 0 ? c->refill_primary : c->refill_bounce;
           tp.defer_lanes = round == 0 ? c->defer_primary : c->defer_bounce;
           Timed t(f, CLS_OCCL, s2);
-          launch_trace<true>(c, tp, s2);
+          launch_trace<true>(c, tp, s2, round == 0 ? ~0ull : ((uint64_t)capw * n_slots) >> (round - 1));
           launches++;
           l_occl++;
         }
@@ -1574,6 +1594,7 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count, (c->flags & BRT_CFG_GREEDY_COLLAPSE) != 0, (c->flags & BRT_CFG_TREELET_PASSES_3) != 0));
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
+    if (const char* e = getenv("BRT_RAYS_PER_WARP")) c->rays_per_warp = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_REFILL_PRIMARY")) c->refill_primary = (uint32_t)std::max(0L, std::min(32L, atol(e)));
     if (const char* e = getenv("BRT_REFILL_BOUNCE")) c->refill_bounce = (uint32_t)std::max(0L, std::min(32L, atol(e)));
     if (const char* e = getenv("BRT_DEFER_PRIMARY")) c->defer_primary = (uint32_t)std::max(0L, std::min(32L, atol(e)));  // tuning aids
