@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--slots", type=int, nargs="+", default=[1, 2, 3, 4])
     ap.add_argument("--frames", type=int, default=40)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="also one frame at a time on the serial schedule: per-kernel-class CUDA-event times")
     args = ap.parse_args()
     pkg = importlib.import_module("hardware-ray-tracer_b200")
     cfg = dict(pkg.scenes.CONFIGS[args.config])
@@ -62,6 +63,18 @@ def main():
         st = ctx.get_stats()
         rays = st.rays_closest + st.rays_occlusion
         out["runs"].append({"slots": n_slots, "ms_per_frame": ms, "rays": int(rays), "mrays_rank": rays / ms / 1e3, "launches": st.launches_total})
+    if args.serial:
+        sctx = pkg.Context(device=0, tile_rank=0, tile_world=args.world, flags=pkg.CFG_NO_OVERLAP)
+        scene.upload(sctx)
+        rows = []
+        for _ in range(5):
+            sctx.render_frame(u, opts, want_image=False)
+            st = sctx.get_stats()
+            rows.append((st.ms_total, st.ms_trace_closest, st.ms_trace_occlusion, st.ms_shade, st.ms_raygen, st.ms_accumulate, st.ms_resolve))
+        rows.sort()
+        m = rows[len(rows) // 2]
+        out["serial_frame_ms"] = dict(zip(("total", "closest", "occlusion", "shade", "raygen", "accumulate", "resolve"), [round(x, 4) for x in m]))
+        out["serial_frame_ms"]["sum_of_kernels"] = round(sum(m[1:]), 4)
     print(json.dumps(out))
 
 
