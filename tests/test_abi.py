@@ -27,7 +27,7 @@ def test_flag_constants_match_header(pkg):
     assert set(cfg) >= {"CFG_COUNTERS", "CFG_NO_TREELET", "CFG_TREELET_ON_REBUILD", "CFG_NO_OVERLAP", "CFG_NO_GRAPH", "CFG_GREEDY_COLLAPSE"}
     for name, value in cfg.items():
         assert getattr(B, name) == value, name
-    for name in ("BOUNCE_REFLECT", "BOUNCE_REFRACT", "BOUNCE_DIFFUSE", "JITTER", "SKY", "GBUFFER", "LIGHT_BVH", "DENOISE"):
+    for name in ("BOUNCE_REFLECT", "BOUNCE_REFRACT", "BOUNCE_DIFFUSE", "JITTER", "SKY", "GBUFFER", "LIGHT_BVH", "DENOISE", "FAST_SHADING"):
         assert getattr(B, name) == defs["RENDER_" + name], name
     values = sorted(cfg.values())
     assert values == [1 << i for i in range(len(values))]  # distinct bits, none skipped
