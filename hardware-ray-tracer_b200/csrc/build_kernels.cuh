@@ -233,9 +233,7 @@ BRT_HD void refit_body(const RefitParams& p, uint32_t i) {
   for (;;) {
     const uint32_t par = p.parent[cur];
     if (par == BRT_MISS) break;
-    fence();
-    if (atomic_add(&p.arrive[par], 1u) == 0u) break;  // the sibling subtree is not finished yet
-    fence();
+    if (atomic_add_acq_rel(&p.arrive[par], 1u) == 0u) break;  // the sibling subtree is not finished yet
     volatile BNode* nd = p.nodes + par;
     const uint32_t l = f2u(nd->lo.w), r = f2u(nd->hi.w);
     volatile const BNode* a = p.nodes + l;
@@ -335,9 +333,7 @@ BRT_HD void wide_cost_body(const WideCostParams& p, uint32_t i) {
   for (;;) {
     const uint32_t par = p.parent[cur];
     if (par == BRT_MISS) break;
-    fence();
-    if (atomic_add(&p.arrive[par], 1u) == 0u) break;  // the sibling subtree is not finished yet
-    fence();
+    if (atomic_add_acq_rel(&p.arrive[par], 1u) == 0u) break;  // the sibling subtree is not finished yet
     volatile const BNode* nd = p.nodes + par;
     const uint32_t l = f2u(nd->lo.w), r = f2u(nd->hi.w);
     wide_cost_node(p.wcost, p.wplan, par, l, r, n_int, box_area(F3(nd->lo.x, nd->lo.y, nd->lo.z), F3(nd->hi.x, nd->hi.y, nd->hi.z)));

@@ -144,6 +144,20 @@ BRT_HD void fence() {
   __threadfence();
 #endif
 }
+// fetch-and-add with acquire-release semantics at device scope: the arrival counters of the bottom-up builder passes. One instruction
+// orders this thread's earlier stores before the add and its later loads after it — what `fence(); atomic_add(); fence();` spelled with
+// two full membars (each ~1 us on the dependent chain of a refit walk).
+BRT_HD uint32_t atomic_add_acq_rel(uint32_t* p, uint32_t v) {
+#ifdef BRT_EMU
+  uint32_t o = *p;
+  *p = o + v;
+  return o;
+#else
+  uint32_t o;
+  asm volatile("atom.acq_rel.gpu.add.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+  return o;
+#endif
+}
 
 // float <-> order-preserving uint (for atomic min/max on floats)
 BRT_HDH uint32_t float_to_ordered(float f) {

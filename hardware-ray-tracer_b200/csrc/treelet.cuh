@@ -172,9 +172,7 @@ BRT_HD void treelet_body(const TreeletParams& p, uint32_t i) {
   for (;;) {
     const uint32_t par = p.parent[cur];
     if (par == BRT_MISS) break;
-    fence();
-    if (atomic_add(&p.arrive[par], 1u) == 0u) break;
-    fence();
+    if (atomic_add_acq_rel(&p.arrive[par], 1u) == 0u) break;
     const uint32_t l = f2u(nodes[par].lo.w), r = f2u(nodes[par].hi.w);
     const float lo[3] = {nodes[par].lo.x, nodes[par].lo.y, nodes[par].lo.z};
     const float hi[3] = {nodes[par].hi.x, nodes[par].hi.y, nodes[par].hi.z};
