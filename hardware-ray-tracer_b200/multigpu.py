@@ -33,12 +33,27 @@ class TiledFrame:
         self.root_only, self.root = bool(root_only), root
         self.device = device
         if self.mode == "p2p":
-            mine = ctx.gather_image_export(width, height)
+            # Set-up is collective and must fail collectively: a rank that cannot map a peer's memory must not leave the others
+            # waiting in the next collective, so every step is attempted on every rank and the outcome is agreed on by an all-reduce.
+            err = None
+            try:
+                mine = ctx.gather_image_export(width, height)
+            except Exception as e:  # noqa: BLE001
+                mine, err = None, e
             handles = [None] * world
             dist.all_gather_object(handles, mine, group=group)
-            ctx.gather_image_open(handles)
-            ctx.gather_configure(root_only, root)
-            dist.barrier(group=group)  # set-up only: everybody's images are mapped before the first peer store
+            if err is None and all(h is not None for h in handles):
+                try:
+                    ctx.gather_image_open(handles)
+                    ctx.gather_configure(root_only, root)
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("a peer could not export its gather images")
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # (also the barrier: everybody's images are mapped before the first peer store)
+            if int(ok.item()) == 0:
+                raise RuntimeError(f"fused exchange unavailable on this box: {err or 'a peer failed to map the gather images'}")
             self._copy_stream = torch.cuda.Stream(device=device)
             self._fetch_events = {}
             self._next = 0
