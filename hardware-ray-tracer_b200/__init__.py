@@ -19,7 +19,6 @@ def TiledFrame(*args, **kwargs):
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libbrt.so")
-LIB_COUNTERS_PATH = LIB_PATH  # counters are a runtime flag (BRT_CFG_COUNTERS), same library
 
 _lib = None
 
