@@ -336,6 +336,12 @@ enum { CLS_RAYGEN = 0, CLS_CLOSEST, CLS_SHADE, CLS_OCCL, CLS_ACCUM, CLS_RESOLVE,
 
 using namespace brt;
 
+// host copy of what a device table holds (upload_if_changed)
+struct CachedTable {
+  std::vector<unsigned char> host;
+  const void* dev = nullptr;
+};
+
 // Everything one frame in flight owns: its streams, wavefront buffers, output images and timing events. The reference keeps
 // MAX_FRAMES_IN_FLIGHT = 2 frames in flight with a fence per frame (VK/SwapChain.h:8, VK/SwapChain.cpp:45-60,92-131) so that
 // the tail of one frame overlaps the head of the next; brt_render_frame_async / brt_frame_wait expose the same here.
@@ -408,6 +414,7 @@ struct brt_context {
   std::vector<brt_light_bvh_node> light_bvh;  // RT/Scene.h:123-130, built on the host by build_tables
   DevBuf d_light_bvh;
   DevBuf d_materials, d_mat_ext, d_lights, d_inst_shade, d_inst_src, d_inst_ids, d_mesh_bounds, d_visible;
+  CachedTable t_light_bvh, t_materials, t_mat_ext, t_lights, t_mesh_bounds, t_inst_shade, t_instance_info, t_sky, t_scene_info, t_inst_src, t_inst_ids;
   DevBuf d_instance_info, d_sky, d_scene_info;  // the reference's InstanceInfo[] / SkyInfo / SceneBufferInfo (RT/Scene.h:84-121) for callers that bind them
   brt_scene_buffer_info scene_info{};
   DevBuf d_tlas_nodes, d_tlas_inst;
@@ -502,6 +509,16 @@ int guarded(brt_context* ctx, F&& f) {
 void upload(cudaStream_t s, DevBuf& buf, const void* src, size_t bytes) {
   buf.ensure(std::max<size_t>(bytes, 16));
   if (bytes) BRT_CUDA(cudaMemcpyAsync(buf.ptr(), src, bytes, cudaMemcpyHostToDevice, s));
+}
+
+// Scene tables are re-derived by every build; most of them do not change from one per-frame re-build to the next (C4: only the bounds of
+// the animated mesh do). Each table keeps a host copy of what is on the device and is uploaded only when it differs.
+void upload_if_changed(cudaStream_t s, DevBuf& buf, CachedTable& cache, const void* src, size_t bytes) {
+  buf.ensure(std::max<size_t>(bytes, 16));
+  if (cache.dev == buf.ptr() && cache.host.size() == bytes && (bytes == 0 || std::memcmp(cache.host.data(), src, bytes) == 0)) return;
+  cache.host.assign(static_cast<const unsigned char*>(src), static_cast<const unsigned char*>(src) + bytes);
+  cache.dev = buf.ptr();
+  if (bytes) BRT_CUDA(cudaMemcpyAsync(buf.ptr(), cache.host.data(), bytes, cudaMemcpyHostToDevice, s));
 }
 
 uint32_t grid_for(const brt_context* c, uint32_t n, uint32_t block, uint32_t blocks_per_sm) {
@@ -643,10 +660,10 @@ void build_light_bvh(const std::vector<brt_light>& lights, std::vector<brt_light
 void build_tables(brt_context* c) {
   cudaStream_t s = c->stream;
   build_light_bvh(c->lights, c->light_bvh);
-  upload(s, c->d_light_bvh, c->light_bvh.data(), c->light_bvh.size() * sizeof(brt_light_bvh_node));
-  upload(s, c->d_materials, c->materials.data(), c->materials.size() * sizeof(brt_material));
-  upload(s, c->d_mat_ext, c->mat_ext.data(), c->mat_ext.size() * 4);
-  upload(s, c->d_lights, c->lights.data(), c->lights.size() * sizeof(brt_light));
+  upload_if_changed(s, c->d_light_bvh, c->t_light_bvh, c->light_bvh.data(), c->light_bvh.size() * sizeof(brt_light_bvh_node));
+  upload_if_changed(s, c->d_materials, c->t_materials, c->materials.data(), c->materials.size() * sizeof(brt_material));
+  upload_if_changed(s, c->d_mat_ext, c->t_mat_ext, c->mat_ext.data(), c->mat_ext.size() * 4);
+  upload_if_changed(s, c->d_lights, c->t_lights, c->lights.data(), c->lights.size() * sizeof(brt_light));
   // exact object-space box of every mesh (read by the TLAS builder and Smart Culling)
   std::vector<float> mb(std::max<size_t>(c->meshes.size(), 1) * 8, 0.0f);
   for (size_t mi = 0; mi < c->meshes.size(); ++mi)
@@ -654,7 +671,7 @@ void build_tables(brt_context* c) {
       mb[8 * mi + k] = c->meshes[mi]->lo[k];
       mb[8 * mi + 4 + k] = c->meshes[mi]->hi[k];
     }
-  upload(s, c->d_mesh_bounds, mb.data(), mb.size() * 4);
+  upload_if_changed(s, c->d_mesh_bounds, c->t_mesh_bounds, mb.data(), mb.size() * 4);
   std::vector<InstShade> shade(c->instances.size());
   for (size_t i = 0; i < c->instances.size(); ++i) {
     const InstanceData& in = c->instances[i];
@@ -670,7 +687,7 @@ void build_tables(brt_context* c) {
     r.material = in.material;
     r.mesh = in.mesh;
   }
-  upload(s, c->d_inst_shade, shade.data(), shade.size() * sizeof(InstShade));
+  upload_if_changed(s, c->d_inst_shade, c->t_inst_shade, shade.data(), shade.size() * sizeof(InstShade));
   // the reference's own tables (RT/Scene.cpp:357-403): InstanceInfo per instance, SkyInfo, SceneBufferInfo
   {
     std::vector<brt_instance_info> info(std::max<size_t>(c->instances.size(), 1));
@@ -678,12 +695,12 @@ void build_tables(brt_context* c) {
       const MeshData& m = *c->meshes[c->instances[i].mesh];
       info[i] = brt_instance_info{(uint64_t)m.vertices.ptr(), (uint64_t)m.indices.ptr(), c->instances[i].material, 0u};
     }
-    upload(s, c->d_instance_info, info.data(), info.size() * sizeof(brt_instance_info));
-    upload(s, c->d_sky, &c->sky, sizeof(brt_sky));
+    upload_if_changed(s, c->d_instance_info, c->t_instance_info, info.data(), info.size() * sizeof(brt_instance_info));
+    upload_if_changed(s, c->d_sky, c->t_sky, &c->sky, sizeof(brt_sky));
     c->scene_info = brt_scene_buffer_info{(uint64_t)c->d_materials.ptr(), sizeof(brt_material), (uint64_t)c->d_lights.ptr(), sizeof(brt_light),
                                           (uint64_t)c->lights.size(), sizeof(brt_vertex), (uint64_t)c->d_instance_info.ptr(), sizeof(brt_instance_info),
                                           (uint64_t)c->d_sky.ptr(), sizeof(brt_sky)};
-    upload(s, c->d_scene_info, &c->scene_info, sizeof(c->scene_info));
+    upload_if_changed(s, c->d_scene_info, c->t_scene_info, &c->scene_info, sizeof(c->scene_info));
   }
   // world box of all instances (centre / extent form of |M| box): the grid of the bounce rounds' hit sort
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -729,8 +746,8 @@ void build_tlas(brt_context* c) {
   c->tlas_count = (uint32_t)src.size();
   c->tlas = BuildResult{};
   if (c->tlas_count) {
-    upload(s, c->d_inst_src, src.data(), src.size() * sizeof(InstRec));
-    upload(s, c->d_inst_ids, ids.data(), ids.size() * 4);
+    upload_if_changed(s, c->d_inst_src, c->t_inst_src, src.data(), src.size() * sizeof(InstRec));
+    upload_if_changed(s, c->d_inst_ids, c->t_inst_ids, ids.data(), ids.size() * 4);
     c->d_tlas_nodes.ensure((size_t)Builder::node_capacity(c->tlas_count) * sizeof(Node8));
     c->d_tlas_inst.ensure((size_t)c->tlas_count * sizeof(InstRec));
     c->builder->build_instances(s, c->d_inst_shade.as<InstShade>(), c->d_inst_ids.as<uint32_t>(), c->d_inst_src.as<InstRec>(), c->tlas_count,

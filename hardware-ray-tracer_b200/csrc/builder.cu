@@ -176,6 +176,9 @@ struct SmallBuildParams {
   uint2* queue[2];
   float4* mesh_bounds;     // may be null
   uint32_t in_smem;        // the binary tree and every intermediate array live in dynamic shared memory (n <= BRT_SMEM_BUILD_MAX)
+  uint32_t fused_prologue; // instance builds: the kernel also resets the globals and computes the instance boxes (two launches less)
+  InitGlobalsParams init;
+  InstBoundsParams inst;
 };
 // Up to BRT_SMEM_BUILD_MAX primitives (the per-frame TLAS of C4: 513 instances) the binary nodes, parent links, arrival counters, subtree
 // counts, the collapse's cost table and plan, the sorted keys and both collapse queues fit the SM's shared memory (140 bytes per
@@ -187,6 +190,14 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
   __shared__ unsigned long long sk[BRT_SMALL_BUILD_MAX];  // (Morton key << 32 | primitive): unique, so the sort is stable by construction
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   SmallBuildParams p = p_in;
+  if (p.fused_prologue) {
+    if (threadIdx.x == 0) init_globals_body(p.init, 0);
+    __threadfence();
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < p.n; i += blockDim.x) inst_bounds_body(p.inst, i);
+    __threadfence();
+    __syncthreads();
+  }
   if (p.in_smem) {
     const uint32_t n = p.n;
     unsigned char* at = dyn_smem;
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
     uint32_t* vals_sorted = reinterpret_cast<uint32_t*>(take((size_t)n * 4));
     uint2* q0 = reinterpret_cast<uint2*>(take((size_t)(n / 2 + 8) * 8));
     uint2* q1 = reinterpret_cast<uint2*>(take((size_t)(n / 2 + 8) * 8));
-    if (threadIdx.x == 0) q0[0] = p.queue[0][0];  // the root work item written by k_init_globals
+    if (threadIdx.x == 0) q0[0] = p.queue[0][0];  // the root work item written by init_globals_body
     p.keys_sorted = keys_sorted;
     p.vals_sorted = vals_sorted;
     p.hier.keys = keys_sorted;
@@ -342,6 +353,11 @@ void Builder::run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treel
     sp.queue[1] = queue_[1].as<uint2>();
     sp.mesh_bounds = d_mesh_bounds;
     sp.in_smem = n <= BRT_SMEM_BUILD_MAX && !getenv("BRT_NO_SMEM_BUILD") ? 1u : 0u;
+    sp.fused_prologue = fused_small_ ? 1u : 0u;
+    if (fused_small_) {
+      std::memcpy(&sp.init, fused_params_, sizeof(sp.init));
+      std::memcpy(&sp.inst, fused_params_ + sizeof(sp.init), sizeof(sp.inst));
+    }
     const size_t dyn = sp.in_smem ? small_build_smem_bytes(n) : 0;
     if (dyn > small_build_smem_set_) {
       BRT_CUDA(cudaFuncSetAttribute(k_build_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_build_smem_bytes(BRT_SMEM_BUILD_MAX)));
@@ -539,10 +555,26 @@ void Builder::build_instances(cudaStream_t stream, const InstShade* d_shade, con
   ensure_scratch(n);
   BuildGlobals* g = globals_.as<BuildGlobals>();
   InitGlobalsParams ip{1, nullptr, g, 0u, queue_[0].as<uint2>()};
+  InstBoundsParams p{n, nullptr, d_shade, d_inst_ids, d_mesh_bounds, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g};
+#ifndef BRT_EMU
+  if (n >= 2 && n <= BRT_SMALL_BUILD_MAX) {  // the one-block kernel resets the globals and computes the instance boxes itself
+    static_assert(sizeof(InitGlobalsParams) + sizeof(InstBoundsParams) <= sizeof(fused_params_), "fused_params_ too small");
+    fused_small_ = true;
+    std::memcpy(fused_params_, &ip, sizeof(ip));
+    std::memcpy(fused_params_ + sizeof(ip), &p, sizeof(p));
+    try {
+      run(stream, n, 1, false, out_nodes, nullptr, nullptr, nullptr, d_src, out_inst, nullptr, res);
+    } catch (...) {
+      fused_small_ = false;
+      throw;
+    }
+    fused_small_ = false;
+    return;
+  }
+#endif
   BRT_LAUNCH_1D(k_init_globals, ip, 1, 32, stream);
   BRT_CHECK_LAUNCH();
   const uint32_t grid_n = std::max(1u, std::min(div_up(n, 256u), (uint32_t)sm_count_ * 8u));
-  InstBoundsParams p{n, nullptr, d_shade, d_inst_ids, d_mesh_bounds, prim_lo_.as<float4>(), prim_hi_.as<float4>(), g};
   BRT_LAUNCH_1D(k_inst_bounds, p, grid_n, 256, stream);
   BRT_CHECK_LAUNCH();
   run(stream, n, 1, false, out_nodes, nullptr, nullptr, nullptr, d_src, out_inst, nullptr, res);

@@ -42,6 +42,8 @@ class Builder {
   void run(cudaStream_t stream, uint32_t n, uint32_t max_leaf, bool treelets, Node8* out_nodes, const float* d_vertices,
            const uint32_t* d_indices, TriRec* out_tris, const InstRec* d_src, InstRec* out_inst, float4* d_mesh_bounds, BuildResult* res);
   void ensure_scratch(uint32_t n);
+  bool fused_small_ = false;  // build_instances -> run(): the one-block kernel runs the prologue (globals, instance boxes) too
+  alignas(16) unsigned char fused_params_[192] = {0};  // InitGlobalsParams + InstBoundsParams of that call (their types live in builder.cu)
   size_t small_build_smem_set_ = 0;  // dynamic shared memory the one-block build kernel has been allowed so far
   int treelet_passes_ = 1;  // SAH treelet passes of a first ("fast trace") build: 1 (4.7 ms for 1M triangles, SAH 35.56) or 3 (9.5 ms, SAH 35.02)
   int sm_count_;
