@@ -427,6 +427,7 @@ struct brt_context {
   cudaEvent_t prev_head = nullptr;        // ev_head of the frame submitted last: the next frame starts behind it (staggered frames)
   uint32_t last_slot = 0;                 // slot of the frame most recently waited for (brt_get_aov / brt_device_image read it)
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
+  uint32_t shade_ahead = 0;  // tuning aid: slots ahead of which the shade kernels request path heads into the L2 (BRT_SHADE_AHEAD)
   uint32_t rays_per_warp = 0;  // 0 = full grid always; else bounce-round launches are sized for this many rays per warp (BRT_RAYS_PER_WARP)
   uint32_t refill_primary = 0, refill_bounce = BRT_REFILL_LANES_INCOHERENT;  // lanes still busy below which a warp refills its idle lanes
   uint32_t defer_primary = 0, defer_bounce = 0;  // deferred-leaf traversal: lanes with a parked primitive test that trigger a pass (0 = off)
@@ -1272,6 +1273,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           sp.aov_nrm = f->has_gbuffer ? f->d_aov_nrm.as<float4>() : nullptr;
           sp.fc = f->d_consts.as<FrameConsts>();
           sp.order = order;
+          sp.ahead = c->shade_ahead;
           Timed t(f, CLS_SHADE, s);
   #ifdef BRT_EMU
           BRT_LAUNCH_1D(k_shade, sp, 1, 128, s);
@@ -1611,6 +1613,8 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     c->own_stream = true;
     c->builder.reset(new Builder(c->sm_count, (c->flags & BRT_CFG_GREEDY_COLLAPSE) != 0, (c->flags & BRT_CFG_TREELET_PASSES_3) != 0));
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
+    // measured slower on C2 / C3 / C5 at every distance tried (profiles/r2_ncu_summary.md §4): off unless asked for
+    if (const char* e = getenv("BRT_SHADE_AHEAD")) c->shade_ahead = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_RAYS_PER_WARP")) c->rays_per_warp = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_REFILL_PRIMARY")) c->refill_primary = (uint32_t)std::max(0L, std::min(32L, atol(e)));
     if (const char* e = getenv("BRT_REFILL_BOUNCE")) c->refill_bounce = (uint32_t)std::max(0L, std::min(32L, atol(e)));

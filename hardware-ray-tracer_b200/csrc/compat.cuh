@@ -46,6 +46,9 @@ BRT_HDH float u2f(uint32_t u) {
   return f;
 #endif
 }
+#ifndef BRT_EMU
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 // explicit fused multiply-add (the build uses -fmad=false, so this is the only way to get an FFMA)
 BRT_HD float fma_rn(float a, float b, float c) {
 #ifdef BRT_EMU

@@ -228,6 +228,7 @@ struct ShadeParams {
   float4* aov_nrm;
   const FrameConsts* fc;  // sky
   const uint32_t* order;  // bounce rounds: path slots in the order of their hit positions (hit sort, below); null = queue order
+  uint32_t ahead;         // CUDA kernels: the head of slot i + ahead is requested into the L2 while slot i is shaded (0 = off)
 };
 
 // Light BVH sampling (RT/Scene.h:123-130, SH/raytracing.slang:76; rule in DESIGN.md §13): stochastic descent from the root, a child
@@ -299,18 +300,63 @@ BRT_HD f3 sky_color(const brt_sky& s, f3 dir) {
 // Shading is split in two so that the CUDA kernel can compact the hits of a block before the expensive part (brt_api.cu):
 //   shade_prologue  every path slot: bookkeeping, primary-hit AOVs, and the whole miss shader; returns true for a hit
 //   shade_hit       rchitMain: geometry fetch, BRDF x lights, shadow rays, bounce
-BRT_HD bool shade_prologue(const ShadeParams& p, uint32_t i) {
-  const uint32_t px = p.cur.px[i];
-  if (i == 0) p.sctr->n_items = p.count_ptr ? *p.count_ptr : p.count;
-  {
-    const float4 w = p.cur.w[i];
-    p.aux[i] = make_float4(w.x, w.y, w.z, u2f(px));
+// The head of a path slot: everything the prologue reads. With BRT_SHADE_HOIST_HEAD it is fetched together BEFORE the first branch (fetched
+// where they are used, px -> branch -> hit_inst -> branch -> hit / ray are three dependent trips to DRAM at five blocks per SM: 46 % of
+// the stall samples of k_shade_primary are on those waits, profiles/r2_ncu_summary.md §4); hit_inst / hit of a padding slot
+// (px == BRT_MISS) are in bounds and unused.
+struct PathHead {
+  uint32_t px, inst_id;
+  float4 hit, w;
+};
+// The queues are streamed once, at addresses known long in advance, by a kernel that keeps ~20 warps per SM busy with arithmetic: the head
+// (and ray) of the slot that is `ahead` slots further on — roughly what the resident blocks reach next — is pulled into the L2 now.
+BRT_HD void shade_prefetch(const ShadeParams& p, uint32_t i) {
+#ifndef BRT_EMU
+  prefetch_l2(p.cur.px + i);
+  prefetch_l2(p.hit_inst + i);
+  prefetch_l2(p.hit + i);
+  prefetch_l2(p.cur.w + i);
+  prefetch_l2(p.cur.o + i);
+  prefetch_l2(p.cur.d + i);
+  prefetch_l2(p.cur.seed + i);
+#endif
+}
+// Both hoists are OFF by default. In the serial schedule they take 7 % off the shade kernels of C3 (16.6 -> 15.4 ms per frame), but with the
+// head hoist the frame time of the PRODUCT schedule (two overlapping chains) became bistable per process and box: 121.7 ms in some
+// processes, 126.5 ms in others, steady within a process, against a steady 122.9 ms without it (profiles/r2_ncu_summary.md §5).
+#ifndef BRT_SHADE_HOIST_HEAD
+#define BRT_SHADE_HOIST_HEAD 0
+#endif
+#ifndef BRT_SHADE_HOIST_HIT
+#define BRT_SHADE_HOIST_HIT 0
+#endif
+BRT_HD PathHead shade_load(const ShadeParams& p, uint32_t i) {
+  PathHead h;
+  h.px = p.cur.px[i];
+  h.w = p.cur.w[i];
+#if BRT_SHADE_HOIST_HEAD
+  h.inst_id = p.hit_inst[i];
+  h.hit = p.hit[i];
+#else
+  h.inst_id = BRT_MISS;
+  h.hit = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (h.px != BRT_MISS) {
+    h.inst_id = p.hit_inst[i];
+    h.hit = p.hit[i];
   }
+#endif
+  return h;
+}
+
+BRT_HD bool shade_prologue(const ShadeParams& p, uint32_t i, const PathHead& h) {
+  const uint32_t px = h.px;
+  if (i == 0) p.sctr->n_items = p.count_ptr ? *p.count_ptr : p.count;
+  p.aux[i] = make_float4(h.w.x, h.w.y, h.w.z, u2f(px));
   if (px == BRT_MISS) return false;
   const bool lbvh = (p.flags & BRT_RENDER_LIGHT_BVH) != 0u;  // one stochastically chosen light per hit instead of the loop
   const uint32_t n_slots = (p.n_lights && !lbvh) ? p.n_lights : 1u;
-  const uint32_t inst_id = p.hit_inst[i];
-  const float4 hit = p.hit[i];
+  const uint32_t inst_id = h.inst_id;
+  const float4 hit = h.hit;
   if (p.write_aov && (px >> BRT_SLOT_BITS) == 0u) {
     uint32_t x, y;
     slot_to_pixel(p.map, px & BRT_SLOT_MASK, x, y);
@@ -332,21 +378,35 @@ BRT_HD bool shade_prologue(const ShadeParams& p, uint32_t i) {
   return true;
 }
 
-BRT_HD void shade_hit(const ShadeParams& p, uint32_t i) {
-  const uint32_t px = p.cur.px[i];
+BRT_HD void shade_hit(const ShadeParams& p, uint32_t i, uint32_t px, uint32_t inst_id, float4 hit) {
   const bool lbvh = (p.flags & BRT_RENDER_LIGHT_BVH) != 0u;
   const uint32_t n_slots = (p.n_lights && !lbvh) ? p.n_lights : 1u;
-  const float4 ro = p.cur.o[i], rd = p.cur.d[i];
-  const f3 ray_o = F3(ro.x, ro.y, ro.z), ray_d = F3(rd.x, rd.y, rd.z);
-  const uint32_t inst_id = p.hit_inst[i];
-  const float4 hit = p.hit[i];
+  // everything that depends on (i, inst_id) only is requested here, ahead of the dependent fetches (indices -> vertices)
+  const float4 rd = p.cur.d[i];
+#if BRT_SHADE_HOIST_HIT
+  uint32_t seed = p.cur.seed[i];
+#endif
+  const f3 ray_d = F3(rd.x, rd.y, rd.z);
   // rchitMain :136-169
   const InstShade& in = p.inst[inst_id];
   const float4 o2w[3] = {in.o2w[0], in.o2w[1], in.o2w[2]};
   const float4 w2o[3] = {in.w2o[0], in.w2o[1], in.w2o[2]};
+  const uint32_t mat_id = in.material;
+  Material mat;
+#define BRT_LOAD_MATERIAL                                                                                                     \
+  {                                                                                                                           \
+    const float* m = p.materials + 13 * (size_t)mat_id; /* SH/objects.slang:56-59 */                                          \
+    mat.color = F3(m[0], m[1], m[2]);                                                                                         \
+    mat.subsurface = m[3]; mat.metallic = m[4]; mat.roughness = m[5]; mat.specular = m[6]; mat.specularTint = m[7];           \
+    mat.anisotropic = m[8]; mat.sheen = m[9]; mat.sheenTint = m[10]; mat.clearCoat = m[11]; mat.clearCoatGloss = m[12];       \
+  }
+#if BRT_SHADE_HOIST_HIT
+  BRT_LOAD_MATERIAL
+#endif
   f3 pos, nrm;
   if (in.kind == 1u) {
-    const f3 oo = xform_point(w2o, ray_o), od = xform_dir(w2o, ray_d);
+    const float4 ro = p.cur.o[i];  // only the analytic sphere needs the origin
+    const f3 oo = xform_point(w2o, F3(ro.x, ro.y, ro.z)), od = xform_dir(w2o, ray_d);
     pos = oo + od * hit.x;
     nrm = (pos - xyz(in.sphere)) * (1.0f / in.sphere.w);
   } else {
@@ -362,13 +422,10 @@ BRT_HD void shade_hit(const ShadeParams& p, uint32_t i) {
   }
   const f3 worldPos = xform_point(o2w, pos);                       // :149
   const f3 worldNormal = normalize(xform_normal(w2o, nrm));        // :150
-  Material mat;
-  {
-    const float* m = p.materials + 13 * (size_t)in.material;  // SH/objects.slang:56-59
-    mat.color = F3(m[0], m[1], m[2]);
-    mat.subsurface = m[3]; mat.metallic = m[4]; mat.roughness = m[5]; mat.specular = m[6]; mat.specularTint = m[7];
-    mat.anisotropic = m[8]; mat.sheen = m[9]; mat.sheenTint = m[10]; mat.clearCoat = m[11]; mat.clearCoatGloss = m[12];
-  }
+#if !BRT_SHADE_HOIST_HIT
+  BRT_LOAD_MATERIAL
+#endif
+#undef BRT_LOAD_MATERIAL
   f3 N = normalize(worldNormal);  // :154
   const f3 V = ray_d;             // :155
   bool flipped = false;
@@ -386,7 +443,9 @@ BRT_HD void shade_hit(const ShadeParams& p, uint32_t i) {
   // calculateColor :72-88 — the unshadowed contribution of each light goes to contrib[l][slot]; lights
   // whose contribution is not exactly zero get a shadow ray (a zero times the shadow factor is zero
   // either way), which blanks the entry when it is blocked.
+#if !BRT_SHADE_HOIST_HIT
   uint32_t seed = p.cur.seed[i];
+#endif
   for (uint32_t l = 0; l < n_slots; ++l) {
     f3 contrib = F3(0.0f);
     uint32_t li = l;
@@ -425,7 +484,7 @@ BRT_HD void shade_hit(const ShadeParams& p, uint32_t i) {
   const float r1 = rnd(seed), r2 = rnd(seed), r3 = rnd(seed);
   const float4 w4 = p.cur.w[i];
   f3 weight = F3(w4.x, w4.y, w4.z);
-  const float2 ext = p.mat_ext[in.material];  // transmission, ior
+  const float2 ext = p.mat_ext[mat_id];  // transmission, ior
   f3 ndir = F3(0.0f);
   f3 norg = worldPos + N * 0.001f;  // :165
   if ((p.flags & BRT_RENDER_BOUNCE_REFRACT) && ext.x > 0.0f) {
@@ -466,7 +525,8 @@ BRT_HD void shade_hit(const ShadeParams& p, uint32_t i) {
 }
 
 BRT_HD void shade_body(const ShadeParams& p, uint32_t i) {
-  if (shade_prologue(p, i)) shade_hit(p, i);
+  const PathHead h = shade_load(p, i);
+  if (shade_prologue(p, i, h)) shade_hit(p, i, h.px, h.inst_id, h.hit);
 }
 
 // ---- hit sort (bounce rounds) -------------------------------------------------------------------------

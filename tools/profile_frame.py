@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--hit-sort", action="store_true", help="bounce rounds shaded in the order of their hit positions (BRT_CFG_HIT_SORT)")
     ap.add_argument("--graph", action="store_true", help="product schedule: two streams + replayed frame graph (total time only)")
     ap.add_argument("--fast-shading", action="store_true", help="BRT_RENDER_FAST_SHADING")
+    ap.add_argument("--flush", action="store_true", help="write 256 MiB (larger than the L2) before every frame, like bench.py")
     ap.add_argument("--spp", type=int, default=0, help="override the config's samples per pixel")
     args = ap.parse_args()
     pkg = importlib.import_module("hardware-ray-tracer_b200")
@@ -46,7 +47,15 @@ def main():
         cfg["spp"] = args.spp
     if args.fast_shading:
         cfg["flags"] |= pkg.FAST_SHADING
+    rt, flush_buf = None, None
+    if args.flush:
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so")
+        flush_buf = ctypes.c_void_p()
+        assert rt.cudaMalloc(ctypes.byref(flush_buf), ctypes.c_size_t(256 << 20)) == 0
     for f in range(args.frames):
+        if rt is not None:
+            assert rt.cudaMemset(flush_buf, f & 0xff, ctypes.c_size_t(256 << 20)) == 0 and rt.cudaDeviceSynchronize() == 0
         ctx.render_frame(u, ctx.opts(w, h, cfg["spp"], cfg["flags"]), want_image=False)
         s = ctx.get_stats()
         rays = s.rays_closest + s.rays_occlusion
