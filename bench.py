@@ -38,6 +38,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# before anything initialises CUDA: the frames in flight and the fused exchange use more streams than the default 8 hardware work
+# queues (hardware-ray-tracer_b200/__init__.py sets the same default)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 NODE_BYTES, TRI_BYTES, INST_BYTES, RAY_IO_BYTES = 80, 48, 96, 48  # algorithmic bytes per visit / per ray
 
@@ -514,7 +517,7 @@ def measure_multi(g, name, steps, warmup, exchange):
             last_host = hosts[(steps - 1) % S].clone()  # (the 8-bit pass below reuses the host buffers)
         ms_e2e8 = timed_region(steps, 2, opts8, True)
         frame.check()
-        rec["schedule"] = (f"one timed region around all K steps: {S} frames in flight per rank (slot k <-> gather image k on rank 0), resolve kernels store "
+        rec["schedule"] = (f"one timed region around all K steps: {S} frames in flight per rank (slot k <-> gather image k on rank 0), the frame's last kernels store its tiles "
                            "straight into rank 0's image over NVLink, completion by device-side flags (no collective, no host barrier); rank 0 copies every "
                            "frame to pinned host memory on a side stream inside the region (e2e); L2 flushed in-stream before every frame")
         rec["frames_in_flight"] = S

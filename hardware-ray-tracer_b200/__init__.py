@@ -7,6 +7,11 @@ it with ctypes; there is no CPU fallback — `load()` raises when the library is
 import ctypes
 import os
 
+# A frame in flight uses two CUDA streams, the fused multi-GPU exchange adds a stream whose head is a kernel that WAITS (device-side
+# completion flags). With the default of 8 hardware work queues, streams share queues and everything queued behind such a wait stalls
+# with it: 0.16 ms per C5 frame on the receiving rank (profiles/r2_configs.md). Only honoured if CUDA is not initialised yet in this process.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from . import _binding as binding
 from ._binding import *  # noqa: F401,F403
 from . import scenes  # noqa: F401

@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ p, ui
   if ((a.x ^ a.y ^ a.z ^ a.w) == 0x9e3779b9u) *out = a.x;  // keeps the loads alive; practically never true
 }
 // ---- fused multi-GPU exchange: resolve + peer stores + device-side completion flags (GatherFlags, render_kernels.cuh) -------------
+#ifndef BRT_GATHER_POLL_NS
+#define BRT_GATHER_POLL_NS 100
+#endif
 #ifndef BRT_GATHER_TIMEOUT_NS
 #define BRT_GATHER_TIMEOUT_NS 20000000000ull  // a wait gives up after 20 s (a rank died or never submitted the frame) instead of hanging the GPU
 #endif
@@ -120,7 +123,7 @@ __device__ void wait_flags(const uint32_t* flags, uint32_t n, uint32_t seq, uint
         *timeout_flag = 1u;
         break;
       }
-      __nanosleep(100);
+      __nanosleep(BRT_GATHER_POLL_NS);
     }
   }
 }
@@ -145,6 +148,48 @@ __global__ void __launch_bounds__(32) k_gather_release(const GatherReleaseParams
 __global__ void __launch_bounds__(256) k_resolve_peers(const ResolveParams p) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.count; i += stride) resolve_body(p, i);
+  __threadfence_system();  // this thread's peer stores are ordered before the block's arrival below, at system scope
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(p.done, 1u);
+    if (prev == gridDim.x - 1u) {
+      __threadfence_system();
+      *p.done = 0u;  // for the next frame of this slot (replayed graph)
+      const uint32_t seq = p.fc->gather_seq;
+      for (uint32_t k = 0; k < p.n_peers; ++k) st_release_sys(&p.peer_flags[k]->arrive[p.img][p.rank], seq);
+    }
+  }
+}
+// The same exchange with the transfer taken out of the resolve kernel: k_resolve writes the local image and the packed tiles, then a SMALL
+// grid copies the packed tiles into the receivers' gather images, four independent 16-byte loads in flight per thread. A full grid of
+// resolve blocks that store over NVLink holds every thread slot of the GPU while the stores drain into the root's links (7 x 16.6 MB per
+// C5 frame on 8 GPUs: 0.2 ms per frame during which nothing else runs); a few dozen blocks keep the links busy just as well and leave
+// the SMs to the other frames in flight.
+__device__ __forceinline__ void push_pixel(const ResolveParams& p, uint32_t i, const float4 v) {
+  const uint32_t tile = (i >> 10) * p.map.tile_world + p.map.tile_rank;
+  if (tile >= p.map.n_tiles) return;
+  const uint32_t lx = i & 31u, ly = (i >> 5) & 31u;
+  const uint32_t x = (tile % p.map.tiles_x) * BRT_TILE + lx, y = (tile / p.map.tiles_x) * BRT_TILE + ly;
+  if (x >= p.map.width || y >= p.map.height) return;
+  const size_t pix = (size_t)y * p.map.width + x;
+  if (p.format == BRT_FORMAT_R32G32B32A32_SFLOAT) {
+    for (uint32_t k = 0; k < p.n_peers; ++k) static_cast<float4*>(p.peers[k])[pix] = v;
+  } else {
+    const uint32_t texel = pack_present(v, p.format);
+    for (uint32_t k = 0; k < p.n_peers; ++k) static_cast<uint32_t*>(p.peers[k])[pix] = texel;
+  }
+}
+__global__ void __launch_bounds__(256) k_push_peers(const ResolveParams p) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3u * stride < p.count; i += 4u * stride) {
+    const float4 v0 = p.tiles[i], v1 = p.tiles[i + stride], v2 = p.tiles[i + 2u * stride], v3 = p.tiles[i + 3u * stride];
+    push_pixel(p, i, v0);
+    push_pixel(p, i + stride, v1);
+    push_pixel(p, i + 2u * stride, v2);
+    push_pixel(p, i + 3u * stride, v3);
+  }
+  for (; i < p.count; i += stride) push_pixel(p, i, p.tiles[i]);
   __threadfence_system();  // this thread's peer stores are ordered before the block's arrival below, at system scope
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -427,6 +472,8 @@ struct brt_context {
   cudaEvent_t prev_head = nullptr;        // ev_head of the frame submitted last: the next frame starts behind it (staggered frames)
   uint32_t last_slot = 0;                 // slot of the frame most recently waited for (brt_get_aov / brt_device_image read it)
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
+  uint32_t peer_grid = 0;    // blocks of the kernel that stores into the receivers' gather images (0 = default: 64, or a full grid for the fused kernel); BRT_PEER_GRID
+  bool peer_push = true;     // resolve locally, then push the tiles with a small grid (false: one fused full-grid kernel); BRT_PEER_PUSH
   uint32_t shade_ahead = 0;  // tuning aid: slots ahead of which the shade kernels request path heads into the L2 (BRT_SHADE_AHEAD)
   uint32_t rays_per_warp = 0;  // 0 = full grid always; else bounce-round launches are sized for this many rays per warp (BRT_RAYS_PER_WARP)
   uint32_t refill_primary = 0, refill_bounce = BRT_REFILL_LANES_INCOHERENT;  // lanes still busy below which a warp refills its idle lanes
@@ -1382,11 +1429,25 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
         rp.fc = f->d_consts.as<FrameConsts>();
         GatherFlags* mine = reinterpret_cast<GatherFlags*>(static_cast<char*>(c->d_gather.ptr()) + (size_t)BRT_GATHER_IMAGES * img_bytes);
         Timed t(f, CLS_RESOLVE, s);
-        // the receivers must have released the previous frame of this image before its pixels are overwritten (device-side wait)
-        k_gather_wait_consumed<<<1, 32, 0, s>>>(mine, gimg, rp.fc, first, n_dst);
-        k_resolve_peers<<<grid_for(c, cap, 256, 8), 256, 0, s>>>(rp);
-        BRT_CHECK_LAUNCH();
-        launches += 2;
+        if (c->peer_push) {
+          ResolveParams local = rp;  // resolve into the local image and the packed tiles ...
+          local.n_peers = 0;
+          local.tiles = f->d_tiles.as<float4>();
+          BRT_LAUNCH_1D(k_resolve, local, grid_for(c, cap, 256, 8), 256, s);
+          rp.tiles = f->d_tiles.as<float4>();
+          // ... the receivers must have released the previous frame of this image before its pixels are overwritten (device-side wait) ...
+          k_gather_wait_consumed<<<1, 32, 0, s>>>(mine, gimg, rp.fc, first, n_dst);
+          // ... and a small grid carries the tiles over NVLink while the SMs work on the other frames in flight
+          k_push_peers<<<std::max(1u, std::min(c->peer_grid ? c->peer_grid : 64u, grid_for(c, cap, 256, 8))), 256, 0, s>>>(rp);
+          BRT_CHECK_LAUNCH();
+          launches += 3;
+        } else {
+          // the receivers must have released the previous frame of this image before its pixels are overwritten (device-side wait)
+          k_gather_wait_consumed<<<1, 32, 0, s>>>(mine, gimg, rp.fc, first, n_dst);
+          k_resolve_peers<<<c->peer_grid ? std::min(c->peer_grid, grid_for(c, cap, 256, 8)) : grid_for(c, cap, 256, 8), 256, 0, s>>>(rp);
+          BRT_CHECK_LAUNCH();
+          launches += 2;
+        }
       } else
 #endif
       {
@@ -1602,6 +1663,9 @@ int brt_create(const brt_config* cfg, brt_context** out) {
       c->flags = cfg->flags;
       if (c->tile_rank >= c->tile_world) invalid("brt_create: tile_rank >= tile_world");
     }
+    // more hardware work queues than the default 8 (read when CUDA initialises: only effective if this is the first CUDA call of the
+    // process): two streams per frame in flight plus the exchange stream must not share queues
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     BRT_CUDA(cudaGetDeviceCount(&n));
     if (n <= 0 || c->device < 0 || c->device >= n) throw CudaError("brt_create: no usable CUDA device (this library has no CPU path)");
@@ -1615,6 +1679,8 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
     // measured slower on C2 / C3 / C5 at every distance tried (profiles/r2_ncu_summary.md §4): off unless asked for
     if (const char* e = getenv("BRT_SHADE_AHEAD")) c->shade_ahead = (uint32_t)std::max(0L, atol(e));
+    if (const char* e = getenv("BRT_PEER_PUSH")) c->peer_push = atoi(e) != 0;
+    if (const char* e = getenv("BRT_PEER_GRID")) c->peer_grid = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_RAYS_PER_WARP")) c->rays_per_warp = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_REFILL_PRIMARY")) c->refill_primary = (uint32_t)std::max(0L, std::min(32L, atol(e)));
     if (const char* e = getenv("BRT_REFILL_BOUNCE")) c->refill_bounce = (uint32_t)std::max(0L, std::min(32L, atol(e)));

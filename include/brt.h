@@ -316,7 +316,9 @@ BRT_API int brt_render_frame(brt_context* ctx, const brt_uniform* u, const brt_r
  * brt_frame_wait(slot) returns when that frame and its copy are complete and folds its timings into brt_get_stats.
  * The latency-bound tail of one frame's wavefronts then overlaps the head of the next one. Scene-changing calls
  * (build, mesh update, Smart Culling) drain all slots first. With tile_world > 1 the image holds this rank's tiles only. */
+#ifndef BRT_FRAMES_IN_FLIGHT
 #define BRT_FRAMES_IN_FLIGHT 4 /* slots available; the reference uses 2; more let the latency-bound tail of small frames (one rank's share of a tiled frame) overlap */
+#endif
 BRT_API int brt_render_frame_async(brt_context* ctx, const brt_uniform* u, const brt_render_opts* opts, uint32_t slot, float* rgba_host);
 BRT_API int brt_frame_wait(brt_context* ctx, uint32_t slot);
 /* the cudaStream_t a slot's frame is enqueued on (slot 0: the context's stream), e.g. to order caller work after it */
@@ -341,7 +343,9 @@ BRT_API int brt_untile(brt_context* ctx, const void* d_all, uint32_t width, uint
  * BRT_GATHER_IMAGES frames are in flight per rank. Every rank must submit the same frames on the same slots in the same order; a
  * receiver must release every frame it receives. A wait gives up after 20 s (brt_gather_timed_out) instead of hanging the GPU.
  * Replaces nothing in the reference (single GPU, VK/Device.cpp:388-389); it is the tile split the north star names. */
+#ifndef BRT_GATHER_IMAGES
 #define BRT_GATHER_IMAGES 4
+#endif
 #define BRT_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 BRT_API int brt_gather_image_export(brt_context* ctx, uint32_t width, uint32_t height, void* handle_out);
 /* handles: tile_world handles of BRT_IPC_HANDLE_BYTES bytes each, in rank order (the own one is ignored) */

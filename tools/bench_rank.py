@@ -19,27 +19,33 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c5")
     ap.add_argument("--world", type=int, default=8)
+    ap.add_argument("--rank", type=int, default=0, help="which rank's tiles (tile_id %% world == rank)")
     ap.add_argument("--slots", type=int, nargs="+", default=[1, 2, 3, 4])
     ap.add_argument("--frames", type=int, default=40)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--flush-mb", type=int, default=0, help="write this many MiB on the frame's stream before every frame (bench.py: 160)")
     ap.add_argument("--serial", action="store_true", help="also one frame at a time on the serial schedule: per-kernel-class CUDA-event times")
     args = ap.parse_args()
     pkg = importlib.import_module("hardware-ray-tracer_b200")
     cfg = dict(pkg.scenes.CONFIGS[args.config])
     scene = pkg.scenes.make_scene(cfg.pop("scene"))
     dev = torch.device("cuda", 0)
-    ctx = pkg.Context(device=0, tile_rank=0, tile_world=args.world, flags=pkg.CFG_NO_GRAPH if args.no_graph else 0)
+    ctx = pkg.Context(device=0, tile_rank=args.rank, tile_world=args.world, flags=pkg.CFG_NO_GRAPH if args.no_graph else 0)
     scene.upload(ctx)
     w, h = cfg["width"], cfg["height"]
     u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
     opts = ctx.opts(w, h, cfg["spp"], cfg["flags"])
-    out = {"config": args.config, "world": args.world, "graph": not args.no_graph, "runs": []}
+    flush = torch.empty(args.flush_mb << 20, dtype=torch.uint8, device=dev) if args.flush_mb else None
+    out = {"config": args.config, "world": args.world, "rank": args.rank, "flush_mb": args.flush_mb, "graph": not args.no_graph, "runs": []}
     for n_slots in args.slots:
         streams = [torch.cuda.ExternalStream(ctx.frame_stream(k), device=dev) for k in range(n_slots)]
 
         def submit(i):
             k = i % n_slots
             ctx.frame_wait(k)
+            if flush is not None:
+                with torch.cuda.stream(streams[k]):
+                    flush.fill_(i & 0xff)
             ctx.render_frame_async(u, opts, k, None)
 
         for i in range(2 * n_slots):
@@ -64,7 +70,7 @@ def main():
         rays = st.rays_closest + st.rays_occlusion
         out["runs"].append({"slots": n_slots, "ms_per_frame": ms, "rays": int(rays), "mrays_rank": rays / ms / 1e3, "launches": st.launches_total})
     if args.serial:
-        sctx = pkg.Context(device=0, tile_rank=0, tile_world=args.world, flags=pkg.CFG_NO_OVERLAP)
+        sctx = pkg.Context(device=0, tile_rank=args.rank, tile_world=args.world, flags=pkg.CFG_NO_OVERLAP)
         scene.upload(sctx)
         rows = []
         for _ in range(5):

@@ -9,6 +9,8 @@ ap.add_argument("--async", dest="asyn", action="store_true")
 ap.add_argument("--torch", action="store_true")
 ap.add_argument("--flush", action="store_true")
 ap.add_argument("--slots", type=int, default=1)
+ap.add_argument("--no-graph", action="store_true", help="two real streams, kernels launched individually (BRT_CFG_NO_GRAPH)")
+ap.add_argument("--serial", action="store_true", help="BRT_CFG_NO_OVERLAP: one stream")
 a = ap.parse_args()
 pkg = importlib.import_module("hardware-ray-tracer_b200")
 torch = None
@@ -18,7 +20,7 @@ if a.torch or a.flush:
     buf = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")
 cfg = dict(pkg.scenes.CONFIGS[a.config])
 scene = pkg.scenes.make_scene(cfg.pop("scene"))
-ctx = pkg.Context(device=0, flags=0)
+ctx = pkg.Context(device=0, flags=(pkg.CFG_NO_GRAPH if a.no_graph else 0) | (pkg.CFG_NO_OVERLAP if a.serial else 0))
 scene.upload(ctx)
 w, h = cfg["width"], cfg["height"]
 u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
@@ -39,4 +41,4 @@ for f in range(a.frames):
     else:
         ctx.render_frame(u, opts, want_image=False)
     ms.append(round((time.perf_counter() - t0) * 1e3, 2))
-print(json.dumps({"lib": os.environ.get("BRT_LIB", "lib").split("/")[-2], "async": a.asyn, "torch": a.torch, "flush": a.flush, "slots": a.slots, "wall_ms": ms}))
+print(json.dumps({"lib": os.environ.get("BRT_LIB", "x/lib/libbrt.so").split("/")[-2], "async": a.asyn, "torch": a.torch, "flush": a.flush, "slots": a.slots, "graph": not a.no_graph, "serial": a.serial, "wall_ms": ms}))
