@@ -395,7 +395,7 @@ struct FrameSlot {
   cudaStream_t stream2 = nullptr;  // shadow chain (occlusion + accumulate), overlapped with the next round's traversal
   bool own_stream = false;
   cudaEvent_t ev_shade = nullptr, ev_acc[2] = {nullptr, nullptr};
-  cudaEvent_t ev_head = nullptr;  // recorded when the frame's last full-width wavefront (round 0 of the last batch) has been traced
+  cudaEvent_t ev_head = nullptr;  // recorded when round 0 of the frame's first sample batch has been traced (brt_context::stagger)
   uint32_t cap = 0;    // path slots per sample (owned tiles * 1024)
   uint32_t batch = 1;  // samples traced together in one wavefront
   size_t frame_bytes = 0;
@@ -472,6 +472,8 @@ struct brt_context {
   cudaEvent_t prev_head = nullptr;        // ev_head of the frame submitted last: the next frame starts behind it (staggered frames)
   uint32_t last_slot = 0;                 // slot of the frame most recently waited for (brt_get_aov / brt_device_image read it)
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
+  bool stagger_first = true; // ... of the frame's first sample batch (false: of its last one); BRT_STAGGER_FIRST
+  uint32_t stagger = 3;      // where in a frame the next frame in flight may start: 0 at once, 1 / 2 / 3 after round 0's closest-hit trace / shade / occlusion trace (BRT_STAGGER)
   uint32_t peer_grid = 0;    // blocks of the kernel that stores into the receivers' gather images (0 = default: 64, or a full grid for the fused kernel); BRT_PEER_GRID
   bool peer_push = true;     // resolve locally, then push the tiles with a small grid (false: one fused full-grid kernel); BRT_PEER_PUSH
   uint32_t shade_ahead = 0;  // tuning aid: slots ahead of which the shade kernels request path heads into the L2 (BRT_SHADE_AHEAD)
@@ -1148,10 +1150,10 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
     f->h_consts->scene_lo[k] = c->scene_lo[k];
     f->h_consts->scene_inv[k] = ext > 0.0f ? (float)(1u << BRT_HITSORT_CELL_BITS) / ext : 0.0f;
   }
-  // Frames in flight are staggered: this frame starts when the previous one has traced its last full-width wavefront, so
+  // Frames in flight are staggered: this frame starts when the previous one has traced round 0 of its first sample batch, so
   // that its saturating head overlaps the latency-bound tail (bounce rounds, resolve, copy-out) of the previous frame
-  // instead of running in lockstep with it.
-  if (c->prev_head && c->prev_head != f->ev_head) BRT_CUDA(cudaStreamWaitEvent(s, c->prev_head, 0));
+  // instead of running in lockstep with it, and two multi-batch frames run side by side (profiles/r2_configs.md).
+  if (c->stagger && c->prev_head && c->prev_head != f->ev_head) BRT_CUDA(cudaStreamWaitEvent(s, c->prev_head, 0));
 
   // Full-frame clears that only the pixels this slot never writes depend on (AOVs of pixels outside the crop / of other ranks' tiles,
   // the local image outside this rank's tiles): every owned pixel inside the crop is rewritten by every frame, so they are done once per
@@ -1205,6 +1207,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
     const uint32_t c_batch = f->batch;
     for (uint32_t sample = 0; sample < o.spp; sample += f->batch) {
       const uint32_t nb = std::min(f->batch, o.spp - sample);  // samples in this wavefront
+      const bool head_batch = c->stagger_first ? sample == 0 : sample + c_batch >= o.spp;  // the batch whose round 0 releases the next frame in flight
       const uint32_t capw = cap * nb;                          // its path slots
       if (rounds) BRT_CUDA(cudaMemsetAsync(f->d_alive.ptr(), 0, (size_t)capw * 4, s));  // (the radiance terms themselves need no clearing)
       {
@@ -1253,6 +1256,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           launch_trace<false>(c, tp, s, round == 0 ? ~0ull : (uint64_t)capw >> (round - 1));  // (a bounce round holds at most the previous round's hits)
           launches++;
           l_closest++;
+          if (c->stagger == 1 && round == 0 && head_batch) record_event(f->ev_head, s);
         }
         const uint32_t* order = nullptr;
 #ifndef BRT_EMU
@@ -1332,6 +1336,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           BRT_CHECK_LAUNCH();
           launches++;
         }
+        if (c->stagger == 2 && round == 0 && head_batch) record_event(f->ev_head, s);
         if (s2 != s) {
           BRT_CUDA(cudaEventRecord(f->ev_shade, s));
           BRT_CUDA(cudaStreamWaitEvent(s2, f->ev_shade, 0));
@@ -1357,7 +1362,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           launches++;
           l_occl++;
         }
-        if (round == 0 && sample + c_batch >= o.spp) record_event(f->ev_head, s2);
+        if ((c->stagger == 3 || c->stagger == 0) && round == 0 && head_batch) record_event(f->ev_head, s2);
         {
           AccumParams ap{};
           ap.count = 0;
@@ -1679,6 +1684,8 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     if (const char* e = getenv("BRT_WAVEFRONT_PATHS")) c->target_wavefront = (uint32_t)std::max(1L, atol(e));
     // measured slower on C2 / C3 / C5 at every distance tried (profiles/r2_ncu_summary.md §4): off unless asked for
     if (const char* e = getenv("BRT_SHADE_AHEAD")) c->shade_ahead = (uint32_t)std::max(0L, atol(e));
+    if (const char* e = getenv("BRT_STAGGER_FIRST")) c->stagger_first = atoi(e) != 0;
+    if (const char* e = getenv("BRT_STAGGER")) c->stagger = (uint32_t)std::max(0L, std::min(3L, atol(e)));
     if (const char* e = getenv("BRT_PEER_PUSH")) c->peer_push = atoi(e) != 0;
     if (const char* e = getenv("BRT_PEER_GRID")) c->peer_grid = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_RAYS_PER_WARP")) c->rays_per_warp = (uint32_t)std::max(0L, atol(e));

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--slots", type=int, nargs="+", default=[1, 2, 3, 4])
     ap.add_argument("--frames", type=int, default=40)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--depth", type=int, default=0, help="override the config's depthMax (rounds per frame)")
+    ap.add_argument("--spp", type=int, default=0, help="override the config's samples per pixel (fixed cost per frame vs cost per path)")
     ap.add_argument("--flush-mb", type=int, default=0, help="write this many MiB on the frame's stream before every frame (bench.py: 160)")
     ap.add_argument("--serial", action="store_true", help="also one frame at a time on the serial schedule: per-kernel-class CUDA-event times")
     args = ap.parse_args()
@@ -33,7 +35,11 @@ def main():
     ctx = pkg.Context(device=0, tile_rank=args.rank, tile_world=args.world, flags=pkg.CFG_NO_GRAPH if args.no_graph else 0)
     scene.upload(ctx)
     w, h = cfg["width"], cfg["height"]
+    if args.depth:
+        cfg["depth_max"] = args.depth
     u = scene.uniform(ctx, w, h, 0, cfg["depth_max"])
+    if args.spp:
+        cfg["spp"] = args.spp
     opts = ctx.opts(w, h, cfg["spp"], cfg["flags"])
     flush = torch.empty(args.flush_mb << 20, dtype=torch.uint8, device=dev) if args.flush_mb else None
     out = {"config": args.config, "world": args.world, "rank": args.rank, "flush_mb": args.flush_mb, "graph": not args.no_graph, "runs": []}
