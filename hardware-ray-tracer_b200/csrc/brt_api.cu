@@ -473,7 +473,7 @@ struct brt_context {
   uint32_t last_slot = 0;                 // slot of the frame most recently waited for (brt_get_aov / brt_device_image read it)
   uint32_t target_wavefront = 16u << 20;  // paths per wavefront aimed for (BRT_WAVEFRONT_PATHS overrides, for tuning)
   bool stagger_first = true; // ... of the frame's first sample batch (false: of its last one); BRT_STAGGER_FIRST
-  uint32_t stagger = 3;      // where in a frame the next frame in flight may start: 0 at once, 1 / 2 / 3 after round 0's closest-hit trace / shade / occlusion trace (BRT_STAGGER)
+  uint32_t stagger = 4;      // where in a frame the next frame in flight may start: 0 at once, 1 / 2 / 3 after round 0's closest-hit trace / shade / occlusion trace, 4 = by the frame's depth (BRT_STAGGER)
   uint32_t peer_grid = 0;    // blocks of the kernel that stores into the receivers' gather images (0 = default: 64, or a full grid for the fused kernel); BRT_PEER_GRID
   bool peer_push = true;     // resolve locally, then push the tiles with a small grid (false: one fused full-grid kernel); BRT_PEER_PUSH
   uint32_t shade_ahead = 0;  // tuning aid: slots ahead of which the shade kernels request path heads into the L2 (BRT_SHADE_AHEAD)
@@ -1153,6 +1153,9 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
   // Frames in flight are staggered: this frame starts when the previous one has traced round 0 of its first sample batch, so
   // that its saturating head overlaps the latency-bound tail (bounce rounds, resolve, copy-out) of the previous frame
   // instead of running in lockstep with it, and two multi-batch frames run side by side (profiles/r2_configs.md).
+  // where in this frame the NEXT one may start: frames of up to three rounds have no latency-bound tail worth waiting for and release their
+  // successor right behind round 0's closest-hit trace, longer ones behind round 0's occlusion trace (measured: profiles/r2_configs.md)
+  const uint32_t stagger = c->stagger != 4u ? c->stagger : (rounds <= 3u ? 1u : 3u);
   if (c->stagger && c->prev_head && c->prev_head != f->ev_head) BRT_CUDA(cudaStreamWaitEvent(s, c->prev_head, 0));
 
   // Full-frame clears that only the pixels this slot never writes depend on (AOVs of pixels outside the crop / of other ranks' tiles,
@@ -1256,7 +1259,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           launch_trace<false>(c, tp, s, round == 0 ? ~0ull : (uint64_t)capw >> (round - 1));  // (a bounce round holds at most the previous round's hits)
           launches++;
           l_closest++;
-          if (c->stagger == 1 && round == 0 && head_batch) record_event(f->ev_head, s);
+          if (stagger == 1 && round == 0 && head_batch) record_event(f->ev_head, s);
         }
         const uint32_t* order = nullptr;
 #ifndef BRT_EMU
@@ -1336,7 +1339,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           BRT_CHECK_LAUNCH();
           launches++;
         }
-        if (c->stagger == 2 && round == 0 && head_batch) record_event(f->ev_head, s);
+        if (stagger == 2 && round == 0 && head_batch) record_event(f->ev_head, s);
         if (s2 != s) {
           BRT_CUDA(cudaEventRecord(f->ev_shade, s));
           BRT_CUDA(cudaStreamWaitEvent(s2, f->ev_shade, 0));
@@ -1362,7 +1365,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           launches++;
           l_occl++;
         }
-        if ((c->stagger == 3 || c->stagger == 0) && round == 0 && head_batch) record_event(f->ev_head, s2);
+        if ((stagger == 3 || stagger == 0) && round == 0 && head_batch) record_event(f->ev_head, s2);
         {
           AccumParams ap{};
           ap.count = 0;
@@ -1685,7 +1688,7 @@ int brt_create(const brt_config* cfg, brt_context** out) {
     // measured slower on C2 / C3 / C5 at every distance tried (profiles/r2_ncu_summary.md §4): off unless asked for
     if (const char* e = getenv("BRT_SHADE_AHEAD")) c->shade_ahead = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_STAGGER_FIRST")) c->stagger_first = atoi(e) != 0;
-    if (const char* e = getenv("BRT_STAGGER")) c->stagger = (uint32_t)std::max(0L, std::min(3L, atol(e)));
+    if (const char* e = getenv("BRT_STAGGER")) c->stagger = (uint32_t)std::max(0L, std::min(4L, atol(e)));
     if (const char* e = getenv("BRT_PEER_PUSH")) c->peer_push = atoi(e) != 0;
     if (const char* e = getenv("BRT_PEER_GRID")) c->peer_grid = (uint32_t)std::max(0L, atol(e));
     if (const char* e = getenv("BRT_RAYS_PER_WARP")) c->rays_per_warp = (uint32_t)std::max(0L, atol(e));
