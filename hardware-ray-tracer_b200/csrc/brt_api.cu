@@ -1446,7 +1446,7 @@ void render_frame_device(brt_context* c, FrameSlot* f, const brt_uniform& u, con
           // ... the receivers must have released the previous frame of this image before its pixels are overwritten (device-side wait) ...
           k_gather_wait_consumed<<<1, 32, 0, s>>>(mine, gimg, rp.fc, first, n_dst);
           // ... and a small grid carries the tiles over NVLink while the SMs work on the other frames in flight
-          k_push_peers<<<std::max(1u, std::min(c->peer_grid ? c->peer_grid : 64u, grid_for(c, cap, 256, 8))), 256, 0, s>>>(rp);
+          k_push_peers<<<std::max(1u, std::min(c->peer_grid ? c->peer_grid : 64u * n_dst, grid_for(c, cap, 256, 8))), 256, 0, s>>>(rp);  // (64 blocks per receiver)
           BRT_CHECK_LAUNCH();
           launches += 3;
         } else {
