@@ -190,6 +190,14 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
   __shared__ unsigned long long sk[BRT_SMALL_BUILD_MAX];  // (Morton key << 32 | primitive): unique, so the sort is stable by construction
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   SmallBuildParams p = p_in;
+#ifdef BRT_BUILD_SMALL_TIMING
+  unsigned long long ts[10];
+  int nts = 0;
+#define BRT_STAMP() do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ts[nts++] = t_; } } while (0)
+#else
+#define BRT_STAMP() do {} while (0)
+#endif
+  BRT_STAMP();
   if (p.fused_prologue) {
     if (threadIdx.x == 0) init_globals_body(p.init, 0);
     __threadfence();
@@ -233,6 +241,7 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
     p.queue[1] = q1;
   }
   const uint32_t tid = threadIdx.x, nt = blockDim.x, n = p.n;
+  BRT_STAMP();  // 1: prologue + smem carve-up
   uint32_t np2 = 2;
   while (np2 < n) np2 <<= 1;
   for (uint32_t i = tid; i < np2; i += nt) {
@@ -257,6 +266,7 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
       }
       __syncthreads();
     }
+  BRT_STAMP();  // 2: morton + sort
   for (uint32_t i = tid; i < n; i += nt) {
     p.keys_sorted[i] = (uint32_t)(sk[i] >> 32);
     p.vals_sorted[i] = (uint32_t)sk[i];
@@ -266,9 +276,11 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
   for (uint32_t i = tid; i + 1 < n; i += nt) hierarchy_body(p.hier, i);
   __threadfence();
   __syncthreads();
+  BRT_STAMP();  // 3: hierarchy
   for (uint32_t i = tid; i < n; i += nt) refit_body(p.refit, i);
   __threadfence();
   __syncthreads();
+  BRT_STAMP();  // 4: refit + cost table
   CollapseParams cp = p.collapse;
   for (uint32_t level = 0; level < 62; ++level) {
     const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&cp.g->level_count[level]);
@@ -280,10 +292,16 @@ __global__ void __launch_bounds__(BRT_SMALL_BUILD_THREADS) k_build_small(const S
     __threadfence();
     __syncthreads();
   }
+  BRT_STAMP();  // 5: collapse
   if (p.mesh_bounds && tid == 0) {
     MeshBoundsParams mb{1, nullptr, cp.g, p.mesh_bounds};
     mesh_bounds_body(mb, 0);
   }
+#ifdef BRT_BUILD_SMALL_TIMING
+  if (threadIdx.x == 0)
+    printf("k_build_small n=%u smem=%u: prologue %llu sort %llu hierarchy %llu refit %llu collapse %llu ns (levels %u)\n", p.n, p.in_smem, ts[1] - ts[0], ts[2] - ts[1],
+           ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], cp.g->levels);
+#endif
 }
 #endif
 
