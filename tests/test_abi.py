@@ -76,3 +76,12 @@ def test_tile_buffer_bytes(pkg):
     assert lib.brt_tile_buffer_bytes(1920, 1080, 1) == 60 * 34 * 1024 * 16
     assert lib.brt_tile_buffer_bytes(1920, 1080, 8) == ((60 * 34 + 7) // 8) * 1024 * 16
     assert lib.brt_tile_buffer_bytes(31, 1, 4) == 1024 * 16
+
+
+def test_package_asks_for_more_hardware_work_queues():
+    """Importing the package sets CUDA_DEVICE_MAX_CONNECTIONS (unless the user already did): frames in flight + the fused exchange use more
+    streams than CUDA's default 8 hardware queues (profiles/r2_configs.md)."""
+    import importlib
+    import os
+    importlib.import_module("hardware-ray-tracer_b200")
+    assert int(os.environ["CUDA_DEVICE_MAX_CONNECTIONS"]) >= 8

@@ -52,19 +52,25 @@ def _worker(rank, world, port, out_dir):
     np.save(os.path.join(out_dir, f"nccl{rank}.npy"), torch.stack(imgs).cpu().numpy())
     ctx.close()
 
-    # ---- fused exchange, every rank receives, synchronous calls
-    ctx = pkg.Context(device=rank, tile_rank=rank, tile_world=world)
-    scene.upload(ctx)
-    frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="p2p")
-    host = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
+    # ---- fused exchange, every rank receives, synchronous calls: frames 0-2 with the default form (local resolve + small-grid push kernel),
+    # frames 3-5 with the one-kernel form (BRT_PEER_PUSH=0, read by brt_create)
     imgs = []
-    for k in range(6):
-        frame.render(uniform(ctx, k), ctx.opts(w, h, 2, flags))
-        frame.to_host(host)
-        imgs.append(host.numpy().reshape(h, w, 4).copy())
+    host = torch.empty(h * w * 4, dtype=torch.float32).pin_memory()
+    for form in (None, "0"):
+        if form is not None:
+            os.environ["BRT_PEER_PUSH"] = form
+        ctx = pkg.Context(device=rank, tile_rank=rank, tile_world=world)
+        os.environ.pop("BRT_PEER_PUSH", None)
+        scene.upload(ctx)
+        frame = pkg.TiledFrame(ctx, w, h, rank, world, dev, mode="p2p")
+        for k in range(len(imgs), len(imgs) + 3):
+            frame.render(uniform(ctx, k), ctx.opts(w, h, 2, flags))
+            frame.to_host(host)
+            imgs.append(host.numpy().reshape(h, w, 4).copy())
+        frame.check()
+        dist.barrier()
+        ctx.close()
     np.save(os.path.join(out_dir, f"p2p_all{rank}.npy"), np.stack(imgs))
-    frame.check()
-    ctx.close()
 
     # ---- fused exchange, root only, FOUR frames in flight, no host barrier anywhere: RGBA32F, then B8G8R8A8_UNORM
     for name, fmt, dtype, per_px in (("f32", 0, torch.float32, 4), ("bgra8", pkg.render_format(pkg.FORMAT_BGRA8_UNORM), torch.uint8, 4)):
