@@ -263,3 +263,32 @@ def test_frame_graph_replay(pkg, orc_mod, make):
     assert np.array_equal(ia.view(np.uint32), io.view(np.uint32))
     # per-class kernel times exist only for individually launched kernels
     assert b.get_stats().ms_trace_closest > 0.0 and a.get_stats().ms_trace_closest == 0.0
+
+
+@pytest.mark.parametrize("stagger", ["0", "1", "2", "3", "4"])
+def test_release_point_of_frames_in_flight(pkg, make, monkeypatch, stagger):
+    """BRT_STAGGER / BRT_STAGGER_FIRST decide where in a frame the NEXT frame in flight may start (at once; behind round 0's closest-hit
+    trace / shade / occlusion trace of the first sample batch; by depth). Scheduling only: six different multi-batch frames over three
+    slots give the bits of the synchronous call under every setting."""
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    ref_ctx = make()
+    monkeypatch.setenv("BRT_STAGGER", stagger)
+    monkeypatch.setenv("BRT_WAVEFRONT_PATHS", "20000")  # 160x90 -> one sample per wavefront: four batches per frame
+    if stagger == "3":
+        monkeypatch.setenv("BRT_STAGGER_FIRST", "0")  # the release point of round 2: the LAST batch
+    a = make()
+    scene.upload(a)
+    scene.upload(ref_ctx)
+    w, h, spp, flags = 160, 90, 4, 3
+    uni = [scene.uniform(a, w, h, fr, 1 + fr % 4) for fr in range(6)]  # depthMax 1..4: both sides of the by-depth rule
+    for k, u in enumerate(uni):
+        u.viewInverse[3] += 0.25 * k
+    ref = [ref_ctx.render_frame(u, ref_ctx.opts(w, h, spp, flags)).copy() for u in uni]
+    out = [np.zeros((h, w, 4), np.float32) for _ in uni]
+    for k, u in enumerate(uni):
+        a.render_frame_async(u, a.opts(w, h, spp, flags), k % 3, out[k].ctypes.data)
+    for s in range(3):
+        a.frame_wait(s)
+    for k in range(len(uni)):
+        assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), (stagger, k)
+    assert len({o.tobytes() for o in out}) == len(out)  # the frames really differ
