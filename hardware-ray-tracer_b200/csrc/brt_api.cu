@@ -160,11 +160,11 @@ __global__ void __launch_bounds__(256) k_resolve_peers(const ResolveParams p) {
     }
   }
 }
-// The same exchange with the transfer taken out of the resolve kernel: k_resolve writes the local image and the packed tiles, then a SMALL
-// grid copies the packed tiles into the receivers' gather images, four independent 16-byte loads in flight per thread. A full grid of
-// resolve blocks that store over NVLink holds every thread slot of the GPU while the stores drain into the root's links (7 x 16.6 MB per
-// C5 frame on 8 GPUs: 0.2 ms per frame during which nothing else runs); a few dozen blocks keep the links busy just as well and leave
-// the SMs to the other frames in flight.
+// The same exchange with the transfer taken out of the resolve kernel (the default): k_resolve writes the local image and the packed tiles, then
+// a SMALL grid (64 blocks per receiver) copies the packed tiles into the receivers' gather images, four independent 16-byte loads in flight per
+// thread, and publishes the arrival flags. NVLink needs a few dozen blocks, not every thread slot of the GPU, and the other frames in flight keep
+// the SMs. Measured on 2 and 8 GPUs it is exactly as fast as the one-kernel form at any grid size from 16 blocks up (profiles/r2_configs.md: what
+// the exchange did cost was a shared hardware work queue, not this kernel); it is kept as the default because it is the form that leaves the SMs alone.
 __device__ __forceinline__ void push_pixel(const ResolveParams& p, uint32_t i, const float4 v) {
   const uint32_t tile = (i >> 10) * p.map.tile_world + p.map.tile_rank;
   if (tile >= p.map.n_tiles) return;
