@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) k_resolve_peers(const ResolveParams p) {
 // the SMs. Measured on 2 and 8 GPUs it is exactly as fast as the one-kernel form at any grid size from 16 blocks up (profiles/r2_configs.md: what
 // the exchange did cost was a shared hardware work queue, not this kernel); it is kept as the default because it is the form that leaves the SMs alone.
 __device__ __forceinline__ void push_pixel(const ResolveParams& p, uint32_t i, const float4 v) {
-  const uint32_t tile = (i >> 10) * p.map.tile_world + p.map.tile_rank;
+  const uint32_t tile = tile_of_rank(i >> 10, p.map.tile_rank, p.map.tile_world);
   if (tile >= p.map.n_tiles) return;
   const uint32_t lx = i & 31u, ly = (i >> 5) & 31u;
   const uint32_t x = (tile % p.map.tiles_x) * BRT_TILE + lx, y = (tile / p.map.tiles_x) * BRT_TILE + ly;

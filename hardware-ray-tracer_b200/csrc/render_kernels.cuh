@@ -55,10 +55,16 @@ BRT_HD uint32_t compact5(uint32_t v) {  // even bits of a 10-bit Morton code -> 
   v = (v | (v >> 4)) & 0x01fu;
   return v;
 }
-// path slot -> pixel. Slots are laid out tile by tile (this rank's k-th tile = tile k*world + rank),
+// Which rank owns which 32x32 tile: the tiles (row-major ids) are dealt in groups of `world` consecutive ones, and inside group k the ranks are
+// rotated by k: the rank's k-th tile is  k * world + (rank + k) % world.  (Plain tile_id % world == rank puts a rank's tiles into COLUMNS
+// whenever the number of tile columns is a multiple of world — 4K has 120, so on 8 GPUs every rank rendered vertical stripes and the
+// slowest rank of C3 had 2.2 % more work than the mean; rotated, the stripes become diagonals.)
+BRT_HD uint32_t tile_of_rank(uint32_t k, uint32_t rank, uint32_t world) { return k * world + (rank + k) % world; }
+BRT_HD uint32_t rank_of_tile(uint32_t tile, uint32_t world) { return (tile % world + world - (tile / world) % world) % world; }  // (its k is tile / world)
+// path slot -> pixel. Slots are laid out tile by tile (this rank's k-th tile: tile_of_rank),
 // Morton order inside the 32x32 tile, so one warp covers an 8x4 pixel block.
 BRT_HD bool slot_to_pixel(const TileMap& m, uint32_t slot, uint32_t& x, uint32_t& y) {
-  const uint32_t tile = (slot >> 10) * m.tile_world + m.tile_rank;
+  const uint32_t tile = tile_of_rank(slot >> 10, m.tile_rank, m.tile_world);
   if (tile >= m.n_tiles) return false;
   const uint32_t j = slot & 1023u;
   x = (tile % m.tiles_x) * BRT_TILE + compact5(j);
@@ -669,7 +675,7 @@ struct ResolveParams {
 };
 BRT_HD void resolve_body(const ResolveParams& p, uint32_t i) {
   // unlike the path slots this walks the tile row by row so that both stores coalesce
-  const uint32_t tile = (i >> 10) * p.map.tile_world + p.map.tile_rank;
+  const uint32_t tile = tile_of_rank(i >> 10, p.map.tile_rank, p.map.tile_world);
   if (tile >= p.map.n_tiles) return;
   const uint32_t lx = i & 31u, ly = (i >> 5) & 31u;
   const uint32_t x = (tile % p.map.tiles_x) * BRT_TILE + lx, y = (tile / p.map.tiles_x) * BRT_TILE + ly;
@@ -715,7 +721,7 @@ struct UntileParams {
 BRT_HD void untile_body(const UntileParams& p, uint32_t i) {
   const uint32_t x = i % p.width, y = i / p.width;
   const uint32_t tile = (y / BRT_TILE) * p.tiles_x + x / BRT_TILE;
-  const uint32_t rank = tile % p.tile_world, k = tile / p.tile_world;
+  const uint32_t rank = rank_of_tile(tile, p.tile_world), k = tile / p.tile_world;
   p.image[i] = p.all[(size_t)rank * p.slots_per_rank + (size_t)k * 1024u + (y % BRT_TILE) * BRT_TILE + (x % BRT_TILE)];
 }
 

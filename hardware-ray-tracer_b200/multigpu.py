@@ -1,7 +1,7 @@
 """Tile-parallel rendering over the GPUs of one box.
 
 Every rank (one process per GPU, torch.distributed) holds a replica of the scene and a `brt_context` created with
-(tile_rank, tile_world) = (rank, world): it traces only the 32x32 tiles with tile_id % world == rank. Smart-Culling results and
+(tile_rank, tile_world) = (rank, world): it traces only its 32x32 tiles (groups of `world` consecutive tiles, ranks rotated by the group index: csrc/render_kernels.cuh, tile_of_rank). Smart-Culling results and
 the BVH are identical on every rank by construction (same inputs, deterministic builder), so only finished pixels cross GPUs.
 
 Two exchange modes:

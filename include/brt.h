@@ -136,7 +136,8 @@ typedef struct brt_accel_info {
 typedef struct brt_config {
   uint32_t struct_size; /* sizeof(brt_config) */
   int32_t device;       /* CUDA device ordinal */
-  uint32_t tile_rank;   /* this context renders image tiles with tile_id % tile_world == tile_rank */
+  uint32_t tile_rank;   /* this context renders the 32x32 image tiles t (row-major ids) with (t % W + W - (t / W) % W) % W == tile_rank, W = tile_world:
+                         * groups of W consecutive tiles, ranks rotated by the group index (diagonals, not columns, when the tile columns are a multiple of W) */
   uint32_t tile_world;  /* 1 = whole image */
   uint32_t flags;       /* BRT_CFG_* */
 } brt_config;

@@ -575,7 +575,8 @@ bool owns_tile(const orc_context* c, uint32_t px, uint32_t py, uint32_t width) {
   if (c->tile_world <= 1) return true;
   uint32_t tiles_x = (width + 31) / 32;
   uint32_t tile = (py / 32) * tiles_x + (px / 32);
-  return tile % c->tile_world == c->tile_rank;
+  // groups of `world` consecutive tiles, ranks rotated by the group index (csrc/render_kernels.cuh: tile_of_rank)
+  return (tile % c->tile_world + c->tile_world - (tile / c->tile_world) % c->tile_world) % c->tile_world == c->tile_rank;
 }
 
 }  // namespace

@@ -405,7 +405,8 @@ def tiles_and_crop(pkg, orc_mod, make_ranked):
         scene.upload(api)
         part = api.render_frame(u, api.opts(w, h, 1, R | T))
         ty, tx = np.meshgrid(np.arange(h) // 32, np.arange(w) // 32, indexing="ij")
-        own = (ty * ((w + 31) // 32) + tx) % world == rank
+        tile = ty * ((w + 31) // 32) + tx
+        own = (tile % world + world - (tile // world) % world) % world == rank  # tile_of_rank (csrc/render_kernels.cuh)
         assert (part[~own] == 0).all()
         assert np.array_equal(part[own].view(np.uint32), ref[own].view(np.uint32))
         acc += part

@@ -19,7 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c5")
     ap.add_argument("--world", type=int, default=8)
-    ap.add_argument("--rank", type=int, default=0, help="which rank's tiles (tile_id %% world == rank)")
+    ap.add_argument("--rank", type=int, default=0, help="which rank's tiles")
     ap.add_argument("--slots", type=int, nargs="+", default=[1, 2, 3, 4])
     ap.add_argument("--frames", type=int, default=40)
     ap.add_argument("--no-graph", action="store_true")
