@@ -148,3 +148,26 @@ def test_warp_kernels_equal_scalar(pkg, emu_lib, monkeypatch):
     emu_lib.brt_emu_warp_treelet_stats(C.byref(checks), C.byref(invalid), C.byref(dev))
     assert checks.value >= 4 and invalid.value == 0
     assert dev.value < 0.05  # equal on the terrain; the icosphere's many ties let the two versions settle on slightly different trees
+
+
+def test_shade_hoist_variants_give_the_same_bits(pkg, emu_lib):
+    """BRT_SHADE_HOIST_HEAD / BRT_SHADE_HOIST_HIT (opt-in builds: the shade kernels request a path's loads ahead of the branches they sit
+    behind, profiles/r2_ncu_summary.md §5) only move loads: same frames, bit for bit, as the default build."""
+    import ctypes
+    import os
+    import subprocess
+    import numpy as np
+    emu_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+    subprocess.check_call(["make", "-s", "-C", emu_dir, "libbrt_emu_hoist.so"])
+    hoist = ctypes.CDLL(os.path.join(emu_dir, "libbrt_emu_hoist.so"))
+    scene = pkg.scenes.make_scene("terrain", small=True)
+    a = pkg.binding.SceneApi(emu_lib, "brt_", 0, 0, 1, 0)
+    b = pkg.binding.SceneApi(hoist, "brt_", 0, 0, 1, 0)
+    scene.upload(a)
+    scene.upload(b)
+    for depth, flags in ((1, 0), (3, 3), (4, 7)):
+        u = scene.uniform(a, 96, 54, depth, depth)
+        ia = a.render_frame(u, a.opts(96, 54, 2, flags))
+        ib = b.render_frame(u, b.opts(96, 54, 2, flags))
+        assert np.array_equal(ia.view(np.uint32), ib.view(np.uint32)), (depth, flags)
+        assert np.array_equal(a.get_aov(pkg.AOV_PRIM_ID, 96, 54), b.get_aov(pkg.AOV_PRIM_ID, 96, 54))
